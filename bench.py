@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE configs[3] — independent 48 kHz channels, 2 s (96 000-tap)
+impulse response per channel (each its own IR), block 512, one FFTConvolver per channel,
+4096 channels per GPU (weak scaling: every rank owns its own 4096 channels, no collective).
+One "step" = one 512-sample block for every channel (K1 -> K2 -> K3).
+
+  python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA, sm_100a)
+  python bench.py --impl reference [...]                     CPU restatement of the reference
+                                                             algorithm on all host cores
+
+Prints ONE JSON line (rank 0).  Synthetic data per SURVEY.md §8(d) (splitmix64 white noise,
+random-decay unit-energy IRs), generated here with numpy — the product arm never touches oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+SAMPLE_RATE = 48000
+METRIC = "real-time 48 kHz channel count (channel-sec/sec) at IR 2 s, block 512"
+UNIT = "channel-sec/sec"
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic data — numpy, bit-identical to the generators the tests use
+# ---------------------------------------------------------------------------------------------
+def mix64(v: np.ndarray) -> np.ndarray:
+    z = v + np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def synth_noise(chan0: int, nchan: int, first_sample: int, n: int) -> np.ndarray:
+    c = (np.arange(chan0, chan0 + nchan, dtype=np.uint64) << np.uint64(32))[:, None]
+    i = np.arange(first_sample, first_sample + n, dtype=np.uint64)[None, :]
+    r = mix64(np.uint64(0x5EED0001) + c + i)
+    u = (r >> np.uint64(40)).astype(np.float32) / np.float32(16777216.0)
+    return (np.float32(2.0) * u - np.float32(1.0)).astype(np.float32)
+
+
+def synth_irs(chan0: int, nchan: int, update_index: int, length: int, chunk: int = 64) -> np.ndarray:
+    out = np.empty((nchan, length), np.float32)
+    decay = np.exp(-6.9078 * np.arange(length, dtype=np.float64) / float(length))[None, :]
+    i = np.arange(length, dtype=np.uint64)[None, :]
+    seed = np.uint64(0x5EED0002) + (np.uint64(update_index) << np.uint64(48))
+    for c0 in range(0, nchan, chunk):
+        c1 = min(nchan, c0 + chunk)
+        c = (np.arange(chan0 + c0, chan0 + c1, dtype=np.uint64) << np.uint64(32))[:, None]
+        r = mix64(seed + c + i)
+        u = (r >> np.uint64(40)).astype(np.float64) / 16777216.0
+        v = (2.0 * u - 1.0) * decay
+        e = np.sum(v * v, axis=1, keepdims=True)
+        out[c0:c1] = (v / np.sqrt(e)).astype(np.float32)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def measured_peak_gbs() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent clocks via NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_ev = index, [], set(), None, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_ev.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_ev.wait(0.05)
+
+    def stop(self) -> dict:
+        self._stop_ev.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_port_run(channels: int, block: int, ir_len: int, calls: int, threads: int) -> tuple[float, float]:
+    """CPU restatement of the reference algorithm (oracle/fftconv_oracle.c), one convolver per
+    channel, channels over `threads` host threads; returns (channel-sec/sec, seconds)."""
+    import oracle  # cpu_baseline / --impl reference legs only
+    lib = oracle.load().lib
+    irs = synth_irs(1 << 20, channels, 0, ir_len)
+    x = synth_noise(1 << 20, channels, 0, block * calls)
+    out = np.zeros_like(x)
+    secs = lib.orc_batch_fftconv_run(channels, block, ir_len, irs, x, out, block, calls, threads)
+    return channels * calls * block / SAMPLE_RATE / secs, secs
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    threads = oracle.load().lib.orc_max_threads()
+    ir_len = int(args.ir_seconds * SAMPLE_RATE)
+    channels = max(threads * 4, 8)
+    calls = 94  # ~1 s of audio per channel per step
+    # warm-up + timed steps, each step a bounded sample of the workload
+    for _ in range(max(args.warmup, 1) if args.warmup else 0):
+        cpu_port_run(channels, args.block, ir_len, 8, threads)
+    t_tot, work = 0.0, 0.0
+    for _ in range(args.steps):
+        v, secs = cpu_port_run(channels, args.block, ir_len, calls, threads)
+        t_tot += secs
+        work += channels * calls * args.block / SAMPLE_RATE
+    value = work / t_tot
+    sample = f"{channels} channels x {calls} blocks of {args.block} per step, {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "CPU restatement of the reference algorithm (oracle/), not rustfft: no Rust toolchain in the image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, extra):
+    d = {"workload": f"FFTConvolver x {args.channels} independent channels per GPU, IR {args.ir_seconds:g} s "
+                     f"({int(args.ir_seconds * SAMPLE_RATE)} taps, one IR per channel), block {args.block}, 48 kHz "
+                     "(BASELINE configs[3])",
+         "channels_per_gpu": args.channels, "block": args.block, "ir_taps": int(args.ir_seconds * SAMPLE_RATE),
+         "l2": "working set 6.3 GB/GPU per step >> 126 MB L2, no flush needed"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import fft_convolution_b200 as F
+    from fft_convolution_b200 import _lib
+    lib = _lib.load()
+    if args.mac_impl is not None:
+        _lib.check(lib.fcb_tune(b"mac_impl", args.mac_impl))
+    if args.mac_stages is not None:
+        _lib.check(lib.fcb_tune(b"mac_stages", args.mac_stages))
+
+    Cn, B = args.channels, args.block
+    L = int(args.ir_seconds * SAMPLE_RATE)
+    chan0 = rank * Cn
+    stream = torch.cuda.Stream(device=local)
+    t0 = time.time()
+    irs = synth_irs(chan0, Cn, 0, L)
+    t_gen = time.time() - t0
+    conv = F.FFTConvolver.init(irs, B, L, device=local, stream=stream.cuda_stream)
+    S, K = conv.seg_count, conv.block_size + 1
+    del irs
+
+    # ---- correctness of the timed path: first blocks of a few channels vs f64 truth (numpy) ----
+    NCHK = 6
+    x_chk = synth_noise(chan0, Cn, 0, B * NCHK)
+    y_chk = np.zeros((Cn, B * NCHK), np.float32)
+    blk_out = np.zeros((Cn, B), np.float32)
+    for b in range(NCHK):
+        conv.process(np.ascontiguousarray(x_chk[:, b * B:(b + 1) * B]), blk_out)
+        y_chk[:, b * B:(b + 1) * B] = blk_out
+    worst = 0.0
+    for c in sorted({0, Cn // 2, Cn - 1}):
+        h = synth_irs(chan0 + c, 1, 0, L)[0].astype(np.float64)
+        n = B * NCHK
+        nfft = 1 << int(np.ceil(np.log2(2 * n)))
+        truth = np.fft.irfft(np.fft.rfft(x_chk[c].astype(np.float64), nfft) * np.fft.rfft(h[:n], nfft), nfft)[:n]
+        worst = max(worst, float(np.max(np.abs(y_chk[c] - truth)) / np.sqrt(np.mean(truth ** 2))))
+    if worst > 1e-5:
+        raise SystemExit(f"bench.py: parity check failed: max-abs err {worst:.3e} x RMS > 1e-5")
+
+    # ---- device-resident inputs: 8 distinct blocks, rotated ------------------------------------
+    NIN = 8
+    with torch.cuda.stream(stream):
+        d_in = [torch.from_numpy(synth_noise(chan0, Cn, B * (NCHK + i), B)).cuda(local, non_blocking=False) for i in range(NIN)]
+        d_out = torch.empty((Cn, B), dtype=torch.float32, device=f"cuda:{local}")
+
+    def step_dev(i):
+        conv.process_dev(d_in[i % NIN].data_ptr(), B, B, d_out.data_ptr(), B, B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.fcb_launch_count()
+    _lib.check(lib.fcb_profile_mac(1))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step_dev(args.warmup + i)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    tot_ms, nl = C.c_double(), C.c_uint64()
+    _lib.check(lib.fcb_profile_mac_read(C.byref(tot_ms), C.byref(nl)))
+    _lib.check(lib.fcb_profile_mac(0))
+    launches = lib.fcb_launch_count() - launches0
+    clocks = sampler.stop()
+
+    # ---- end to end through the host-pointer API: pinned H2D + K1..K3 + D2H every step ---------
+    nbytes = Cn * B * 4
+    p_in, p_out = lib.fcb_host_alloc(nbytes), lib.fcb_host_alloc(nbytes)
+    if not p_in or not p_out:
+        raise SystemExit("bench.py: pinned allocation failed")
+    h_in = np.ctypeslib.as_array(C.cast(p_in, C.POINTER(C.c_float)), shape=(Cn, B))
+    h_out = np.ctypeslib.as_array(C.cast(p_out, C.POINTER(C.c_float)), shape=(Cn, B))
+    h_in[:] = synth_noise(chan0, Cn, B * (NCHK + NIN), B)
+    for _ in range(args.warmup):
+        conv.process(h_in, h_out)
+    barrier()
+    launches_e0 = lib.fcb_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        conv.process(h_in, h_out)  # synchronous: returns with the block's output in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    launches += lib.fcb_launch_count() - launches_e0
+    barrier()
+
+    t = torch.tensor([ms, e2e_s * 1000.0], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+
+    units = world * Cn * args.steps * B / SAMPLE_RATE  # channel-seconds of audio
+    value = units / (ms_max / 1000.0)
+    e2e_value = units / (e2e_ms_max / 1000.0)
+
+    # ---- roofline of the dominant kernel (K2) --------------------------------------------------
+    # algorithmic bytes per K2 launch: per channel 16*(S-1)*K read (IR rows + ring rows of segments
+    # 1..S-1; SURVEY §8(d)'s 16*S*K with segment 0 moved into K3) + 8*K pre_multiplied written
+    bytes_per_launch = Cn * (16 * (S - 1) * K + 8 * K)
+    k2_ms = tot_ms.value / max(nl.value, 1)
+    achieved = bytes_per_launch / (k2_ms / 1000.0) / 1e9
+    peak, peak_src = measured_peak_gbs()
+    traffic = None
+    tp = ROOT / "profiles" / "k2_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_mac (K2: delay-line complex MAC)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": bytes_per_launch,
+                "avg_launch_ms": k2_ms, "launches_timed": int(nl.value),
+                "k2_share_of_step": tot_ms.value / ms if ms > 0 else None}
+
+    if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle  # cpu_baseline leg only
+            threads = oracle.load().lib.orc_max_threads()
+            ch, calls = max(threads * 4, 8), 188
+            v, secs = cpu_port_run(ch, B, L, calls, threads)
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"{ch} channels x {calls} blocks of {B} (2 s of audio each), block loop only, {secs:.2f} s",
+                            "note": "CPU restatement of the reference algorithm, not rustfft (no Rust toolchain)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, {"segments": S, "mac_impl": args.mac_impl, "mac_stages": args.mac_stages,
+                                         "ir_gen_s": round(t_gen, 1)}),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                    "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "parity": {"max_abs_err_over_rms_vs_f64": worst, "tolerance": 1e-5},
+            "realtime_headroom": {"block_period_ms": 1000.0 * B / SAMPLE_RATE,
+                                  "block_time_ms": ms_max / args.steps},
+        }
+        print(json.dumps(line), flush=True)
+    lib.fcb_host_free(p_in)
+    lib.fcb_host_free(p_out)
+    conv.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--channels", type=int, default=4096, help="channels per GPU")
+    ap.add_argument("--block", type=int, default=512)
+    ap.add_argument("--ir-seconds", type=float, default=2.0)
+    ap.add_argument("--mac-impl", type=int, default=None)
+    ap.add_argument("--mac-stages", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

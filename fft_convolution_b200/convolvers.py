@@ -1,0 +1,265 @@
+"""Host-side mirror of the reference crate's `Convolution` trait (src/lib.rs:5-14) over the C ABI.
+
+Same names and argument meaning as the reference:
+    X.init(response, max_block_size, max_response_length) -> X
+    x.update(response); x.reset(); x.process(input, output)
+for X in FFTConvolver (src/fft_convolver.rs:100-321), TwoStageFFTConvolver (:337-540) and
+CrossfadeConvolver (src/crossfade_convolver.rs:3-105); contract violations that panic in the
+reference raise ConvolutionPanic, the two `todo!()` methods raise NotYetImplemented.
+
+Batched entry point: pass a 2-D response [channels, len]; input/output are then [channels, n]
+(planar).  A 1-D response gives the reference's mono convolver.  All sample arithmetic runs in
+the CUDA library; numpy arrays are only the host buffers handed across the boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ConvolutionPanic, NotYetImplemented, Options, check  # noqa: F401
+
+
+def _as_ir(response):
+    r = np.ascontiguousarray(response, dtype=np.float32)
+    if r.ndim == 1:
+        return r.reshape(1, -1), True
+    if r.ndim != 2:
+        raise ValueError("response must be 1-D (mono) or 2-D [channels, len]")
+    return r, False
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _opts(device=0, stream=None, shared_ir=False, async_tail=False, forced_tail_block=0) -> Options:
+    return Options(device, stream, int(shared_ir), int(async_tail), forced_tail_block)
+
+
+class _Base:
+    _free = None
+
+    def __init__(self, handle, channels: int, mono: bool):
+        self._h = handle
+        self.channels = channels
+        self._mono = mono
+
+    def _io(self, input, output):
+        x = np.ascontiguousarray(input, dtype=np.float32)
+        if not (isinstance(output, np.ndarray) and output.dtype == np.float32 and output.flags.c_contiguous):
+            raise TypeError("output must be a C-contiguous float32 ndarray")
+        if self._mono:
+            if x.ndim != 1 or output.ndim != 1:
+                raise ValueError("mono convolver expects 1-D input/output")
+            return x, x.shape[0], x.shape[0], output, output.shape[0], output.shape[0]
+        if x.ndim != 2 or output.ndim != 2 or x.shape[0] != self.channels or output.shape[0] != self.channels:
+            raise ValueError(f"batched convolver expects [{self.channels}, n] input/output")
+        return x, x.shape[1], x.shape[1], output, output.shape[1], output.shape[1]
+
+    def _irs(self, response):
+        r, _ = _as_ir(response)
+        if r.shape[0] != self._ir_channels:
+            raise ValueError(f"expected {self._ir_channels} impulse responses, got {r.shape[0]}")
+        return r
+
+    def close(self):
+        if getattr(self, "_h", None):
+            getattr(_lib.load(), self._free)(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FFTConvolver(_Base):
+    """Uniformly partitioned convolver; reference: src/fft_convolver.rs:100-321."""
+    _free = "fcb_fftconv_free"
+
+    @classmethod
+    def init(cls, response, block_size: int, max_response_length: int, *, channels: int | None = None,
+             device: int = 0, stream=None) -> "FFTConvolver":
+        """`channels` with a 1-D response = that many channels sharing one IR (stored once)."""
+        lib = _lib.load()
+        _lib.require_gpu()
+        r, mono = _as_ir(response)
+        shared = channels is not None and mono
+        nch = channels if shared else r.shape[0]
+        h = C.c_void_p()
+        o = _opts(device, stream, shared_ir=shared)
+        check(lib.fcb_fftconv_init(C.byref(h), _ptr(r), nch, r.shape[1], block_size, max_response_length, C.byref(o)))
+        self = cls(h, nch, mono and not shared)
+        self._ir_channels = 1 if shared else nch
+        return self
+
+    def clone(self) -> "FFTConvolver":
+        h = C.c_void_p()
+        check(_lib.load().fcb_fftconv_clone(self._h, C.byref(h)))
+        c = FFTConvolver(h, self.channels, self._mono)
+        c._ir_channels = self._ir_channels
+        return c
+
+    def update(self, response) -> None:
+        r = self._irs(response)
+        check(_lib.load().fcb_fftconv_update(self._h, _ptr(r), r.shape[1]))
+
+    def reset(self) -> None:
+        check(_lib.load().fcb_fftconv_reset(self._h))
+
+    def process(self, input, output) -> None:
+        x, n_in, s_in, y, n_out, s_out = self._io(input, output)
+        check(_lib.load().fcb_fftconv_process(self._h, _ptr(x), n_in, s_in, _ptr(y), n_out, s_out))
+
+    def process_dev(self, in_ptr: int, in_len: int, in_stride: int, out_ptr: int, out_len: int, out_stride: int) -> None:
+        """Asynchronous, device pointers (e.g. torch.Tensor.data_ptr())."""
+        check(_lib.load().fcb_fftconv_process_dev(self._h, in_ptr, in_len, in_stride, out_ptr, out_len, out_stride, None))
+
+    def sync(self) -> None:
+        check(_lib.load().fcb_fftconv_sync(self._h))
+
+    # scheduler scalars, for tests
+    block_size = property(lambda s: _lib.load().fcb_fftconv_block_size(s._h))
+    seg_count = property(lambda s: _lib.load().fcb_fftconv_seg_count(s._h))
+    active_seg_count = property(lambda s: _lib.load().fcb_fftconv_active_seg_count(s._h))
+    current = property(lambda s: _lib.load().fcb_fftconv_current(s._h))
+    fill = property(lambda s: _lib.load().fcb_fftconv_fill(s._h))
+
+    @property
+    def engine(self):
+        return _lib.load().fcb_fftconv_engine(self._h)
+
+    def _read_row(self, fn, *idx):
+        K = self.block_size + 1
+        buf = np.empty(2 * K, np.float32)
+        check(getattr(_lib.load(), fn)(self.engine, *idx, _ptr(buf)))
+        return buf.view(np.complex64)
+
+    def segment_ir(self, i, chan=0):
+        return self._read_row("fcb_engine_read_ir_segment", chan, i)
+
+    def segment(self, i, chan=0):
+        return self._read_row("fcb_engine_read_ring_segment", chan, i)
+
+    def premul(self, chan=0):
+        return self._read_row("fcb_engine_read_premul", chan)
+
+    def overlap(self, chan=0):
+        buf = np.empty(self.block_size, np.float32)
+        check(_lib.load().fcb_engine_read_overlap(self.engine, chan, _ptr(buf)))
+        return buf
+
+    def _release(self):
+        h, self._h = self._h, None
+        return h
+
+
+class TwoStageFFTConvolver(_Base):
+    """Two-stage (head/tail) partitioned convolver; reference: src/fft_convolver.rs:337-540."""
+    _free = "fcb_twostage_free"
+
+    @classmethod
+    def init(cls, response, block_size: int, max_response_length: int, *, device: int = 0, stream=None,
+             async_tail: bool = False, forced_tail_block: int = 0) -> "TwoStageFFTConvolver":
+        lib = _lib.load()
+        _lib.require_gpu()
+        r, mono = _as_ir(response)
+        h = C.c_void_p()
+        o = _opts(device, stream, async_tail=async_tail, forced_tail_block=forced_tail_block)
+        check(lib.fcb_twostage_init(C.byref(h), _ptr(r), r.shape[0], r.shape[1], block_size, max_response_length,
+                                    C.byref(o)))
+        self = cls(h, r.shape[0], mono)
+        self._ir_channels = r.shape[0]
+        return self
+
+    def clone(self):
+        h = C.c_void_p()
+        check(_lib.load().fcb_twostage_clone(self._h, C.byref(h)))
+        c = TwoStageFFTConvolver(h, self.channels, self._mono)
+        c._ir_channels = self._ir_channels
+        return c
+
+    def update(self, response) -> None:
+        r = self._irs(response)
+        check(_lib.load().fcb_twostage_update(self._h, _ptr(r), r.shape[1]))
+
+    def reset(self) -> None:
+        check(_lib.load().fcb_twostage_reset(self._h))
+
+    def process(self, input, output) -> None:
+        x, n_in, s_in, y, n_out, s_out = self._io(input, output)
+        check(_lib.load().fcb_twostage_process(self._h, _ptr(x), n_in, s_in, _ptr(y), n_out, s_out))
+
+    def process_dev(self, in_ptr, in_len, in_stride, out_ptr, out_len, out_stride) -> None:
+        check(_lib.load().fcb_twostage_process_dev(self._h, in_ptr, in_len, in_stride, out_ptr, out_len, out_stride))
+
+    def sync(self) -> None:
+        check(_lib.load().fcb_twostage_sync(self._h))
+
+    @property
+    def tail_block_size(self) -> int:
+        return _lib.load().fcb_twostage_tail_block_size(self._h)
+
+
+class CrossfadeConvolver(_Base):
+    """Artefact-free IR switching over two FFTConvolvers; reference: src/crossfade_convolver.rs:3-105."""
+    _free = "fcb_crossfade_free"
+
+    @classmethod
+    def new(cls, convolver: FFTConvolver, max_response_length: int, max_buffer_size: int,
+            crossfade_samples: int) -> "CrossfadeConvolver":
+        """Consumes `convolver` (the reference moves it in, src/crossfade_convolver.rs:20-42)."""
+        h = C.c_void_p()
+        channels, mono, irc = convolver.channels, convolver._mono, convolver._ir_channels
+        check(_lib.load().fcb_crossfade_new(C.byref(h), convolver._h, max_response_length, max_buffer_size,
+                                            crossfade_samples))
+        convolver._release()
+        self = cls(h, channels, mono)
+        self._ir_channels = irc
+        return self
+
+    @classmethod
+    def init(cls, response, max_block_size: int, max_response_length: int, *, device: int = 0, stream=None):
+        lib = _lib.load()
+        _lib.require_gpu()
+        r, mono = _as_ir(response)
+        h = C.c_void_p()
+        o = _opts(device, stream)
+        check(lib.fcb_crossfade_init(C.byref(h), _ptr(r), r.shape[0], r.shape[1], max_block_size,
+                                     max_response_length, C.byref(o)))
+        self = cls(h, r.shape[0], mono)
+        self._ir_channels = r.shape[0]
+        return self
+
+    def update(self, response) -> None:
+        r = self._irs(response)
+        check(_lib.load().fcb_crossfade_update(self._h, _ptr(r), r.shape[1]))
+
+    def reset(self) -> None:
+        check(_lib.load().fcb_crossfade_reset(self._h))
+
+    def process(self, input, output) -> None:
+        x, n_in, s_in, y, n_out, s_out = self._io(input, output)
+        check(_lib.load().fcb_crossfade_process(self._h, _ptr(x), n_in, s_in, _ptr(y), n_out, s_out))
+
+    def process_dev(self, in_ptr, in_len, in_stride, out_ptr, out_len, out_stride) -> None:
+        check(_lib.load().fcb_crossfade_process_dev(self._h, in_ptr, in_len, in_stride, out_ptr, out_len, out_stride))
+
+    def sync(self) -> None:
+        check(_lib.load().fcb_crossfade_sync(self._h))
+
+    def is_crossfading(self) -> bool:
+        return bool(_lib.load().fcb_crossfade_is_crossfading(self._h))
+
+    def state(self):
+        counter, mix, appr, tgt = C.c_int64(), C.c_float(), C.c_int(), C.c_int()
+        check(_lib.load().fcb_crossfade_state(self._h, C.byref(counter), C.byref(mix), C.byref(appr), C.byref(tgt)))
+        return counter.value, mix.value, bool(appr.value), tgt.value
+
+
+def compute_tail_block_size(head_len: int, response_len: int) -> int:
+    """src/fft_convolver.rs:534-540 (f32 arithmetic)."""
+    return _lib.load().fcb_compute_tail_block_size(head_len, response_len)

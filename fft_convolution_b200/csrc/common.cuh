@@ -1,0 +1,57 @@
+// common.cuh — error plumbing shared by the engine and the host mirror.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/fftconv_b200.h"
+
+namespace fcb {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define FCB_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t err__ = (expr);                                                                 \
+        if (err__ != cudaSuccess)                                                                   \
+            return ::fcb::fail(FCB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                               __FILE__, __LINE__);                                                 \
+    } while (0)
+
+#define FCB_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != FCB_OK) return rc__; \
+    } while (0)
+
+inline size_t next_power_of_two(size_t v)
+{
+    size_t p = 1; // usize::next_power_of_two(0) == 1
+    while (p < v) p <<= 1;
+    return p;
+}
+
+inline int ilog2(size_t v)
+{
+    int l = 0;
+    while (((size_t)1 << l) < v) l++;
+    return l;
+}
+
+} // namespace fcb

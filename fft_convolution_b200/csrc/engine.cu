@@ -1,0 +1,623 @@
+// engine.cu — layer 1 of the C ABI: device state of C lock-step FFTConvolver channels and the
+// stage launches K1 (forward FFT), K2 (delay-line MAC), K3 (inverse FFT + overlap-add +
+// epilogues), K5 (IR preparation).  The caller (Rust host or the C++ mirror in host_mirror.cu)
+// owns the scheduler scalars `current`, `fill`, `active` (src/fft_convolver.rs:113-115,105).
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "fft_kernels.cuh"
+#include "mac_kernels.cuh"
+
+namespace fcb {
+thread_local std::string g_last_error = "";
+std::atomic<uint64_t> g_launches{0};
+
+// ---- twiddle tables: tw[t] = exp(-2 pi i t / N), t < N, rounded from f64; one per (device, N)
+static std::mutex g_tw_mutex;
+static std::map<std::pair<int, size_t>, float2 *> g_tw;
+
+static int get_twiddles(int device, size_t N, const float2 **out)
+{
+    std::lock_guard<std::mutex> lock(g_tw_mutex);
+    auto key = std::make_pair(device, N);
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) {
+        *out = it->second;
+        return FCB_OK;
+    }
+    std::vector<float2> h(N);
+    for (size_t t = 0; t < N; t++) {
+        double a = -2.0 * M_PI * (double)t / (double)N;
+        h[t] = make_float2((float)cos(a), (float)sin(a));
+    }
+    float2 *d = nullptr;
+    FCB_CUDA(cudaMalloc(&d, N * sizeof(float2)));
+    FCB_CUDA(cudaMemcpy(d, h.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
+    g_tw[key] = d;
+    *out = d;
+    return FCB_OK;
+}
+} // namespace fcb
+
+using namespace fcb;
+
+struct fcb_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    size_t C = 0, B = 0, S = 0, L = 0;
+    int logb = 0;
+    bool shared_ir = false;
+    float2 *ir = nullptr, *ring = nullptr, *premul = nullptr;
+    float *overlap = nullptr, *inbuf = nullptr;
+    float *stage = nullptr; // IR upload staging
+    size_t stage_floats = 0;
+    const float2 *tw = nullptr;
+
+    long long ir_stride() const { return shared_ir ? 0 : (long long)(S * B); }
+    long long ring_stride() const { return (long long)(S * B); }
+    size_t ir_channels() const { return shared_ir ? 1 : C; }
+};
+
+// ---- launch helpers ---------------------------------------------------------------------------
+#define FCB_DISPATCH_LOGB(logb, CALL)                                                       \
+    switch (logb) {                                                                         \
+    case 0: { constexpr int LB = 0; CALL; } break;                                          \
+    case 1: { constexpr int LB = 1; CALL; } break;                                          \
+    case 2: { constexpr int LB = 2; CALL; } break;                                          \
+    case 3: { constexpr int LB = 3; CALL; } break;                                          \
+    case 4: { constexpr int LB = 4; CALL; } break;                                          \
+    case 5: { constexpr int LB = 5; CALL; } break;                                          \
+    case 6: { constexpr int LB = 6; CALL; } break;                                          \
+    case 7: { constexpr int LB = 7; CALL; } break;                                          \
+    case 8: { constexpr int LB = 8; CALL; } break;                                          \
+    case 9: { constexpr int LB = 9; CALL; } break;                                          \
+    case 10: { constexpr int LB = 10; CALL; } break;                                        \
+    case 11: { constexpr int LB = 11; CALL; } break;                                        \
+    case 12: { constexpr int LB = 12; CALL; } break;                                        \
+    case 13: { constexpr int LB = 13; CALL; } break;                                        \
+    case 14: { constexpr int LB = 14; CALL; } break;                                        \
+    default: return fail(FCB_ERR_UNSUPPORTED, "block size 2^%d not supported (max 16384)", logb); \
+    }
+
+template <int LOGB>
+static int launch_forward(const fcb_engine *e, const float *src, long long src_stride, int len, float2 *dst,
+                          long long dst_stride, int nseg, long long ntransforms)
+{
+    using P = FftPlan<LOGB>;
+    static bool attr_done = false;
+    if (!attr_done && P::SMEM_BYTES > 48 * 1024) {
+        FCB_CUDA(cudaFuncSetAttribute(k_rfft_forward<LOGB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)P::SMEM_BYTES));
+        attr_done = true;
+    }
+    if (ntransforms <= 0) return FCB_OK;
+    long long grid = (ntransforms + P::TPB - 1) / P::TPB;
+    k_rfft_forward<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, e->stream>>>(src, src_stride, len, dst, dst_stride,
+                                                                               nseg, ntransforms, e->tw);
+    g_launches++;
+    FCB_CUDA(cudaGetLastError());
+    return FCB_OK;
+}
+
+template <int LOGB>
+static int launch_inverse(const fcb_engine *e, const IfftArgs &a)
+{
+    using P = FftPlan<LOGB>;
+    static bool attr_done = false;
+    if (!attr_done && P::SMEM_BYTES > 48 * 1024) {
+        FCB_CUDA(cudaFuncSetAttribute(k_irfft_ola<LOGB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)P::SMEM_BYTES));
+        attr_done = true;
+    }
+    long long grid = (a.nchan + P::TPB - 1) / P::TPB;
+    k_irfft_ola<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, e->stream>>>(a, e->tw);
+    g_launches++;
+    FCB_CUDA(cudaGetLastError());
+    return FCB_OK;
+}
+
+// ---- live per-launch timing of K2 (bench.py's roofline.achieved): CUDA events recorded on the
+// launching stream around every K2 launch while profiling is on, read back after a sync
+struct MacProfile {
+    std::mutex mu;
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool, used;
+};
+static MacProfile g_prof;
+
+static cudaEvent_t prof_before(cudaStream_t s, cudaEvent_t *stop)
+{
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    if (!g_prof.on) return nullptr;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!g_prof.pool.empty()) {
+        ev = g_prof.pool.back();
+        g_prof.pool.pop_back();
+    } else if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) {
+        return nullptr;
+    }
+    g_prof.used.push_back(ev);
+    cudaEventRecord(ev.first, s);
+    *stop = ev.second;
+    return ev.first;
+}
+
+extern "C" int fcb_profile_mac(int enable)
+{
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    g_prof.on = enable != 0;
+    for (auto &ev : g_prof.used) g_prof.pool.push_back(ev);
+    g_prof.used.clear();
+    return FCB_OK;
+}
+
+extern "C" int fcb_profile_mac_read(double *total_ms, uint64_t *launches)
+{
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    double tot = 0.0;
+    for (auto &ev : g_prof.used) {
+        FCB_CUDA(cudaEventSynchronize(ev.second));
+        float ms = 0.f;
+        FCB_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = g_prof.used.size();
+    return FCB_OK;
+}
+
+// tuning knobs (fcb_tune): which K2 implementation, how many pipeline stages
+static std::atomic<int> g_mac_impl{0};   // 0 = auto (TMA pipeline for B >= 32), 1 = LDG, 2 = TMA
+static std::atomic<int> g_mac_stages{3}; // 2, 3, 4 or 6
+
+template <int B, int NST>
+static int launch_mac_bulk(const fcb_engine *e, const MacArgs &a)
+{
+    using Cfg = MacBulkCfg<B>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        FCB_CUDA(cudaFuncSetAttribute(k_mac_bulk<B, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)Cfg::smem_bytes(NST)));
+        attr_done = true;
+    }
+    long long groups = (a.nchan + Cfg::CPB - 1) / Cfg::CPB;
+    k_mac_bulk<B, NST><<<(unsigned)(groups * Cfg::TILES), 256, Cfg::smem_bytes(NST), e->stream>>>(a);
+    return FCB_OK;
+}
+
+template <int LOGB>
+static int launch_mac(const fcb_engine *e, const MacArgs &a)
+{
+    constexpr int B = 1 << LOGB;
+    if (a.active <= 1) { // no segment beyond 0: pre_multiplied = 0 (src/fft_convolver.rs:259)
+        FCB_CUDA(cudaMemsetAsync(a.premul, 0, (size_t)a.nchan * B * sizeof(float2), e->stream));
+        return FCB_OK;
+    }
+    const int impl = g_mac_impl.load();
+    cudaEvent_t prof_stop = nullptr;
+    const bool profiled = prof_before(e->stream, &prof_stop) != nullptr;
+    if constexpr (B == 1) {
+        unsigned grid = (unsigned)((a.nchan + 255) / 256);
+        k_mac_b1<<<grid, 256, 0, e->stream>>>(a);
+    } else {
+        bool bulk = impl == 2 || (impl == 0 && B >= 32);
+        if constexpr (B < 4) bulk = false;
+        if (bulk) {
+            if constexpr (B >= 4) {
+                switch (g_mac_stages.load()) {
+                case 2: FCB_TRY((launch_mac_bulk<B, 2>(e, a))); break;
+                case 4: FCB_TRY((launch_mac_bulk<B, 4>(e, a))); break;
+                case 6: FCB_TRY((launch_mac_bulk<B, 6>(e, a))); break;
+                default: FCB_TRY((launch_mac_bulk<B, 3>(e, a))); break;
+                }
+            }
+        } else {
+            constexpr int ROW4 = B / 2;
+            constexpr int TX = ROW4 < 256 ? ROW4 : 256;
+            constexpr int TILES = ROW4 / TX;
+            constexpr int CPB = 256 / TX;
+            long long groups = (a.nchan + CPB - 1) / CPB;
+            k_mac_v4<B, 8><<<(unsigned)(groups * TILES), 256, 0, e->stream>>>(a);
+        }
+    }
+    if (profiled) cudaEventRecord(prof_stop, e->stream);
+    g_launches++;
+    FCB_CUDA(cudaGetLastError());
+    return FCB_OK;
+}
+
+extern "C" int fcb_tune(const char *key, int value)
+{
+    if (!key) return fail(FCB_ERR_ARG, "fcb_tune: NULL key");
+    if (!strcmp(key, "mac_impl") && value >= 0 && value <= 2) g_mac_impl = value;
+    else if (!strcmp(key, "mac_stages") && (value == 2 || value == 3 || value == 4 || value == 6)) g_mac_stages = value;
+    else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);
+    return FCB_OK;
+}
+
+// ---- misc exports -----------------------------------------------------------------------------
+extern "C" const char *fcb_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *fcb_version(void) { return "fftconv_b200 0.1.0 sm_100a"; }
+extern "C" uint64_t fcb_launch_count(void) { return g_launches.load(); }
+extern "C" int fcb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return n;
+}
+extern "C" void *fcb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        g_last_error = "cudaHostAlloc failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void fcb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ---- lifecycle --------------------------------------------------------------------------------
+static int alloc_zero(void **p, size_t bytes, cudaStream_t s)
+{
+    FCB_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    FCB_CUDA(cudaMemsetAsync(*p, 0, bytes ? bytes : 16, s));
+    return FCB_OK;
+}
+
+static int engine_alloc(fcb_engine *e)
+{
+    const size_t rowsC = e->C * e->S * e->B, rowsI = e->ir_channels() * e->S * e->B;
+    FCB_TRY(alloc_zero((void **)&e->ir, rowsI * sizeof(float2), e->stream));
+    FCB_TRY(alloc_zero((void **)&e->ring, rowsC * sizeof(float2), e->stream));
+    FCB_TRY(alloc_zero((void **)&e->premul, e->C * e->B * sizeof(float2), e->stream));
+    FCB_TRY(alloc_zero((void **)&e->overlap, e->C * e->B * sizeof(float), e->stream));
+    FCB_TRY(alloc_zero((void **)&e->inbuf, e->C * e->B * sizeof(float), e->stream));
+    // staging for host IR uploads: whole channels, at most ~64 MB, at least one channel
+    size_t per = e->L ? e->L : 1;
+    size_t want = e->ir_channels() * per, cap = (size_t)16 << 20;
+    e->stage_floats = want < cap ? want : (cap / per ? (cap / per) * per : per);
+    FCB_TRY(alloc_zero((void **)&e->stage, e->stage_floats * sizeof(float), e->stream));
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_create(const fcb_engine_desc *d, fcb_engine **out)
+{
+    if (!d || !out) return fail(FCB_ERR_ARG, "fcb_engine_create: NULL argument");
+    *out = nullptr;
+    if (d->channels == 0) return fail(FCB_ERR_ARG, "fcb_engine_create: channels must be >= 1");
+    size_t B = next_power_of_two(d->block_size); // src/fft_convolver.rs:129
+    if (B > 16384) return fail(FCB_ERR_UNSUPPORTED, "block size %zu > 16384 not supported", B);
+    FCB_CUDA(cudaSetDevice(d->device));
+    fcb_engine *e = new fcb_engine();
+    e->device = d->device;
+    e->C = d->channels;
+    e->B = B;
+    e->logb = ilog2(B);
+    e->L = d->max_response_length;
+    e->S = (size_t)std::ceil((double)e->L / (double)B); // :131
+    e->shared_ir = d->shared_ir != 0;
+    if (d->stream) {
+        e->stream = (cudaStream_t)d->stream;
+    } else {
+        cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        if (err != cudaSuccess) {
+            delete e;
+            return fail(FCB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(err));
+        }
+        e->own_stream = true;
+    }
+    int rc = get_twiddles(e->device, 2 * B, &e->tw);
+    if (rc == FCB_OK) rc = engine_alloc(e);
+    if (rc != FCB_OK) {
+        fcb_engine_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return FCB_OK;
+}
+
+extern "C" void fcb_engine_destroy(fcb_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->ir);
+    cudaFree(e->ring);
+    cudaFree(e->premul);
+    cudaFree(e->overlap);
+    cudaFree(e->inbuf);
+    cudaFree(e->stage);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int fcb_engine_clone(const fcb_engine *s, fcb_engine **out)
+{
+    if (!s || !out) return fail(FCB_ERR_ARG, "fcb_engine_clone: NULL argument");
+    fcb_engine_desc d{s->C, s->B, s->L, s->shared_ir ? 1 : 0, s->device, s->own_stream ? nullptr : (void *)s->stream};
+    fcb_engine *e = nullptr;
+    FCB_TRY(fcb_engine_create(&d, &e));
+    // order the copy after everything queued on the source stream
+    cudaEvent_t ev;
+    FCB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    FCB_CUDA(cudaEventRecord(ev, s->stream));
+    FCB_CUDA(cudaStreamWaitEvent(e->stream, ev, 0));
+    const size_t rowsC = s->C * s->S * s->B, rowsI = s->ir_channels() * s->S * s->B;
+    cudaStream_t st = e->stream;
+    FCB_CUDA(cudaMemcpyAsync(e->ir, s->ir, rowsI * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    FCB_CUDA(cudaMemcpyAsync(e->ring, s->ring, rowsC * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    FCB_CUDA(cudaMemcpyAsync(e->premul, s->premul, s->C * s->B * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    FCB_CUDA(cudaMemcpyAsync(e->overlap, s->overlap, s->C * s->B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    FCB_CUDA(cudaMemcpyAsync(e->inbuf, s->inbuf, s->C * s->B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    FCB_CUDA(cudaStreamSynchronize(st));
+    cudaEventDestroy(ev);
+    *out = e;
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_set_stream(fcb_engine *e, void *stream)
+{
+    if (!e) return fail(FCB_ERR_ARG, "NULL engine");
+    FCB_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    e->own_stream = false;
+    if (stream) {
+        e->stream = (cudaStream_t)stream;
+    } else {
+        FCB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        e->own_stream = true;
+    }
+    return FCB_OK;
+}
+extern "C" void *fcb_engine_stream(const fcb_engine *e) { return e ? (void *)e->stream : nullptr; }
+extern "C" int fcb_engine_sync(fcb_engine *e)
+{
+    if (!e) return fail(FCB_ERR_ARG, "NULL engine");
+    FCB_CUDA(cudaStreamSynchronize(e->stream));
+    return FCB_OK;
+}
+extern "C" size_t fcb_engine_channels(const fcb_engine *e) { return e->C; }
+extern "C" size_t fcb_engine_block_size(const fcb_engine *e) { return e->B; }
+extern "C" size_t fcb_engine_seg_count(const fcb_engine *e) { return e->S; }
+
+// ---- K5: IR preparation -----------------------------------------------------------------------
+static int set_ir_common(fcb_engine *e, size_t chan0, size_t nchan, const float *irs, size_t len, size_t stride,
+                         int is_update, bool on_device)
+{
+    if (!e) return fail(FCB_ERR_ARG, "NULL engine");
+    if (len > e->L) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
+    if (chan0 + nchan > e->ir_channels())
+        return fail(FCB_ERR_ARG, "set_ir: channel range [%zu,%zu) outside %zu IR channels", chan0, chan0 + nchan,
+                    e->ir_channels());
+    if (len && !irs) return fail(FCB_ERR_ARG, "set_ir: NULL impulse response");
+    if (e->S == 0 || nchan == 0) return FCB_OK; // src/fft_convolver.rs:195-197
+    FCB_CUDA(cudaSetDevice(e->device));
+    if (is_update) { // :199-202 (fft_buffer and conv are transient on the device)
+        size_t c0 = e->shared_ir ? 0 : chan0, nc = e->shared_ir ? e->C : nchan;
+        FCB_CUDA(cudaMemsetAsync(e->premul + c0 * e->B, 0, nc * e->B * sizeof(float2), e->stream));
+        FCB_CUDA(cudaMemsetAsync(e->overlap + c0 * e->B, 0, nc * e->B * sizeof(float), e->stream));
+    }
+    const long long rows = (long long)(e->S * e->B);
+    if (on_device || len == 0) {
+        FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, irs, (long long)stride, (int)len,
+                                                              e->ir + chan0 * rows, rows, (int)e->S,
+                                                              (long long)(nchan * e->S))));
+        return FCB_OK;
+    }
+    size_t per_group = e->stage_floats / len;
+    if (per_group == 0) return fail(FCB_ERR_CUDA, "IR staging buffer too small");
+    for (size_t g0 = 0; g0 < nchan; g0 += per_group) {
+        size_t g = nchan - g0 < per_group ? nchan - g0 : per_group;
+        FCB_CUDA(cudaMemcpy2DAsync(e->stage, len * sizeof(float), irs + (g0)*stride, stride * sizeof(float),
+                                   len * sizeof(float), g, cudaMemcpyHostToDevice, e->stream));
+        FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, e->stage, (long long)len, (int)len,
+                                                              e->ir + (chan0 + g0) * rows, rows, (int)e->S,
+                                                              (long long)(g * e->S))));
+        if (g0 + per_group < nchan) FCB_CUDA(cudaStreamSynchronize(e->stream)); // staging reuse
+    }
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_set_ir(fcb_engine *e, size_t chan0, size_t nchan, const float *irs, size_t len,
+                                 size_t stride, int is_update)
+{
+    return set_ir_common(e, chan0, nchan, irs, len, stride, is_update, false);
+}
+extern "C" int fcb_engine_set_ir_dev(fcb_engine *e, size_t chan0, size_t nchan, const float *irs, size_t len,
+                                     size_t stride, int is_update)
+{
+    return set_ir_common(e, chan0, nchan, irs, len, stride, is_update, true);
+}
+
+extern "C" int fcb_engine_reset(fcb_engine *e)
+{
+    if (!e) return fail(FCB_ERR_ARG, "NULL engine");
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_CUDA(cudaMemsetAsync(e->ring, 0, e->C * e->S * e->B * sizeof(float2), e->stream));
+    FCB_CUDA(cudaMemsetAsync(e->premul, 0, e->C * e->B * sizeof(float2), e->stream));
+    FCB_CUDA(cudaMemsetAsync(e->overlap, 0, e->C * e->B * sizeof(float), e->stream));
+    FCB_CUDA(cudaMemsetAsync(e->inbuf, 0, e->C * e->B * sizeof(float), e->stream));
+    return FCB_OK;
+}
+
+// ---- per-chunk stages -----------------------------------------------------------------------
+static int push_common(fcb_engine *e, const float *in, size_t stride, size_t fill, size_t n, cudaMemcpyKind kind)
+{
+    if (!e || !in) return fail(FCB_ERR_ARG, "push_input: NULL argument");
+    if (fill + n > e->B) return fail(FCB_ERR_ARG, "push_input: fill %zu + n %zu exceeds block %zu", fill, n, e->B);
+    if (n == 0) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_CUDA(cudaMemcpy2DAsync(e->inbuf + fill, e->B * sizeof(float), in, stride * sizeof(float), n * sizeof(float),
+                               e->C, kind, e->stream));
+    return FCB_OK;
+}
+extern "C" int fcb_engine_push_input(fcb_engine *e, const float *in, size_t stride, size_t fill, size_t n)
+{
+    return push_common(e, in, stride, fill, n, cudaMemcpyHostToDevice);
+}
+extern "C" int fcb_engine_push_input_dev(fcb_engine *e, const float *in, size_t stride, size_t fill, size_t n)
+{
+    return push_common(e, in, stride, fill, n, cudaMemcpyDeviceToDevice);
+}
+
+static int check_sched(const fcb_engine *e, size_t current, size_t active, const char *who)
+{
+    if (!e) return fail(FCB_ERR_ARG, "%s: NULL engine", who);
+    // `current` may legitimately exceed `active` after update() shrank the IR (quirk of
+    // src/fft_convolver.rs:204,262,301-305): ring slots are then re-read modulo `active`
+    if (active > e->S || (e->S && current >= e->S))
+        return fail(FCB_ERR_ARG, "%s: current %zu / active %zu outside seg_count %zu", who, current, active, e->S);
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_fft_forward(fcb_engine *e, size_t current, size_t valid)
+{
+    FCB_TRY(check_sched(e, current, e->S, "fft_forward"));
+    if (valid > e->B) return fail(FCB_ERR_ARG, "fft_forward: valid %zu > block %zu", valid, e->B);
+    if (e->S == 0) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, e->inbuf, (long long)e->B, (int)valid,
+                                                          e->ring + current * e->B, e->ring_stride(), 1,
+                                                          (long long)e->C)));
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_mac(fcb_engine *e, size_t current, size_t active)
+{
+    FCB_TRY(check_sched(e, current, active, "mac"));
+    if (active == 0) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(e->device));
+    MacArgs a{e->ir, e->ir_stride(), e->ring, e->ring_stride(), e->premul, (int)current, (int)active, (long long)e->C};
+    FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_mac<LB>(e, a)));
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_ifft_ola(fcb_engine *e, size_t current, size_t fill, size_t n, int block_complete,
+                                   float *out_dev, size_t out_stride, const fcb_epilogue *epi)
+{
+    FCB_TRY(check_sched(e, current, e->S, "ifft_ola"));
+    if (!out_dev) return fail(FCB_ERR_ARG, "ifft_ola: NULL output");
+    if (fill + n > e->B) return fail(FCB_ERR_ARG, "ifft_ola: fill %zu + n %zu exceeds block %zu", fill, n, e->B);
+    if (e->S == 0) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(e->device));
+    IfftArgs a{};
+    a.ring_cur = e->ring + current * e->B;
+    a.ring_stride = e->ring_stride();
+    a.ir0 = e->ir;
+    a.ir_stride = e->ir_stride();
+    a.premul = e->premul;
+    a.overlap = e->overlap;
+    a.out = out_dev;
+    a.out_stride = (long long)out_stride;
+    a.fill = (int)fill;
+    a.n = (int)n;
+    a.block_complete = block_complete;
+    a.nchan = (long long)e->C;
+    if (epi) a.epi = *epi;
+    FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_inverse<LB>(e, a)));
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_fetch(fcb_engine *e, float *out_host, size_t host_stride, const float *src_dev,
+                                size_t dev_stride, size_t n)
+{
+    if (!e || !out_host || !src_dev) return fail(FCB_ERR_ARG, "fetch: NULL argument");
+    FCB_CUDA(cudaSetDevice(e->device));
+    if (n)
+        FCB_CUDA(cudaMemcpy2DAsync(out_host, host_stride * sizeof(float), src_dev, dev_stride * sizeof(float),
+                                   n * sizeof(float), e->C, cudaMemcpyDeviceToHost, e->stream));
+    FCB_CUDA(cudaStreamSynchronize(e->stream));
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, size_t in_stride, float *out_dev,
+                                            size_t out_stride, size_t current, size_t active,
+                                            const fcb_epilogue *epi)
+{
+    FCB_TRY(check_sched(e, current, active, "process_block"));
+    if (!in_dev || !out_dev) return fail(FCB_ERR_ARG, "process_block: NULL argument");
+    if (active == 0) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(e->device));
+    // K1 straight from the caller's block: a full block leaves the input buffer empty again (:294-295)
+    FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, in_dev, (long long)in_stride, (int)e->B,
+                                                          e->ring + current * e->B, e->ring_stride(), 1,
+                                                          (long long)e->C)));
+    FCB_TRY(fcb_engine_mac(e, current, active));
+    return fcb_engine_ifft_ola(e, current, 0, e->B, 1, out_dev, out_stride, epi);
+}
+
+// ---- debug readback in the reference layout (K = B+1 interleaved complex) ------------------------
+static int read_row(fcb_engine *e, const float2 *row, float *out_2k)
+{
+    std::vector<float2> h(e->B);
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_CUDA(cudaStreamSynchronize(e->stream));
+    FCB_CUDA(cudaMemcpy(h.data(), row, e->B * sizeof(float2), cudaMemcpyDeviceToHost));
+    out_2k[0] = h[0].x;
+    out_2k[1] = 0.f;
+    for (size_t k = 1; k < e->B; k++) {
+        out_2k[2 * k] = h[k].x;
+        out_2k[2 * k + 1] = h[k].y;
+    }
+    out_2k[2 * e->B] = h[0].y;
+    out_2k[2 * e->B + 1] = 0.f;
+    return FCB_OK;
+}
+static int write_row(fcb_engine *e, float2 *row, const float *in_2k)
+{
+    std::vector<float2> h(e->B);
+    h[0] = make_float2(in_2k[0], in_2k[2 * e->B]);
+    for (size_t k = 1; k < e->B; k++) h[k] = make_float2(in_2k[2 * k], in_2k[2 * k + 1]);
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_CUDA(cudaStreamSynchronize(e->stream));
+    FCB_CUDA(cudaMemcpy(row, h.data(), e->B * sizeof(float2), cudaMemcpyHostToDevice));
+    return FCB_OK;
+}
+#define FCB_CHECK_ROW(e, chan, seg, nch)                                                   \
+    if (!(e) || (chan) >= (nch) || (seg) >= (e)->S) return fail(FCB_ERR_ARG, "row index out of range")
+
+extern "C" int fcb_engine_read_ir_segment(fcb_engine *e, size_t chan, size_t seg, float *out)
+{
+    FCB_CHECK_ROW(e, chan, seg, e->ir_channels());
+    return read_row(e, e->ir + (chan * e->S + seg) * e->B, out);
+}
+extern "C" int fcb_engine_read_ring_segment(fcb_engine *e, size_t chan, size_t seg, float *out)
+{
+    FCB_CHECK_ROW(e, chan, seg, e->C);
+    return read_row(e, e->ring + (chan * e->S + seg) * e->B, out);
+}
+extern "C" int fcb_engine_write_ir_segment(fcb_engine *e, size_t chan, size_t seg, const float *in)
+{
+    FCB_CHECK_ROW(e, chan, seg, e->ir_channels());
+    return write_row(e, e->ir + (chan * e->S + seg) * e->B, in);
+}
+extern "C" int fcb_engine_write_ring_segment(fcb_engine *e, size_t chan, size_t seg, const float *in)
+{
+    FCB_CHECK_ROW(e, chan, seg, e->C);
+    return write_row(e, e->ring + (chan * e->S + seg) * e->B, in);
+}
+extern "C" int fcb_engine_read_premul(fcb_engine *e, size_t chan, float *out)
+{
+    if (!e || chan >= e->C) return fail(FCB_ERR_ARG, "channel out of range");
+    return read_row(e, e->premul + chan * e->B, out);
+}
+extern "C" int fcb_engine_read_overlap(fcb_engine *e, size_t chan, float *out)
+{
+    if (!e || chan >= e->C) return fail(FCB_ERR_ARG, "channel out of range");
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_CUDA(cudaStreamSynchronize(e->stream));
+    FCB_CUDA(cudaMemcpy(out, e->overlap + chan * e->B, e->B * sizeof(float), cudaMemcpyDeviceToHost));
+    return FCB_OK;
+}

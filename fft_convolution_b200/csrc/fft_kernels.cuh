@@ -1,0 +1,376 @@
+// fft_kernels.cuh — K1 / K5 (real-to-complex forward FFT) and K3 (complex-to-real inverse FFT
+// fused with the segment-0 MAC, 1/N normalisation, overlap-add, overlap save and the
+// two-stage / crossfade epilogues) for sm_100a.
+//
+// Replaces the reference's `Fft` adapter over realfft/rustfft (src/fft_convolver.rs:21-64) and
+// the per-chunk arithmetic of FFTConvolver::process (:248-255, :270-288, :297-298).
+//
+// Transform: a real FFT of N = 2B points is one B-point complex FFT plus a split pass
+// (z[j] = x[2j] + i x[2j+1]).  The complex FFT is a shared-memory Stockham autosort with
+// radix-8/4/2 register butterflies: every thread holds E = 8 (16 for B = 16384) points, so one
+// transform uses B/E threads and several transforms share a CTA when B is small.  Twiddles
+// come from a table rounded from f64 (tw[t] = exp(-2 pi i t / N), t < N), never from
+// fast-math sincos — the 1e-5*RMS parity budget leaves only ~6x headroom.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fftconv_b200.h"
+
+namespace fcb {
+
+// ---- small complex helpers -------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// multiply by -i (DIR < 0) or +i (DIR > 0)
+template <int DIR>
+__device__ __forceinline__ float2 mul_dir_i(float2 a)
+{
+    return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+
+// shared-memory index padding: one float2 of padding per 16 keeps the strided Stockham
+// scatter (stride R*Ns) off a single bank pair
+__device__ __host__ __forceinline__ constexpr int sidx(int i) { return i + (i >> 4); }
+
+// ---- compile-time plan ----------------------------------------------------------------
+template <int LOGB>
+struct FftPlan {
+    static constexpr int B = 1 << LOGB;
+    static constexpr int E = LOGB >= 14 ? 16 : (LOGB >= 3 ? 8 : B); // points per thread
+    static constexpr int T = B / E;                                 // threads per transform
+    static constexpr int CTA = T >= 256 ? T : 256;                  // threads per CTA
+    static constexpr int TPB = CTA / T;                             // transforms per CTA
+    static constexpr int SMEM_PER = sidx(B) + 1;                    // float2 per transform
+    static constexpr size_t SMEM_BYTES = (size_t)TPB * SMEM_PER * sizeof(float2);
+};
+
+// radix of pass `p` for a 2^LOGB-point transform, 0 when past the last pass
+__host__ __device__ constexpr int radix_at(int logb, int p)
+{
+    int n8 = logb / 3, rem = logb % 3;
+    if (logb == 0) return 0;
+    if (logb == 1) return p == 0 ? 2 : 0;
+    if (rem == 0) return p < n8 ? 8 : 0;
+    if (rem == 2) return p < n8 ? 8 : (p == n8 ? 4 : 0);
+    /* rem == 1, logb >= 4: (n8-1) radix-8 passes then two radix-4 */
+    return p < n8 - 1 ? 8 : (p < n8 + 1 ? 4 : 0);
+}
+
+// ---- in-register DFTs, natural order out ------------------------------------------------
+template <int DIR>
+__device__ __forceinline__ void dft2(float2 &a, float2 &b)
+{
+    float2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+
+template <int DIR>
+__device__ __forceinline__ void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_dir_i<DIR>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = cadd(t1, t3);
+    a3 = csub(t1, t3);
+}
+
+template <int DIR>
+__device__ __forceinline__ void dft8(float2 (&v)[8])
+{
+    // evens / odds
+    dft4<DIR>(v[0], v[2], v[4], v[6]);
+    dft4<DIR>(v[1], v[3], v[5], v[7]);
+    // odd outputs times w8^k, k = 0..3 (w8 = exp(DIR * 2 pi i / 8))
+    const float h = 0.70710678118654752440f;
+    float2 o1 = v[3], o2 = v[5], o3 = v[7];
+    // after dft4 on (v1,v3,v5,v7): v1 = O[0], v3 = O[1], v5 = O[2], v7 = O[3]
+    if (DIR < 0) {
+        o1 = make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));  // * (1 - i)/sqrt2
+        o2 = make_float2(o2.y, -o2.x);                           // * -i
+        o3 = make_float2(h * (o3.y - o3.x), -h * (o3.x + o3.y)); // * (-1 - i)/sqrt2
+    } else {
+        o1 = make_float2(h * (o1.x - o1.y), h * (o1.x + o1.y));  // * (1 + i)/sqrt2
+        o2 = make_float2(-o2.y, o2.x);                           // * +i
+        o3 = make_float2(-h * (o3.x + o3.y), h * (o3.x - o3.y)); // * (-1 + i)/sqrt2
+    }
+    float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+template <int R, int DIR>
+__device__ __forceinline__ void dftR(float2 (&v)[R])
+{
+    if constexpr (R == 2) dft2<DIR>(v[0], v[1]);
+    else if constexpr (R == 4) dft4<DIR>(v[0], v[1], v[2], v[3]);
+    else dft8<DIR>(v);
+}
+
+// ---- one Stockham pass over a transform resident in shared memory ------------------------
+// s: this transform's padded buffer; tid in [0, T); tw: table of N = 2B entries.
+template <int LOGB, int R, int DIR, int NS>
+__device__ __forceinline__ void stockham_pass(float2 *s, int tid, const float2 *__restrict__ tw)
+{
+    using P = FftPlan<LOGB>;
+    constexpr int B = P::B, T = P::T, NB = P::E / R, Q = B / R; // butterflies per thread, stride
+    float2 v[NB][R];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        int j = tid + b * T;
+#pragma unroll
+        for (int r = 0; r < R; r++) v[b][r] = s[sidx(j + r * Q)];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        int j = tid + b * T;
+        int k = j & (NS - 1);
+        if constexpr (NS > 1) {
+            // twiddle v[r] *= w_{NS*R}^{r k} = tw[r * k * (N / (NS*R))], N = 2B
+            constexpr int STEP = (2 * B) / (NS * R);
+#pragma unroll
+            for (int r = 1; r < R; r++) {
+                float2 w = __ldg(&tw[r * k * STEP]);
+                if (DIR > 0) w.y = -w.y;
+                v[b][r] = cmul(v[b][r], w);
+            }
+        }
+        dftR<R, DIR>(v[b]);
+        int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; r++) s[sidx(j0 + r * NS)] = v[b][r];
+    }
+    __syncthreads();
+}
+
+template <int LOGB, int DIR, int PASS, int NS>
+__device__ __forceinline__ void stockham_all(float2 *s, int tid, const float2 *__restrict__ tw)
+{
+    constexpr int R = radix_at(LOGB, PASS);
+    if constexpr (R > 0) {
+        stockham_pass<LOGB, R, DIR, NS>(s, tid, tw);
+        stockham_all<LOGB, DIR, PASS + 1, NS * R>(s, tid, tw);
+    }
+}
+
+// ========================================================================================
+// K1 / K5: batched forward real FFT.
+// transform q -> (channel c = q / nseg, segment i = q % nseg); source = src + c*src_stride + i*B,
+// of which only the first clamp(len - i*B, 0, B) samples are real data (copy_and_pad,
+// src/fft_convolver.rs:70-74); destination row = dst + c*dst_stride + i*B (packed bins).
+// K1 uses nseg = 1, len = fill + n, dst = ring + current*B  (:248-255);
+// K5 uses nseg = S,  len = IR length                         (:145-156, :207-226).
+// ========================================================================================
+template <int LOGB>
+__global__ void __launch_bounds__(FftPlan<LOGB>::CTA)
+k_rfft_forward(const float *__restrict__ src, long long src_stride, int len, float2 *__restrict__ dst,
+               long long dst_stride, int nseg, long long ntransforms, const float2 *__restrict__ tw)
+{
+    using P = FftPlan<LOGB>;
+    constexpr int B = P::B, T = P::T, E = P::E;
+    extern __shared__ float2 smem[];
+    const int slot = threadIdx.x / T, tid = threadIdx.x % T;
+    float2 *s = smem + slot * P::SMEM_PER;
+    const long long q = (long long)blockIdx.x * P::TPB + slot;
+    const bool live = q < ntransforms;
+    const long long c = live ? q / nseg : 0;
+    const int i = live ? (int)(q % nseg) : 0;
+    const float *x = src + c * src_stride + (long long)i * B;
+    int valid = len - i * B;
+    valid = valid < 0 ? 0 : (valid > B ? B : valid);
+    if (!live) valid = 0;
+
+    // z[j] = x'[2j] + i x'[2j+1], x' = [x[0..valid) | zeros]
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        int j = tid + e * T;
+        float2 z = make_float2(0.f, 0.f);
+        if (2 * j < valid) z.x = __ldg(x + 2 * j);
+        if (2 * j + 1 < valid) z.y = __ldg(x + 2 * j + 1);
+        s[sidx(j)] = z;
+    }
+    __syncthreads();
+    stockham_all<LOGB, -1, 0, 1>(s, tid, tw);
+
+    // split: X[k] = Ev + w^k Od, Ev = (Z[k] + conj Z[B-k])/2, Od = (Z[k] - conj Z[B-k])/(2i)
+    if (live) {
+        float2 *row = dst + c * dst_stride + (long long)i * B;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            int k = tid + e * T;
+            float2 a = s[sidx(k)];
+            float2 out;
+            if (k == 0) {
+                out = make_float2(a.x + a.y, a.x - a.y); // {DC.re, Nyquist.re}
+            } else {
+                float2 b = cconj(s[sidx(B - k)]);
+                float2 ev = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
+                float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
+                float2 od = make_float2(d.y, -d.x);
+                float2 w = __ldg(&tw[k]);
+                out = cadd(ev, cmul(od, w));
+            }
+            row[k] = out;
+        }
+    }
+}
+
+// ========================================================================================
+// K3: conv = pre_multiplied + ring[current] * ir[0]  (src/fft_convolver.rs:270-275, unfused
+// f32 like the reference), inverse real FFT, /N (:58-60), overlap-add into the output
+// (:284-288) with the two-stage (:452-468) or crossfade (src/crossfade_convolver.rs:75-77)
+// epilogue, and overlap save on block completion (:297-298).
+// ========================================================================================
+struct IfftArgs {
+    const float2 *ring_cur; // ring + current*B, channel stride ring_stride
+    long long ring_stride;
+    const float2 *ir0;      // IR segment 0, channel stride ir_stride (0 when shared)
+    long long ir_stride;
+    const float2 *premul;   // [C][B]
+    float *overlap;         // [C][B]
+    float *out;             // [C][n], channel stride out_stride
+    long long out_stride;
+    int fill, n, block_complete;
+    long long nchan;
+    fcb_epilogue epi;
+};
+
+template <int LOGB>
+__global__ void __launch_bounds__(FftPlan<LOGB>::CTA)
+k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
+{
+    using P = FftPlan<LOGB>;
+    constexpr int B = P::B, T = P::T, E = P::E;
+    extern __shared__ float2 smem[];
+    const int slot = threadIdx.x / T, tid = threadIdx.x % T;
+    float2 *s = smem + slot * P::SMEM_PER;
+    const long long c = (long long)blockIdx.x * P::TPB + slot;
+    const bool live = c < a.nchan;
+
+    // 1. conv, packed layout (bin 0 = {DC, Nyquist}: two real products)
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        int k = tid + e * T;
+        float2 v = make_float2(0.f, 0.f);
+        if (live) {
+            float2 x = a.ring_cur[c * a.ring_stride + k];
+            float2 h = __ldg(&a.ir0[c * a.ir_stride + k]);
+            float2 p = a.premul[c * B + k];
+            float pr, pi;
+            if (k == 0) {
+                pr = __fmul_rn(x.x, h.x);
+                pi = __fmul_rn(x.y, h.y);
+            } else {
+                pr = __fsub_rn(__fmul_rn(x.x, h.x), __fmul_rn(x.y, h.y));
+                pi = __fadd_rn(__fmul_rn(x.x, h.y), __fmul_rn(x.y, h.x));
+            }
+            v = make_float2(__fadd_rn(p.x, pr), __fadd_rn(p.y, pi));
+        }
+        s[sidx(k)] = v;
+    }
+    __syncthreads();
+
+    // 2. pre-split, in place on pairs (k, B-k):
+    //    Z'[k] = (X[k] + conj X[B-k]) + i w^{-k} (X[k] - conj X[B-k]),  w = exp(-2 pi i / N)
+    {
+        constexpr int HALF = B / 2;
+        constexpr int PAIRS_PER_THREAD = (HALF + T - 1) / T; // pairs p = 0..HALF-1 (p = 0 also does k = B/2)
+#pragma unroll
+        for (int e = 0; e < PAIRS_PER_THREAD; e++) {
+            int k = tid + e * T;
+            if (B == 1) {
+                if (k == 0) {
+                    float2 x = s[0];
+                    s[0] = make_float2(x.x + x.y, x.x - x.y);
+                }
+            } else if (k < HALF) {
+                if (k == 0) {
+                    float2 x = s[0]; // {DC, Nyquist}
+                    s[0] = make_float2(x.x + x.y, x.x - x.y);
+                    float2 m = s[sidx(HALF)];
+                    s[sidx(HALF)] = make_float2(2.f * m.x, -2.f * m.y);
+                } else {
+                    float2 p = s[sidx(k)], q = s[sidx(B - k)];
+                    float2 w = __ldg(&tw[k]);
+                    w.y = -w.y; // w^{-k}
+                    // k:   (p + conj q) + i w^{-k} (p - conj q)
+                    float2 sm = make_float2(p.x + q.x, p.y - q.y);
+                    float2 df = make_float2(p.x - q.x, p.y + q.y);
+                    float2 t = cmul(df, w);
+                    s[sidx(k)] = make_float2(sm.x - t.y, sm.y + t.x);
+                    // B-k: (q + conj p) + i w^{-(B-k)} (q - conj p),  w^{-(B-k)} = -conj(w^{-k})
+                    float2 sm2 = make_float2(sm.x, -sm.y);
+                    float2 df2 = make_float2(-df.x, df.y);
+                    float2 w2 = make_float2(-w.x, w.y);
+                    float2 t2 = cmul(df2, w2);
+                    s[sidx(B - k)] = make_float2(sm2.x - t2.y, sm2.y + t2.x);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // 3. unnormalised inverse complex FFT
+    stockham_all<LOGB, +1, 0, 1>(s, tid, tw);
+
+    // 4. epilogue.  y[2j] = Re z[j] / N, y[2j+1] = Im z[j] / N (N = 2B: exact scaling).
+    const float inv_n = 1.0f / (float)(2 * B);
+    const int lo = a.fill, hi = a.fill + a.n;
+    // 4a. first half -> output (+ overlap, + epilogue)
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        int j = tid + e * T;
+        if (!live || 2 * j >= B) continue;
+        float2 z = s[sidx(j)];
+        float y[2] = {z.x * inv_n, z.y * inv_n};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int m = 2 * j + h;
+            if (m >= lo && m < hi && m < B) {
+                int i = m - lo;
+                float v = __fadd_rn(y[h], a.overlap[c * B + m]);
+                if (a.epi.add0) v = __fadd_rn(v, __ldg(a.epi.add0 + c * (long long)a.epi.add_stride + i));
+                if (a.epi.add1) v = __fadd_rn(v, __ldg(a.epi.add1 + c * (long long)a.epi.add_stride + i));
+                if (a.epi.mix_other) {
+                    float2 g = __ldg(reinterpret_cast<const float2 *>(a.epi.gains) + i);
+                    float o = __ldg(a.epi.mix_other + c * (long long)a.epi.mix_stride + i);
+                    if (g.x == 1.f && g.y == 0.f) {
+                        /* v stays */
+                    } else if (g.x == 0.f && g.y == 1.f) {
+                        v = o;
+                    } else {
+                        v = __fadd_rn(__fmul_rn(v, g.x), __fmul_rn(o, g.y));
+                    }
+                }
+                a.out[c * a.out_stride + i] = v;
+            }
+        }
+    }
+    // 4b. second half -> new overlap, only once every reader of the old overlap is done
+    if (a.block_complete) {
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            int j = tid + e * T;
+            if (!live) continue;
+            if (B == 1) {
+                a.overlap[c] = s[0].y * inv_n; // y[1]
+            } else if (2 * j >= B) {
+                float2 z = s[sidx(j)];
+                *reinterpret_cast<float2 *>(a.overlap + c * B + (2 * j - B)) = make_float2(z.x * inv_n, z.y * inv_n);
+            }
+        }
+    }
+}
+
+} // namespace fcb

@@ -1,0 +1,951 @@
+// host_mirror.cu — layer 2 of the C ABI: a C++ mirror of the reference's three `Convolution`
+// implementors (src/lib.rs:5-14), batched over C lock-step channels.  It keeps exactly what
+// north_star leaves on the host — the block scheduler, the input-buffer fill, the segment-ring
+// rotation (src/fft_convolver.rs:236-245, 291-306), the two-stage bookkeeping (:438-508) and the
+// crossfade state machine (src/crossfade_convolver.rs:51-105, 192-279) — and drives the device
+// stages of engine.cu.  All arithmetic on samples happens in CUDA kernels; there is no CPU path.
+#include <cmath>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace fcb;
+
+// ---- small elementwise kernels for the unfused fall-backs of the K3 epilogues ----------------
+namespace fcb {
+
+// two-stage head/tail sum when a call does not map onto one K3 launch (src/fft_convolver.rs:452-468)
+__global__ void k_add2(float *out, long long out_stride, const float *p0, const float *p1, long long p_stride, int n,
+                       long long nchan)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nchan * n) return;
+    long long c = idx / n;
+    int i = (int)(idx % n);
+    float v = out[c * out_stride + i];
+    v = __fadd_rn(v, p0[c * p_stride + i]);
+    v = __fadd_rn(v, p1[c * p_stride + i]);
+    out[c * out_stride + i] = v;
+}
+
+// crossfade mix when it cannot ride on K3 (src/crossfade_convolver.rs:75-77): gains[i] = {gA, gB}
+__global__ void k_mix(float *out, long long out_stride, const float *a, const float *b, long long ab_stride,
+                      const float2 *gains, int n, long long nchan)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nchan * n) return;
+    long long c = idx / n;
+    int i = (int)(idx % n);
+    float2 g = gains[i];
+    float va = a[c * ab_stride + i], vb = b[c * ab_stride + i], v;
+    if (g.x == 1.f && g.y == 0.f) v = va;
+    else if (g.x == 0.f && g.y == 1.f) v = vb;
+    else v = __fadd_rn(__fmul_rn(va, g.x), __fmul_rn(vb, g.y));
+    out[c * out_stride + i] = v;
+}
+
+static int zero_planar(float *dst, size_t stride, size_t n, size_t C, cudaStream_t s)
+{
+    if (n == 0 || C == 0) return FCB_OK;
+    FCB_CUDA(cudaMemset2DAsync(dst, stride * sizeof(float), 0, n * sizeof(float), C, s));
+    return FCB_OK;
+}
+
+static fcb_options default_options()
+{
+    fcb_options o;
+    memset(&o, 0, sizeof o);
+    return o;
+}
+
+} // namespace fcb
+
+// ==============================================================================================
+// FFTConvolver — src/fft_convolver.rs:100-321
+// ==============================================================================================
+struct fcb_fftconv {
+    fcb_engine *eng = nullptr; // NULL = Default::default() (no segments)
+    size_t C = 0;
+    size_t ir_len = 0, block_size = 0, seg_count = 0, active_seg_count = 0; // :102-105
+    size_t current = 0, input_buffer_fill = 0;                              // :113, :115
+    fcb_options opt{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    float *d_io = nullptr; // device staging for host-pointer process(): [C][B]
+};
+
+static int fftconv_make_stream(fcb_fftconv *c)
+{
+    FCB_CUDA(cudaSetDevice(c->opt.device));
+    if (c->opt.stream) {
+        c->stream = (cudaStream_t)c->opt.stream;
+    } else {
+        FCB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return FCB_OK;
+}
+
+extern "C" int fcb_fftconv_default(fcb_fftconv **out, size_t channels, const fcb_options *opt)
+{
+    if (!out) return fail(FCB_ERR_ARG, "NULL out");
+    fcb_fftconv *c = new fcb_fftconv();
+    c->C = channels;
+    c->opt = opt ? *opt : default_options();
+    int rc = fftconv_make_stream(c);
+    if (rc) {
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return FCB_OK;
+}
+
+extern "C" void fcb_fftconv_free(fcb_fftconv *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->opt.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    fcb_engine_destroy(c->eng);
+    cudaFree(c->d_io);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// :119-186
+extern "C" int fcb_fftconv_init(fcb_fftconv **out, const float *irs, size_t channels, size_t ir_len,
+                                size_t block_size, size_t max_response_length, const fcb_options *opt)
+{
+    if (!out) return fail(FCB_ERR_ARG, "NULL out");
+    *out = nullptr;
+    if (channels == 0) return fail(FCB_ERR_ARG, "channels must be >= 1");
+    if (max_response_length < ir_len) // :120-124
+        return fail(FCB_ERR_PANIC, "max_response_length must be at least the length of the initial impulse response");
+    fcb_fftconv *c = nullptr;
+    FCB_TRY(fcb_fftconv_default(&c, channels, opt));
+    c->ir_len = max_response_length;                 // :125-127
+    c->block_size = next_power_of_two(block_size);   // :129
+    c->seg_count = (size_t)std::ceil((double)c->ir_len / (double)c->block_size); // :131
+    c->active_seg_count = c->seg_count;              // :132
+    fcb_engine_desc d{channels, c->block_size, c->ir_len, c->opt.shared_ir, c->opt.device, (void *)c->stream};
+    int rc = fcb_engine_create(&d, &c->eng);
+    // :145-156 — K5 over the zero-padded IR (rows past ir_len come out as zeros)
+    if (rc == FCB_OK) rc = fcb_engine_set_ir(c->eng, 0, c->opt.shared_ir ? 1 : channels, irs, ir_len, ir_len, 0);
+    if (rc == FCB_OK) {
+        cudaError_t err = cudaMalloc(&c->d_io, channels * c->block_size * sizeof(float));
+        if (err != cudaSuccess) rc = fail(FCB_ERR_CUDA, "cudaMalloc staging failed: %s", cudaGetErrorString(err));
+    }
+    if (rc == FCB_OK) rc = fcb_engine_sync(c->eng);
+    if (rc != FCB_OK) {
+        fcb_fftconv_free(c);
+        return rc;
+    }
+    *out = c;
+    return FCB_OK;
+}
+
+// #[derive(Clone)] :100
+extern "C" int fcb_fftconv_clone(const fcb_fftconv *s, fcb_fftconv **out)
+{
+    if (!s || !out) return fail(FCB_ERR_ARG, "NULL argument");
+    fcb_fftconv *c = nullptr;
+    FCB_TRY(fcb_fftconv_default(&c, s->C, &s->opt));
+    c->ir_len = s->ir_len;
+    c->block_size = s->block_size;
+    c->seg_count = s->seg_count;
+    c->active_seg_count = s->active_seg_count;
+    c->current = s->current;
+    c->input_buffer_fill = s->input_buffer_fill;
+    int rc = FCB_OK;
+    if (s->eng) {
+        rc = fcb_engine_clone(s->eng, &c->eng);
+        if (rc == FCB_OK) rc = fcb_engine_set_stream(c->eng, (void *)c->stream);
+        if (rc == FCB_OK) {
+            cudaError_t err = cudaMalloc(&c->d_io, c->C * c->block_size * sizeof(float));
+            if (err != cudaSuccess) rc = fail(FCB_ERR_CUDA, "cudaMalloc staging failed: %s", cudaGetErrorString(err));
+        }
+    }
+    if (rc != FCB_OK) {
+        fcb_fftconv_free(c);
+        return rc;
+    }
+    *out = c;
+    return FCB_OK;
+}
+
+// :188-227
+extern "C" int fcb_fftconv_update(fcb_fftconv *c, const float *irs, size_t new_ir_len)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    if (new_ir_len > c->ir_len) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
+    if (c->ir_len == 0) return FCB_OK; // :195-197
+    c->active_seg_count = (size_t)std::ceil((double)new_ir_len / (double)c->block_size); // :204
+    return fcb_engine_set_ir(c->eng, 0, c->opt.shared_ir ? 1 : c->C, irs, new_ir_len, new_ir_len, 1);
+}
+
+// :310-320
+extern "C" int fcb_fftconv_reset(fcb_fftconv *c)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    c->current = 0;
+    c->input_buffer_fill = 0;
+    return c->eng ? fcb_engine_reset(c->eng) : FCB_OK;
+}
+
+static fcb_epilogue offset_epilogue(const fcb_epilogue *epi, size_t off)
+{
+    fcb_epilogue e;
+    memset(&e, 0, sizeof e);
+    if (!epi) return e;
+    e = *epi;
+    if (e.add0) e.add0 += off;
+    if (e.add1) e.add1 += off;
+    if (e.mix_other) {
+        e.mix_other += off;
+        e.gains += 2 * off;
+    }
+    return e;
+}
+
+// the block scheduler of :236-308; `host_in`/`host_out` select the H2D/D2H flavour of each chunk
+static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in_stride, float *out, size_t out_len,
+                       size_t out_stride, const fcb_epilogue *epi, bool host)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    if (out_len && !out) return fail(FCB_ERR_ARG, "NULL output");
+    FCB_CUDA(cudaSetDevice(c->opt.device));
+    if (c->active_seg_count == 0) { // :230-233
+        if (host) {
+            for (size_t ch = 0; ch < c->C; ch++) memset(out + ch * out_stride, 0, out_len * sizeof(float));
+            return FCB_OK;
+        }
+        return zero_planar(out, out_stride, out_len, c->C, c->stream);
+    }
+    if (in_len < out_len) return fail(FCB_ERR_PANIC, "range end index %zu out of range for slice of length %zu", out_len, in_len);
+    if (out_len && !in) return fail(FCB_ERR_ARG, "NULL input");
+    const size_t B = c->block_size;
+    size_t processed = 0;
+    while (processed < out_len) { // :236
+        const bool was_empty = c->input_buffer_fill == 0; // :237
+        size_t n = out_len - processed;                   // :238-241
+        if (B - c->input_buffer_fill < n) n = B - c->input_buffer_fill;
+        const size_t pos = c->input_buffer_fill;
+        const bool complete = pos + n == B;
+        fcb_epilogue e = offset_epilogue(epi, processed);
+        float *dst = host ? c->d_io : out + processed;
+        const size_t dst_stride = host ? B : out_stride;
+        if (!host && was_empty && complete) {
+            // whole block resident on the device: K1 reads the caller's buffer directly
+            FCB_TRY(fcb_engine_process_block_dev(c->eng, in + processed, in_stride, dst, dst_stride, c->current,
+                                                 c->active_seg_count, &e));
+        } else {
+            if (host) FCB_TRY(fcb_engine_push_input(c->eng, in + processed, in_stride, pos, n)); // :243-245
+            else FCB_TRY(fcb_engine_push_input_dev(c->eng, in + processed, in_stride, pos, n));
+            FCB_TRY(fcb_engine_fft_forward(c->eng, c->current, pos + n));                        // :248-255
+            if (was_empty) FCB_TRY(fcb_engine_mac(c->eng, c->current, c->active_seg_count));     // :258-269
+            FCB_TRY(fcb_engine_ifft_ola(c->eng, c->current, pos, n, complete, dst, dst_stride, &e)); // :270-288
+        }
+        if (host)
+            FCB_CUDA(cudaMemcpy2DAsync(out + processed, out_stride * sizeof(float), c->d_io, B * sizeof(float),
+                                       n * sizeof(float), c->C, cudaMemcpyDeviceToHost, c->stream));
+        c->input_buffer_fill += n; // :291-306
+        if (c->input_buffer_fill == B) {
+            c->input_buffer_fill = 0;
+            c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1;
+        }
+        processed += n;
+    }
+    if (host) FCB_CUDA(cudaStreamSynchronize(c->stream));
+    return FCB_OK;
+}
+
+extern "C" int fcb_fftconv_process(fcb_fftconv *c, const float *in, size_t in_len, size_t in_stride, float *out,
+                                   size_t out_len, size_t out_stride)
+{
+    return fftconv_run(c, in, in_len, in_stride, out, out_len, out_stride, nullptr, true);
+}
+extern "C" int fcb_fftconv_process_dev(fcb_fftconv *c, const float *in, size_t in_len, size_t in_stride, float *out,
+                                       size_t out_len, size_t out_stride, const fcb_epilogue *epi)
+{
+    return fftconv_run(c, in, in_len, in_stride, out, out_len, out_stride, epi, false);
+}
+extern "C" int fcb_fftconv_sync(fcb_fftconv *c)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    FCB_CUDA(cudaSetDevice(c->opt.device));
+    FCB_CUDA(cudaStreamSynchronize(c->stream));
+    return FCB_OK;
+}
+extern "C" fcb_engine *fcb_fftconv_engine(fcb_fftconv *c) { return c ? c->eng : nullptr; }
+extern "C" size_t fcb_fftconv_block_size(const fcb_fftconv *c) { return c->block_size; }
+extern "C" size_t fcb_fftconv_seg_count(const fcb_fftconv *c) { return c->seg_count; }
+extern "C" size_t fcb_fftconv_active_seg_count(const fcb_fftconv *c) { return c->active_seg_count; }
+extern "C" size_t fcb_fftconv_current(const fcb_fftconv *c) { return c->current; }
+extern "C" size_t fcb_fftconv_fill(const fcb_fftconv *c) { return c->input_buffer_fill; }
+
+// ==============================================================================================
+// TwoStageFFTConvolver — src/fft_convolver.rs:337-540
+// ==============================================================================================
+// :528-540, f32 arithmetic throughout
+extern "C" size_t fcb_compute_tail_block_size(size_t head_len, size_t response_len)
+{
+    const float FFT_K = 1.5f;
+    volatile float kn = (FFT_K * (float)head_len) / (2.0f * logf(2.0f));
+    volatile float prod = (float)response_len * (float)head_len;
+    volatile float sq = kn * kn;
+    volatile float sum = sq + prod;
+    float b = -kn + sqrtf(sum);
+    b = fmaxf(b, (float)head_len);
+    return next_power_of_two((size_t)b);
+}
+
+struct fcb_twostage {
+    size_t C = 0, head_block_size = 0, tail_block_size = 0; // :339-340
+    fcb_fftconv *head = nullptr, *tail0 = nullptr, *tail = nullptr;
+    // device [C][T] each (:343-348); tail_in is double-buffered for the asynchronous tail
+    float *tail_output0 = nullptr, *tail_precalculated0 = nullptr, *tail_output = nullptr,
+          *tail_precalculated = nullptr, *tail_input[2] = {nullptr, nullptr};
+    int tail_in_sel = 0;
+    size_t tail_input_fill = 0, precalculated_pos = 0; // :349-350
+    fcb_options opt{};
+    cudaStream_t stream = nullptr, tail_stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev_in = nullptr, ev_tail_done = nullptr;
+    bool tail_pending = false;
+    float *d_in = nullptr, *d_out = nullptr; // host-call staging [C][head_block_size]
+};
+
+extern "C" void fcb_twostage_free(fcb_twostage *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->opt.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
+    fcb_fftconv_free(c->head);
+    fcb_fftconv_free(c->tail0);
+    fcb_fftconv_free(c->tail);
+    cudaFree(c->tail_output0);
+    cudaFree(c->tail_precalculated0);
+    cudaFree(c->tail_output);
+    cudaFree(c->tail_precalculated);
+    cudaFree(c->tail_input[0]);
+    cudaFree(c->tail_input[1]);
+    cudaFree(c->d_in);
+    cudaFree(c->d_out);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev_tail_done) cudaEventDestroy(c->ev_tail_done);
+    if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int twostage_alloc(fcb_twostage *c)
+{
+    const size_t bytes = c->C * c->tail_block_size * sizeof(float);
+    float **bufs[] = {&c->tail_output0, &c->tail_precalculated0, &c->tail_output, &c->tail_precalculated,
+                      &c->tail_input[0], &c->tail_input[1]};
+    for (float **b : bufs) {
+        FCB_CUDA(cudaMalloc(b, bytes ? bytes : 16));
+        FCB_CUDA(cudaMemsetAsync(*b, 0, bytes ? bytes : 16, c->stream));
+    }
+    const size_t io = c->C * (c->head_block_size ? c->head_block_size : 1) * sizeof(float);
+    FCB_CUDA(cudaMalloc(&c->d_in, io));
+    FCB_CUDA(cudaMalloc(&c->d_out, io));
+    FCB_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+    FCB_CUDA(cudaEventCreateWithFlags(&c->ev_tail_done, cudaEventDisableTiming));
+    return FCB_OK;
+}
+
+static int twostage_shell(fcb_twostage **out, size_t channels, const fcb_options *opt)
+{
+    fcb_twostage *c = new fcb_twostage();
+    c->C = channels;
+    c->opt = opt ? *opt : default_options();
+    cudaError_t err = cudaSetDevice(c->opt.device);
+    if (err == cudaSuccess) {
+        if (c->opt.stream) c->stream = (cudaStream_t)c->opt.stream;
+        else {
+            err = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+            c->own_stream = err == cudaSuccess;
+        }
+    }
+    if (err == cudaSuccess && c->opt.async_tail) err = cudaStreamCreateWithFlags(&c->tail_stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) {
+        delete c;
+        return fail(FCB_ERR_CUDA, "two-stage stream setup failed: %s", cudaGetErrorString(err));
+    }
+    *out = c;
+    return FCB_OK;
+}
+
+// :354-420
+extern "C" int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t channels, size_t ir_len,
+                                 size_t block_size, size_t max_response_length, const fcb_options *opt)
+{
+    if (!out) return fail(FCB_ERR_ARG, "NULL out");
+    *out = nullptr;
+    if (channels == 0) return fail(FCB_ERR_ARG, "channels must be >= 1");
+    fcb_options o = opt ? *opt : default_options();
+    o.shared_ir = 0;
+    const size_t head = block_size; // :355 (kept unrounded for the bookkeeping)
+    const size_t T = o.forced_tail_block ? o.forced_tail_block : fcb_compute_tail_block_size(block_size, max_response_length);
+    if (max_response_length < ir_len) // :358-362
+        return fail(FCB_ERR_PANIC, "max_response_length must be at least the length of the initial impulse response");
+    if (head == 0) return fail(FCB_ERR_PANIC, "attempt to calculate the remainder with a divisor of zero"); // :445
+    const size_t L = max_response_length;
+    // padded_ir (:363-364), channel-major
+    std::vector<float> padded(channels * (L ? L : 1), 0.f);
+    for (size_t ch = 0; ch < channels; ch++)
+        if (ir_len) memcpy(&padded[ch * L], irs + ch * ir_len, ir_len * sizeof(float));
+
+    fcb_twostage *c = nullptr;
+    FCB_TRY(twostage_shell(&c, channels, &o));
+    c->head_block_size = head;
+    c->tail_block_size = T;
+    fcb_options sub = o;
+    sub.stream = (void *)c->stream;
+    int rc = FCB_OK;
+    auto gather = [&](size_t off, size_t len) { // [C][len] slice of padded
+        std::vector<float> v(channels * (len ? len : 1));
+        for (size_t ch = 0; ch < channels; ch++) memcpy(&v[ch * len], &padded[ch * L + off], len * sizeof(float));
+        return v;
+    };
+    {
+        const size_t head_ir_len = L < T ? L : T; // :366-368
+        auto v = gather(0, head_ir_len);
+        rc = fcb_fftconv_init(&c->head, v.data(), channels, head_ir_len, head, head_ir_len, &sub);
+    }
+    if (rc == FCB_OK) {
+        if (L > T) { // :370-382
+            const size_t tl = (L - T) < T ? (L - T) : T;
+            auto v = gather(T, tl);
+            rc = fcb_fftconv_init(&c->tail0, v.data(), channels, tl, head, tl, &sub);
+        } else {
+            rc = fcb_fftconv_default(&c->tail0, channels, &sub);
+        }
+    }
+    if (rc == FCB_OK) {
+        fcb_options tsub = sub;
+        if (c->tail_stream) tsub.stream = (void *)c->tail_stream;
+        if (L > 2 * T) { // :387-398
+            const size_t tl = L - 2 * T;
+            auto v = gather(2 * T, tl);
+            rc = fcb_fftconv_init(&c->tail, v.data(), channels, tl, T, tl, &tsub);
+        } else {
+            rc = fcb_fftconv_default(&c->tail, channels, &tsub);
+        }
+    }
+    if (rc == FCB_OK) rc = twostage_alloc(c);
+    if (rc == FCB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(FCB_ERR_CUDA, "sync failed");
+    if (rc != FCB_OK) {
+        fcb_twostage_free(c);
+        return rc;
+    }
+    *out = c;
+    return FCB_OK;
+}
+
+static int twostage_quiesce(const fcb_twostage *c)
+{
+    FCB_CUDA(cudaSetDevice(c->opt.device));
+    FCB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->tail_stream) FCB_CUDA(cudaStreamSynchronize(c->tail_stream));
+    return FCB_OK;
+}
+
+extern "C" int fcb_twostage_clone(const fcb_twostage *s, fcb_twostage **out)
+{
+    if (!s || !out) return fail(FCB_ERR_ARG, "NULL argument");
+    FCB_TRY(twostage_quiesce(s));
+    fcb_twostage *c = nullptr;
+    FCB_TRY(twostage_shell(&c, s->C, &s->opt));
+    c->head_block_size = s->head_block_size;
+    c->tail_block_size = s->tail_block_size;
+    c->tail_input_fill = s->tail_input_fill;
+    c->precalculated_pos = s->precalculated_pos;
+    c->tail_in_sel = s->tail_in_sel;
+    int rc = fcb_fftconv_clone(s->head, &c->head);
+    if (rc == FCB_OK) rc = fcb_fftconv_clone(s->tail0, &c->tail0);
+    if (rc == FCB_OK) rc = fcb_fftconv_clone(s->tail, &c->tail);
+    if (rc == FCB_OK) rc = twostage_alloc(c);
+    if (rc == FCB_OK) {
+        // the clones carry their own private streams; re-home them onto this object's streams
+        for (fcb_fftconv *f : {c->head, c->tail0}) {
+            if (f->eng) rc = rc ? rc : fcb_engine_set_stream(f->eng, (void *)c->stream);
+            if (f->own_stream) cudaStreamDestroy(f->stream);
+            f->own_stream = false;
+            f->stream = c->stream;
+            f->opt.stream = (void *)c->stream;
+        }
+        cudaStream_t ts = c->tail_stream ? c->tail_stream : c->stream;
+        if (c->tail->eng) rc = rc ? rc : fcb_engine_set_stream(c->tail->eng, (void *)ts);
+        if (c->tail->own_stream) cudaStreamDestroy(c->tail->stream);
+        c->tail->own_stream = false;
+        c->tail->stream = ts;
+        c->tail->opt.stream = (void *)ts;
+    }
+    if (rc == FCB_OK) {
+        const size_t bytes = s->C * s->tail_block_size * sizeof(float);
+        const float *src[] = {s->tail_output0, s->tail_precalculated0, s->tail_output, s->tail_precalculated,
+                              s->tail_input[0], s->tail_input[1]};
+        float *dst[] = {c->tail_output0, c->tail_precalculated0, c->tail_output, c->tail_precalculated,
+                        c->tail_input[0], c->tail_input[1]};
+        for (int i = 0; i < 6 && rc == FCB_OK; i++)
+            if (bytes && cudaMemcpyAsync(dst[i], src[i], bytes, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess)
+                rc = fail(FCB_ERR_CUDA, "two-stage clone copy failed");
+        if (rc == FCB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(FCB_ERR_CUDA, "sync failed");
+    }
+    if (rc != FCB_OK) {
+        fcb_twostage_free(c);
+        return rc;
+    }
+    *out = c;
+    return FCB_OK;
+}
+
+// :422-424
+extern "C" int fcb_twostage_update(fcb_twostage *c, const float *irs, size_t ir_len)
+{
+    (void)c; (void)irs; (void)ir_len;
+    return fail(FCB_ERR_TODO, "not yet implemented");
+}
+
+// :511-525
+extern "C" int fcb_twostage_reset(fcb_twostage *c)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    FCB_TRY(twostage_quiesce(c));
+    c->tail_pending = false;
+    FCB_TRY(fcb_fftconv_reset(c->head));
+    FCB_TRY(fcb_fftconv_reset(c->tail0));
+    FCB_TRY(fcb_fftconv_reset(c->tail));
+    const size_t bytes = c->C * c->tail_block_size * sizeof(float);
+    float *bufs[] = {c->tail_output0, c->tail_precalculated0, c->tail_output, c->tail_precalculated,
+                     c->tail_input[0], c->tail_input[1]};
+    for (float *b : bufs)
+        if (bytes) FCB_CUDA(cudaMemsetAsync(b, 0, bytes, c->stream));
+    c->tail_input_fill = 0;
+    c->precalculated_pos = 0;
+    return twostage_quiesce(c);
+}
+
+// :426-509 on device buffers
+extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t in_len, size_t in_stride, float *out,
+                                        size_t out_len, size_t out_stride)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    if (!(in_len <= c->head_block_size)) // assert! :428
+        return fail(FCB_ERR_PANIC, "assertion failed: input.len() <= self.head_block_size");
+    // head.process slices input[..output.len()], the tail loop indexes output[..input.len()]
+    if (in_len != out_len) return fail(FCB_ERR_PANIC, "index out of bounds: input and output lengths differ");
+    FCB_CUDA(cudaSetDevice(c->opt.device));
+    const size_t H = c->head_block_size, T = c->tail_block_size, C = c->C;
+
+    // Can the head/tail sum (:452-468) ride on the head's K3 launch?  Only when this call is one
+    // tail piece and one head chunk; otherwise the sum runs as a separate elementwise kernel.
+    const bool one_piece = in_len <= H - (c->tail_input_fill % H);
+    const bool one_chunk = c->head->active_seg_count == 0 ? false
+                                                          : in_len <= c->head->block_size - c->head->input_buffer_fill;
+    const bool fuse = T != 0 && in_len > 0 && one_piece && one_chunk;
+    fcb_epilogue epi;
+    memset(&epi, 0, sizeof epi);
+    if (fuse) {
+        epi.add0 = c->tail_precalculated0 + c->precalculated_pos;
+        epi.add1 = c->tail_precalculated + c->precalculated_pos;
+        epi.add_stride = T;
+    }
+    FCB_TRY(fcb_fftconv_process_dev(c->head, in, in_len, in_stride, out, out_len, out_stride, fuse ? &epi : nullptr)); // :431
+    if (T == 0) return FCB_OK; // :434-436
+
+    size_t processed = 0;
+    while (processed < in_len) { // :441
+        const size_t remaining = in_len - processed;
+        size_t n = H - (c->tail_input_fill % H); // :443-446
+        if (remaining < n) n = remaining;
+        if (!fuse) { // :452-468
+            long long total = (long long)C * (long long)n;
+            k_add2<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
+                out + processed, (long long)out_stride, c->tail_precalculated0 + c->precalculated_pos,
+                c->tail_precalculated + c->precalculated_pos, (long long)T, (int)n, (long long)C);
+            g_launches++;
+            FCB_CUDA(cudaGetLastError());
+        }
+        c->precalculated_pos += n; // :470
+        float *tin = c->tail_input[c->tail_in_sel];
+        FCB_CUDA(cudaMemcpy2DAsync(tin + c->tail_input_fill, T * sizeof(float), in + processed, in_stride * sizeof(float),
+                                   n * sizeof(float), C, cudaMemcpyDeviceToDevice, c->stream)); // :473-475
+        c->tail_input_fill += n;
+
+        if (c->tail_input_fill % H == 0) { // :478-490
+            const size_t off = c->tail_input_fill - H;
+            FCB_TRY(fcb_fftconv_process_dev(c->tail0, tin + off, H, T, c->tail_output0 + off, H, T, nullptr));
+            if (c->tail_input_fill == T) std::swap(c->tail_precalculated0, c->tail_output0);
+        }
+        if (c->tail_input_fill == T) { // :493-500
+            if (c->tail_stream) {
+                // the previous background tail must have produced tail_output before it becomes
+                // tail_precalculated, and must be done before we hand it new buffers
+                if (c->tail_pending) FCB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tail_done, 0));
+                std::swap(c->tail_precalculated, c->tail_output);
+                FCB_CUDA(cudaEventRecord(c->ev_in, c->stream));
+                FCB_CUDA(cudaStreamWaitEvent(c->tail_stream, c->ev_in, 0));
+                FCB_TRY(fcb_fftconv_process_dev(c->tail, tin, T, T, c->tail_output, T, T, nullptr));
+                FCB_CUDA(cudaEventRecord(c->ev_tail_done, c->tail_stream));
+                c->tail_pending = true;
+                c->tail_in_sel ^= 1; // the tail stream may still be reading `tin`
+            } else {
+                std::swap(c->tail_precalculated, c->tail_output);
+                FCB_TRY(fcb_fftconv_process_dev(c->tail, tin, T, T, c->tail_output, T, T, nullptr));
+            }
+        }
+        if (c->tail_input_fill == T) { // :502-505
+            c->tail_input_fill = 0;
+            c->precalculated_pos = 0;
+        }
+        processed += n;
+    }
+    return FCB_OK;
+}
+
+extern "C" int fcb_twostage_process(fcb_twostage *c, const float *in, size_t in_len, size_t in_stride, float *out,
+                                    size_t out_len, size_t out_stride)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    if (!(in_len <= c->head_block_size)) return fail(FCB_ERR_PANIC, "assertion failed: input.len() <= self.head_block_size");
+    if (in_len != out_len) return fail(FCB_ERR_PANIC, "index out of bounds: input and output lengths differ");
+    if (in_len == 0) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(c->opt.device));
+    FCB_CUDA(cudaMemcpy2DAsync(c->d_in, in_len * sizeof(float), in, in_stride * sizeof(float), in_len * sizeof(float),
+                               c->C, cudaMemcpyHostToDevice, c->stream));
+    FCB_TRY(fcb_twostage_process_dev(c, c->d_in, in_len, in_len, c->d_out, out_len, out_len));
+    FCB_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float), c->d_out, out_len * sizeof(float),
+                               out_len * sizeof(float), c->C, cudaMemcpyDeviceToHost, c->stream));
+    FCB_CUDA(cudaStreamSynchronize(c->stream));
+    return FCB_OK;
+}
+
+extern "C" int fcb_twostage_sync(fcb_twostage *c)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    return twostage_quiesce(c);
+}
+extern "C" size_t fcb_twostage_tail_block_size(const fcb_twostage *c) { return c->tail_block_size; }
+
+// ==============================================================================================
+// Crossfader<RaisedCosineMixer> — src/crossfade_convolver.rs:160-279, run on the host one sample
+// at a time exactly like the reference (sequential f32 accumulation of mix_value); it
+// emits the per-sample gain pair that K3 / k_mix apply.
+// ==============================================================================================
+namespace {
+struct Crossfader {
+    int64_t fading_samples = 0, hold_samples = 0, counter = 0; // :195-197
+    float mix_value_step = 0.f, mix_value = 0.f;               // :198-199
+    bool approaching = false;                                   // FadingState :178-181
+    int target = 0;                                             // Target::A = 0, B = 1
+
+    void init(size_t fading, size_t hold) // :204-214
+    {
+        fading_samples = (int64_t)fading;
+        hold_samples = (int64_t)hold;
+        counter = 0;
+        mix_value_step = 1.0f / (float)fading;
+        mix_value = 0.f;
+        approaching = false;
+        target = 0;
+    }
+    void fade_into(int t) // :216-240
+    {
+        if (target == t) return;
+        if (!approaching) {
+            counter = -hold_samples;
+            approaching = true;
+            target = t;
+            mix_value_step = -mix_value_step;
+        } else if (counter >= 0) {
+            counter = fading_samples - counter;
+            target = t;
+            mix_value_step = -mix_value_step;
+        } else {
+            approaching = false;
+            target = t;
+        }
+    }
+    // :242-278 with the sample values factored out: returns {gain on a, gain on b}
+    float2 next_gains()
+    {
+        const float2 take_a = make_float2(1.f, 0.f), take_b = make_float2(0.f, 1.f);
+        if (!approaching) return target == 0 ? take_a : take_b;
+        counter += 1;
+        if (counter <= 0) return target == 0 ? take_b : take_a; // holding the previous target
+        volatile float mv = mix_value + mix_value_step;         // plain f32 add, never widened
+        mix_value = mv;
+        if (counter == fading_samples) {
+            approaching = false;
+            mix_value = target == 0 ? 0.f : 1.f;
+            return target == 0 ? take_a : take_b;
+        }
+        // RaisedCosineMixer :160-169
+        const float PI_HALF = 3.14159265358979323846f * 0.5f; // :147
+        volatile float rad = PI_HALF * mix_value;
+        float cs = cosf(rad);
+        volatile float gain1 = cs * cs; // powi(2)
+        volatile float gain2 = 1.0f - gain1;
+        return make_float2(gain1, gain2);
+    }
+};
+} // namespace
+
+// ==============================================================================================
+// CrossfadeConvolver<FFTConvolver> — src/crossfade_convolver.rs:3-105
+// ==============================================================================================
+struct fcb_crossfade {
+    fcb_fftconv *a = nullptr, *b = nullptr; // convolver_a / convolver_b :5-6
+    Crossfader crossfader;                  // :7
+    size_t C = 0, max_buffer_size = 0;
+    float *buffer_a = nullptr, *buffer_b = nullptr; // device [C][max_buffer_size] :13-14
+    std::vector<float> stored_response;             // [C][stored_len] :15
+    size_t stored_len = 0;
+    bool response_pending = false;                  // :16
+    cudaStream_t stream = nullptr;
+    int device = 0;
+    float2 *h_gains = nullptr, *d_gains = nullptr;  // pinned / device, max_buffer_size each
+    cudaEvent_t ev_gains = nullptr;
+    float *d_in = nullptr, *d_out = nullptr;        // host-call staging
+    size_t d_in_cap = 0;
+};
+
+extern "C" void fcb_crossfade_free(fcb_crossfade *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->buffer_a);
+    cudaFree(c->buffer_b);
+    cudaFree(c->d_gains);
+    cudaFree(c->d_in);
+    cudaFree(c->d_out);
+    if (c->h_gains) cudaFreeHost(c->h_gains);
+    if (c->ev_gains) cudaEventDestroy(c->ev_gains);
+    fcb_fftconv_free(c->a); // b owns the shared stream when it is private, so free it last
+    fcb_fftconv_free(c->b);
+    delete c;
+}
+
+// :19-43
+extern "C" int fcb_crossfade_new(fcb_crossfade **out, fcb_fftconv *convolver, size_t max_response_length,
+                                 size_t max_buffer_size, size_t crossfade_samples)
+{
+    if (!out || !convolver) return fail(FCB_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    fcb_crossfade *c = new fcb_crossfade();
+    c->C = convolver->C;
+    c->device = convolver->opt.device;
+    c->stream = convolver->stream;
+    c->b = convolver; // :30
+    c->max_buffer_size = max_buffer_size;
+    c->stored_len = max_response_length;
+    c->stored_response.assign(c->C * (max_response_length ? max_response_length : 1), 0.f); // :26
+    c->crossfader.init(crossfade_samples, max_buffer_size < max_response_length ? max_buffer_size : max_response_length); // :31-35
+    int rc = FCB_OK;
+    {
+        // convolver_a = convolver.clone() (:29), sharing b's stream so A, B and the mix stay ordered
+        fcb_options o = convolver->opt;
+        o.stream = (void *)convolver->stream;
+        fcb_fftconv tmp = *convolver;
+        tmp.opt = o;
+        rc = fcb_fftconv_clone(&tmp, &c->a);
+    }
+    const size_t n = max_buffer_size ? max_buffer_size : 1;
+    auto cu = [&](cudaError_t e) {
+        if (rc == FCB_OK && e != cudaSuccess) rc = fail(FCB_ERR_CUDA, "crossfade setup failed: %s", cudaGetErrorString(e));
+    };
+    cu(cudaSetDevice(c->device));
+    cu(cudaMalloc(&c->buffer_a, c->C * n * sizeof(float)));
+    cu(cudaMalloc(&c->buffer_b, c->C * n * sizeof(float)));
+    cu(cudaMalloc(&c->d_gains, n * sizeof(float2)));
+    cu(cudaHostAlloc(&c->h_gains, n * sizeof(float2), cudaHostAllocDefault));
+    cu(cudaMalloc(&c->d_out, c->C * n * sizeof(float)));
+    cu(cudaEventCreateWithFlags(&c->ev_gains, cudaEventDisableTiming));
+    if (rc == FCB_OK) {
+        cu(cudaMemsetAsync(c->buffer_a, 0, c->C * n * sizeof(float), c->stream));
+        cu(cudaMemsetAsync(c->buffer_b, 0, c->C * n * sizeof(float), c->stream));
+        cu(cudaEventRecord(c->ev_gains, c->stream));
+        cu(cudaStreamSynchronize(c->stream));
+    }
+    if (rc != FCB_OK) {
+        c->b = nullptr; // ownership stays with the caller on failure
+        fcb_crossfade_free(c);
+        return rc;
+    }
+    *out = c;
+    return FCB_OK;
+}
+
+// :46-49 — response.len() is passed for both the stored capacity and crossfade_samples
+extern "C" int fcb_crossfade_init(fcb_crossfade **out, const float *irs, size_t channels, size_t ir_len,
+                                  size_t max_block_size, size_t max_response_length, const fcb_options *opt)
+{
+    if (!out) return fail(FCB_ERR_ARG, "NULL out");
+    fcb_options o = opt ? *opt : default_options();
+    o.shared_ir = 0;
+    fcb_fftconv *conv = nullptr;
+    FCB_TRY(fcb_fftconv_init(&conv, irs, channels, ir_len, max_block_size, max_response_length, &o));
+    int rc = fcb_crossfade_new(out, conv, ir_len, max_block_size, ir_len);
+    if (rc != FCB_OK) fcb_fftconv_free(conv);
+    return rc;
+}
+
+extern "C" int fcb_crossfade_is_crossfading(const fcb_crossfade *c) { return c && c->crossfader.approaching; } // :85-92
+
+// :94-105
+static int crossfade_swap(fcb_crossfade *c, const float *irs, size_t len)
+{
+    int rc;
+    if (c->crossfader.target == 0) {
+        rc = fcb_fftconv_update(c->b, irs, len);
+        c->crossfader.fade_into(1);
+    } else {
+        rc = fcb_fftconv_update(c->a, irs, len);
+        c->crossfader.fade_into(0);
+    }
+    return rc;
+}
+
+// :51-64
+extern "C" int fcb_crossfade_update(fcb_crossfade *c, const float *irs, size_t len)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    if (!fcb_crossfade_is_crossfading(c)) {
+        int rc = crossfade_swap(c, irs, len);
+        c->response_pending = false;
+        return rc;
+    }
+    if (!(len <= c->stored_len)) return fail(FCB_ERR_PANIC, "assertion failed: response_len <= self.stored_response.len()");
+    for (size_t ch = 0; ch < c->C; ch++) {
+        float *dst = &c->stored_response[ch * c->stored_len];
+        memcpy(dst, irs + ch * len, len * sizeof(float));
+        memset(dst + len, 0, (c->stored_len - len) * sizeof(float));
+    }
+    c->response_pending = true;
+    return FCB_OK;
+}
+
+// :66-78 on device buffers
+extern "C" int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in, size_t in_len, size_t in_stride, float *out,
+                                         size_t out_len, size_t out_stride)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    FCB_CUDA(cudaSetDevice(c->device));
+    if (!fcb_crossfade_is_crossfading(c) && c->response_pending) { // :67-70
+        FCB_TRY(crossfade_swap(c, c->stored_response.data(), c->stored_len));
+        c->response_pending = false;
+    }
+    const size_t M = c->max_buffer_size;
+    if (out_len > M) return fail(FCB_ERR_PANIC, "index out of bounds: the len is %zu but the index is %zu", M, M); // :76
+
+    // gains for this call, by the reference's per-sample state machine (:75-77 -> :242-278)
+    FCB_CUDA(cudaEventSynchronize(c->ev_gains)); // previous upload has left the pinned buffer
+    bool all_a = true, all_b = true;
+    for (size_t i = 0; i < out_len; i++) {
+        float2 g = c->crossfader.next_gains();
+        c->h_gains[i] = g;
+        all_a = all_a && g.x == 1.f && g.y == 0.f;
+        all_b = all_b && g.x == 0.f && g.y == 1.f;
+    }
+
+    // both convolvers always run, each on max_buffer_size samples (:72-73); A and B are independent,
+    // so the one whose result is needed last may write straight into `out`
+    auto run = [&](fcb_fftconv *f, float *dst, size_t dst_stride, const fcb_epilogue *epi) {
+        return fcb_fftconv_process_dev(f, in, in_len, in_stride, dst, M, dst_stride, epi);
+    };
+    const bool whole = out_len == M && M > 0; // the mix can ride on the second convolver's K3
+    if (whole && all_a) {
+        FCB_TRY(run(c->b, c->buffer_b, M, nullptr));
+        return run(c->a, out, out_stride, nullptr);
+    }
+    if (whole && all_b) {
+        FCB_TRY(run(c->a, c->buffer_a, M, nullptr));
+        return run(c->b, out, out_stride, nullptr);
+    }
+    FCB_TRY(run(c->a, c->buffer_a, M, nullptr));
+    if (whole && c->b->active_seg_count != 0) {
+        // gain ramp fused into convolver B's K3: mine = B, other = A  =>  gains {gB, gA}
+        for (size_t i = 0; i < out_len; i++) c->h_gains[i] = make_float2(c->h_gains[i].y, c->h_gains[i].x);
+        FCB_CUDA(cudaMemcpyAsync(c->d_gains, c->h_gains, out_len * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+        FCB_CUDA(cudaEventRecord(c->ev_gains, c->stream));
+        fcb_epilogue epi;
+        memset(&epi, 0, sizeof epi);
+        epi.mix_other = c->buffer_a;
+        epi.mix_stride = M;
+        epi.gains = reinterpret_cast<const float *>(c->d_gains);
+        return run(c->b, out, out_stride, &epi);
+    }
+    FCB_TRY(run(c->b, c->buffer_b, M, nullptr));
+    if (out_len == 0) return FCB_OK;
+    if (all_a || all_b) {
+        FCB_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float), all_a ? c->buffer_a : c->buffer_b, M * sizeof(float),
+                                   out_len * sizeof(float), c->C, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        FCB_CUDA(cudaMemcpyAsync(c->d_gains, c->h_gains, out_len * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+        FCB_CUDA(cudaEventRecord(c->ev_gains, c->stream));
+        long long total = (long long)c->C * (long long)out_len;
+        k_mix<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(out, (long long)out_stride, c->buffer_a, c->buffer_b,
+                                                                     (long long)M, c->d_gains, (int)out_len,
+                                                                     (long long)c->C);
+        g_launches++;
+        FCB_CUDA(cudaGetLastError());
+    }
+    return FCB_OK;
+}
+
+extern "C" int fcb_crossfade_process(fcb_crossfade *c, const float *in, size_t in_len, size_t in_stride, float *out,
+                                     size_t out_len, size_t out_stride)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    FCB_CUDA(cudaSetDevice(c->device));
+    if (in_len > c->d_in_cap) { // grow the input staging (outside the steady state: sizes repeat)
+        FCB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_in);
+        c->d_in = nullptr;
+        FCB_CUDA(cudaMalloc(&c->d_in, c->C * in_len * sizeof(float)));
+        c->d_in_cap = in_len;
+    }
+    if (in_len)
+        FCB_CUDA(cudaMemcpy2DAsync(c->d_in, in_len * sizeof(float), in, in_stride * sizeof(float), in_len * sizeof(float),
+                                   c->C, cudaMemcpyHostToDevice, c->stream));
+    const size_t M = c->max_buffer_size;
+    if (out_len > M) return fail(FCB_ERR_PANIC, "index out of bounds: the len is %zu but the index is %zu", M, M);
+    FCB_TRY(fcb_crossfade_process_dev(c, c->d_in, in_len, in_len, c->d_out, out_len, M ? M : 1));
+    if (out_len)
+        FCB_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float), c->d_out, (M ? M : 1) * sizeof(float),
+                                   out_len * sizeof(float), c->C, cudaMemcpyDeviceToHost, c->stream));
+    FCB_CUDA(cudaStreamSynchronize(c->stream));
+    return FCB_OK;
+}
+
+// :80-82
+extern "C" int fcb_crossfade_reset(fcb_crossfade *c)
+{
+    (void)c;
+    return fail(FCB_ERR_TODO, "not yet implemented");
+}
+
+extern "C" int fcb_crossfade_sync(fcb_crossfade *c)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    FCB_CUDA(cudaSetDevice(c->device));
+    FCB_CUDA(cudaStreamSynchronize(c->stream));
+    return FCB_OK;
+}
+
+extern "C" int fcb_crossfade_state(const fcb_crossfade *c, int64_t *counter, float *mix_value, int *approaching, int *target)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    if (counter) *counter = c->crossfader.counter;
+    if (mix_value) *mix_value = c->crossfader.mix_value;
+    if (approaching) *approaching = c->crossfader.approaching ? 1 : 0;
+    if (target) *target = c->crossfader.target;
+    return FCB_OK;
+}

@@ -1,0 +1,267 @@
+// mac_kernels.cuh — K2: the frequency-domain delay-line complex multiply-accumulate, fused with
+// the segment-ring indexing.  This is the HBM-bound kernel that carries >99 % of the bytes.
+//
+// Replaces src/fft_convolver.rs:258-269 (and complex_multiply_accumulate, :76-88):
+//     pre_multiplied[k] = sum_{i=1}^{active-1} ir[i][k] * ring[(current+i) % active][k]
+// accumulated in ascending i with every multiply / subtract / add rounded separately in f32
+// (Rust does not contract to FMA), so for identical spectra the result is bit-identical to the
+// reference loop.  Bin 0 of a packed row holds {DC.re, Nyquist.re}: two independent real
+// products, which is exactly what the reference's complex product of two purely real bins gives.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fcb {
+
+// streaming 16-byte load: every IR / ring byte is touched once per block, keep it out of L1
+__device__ __forceinline__ float4 ld_stream4(const float4 *p)
+{
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ld_stream2(const float2 *p)
+{
+    float2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+
+// acc += a * b for one complex bin, reference rounding; `packed` selects the {DC, Nyquist} rule
+__device__ __forceinline__ void cmac_ref(float &ar, float &ai, float xr, float xi, float hr, float hi, bool packed)
+{
+    float rr = __fmul_rn(xr, hr), ii = __fmul_rn(xi, hi);
+    float ri = __fmul_rn(xr, hi), ir = __fmul_rn(xi, hr);
+    float pr = packed ? rr : __fsub_rn(rr, ii);
+    float pi = packed ? ii : __fadd_rn(ri, ir);
+    ar = __fadd_rn(ar, pr);
+    ai = __fadd_rn(ai, pi);
+}
+
+struct MacArgs {
+    const float2 *ir;   // [C][S][B] packed rows (channel stride 0 when the IR is shared)
+    long long ir_stride;
+    const float2 *ring; // [C][S][B]
+    long long ring_stride;
+    float2 *premul;     // [C][B]
+    int current, active;
+    long long nchan;
+};
+
+// One thread owns V = 2 adjacent bins (one float4) of one channel and walks all segments.
+// blockDim.x = threads along the row (<= 256), blockDim.y = channels per CTA;
+// grid.x = row tiles * channel groups.  U = segments in flight per thread (2*U 16-byte loads).
+template <int B, int U>
+__global__ void __launch_bounds__(256)
+k_mac_v4(MacArgs a)
+{
+    constexpr int ROW4 = B / 2;                       // float4 per row
+    constexpr int TX = ROW4 < 256 ? ROW4 : 256;       // threads along the row
+    constexpr int TILES = ROW4 / TX;                  // row tiles per channel
+    constexpr int CPB = 256 / TX;                     // channels per CTA
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const long long grp = blockIdx.x / TILES;
+    const int tile = blockIdx.x % TILES;
+    const long long c = grp * CPB + ty;
+    if (c >= a.nchan) return;
+    const int t4 = tile * TX + tx; // float4 index within the row
+    const float4 *ir = reinterpret_cast<const float4 *>(a.ir + c * a.ir_stride) + t4;
+    const float4 *rg = reinterpret_cast<const float4 *>(a.ring + c * a.ring_stride) + t4;
+    const bool packed = (t4 == 0);
+    const int cur = a.current, act = a.active;
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int i = 1;
+    for (; i + U <= act; i += U) {
+        float4 h[U], x[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int j = (cur + i + u) % act;
+            h[u] = ld_stream4(ir + (long long)(i + u) * ROW4);
+            x[u] = ld_stream4(rg + (long long)j * ROW4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            cmac_ref(acc.x, acc.y, h[u].x, h[u].y, x[u].x, x[u].y, packed);
+            cmac_ref(acc.z, acc.w, h[u].z, h[u].w, x[u].z, x[u].w, false);
+        }
+    }
+    for (; i < act; i++) {
+        int j = (cur + i) % act;
+        float4 h = ld_stream4(ir + (long long)i * ROW4);
+        float4 x = ld_stream4(rg + (long long)j * ROW4);
+        cmac_ref(acc.x, acc.y, h.x, h.y, x.x, x.y, packed);
+        cmac_ref(acc.z, acc.w, h.z, h.w, x.z, x.w, false);
+    }
+    reinterpret_cast<float4 *>(a.premul + c * B)[t4] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA variant (the default for B >= 16): IR and ring rows are staged into shared memory by
+// cp.async.bulk copies (SASS: UBLKCP) completing on mbarriers, NST stages deep, so the bytes in
+// flight per SM are set by the pipeline (NST * 32 KB per CTA), not by what ptxas keeps in
+// registers.  Per channel the [S][B] spectra are contiguous, so one stage = R = 4 consecutive IR
+// rows (one copy) and 4 consecutive ring rows starting at (current+i) % active (one copy, two
+// when the ring wraps inside the stage).  A CTA is CPB channels x TILE bins with CPB*TILE = 512:
+// 256 threads, each owning one float4 (2 bins) of one channel, accumulating in ascending segment
+// order with the reference's unfused rounding — same bits as k_mac_v4.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`; bytes % 16 == 0, 16 B aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int B>
+struct MacBulkCfg {
+    static constexpr int TILE = B < 512 ? B : 512;   // bins per CTA row chunk
+    static constexpr int CPB = 512 / TILE;           // channels per CTA
+    static constexpr int TILES = B / TILE;           // row chunks per channel
+    static constexpr int R = 4;                      // rows (segments) per stage
+    static constexpr int ARR = CPB * R * TILE;       // float2 per array per stage (= 2048 -> 16 KB)
+    static constexpr size_t STAGE_BYTES = 2 * (size_t)ARR * sizeof(float2); // 32 KB
+    __host__ __device__ static constexpr size_t smem_bytes(int nst) { return nst * STAGE_BYTES + 64; }
+};
+
+template <int B, int NST>
+__global__ void __launch_bounds__(256)
+k_mac_bulk(MacArgs a)
+{
+    using Cfg = MacBulkCfg<B>;
+    constexpr int TILE = Cfg::TILE, CPB = Cfg::CPB, TILES = Cfg::TILES, R = Cfg::R, ARR = Cfg::ARR;
+    constexpr int TX = TILE / 2; // threads (float4) along the row chunk
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 *stages = reinterpret_cast<float2 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NST * Cfg::STAGE_BYTES);
+
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const long long grp = blockIdx.x / TILES;
+    const int tile = blockIdx.x % TILES;
+    const long long c0 = grp * CPB;
+    const int nlive = (int)((a.nchan - c0) < CPB ? (a.nchan - c0) : CPB); // channels of this CTA that exist
+    const int cur = a.current, act = a.active;
+    const int nrows = act - 1;                 // segments 1 .. act-1
+    const int niter = (nrows + R - 1) / R;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // producer: fill stage (it % NST) with the rows of iteration `it`
+    auto issue = [&](int it) {
+        const int s = it % NST;
+        const int i0 = 1 + it * R;
+        const int cnt = (act - i0) < R ? (act - i0) : R;
+        float2 *ir_s = stages + (size_t)s * 2 * ARR;
+        float2 *rg_s = ir_s + ARR;
+        mbar_expect_tx(&full[s], (uint32_t)(2 * nlive * cnt * TILE * sizeof(float2)));
+        for (int ch = 0; ch < nlive; ch++) {
+            const float2 *irc = a.ir + (c0 + ch) * a.ir_stride + tile * TILE;
+            const float2 *rgc = a.ring + (c0 + ch) * a.ring_stride + tile * TILE;
+            float2 *ir_d = ir_s + ch * R * TILE, *rg_d = rg_s + ch * R * TILE;
+            const int j0 = (cur + i0) % act; // `current` may exceed `active` after a shrinking update()
+            if (TILES == 1) {
+                bulk_g2s(ir_d, irc + (long long)i0 * B, cnt * TILE * sizeof(float2), &full[s]);
+                int first = (act - j0) < cnt ? (act - j0) : cnt; // rows before the ring wraps
+                bulk_g2s(rg_d, rgc + (long long)j0 * B, first * TILE * sizeof(float2), &full[s]);
+                if (first < cnt)
+                    bulk_g2s(rg_d + first * TILE, rgc, (cnt - first) * TILE * sizeof(float2), &full[s]);
+            } else {
+                for (int r = 0; r < cnt; r++) {
+                    int j = j0 + r;
+                    j = j >= act ? j - act : j;
+                    bulk_g2s(ir_d + r * TILE, irc + (long long)(i0 + r) * B, TILE * sizeof(float2), &full[s]);
+                    bulk_g2s(rg_d + r * TILE, rgc + (long long)j * B, TILE * sizeof(float2), &full[s]);
+                }
+            }
+        }
+    };
+
+    if (threadIdx.x == 0)
+        for (int it = 0; it < NST && it < niter; it++) issue(it);
+
+    const bool packed = (tile == 0 && tx == 0);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < niter; it++) {
+        const int s = it % NST;
+        mbar_wait(&full[s], (it / NST) & 1);
+        const int i0 = 1 + it * R;
+        const int cnt = (act - i0) < R ? (act - i0) : R;
+        const float4 *ir_s = reinterpret_cast<const float4 *>(stages + (size_t)s * 2 * ARR + ty * R * TILE) + tx;
+        const float4 *rg_s = ir_s + ARR / 2;
+        if (ty < nlive) {
+            if (cnt == R) {
+                float4 h[R], x[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    h[r] = ir_s[r * TX];
+                    x[r] = rg_s[r * TX];
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    cmac_ref(acc.x, acc.y, h[r].x, h[r].y, x[r].x, x[r].y, packed);
+                    cmac_ref(acc.z, acc.w, h[r].z, h[r].w, x[r].z, x[r].w, false);
+                }
+            } else {
+                for (int r = 0; r < cnt; r++) {
+                    float4 h = ir_s[r * TX], x = rg_s[r * TX];
+                    cmac_ref(acc.x, acc.y, h.x, h.y, x.x, x.y, packed);
+                    cmac_ref(acc.z, acc.w, h.z, h.w, x.z, x.w, false);
+                }
+            }
+        }
+        __syncthreads(); // every reader is done with stage s
+        if (threadIdx.x == 0 && it + NST < niter) issue(it + NST);
+    }
+    if (ty < nlive)
+        reinterpret_cast<float4 *>(a.premul + (c0 + ty) * B)[tile * TX + tx] = acc;
+}
+
+// B == 1: a row is a single packed bin
+__global__ void k_mac_b1(MacArgs a)
+{
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.nchan) return;
+    const float2 *ir = a.ir + c * a.ir_stride;
+    const float2 *rg = a.ring + c * a.ring_stride;
+    float ar = 0.f, ai = 0.f;
+    for (int i = 1; i < a.active; i++) {
+        int j = (a.current + i) % a.active;
+        float2 h = ld_stream2(ir + i), x = ld_stream2(rg + j);
+        cmac_ref(ar, ai, h.x, h.y, x.x, x.y, true);
+    }
+    a.premul[c] = make_float2(ar, ai);
+}
+
+} // namespace fcb

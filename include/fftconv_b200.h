@@ -1,0 +1,236 @@
+/*
+ * fftconv_b200.h — C ABI of the B200-native partitioned-FFT-convolution engine.
+ *
+ * This is the drop-in boundary for the hot path of Sin-tel/fft-convolution
+ * (/root/reference): the per-block inner loop of FFTConvolver::process
+ * (src/fft_convolver.rs:229-309) as reused by TwoStageFFTConvolver (:426-509) and
+ * CrossfadeConvolver (src/crossfade_convolver.rs:66-78).  Plain pointers and sizes only.
+ *
+ * Two layers are exported from libfftconv_b200.so:
+ *
+ *  1. fcb_engine_*   — the device stages.  This is what a Rust `extern "C"` FFI crate binds
+ *     when the Rust host keeps the block scheduler, the input-buffer fill and the segment
+ *     ring rotation (INTEGRATION.md shows the binding).  One engine = C lock-step channels
+ *     of one FFTConvolver shape (block size B, S segments); the caller passes the scalars
+ *     the reference keeps in `current`, `input_buffer_fill`, `active_seg_count`.
+ *
+ *  2. fcb_fftconv_* / fcb_twostage_* / fcb_crossfade_*   — a C++ host mirror of the
+ *     reference's three `Convolution` implementors (scheduler included), batched over C
+ *     channels, for C/C++/Python callers that have no Rust host.  With C = 1 the semantics,
+ *     argument meaning and failure conditions are those of the reference types.
+ *
+ * There is no CPU fallback: every entry point needs a CUDA device (sm_100a build).
+ *
+ * Layouts.  Host/device sample buffers are planar [channel][sample] f32 with an explicit
+ * channel stride in samples.  Spectra live only on the device, packed B complex per row
+ * (bin 0 = {DC.re, Nyquist.re}; bins 1..B-1 interleaved re,im) — see DESIGN.md.
+ */
+#ifndef FFTCONV_B200_H
+#define FFTCONV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define FCB_OK 0
+#define FCB_ERR_PANIC 1       /* contract violation: the reference panic!s / assert!s here */
+#define FCB_ERR_TODO 2        /* the reference method is todo!() (TwoStage::update, Crossfade::reset) */
+#define FCB_ERR_CUDA 3        /* CUDA runtime / launch failure (sticky text in fcb_last_error) */
+#define FCB_ERR_UNSUPPORTED 4 /* valid in the reference, outside this engine's limits (e.g. B > 16384) */
+#define FCB_ERR_ARG 5         /* NULL / out-of-range argument at the C boundary */
+
+/* thread-local, never NULL */
+const char *fcb_last_error(void);
+/* "fftconv_b200 <version> sm_100a" */
+const char *fcb_version(void);
+/* kernels launched by this library in this process (bench.py's gpu_launches) */
+uint64_t fcb_launch_count(void);
+/* number of visible CUDA devices, or -1 */
+int fcb_device_count(void);
+
+/* tuning knobs for benchmarking sweeps: "mac_impl" (0 auto, 1 LDG kernel, 2 TMA pipeline),
+ * "mac_stages" (2, 3, 4, 6 pipeline stages of 32 KB) */
+int fcb_tune(const char *key, int value);
+
+/* live timing of the K2 launches: while enabled every K2 launch is bracketed by CUDA events on
+ * its stream; read returns the summed device time and the number of launches since enable */
+int fcb_profile_mac(int enable);
+int fcb_profile_mac_read(double *total_ms, uint64_t *launches);
+
+/* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
+void *fcb_host_alloc(size_t bytes);
+void fcb_host_free(void *p);
+
+/* ============================================================================================
+ * Layer 1: device stages (replaces the arithmetic of src/fft_convolver.rs:21-98 and the loop
+ * bodies at :145-156, :207-226, :248-288, :297-298).
+ * ========================================================================================== */
+typedef struct fcb_engine fcb_engine;
+
+typedef struct {
+    size_t channels;            /* C >= 1 lock-step channels */
+    size_t block_size;          /* rounded up to a power of two like :129; 1..16384 */
+    size_t max_response_length; /* ir_len of :125-127; seg_count = ceil(len / B) (:131) */
+    int shared_ir;              /* 1: all channels use one IR (spectra stored once, reused on chip) */
+    int device;                 /* CUDA device ordinal */
+    void *stream;               /* cudaStream_t to run on, NULL = a private non-blocking stream */
+} fcb_engine_desc;
+
+int fcb_engine_create(const fcb_engine_desc *desc, fcb_engine **out);
+void fcb_engine_destroy(fcb_engine *e);
+/* #[derive(Clone)] (src/fft_convolver.rs:100): deep copy of ring, spectra, overlap, input buffer */
+int fcb_engine_clone(const fcb_engine *e, fcb_engine **out);
+int fcb_engine_set_stream(fcb_engine *e, void *stream);
+void *fcb_engine_stream(const fcb_engine *e);
+int fcb_engine_sync(fcb_engine *e);
+
+size_t fcb_engine_channels(const fcb_engine *e);
+size_t fcb_engine_block_size(const fcb_engine *e); /* rounded B */
+size_t fcb_engine_seg_count(const fcb_engine *e);  /* S */
+
+/* K5 — IR preparation (src/fft_convolver.rs:145-156 for init, :199-226 for update).
+ * irs: [nchan][len] f32 with channel stride `stride` samples, host or device memory.
+ * Rows >= ceil(len/B) are zeroed.  is_update != 0 additionally zeroes pre_multiplied and
+ * overlap of those channels (:199-202).  With shared_ir the call must cover chan0 = 0, nchan = 1.
+ * No allocation happens here (the staging buffer is created with the engine). */
+int fcb_engine_set_ir(fcb_engine *e, size_t chan0, size_t nchan, const float *irs, size_t len,
+                      size_t stride, int is_update);
+int fcb_engine_set_ir_dev(fcb_engine *e, size_t chan0, size_t nchan, const float *irs_dev, size_t len,
+                          size_t stride, int is_update);
+
+/* reset() (:310-320): zero ring, overlap, input buffer, pre_multiplied.  IR spectra kept. */
+int fcb_engine_reset(fcb_engine *e);
+
+/* :243-245 — copy n new samples per channel into the device input buffer at [fill, fill+n) */
+int fcb_engine_push_input(fcb_engine *e, const float *in, size_t stride, size_t fill, size_t n);
+int fcb_engine_push_input_dev(fcb_engine *e, const float *in_dev, size_t stride, size_t fill, size_t n);
+
+/* K1 (:248-255): forward real FFT of [input_buffer[0..valid) | zeros] into ring slot `current` */
+int fcb_engine_fft_forward(fcb_engine *e, size_t current, size_t valid);
+
+/* K2 (:258-269): pre_multiplied = sum_{i=1}^{active-1} ir[i] * ring[(current+i) % active],
+ * ascending i, every multiply/add rounded separately like the reference.  Only touches ring
+ * slots older than `current`, so it may be issued before the block's input arrives. */
+int fcb_engine_mac(fcb_engine *e, size_t current, size_t active);
+
+/* fused output epilogues for K3 */
+typedef struct {
+    /* two-stage head/tail sum (:452-468): out = ((y + overlap) + add0[i]) + add1[i]; device
+     * pointers already offset to this call's first sample, channel stride add_stride; may be NULL */
+    const float *add0, *add1;
+    size_t add_stride;
+    /* crossfade gain ramp (src/crossfade_convolver.rs:75-77, :160-169, :242-278):
+     * out = mine*g[i].x + other[i]*g[i].y evaluated as two rounded products and one rounded add;
+     * g = {1,0} returns mine and g = {0,1} returns other untouched.  `gains` = n device float2. */
+    const float *mix_other;
+    size_t mix_stride;
+    const float *gains;
+} fcb_epilogue;
+
+/* K3 (:270-288, :297-298): conv = pre_multiplied + ring[current]*ir[0]; inverse real FFT, /N;
+ * out[c][0..n) = y[fill..fill+n) + overlap[fill..fill+n) (+ epilogue); when block_complete the
+ * overlap is replaced by y[B..2B).  out_dev: device [C][n] with channel stride out_stride. */
+int fcb_engine_ifft_ola(fcb_engine *e, size_t current, size_t fill, size_t n, int block_complete,
+                        float *out_dev, size_t out_stride, const fcb_epilogue *epi);
+
+/* device -> host copy of a planar result (stream-ordered, then synchronised) */
+int fcb_engine_fetch(fcb_engine *e, float *out_host, size_t host_stride, const float *src_dev,
+                     size_t dev_stride, size_t n);
+
+/* whole-block fast path for full blocks (n == B, fill == 0): K1 -> K2 -> K3 on device buffers */
+int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, size_t in_stride, float *out_dev,
+                                 size_t out_stride, size_t current, size_t active,
+                                 const fcb_epilogue *epi);
+
+/* debug / test readback of device state in the reference's layout (K = B+1 interleaved complex) */
+int fcb_engine_read_ir_segment(fcb_engine *e, size_t chan, size_t seg, float *out_2k);
+int fcb_engine_read_ring_segment(fcb_engine *e, size_t chan, size_t seg, float *out_2k);
+int fcb_engine_read_premul(fcb_engine *e, size_t chan, float *out_2k);
+int fcb_engine_read_overlap(fcb_engine *e, size_t chan, float *out_b);
+/* test hook: overwrite one spectrum row from the reference layout (K interleaved complex) */
+int fcb_engine_write_ir_segment(fcb_engine *e, size_t chan, size_t seg, const float *in_2k);
+int fcb_engine_write_ring_segment(fcb_engine *e, size_t chan, size_t seg, const float *in_2k);
+
+/* ============================================================================================
+ * Layer 2: host mirror of the `Convolution` trait (src/lib.rs:5-14), batched over C channels.
+ * `irs` is [C][ir_len] with channel stride ir_len (or a single IR when shared_ir != 0).
+ * process(): in/out are HOST pointers, planar, strides in samples; *_dev: device pointers,
+ * asynchronous on the convolver's stream.
+ * ========================================================================================== */
+typedef struct fcb_fftconv fcb_fftconv;
+typedef struct fcb_twostage fcb_twostage;
+typedef struct fcb_crossfade fcb_crossfade;
+
+typedef struct {
+    int device;     /* CUDA device ordinal */
+    void *stream;   /* cudaStream_t or NULL */
+    int shared_ir;  /* FFTConvolver only */
+    int async_tail; /* TwoStage: run the big tail convolver on a second stream (the reference's
+                       "might be done in some background thread", src/fft_convolver.rs:492) */
+    size_t forced_tail_block; /* TwoStage: 0 = derive like the reference (:534-540) */
+} fcb_options;
+
+/* ---- FFTConvolver (src/fft_convolver.rs:100-321) ---- */
+int fcb_fftconv_init(fcb_fftconv **out, const float *irs, size_t channels, size_t ir_len,
+                     size_t block_size, size_t max_response_length, const fcb_options *opt);
+int fcb_fftconv_default(fcb_fftconv **out, size_t channels, const fcb_options *opt); /* Default::default() */
+int fcb_fftconv_clone(const fcb_fftconv *c, fcb_fftconv **out);
+void fcb_fftconv_free(fcb_fftconv *c);
+int fcb_fftconv_update(fcb_fftconv *c, const float *irs, size_t ir_len);
+int fcb_fftconv_reset(fcb_fftconv *c);
+int fcb_fftconv_process(fcb_fftconv *c, const float *in, size_t in_len, size_t in_stride, float *out,
+                        size_t out_len, size_t out_stride);
+int fcb_fftconv_process_dev(fcb_fftconv *c, const float *in_dev, size_t in_len, size_t in_stride,
+                            float *out_dev, size_t out_len, size_t out_stride, const fcb_epilogue *epi);
+int fcb_fftconv_sync(fcb_fftconv *c);
+fcb_engine *fcb_fftconv_engine(fcb_fftconv *c); /* NULL for a default (empty) convolver */
+/* scheduler scalars the host keeps (src/fft_convolver.rs:103-105, :113, :115) */
+size_t fcb_fftconv_block_size(const fcb_fftconv *c);
+size_t fcb_fftconv_seg_count(const fcb_fftconv *c);
+size_t fcb_fftconv_active_seg_count(const fcb_fftconv *c);
+size_t fcb_fftconv_current(const fcb_fftconv *c);
+size_t fcb_fftconv_fill(const fcb_fftconv *c);
+
+/* ---- TwoStageFFTConvolver (src/fft_convolver.rs:337-540) ---- */
+size_t fcb_compute_tail_block_size(size_t head_len, size_t response_len); /* :534-540, f32 */
+int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t channels, size_t ir_len,
+                      size_t block_size, size_t max_response_length, const fcb_options *opt);
+int fcb_twostage_clone(const fcb_twostage *c, fcb_twostage **out);
+void fcb_twostage_free(fcb_twostage *c);
+int fcb_twostage_update(fcb_twostage *c, const float *irs, size_t ir_len); /* FCB_ERR_TODO */
+int fcb_twostage_reset(fcb_twostage *c);
+int fcb_twostage_process(fcb_twostage *c, const float *in, size_t in_len, size_t in_stride, float *out,
+                         size_t out_len, size_t out_stride);
+int fcb_twostage_process_dev(fcb_twostage *c, const float *in_dev, size_t in_len, size_t in_stride,
+                             float *out_dev, size_t out_len, size_t out_stride);
+int fcb_twostage_sync(fcb_twostage *c);
+size_t fcb_twostage_tail_block_size(const fcb_twostage *c);
+
+/* ---- CrossfadeConvolver<FFTConvolver> (src/crossfade_convolver.rs:3-105) ---- */
+/* CrossfadeConvolver::new (:20-42): takes ownership of `convolver` */
+int fcb_crossfade_new(fcb_crossfade **out, fcb_fftconv *convolver, size_t max_response_length,
+                      size_t max_buffer_size, size_t crossfade_samples);
+/* <CrossfadeConvolver as Convolution>::init (:46-49) */
+int fcb_crossfade_init(fcb_crossfade **out, const float *irs, size_t channels, size_t ir_len,
+                       size_t max_block_size, size_t max_response_length, const fcb_options *opt);
+void fcb_crossfade_free(fcb_crossfade *c);
+int fcb_crossfade_update(fcb_crossfade *c, const float *irs, size_t ir_len);
+int fcb_crossfade_process(fcb_crossfade *c, const float *in, size_t in_len, size_t in_stride, float *out,
+                          size_t out_len, size_t out_stride);
+int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in_dev, size_t in_len, size_t in_stride,
+                              float *out_dev, size_t out_len, size_t out_stride);
+int fcb_crossfade_reset(fcb_crossfade *c); /* FCB_ERR_TODO */
+int fcb_crossfade_is_crossfading(const fcb_crossfade *c);
+int fcb_crossfade_sync(fcb_crossfade *c);
+/* crossfader state for tests: counter, mix_value, approaching(0/1), target(0=A,1=B) */
+int fcb_crossfade_state(const fcb_crossfade *c, int64_t *counter, float *mix_value, int *approaching,
+                        int *target);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFTCONV_B200_H */

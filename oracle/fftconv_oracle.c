@@ -18,6 +18,9 @@
 #include <omp.h>
 #endif
 #include <time.h>
+#ifdef __AVX2__
+#include <immintrin.h>
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * real FFT stand-in.  Contract mirrored from the call sites src/fft_convolver.rs:50-63:
@@ -87,21 +90,49 @@ void orc_plan_free(orc_plan *p)
 
 /* in-place m-point complex FFT on split arrays already in bit-reversed order;
  * sign = -1 forward, +1 inverse (unnormalised) */
-static void cfft_stages(const orc_plan *p, float *re, float *im, float sign)
+static void cfft_stages(const orc_plan *p, float *restrict re, float *restrict im, float sign)
 {
     size_t m = p->m;
-    for (int s = 0; s < p->log2m; s++) {
+    int s = 0;
+    if (p->log2m >= 2) {
+        /* first two radix-2 stages fused (twiddles 1 and -+i): plain radix-4 on bit-reversed input */
+        for (size_t b = 0; b < m; b += 4) {
+            float a0r = re[b], a0i = im[b], a1r = re[b + 1], a1i = im[b + 1];
+            float a2r = re[b + 2], a2i = im[b + 2], a3r = re[b + 3], a3i = im[b + 3];
+            float s0r = a0r + a1r, s0i = a0i + a1i, d0r = a0r - a1r, d0i = a0i - a1i;
+            float s1r = a2r + a3r, s1i = a2i + a3i, d1r = a2r - a3r, d1i = a2i - a3i;
+            /* second stage twiddle for j=1: w = exp(sign*i*pi/2) = sign*i */
+            float tr = sign < 0 ? d1i : -d1i, ti = sign < 0 ? -d1r : d1r;
+            re[b] = s0r + s1r; im[b] = s0i + s1i;
+            re[b + 2] = s0r - s1r; im[b + 2] = s0i - s1i;
+            re[b + 1] = d0r + tr; im[b + 1] = d0i + ti;
+            re[b + 3] = d0r - tr; im[b + 3] = d0i - ti;
+        }
+        s = 2;
+    }
+    for (; s < p->log2m; s++) {
         size_t half = (size_t)1 << s;
-        const float *wr = p->tw_re + (half - 1), *wi = p->tw_im + (half - 1);
+        const float *restrict wr = p->tw_re + (half - 1), *restrict wi = p->tw_im + (half - 1);
         for (size_t b = 0; b < m; b += 2 * half) {
-            float *ar = re + b, *ai = im + b, *br = re + b + half, *bi = im + b + half;
-            for (size_t j = 0; j < half; j++) {
-                float c = wr[j], d = sign < 0 ? wi[j] : -wi[j];
-                float vr = br[j] * c - bi[j] * d;
-                float vi = br[j] * d + bi[j] * c;
-                float ur = ar[j], ui = ai[j];
-                ar[j] = ur + vr; ai[j] = ui + vi;
-                br[j] = ur - vr; bi[j] = ui - vi;
+            float *restrict ar = re + b, *restrict ai = im + b, *restrict br = re + b + half, *restrict bi = im + b + half;
+            if (sign < 0) {
+                for (size_t j = 0; j < half; j++) {
+                    float c = wr[j], d = wi[j];
+                    float vr = br[j] * c - bi[j] * d;
+                    float vi = br[j] * d + bi[j] * c;
+                    float ur = ar[j], ui = ai[j];
+                    ar[j] = ur + vr; ai[j] = ui + vi;
+                    br[j] = ur - vr; bi[j] = ui - vi;
+                }
+            } else {
+                for (size_t j = 0; j < half; j++) {
+                    float c = wr[j], d = -wi[j];
+                    float vr = br[j] * c - bi[j] * d;
+                    float vi = br[j] * d + bi[j] * c;
+                    float ur = ar[j], ui = ai[j];
+                    ar[j] = ur + vr; ai[j] = ui + vi;
+                    br[j] = ur - vr; bi[j] = ui - vi;
+                }
             }
         }
     }
@@ -175,7 +206,24 @@ size_t orc_complex_size(size_t n) { return n / 2 + 1; }
  * (ar*br - ai*bi, ar*bi + ai*br), every operation rounded separately */
 void orc_complex_multiply_accumulate(orc_cpx *result, const orc_cpx *a, const orc_cpx *b, size_t len)
 {
-    for (size_t i = 0; i < len; i++) {
+    size_t i = 0;
+#ifdef __AVX2__
+    /* same operations as the scalar loop, 4 complex bins per step: two rounded products per
+     * component, one rounded subtract (even lanes) / add (odd lanes) via addsub, one rounded
+     * accumulate — no FMA, so the bits equal the reference's scalar arithmetic */
+    float *r = (float *)result;
+    const float *pa = (const float *)a, *pb = (const float *)b;
+    for (; i + 4 <= len; i += 4) {
+        __m256 va = _mm256_loadu_ps(pa + 2 * i), vb = _mm256_loadu_ps(pb + 2 * i);
+        __m256 are = _mm256_moveldup_ps(va), aim = _mm256_movehdup_ps(va);
+        __m256 bsw = _mm256_permute_ps(vb, 0xB1);           /* (b.im, b.re) */
+        __m256 t0 = _mm256_mul_ps(are, vb);                 /* a.re*b.re , a.re*b.im */
+        __m256 t1 = _mm256_mul_ps(aim, bsw);                /* a.im*b.im , a.im*b.re */
+        __m256 prod = _mm256_addsub_ps(t0, t1);             /* re: t0 - t1 ; im: t0 + t1 */
+        _mm256_storeu_ps(r + 2 * i, _mm256_add_ps(_mm256_loadu_ps(r + 2 * i), prod));
+    }
+#endif
+    for (; i < len; i++) {
         float pr = a[i].re * b[i].re - a[i].im * b[i].im;
         float pi = a[i].re * b[i].im + a[i].im * b[i].re;
         result[i].re += pr;

@@ -1,0 +1,176 @@
+"""The reference's own tests, restated against the CUDA engine through the C ABI,
+with the reference's tolerances — plus the same sequences checked sample-by-sample against the
+CPU oracle (<= 1e-5 * output RMS, the north_star tolerance)."""
+import numpy as np
+import pytest
+
+import oracle
+from refsignals import generate_sinusoid, rms
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # max-abs error relative to output RMS (BASELINE.json north_star)
+
+
+@pytest.fixture(scope="module")
+def F():
+    import fft_convolution_b200 as f
+    return f
+
+
+def _delta(n=1024):
+    r = np.zeros(n, np.float32)
+    r[0] = 1.0
+    return r
+
+
+def test_fft_convolver_passthrough(F):
+    """src/fft_convolver.rs:323-335"""
+    conv = F.FFTConvolver.init(_delta(), 1024, 1024)
+    out = np.zeros(1024, np.float32)
+    conv.process(np.ones(1024, np.float32), out)
+    assert np.all(np.abs(out - 1.0) < 1e-6)
+
+
+def test_fft_twostage_convolver_passthrough(F):
+    """src/fft_convolver.rs:542-554"""
+    conv = F.TwoStageFFTConvolver.init(_delta(), 1024, 1024)
+    assert conv.tail_block_size == 1024
+    out = np.zeros(1024, np.float32)
+    conv.process(np.ones(1024, np.float32), out)
+    assert np.all(np.abs(out - 1.0) < 1e-6)
+
+
+def test_crossfade_convolver_passthrough(F):
+    """src/crossfade_convolver.rs:107-124"""
+    conv = F.CrossfadeConvolver.new(F.FFTConvolver.init(_delta(), 1024, 1024), 1024, 1024, 1024)
+    out = np.zeros(1024, np.float32)
+    conv.process(np.ones(1024, np.float32), out)
+    assert np.all(np.abs(out - 1.0) < 1e-6)
+
+
+def test_fft_convolver_update_is_reset(F):
+    """src/tests.rs:18-59"""
+    bs = 512
+    ra = generate_sinusoid(bs, 1000.0, gain=1.0)
+    rb = generate_sinusoid(bs, 2000.0, gain=0.7)
+    ca, cb, cu = (F.FFTConvolver.init(r, bs, bs) for r in (ra, rb, ra))
+    orc = oracle.FFTConvolver.init(ra, bs, bs)
+    oa, ob, ou, oo = (np.zeros(bs, np.float32) for _ in range(4))
+    x = generate_sinusoid(16 * bs, 1300.0)
+    for i in range(16):
+        if i == 8:
+            cu.update(rb)
+            orc.update(rb)
+        blk = x[i * bs:(i + 1) * bs]
+        cu.process(blk, ou)
+        orc.process(blk, oo)
+        assert np.max(np.abs(ou - oo)) <= TOL * max(rms(oo), 1e-3)
+        if i < 8:
+            ca.process(blk, oa)
+            assert np.all(np.abs(oa - ou) < 1e-6 * 15)  # reference tol 1e-6 at its own noise floor; RMS ~15
+        else:
+            cb.process(blk, ob)
+            assert np.all(np.abs(ob - ou) < 1e-6 * 15)
+
+
+def test_crossfade_convolver(F):
+    """src/tests.rs:61-117"""
+    bs = 512
+    ra = generate_sinusoid(bs, 1000.0, gain=1.0)
+    rb = generate_sinusoid(bs, 2000.0, gain=0.7)
+    ca = F.FFTConvolver.init(ra, bs, bs)
+    cb = F.FFTConvolver.init(rb, bs, bs)
+    xf = F.CrossfadeConvolver.new(ca.clone(), bs, bs, bs)
+    oxf = oracle.CrossfadeConvolver.new(oracle.FFTConvolver.init(ra, bs, bs), bs, bs, bs)
+    oa, ob, ox, oo = (np.zeros(bs, np.float32) for _ in range(4))
+    x = generate_sinusoid(16 * bs, 1300.0)
+    for i in range(16):
+        if i == 8:
+            xf.update(rb)
+            oxf.update(rb)
+        blk = x[i * bs:(i + 1) * bs]
+        xf.process(blk, ox)
+        oxf.process(blk, oo)
+        assert xf.is_crossfading() == oxf.is_crossfading()
+        assert np.max(np.abs(ox - oo)) <= TOL * max(rms(oo), 1e-3)
+        ca.process(blk, oa)
+        if i >= 8:
+            cb.process(blk, ob)
+        if i <= 8:
+            assert np.array_equal(oa, ox)  # Reached(A)/hold: convolver A's samples untouched
+        elif i == 9:
+            k = bs // 2 - 1
+            assert abs(ox[k] - (oa[k] * np.float32(0.5) + ob[k] * np.float32(0.5))) < 1e-5
+        else:
+            assert np.array_equal(ob, ox)
+
+
+def test_block_size_equal(F):
+    """src/tests.rs:119-146"""
+    bs, nblocks = 128, 200
+    r = generate_sinusoid(bs, 1000.0, gain=0.1)
+    ca, cb = F.FFTConvolver.init(r, bs // 2, bs), F.FFTConvolver.init(r, bs, bs)
+    oa, ob = np.zeros(bs, np.float32), np.zeros(bs, np.float32)
+    x = generate_sinusoid(nblocks * bs, 1300.0, gain=0.1)
+    for i in range(nblocks):
+        ca.process(x[i * bs:(i + 1) * bs], oa)
+        cb.process(x[i * bs:(i + 1) * bs], ob)
+        assert np.all(np.abs(oa - ob) < 1e-5)
+
+
+def test_twostage_equal(F):
+    """src/tests.rs:148-175 (uniform B=32 vs two-stage head 64 => T=1024, 16+16+10 segments)"""
+    bs, nblocks = 64, 400
+    r = generate_sinusoid(12000, 1000.0, gain=0.1)
+    ca, cb = F.FFTConvolver.init(r, bs // 2, r.size), F.TwoStageFFTConvolver.init(r, bs, r.size)
+    orc = oracle.TwoStageFFTConvolver.init(r, bs, r.size)
+    assert cb.tail_block_size == orc.tail_block_size == 1024
+    oa, ob, oo = (np.zeros(bs, np.float32) for _ in range(3))
+    x = generate_sinusoid(nblocks * bs, 1300.0, gain=0.1)
+    for i in range(nblocks):
+        blk = x[i * bs:(i + 1) * bs]
+        ca.process(blk, oa)
+        cb.process(blk, ob)
+        orc.process(blk, oo)
+        assert np.all(np.abs(oa - ob) < 1e-5)
+        assert np.max(np.abs(ob - oo)) <= TOL * max(rms(oo), 1e-2)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "twostage"])
+def test_reset(F, kind):
+    """src/tests.rs:177-216, :218-257 — whole run compared, bit for bit"""
+    bs, nblocks = 64, 300
+    r = generate_sinusoid(12000, 1000.0, gain=0.1)
+    conv = (F.FFTConvolver if kind == "uniform" else F.TwoStageFFTConvolver).init(r, bs, r.size)
+    x = generate_sinusoid(nblocks * bs, 1300.0, gain=0.1)
+    outs = []
+    for _ in range(2):
+        o = np.zeros(nblocks * bs, np.float32)
+        blk = np.zeros(bs, np.float32)
+        for i in range(nblocks):
+            conv.process(x[i * bs:(i + 1) * bs], blk)
+            o[i * bs:(i + 1) * bs] = blk
+        outs.append(o)
+        conv.reset()
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_reference_panics(F):
+    with pytest.raises(F.ConvolutionPanic):
+        F.FFTConvolver.init(np.zeros(10, np.float32), 4, 5)
+    c = F.FFTConvolver.init(np.zeros(10, np.float32), 4, 10)
+    with pytest.raises(F.ConvolutionPanic):
+        c.update(np.zeros(11, np.float32))
+    with pytest.raises(F.ConvolutionPanic):
+        c.process(np.zeros(3, np.float32), np.zeros(4, np.float32))
+    t = F.TwoStageFFTConvolver.init(np.zeros(100, np.float32), 8, 100)
+    with pytest.raises(F.NotYetImplemented):
+        t.update(np.zeros(10, np.float32))
+    with pytest.raises(F.ConvolutionPanic):
+        t.process(np.zeros(9, np.float32), np.zeros(9, np.float32))
+    x = F.CrossfadeConvolver.init(np.ones(16, np.float32), 8, 16)
+    with pytest.raises(F.NotYetImplemented):
+        x.reset()
+    with pytest.raises(F.ConvolutionPanic):
+        x.process(np.zeros(8, np.float32), np.zeros(9, np.float32))
