@@ -117,7 +117,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_ev.wait(0.05)
+            self._stop_ev.wait(0.01)
 
     def stop(self) -> dict:
         self._stop_ev.set()
@@ -129,14 +129,21 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
+_CPU_DATA: dict = {}
+
+
 def cpu_port_run(channels: int, block: int, ir_len: int, calls: int, threads: int) -> tuple[float, float]:
     """CPU restatement of the reference algorithm (oracle/fftconv_oracle.c), one convolver per
-    channel, channels over `threads` host threads; returns (channel-sec/sec, seconds)."""
+    channel, channels over `threads` host threads; returns (channel-sec/sec, seconds of the block
+    loop).  The synthetic data is generated once per shape and reused by later steps."""
     import oracle  # cpu_baseline / --impl reference legs only
     lib = oracle.load().lib
-    irs = synth_irs(1 << 20, channels, 0, ir_len)
-    x = synth_noise(1 << 20, channels, 0, block * calls)
-    out = np.zeros_like(x)
+    key = (channels, block, ir_len, calls)
+    if key not in _CPU_DATA:
+        _CPU_DATA.clear()
+        _CPU_DATA[key] = (synth_irs(1 << 20, channels, 0, ir_len), synth_noise(1 << 20, channels, 0, block * calls))
+    irs, x = _CPU_DATA[key]
+    out = np.empty_like(x)
     secs = lib.orc_batch_fftconv_run(channels, block, ir_len, irs, x, out, block, calls, threads)
     return channels * calls * block / SAMPLE_RATE / secs, secs
 
@@ -151,8 +158,8 @@ def run_reference(args) -> None:
     channels = max(threads * 4, 8)
     calls = 94  # ~1 s of audio per channel per step
     # warm-up + timed steps, each step a bounded sample of the workload
-    for _ in range(max(args.warmup, 1) if args.warmup else 0):
-        cpu_port_run(channels, args.block, ir_len, 8, threads)
+    for _ in range(min(args.warmup, 3)):
+        cpu_port_run(channels, args.block, ir_len, calls, threads)
     t_tot, work = 0.0, 0.0
     for _ in range(args.steps):
         v, secs = cpu_port_run(channels, args.block, ir_len, calls, threads)
@@ -353,8 +360,8 @@ def run_b200(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--channels", type=int, default=4096, help="channels per GPU")
     ap.add_argument("--block", type=int, default=512)

@@ -54,6 +54,7 @@ struct fcb_engine {
     bool shared_ir = false;
     float2 *ir = nullptr, *ring = nullptr, *premul = nullptr;
     float *overlap = nullptr, *inbuf = nullptr;
+    float *scratch = nullptr; // [C][B] output staging for layer-1 callers (fcb_engine_scratch)
     float *stage = nullptr; // IR upload staging
     size_t stage_floats = 0;
     const float2 *tw = nullptr;
@@ -284,6 +285,7 @@ static int engine_alloc(fcb_engine *e)
     FCB_TRY(alloc_zero((void **)&e->premul, e->C * e->B * sizeof(float2), e->stream));
     FCB_TRY(alloc_zero((void **)&e->overlap, e->C * e->B * sizeof(float), e->stream));
     FCB_TRY(alloc_zero((void **)&e->inbuf, e->C * e->B * sizeof(float), e->stream));
+    FCB_TRY(alloc_zero((void **)&e->scratch, e->C * e->B * sizeof(float), e->stream));
     // staging for host IR uploads: whole channels, at most ~64 MB, at least one channel
     size_t per = e->L ? e->L : 1;
     size_t want = e->ir_channels() * per, cap = (size_t)16 << 20;
@@ -338,6 +340,7 @@ extern "C" void fcb_engine_destroy(fcb_engine *e)
     cudaFree(e->premul);
     cudaFree(e->overlap);
     cudaFree(e->inbuf);
+    cudaFree(e->scratch);
     cudaFree(e->stage);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -388,6 +391,7 @@ extern "C" int fcb_engine_sync(fcb_engine *e)
     FCB_CUDA(cudaStreamSynchronize(e->stream));
     return FCB_OK;
 }
+extern "C" float *fcb_engine_scratch(fcb_engine *e) { return e ? e->scratch : nullptr; }
 extern "C" size_t fcb_engine_channels(const fcb_engine *e) { return e->C; }
 extern "C" size_t fcb_engine_block_size(const fcb_engine *e) { return e->B; }
 extern "C" size_t fcb_engine_seg_count(const fcb_engine *e) { return e->S; }

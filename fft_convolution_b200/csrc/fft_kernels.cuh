@@ -284,7 +284,7 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
     //    Z'[k] = (X[k] + conj X[B-k]) + i w^{-k} (X[k] - conj X[B-k]),  w = exp(-2 pi i / N)
     {
         constexpr int HALF = B / 2;
-        constexpr int PAIRS_PER_THREAD = (HALF + T - 1) / T; // pairs p = 0..HALF-1 (p = 0 also does k = B/2)
+        constexpr int PAIRS_PER_THREAD = HALF >= T ? HALF / T : 1; // pairs p = 0..HALF-1 (p = 0 also does k = B/2)
 #pragma unroll
         for (int e = 0; e < PAIRS_PER_THREAD; e++) {
             int k = tid + e * T;

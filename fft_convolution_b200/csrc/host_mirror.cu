@@ -73,7 +73,7 @@ struct fcb_fftconv {
     fcb_options opt{};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    float *d_io = nullptr; // device staging for host-pointer process(): [C][B]
+    float *d_io = nullptr; // device staging for host-pointer process(): [C][B] (the engine's scratch)
 };
 
 static int fftconv_make_stream(fcb_fftconv *c)
@@ -109,7 +109,6 @@ extern "C" void fcb_fftconv_free(fcb_fftconv *c)
     cudaSetDevice(c->opt.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     fcb_engine_destroy(c->eng);
-    cudaFree(c->d_io);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -133,10 +132,7 @@ extern "C" int fcb_fftconv_init(fcb_fftconv **out, const float *irs, size_t chan
     int rc = fcb_engine_create(&d, &c->eng);
     // :145-156 — K5 over the zero-padded IR (rows past ir_len come out as zeros)
     if (rc == FCB_OK) rc = fcb_engine_set_ir(c->eng, 0, c->opt.shared_ir ? 1 : channels, irs, ir_len, ir_len, 0);
-    if (rc == FCB_OK) {
-        cudaError_t err = cudaMalloc(&c->d_io, channels * c->block_size * sizeof(float));
-        if (err != cudaSuccess) rc = fail(FCB_ERR_CUDA, "cudaMalloc staging failed: %s", cudaGetErrorString(err));
-    }
+    if (rc == FCB_OK) c->d_io = fcb_engine_scratch(c->eng);
     if (rc == FCB_OK) rc = fcb_engine_sync(c->eng);
     if (rc != FCB_OK) {
         fcb_fftconv_free(c);
@@ -162,10 +158,7 @@ extern "C" int fcb_fftconv_clone(const fcb_fftconv *s, fcb_fftconv **out)
     if (s->eng) {
         rc = fcb_engine_clone(s->eng, &c->eng);
         if (rc == FCB_OK) rc = fcb_engine_set_stream(c->eng, (void *)c->stream);
-        if (rc == FCB_OK) {
-            cudaError_t err = cudaMalloc(&c->d_io, c->C * c->block_size * sizeof(float));
-            if (err != cudaSuccess) rc = fail(FCB_ERR_CUDA, "cudaMalloc staging failed: %s", cudaGetErrorString(err));
-        }
+        if (rc == FCB_OK) c->d_io = fcb_engine_scratch(c->eng);
     }
     if (rc != FCB_OK) {
         fcb_fftconv_free(c);
@@ -548,7 +541,10 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
     const bool one_piece = in_len <= H - (c->tail_input_fill % H);
     const bool one_chunk = c->head->active_seg_count == 0 ? false
                                                           : in_len <= c->head->block_size - c->head->input_buffer_fill;
-    const bool fuse = T != 0 && in_len > 0 && one_piece && one_chunk;
+    // a head block size that does not divide T runs off the end of tail_input: the reference's
+    // slice at :473 panics there (every non-power-of-two head size does, eventually)
+    const bool overflow = c->tail_input_fill + (one_piece ? in_len : 0) > T;
+    const bool fuse = T != 0 && in_len > 0 && one_piece && one_chunk && !overflow;
     fcb_epilogue epi;
     memset(&epi, 0, sizeof epi);
     if (fuse) {
@@ -564,7 +560,7 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
         const size_t remaining = in_len - processed;
         size_t n = H - (c->tail_input_fill % H); // :443-446
         if (remaining < n) n = remaining;
-        if (!fuse) { // :452-468
+        if (!fuse && c->precalculated_pos + n <= T) { // :452-468 (past T the reference panics at :456)
             long long total = (long long)C * (long long)n;
             k_add2<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
                 out + processed, (long long)out_stride, c->tail_precalculated0 + c->precalculated_pos,
@@ -573,6 +569,8 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
             FCB_CUDA(cudaGetLastError());
         }
         c->precalculated_pos += n; // :470
+        if (c->tail_input_fill + n > T) // slice index panic at :473
+            return fail(FCB_ERR_PANIC, "range end index %zu out of range for slice of length %zu", c->tail_input_fill + n, T);
         float *tin = c->tail_input[c->tail_in_sel];
         FCB_CUDA(cudaMemcpy2DAsync(tin + c->tail_input_fill, T * sizeof(float), in + processed, in_stride * sizeof(float),
                                    n * sizeof(float), C, cudaMemcpyDeviceToDevice, c->stream)); // :473-475

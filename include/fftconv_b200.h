@@ -137,6 +137,10 @@ typedef struct {
 int fcb_engine_ifft_ola(fcb_engine *e, size_t current, size_t fill, size_t n, int block_complete,
                         float *out_dev, size_t out_stride, const fcb_epilogue *epi);
 
+/* a device buffer [C][B] (channel stride B) owned by the engine, for callers that have no device
+ * allocator of their own: pass it as out_dev to ifft_ola, then fetch() it */
+float *fcb_engine_scratch(fcb_engine *e);
+
 /* device -> host copy of a planar result (stream-ordered, then synchronised) */
 int fcb_engine_fetch(fcb_engine *e, float *out_host, size_t host_stride, const float *src_dev,
                      size_t dev_stride, size_t n);

@@ -545,6 +545,8 @@ int orc_twostage_process(orc_twostage *c, const float *input, size_t in_len, flo
         if (remaining < processing) processing = remaining;
         size_t sum_begin = processed, sum_end = processed + processing;
 
+        if (c->precalculated_pos + processing > T || c->tail_input_fill + processing > T)
+            return ORC_PANIC; /* index / slice panic at :456 / :473 (head size not dividing T) */
         { /* :453-459 */
             size_t pp = c->precalculated_pos;
             for (size_t i = sum_begin; i < sum_end; i++) output[i] += c->tail_precalculated0[pp++];

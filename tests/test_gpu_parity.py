@@ -201,7 +201,7 @@ def test_clone_is_deep(F):
 
 
 @pytest.mark.parametrize("async_tail", [False, True])
-@pytest.mark.parametrize("H,L,sizes", [(64, 12000, [64]), (64, 12000, [17, 64, 5, 33]), (48, 5000, [48, 11]),
+@pytest.mark.parametrize("H,L,sizes", [(64, 12000, [64]), (64, 12000, [17, 64, 5, 33]), (16, 5000, [16, 11, 3]),
                                       (128, 2000, [128]), (32, 40, [32])])
 def test_twostage_vs_oracle(F, H, L, sizes, async_tail):
     """two-stage bookkeeping incl. ragged calls, non-power-of-two head, absent tail stages"""
@@ -217,6 +217,30 @@ def test_twostage_vs_oracle(F, H, L, sizes, async_tail):
         yt = oracle_np.truth_f64(x[c], irs[c])
         assert np.max(np.abs(y[c] - yo)) <= TOL * rms(yt)
         assert np.max(np.abs(y[c] - yt)) <= TOL * rms(yt)
+
+
+def test_twostage_non_power_of_two_head_panics_like_reference(F):
+    """head 48 does not divide T = 512: the reference's tail_input slice (src/fft_convolver.rs:473)
+    panics on the 11th block; engine and oracle must fail at the same call, agreeing until then."""
+    H, L = 48, 5000
+    h = oracle.gen_ir(0, 0, L)
+    x = oracle.gen_noise(0, 0, H * 12)
+    g, o = F.TwoStageFFTConvolver.init(h, H, L), oracle.TwoStageFFTConvolver.init(h, H, L)
+    assert g.tail_block_size == o.tail_block_size == 512
+    og, oo = np.zeros(H, np.float32), np.zeros(H, np.float32)
+    failed_at = None
+    for i in range(12):
+        blk = x[i * H:(i + 1) * H]
+        try:
+            o.process(blk, oo)
+        except oracle.OraclePanic:
+            with pytest.raises(F.ConvolutionPanic):
+                g.process(blk, og)
+            failed_at = i
+            break
+        g.process(blk, og)
+        assert np.max(np.abs(og - oo)) <= 2e-5 * max(rms(oo), 0.05)
+    assert failed_at == 10
 
 
 def test_twostage_config2_shape(F):
@@ -251,16 +275,12 @@ def test_crossfade_sequences_vs_oracle(F):
                 os_[c].update(irs[upd[i]][c])
         n_out = B if i % 9 else B - 13  # sometimes a short output: crossfader advances by out.len() only
         blk = np.ascontiguousarray(x[:, i * B:(i + 1) * B])
-        og[:] = 0
-        g.process(blk, og[:, :n_out] if n_out == B else np.ascontiguousarray(og[:, :n_out]))
-        if n_out != B:
-            tmp = np.zeros((C, n_out), np.float32)
-            # redo on a fresh buffer is not possible (state advanced): compare via the oracle only
+        og = np.zeros((C, n_out), np.float32)
+        g.process(blk, og)
         for c in range(C):
             oo[:] = 0
             os_[c].process(blk[c], oo[:n_out])
-            if n_out == B:
-                assert np.max(np.abs(og[c, :n_out] - oo[:n_out])) <= 2e-5 * max(rms(oo[:n_out]), 0.05), (i, c)
+            assert np.max(np.abs(og[c] - oo[:n_out])) <= 2e-5 * max(rms(oo[:n_out]), 0.05), (i, c)
             assert g.is_crossfading() == os_[c].is_crossfading()
             cnt, mix, appr, tgt = g.state()
             s = os_[c].crossfader

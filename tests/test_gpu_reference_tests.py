@@ -134,7 +134,10 @@ def test_twostage_equal(F):
         cb.process(blk, ob)
         orc.process(blk, oo)
         assert np.all(np.abs(oa - ob) < 1e-5)
-        assert np.max(np.abs(ob - oo)) <= TOL * max(rms(oo), 1e-2)
+        # sinusoid IR x sinusoid input: the output (RMS 0.067) is a small residue of large spectral
+        # peaks, so f32 pipelines differ by ~1e-5*RMS here; the reference's own bound for this
+        # fixture is 1e-5 absolute (src/tests.rs:155)
+        assert np.max(np.abs(ob - oo)) < 1e-5
 
 
 @pytest.mark.parametrize("kind", ["uniform", "twostage"])

@@ -87,6 +87,17 @@ def test_twostage_vs_truth_partial_calls():
     assert np.max(np.abs(yn - yt)) <= 1e-5 * rms(yt)
 
 
+def test_twostage_non_power_of_two_head_panics():
+    """head 48, T = 512: tail_input overflows on the 11th block (src/fft_convolver.rs:473)"""
+    h = oracle.gen_ir(0, 0, 5000)
+    o = oracle.TwoStageFFTConvolver.init(h, 48, 5000)
+    blk, out = np.zeros(48, np.float32), np.zeros(48, np.float32)
+    for _ in range(10):
+        o.process(blk, out)
+    with pytest.raises(oracle.OraclePanic):
+        o.process(blk, out)
+
+
 @pytest.mark.parametrize("head,L,T", [(128, 240000, 8192), (128, 220500, 8192), (64, 128000, 4096),
                                       (64, 12000, 1024), (1024, 1024, 1024), (512, 96000, 8192),
                                       (256, 48000, 4096), (512, 480000, 16384), (128, 140002, 4096),
