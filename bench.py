@@ -70,6 +70,31 @@ def synth_irs(chan0: int, nchan: int, update_index: int, length: int, chunk: int
 
 
 # ---------------------------------------------------------------------------------------------
+# multi-GPU plan: channels are independent, so ranks own disjoint contiguous channel ranges and
+# the data path has no collective; the only exchange is the max over ranks of the timings.
+def rank_channel_range(rank: int, world: int, channels_per_gpu: int) -> tuple[int, int]:
+    """global [first, last) channel indices owned by `rank` (weak scaling: fixed per-GPU count)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank outside world")
+    return rank * channels_per_gpu, (rank + 1) * channels_per_gpu
+
+
+def reduce_max(values, device=None):
+    """max over ranks of a list of floats (identity when torch.distributed is not initialised)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def aggregate_value(world: int, channels_per_gpu: int, steps: int, block: int, ms_max: float) -> float:
+    """whole-job channel-seconds of audio per wall second"""
+    return world * channels_per_gpu * steps * block / SAMPLE_RATE / (ms_max / 1000.0)
+
+
+# ---------------------------------------------------------------------------------------------
 def measured_peak_gbs() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -212,10 +237,12 @@ def run_b200(args) -> None:
         _lib.check(lib.fcb_tune(b"mac_impl", args.mac_impl))
     if args.mac_stages is not None:
         _lib.check(lib.fcb_tune(b"mac_stages", args.mac_stages))
+    if args.pipe_group is not None:
+        _lib.check(lib.fcb_tune(b"pipe_group", args.pipe_group))
 
     Cn, B = args.channels, args.block
     L = int(args.ir_seconds * SAMPLE_RATE)
-    chan0 = rank * Cn
+    chan0, _ = rank_channel_range(rank, world, Cn)
     stream = torch.cuda.Stream(device=local)
     t0 = time.time()
     irs = synth_irs(chan0, Cn, 0, L)
@@ -296,14 +323,9 @@ def run_b200(args) -> None:
     launches += lib.fcb_launch_count() - launches_e0
     barrier()
 
-    t = torch.tensor([ms, e2e_s * 1000.0], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
-
-    units = world * Cn * args.steps * B / SAMPLE_RATE  # channel-seconds of audio
-    value = units / (ms_max / 1000.0)
-    e2e_value = units / (e2e_ms_max / 1000.0)
+    ms_max, e2e_ms_max = reduce_max([ms, e2e_s * 1000.0], device=f"cuda:{local}")
+    value = aggregate_value(world, Cn, args.steps, B, ms_max)
+    e2e_value = aggregate_value(world, Cn, args.steps, B, e2e_ms_max)
 
     # ---- roofline of the dominant kernel (K2) --------------------------------------------------
     # algorithmic bytes per K2 launch: per channel 16*(S-1)*K read (IR rows + ring rows of segments
@@ -368,6 +390,7 @@ def main():
     ap.add_argument("--ir-seconds", type=float, default=2.0)
     ap.add_argument("--mac-impl", type=int, default=None)
     ap.add_argument("--mac-stages", type=int, default=None)
+    ap.add_argument("--pipe-group", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

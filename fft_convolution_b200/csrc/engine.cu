@@ -58,6 +58,12 @@ struct fcb_engine {
     float *stage = nullptr; // IR upload staging
     size_t stage_floats = 0;
     const float2 *tw = nullptr;
+    // end-to-end pipeline (fcb_engine_process_block_host): channel groups round-robin over streams
+    static constexpr int NPIPE = 4;
+    cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_done[NPIPE] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_start = nullptr;
+    std::vector<cudaEvent_t> pipe_in, pipe_out; // per group: input landed / output computed
 
     long long ir_stride() const { return shared_ir ? 0 : (long long)(S * B); }
     long long ring_stride() const { return (long long)(S * B); }
@@ -87,8 +93,9 @@ struct fcb_engine {
 
 template <int LOGB>
 static int launch_forward(const fcb_engine *e, const float *src, long long src_stride, int len, float2 *dst,
-                          long long dst_stride, int nseg, long long ntransforms)
+                          long long dst_stride, int nseg, long long ntransforms, cudaStream_t st = nullptr)
 {
+    if (!st) st = e->stream;
     using P = FftPlan<LOGB>;
     static bool attr_done = false;
     if (!attr_done && P::SMEM_BYTES > 48 * 1024) {
@@ -98,16 +105,17 @@ static int launch_forward(const fcb_engine *e, const float *src, long long src_s
     }
     if (ntransforms <= 0) return FCB_OK;
     long long grid = (ntransforms + P::TPB - 1) / P::TPB;
-    k_rfft_forward<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, e->stream>>>(src, src_stride, len, dst, dst_stride,
-                                                                               nseg, ntransforms, e->tw);
+    k_rfft_forward<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, st>>>(src, src_stride, len, dst, dst_stride, nseg,
+                                                                        ntransforms, e->tw);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;
 }
 
 template <int LOGB>
-static int launch_inverse(const fcb_engine *e, const IfftArgs &a)
+static int launch_inverse(const fcb_engine *e, const IfftArgs &a, cudaStream_t st = nullptr)
 {
+    if (!st) st = e->stream;
     using P = FftPlan<LOGB>;
     static bool attr_done = false;
     if (!attr_done && P::SMEM_BYTES > 48 * 1024) {
@@ -116,7 +124,7 @@ static int launch_inverse(const fcb_engine *e, const IfftArgs &a)
         attr_done = true;
     }
     long long grid = (a.nchan + P::TPB - 1) / P::TPB;
-    k_irfft_ola<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, e->stream>>>(a, e->tw);
+    k_irfft_ola<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, st>>>(a, e->tw);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;
@@ -175,10 +183,12 @@ extern "C" int fcb_profile_mac_read(double *total_ms, uint64_t *launches)
 // tuning knobs (fcb_tune): which K2 implementation, how many pipeline stages
 static std::atomic<int> g_mac_impl{0};   // 0 = auto (TMA pipeline for B >= 32), 1 = LDG, 2 = TMA
 static std::atomic<int> g_mac_stages{3}; // 2, 3, 4 or 6
+static std::atomic<int> g_pipe_group{512}; // channels per group of the end-to-end pipeline
 
 template <int B, int NST>
-static int launch_mac_bulk(const fcb_engine *e, const MacArgs &a)
+static int launch_mac_bulk(const fcb_engine *e, const MacArgs &a, cudaStream_t st)
 {
+    (void)e;
     using Cfg = MacBulkCfg<B>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -187,34 +197,35 @@ static int launch_mac_bulk(const fcb_engine *e, const MacArgs &a)
         attr_done = true;
     }
     long long groups = (a.nchan + Cfg::CPB - 1) / Cfg::CPB;
-    k_mac_bulk<B, NST><<<(unsigned)(groups * Cfg::TILES), 256, Cfg::smem_bytes(NST), e->stream>>>(a);
+    k_mac_bulk<B, NST><<<(unsigned)(groups * Cfg::TILES), 256, Cfg::smem_bytes(NST), st>>>(a);
     return FCB_OK;
 }
 
 template <int LOGB>
-static int launch_mac(const fcb_engine *e, const MacArgs &a)
+static int launch_mac(const fcb_engine *e, const MacArgs &a, cudaStream_t st = nullptr)
 {
     constexpr int B = 1 << LOGB;
+    if (!st) st = e->stream;
     if (a.active <= 1) { // no segment beyond 0: pre_multiplied = 0 (src/fft_convolver.rs:259)
-        FCB_CUDA(cudaMemsetAsync(a.premul, 0, (size_t)a.nchan * B * sizeof(float2), e->stream));
+        FCB_CUDA(cudaMemsetAsync(a.premul, 0, (size_t)a.nchan * B * sizeof(float2), st));
         return FCB_OK;
     }
     const int impl = g_mac_impl.load();
     cudaEvent_t prof_stop = nullptr;
-    const bool profiled = prof_before(e->stream, &prof_stop) != nullptr;
+    const bool profiled = prof_before(st, &prof_stop) != nullptr;
     if constexpr (B == 1) {
         unsigned grid = (unsigned)((a.nchan + 255) / 256);
-        k_mac_b1<<<grid, 256, 0, e->stream>>>(a);
+        k_mac_b1<<<grid, 256, 0, st>>>(a);
     } else {
         bool bulk = impl == 2 || (impl == 0 && B >= 32);
         if constexpr (B < 4) bulk = false;
         if (bulk) {
             if constexpr (B >= 4) {
                 switch (g_mac_stages.load()) {
-                case 2: FCB_TRY((launch_mac_bulk<B, 2>(e, a))); break;
-                case 4: FCB_TRY((launch_mac_bulk<B, 4>(e, a))); break;
-                case 6: FCB_TRY((launch_mac_bulk<B, 6>(e, a))); break;
-                default: FCB_TRY((launch_mac_bulk<B, 3>(e, a))); break;
+                case 2: FCB_TRY((launch_mac_bulk<B, 2>(e, a, st))); break;
+                case 4: FCB_TRY((launch_mac_bulk<B, 4>(e, a, st))); break;
+                case 6: FCB_TRY((launch_mac_bulk<B, 6>(e, a, st))); break;
+                default: FCB_TRY((launch_mac_bulk<B, 3>(e, a, st))); break;
                 }
             }
         } else {
@@ -223,10 +234,10 @@ static int launch_mac(const fcb_engine *e, const MacArgs &a)
             constexpr int TILES = ROW4 / TX;
             constexpr int CPB = 256 / TX;
             long long groups = (a.nchan + CPB - 1) / CPB;
-            k_mac_v4<B, 8><<<(unsigned)(groups * TILES), 256, 0, e->stream>>>(a);
+            k_mac_v4<B, 8><<<(unsigned)(groups * TILES), 256, 0, st>>>(a);
         }
     }
-    if (profiled) cudaEventRecord(prof_stop, e->stream);
+    if (profiled) cudaEventRecord(prof_stop, st);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;
@@ -237,6 +248,7 @@ extern "C" int fcb_tune(const char *key, int value)
     if (!key) return fail(FCB_ERR_ARG, "fcb_tune: NULL key");
     if (!strcmp(key, "mac_impl") && value >= 0 && value <= 2) g_mac_impl = value;
     else if (!strcmp(key, "mac_stages") && (value == 2 || value == 3 || value == 4 || value == 6)) g_mac_stages = value;
+    else if (!strcmp(key, "pipe_group") && value >= 1) g_pipe_group = value;
     else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);
     return FCB_OK;
 }
@@ -342,6 +354,13 @@ extern "C" void fcb_engine_destroy(fcb_engine *e)
     cudaFree(e->inbuf);
     cudaFree(e->scratch);
     cudaFree(e->stage);
+    for (int i = 0; i < fcb_engine::NPIPE; i++) {
+        if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]);
+        if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]);
+    }
+    if (e->pipe_start) cudaEventDestroy(e->pipe_start);
+    for (cudaEvent_t ev : e->pipe_in) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->pipe_out) cudaEventDestroy(ev);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -560,6 +579,84 @@ extern "C" int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, 
                                                           (long long)e->C)));
     FCB_TRY(fcb_engine_mac(e, current, active));
     return fcb_engine_ifft_ola(e, current, 0, e->B, 1, out_dev, out_stride, epi);
+}
+
+// Full block, host buffers, pipelined: the channels are cut into groups; each group's pinned H2D
+// copy, K1, K2, K3 and D2H copy are queued on one of NPIPE streams, so the PCIe copies of one
+// group overlap the HBM-bound K2 of another.  Groups are independent channels, so the result is
+// the one the unpipelined sequence gives.  Returns after every group's output is in host memory.
+extern "C" int fcb_engine_process_block_host(fcb_engine *e, const float *in, size_t in_stride, float *out,
+                                             size_t out_stride, size_t current, size_t active, size_t group_channels)
+{
+    FCB_TRY(check_sched(e, current, active, "process_block_host"));
+    if (!in || !out) return fail(FCB_ERR_ARG, "process_block_host: NULL argument");
+    if (active == 0) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(e->device));
+    if (!e->pipe_start) { // created on first use, outside the steady state
+        FCB_CUDA(cudaEventCreateWithFlags(&e->pipe_start, cudaEventDisableTiming));
+        for (int i = 0; i < fcb_engine::NPIPE; i++) {
+            FCB_CUDA(cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking));
+            FCB_CUDA(cudaEventCreateWithFlags(&e->pipe_done[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t B = e->B, C = e->C;
+    size_t G = group_channels ? group_channels : (size_t)g_pipe_group.load();
+    if (G > C) G = C;
+    const size_t ngroups = (C + G - 1) / G;
+    while (e->pipe_in.size() < ngroups) { // grows on the first call with this grouping only
+        cudaEvent_t a = nullptr, b = nullptr;
+        FCB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        FCB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        e->pipe_in.push_back(a);
+        e->pipe_out.push_back(b);
+    }
+    // stream roles: pipe[0] = all H2D copies (run ahead at PCIe speed), pipe[1] = all D2H copies,
+    // pipe[2..] = compute, groups alternating so one group's K2 tail overlaps the next group's head
+    cudaStream_t s_in = e->pipe[0], s_out = e->pipe[1];
+    FCB_CUDA(cudaEventRecord(e->pipe_start, e->stream));
+    for (int i = 0; i < fcb_engine::NPIPE; i++) FCB_CUDA(cudaStreamWaitEvent(e->pipe[i], e->pipe_start, 0));
+    for (size_t g = 0; g < ngroups; g++) {
+        const size_t c0 = g * G, nc = (C - c0) < G ? (C - c0) : G;
+        FCB_CUDA(cudaMemcpy2DAsync(e->inbuf + c0 * B, B * sizeof(float), in + c0 * in_stride, in_stride * sizeof(float),
+                                   B * sizeof(float), nc, cudaMemcpyHostToDevice, s_in));
+        FCB_CUDA(cudaEventRecord(e->pipe_in[g], s_in));
+    }
+    for (size_t g = 0; g < ngroups; g++) {
+        cudaStream_t st = e->pipe[2 + g % (fcb_engine::NPIPE - 2)];
+        const size_t c0 = g * G, nc = (C - c0) < G ? (C - c0) : G;
+        float *d_in = e->inbuf + c0 * B, *d_out = e->scratch + c0 * B;
+        FCB_CUDA(cudaStreamWaitEvent(st, e->pipe_in[g], 0));
+        FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, d_in, (long long)B, (int)B,
+                                                              e->ring + c0 * e->ring_stride() + current * B,
+                                                              e->ring_stride(), 1, (long long)nc, st)));
+        MacArgs m{e->ir + (e->shared_ir ? 0 : c0) * (long long)(e->S * B), e->ir_stride(),
+                  e->ring + c0 * e->ring_stride(), e->ring_stride(), e->premul + c0 * B, (int)current, (int)active,
+                  (long long)nc};
+        FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_mac<LB>(e, m, st)));
+        IfftArgs a{};
+        a.ring_cur = e->ring + c0 * e->ring_stride() + current * B;
+        a.ring_stride = e->ring_stride();
+        a.ir0 = e->ir + (e->shared_ir ? 0 : c0) * (long long)(e->S * B);
+        a.ir_stride = e->ir_stride();
+        a.premul = e->premul + c0 * B;
+        a.overlap = e->overlap + c0 * B;
+        a.out = d_out;
+        a.out_stride = (long long)B;
+        a.fill = 0;
+        a.n = (int)B;
+        a.block_complete = 1;
+        a.nchan = (long long)nc;
+        FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_inverse<LB>(e, a, st)));
+        FCB_CUDA(cudaEventRecord(e->pipe_out[g], st));
+        FCB_CUDA(cudaStreamWaitEvent(s_out, e->pipe_out[g], 0));
+        FCB_CUDA(cudaMemcpy2DAsync(out + c0 * out_stride, out_stride * sizeof(float), d_out, B * sizeof(float),
+                                   B * sizeof(float), nc, cudaMemcpyDeviceToHost, s_out));
+    }
+    // the last D2H completes after every compute stream it waited on
+    FCB_CUDA(cudaEventRecord(e->pipe_done[1], s_out));
+    FCB_CUDA(cudaStreamWaitEvent(e->stream, e->pipe_done[1], 0));
+    FCB_CUDA(cudaStreamSynchronize(e->stream));
+    return FCB_OK;
 }
 
 // ---- debug readback in the reference layout (K = B+1 interleaved complex) ------------------------

@@ -229,6 +229,14 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
         fcb_epilogue e = offset_epilogue(epi, processed);
         float *dst = host ? c->d_io : out + processed;
         const size_t dst_stride = host ? B : out_stride;
+        if (host && was_empty && complete && c->C >= 1024) {
+            // many channels, whole block, host buffers: overlap the PCIe copies with K2
+            FCB_TRY(fcb_engine_process_block_host(c->eng, in + processed, in_stride, out + processed, out_stride,
+                                                  c->current, c->active_seg_count, 0));
+            c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1; // :301-305
+            processed += n;
+            continue;
+        }
         if (!host && was_empty && complete) {
             // whole block resident on the device: K1 reads the caller's buffer directly
             FCB_TRY(fcb_engine_process_block_dev(c->eng, in + processed, in_stride, dst, dst_stride, c->current,

@@ -53,7 +53,8 @@ uint64_t fcb_launch_count(void);
 int fcb_device_count(void);
 
 /* tuning knobs for benchmarking sweeps: "mac_impl" (0 auto, 1 LDG kernel, 2 TMA pipeline),
- * "mac_stages" (2, 3, 4, 6 pipeline stages of 32 KB) */
+ * "mac_stages" (2, 3, 4, 6 pipeline stages of 32 KB), "pipe_group" (channels per group of the
+ * end-to-end copy/compute pipeline, default 512) */
 int fcb_tune(const char *key, int value);
 
 /* live timing of the K2 launches: while enabled every K2 launch is bracketed by CUDA events on
@@ -149,6 +150,11 @@ int fcb_engine_fetch(fcb_engine *e, float *out_host, size_t host_stride, const f
 int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, size_t in_stride, float *out_dev,
                                  size_t out_stride, size_t current, size_t active,
                                  const fcb_epilogue *epi);
+
+/* the same with HOST buffers (pinned for full overlap), pipelined over channel groups of
+ * `group_channels` (0 = 512) on internal streams so the PCIe copies overlap K2; synchronous */
+int fcb_engine_process_block_host(fcb_engine *e, const float *in, size_t in_stride, float *out,
+                                  size_t out_stride, size_t current, size_t active, size_t group_channels);
 
 /* debug / test readback of device state in the reference's layout (K = B+1 interleaved complex) */
 int fcb_engine_read_ir_segment(fcb_engine *e, size_t chan, size_t seg, float *out_2k);

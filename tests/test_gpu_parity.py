@@ -177,6 +177,23 @@ def test_batched_channels_match_mono(F):
         assert np.max(np.abs(yb[c] - yo)) <= TOL * rms(yo)
 
 
+def test_pipelined_host_path_large_batch(F):
+    """>= 1024 channels with whole-block host calls take the copy/compute pipeline over channel
+    groups (fcb_engine_process_block_host); it must give the bits of the plain path."""
+    from fft_convolution_b200 import _lib
+    C, B, L = 1024 + 37, 64, 200
+    irs = np.stack([oracle.gen_ir(c % 5, c // 5, L) for c in range(C)])
+    x = np.stack([oracle.gen_noise(c, 0, B * 9) for c in range(C)])
+    _lib.check(_lib.load().fcb_tune(b"pipe_group", 200))
+    yb = _run(F.FFTConvolver.init(irs, B, L), x, [B, B, 40, 24, B])  # mixes pipelined and chunked calls
+    _lib.check(_lib.load().fcb_tune(b"pipe_group", 512))
+    for c in (0, 199, 200, 511, 1023, 1024, C - 1):
+        ym = _run(F.FFTConvolver.init(irs[c], B, L), x[c], [B, B, 40, 24, B])
+        assert np.array_equal(yb[c], ym), c
+        yo = _run(oracle.FFTConvolver.init(irs[c], B, L), x[c], [B, B, 40, 24, B])
+        assert np.max(np.abs(yb[c] - yo)) <= TOL * rms(yo)
+
+
 def test_shared_ir_matches_per_channel_ir(F):
     C, B, L = 5, 64, 700
     h = oracle.gen_ir(9, 0, L)
