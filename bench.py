@@ -157,6 +157,14 @@ class ClockSampler(threading.Thread):
 _CPU_DATA: dict = {}
 
 
+def host_threads() -> int:
+    """all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the OS)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_run(channels: int, block: int, ir_len: int, calls: int, threads: int) -> tuple[float, float]:
     """CPU restatement of the reference algorithm (oracle/fftconv_oracle.c), one convolver per
     channel, channels over `threads` host threads; returns (channel-sec/sec, seconds of the block
@@ -178,7 +186,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     import oracle
-    threads = oracle.load().lib.orc_max_threads()
+    threads = host_threads()
     ir_len = int(args.ir_seconds * SAMPLE_RATE)
     channels = max(threads * 4, 8)
     calls = 94  # ~1 s of audio per channel per step
@@ -350,8 +358,8 @@ def run_b200(args) -> None:
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            import oracle  # cpu_baseline leg only
-            threads = oracle.load().lib.orc_max_threads()
+            import oracle  # noqa: F401  (cpu_baseline leg only)
+            threads = host_threads()
             ch, calls = max(threads * 4, 8), 188
             v, secs = cpu_port_run(ch, B, L, calls, threads)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

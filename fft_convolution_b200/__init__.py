@@ -2,8 +2,10 @@
 trait surface of Sin-tel/fft-convolution.  CUDA only (sm_100a); see DESIGN.md."""
 from ._lib import ConvolutionPanic, CudaError, NotYetImplemented, load as load_library  # noqa: F401
 from .convolvers import (  # noqa: F401
-    CrossfadeConvolver, FFTConvolver, TwoStageFFTConvolver, compute_tail_block_size,
+    CrossfadeConvolver, FFTConvolver, MimoConvolver, TwoStageFFTConvolver, compute_tail_block_size,
+    mimo_segment_range,
 )
 
-__all__ = ["FFTConvolver", "TwoStageFFTConvolver", "CrossfadeConvolver", "compute_tail_block_size",
+__all__ = ["FFTConvolver", "TwoStageFFTConvolver", "CrossfadeConvolver", "MimoConvolver",
+           "compute_tail_block_size", "mimo_segment_range",
            "ConvolutionPanic", "NotYetImplemented", "CudaError", "load_library"]

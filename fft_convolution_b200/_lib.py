@@ -36,6 +36,12 @@ class EngineDesc(C.Structure):
                 ("shared_ir", C.c_int), ("device", C.c_int), ("stream", C.c_void_p)]
 
 
+class MimoDesc(C.Structure):
+    _fields_ = [("n_in", C.c_size_t), ("n_out", C.c_size_t), ("n_streams", C.c_size_t),
+                ("block_size", C.c_size_t), ("max_response_length", C.c_size_t),
+                ("shard_index", C.c_size_t), ("shard_count", C.c_size_t), ("device", C.c_int), ("stream", C.c_void_p)]
+
+
 class Epilogue(C.Structure):
     _fields_ = [("add0", C.c_void_p), ("add1", C.c_void_p), ("add_stride", C.c_size_t),
                 ("mix_other", C.c_void_p), ("mix_stride", C.c_size_t), ("gains", C.c_void_p)]
@@ -117,6 +123,19 @@ SIGNATURES = {
     "fcb_crossfade_is_crossfading": (_i, [_vp]),
     "fcb_crossfade_sync": (_i, [_vp]),
     "fcb_crossfade_state": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(_i), C.POINTER(_i)]),
+    "fcb_mimo_create": (_i, [C.POINTER(MimoDesc), _pp]),
+    "fcb_mimo_destroy": (None, [_vp]),
+    "fcb_mimo_set_ir": (_i, [_vp, _vp, _sz]),
+    "fcb_mimo_reset": (_i, [_vp]),
+    "fcb_mimo_partial_dev": (_i, [_vp, _vp, _sz]),
+    "fcb_mimo_conv_buffer": (_vp, [_vp, C.POINTER(_sz)]),
+    "fcb_mimo_finish_dev": (_i, [_vp, _vp, _sz]),
+    "fcb_mimo_process": (_i, [_vp, _vp, _vp]),
+    "fcb_mimo_sync": (_i, [_vp]),
+    "fcb_mimo_stream": (_vp, [_vp]),
+    "fcb_mimo_block_size": (_sz, [_vp]),
+    "fcb_mimo_seg_count": (_sz, [_vp]),
+    "fcb_mimo_segment_range": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
 }
 
 _lib = None

@@ -10,8 +10,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 SO = PKG / "libfftconv_b200.so"
-SOURCES = ["engine.cu", "host_mirror.cu"]
-HEADERS = ["common.cuh", "fft_kernels.cuh", "mac_kernels.cuh", "../../include/fftconv_b200.h"]
+SOURCES = ["engine.cu", "host_mirror.cu", "mimo.cu"]
+HEADERS = ["common.cuh", "engine_internal.cuh", "fft_kernels.cuh", "mac_kernels.cuh", "../../include/fftconv_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -260,6 +260,86 @@ class CrossfadeConvolver(_Base):
         return counter.value, mix.value, bool(appr.value), tgt.value
 
 
+def mimo_segment_range(seg_count: int, shard_index: int, shard_count: int) -> tuple[int, int]:
+    """IR segments [lo, hi) owned by shard `shard_index` of `shard_count` (the C side's rule)."""
+    return seg_count * shard_index // shard_count, seg_count * (shard_index + 1) // shard_count
+
+
+class MimoConvolver:
+    """OUT x IN convolution matrix: y_out = sum_in FFTConvolver(h[out][in]).process(x_in), built on
+    the same K1/K2/K3 kernels with the IN input rings shared by all outputs.  `responses` is
+    [OUT, IN, len].  With shard_count > 1 this object owns one contiguous range of IR segments and
+    its partial spectra must be all-reduced across shards (see distributed.ShardedMimoConvolver)."""
+
+    def __init__(self, handle, n_in, n_out, n_streams):
+        self._h, self.n_in, self.n_out, self.n_streams = handle, n_in, n_out, n_streams
+
+    @classmethod
+    def init(cls, responses, block_size: int, max_response_length: int, *, n_streams: int = 1,
+             shard_index: int = 0, shard_count: int = 1, device: int = 0, stream=None) -> "MimoConvolver":
+        lib = _lib.load()
+        _lib.require_gpu()
+        r = np.ascontiguousarray(responses, dtype=np.float32)
+        if r.ndim != 3:
+            raise ValueError("responses must be [out, in, len]")
+        n_out, n_in, length = r.shape
+        d = _lib.MimoDesc(n_in, n_out, n_streams, block_size, max_response_length, shard_index, shard_count,
+                          device, stream)
+        h = C.c_void_p()
+        check(lib.fcb_mimo_create(C.byref(d), C.byref(h)))
+        self = cls(h, n_in, n_out, n_streams)
+        check(lib.fcb_mimo_set_ir(h, _ptr(r), length))
+        check(lib.fcb_mimo_sync(h))
+        return self
+
+    block_size = property(lambda s: _lib.load().fcb_mimo_block_size(s._h))
+    seg_count = property(lambda s: _lib.load().fcb_mimo_seg_count(s._h))
+
+    @property
+    def segment_range(self):
+        lo, hi = C.c_size_t(), C.c_size_t()
+        check(_lib.load().fcb_mimo_segment_range(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def process(self, input, output) -> None:
+        """input [NS*IN, B] -> output [NS*OUT, B] (host arrays, one full block)."""
+        x = np.ascontiguousarray(input, dtype=np.float32)
+        B = self.block_size
+        if x.shape != (self.n_streams * self.n_in, B) or output.shape != (self.n_streams * self.n_out, B):
+            raise ValueError("MimoConvolver.process expects one full block: [NS*IN, B] -> [NS*OUT, B]")
+        if not (output.dtype == np.float32 and output.flags.c_contiguous):
+            raise TypeError("output must be a C-contiguous float32 ndarray")
+        check(_lib.load().fcb_mimo_process(self._h, _ptr(x), _ptr(output)))
+
+    def reset(self) -> None:
+        check(_lib.load().fcb_mimo_reset(self._h))
+
+    def partial_dev(self, in_ptr: int, in_stride: int) -> None:
+        check(_lib.load().fcb_mimo_partial_dev(self._h, in_ptr, in_stride))
+
+    def conv_buffer(self) -> tuple[int, int]:
+        n = C.c_size_t()
+        p = _lib.load().fcb_mimo_conv_buffer(self._h, C.byref(n))
+        return p, n.value
+
+    def finish_dev(self, out_ptr: int, out_stride: int) -> None:
+        check(_lib.load().fcb_mimo_finish_dev(self._h, out_ptr, out_stride))
+
+    def sync(self) -> None:
+        check(_lib.load().fcb_mimo_sync(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().fcb_mimo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def compute_tail_block_size(head_len: int, response_len: int) -> int:
     """src/fft_convolver.rs:534-540 (f32 arithmetic)."""
     return _lib.load().fcb_compute_tail_block_size(head_len, response_len)

@@ -8,9 +8,7 @@
 #include <mutex>
 #include <vector>
 
-#include "common.cuh"
-#include "fft_kernels.cuh"
-#include "mac_kernels.cuh"
+#include "engine_internal.cuh"
 
 namespace fcb {
 thread_local std::string g_last_error = "";
@@ -20,7 +18,7 @@ std::atomic<uint64_t> g_launches{0};
 static std::mutex g_tw_mutex;
 static std::map<std::pair<int, size_t>, float2 *> g_tw;
 
-static int get_twiddles(int device, size_t N, const float2 **out)
+int get_twiddles(int device, size_t N, const float2 **out)
 {
     std::lock_guard<std::mutex> lock(g_tw_mutex);
     auto key = std::make_pair(device, N);
@@ -92,10 +90,9 @@ struct fcb_engine {
     }
 
 template <int LOGB>
-static int launch_forward(const fcb_engine *e, const float *src, long long src_stride, int len, float2 *dst,
-                          long long dst_stride, int nseg, long long ntransforms, cudaStream_t st = nullptr)
+static int launch_forward_t(const float2 *tw, cudaStream_t st, const float *src, long long src_stride, int len,
+                            float2 *dst, long long dst_stride, int nseg, long long ntransforms)
 {
-    if (!st) st = e->stream;
     using P = FftPlan<LOGB>;
     static bool attr_done = false;
     if (!attr_done && P::SMEM_BYTES > 48 * 1024) {
@@ -106,16 +103,15 @@ static int launch_forward(const fcb_engine *e, const float *src, long long src_s
     if (ntransforms <= 0) return FCB_OK;
     long long grid = (ntransforms + P::TPB - 1) / P::TPB;
     k_rfft_forward<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, st>>>(src, src_stride, len, dst, dst_stride, nseg,
-                                                                        ntransforms, e->tw);
+                                                                        ntransforms, tw);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;
 }
 
 template <int LOGB>
-static int launch_inverse(const fcb_engine *e, const IfftArgs &a, cudaStream_t st = nullptr)
+static int launch_inverse_t(const float2 *tw, cudaStream_t st, const IfftArgs &a)
 {
-    if (!st) st = e->stream;
     using P = FftPlan<LOGB>;
     static bool attr_done = false;
     if (!attr_done && P::SMEM_BYTES > 48 * 1024) {
@@ -124,7 +120,7 @@ static int launch_inverse(const fcb_engine *e, const IfftArgs &a, cudaStream_t s
         attr_done = true;
     }
     long long grid = (a.nchan + P::TPB - 1) / P::TPB;
-    k_irfft_ola<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, st>>>(a, e->tw);
+    k_irfft_ola<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, st>>>(a, tw);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;
@@ -186,9 +182,8 @@ static std::atomic<int> g_mac_stages{3}; // 2, 3, 4 or 6
 static std::atomic<int> g_pipe_group{512}; // channels per group of the end-to-end pipeline
 
 template <int B, int NST>
-static int launch_mac_bulk(const fcb_engine *e, const MacArgs &a, cudaStream_t st)
+static int launch_mac_bulk(const MacArgs &a, cudaStream_t st)
 {
-    (void)e;
     using Cfg = MacBulkCfg<B>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -202,11 +197,10 @@ static int launch_mac_bulk(const fcb_engine *e, const MacArgs &a, cudaStream_t s
 }
 
 template <int LOGB>
-static int launch_mac(const fcb_engine *e, const MacArgs &a, cudaStream_t st = nullptr)
+static int launch_mac_t(const MacArgs &a, cudaStream_t st)
 {
     constexpr int B = 1 << LOGB;
-    if (!st) st = e->stream;
-    if (a.active <= 1) { // no segment beyond 0: pre_multiplied = 0 (src/fft_convolver.rs:259)
+    if (a.seg_hi <= a.seg_lo) { // no segment to accumulate: pre_multiplied = 0 (src/fft_convolver.rs:259)
         FCB_CUDA(cudaMemsetAsync(a.premul, 0, (size_t)a.nchan * B * sizeof(float2), st));
         return FCB_OK;
     }
@@ -222,10 +216,10 @@ static int launch_mac(const fcb_engine *e, const MacArgs &a, cudaStream_t st = n
         if (bulk) {
             if constexpr (B >= 4) {
                 switch (g_mac_stages.load()) {
-                case 2: FCB_TRY((launch_mac_bulk<B, 2>(e, a, st))); break;
-                case 4: FCB_TRY((launch_mac_bulk<B, 4>(e, a, st))); break;
-                case 6: FCB_TRY((launch_mac_bulk<B, 6>(e, a, st))); break;
-                default: FCB_TRY((launch_mac_bulk<B, 3>(e, a, st))); break;
+                case 2: FCB_TRY((launch_mac_bulk<B, 2>(a, st))); break;
+                case 4: FCB_TRY((launch_mac_bulk<B, 4>(a, st))); break;
+                case 6: FCB_TRY((launch_mac_bulk<B, 6>(a, st))); break;
+                default: FCB_TRY((launch_mac_bulk<B, 3>(a, st))); break;
                 }
             }
         } else {
@@ -242,6 +236,42 @@ static int launch_mac(const fcb_engine *e, const MacArgs &a, cudaStream_t st = n
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;
 }
+
+template <int LOGB>
+static int launch_forward(const fcb_engine *e, const float *src, long long src_stride, int len, float2 *dst,
+                          long long dst_stride, int nseg, long long ntransforms, cudaStream_t st = nullptr)
+{
+    return launch_forward_t<LOGB>(e->tw, st ? st : e->stream, src, src_stride, len, dst, dst_stride, nseg, ntransforms);
+}
+template <int LOGB>
+static int launch_inverse(const fcb_engine *e, const IfftArgs &a, cudaStream_t st = nullptr)
+{
+    return launch_inverse_t<LOGB>(e->tw, st ? st : e->stream, a);
+}
+template <int LOGB>
+static int launch_mac(const fcb_engine *e, const MacArgs &a, cudaStream_t st = nullptr)
+{
+    return launch_mac_t<LOGB>(a, st ? st : e->stream);
+}
+
+namespace fcb {
+int run_forward(int logb, const float2 *tw, cudaStream_t st, const float *src, long long src_stride, int len,
+                float2 *dst, long long dst_stride, int nseg, long long ntransforms)
+{
+    FCB_DISPATCH_LOGB(logb, FCB_TRY(launch_forward_t<LB>(tw, st, src, src_stride, len, dst, dst_stride, nseg, ntransforms)));
+    return FCB_OK;
+}
+int run_mac(int logb, cudaStream_t st, const MacArgs &a)
+{
+    FCB_DISPATCH_LOGB(logb, FCB_TRY(launch_mac_t<LB>(a, st)));
+    return FCB_OK;
+}
+int run_inverse(int logb, const float2 *tw, cudaStream_t st, const IfftArgs &a)
+{
+    FCB_DISPATCH_LOGB(logb, FCB_TRY(launch_inverse_t<LB>(tw, st, a)));
+    return FCB_OK;
+}
+} // namespace fcb
 
 extern "C" int fcb_tune(const char *key, int value)
 {
@@ -522,7 +552,10 @@ extern "C" int fcb_engine_mac(fcb_engine *e, size_t current, size_t active)
     FCB_TRY(check_sched(e, current, active, "mac"));
     if (active == 0) return FCB_OK;
     FCB_CUDA(cudaSetDevice(e->device));
-    MacArgs a{e->ir, e->ir_stride(), e->ring, e->ring_stride(), e->premul, (int)current, (int)active, (long long)e->C};
+    MacArgs a{};
+    a.ir = e->ir; a.ir_stride = e->ir_stride(); a.ring = e->ring; a.ring_stride = e->ring_stride();
+    a.premul = e->premul; a.current = (int)current; a.active = (int)active; a.nchan = (long long)e->C;
+    a.seg_lo = 1; a.seg_hi = (int)active; a.ir_seg0 = 0;
     FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_mac<LB>(e, a)));
     return FCB_OK;
 }
@@ -629,9 +662,11 @@ extern "C" int fcb_engine_process_block_host(fcb_engine *e, const float *in, siz
         FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, d_in, (long long)B, (int)B,
                                                               e->ring + c0 * e->ring_stride() + current * B,
                                                               e->ring_stride(), 1, (long long)nc, st)));
-        MacArgs m{e->ir + (e->shared_ir ? 0 : c0) * (long long)(e->S * B), e->ir_stride(),
-                  e->ring + c0 * e->ring_stride(), e->ring_stride(), e->premul + c0 * B, (int)current, (int)active,
-                  (long long)nc};
+        MacArgs m{};
+        m.ir = e->ir + (e->shared_ir ? 0 : c0) * (long long)(e->S * B); m.ir_stride = e->ir_stride();
+        m.ring = e->ring + c0 * e->ring_stride(); m.ring_stride = e->ring_stride();
+        m.premul = e->premul + c0 * B; m.current = (int)current; m.active = (int)active; m.nchan = (long long)nc;
+        m.seg_lo = 1; m.seg_hi = (int)active; m.ir_seg0 = 0;
         FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_mac<LB>(e, m, st)));
         IfftArgs a{};
         a.ring_cur = e->ring + c0 * e->ring_stride() + current * B;

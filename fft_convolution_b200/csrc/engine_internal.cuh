@@ -1,0 +1,19 @@
+// engine_internal.cuh — launch entry points shared by engine.cu and mimo.cu (not part of the C ABI)
+#pragma once
+
+#include "common.cuh"
+#include "fft_kernels.cuh"
+#include "mac_kernels.cuh"
+
+namespace fcb {
+
+// twiddle table tw[t] = exp(-2 pi i t / N), t < N (device memory, cached per (device, N))
+int get_twiddles(int device, size_t N, const float2 **out);
+
+// K1/K5, K2, K3 for block size 2^logb on stream st
+int run_forward(int logb, const float2 *tw, cudaStream_t st, const float *src, long long src_stride, int len,
+                float2 *dst, long long dst_stride, int nseg, long long ntransforms);
+int run_mac(int logb, cudaStream_t st, const MacArgs &a);
+int run_inverse(int logb, const float2 *tw, cudaStream_t st, const IfftArgs &a);
+
+} // namespace fcb

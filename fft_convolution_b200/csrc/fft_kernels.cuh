@@ -234,7 +234,7 @@ k_rfft_forward(const float *__restrict__ src, long long src_stride, int len, flo
 struct IfftArgs {
     const float2 *ring_cur; // ring + current*B, channel stride ring_stride
     long long ring_stride;
-    const float2 *ir0;      // IR segment 0, channel stride ir_stride (0 when shared)
+    const float2 *ir0;      // IR segment 0, channel stride ir_stride (0 when shared); NULL = conv is `premul` as is
     long long ir_stride;
     const float2 *premul;   // [C][B]
     float *overlap;         // [C][B]
@@ -262,7 +262,9 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
     for (int e = 0; e < E; e++) {
         int k = tid + e * T;
         float2 v = make_float2(0.f, 0.f);
-        if (live) {
+        if (live && !a.ir0) {
+            v = a.premul[c * B + k]; // conv already complete (MIMO: summed over inputs and shards)
+        } else if (live) {
             float2 x = a.ring_cur[c * a.ring_stride + k];
             float2 h = __ldg(&a.ir0[c * a.ir_stride + k]);
             float2 p = a.premul[c * B + k];

@@ -42,13 +42,26 @@ __device__ __forceinline__ void cmac_ref(float &ar, float &ai, float xr, float x
 }
 
 struct MacArgs {
-    const float2 *ir;   // [C][S][B] packed rows (channel stride 0 when the IR is shared)
-    long long ir_stride;
-    const float2 *ring; // [C][S][B]
+    const float2 *ir;   // packed rows [ir channel][rows][B]; row r holds IR segment ir_seg0 + r
+    long long ir_stride;   // per IR channel (0 when one IR is shared by every channel)
+    const float2 *ring; // [ring channel][S][B]
     long long ring_stride;
     float2 *premul;     // [C][B]
     int current, active;
     long long nchan;
+    // segments accumulated: i in [seg_lo, seg_hi).  FFTConvolver: [1, active).  An IR-partition
+    // shard of the MIMO matrix owns a sub-range and stores only those rows (ir_seg0 = first stored).
+    int seg_lo, seg_hi, ir_seg0;
+    // work channel c -> IR channel (c % ir_mod, 0 = identity) and ring channel
+    // ((c / ring_div) * ring_mul + c % ring_mod, ring_div == 0 = identity).  The MIMO matrix uses
+    // c = (stream*OUT + out)*IN + in  ->  IR (out, in), ring (stream, in).
+    long long ir_mod, ring_div, ring_mul, ring_mod;
+
+    __host__ __device__ long long ir_chan(long long c) const { return ir_mod ? c % ir_mod : c; }
+    __host__ __device__ long long ring_chan(long long c) const
+    {
+        return ring_div ? (c / ring_div) * ring_mul + c % ring_mod : c;
+    }
 };
 
 // One thread owns V = 2 adjacent bins (one float4) of one channel and walks all segments.
@@ -68,14 +81,15 @@ k_mac_v4(MacArgs a)
     const long long c = grp * CPB + ty;
     if (c >= a.nchan) return;
     const int t4 = tile * TX + tx; // float4 index within the row
-    const float4 *ir = reinterpret_cast<const float4 *>(a.ir + c * a.ir_stride) + t4;
-    const float4 *rg = reinterpret_cast<const float4 *>(a.ring + c * a.ring_stride) + t4;
+    // IR row r holds segment ir_seg0 + r: bias the base so that `ir + i*ROW4` is segment i
+    const float4 *ir = reinterpret_cast<const float4 *>(a.ir + a.ir_chan(c) * a.ir_stride) + t4 - (long long)a.ir_seg0 * ROW4;
+    const float4 *rg = reinterpret_cast<const float4 *>(a.ring + a.ring_chan(c) * a.ring_stride) + t4;
     const bool packed = (t4 == 0);
-    const int cur = a.current, act = a.active;
+    const int cur = a.current, act = a.active, hi = a.seg_hi;
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int i = 1;
-    for (; i + U <= act; i += U) {
+    int i = a.seg_lo;
+    for (; i + U <= hi; i += U) {
         float4 h[U], x[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -89,7 +103,7 @@ k_mac_v4(MacArgs a)
             cmac_ref(acc.z, acc.w, h[u].z, h[u].w, x[u].z, x[u].w, false);
         }
     }
-    for (; i < act; i++) {
+    for (; i < hi; i++) {
         int j = (cur + i) % act;
         float4 h = ld_stream4(ir + (long long)i * ROW4);
         float4 x = ld_stream4(rg + (long long)j * ROW4);
@@ -168,8 +182,8 @@ k_mac_bulk(MacArgs a)
     const int tile = blockIdx.x % TILES;
     const long long c0 = grp * CPB;
     const int nlive = (int)((a.nchan - c0) < CPB ? (a.nchan - c0) : CPB); // channels of this CTA that exist
-    const int cur = a.current, act = a.active;
-    const int nrows = act - 1;                 // segments 1 .. act-1
+    const int cur = a.current, act = a.active, lo = a.seg_lo, hi = a.seg_hi;
+    const int nrows = hi - lo;                 // segments lo .. hi-1
     const int niter = (nrows + R - 1) / R;
 
     if (threadIdx.x == 0) {
@@ -181,14 +195,14 @@ k_mac_bulk(MacArgs a)
     // producer: fill stage (it % NST) with the rows of iteration `it`
     auto issue = [&](int it) {
         const int s = it % NST;
-        const int i0 = 1 + it * R;
-        const int cnt = (act - i0) < R ? (act - i0) : R;
+        const int i0 = lo + it * R;
+        const int cnt = (hi - i0) < R ? (hi - i0) : R;
         float2 *ir_s = stages + (size_t)s * 2 * ARR;
         float2 *rg_s = ir_s + ARR;
         mbar_expect_tx(&full[s], (uint32_t)(2 * nlive * cnt * TILE * sizeof(float2)));
         for (int ch = 0; ch < nlive; ch++) {
-            const float2 *irc = a.ir + (c0 + ch) * a.ir_stride + tile * TILE;
-            const float2 *rgc = a.ring + (c0 + ch) * a.ring_stride + tile * TILE;
+            const float2 *irc = a.ir + a.ir_chan(c0 + ch) * a.ir_stride + tile * TILE - (long long)a.ir_seg0 * B;
+            const float2 *rgc = a.ring + a.ring_chan(c0 + ch) * a.ring_stride + tile * TILE;
             float2 *ir_d = ir_s + ch * R * TILE, *rg_d = rg_s + ch * R * TILE;
             const int j0 = (cur + i0) % act; // `current` may exceed `active` after a shrinking update()
             if (TILES == 1) {
@@ -216,8 +230,8 @@ k_mac_bulk(MacArgs a)
     for (int it = 0; it < niter; it++) {
         const int s = it % NST;
         mbar_wait(&full[s], (it / NST) & 1);
-        const int i0 = 1 + it * R;
-        const int cnt = (act - i0) < R ? (act - i0) : R;
+        const int i0 = lo + it * R;
+        const int cnt = (hi - i0) < R ? (hi - i0) : R;
         const float4 *ir_s = reinterpret_cast<const float4 *>(stages + (size_t)s * 2 * ARR + ty * R * TILE) + tx;
         const float4 *rg_s = ir_s + ARR / 2;
         if (ty < nlive) {
@@ -249,14 +263,14 @@ k_mac_bulk(MacArgs a)
 }
 
 // B == 1: a row is a single packed bin
-__global__ void k_mac_b1(MacArgs a)
+static __global__ void k_mac_b1(MacArgs a)
 {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.nchan) return;
-    const float2 *ir = a.ir + c * a.ir_stride;
-    const float2 *rg = a.ring + c * a.ring_stride;
+    const float2 *ir = a.ir + a.ir_chan(c) * a.ir_stride - a.ir_seg0;
+    const float2 *rg = a.ring + a.ring_chan(c) * a.ring_stride;
     float ar = 0.f, ai = 0.f;
-    for (int i = 1; i < a.active; i++) {
+    for (int i = a.seg_lo; i < a.seg_hi; i++) {
         int j = (a.current + i) % a.active;
         float2 h = ld_stream2(ir + i), x = ld_stream2(rg + j);
         cmac_ref(ar, ai, h.x, h.y, x.x, x.y, true);

@@ -1,0 +1,295 @@
+// mimo.cu — convolution matrix (BASELINE configs[4]): OUT x IN FFTConvolver-equivalents sharing
+// the IN input-spectrum rings, optionally NS independent streams sharing the one IR matrix, and
+// optionally one IR-partition shard of a multi-GPU job.
+//
+// Semantics: y_out = sum_in FFTConvolver(h[out][in]).process(x_in), i.e. OUT*IN
+// reference convolvers (src/fft_convolver.rs:100-321) with outputs summed over `in`.  Because the
+// inverse FFT and overlap-add are linear, the sum over `in` is taken in the frequency domain and
+// each output gets ONE inverse FFT and ONE overlap buffer; the delay-line sum over segments
+// (:258-269) is associative, so a shard may own only a contiguous range of IR segments and the
+// partial spectra of all shards are summed (NCCL all-reduce, done by the caller) before K3.
+// Full blocks only (n == B per call).
+#include <cmath>
+#include <cstring>
+
+#include "engine_internal.cuh"
+
+using namespace fcb;
+
+namespace fcb {
+
+// conv[s][o][k] = sum_in ( premul[(s*OUT+o)*IN+in][k] + X[s][in][cur][k] * H[o][in][seg 0][k] )
+// ascending `in`; the segment-0 product (src/fft_convolver.rs:270-275) only on the shard that owns
+// segment 0.  One thread per (stream, out, bin).
+__global__ void k_mimo_reduce(const float2 *__restrict__ premul, const float2 *__restrict__ ring_cur,
+                              long long ring_stride, const float2 *__restrict__ ir0, long long ir_stride,
+                              float2 *__restrict__ conv, int B, int n_in, int n_out, long long n_so)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_so * B) return;
+    const long long so = idx / B; // stream*OUT + out
+    const int k = (int)(idx % B);
+    const long long s = so / n_out, o = so % n_out;
+    float ar = 0.f, ai = 0.f;
+    for (int in = 0; in < n_in; in++) {
+        float2 p = premul[(so * n_in + in) * B + k];
+        if (ir0) {
+            float2 x = ring_cur[(s * n_in + in) * ring_stride + k];
+            float2 h = __ldg(&ir0[(o * n_in + in) * ir_stride + k]);
+            float pr, pi;
+            if (k == 0) {
+                pr = __fmul_rn(x.x, h.x);
+                pi = __fmul_rn(x.y, h.y);
+            } else {
+                pr = __fsub_rn(__fmul_rn(x.x, h.x), __fmul_rn(x.y, h.y));
+                pi = __fadd_rn(__fmul_rn(x.x, h.y), __fmul_rn(x.y, h.x));
+            }
+            p.x = __fadd_rn(p.x, pr);
+            p.y = __fadd_rn(p.y, pi);
+        }
+        ar = __fadd_rn(ar, p.x);
+        ai = __fadd_rn(ai, p.y);
+    }
+    conv[so * B + k] = make_float2(ar, ai);
+}
+
+} // namespace fcb
+
+struct fcb_mimo {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    size_t n_in = 0, n_out = 0, n_streams = 1, B = 0, L = 0, S = 0;
+    int logb = 0;
+    size_t seg_lo = 0, seg_hi = 0; // IR segments owned by this shard
+    size_t current = 0;            // ring slot of the next block (src/fft_convolver.rs:113)
+    float2 *ir = nullptr;          // [OUT*IN][seg_hi-seg_lo][B]
+    float2 *ring = nullptr;        // [NS*IN][S][B]
+    float2 *premul = nullptr;      // [NS*OUT*IN][B]
+    float2 *conv = nullptr;        // [NS*OUT][B]  (this shard's partial until all-reduced)
+    float *overlap = nullptr;      // [NS*OUT][B]
+    float *io_in = nullptr, *io_out = nullptr; // staging for the host-pointer call
+    float *stage = nullptr;
+    size_t stage_floats = 0;
+    const float2 *tw = nullptr;
+
+    size_t rows() const { return seg_hi - seg_lo; }
+};
+
+extern "C" void fcb_mimo_destroy(fcb_mimo *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    cudaFree(m->ir);
+    cudaFree(m->ring);
+    cudaFree(m->premul);
+    cudaFree(m->conv);
+    cudaFree(m->overlap);
+    cudaFree(m->io_in);
+    cudaFree(m->io_out);
+    cudaFree(m->stage);
+    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+static int mimo_alloc(void **p, size_t bytes, cudaStream_t s)
+{
+    FCB_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    FCB_CUDA(cudaMemsetAsync(*p, 0, bytes ? bytes : 16, s));
+    return FCB_OK;
+}
+
+extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
+{
+    if (!d || !out) return fail(FCB_ERR_ARG, "fcb_mimo_create: NULL argument");
+    *out = nullptr;
+    if (!d->n_in || !d->n_out) return fail(FCB_ERR_ARG, "fcb_mimo_create: empty matrix");
+    const size_t ns = d->n_streams ? d->n_streams : 1, shards = d->shard_count ? d->shard_count : 1;
+    if (d->shard_index >= shards) return fail(FCB_ERR_ARG, "fcb_mimo_create: shard %zu of %zu", d->shard_index, shards);
+    const size_t B = next_power_of_two(d->block_size);
+    if (B > 16384) return fail(FCB_ERR_UNSUPPORTED, "block size %zu > 16384 not supported", B);
+    FCB_CUDA(cudaSetDevice(d->device));
+    fcb_mimo *m = new fcb_mimo();
+    m->device = d->device;
+    m->n_in = d->n_in;
+    m->n_out = d->n_out;
+    m->n_streams = ns;
+    m->B = B;
+    m->logb = ilog2(B);
+    m->L = d->max_response_length;
+    m->S = (size_t)std::ceil((double)m->L / (double)B);
+    m->seg_lo = m->S * d->shard_index / shards;
+    m->seg_hi = m->S * (d->shard_index + 1) / shards;
+    if (d->stream) m->stream = (cudaStream_t)d->stream;
+    else {
+        cudaError_t err = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+        if (err != cudaSuccess) {
+            delete m;
+            return fail(FCB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(err));
+        }
+        m->own_stream = true;
+    }
+    const size_t pairs = m->n_out * m->n_in;
+    int rc = get_twiddles(m->device, 2 * B, &m->tw);
+    if (!rc) rc = mimo_alloc((void **)&m->ir, pairs * m->rows() * B * sizeof(float2), m->stream);
+    if (!rc) rc = mimo_alloc((void **)&m->ring, ns * m->n_in * m->S * B * sizeof(float2), m->stream);
+    if (!rc) rc = mimo_alloc((void **)&m->premul, ns * pairs * B * sizeof(float2), m->stream);
+    if (!rc) rc = mimo_alloc((void **)&m->conv, ns * m->n_out * B * sizeof(float2), m->stream);
+    if (!rc) rc = mimo_alloc((void **)&m->overlap, ns * m->n_out * B * sizeof(float), m->stream);
+    if (!rc) rc = mimo_alloc((void **)&m->io_in, ns * m->n_in * B * sizeof(float), m->stream);
+    if (!rc) rc = mimo_alloc((void **)&m->io_out, ns * m->n_out * B * sizeof(float), m->stream);
+    const size_t per = m->L ? m->L : 1, cap = (size_t)16 << 20;
+    m->stage_floats = pairs * per < cap ? pairs * per : (cap / per ? (cap / per) * per : per);
+    if (!rc) rc = mimo_alloc((void **)&m->stage, m->stage_floats * sizeof(float), m->stream);
+    if (!rc && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = fail(FCB_ERR_CUDA, "sync failed");
+    if (rc) {
+        fcb_mimo_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return FCB_OK;
+}
+
+// K5 over this shard's segment range: irs = [OUT][IN][len] host, stride `len`
+extern "C" int fcb_mimo_set_ir(fcb_mimo *m, const float *irs, size_t len)
+{
+    if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
+    if (len > m->L) return fail(FCB_ERR_PANIC, "max_response_length must be at least the length of the initial impulse response");
+    if (len && !irs) return fail(FCB_ERR_ARG, "NULL impulse responses");
+    if (m->rows() == 0) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(m->device));
+    const size_t pairs = m->n_out * m->n_in, B = m->B;
+    const long long dst_stride = (long long)(m->rows() * B);
+    const size_t off = m->seg_lo * B;                 // first sample of this shard's first segment
+    const int rem = len > off ? (int)(len - off) : 0; // samples of the IR at or past it
+    if (len == 0) {
+        return run_forward(m->logb, m->tw, m->stream, m->stage, 0, 0, m->ir, dst_stride, (int)m->rows(),
+                           (long long)(pairs * m->rows()));
+    }
+    const size_t per_group = m->stage_floats / len;
+    if (per_group == 0) return fail(FCB_ERR_CUDA, "IR staging buffer too small");
+    for (size_t g0 = 0; g0 < pairs; g0 += per_group) {
+        const size_t g = pairs - g0 < per_group ? pairs - g0 : per_group;
+        FCB_CUDA(cudaMemcpyAsync(m->stage, irs + g0 * len, g * len * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+        FCB_TRY(run_forward(m->logb, m->tw, m->stream, m->stage + off, (long long)len, rem, m->ir + g0 * dst_stride,
+                            dst_stride, (int)m->rows(), (long long)(g * m->rows())));
+        if (g0 + per_group < pairs) FCB_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    return FCB_OK;
+}
+
+extern "C" int fcb_mimo_reset(fcb_mimo *m)
+{
+    if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
+    FCB_CUDA(cudaSetDevice(m->device));
+    const size_t ns = m->n_streams, B = m->B;
+    FCB_CUDA(cudaMemsetAsync(m->ring, 0, ns * m->n_in * m->S * B * sizeof(float2), m->stream));
+    FCB_CUDA(cudaMemsetAsync(m->overlap, 0, ns * m->n_out * B * sizeof(float), m->stream));
+    m->current = 0;
+    return FCB_OK;
+}
+
+// K1 on the NS*IN input blocks, K2 over this shard's segments, reduction over `in` -> conv
+extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_stride)
+{
+    if (!m || !in_dev) return fail(FCB_ERR_ARG, "fcb_mimo_partial_dev: NULL argument");
+    if (m->S == 0) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(m->device));
+    const size_t B = m->B, ns = m->n_streams, pairs = m->n_out * m->n_in;
+    const long long ring_stride = (long long)(m->S * B);
+    FCB_TRY(run_forward(m->logb, m->tw, m->stream, in_dev, (long long)in_stride, (int)B, m->ring + m->current * B,
+                        ring_stride, 1, (long long)(ns * m->n_in)));
+    MacArgs a{};
+    a.ir = m->ir;
+    a.ir_stride = (long long)(m->rows() * B);
+    a.ring = m->ring;
+    a.ring_stride = ring_stride;
+    a.premul = m->premul;
+    a.current = (int)m->current;
+    a.active = (int)m->S;
+    a.nchan = (long long)(ns * pairs);
+    a.seg_lo = (int)(m->seg_lo > 1 ? m->seg_lo : 1);
+    a.seg_hi = (int)m->seg_hi;
+    a.ir_seg0 = (int)m->seg_lo;
+    a.ir_mod = (long long)pairs;
+    a.ring_div = (long long)pairs;
+    a.ring_mul = (long long)m->n_in;
+    a.ring_mod = (long long)m->n_in;
+    FCB_TRY(run_mac(m->logb, m->stream, a));
+    const bool owns0 = m->seg_lo == 0 && m->seg_hi > 0;
+    const long long n_so = (long long)(ns * m->n_out), total = n_so * (long long)B;
+    k_mimo_reduce<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(
+        m->premul, m->ring + m->current * B, ring_stride, owns0 ? m->ir : nullptr, a.ir_stride, m->conv, (int)B,
+        (int)m->n_in, (int)m->n_out, n_so);
+    g_launches++;
+    FCB_CUDA(cudaGetLastError());
+    return FCB_OK;
+}
+
+extern "C" float *fcb_mimo_conv_buffer(fcb_mimo *m, size_t *n_floats)
+{
+    if (!m) return nullptr;
+    if (n_floats) *n_floats = 2 * m->n_streams * m->n_out * m->B;
+    return reinterpret_cast<float *>(m->conv);
+}
+
+// K3 on the (all-reduced) conv: inverse FFT, /N, overlap-add, overlap save; rotates `current`
+extern "C" int fcb_mimo_finish_dev(fcb_mimo *m, float *out_dev, size_t out_stride)
+{
+    if (!m || !out_dev) return fail(FCB_ERR_ARG, "fcb_mimo_finish_dev: NULL argument");
+    FCB_CUDA(cudaSetDevice(m->device));
+    const size_t B = m->B, n_so = m->n_streams * m->n_out;
+    if (m->S == 0) {
+        FCB_CUDA(cudaMemset2DAsync(out_dev, out_stride * sizeof(float), 0, B * sizeof(float), n_so, m->stream));
+        return FCB_OK;
+    }
+    IfftArgs a{};
+    a.ir0 = nullptr; // conv is complete
+    a.premul = m->conv;
+    a.overlap = m->overlap;
+    a.out = out_dev;
+    a.out_stride = (long long)out_stride;
+    a.fill = 0;
+    a.n = (int)B;
+    a.block_complete = 1;
+    a.nchan = (long long)n_so;
+    FCB_TRY(run_inverse(m->logb, m->tw, m->stream, a));
+    m->current = m->current > 0 ? m->current - 1 : m->S - 1; // src/fft_convolver.rs:301-305
+    return FCB_OK;
+}
+
+// single-shard convenience with host buffers: in [NS*IN][B], out [NS*OUT][B]
+extern "C" int fcb_mimo_process(fcb_mimo *m, const float *in, float *out)
+{
+    if (!m || !in || !out) return fail(FCB_ERR_ARG, "fcb_mimo_process: NULL argument");
+    if (m->seg_lo != 0 || m->seg_hi != m->S)
+        return fail(FCB_ERR_ARG, "fcb_mimo_process: this object is one shard of several; use partial/all-reduce/finish");
+    FCB_CUDA(cudaSetDevice(m->device));
+    const size_t B = m->B, ns = m->n_streams;
+    FCB_CUDA(cudaMemcpyAsync(m->io_in, in, ns * m->n_in * B * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    FCB_TRY(fcb_mimo_partial_dev(m, m->io_in, B));
+    FCB_TRY(fcb_mimo_finish_dev(m, m->io_out, B));
+    FCB_CUDA(cudaMemcpyAsync(out, m->io_out, ns * m->n_out * B * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    FCB_CUDA(cudaStreamSynchronize(m->stream));
+    return FCB_OK;
+}
+
+extern "C" int fcb_mimo_sync(fcb_mimo *m)
+{
+    if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
+    FCB_CUDA(cudaSetDevice(m->device));
+    FCB_CUDA(cudaStreamSynchronize(m->stream));
+    return FCB_OK;
+}
+
+extern "C" void *fcb_mimo_stream(fcb_mimo *m) { return m ? (void *)m->stream : nullptr; }
+extern "C" size_t fcb_mimo_block_size(const fcb_mimo *m) { return m->B; }
+extern "C" size_t fcb_mimo_seg_count(const fcb_mimo *m) { return m->S; }
+extern "C" int fcb_mimo_segment_range(const fcb_mimo *m, size_t *lo, size_t *hi)
+{
+    if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
+    if (lo) *lo = m->seg_lo;
+    if (hi) *hi = m->seg_hi;
+    return FCB_OK;
+}

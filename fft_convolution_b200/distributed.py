@@ -1,0 +1,46 @@
+"""Multi-GPU plumbing (torch.distributed is plumbing only; all arithmetic is in the CUDA library).
+
+* Independent channels: every rank owns a disjoint channel range and its own FFTConvolver batch —
+  no collective on the data path (bench.py does exactly this).
+* Convolution matrix with very long IRs: the IR is sharded by partition (contiguous ranges of IR
+  segments); each rank computes the partial spectra of its range and they are summed with one NCCL
+  all-reduce per block (16 x B complex = 64 KB at B = 512), after which every rank runs K3.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .convolvers import MimoConvolver
+
+
+class _DeviceBuffer:
+    """exposes a raw device pointer of the C library to torch through __cuda_array_interface__"""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class ShardedMimoConvolver:
+    """One IR-partition shard per rank of the default process group (NCCL on GPUs)."""
+
+    def __init__(self, responses, block_size: int, max_response_length: int, *, n_streams: int = 1, device: int = 0):
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.m = MimoConvolver.init(responses, block_size, max_response_length, n_streams=n_streams,
+                                    shard_index=self.rank, shard_count=self.world, device=device,
+                                    stream=self.stream.cuda_stream)
+        ptr, n = self.m.conv_buffer()
+        self._keep = _DeviceBuffer(ptr, n)
+        self.conv = torch.as_tensor(self._keep, device=f"cuda:{device}")
+        self.B = self.m.block_size
+
+    def process_dev(self, x: torch.Tensor, out: torch.Tensor) -> None:
+        """x: [NS*IN, B] float32 on this rank's GPU (every rank is given the same block);
+        out: [NS*OUT, B].  Every rank ends with the full result."""
+        with torch.cuda.stream(self.stream):
+            self.m.partial_dev(x.data_ptr(), x.stride(0))
+            if self.world > 1:
+                dist.all_reduce(self.conv, op=dist.ReduceOp.SUM)
+            self.m.finish_dev(out.data_ptr(), out.stride(0))

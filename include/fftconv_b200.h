@@ -240,6 +240,40 @@ int fcb_crossfade_sync(fcb_crossfade *c);
 int fcb_crossfade_state(const fcb_crossfade *c, int64_t *counter, float *mix_value, int *approaching,
                         int *target);
 
+/* ============================================================================================
+ * Convolution matrix (BASELINE configs[4]): y_out = sum_in FFTConvolver(h[out][in]).process(x_in),
+ * OUT x IN reference convolvers sharing the IN input rings; NS independent streams may share the
+ * one IR matrix; an object may be one IR-partition shard (a contiguous range of IR segments) of a
+ * multi-GPU job, in which case the caller all-reduces (sum, f32) the partial spectra returned by
+ * fcb_mimo_conv_buffer between partial and finish.  Full blocks only (B samples per call).
+ * ========================================================================================== */
+typedef struct fcb_mimo fcb_mimo;
+typedef struct {
+    size_t n_in, n_out, n_streams; /* n_streams 0 = 1 */
+    size_t block_size, max_response_length;
+    size_t shard_index, shard_count; /* shard g of G owns IR segments [S*g/G, S*(g+1)/G); 0,0 = all */
+    int device;
+    void *stream;
+} fcb_mimo_desc;
+int fcb_mimo_create(const fcb_mimo_desc *desc, fcb_mimo **out);
+void fcb_mimo_destroy(fcb_mimo *m);
+/* irs: host [OUT][IN][len]; every shard is given the whole IRs and keeps its segment rows */
+int fcb_mimo_set_ir(fcb_mimo *m, const float *irs, size_t len);
+int fcb_mimo_reset(fcb_mimo *m);
+/* in_dev: device [NS*IN][B] (channel stride in_stride).  K1 + K2 over this shard's segments +
+ * sum over inputs -> partial conv spectra in fcb_mimo_conv_buffer ([NS*OUT][B] packed complex) */
+int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_stride);
+float *fcb_mimo_conv_buffer(fcb_mimo *m, size_t *n_floats);
+/* K3 on the (all-reduced) conv buffer -> out_dev [NS*OUT][B]; advances the ring */
+int fcb_mimo_finish_dev(fcb_mimo *m, float *out_dev, size_t out_stride);
+/* single-shard convenience, host buffers: in [NS*IN][B] -> out [NS*OUT][B], synchronous */
+int fcb_mimo_process(fcb_mimo *m, const float *in, float *out);
+int fcb_mimo_sync(fcb_mimo *m);
+void *fcb_mimo_stream(fcb_mimo *m);
+size_t fcb_mimo_block_size(const fcb_mimo *m);
+size_t fcb_mimo_seg_count(const fcb_mimo *m);
+int fcb_mimo_segment_range(const fcb_mimo *m, size_t *lo, size_t *hi);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log; tail -25 gpurun_out/pytest_gpu.log
+echo "== mimo bench 1 GPU"; timeout 600 python scripts/mimo_bench.py 2>gpurun_out/mimo1.err | tee gpurun_out/mimo_1gpu.json; tail -3 gpurun_out/mimo1.err
+timeout 600 python scripts/mimo_bench.py --streams 4 2>>gpurun_out/mimo1.err | tee -a gpurun_out/mimo_1gpu.json

@@ -1,0 +1,114 @@
+"""Convolution matrix (BASELINE configs[4] shape, reduced sizes) against OUT x IN oracle
+convolvers; IR-partition shards emulated on one GPU: partial spectra summed on the host exactly
+as the NCCL all-reduce would (one kernel sequence per shard, never concurrent waiting kernels)."""
+import numpy as np
+import pytest
+
+import oracle
+from mimo_oracle import MimoOracle
+from refsignals import rms
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def F():
+    import fft_convolution_b200 as f
+    return f
+
+
+def _irs(n_out, n_in, L, upd=0):
+    return np.stack([np.stack([oracle.gen_ir(o * n_in + i, upd, L) for i in range(n_in)]) for o in range(n_out)])
+
+
+@pytest.mark.parametrize("n_out,n_in,B,L", [(3, 2, 64, 700), (4, 4, 128, 1500), (16, 16, 32, 200), (1, 1, 256, 1000)])
+def test_mimo_matches_oracle(F, n_out, n_in, B, L):
+    h = _irs(n_out, n_in, L)
+    nblocks = 14
+    x = np.stack([oracle.gen_noise(100 + i, 0, B * nblocks) for i in range(n_in)])
+    g, o = F.MimoConvolver.init(h, B, L), MimoOracle(h, B, L)
+    out = np.zeros((n_out, B), np.float32)
+    for b in range(nblocks):
+        blk = np.ascontiguousarray(x[:, b * B:(b + 1) * B])
+        g.process(blk, out)
+        ref = o.process(blk)
+        assert np.max(np.abs(out - ref)) <= TOL * max(rms(ref), 0.05) * 2, b
+
+
+def test_mimo_streams_share_the_matrix(F):
+    n_out, n_in, B, L, NS = 2, 3, 64, 500, 3
+    h = _irs(n_out, n_in, L)
+    x = np.stack([oracle.gen_noise(200 + i, 0, B * 10) for i in range(NS * n_in)])
+    g = F.MimoConvolver.init(h, B, L, n_streams=NS)
+    singles = [F.MimoConvolver.init(h, B, L) for _ in range(NS)]
+    out = np.zeros((NS * n_out, B), np.float32)
+    one = np.zeros((n_out, B), np.float32)
+    for b in range(10):
+        blk = np.ascontiguousarray(x[:, b * B:(b + 1) * B])
+        g.process(blk, out)
+        for s in range(NS):
+            singles[s].process(blk[s * n_in:(s + 1) * n_in], one)
+            assert np.array_equal(out[s * n_out:(s + 1) * n_out], one)
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_ir_partition_shards_sum_to_the_whole(F, shards):
+    """every shard owns S*g/G..S*(g+1)/G of the IR segments; partial spectra summed (as the NCCL
+    all-reduce does) then K3 on every shard == the unsharded engine up to f32 summation order"""
+    import torch
+    from fft_convolution_b200.distributed import _DeviceBuffer
+    n_out, n_in, B, L = 3, 2, 64, 64 * 11 + 5
+    h = _irs(n_out, n_in, L)
+    x = np.stack([oracle.gen_noise(300 + i, 0, B * 16) for i in range(n_in)])
+    whole = F.MimoConvolver.init(h, B, L)
+    parts = [F.MimoConvolver.init(h, B, L, shard_index=g, shard_count=shards) for g in range(shards)]
+    S = whole.seg_count
+    ranges = [p.segment_range for p in parts]
+    assert ranges == [F.mimo_segment_range(S, g, shards) for g in range(shards)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == S and all(ranges[i][1] == ranges[i + 1][0] for i in range(shards - 1))
+    ref_o = MimoOracle(h, B, L)
+    out_w = np.zeros((n_out, B), np.float32)
+    d_in = torch.empty((n_in, B), dtype=torch.float32, device="cuda")
+    d_out = torch.empty((n_out, B), dtype=torch.float32, device="cuda")
+    for b in range(16):
+        blk = np.ascontiguousarray(x[:, b * B:(b + 1) * B])
+        whole.process(blk, out_w)
+        d_in.copy_(torch.from_numpy(blk))
+        torch.cuda.synchronize()
+        bufs = []
+        for p in parts:
+            p.partial_dev(d_in.data_ptr(), B)
+            p.sync()
+            ptr, n = p.conv_buffer()
+            bufs.append(torch.as_tensor(_DeviceBuffer(ptr, n), device="cuda"))
+        total = torch.stack(bufs).sum(dim=0)  # the all-reduce
+        for p, bview in zip(parts, bufs):
+            bview.copy_(total)
+        torch.cuda.synchronize()
+        outs = []
+        for p in parts:
+            p.finish_dev(d_out.data_ptr(), B)
+            p.sync()
+            outs.append(d_out.cpu().numpy().copy())
+        for o in outs[1:]:
+            assert np.array_equal(o, outs[0])  # every shard ends with the same block
+        ref = ref_o.process(blk)
+        assert np.max(np.abs(outs[0] - ref)) <= 2 * TOL * max(rms(ref), 0.05)
+        assert np.max(np.abs(outs[0] - out_w)) <= 2 * TOL * max(rms(ref), 0.05)
+
+
+def test_nccl_sharded_mimo_two_gpus():
+    """real NCCL all-reduce of the partial spectra over 2 GPUs (skipped on a 1-GPU box)"""
+    import subprocess
+    import sys
+    from pathlib import Path
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(root / "scripts" / "mimo_nccl_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mimo nccl check" in r.stdout
