@@ -180,6 +180,7 @@ extern "C" int fcb_profile_mac_read(double *total_ms, uint64_t *launches)
 static std::atomic<int> g_mac_impl{0};   // 0 = auto (TMA pipeline for B >= 32), 1 = LDG, 2 = TMA
 static std::atomic<int> g_mac_stages{3}; // 2, 3, 4 or 6
 static std::atomic<int> g_pipe_group{512}; // channels per group of the end-to-end pipeline
+namespace fcb { std::atomic<bool> g_mimo_tile{true}; } // matrix K2 with in-CTA reuse (0: generic K2)
 
 template <int B, int NST>
 static int launch_mac_bulk(const MacArgs &a, cudaStream_t st)
@@ -273,12 +274,72 @@ int run_inverse(int logb, const float2 *tw, cudaStream_t st, const IfftArgs &a)
 }
 } // namespace fcb
 
+template <int B, int OT, int ST>
+static int launch_mac_tile(const MacTileArgs &a, cudaStream_t st)
+{
+    using Cfg = MacTileCfg<B, OT, ST>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        FCB_CUDA(cudaFuncSetAttribute(k_mac_tile<B, OT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const long long OG = (a.n_out + OT - 1) / OT, SG = (a.n_streams + ST - 1) / ST;
+    const long long grid = (long long)Cfg::TILES * a.zchunks * OG * a.n_in * SG;
+    cudaEvent_t prof_stop = nullptr;
+    const bool profiled = prof_before(st, &prof_stop) != nullptr;
+    k_mac_tile<B, OT, ST><<<(unsigned)grid, Cfg::TX, Cfg::SMEM_BYTES, st>>>(a);
+    if (profiled) cudaEventRecord(prof_stop, st);
+    g_launches++;
+    FCB_CUDA(cudaGetLastError());
+    return FCB_OK;
+}
+
+namespace fcb {
+// one stream: 8 outputs share each ring tile; several streams: 4 outputs x 4 streams per CTA
+static inline bool tile_wide_streams(int n_streams) { return n_streams >= 2; }
+
+int mac_tile_plan(int logb, int n_in, int n_out, int n_streams, int nsegs, int *zchunks, int *zlen)
+{
+    if (logb < 6) return FCB_ERR_UNSUPPORTED; // B < 64: the generic K2 handles it
+    const int B = 1 << logb, tiles = B < 512 ? 1 : B / 512;
+    const int OT = tile_wide_streams(n_streams) ? 4 : 8, ST = tile_wide_streams(n_streams) ? 4 : 1;
+    const long long base = (long long)tiles * ((n_out + OT - 1) / OT) * n_in * ((n_streams + ST - 1) / ST);
+    long long z = (4 * 148 + base - 1) / base; // aim at >= 4 CTAs per SM worth of work items
+    const long long zmax = nsegs > 8 ? nsegs / 8 : 1;
+    if (z > zmax) z = zmax;
+    if (z < 1) z = 1;
+    const int len = (int)((nsegs + z - 1) / z);
+    *zlen = len > 0 ? len : 1;
+    *zchunks = nsegs > 0 ? (nsegs + *zlen - 1) / *zlen : 1;
+    return FCB_OK;
+}
+
+int run_mac_tile(int logb, cudaStream_t st, MacTileArgs a, int *zchunks_out)
+{
+    const int nsegs = a.seg_hi - a.seg_lo;
+    FCB_TRY(mac_tile_plan(logb, a.n_in, a.n_out, a.n_streams, nsegs > 0 ? nsegs : 0, &a.zchunks, &a.zlen));
+    if (zchunks_out) *zchunks_out = a.zchunks;
+    const bool wide = tile_wide_streams(a.n_streams);
+#define FCB_TILE_CASE(LB)                                                                  \
+    case LB:                                                                               \
+        return wide ? launch_mac_tile<(1 << LB), 4, 4>(a, st) : launch_mac_tile<(1 << LB), 8, 1>(a, st);
+    switch (logb) {
+        FCB_TILE_CASE(6) FCB_TILE_CASE(7) FCB_TILE_CASE(8) FCB_TILE_CASE(9) FCB_TILE_CASE(10) FCB_TILE_CASE(11)
+        FCB_TILE_CASE(12) FCB_TILE_CASE(13) FCB_TILE_CASE(14)
+    default: return FCB_ERR_UNSUPPORTED;
+    }
+#undef FCB_TILE_CASE
+}
+} // namespace fcb
+
 extern "C" int fcb_tune(const char *key, int value)
 {
     if (!key) return fail(FCB_ERR_ARG, "fcb_tune: NULL key");
     if (!strcmp(key, "mac_impl") && value >= 0 && value <= 2) g_mac_impl = value;
     else if (!strcmp(key, "mac_stages") && (value == 2 || value == 3 || value == 4 || value == 6)) g_mac_stages = value;
     else if (!strcmp(key, "pipe_group") && value >= 1) g_pipe_group = value;
+    else if (!strcmp(key, "mimo_tile")) g_mimo_tile = value != 0;
     else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);
     return FCB_OK;
 }

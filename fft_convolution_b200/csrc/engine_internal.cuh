@@ -15,5 +15,9 @@ int run_forward(int logb, const float2 *tw, cudaStream_t st, const float *src, l
                 float2 *dst, long long dst_stride, int nseg, long long ntransforms);
 int run_mac(int logb, cudaStream_t st, const MacArgs &a);
 int run_inverse(int logb, const float2 *tw, cudaStream_t st, const IfftArgs &a);
+// matrix K2 with in-CTA reuse; returns FCB_ERR_UNSUPPORTED for block sizes it is not built for
+int run_mac_tile(int logb, cudaStream_t st, MacTileArgs a, int *zchunks_out);
+// part rows needed by run_mac_tile for this problem (upper bound on zchunks * NS * OUT * IN)
+int mac_tile_plan(int logb, int n_in, int n_out, int n_streams, int nsegs, int *zchunks, int *zlen);
 
 } // namespace fcb

@@ -262,6 +262,163 @@ k_mac_bulk(MacArgs a)
         reinterpret_cast<float4 *>(a.premul + (c0 + ty) * B)[tile * TX + tx] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Matrix variant of K2 (convolution matrix, BASELINE configs[4]): one CTA owns OT outputs x ST
+// streams of ONE input channel and one bin tile, for one chunk of the segment range.  Per stage
+// the producer stages OT IR tiles (h[out][in], shared by the ST streams) and ST ring tiles
+// (x[stream][in], shared by the OT outputs) with cp.async.bulk; every thread keeps OT*ST float4
+// accumulators.  Traffic per complex MAC drops from 16 B to 8/ST + 8/OT bytes, so the IR matrix is
+// read from HBM once per block however many outputs/streams reuse it.  FMA arithmetic: the sum
+// over inputs/shards is re-associated anyway (parity is by tolerance here, not bit-exact).
+// Partial results go to part[((z*NS + s)*OUT + o)*IN + in][B]; k_mimo_reduce sums over z and in.
+// ---------------------------------------------------------------------------------------------
+struct MacTileArgs {
+    const float2 *ir;   // [OUT*IN][rows][B], row r = IR segment ir_seg0 + r
+    long long ir_stride;
+    const float2 *ring; // [NS*IN][S][B]
+    long long ring_stride;
+    float2 *part;       // [Z*NS*OUT*IN][B]
+    int current, active; // ring slot of the current block, ring length S
+    int seg_lo, seg_hi, ir_seg0;
+    int n_in, n_out, n_streams, zchunks, zlen; // zlen = segments per z chunk
+};
+
+__device__ __forceinline__ void cmac_fma2(float4 &acc, const float4 &h, const float4 &x, bool packed)
+{
+    // bins (h.x,h.y)*(x.x,x.y) and (h.z,h.w)*(x.z,x.w); bin 0 of a row is {DC, Nyquist}: two real products
+    if (packed) {
+        acc.x = fmaf(h.x, x.x, acc.x);
+        acc.y = fmaf(h.y, x.y, acc.y);
+    } else {
+        acc.x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc.x));
+        acc.y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc.y));
+    }
+    acc.z = fmaf(h.z, x.z, fmaf(-h.w, x.w, acc.z));
+    acc.w = fmaf(h.z, x.w, fmaf(h.w, x.z, acc.w));
+}
+
+template <int B, int OT, int ST>
+struct MacTileCfg {
+    static constexpr int TILE = B < 512 ? B : 512;
+    static constexpr int TILES = B / TILE;
+    static constexpr int TX = TILE / 2;              // threads per CTA
+    static constexpr int R = 2;                      // segments per stage
+    static constexpr int ARR = R * TILE;             // float2 per (output or stream) per stage
+    static constexpr size_t STAGE_BYTES = (size_t)(OT + ST) * ARR * sizeof(float2);
+    static constexpr int NST = (3 * STAGE_BYTES + 64 <= 220 * 1024) ? 3 : 2;
+    static constexpr size_t SMEM_BYTES = NST * STAGE_BYTES + 64;
+};
+
+template <int B, int OT, int ST>
+__global__ void __launch_bounds__(MacTileCfg<B, OT, ST>::TX)
+k_mac_tile(MacTileArgs a)
+{
+    using Cfg = MacTileCfg<B, OT, ST>;
+    constexpr int TILE = Cfg::TILE, TILES = Cfg::TILES, TX = Cfg::TX, R = Cfg::R, ARR = Cfg::ARR, NST = Cfg::NST;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 *stages = reinterpret_cast<float2 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NST * Cfg::STAGE_BYTES);
+
+    // blockIdx.x = tile + TILES*(z + Z*(og + OG*(in + IN*sg)))
+    const int OG = (a.n_out + OT - 1) / OT;
+    long long bid = blockIdx.x;
+    const int tile = (int)(bid % TILES); bid /= TILES;
+    const int z = (int)(bid % a.zchunks); bid /= a.zchunks;
+    const int og = (int)(bid % OG); bid /= OG;
+    const int in = (int)(bid % a.n_in); bid /= a.n_in;
+    const int sg = (int)bid;
+    const int o0 = og * OT, s0 = sg * ST;
+    const int no = (a.n_out - o0) < OT ? (a.n_out - o0) : OT;
+    const int nsl = (a.n_streams - s0) < ST ? (a.n_streams - s0) : ST;
+    const int lo = a.seg_lo + z * a.zlen;
+    const int hi = (lo + a.zlen) < a.seg_hi ? (lo + a.zlen) : a.seg_hi;
+    const int niter = hi > lo ? (hi - lo + R - 1) / R : 0;
+    const int cur = a.current, act = a.active;
+    const int tx = threadIdx.x;
+
+    if (tx == 0) {
+        for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int it) {
+        const int s = it % NST;
+        const int i0 = lo + it * R;
+        const int cnt = (hi - i0) < R ? (hi - i0) : R;
+        float2 *h_s = stages + (size_t)s * (OT + ST) * ARR;
+        float2 *x_s = h_s + OT * ARR;
+        mbar_expect_tx(&full[s], (uint32_t)((no + nsl) * cnt * TILE * sizeof(float2)));
+        const int j0 = (cur + i0) % act;
+        const int first = (act - j0) < cnt ? (act - j0) : cnt;
+        for (int o = 0; o < no; o++) {
+            const float2 *src = a.ir + ((long long)(o0 + o) * a.n_in + in) * a.ir_stride + tile * TILE - (long long)a.ir_seg0 * B;
+            if (TILES == 1) {
+                bulk_g2s(h_s + o * ARR, src + (long long)i0 * B, cnt * TILE * sizeof(float2), &full[s]);
+            } else {
+                for (int r = 0; r < cnt; r++)
+                    bulk_g2s(h_s + o * ARR + r * TILE, src + (long long)(i0 + r) * B, TILE * sizeof(float2), &full[s]);
+            }
+        }
+        for (int st = 0; st < nsl; st++) {
+            const float2 *src = a.ring + ((long long)(s0 + st) * a.n_in + in) * a.ring_stride + tile * TILE;
+            if (TILES == 1) {
+                bulk_g2s(x_s + st * ARR, src + (long long)j0 * B, first * TILE * sizeof(float2), &full[s]);
+                if (first < cnt)
+                    bulk_g2s(x_s + st * ARR + first * TILE, src, (cnt - first) * TILE * sizeof(float2), &full[s]);
+            } else {
+                for (int r = 0; r < cnt; r++) {
+                    int j = j0 + r;
+                    j = j >= act ? j - act : j;
+                    bulk_g2s(x_s + st * ARR + r * TILE, src + (long long)j * B, TILE * sizeof(float2), &full[s]);
+                }
+            }
+        }
+    };
+
+    if (tx == 0)
+        for (int it = 0; it < NST && it < niter; it++) issue(it);
+
+    const bool packed = (tile == 0 && tx == 0);
+    float4 acc[OT][ST];
+#pragma unroll
+    for (int o = 0; o < OT; o++)
+#pragma unroll
+        for (int st = 0; st < ST; st++) acc[o][st] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int it = 0; it < niter; it++) {
+        const int s = it % NST;
+        mbar_wait(&full[s], (it / NST) & 1);
+        const int i0 = lo + it * R;
+        const int cnt = (hi - i0) < R ? (hi - i0) : R;
+        const float4 *h_s = reinterpret_cast<const float4 *>(stages + (size_t)s * (OT + ST) * ARR) + tx;
+        const float4 *x_s = h_s + OT * ARR / 2;
+        for (int r = 0; r < cnt; r++) {
+            float4 x[ST];
+#pragma unroll
+            for (int st = 0; st < ST; st++) x[st] = st < nsl ? x_s[(st * ARR + r * TILE) / 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int o = 0; o < OT; o++) {
+                if (o < no) {
+                    const float4 h = h_s[(o * ARR + r * TILE) / 2];
+#pragma unroll
+                    for (int st = 0; st < ST; st++) cmac_fma2(acc[o][st], h, x[st], packed);
+                }
+            }
+        }
+        __syncthreads();
+        if (tx == 0 && it + NST < niter) issue(it + NST);
+    }
+#pragma unroll
+    for (int o = 0; o < OT; o++)
+#pragma unroll
+        for (int st = 0; st < ST; st++)
+            if (o < no && st < nsl) {
+                const long long row = (((long long)z * a.n_streams + (s0 + st)) * a.n_out + (o0 + o)) * a.n_in + in;
+                reinterpret_cast<float4 *>(a.part + row * B)[tile * TX + tx] = acc[o][st];
+            }
+}
+
 // B == 1: a row is a single packed bin
 static __global__ void k_mac_b1(MacArgs a)
 {

@@ -17,40 +17,62 @@
 using namespace fcb;
 
 namespace fcb {
+extern std::atomic<bool> g_mimo_tile;
 
-// conv[s][o][k] = sum_in ( premul[(s*OUT+o)*IN+in][k] + X[s][in][cur][k] * H[o][in][seg 0][k] )
-// ascending `in`; the segment-0 product (src/fft_convolver.rs:270-275) only on the shard that owns
-// segment 0.  One thread per (stream, out, bin).
-__global__ void k_mimo_reduce(const float2 *__restrict__ premul, const float2 *__restrict__ ring_cur,
-                              long long ring_stride, const float2 *__restrict__ ir0, long long ir_stride,
-                              float2 *__restrict__ conv, int B, int n_in, int n_out, long long n_so)
+// conv[s][o][k] = sum_in sum_z part[z][s][o][in][k]  +  sum_in X[s][in][cur][k] * H[o][in][seg 0][k]
+// (the segment-0 product, src/fft_convolver.rs:270-275, only on the shard that owns segment 0).
+// CTA = 32 bins x 8 input lanes of one (stream, out): lane y sums its inputs y, y+8, ... over all
+// z chunks, then the 8 lane sums are added in fixed order — deterministic, and parallel enough
+// that the Z*IN partial rows (19 MB at 16x16, Z = 19) stream at memory speed.
+__global__ void __launch_bounds__(256)
+k_mimo_reduce(const float2 *__restrict__ premul, const float2 *__restrict__ ring_cur, long long ring_stride,
+              const float2 *__restrict__ ir0, long long ir_stride, float2 *__restrict__ conv, int B, int n_in,
+              int n_out, long long n_so, int zchunks)
 {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_so * B) return;
-    const long long so = idx / B; // stream*OUT + out
-    const int k = (int)(idx % B);
+    __shared__ float2 lane_sum[8][32];
+    const int kt = (B + 31) / 32;
+    const long long so = blockIdx.x / kt; // stream*OUT + out
+    const int k = (blockIdx.x % kt) * 32 + threadIdx.x;
+    const int y = threadIdx.y;
     const long long s = so / n_out, o = so % n_out;
     float ar = 0.f, ai = 0.f;
-    for (int in = 0; in < n_in; in++) {
-        float2 p = premul[(so * n_in + in) * B + k];
-        if (ir0) {
-            float2 x = ring_cur[(s * n_in + in) * ring_stride + k];
-            float2 h = __ldg(&ir0[(o * n_in + in) * ir_stride + k]);
-            float pr, pi;
-            if (k == 0) {
-                pr = __fmul_rn(x.x, h.x);
-                pi = __fmul_rn(x.y, h.y);
-            } else {
-                pr = __fsub_rn(__fmul_rn(x.x, h.x), __fmul_rn(x.y, h.y));
-                pi = __fadd_rn(__fmul_rn(x.x, h.y), __fmul_rn(x.y, h.x));
+    if (k < B) {
+        for (int in = y; in < n_in; in += 8) {
+            float2 p = premul[(so * n_in + in) * B + k];
+            for (int z = 1; z < zchunks; z++) {
+                float2 q = premul[(((long long)z * n_so + so) * n_in + in) * B + k];
+                p.x += q.x;
+                p.y += q.y;
             }
-            p.x = __fadd_rn(p.x, pr);
-            p.y = __fadd_rn(p.y, pi);
+            if (ir0) {
+                float2 x = ring_cur[(s * n_in + in) * ring_stride + k];
+                float2 h = __ldg(&ir0[(o * n_in + in) * ir_stride + k]);
+                float pr, pi;
+                if (k == 0) {
+                    pr = __fmul_rn(x.x, h.x);
+                    pi = __fmul_rn(x.y, h.y);
+                } else {
+                    pr = __fsub_rn(__fmul_rn(x.x, h.x), __fmul_rn(x.y, h.y));
+                    pi = __fadd_rn(__fmul_rn(x.x, h.y), __fmul_rn(x.y, h.x));
+                }
+                p.x = __fadd_rn(p.x, pr);
+                p.y = __fadd_rn(p.y, pi);
+            }
+            ar = __fadd_rn(ar, p.x);
+            ai = __fadd_rn(ai, p.y);
         }
-        ar = __fadd_rn(ar, p.x);
-        ai = __fadd_rn(ai, p.y);
     }
-    conv[so * B + k] = make_float2(ar, ai);
+    lane_sum[y][threadIdx.x] = make_float2(ar, ai);
+    __syncthreads();
+    if (y == 0 && k < B) {
+        float2 t = lane_sum[0][threadIdx.x];
+#pragma unroll
+        for (int l = 1; l < 8; l++) {
+            t.x = __fadd_rn(t.x, lane_sum[l][threadIdx.x].x);
+            t.y = __fadd_rn(t.y, lane_sum[l][threadIdx.x].y);
+        }
+        conv[so * B + k] = t;
+    }
 }
 
 } // namespace fcb
@@ -65,7 +87,8 @@ struct fcb_mimo {
     size_t current = 0;            // ring slot of the next block (src/fft_convolver.rs:113)
     float2 *ir = nullptr;          // [OUT*IN][seg_hi-seg_lo][B]
     float2 *ring = nullptr;        // [NS*IN][S][B]
-    float2 *premul = nullptr;      // [NS*OUT*IN][B]
+    float2 *premul = nullptr;      // [Z*NS*OUT*IN][B]  (Z segment chunks of the tile kernel, >= 1)
+    int zmax = 1;
     float2 *conv = nullptr;        // [NS*OUT][B]  (this shard's partial until all-reduced)
     float *overlap = nullptr;      // [NS*OUT][B]
     float *io_in = nullptr, *io_out = nullptr; // staging for the host-pointer call
@@ -134,7 +157,11 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
     int rc = get_twiddles(m->device, 2 * B, &m->tw);
     if (!rc) rc = mimo_alloc((void **)&m->ir, pairs * m->rows() * B * sizeof(float2), m->stream);
     if (!rc) rc = mimo_alloc((void **)&m->ring, ns * m->n_in * m->S * B * sizeof(float2), m->stream);
-    if (!rc) rc = mimo_alloc((void **)&m->premul, ns * pairs * B * sizeof(float2), m->stream);
+    {
+        int z = 1, zl = 1;
+        if (mac_tile_plan(m->logb, (int)m->n_in, (int)m->n_out, (int)ns, (int)m->rows(), &z, &zl) == FCB_OK) m->zmax = z;
+    }
+    if (!rc) rc = mimo_alloc((void **)&m->premul, (size_t)m->zmax * ns * pairs * B * sizeof(float2), m->stream);
     if (!rc) rc = mimo_alloc((void **)&m->conv, ns * m->n_out * B * sizeof(float2), m->stream);
     if (!rc) rc = mimo_alloc((void **)&m->overlap, ns * m->n_out * B * sizeof(float), m->stream);
     if (!rc) rc = mimo_alloc((void **)&m->io_in, ns * m->n_in * B * sizeof(float), m->stream);
@@ -200,28 +227,55 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
     const long long ring_stride = (long long)(m->S * B);
     FCB_TRY(run_forward(m->logb, m->tw, m->stream, in_dev, (long long)in_stride, (int)B, m->ring + m->current * B,
                         ring_stride, 1, (long long)(ns * m->n_in)));
-    MacArgs a{};
-    a.ir = m->ir;
-    a.ir_stride = (long long)(m->rows() * B);
-    a.ring = m->ring;
-    a.ring_stride = ring_stride;
-    a.premul = m->premul;
-    a.current = (int)m->current;
-    a.active = (int)m->S;
-    a.nchan = (long long)(ns * pairs);
-    a.seg_lo = (int)(m->seg_lo > 1 ? m->seg_lo : 1);
-    a.seg_hi = (int)m->seg_hi;
-    a.ir_seg0 = (int)m->seg_lo;
-    a.ir_mod = (long long)pairs;
-    a.ring_div = (long long)pairs;
-    a.ring_mul = (long long)m->n_in;
-    a.ring_mod = (long long)m->n_in;
-    FCB_TRY(run_mac(m->logb, m->stream, a));
+    const int seg_lo = (int)(m->seg_lo > 1 ? m->seg_lo : 1), seg_hi = (int)m->seg_hi;
+    const long long ir_stride = (long long)(m->rows() * B);
+    int zchunks = 1;
+    bool done = false;
+    if (g_mimo_tile.load() && m->zmax >= 1 && seg_hi > seg_lo) {
+        MacTileArgs t{};
+        t.ir = m->ir;
+        t.ir_stride = ir_stride;
+        t.ring = m->ring;
+        t.ring_stride = ring_stride;
+        t.part = m->premul;
+        t.current = (int)m->current;
+        t.active = (int)m->S;
+        t.seg_lo = seg_lo;
+        t.seg_hi = seg_hi;
+        t.ir_seg0 = (int)m->seg_lo;
+        t.n_in = (int)m->n_in;
+        t.n_out = (int)m->n_out;
+        t.n_streams = (int)ns;
+        int rc = run_mac_tile(m->logb, m->stream, t, &zchunks);
+        if (rc == FCB_OK) done = true;
+        else if (rc != FCB_ERR_UNSUPPORTED) return rc;
+        if (done && zchunks > m->zmax) return fail(FCB_ERR_CUDA, "mimo: tile plan grew past its workspace");
+    }
+    if (!done) {
+        zchunks = 1;
+        MacArgs a{};
+        a.ir = m->ir;
+        a.ir_stride = ir_stride;
+        a.ring = m->ring;
+        a.ring_stride = ring_stride;
+        a.premul = m->premul;
+        a.current = (int)m->current;
+        a.active = (int)m->S;
+        a.nchan = (long long)(ns * pairs);
+        a.seg_lo = seg_lo;
+        a.seg_hi = seg_hi;
+        a.ir_seg0 = (int)m->seg_lo;
+        a.ir_mod = (long long)pairs;
+        a.ring_div = (long long)pairs;
+        a.ring_mul = (long long)m->n_in;
+        a.ring_mod = (long long)m->n_in;
+        FCB_TRY(run_mac(m->logb, m->stream, a));
+    }
     const bool owns0 = m->seg_lo == 0 && m->seg_hi > 0;
-    const long long n_so = (long long)(ns * m->n_out), total = n_so * (long long)B;
-    k_mimo_reduce<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(
-        m->premul, m->ring + m->current * B, ring_stride, owns0 ? m->ir : nullptr, a.ir_stride, m->conv, (int)B,
-        (int)m->n_in, (int)m->n_out, n_so);
+    const long long n_so = (long long)(ns * m->n_out);
+    k_mimo_reduce<<<(unsigned)(n_so * ((B + 31) / 32)), dim3(32, 8), 0, m->stream>>>(
+        m->premul, m->ring + m->current * B, ring_stride, owns0 ? m->ir : nullptr, ir_stride, m->conv, (int)B,
+        (int)m->n_in, (int)m->n_out, n_so, zchunks);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;

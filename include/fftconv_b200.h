@@ -54,7 +54,8 @@ int fcb_device_count(void);
 
 /* tuning knobs for benchmarking sweeps: "mac_impl" (0 auto, 1 LDG kernel, 2 TMA pipeline),
  * "mac_stages" (2, 3, 4, 6 pipeline stages of 32 KB), "pipe_group" (channels per group of the
- * end-to-end copy/compute pipeline, default 512) */
+ * end-to-end copy/compute pipeline, default 512), "mimo_tile" (1 = matrix K2 with in-CTA reuse of
+ * IR and ring tiles, 0 = the per-channel K2) */
 int fcb_tune(const char *key, int value);
 
 /* live timing of the K2 launches: while enabled every K2 launch is bracketed by CUDA events on

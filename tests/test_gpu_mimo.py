@@ -112,3 +112,29 @@ def test_nccl_sharded_mimo_two_gpus():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "mimo nccl check" in r.stdout
+
+
+@pytest.mark.parametrize("n_streams,B", [(1, 512), (5, 64), (4, 1024)])
+def test_tile_kernel_matches_generic_k2(F, n_streams, B):
+    """matrix K2 with in-CTA reuse (k_mac_tile) vs the per-channel K2: same sums, different
+    association — equal to f32 rounding, and both within tolerance of the oracle"""
+    from fft_convolution_b200 import _lib
+    lib = _lib.load()
+    n_out, n_in, L = 5, 3, B * 21 + 3
+    h = _irs(n_out, n_in, L)
+    x = np.stack([oracle.gen_noise(400 + i, 0, B * 8) for i in range(n_streams * n_in)])
+    outs = {}
+    for tile in (1, 0):
+        _lib.check(lib.fcb_tune(b"mimo_tile", tile))
+        g = F.MimoConvolver.init(h, B, L, n_streams=n_streams)
+        y = np.zeros((n_streams * n_out, B * 8), np.float32)
+        blk_out = np.zeros((n_streams * n_out, B), np.float32)
+        for b in range(8):
+            g.process(np.ascontiguousarray(x[:, b * B:(b + 1) * B]), blk_out)
+            y[:, b * B:(b + 1) * B] = blk_out
+        outs[tile] = y
+    _lib.check(lib.fcb_tune(b"mimo_tile", 1))
+    ref = MimoOracle(h, B, L).process(x[:n_in])
+    r = rms(ref)
+    assert np.max(np.abs(outs[1][:n_out] - ref)) <= 2 * TOL * r
+    assert np.max(np.abs(outs[1] - outs[0])) <= 2 * TOL * r
