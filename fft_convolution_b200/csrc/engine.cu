@@ -667,7 +667,9 @@ extern "C" int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, 
     if (!in_dev || !out_dev) return fail(FCB_ERR_ARG, "process_block: NULL argument");
     if (active == 0) return FCB_OK;
     FCB_CUDA(cudaSetDevice(e->device));
-    // K1 straight from the caller's block: a full block leaves the input buffer empty again (:294-295)
+    // K1 straight from the caller's block: a full block leaves the input buffer empty again (:294-295).
+    // (Running K1 on a side stream underneath K2 was measured in round 1: no gain — K1 then competes
+    // with the HBM-bound K2 for the same bandwidth.)
     FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, in_dev, (long long)in_stride, (int)e->B,
                                                           e->ring + current * e->B, e->ring_stride(), 1,
                                                           (long long)e->C)));

@@ -49,6 +49,9 @@ struct FftPlan {
     static constexpr int TPB = CTA / T;                             // transforms per CTA
     static constexpr int SMEM_PER = sidx(B) + 1;                    // float2 per transform
     static constexpr size_t SMEM_BYTES = (size_t)TPB * SMEM_PER * sizeof(float2);
+    // (tried in round 1: capping at 32 registers for 8 CTAs/SM — spills made K1/K5 slower, K3 only
+    // 12 % faster; left at the natural 40 registers / 6 CTAs per SM)
+    static constexpr int MIN_CTAS = 1;
 };
 
 // radix of pass `p` for a 2^LOGB-point transform, 0 when past the last pass
@@ -172,7 +175,7 @@ __device__ __forceinline__ void stockham_all(float2 *s, int tid, const float2 *_
 // K5 uses nseg = S,  len = IR length                         (:145-156, :207-226).
 // ========================================================================================
 template <int LOGB>
-__global__ void __launch_bounds__(FftPlan<LOGB>::CTA)
+__global__ void __launch_bounds__(FftPlan<LOGB>::CTA, FftPlan<LOGB>::MIN_CTAS)
 k_rfft_forward(const float *__restrict__ src, long long src_stride, int len, float2 *__restrict__ dst,
                long long dst_stride, int nseg, long long ntransforms, const float2 *__restrict__ tw)
 {
@@ -246,7 +249,7 @@ struct IfftArgs {
 };
 
 template <int LOGB>
-__global__ void __launch_bounds__(FftPlan<LOGB>::CTA)
+__global__ void __launch_bounds__(FftPlan<LOGB>::CTA, FftPlan<LOGB>::MIN_CTAS)
 k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
 {
     using P = FftPlan<LOGB>;
