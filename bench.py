@@ -247,6 +247,10 @@ def run_b200(args) -> None:
         _lib.check(lib.fcb_tune(b"mac_stages", args.mac_stages))
     if args.pipe_group is not None:
         _lib.check(lib.fcb_tune(b"pipe_group", args.pipe_group))
+    fused = args.fused != 0 and args.block <= 512 and args.block >= 32
+    _lib.check(lib.fcb_tune(b"fused_block", 1 if fused else 0))
+    if args.fused_stages is not None:
+        _lib.check(lib.fcb_tune(b"fused_stages", args.fused_stages))
 
     Cn, B = args.channels, args.block
     L = int(args.ir_seconds * SAMPLE_RATE)
@@ -335,25 +339,36 @@ def run_b200(args) -> None:
     value = aggregate_value(world, Cn, args.steps, B, ms_max)
     e2e_value = aggregate_value(world, Cn, args.steps, B, e2e_ms_max)
 
-    # ---- roofline of the dominant kernel (K2) --------------------------------------------------
-    # algorithmic bytes per K2 launch: per channel 16*(S-1)*K read (IR rows + ring rows of segments
-    # 1..S-1; SURVEY §8(d)'s 16*S*K with segment 0 moved into K3) + 8*K pre_multiplied written
-    bytes_per_launch = Cn * (16 * (S - 1) * K + 8 * K)
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    # K2 (three-launch path): per channel 16*(S-1)*K read (IR rows + ring rows of segments 1..S-1;
+    # SURVEY §8(d)'s 16*S*K with segment 0 moved into K3) + 8*K pre_multiplied written.
+    # Fused kernel: the same MAC stream plus everything K1 and K3 touch — 8*K IR segment 0 read,
+    # 8*K ring slot written, 4*B input read, 4*B overlap read, 4*B overlap written, 4*B output written.
+    mac_bytes = 16 * (S - 1) * K
+    if fused:
+        bytes_per_launch = Cn * (mac_bytes + 8 * K + 8 * K + 16 * B)
+        kname = "k_block_fused (K1+K2+K3 in one launch; K2's delay-line MAC is %.1f %% of its bytes)" % (
+            100.0 * mac_bytes / (mac_bytes + 16 * K + 16 * B))
+    else:
+        bytes_per_launch = Cn * (mac_bytes + 8 * K)
+        kname = "k_mac_bulk (K2: delay-line complex MAC)"
     k2_ms = tot_ms.value / max(nl.value, 1)
     achieved = bytes_per_launch / (k2_ms / 1000.0) / 1e9
     peak, peak_src = measured_peak_gbs()
     traffic = None
-    tp = ROOT / "profiles" / "k2_traffic.json"
+    tp = ROOT / "profiles" / ("fused_traffic.json" if fused else "k2_traffic.json")
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            t = json.loads(tp.read_text())
+            if t.get("channels") == Cn:
+                traffic = t.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_mac (K2: delay-line complex MAC)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": k2_ms, "launches_timed": int(nl.value),
-                "k2_share_of_step": tot_ms.value / ms if ms > 0 else None}
+                "kernel_share_of_step": tot_ms.value / ms if ms > 0 else None}
 
     if rank == 0:
         cpu_baseline = None
@@ -369,7 +384,7 @@ def run_b200(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, {"segments": S, "mac_impl": args.mac_impl, "mac_stages": args.mac_stages,
+            "config": config_dict(args, {"segments": S, "mac_impl": args.mac_impl, "mac_stages": args.mac_stages, "fused_block": bool(fused),
                                          "ir_gen_s": round(t_gen, 1)}),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
@@ -399,6 +414,8 @@ def main():
     ap.add_argument("--mac-impl", type=int, default=None)
     ap.add_argument("--mac-stages", type=int, default=None)
     ap.add_argument("--pipe-group", type=int, default=None)
+    ap.add_argument("--fused-stages", type=int, default=None)
+    ap.add_argument("--fused", type=int, default=1, help="1: one fused K1+K2+K3 kernel per block (default), 0: three launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -180,7 +180,9 @@ extern "C" int fcb_profile_mac_read(double *total_ms, uint64_t *launches)
 static std::atomic<int> g_mac_impl{0};   // 0 = auto (TMA pipeline for B >= 32), 1 = LDG, 2 = TMA
 static std::atomic<int> g_mac_stages{3}; // 2, 3, 4 or 6
 static std::atomic<int> g_pipe_group{512}; // channels per group of the end-to-end pipeline
-namespace fcb { std::atomic<bool> g_mimo_tile{true}; } // matrix K2 with in-CTA reuse (0: generic K2)
+namespace fcb { std::atomic<bool> g_mimo_tile{true}; }
+static std::atomic<int> g_fused_stages{2}; // 2 stages (64 KB) -> 3 CTAs/SM: measured best (0.886 vs 0.890 ms)
+static std::atomic<bool> g_fused_block{true}; // whole blocks with B in 32..512: one fused K1+K2+K3 kernel // matrix K2 with in-CTA reuse (0: generic K2)
 
 template <int B, int NST>
 static int launch_mac_bulk(const MacArgs &a, cudaStream_t st)
@@ -236,6 +238,72 @@ static int launch_mac_t(const MacArgs &a, cudaStream_t st)
     g_launches++;
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;
+}
+
+// whole block, channels [c0, c0+nc): fused K1+K2+K3 (B in 32..512); false = not applicable
+template <int LOGB, int NST>
+static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, size_t nc, const float *in_dev,
+                              size_t in_stride, float *out_dev, size_t out_stride, size_t current, size_t active,
+                              const fcb_epilogue *epi)
+{
+    using Cfg = FusedCfg<LOGB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        FCB_CUDA(cudaFuncSetAttribute(k_block_fused<LOGB, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)Cfg::smem_bytes(NST)));
+        attr_done = true;
+    }
+    const size_t B = e->B;
+    FusedArgs fa{};
+    fa.in = in_dev + c0 * in_stride;
+    fa.in_stride = (long long)in_stride;
+    fa.mac.ir = e->ir + (e->shared_ir ? 0 : c0) * (long long)(e->S * B);
+    fa.mac.ir_stride = e->ir_stride();
+    fa.mac.ring = e->ring + c0 * e->ring_stride();
+    fa.mac.ring_stride = e->ring_stride();
+    fa.mac.current = (int)current;
+    fa.mac.active = (int)active;
+    fa.mac.nchan = (long long)nc;
+    fa.mac.seg_lo = 1;
+    fa.mac.seg_hi = (int)active;
+    fa.ifft.overlap = e->overlap + c0 * B;
+    fa.ifft.out = out_dev + c0 * out_stride;
+    fa.ifft.out_stride = (long long)out_stride;
+    if (epi) {
+        fa.ifft.epi = *epi;
+        if (fa.ifft.epi.add0) fa.ifft.epi.add0 += c0 * epi->add_stride;
+        if (fa.ifft.epi.add1) fa.ifft.epi.add1 += c0 * epi->add_stride;
+        if (fa.ifft.epi.mix_other) fa.ifft.epi.mix_other += c0 * epi->mix_stride;
+    }
+    cudaEvent_t prof_stop = nullptr;
+    const bool profiled = prof_before(st, &prof_stop) != nullptr;
+    const unsigned grid = (unsigned)((nc + Cfg::CPB - 1) / Cfg::CPB);
+    k_block_fused<LOGB, NST><<<grid, 256, Cfg::smem_bytes(NST), st>>>(fa, e->tw);
+    if (profiled) cudaEventRecord(prof_stop, st);
+    g_launches++;
+    FCB_CUDA(cudaGetLastError());
+    return FCB_OK;
+}
+
+static bool fused_applicable(const fcb_engine *e, size_t active)
+{
+    return g_fused_block.load() && e->logb >= 5 && e->logb <= 9 && active >= 1;
+}
+
+static int run_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, size_t nc, const float *in_dev,
+                           size_t in_stride, float *out_dev, size_t out_stride, size_t current, size_t active,
+                           const fcb_epilogue *epi)
+{
+    const bool two = g_fused_stages.load() == 2; // 2 stages -> 3 CTAs/SM, 3 stages -> 2 CTAs/SM
+#define FCB_FUSED_CASE(LB)                                                                                       \
+    case LB:                                                                                                     \
+        return two ? launch_block_fused<LB, 2>(e, st, c0, nc, in_dev, in_stride, out_dev, out_stride, current, active, epi) \
+                   : launch_block_fused<LB, 3>(e, st, c0, nc, in_dev, in_stride, out_dev, out_stride, current, active, epi);
+    switch (e->logb) {
+        FCB_FUSED_CASE(5) FCB_FUSED_CASE(6) FCB_FUSED_CASE(7) FCB_FUSED_CASE(8) FCB_FUSED_CASE(9)
+    default: return fail(FCB_ERR_UNSUPPORTED, "fused block kernel: block size not covered");
+    }
+#undef FCB_FUSED_CASE
 }
 
 template <int LOGB>
@@ -340,6 +408,8 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "mac_stages") && (value == 2 || value == 3 || value == 4 || value == 6)) g_mac_stages = value;
     else if (!strcmp(key, "pipe_group") && value >= 1) g_pipe_group = value;
     else if (!strcmp(key, "mimo_tile")) g_mimo_tile = value != 0;
+    else if (!strcmp(key, "fused_block")) g_fused_block = value != 0;
+    else if (!strcmp(key, "fused_stages") && (value == 2 || value == 3)) g_fused_stages = value;
     else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);
     return FCB_OK;
 }
@@ -667,6 +737,8 @@ extern "C" int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, 
     if (!in_dev || !out_dev) return fail(FCB_ERR_ARG, "process_block: NULL argument");
     if (active == 0) return FCB_OK;
     FCB_CUDA(cudaSetDevice(e->device));
+    if (fused_applicable(e, active))
+        return run_block_fused(e, e->stream, 0, e->C, in_dev, in_stride, out_dev, out_stride, current, active, epi);
     // K1 straight from the caller's block: a full block leaves the input buffer empty again (:294-295).
     // (Running K1 on a side stream underneath K2 was measured in round 1: no gain — K1 then competes
     // with the HBM-bound K2 for the same bandwidth.)
@@ -722,6 +794,14 @@ extern "C" int fcb_engine_process_block_host(fcb_engine *e, const float *in, siz
         const size_t c0 = g * G, nc = (C - c0) < G ? (C - c0) : G;
         float *d_in = e->inbuf + c0 * B, *d_out = e->scratch + c0 * B;
         FCB_CUDA(cudaStreamWaitEvent(st, e->pipe_in[g], 0));
+        if (fused_applicable(e, active)) {
+            FCB_TRY(run_block_fused(e, st, c0, nc, e->inbuf, B, e->scratch, B, current, active, nullptr));
+            FCB_CUDA(cudaEventRecord(e->pipe_out[g], st));
+            FCB_CUDA(cudaStreamWaitEvent(s_out, e->pipe_out[g], 0));
+            FCB_CUDA(cudaMemcpy2DAsync(out + c0 * out_stride, out_stride * sizeof(float), d_out, B * sizeof(float),
+                                       B * sizeof(float), nc, cudaMemcpyDeviceToHost, s_out));
+            continue;
+        }
         FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, d_in, (long long)B, (int)B,
                                                               e->ring + c0 * e->ring_stride() + current * B,
                                                               e->ring_stride(), 1, (long long)nc, st)));

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "fft_kernels.cuh"
 #include "mac_kernels.cuh"
+#include "fused_kernel.cuh"
 
 namespace fcb {
 

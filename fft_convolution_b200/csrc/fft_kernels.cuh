@@ -122,7 +122,7 @@ __device__ __forceinline__ void dftR(float2 (&v)[R])
 // ---- one Stockham pass over a transform resident in shared memory ------------------------
 // s: this transform's padded buffer; tid in [0, T); tw: table of N = 2B entries.
 template <int LOGB, int R, int DIR, int NS>
-__device__ __forceinline__ void stockham_pass(float2 *s, int tid, const float2 *__restrict__ tw)
+__device__ __forceinline__ void stockham_pass(float2 *s, int tid, const float2 *__restrict__ tw, bool work = true)
 {
     using P = FftPlan<LOGB>;
     constexpr int B = P::B, T = P::T, NB = P::E / R, Q = B / R; // butterflies per thread, stride
@@ -131,11 +131,12 @@ __device__ __forceinline__ void stockham_pass(float2 *s, int tid, const float2 *
     for (int b = 0; b < NB; b++) {
         int j = tid + b * T;
 #pragma unroll
-        for (int r = 0; r < R; r++) v[b][r] = s[sidx(j + r * Q)];
+        for (int r = 0; r < R; r++) v[b][r] = work ? s[sidx(j + r * Q)] : make_float2(0.f, 0.f);
     }
     __syncthreads();
 #pragma unroll
     for (int b = 0; b < NB; b++) {
+        if (!work) break;
         int j = tid + b * T;
         int k = j & (NS - 1);
         if constexpr (NS > 1) {
@@ -157,12 +158,12 @@ __device__ __forceinline__ void stockham_pass(float2 *s, int tid, const float2 *
 }
 
 template <int LOGB, int DIR, int PASS, int NS>
-__device__ __forceinline__ void stockham_all(float2 *s, int tid, const float2 *__restrict__ tw)
+__device__ __forceinline__ void stockham_all(float2 *s, int tid, const float2 *__restrict__ tw, bool work = true)
 {
     constexpr int R = radix_at(LOGB, PASS);
     if constexpr (R > 0) {
-        stockham_pass<LOGB, R, DIR, NS>(s, tid, tw);
-        stockham_all<LOGB, DIR, PASS + 1, NS * R>(s, tid, tw);
+        stockham_pass<LOGB, R, DIR, NS>(s, tid, tw, work);
+        stockham_all<LOGB, DIR, PASS + 1, NS * R>(s, tid, tw, work);
     }
 }
 

@@ -1,0 +1,271 @@
+// fused_kernel.cuh — one kernel per whole block (n == B, fill == 0) for B <= 512:
+// K1 (forward FFT of the new block into ring[current]), K2 (delay-line MAC, TMA pipeline) and K3
+// (segment-0 MAC, inverse FFT, /N, overlap-add, epilogue, overlap save) in the same CTA.
+//
+// Why: K1 and K3 are latency-bound (a dependent chain of FFT passes) and, launched on their own,
+// cost ~5 % of the step.  Here a CTA starts its TMA pipeline first, does the forward FFT while the
+// first stages land, and runs the inverse FFT after its stream ends while the co-resident CTA keeps
+// the HBM pipes busy; the step becomes one launch and `pre_multiplied` never leaves the chip.
+// Same arithmetic, same order as the separate kernels (src/fft_convolver.rs:248-298): outputs are
+// bit-identical to the K1 -> K2 -> K3 sequence.
+#pragma once
+
+#include "fft_kernels.cuh"
+#include "mac_kernels.cuh"
+
+namespace fcb {
+
+struct FusedArgs {
+    const float *in;      // [C][B] new block, channel stride in_stride
+    long long in_stride;
+    MacArgs mac;          // ir / ring / strides / current / active / nchan (premul unused)
+    IfftArgs ifft;        // overlap / out / out_stride / epilogue (fill = 0, n = B, complete)
+};
+
+template <int LOGB>
+struct FusedCfg {
+    static constexpr int B = 1 << LOGB;
+    static constexpr int CPB = 512 / B;              // channels per CTA (B <= 512)
+    static constexpr int R = 4;                      // rows per stage
+    static constexpr int ARR = CPB * R * B;          // float2 per array per stage (= 2048)
+    static constexpr size_t STAGE_BYTES = 2 * (size_t)ARR * sizeof(float2);
+    static constexpr int FFT_PER = (sidx(B) + 2) & ~1; // float2 per transform buffer (even: rows stay 16-byte aligned)
+    static constexpr size_t FFT_BYTES = (size_t)CPB * FFT_PER * sizeof(float2);
+    __host__ __device__ static constexpr size_t smem_bytes(int nst) { return nst * STAGE_BYTES + 64 + ((FFT_BYTES + 15) / 16) * 16; }
+};
+
+template <int LOGB, int NST>
+__global__ void __launch_bounds__(256)
+k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
+{
+    using Cfg = FusedCfg<LOGB>;
+    using P = FftPlan<LOGB>;
+    constexpr int B = Cfg::B, CPB = Cfg::CPB, R = Cfg::R, ARR = Cfg::ARR;
+    constexpr int TX = B / 2;             // MAC threads along a row (float4 each)
+    constexpr int T = P::T, E = P::E;     // FFT threads per transform, points per thread
+    static_assert(CPB * T <= 256, "FFT lanes must fit the CTA");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 *stages = reinterpret_cast<float2 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NST * Cfg::STAGE_BYTES);
+    float2 *fbuf = reinterpret_cast<float2 *>(smem_raw + NST * Cfg::STAGE_BYTES + 64);
+
+    const MacArgs &a = fa.mac;
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;                 // MAC role
+    const int fslot = tid / T, flane = tid % T;             // FFT role (threads 0 .. CPB*T-1)
+    const bool fwork = tid < CPB * T;
+    const long long c0 = (long long)blockIdx.x * CPB;
+    const int nlive = (int)((a.nchan - c0) < CPB ? (a.nchan - c0) : CPB);
+    const int cur = a.current, act = a.active, lo = a.seg_lo, hi = a.seg_hi;
+    const int niter = hi > lo ? (hi - lo + R - 1) / R : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int it) {
+        const int s = it % NST;
+        const int i0 = lo + it * R;
+        const int cnt = (hi - i0) < R ? (hi - i0) : R;
+        float2 *ir_s = stages + (size_t)s * 2 * ARR;
+        float2 *rg_s = ir_s + ARR;
+        mbar_expect_tx(&full[s], (uint32_t)(2 * nlive * cnt * B * sizeof(float2)));
+        const int j0 = (cur + i0) % act;
+        const int first = (act - j0) < cnt ? (act - j0) : cnt;
+        for (int ch = 0; ch < nlive; ch++) {
+            const float2 *irc = a.ir + a.ir_chan(c0 + ch) * a.ir_stride - (long long)a.ir_seg0 * B;
+            const float2 *rgc = a.ring + a.ring_chan(c0 + ch) * a.ring_stride;
+            bulk_g2s(ir_s + ch * R * B, irc + (long long)i0 * B, cnt * B * sizeof(float2), &full[s]);
+            bulk_g2s(rg_s + ch * R * B, rgc + (long long)j0 * B, first * B * sizeof(float2), &full[s]);
+            if (first < cnt) bulk_g2s(rg_s + ch * R * B + first * B, rgc, (cnt - first) * B * sizeof(float2), &full[s]);
+        }
+    };
+    // the MAC stream never touches ring[current]: start it before the forward FFT
+    if (tid == 0)
+        for (int it = 0; it < NST && it < niter; it++) issue(it);
+
+    // segment-0 IR bins of this thread, fetched now so the latency hides under the whole stream
+    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool mlive = ty < nlive;
+    if (mlive) h0 = __ldg(reinterpret_cast<const float4 *>(a.ir + a.ir_chan(c0 + ty) * a.ir_stride + (long long)(0 - a.ir_seg0) * B) + tx);
+
+    // ---- K1: forward real FFT of the new block (src/fft_convolver.rs:248-255) -------------------
+    float2 *fs = fbuf + (fwork ? fslot : 0) * Cfg::FFT_PER;
+    const bool flive = fwork && fslot < nlive;
+    if (fwork) {
+        const float *x = fa.in + (c0 + fslot) * fa.in_stride;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            int j = flane + e * T;
+            float2 z = make_float2(0.f, 0.f);
+            if (flive && 2 * j < B) z.x = __ldg(x + 2 * j);
+            if (flive && 2 * j + 1 < B) z.y = __ldg(x + 2 * j + 1);
+            fs[sidx(j)] = z;
+        }
+    }
+    __syncthreads();
+    stockham_all<LOGB, -1, 0, 1>(fs, flane, tw, fwork);
+    // split -> packed spectrum; written to ring[current] and kept in shared memory for segment 0
+    float2 xk[E];
+    if (fwork) {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            int k = flane + e * T;
+            float2 p = fs[sidx(k)];
+            if (k == 0) {
+                xk[e] = make_float2(p.x + p.y, p.x - p.y);
+            } else {
+                float2 q = cconj(fs[sidx(B - k)]);
+                float2 ev = make_float2(0.5f * (p.x + q.x), 0.5f * (p.y + q.y));
+                float2 d = make_float2(0.5f * (p.x - q.x), 0.5f * (p.y - q.y));
+                float2 od = make_float2(d.y, -d.x);
+                xk[e] = cadd(ev, cmul(od, __ldg(&tw[k])));
+            }
+        }
+    }
+    __syncthreads(); // every Z[k], Z[B-k] has been read
+    if (fwork) {
+        float2 *row = flive ? const_cast<float2 *>(a.ring) + a.ring_chan(c0 + fslot) * a.ring_stride + (long long)cur * B : nullptr;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            int k = flane + e * T;
+            fs[k] = xk[e]; // unpadded packed row: the MAC threads read it as float4
+            if (flive) row[k] = xk[e];
+        }
+    }
+    __syncthreads();
+
+    // ---- K2: delay-line MAC over segments lo..hi-1 (src/fft_convolver.rs:258-269) ---------------
+    const bool packed = (tx == 0);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < niter; it++) {
+        const int s = it % NST;
+        mbar_wait(&full[s], (it / NST) & 1);
+        const int i0 = lo + it * R;
+        const int cnt = (hi - i0) < R ? (hi - i0) : R;
+        const float4 *ir_s = reinterpret_cast<const float4 *>(stages + (size_t)s * 2 * ARR + ty * R * B) + tx;
+        const float4 *rg_s = ir_s + ARR / 2;
+        if (mlive) {
+            if (cnt == R) {
+                float4 h[R], x[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    h[r] = ir_s[r * TX];
+                    x[r] = rg_s[r * TX];
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    cmac_ref(acc.x, acc.y, h[r].x, h[r].y, x[r].x, x[r].y, packed);
+                    cmac_ref(acc.z, acc.w, h[r].z, h[r].w, x[r].z, x[r].w, false);
+                }
+            } else {
+                for (int r = 0; r < cnt; r++) {
+                    float4 h = ir_s[r * TX], x = rg_s[r * TX];
+                    cmac_ref(acc.x, acc.y, h.x, h.y, x.x, x.y, packed);
+                    cmac_ref(acc.z, acc.w, h.z, h.w, x.z, x.w, false);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && it + NST < niter) issue(it + NST);
+    }
+
+    // ---- K3: conv = pre_multiplied + X[current] * H[0] (:270-275), inverse FFT, overlap-add ------
+    float4 conv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mlive) {
+        const float4 x = reinterpret_cast<const float4 *>(fbuf + ty * Cfg::FFT_PER)[tx];
+        conv = acc;
+        // the reference multiplies segments[current] (a) by segments_ir[0] (b): im = a.re*b.im + a.im*b.re
+        cmac_ref(conv.x, conv.y, x.x, x.y, h0.x, h0.y, packed);
+        cmac_ref(conv.z, conv.w, x.z, x.w, h0.z, h0.w, false);
+    }
+    __syncthreads(); // all X[current] rows consumed before the buffer is reused
+    if (mlive) {
+        float2 *d = fbuf + ty * Cfg::FFT_PER;
+        d[sidx(2 * tx)] = make_float2(conv.x, conv.y);
+        d[sidx(2 * tx + 1)] = make_float2(conv.z, conv.w);
+    } else if (ty < CPB) {
+        float2 *d = fbuf + ty * Cfg::FFT_PER;
+        d[sidx(2 * tx)] = make_float2(0.f, 0.f);
+        d[sidx(2 * tx + 1)] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    // pre-split in place (same code path as k_irfft_ola)
+    if (fwork) {
+        constexpr int HALF = B / 2;
+        constexpr int PAIRS = HALF >= T ? HALF / T : 1;
+#pragma unroll
+        for (int e = 0; e < PAIRS; e++) {
+            int k = flane + e * T;
+            if (k < HALF) {
+                if (k == 0) {
+                    float2 x = fs[0];
+                    fs[0] = make_float2(x.x + x.y, x.x - x.y);
+                    float2 m = fs[sidx(HALF)];
+                    fs[sidx(HALF)] = make_float2(2.f * m.x, -2.f * m.y);
+                } else {
+                    float2 p = fs[sidx(k)], q = fs[sidx(B - k)];
+                    float2 w = __ldg(&tw[k]);
+                    w.y = -w.y;
+                    float2 sm = make_float2(p.x + q.x, p.y - q.y);
+                    float2 df = make_float2(p.x - q.x, p.y + q.y);
+                    float2 t = cmul(df, w);
+                    fs[sidx(k)] = make_float2(sm.x - t.y, sm.y + t.x);
+                    float2 sm2 = make_float2(sm.x, -sm.y);
+                    float2 df2 = make_float2(-df.x, df.y);
+                    float2 w2 = make_float2(-w.x, w.y);
+                    float2 t2 = cmul(df2, w2);
+                    fs[sidx(B - k)] = make_float2(sm2.x - t2.y, sm2.y + t2.x);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    stockham_all<LOGB, +1, 0, 1>(fs, flane, tw, fwork);
+
+    const IfftArgs &o = fa.ifft;
+    const float inv_n = 1.0f / (float)(2 * B);
+    const long long c = c0 + fslot;
+    if (flive) {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            int j = flane + e * T;
+            if (2 * j >= B) continue;
+            float2 z = fs[sidx(j)];
+            float y[2] = {z.x * inv_n, z.y * inv_n};
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int i = 2 * j + h;
+                float v = __fadd_rn(y[h], o.overlap[c * B + i]);
+                if (o.epi.add0) v = __fadd_rn(v, __ldg(o.epi.add0 + c * (long long)o.epi.add_stride + i));
+                if (o.epi.add1) v = __fadd_rn(v, __ldg(o.epi.add1 + c * (long long)o.epi.add_stride + i));
+                if (o.epi.mix_other) {
+                    float2 g = __ldg(reinterpret_cast<const float2 *>(o.epi.gains) + i);
+                    float ot = __ldg(o.epi.mix_other + c * (long long)o.epi.mix_stride + i);
+                    if (g.x == 1.f && g.y == 0.f) {
+                    } else if (g.x == 0.f && g.y == 1.f) {
+                        v = ot;
+                    } else {
+                        v = __fadd_rn(__fmul_rn(v, g.x), __fmul_rn(ot, g.y));
+                    }
+                }
+                o.out[c * o.out_stride + i] = v;
+            }
+        }
+    }
+    __syncthreads(); // every reader of the old overlap is done
+    if (flive) {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            int j = flane + e * T;
+            if (2 * j >= B) {
+                float2 z = fs[sidx(j)];
+                *reinterpret_cast<float2 *>(o.overlap + c * B + (2 * j - B)) = make_float2(z.x * inv_n, z.y * inv_n);
+            }
+        }
+    }
+}
+
+} // namespace fcb

@@ -194,6 +194,32 @@ def test_pipelined_host_path_large_batch(F):
         assert np.max(np.abs(yb[c] - yo)) <= TOL * rms(yo)
 
 
+@pytest.mark.parametrize("B,C", [(32, 19), (64, 9), (128, 5), (256, 3), (512, 2), (512, 1)])
+def test_fused_block_kernel_is_bit_identical_to_three_kernels(F, B, C):
+    """whole blocks with B in 32..512 run as ONE fused K1+K2+K3 kernel; it must give the bits of
+    the K1 -> K2 -> K3 sequence (channel counts that leave a CTA partly empty included)"""
+    from fft_convolution_b200 import _lib
+    lib = _lib.load()
+    L = B * 7 + 3
+    irs = np.stack([oracle.gen_ir(c, 0, L) for c in range(C)])
+    x = np.stack([oracle.gen_noise(c, 0, B * 11) for c in range(C)])
+    outs = []
+    for fused in (1, 0):
+        _lib.check(lib.fcb_tune(b"fused_block", fused))
+        conv = F.FFTConvolver.init(irs, B, L)
+        y = _run(conv, x, [B, B, B // 2, B // 2, B])  # whole blocks and split blocks interleaved
+        outs.append(y)
+        if fused:  # ring / overlap state left behind must match too
+            st_f = (conv.segment(conv.current, chan=C - 1).copy(), conv.overlap(chan=C - 1).copy())
+        else:
+            st_u = (conv.segment(conv.current, chan=C - 1).copy(), conv.overlap(chan=C - 1).copy())
+    _lib.check(lib.fcb_tune(b"fused_block", 1))
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(st_f[0], st_u[0]) and np.array_equal(st_f[1], st_u[1])
+    yo = _run(oracle.FFTConvolver.init(irs[0], B, L), x[0], [B])
+    assert np.max(np.abs(outs[0][0] - yo)) <= TOL * rms(yo)
+
+
 def test_shared_ir_matches_per_channel_ir(F):
     C, B, L = 5, 64, 700
     h = oracle.gen_ir(9, 0, L)
