@@ -79,6 +79,7 @@ SIGNATURES = {
     "fcb_engine_mac": (_i, [_vp, _sz, _sz]),
     "fcb_engine_ifft_ola": (_i, [_vp, _sz, _sz, _sz, _i, _vp, _sz, C.POINTER(Epilogue)]),
     "fcb_engine_scratch": (_vp, [_vp]),
+    "fcb_engine_input_buffer": (_vp, [_vp]),
     "fcb_engine_fetch": (_i, [_vp, _vp, _sz, _vp, _sz, _sz]),
     "fcb_engine_process_block_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz, C.POINTER(Epilogue)]),
     "fcb_engine_process_block_host": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz, _sz]),

@@ -62,6 +62,8 @@ struct fcb_engine {
     cudaEvent_t pipe_done[NPIPE] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pipe_start = nullptr;
     std::vector<cudaEvent_t> pipe_in, pipe_out; // per group: input landed / output computed
+    std::vector<size_t> pipe_cut;               // group boundaries, rebuilt only when the group size changes
+    size_t pipe_cut_G = 0;
 
     long long ir_stride() const { return shared_ir ? 0 : (long long)(S * B); }
     long long ring_stride() const { return (long long)(S * B); }
@@ -572,6 +574,7 @@ extern "C" int fcb_engine_sync(fcb_engine *e)
     return FCB_OK;
 }
 extern "C" float *fcb_engine_scratch(fcb_engine *e) { return e ? e->scratch : nullptr; }
+extern "C" float *fcb_engine_input_buffer(fcb_engine *e) { return e ? e->inbuf : nullptr; }
 extern "C" size_t fcb_engine_channels(const fcb_engine *e) { return e->C; }
 extern "C" size_t fcb_engine_block_size(const fcb_engine *e) { return e->B; }
 extern "C" size_t fcb_engine_seg_count(const fcb_engine *e) { return e->S; }
@@ -770,7 +773,29 @@ extern "C" int fcb_engine_process_block_host(fcb_engine *e, const float *in, siz
     const size_t B = e->B, C = e->C;
     size_t G = group_channels ? group_channels : (size_t)g_pipe_group.load();
     if (G > C) G = C;
-    const size_t ngroups = (C + G - 1) / G;
+    // group boundaries: full groups of G with a short first and last group (G/4), so the pipeline
+    // fills and drains on a quarter-size copy instead of a full one
+    std::vector<size_t> &cut = e->pipe_cut;
+    if (e->pipe_cut_G != G) { // first call with this grouping (not in the steady state)
+    cut.clear();
+    cut.push_back(0);
+    if (C >= 4 * G && G >= 4) {
+        const size_t edge = G / 4;
+        cut.push_back(edge);
+        size_t c = edge;
+        while (c + G + edge <= C) {
+            c += G;
+            cut.push_back(c);
+        }
+        if (C - c > edge) cut.push_back(C - edge);
+        cut.push_back(C);
+    } else {
+        for (size_t c = G; c < C; c += G) cut.push_back(c);
+        cut.push_back(C);
+    }
+    e->pipe_cut_G = G;
+    }
+    const size_t ngroups = cut.size() - 1;
     while (e->pipe_in.size() < ngroups) { // grows on the first call with this grouping only
         cudaEvent_t a = nullptr, b = nullptr;
         FCB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -783,16 +808,22 @@ extern "C" int fcb_engine_process_block_host(fcb_engine *e, const float *in, siz
     cudaStream_t s_in = e->pipe[0], s_out = e->pipe[1];
     FCB_CUDA(cudaEventRecord(e->pipe_start, e->stream));
     for (int i = 0; i < fcb_engine::NPIPE; i++) FCB_CUDA(cudaStreamWaitEvent(e->pipe[i], e->pipe_start, 0));
-    for (size_t g = 0; g < ngroups; g++) {
-        const size_t c0 = g * G, nc = (C - c0) < G ? (C - c0) : G;
+    // enqueue order: copy-in of group g+1 is queued right after group g's kernel, so the first kernel
+    // is in the GPU's queue after two driver calls instead of after every copy has been queued
+    auto queue_copy_in = [&](size_t g) -> int {
+        const size_t c0 = cut[g], nc = cut[g + 1] - cut[g];
         FCB_CUDA(cudaMemcpy2DAsync(e->inbuf + c0 * B, B * sizeof(float), in + c0 * in_stride, in_stride * sizeof(float),
                                    B * sizeof(float), nc, cudaMemcpyHostToDevice, s_in));
         FCB_CUDA(cudaEventRecord(e->pipe_in[g], s_in));
-    }
+        return FCB_OK;
+    };
+    FCB_TRY(queue_copy_in(0));
+    if (ngroups > 1) FCB_TRY(queue_copy_in(1));
     for (size_t g = 0; g < ngroups; g++) {
         cudaStream_t st = e->pipe[2 + g % (fcb_engine::NPIPE - 2)];
-        const size_t c0 = g * G, nc = (C - c0) < G ? (C - c0) : G;
+        const size_t c0 = cut[g], nc = cut[g + 1] - cut[g];
         float *d_in = e->inbuf + c0 * B, *d_out = e->scratch + c0 * B;
+        if (g + 2 < ngroups) FCB_TRY(queue_copy_in(g + 2));
         FCB_CUDA(cudaStreamWaitEvent(st, e->pipe_in[g], 0));
         if (fused_applicable(e, active)) {
             FCB_TRY(run_block_fused(e, st, c0, nc, e->inbuf, B, e->scratch, B, current, active, nullptr));

@@ -178,6 +178,15 @@ extern "C" int fcb_fftconv_update(fcb_fftconv *c, const float *irs, size_t new_i
     return fcb_engine_set_ir(c->eng, 0, c->opt.shared_ir ? 1 : c->C, irs, new_ir_len, new_ir_len, 1);
 }
 
+// the same from device memory (irs_dev: [C][stride]); used by the crossfade's deferred swap
+static int fftconv_update_dev(fcb_fftconv *c, const float *irs_dev, size_t new_ir_len, size_t stride)
+{
+    if (new_ir_len > c->ir_len) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
+    if (c->ir_len == 0) return FCB_OK;
+    c->active_seg_count = (size_t)std::ceil((double)new_ir_len / (double)c->block_size);
+    return fcb_engine_set_ir_dev(c->eng, 0, c->opt.shared_ir ? 1 : c->C, irs_dev, new_ir_len, stride, 1);
+}
+
 // :310-320
 extern "C" int fcb_fftconv_reset(fcb_fftconv *c)
 {
@@ -237,7 +246,13 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
             processed += n;
             continue;
         }
-        if (!host && was_empty && complete) {
+        if (host && was_empty && complete) {
+            // whole block from host memory: one copy in, the whole-block device path (one fused
+            // kernel for B <= 512), one copy out
+            FCB_TRY(fcb_engine_push_input(c->eng, in + processed, in_stride, 0, B));
+            FCB_TRY(fcb_engine_process_block_dev(c->eng, fcb_engine_input_buffer(c->eng), B, c->d_io, B, c->current,
+                                                 c->active_seg_count, &e));
+        } else if (!host && was_empty && complete) {
             // whole block resident on the device: K1 reads the caller's buffer directly
             FCB_TRY(fcb_engine_process_block_dev(c->eng, in + processed, in_stride, dst, dst_stride, c->current,
                                                  c->active_seg_count, &e));
@@ -711,7 +726,9 @@ struct fcb_crossfade {
     Crossfader crossfader;                  // :7
     size_t C = 0, max_buffer_size = 0;
     float *buffer_a = nullptr, *buffer_b = nullptr; // device [C][max_buffer_size] :13-14
-    std::vector<float> stored_response;             // [C][stored_len] :15
+    float *stored_response = nullptr;               // DEVICE [C][stored_len] (:15): uploaded when update()
+                                                    // is called mid-fade, so the deferred swap inside
+                                                    // process() is K5 only — no host copy, no PCIe
     size_t stored_len = 0;
     bool response_pending = false;                  // :16
     cudaStream_t stream = nullptr;
@@ -729,6 +746,7 @@ extern "C" void fcb_crossfade_free(fcb_crossfade *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->buffer_a);
     cudaFree(c->buffer_b);
+    cudaFree(c->stored_response);
     cudaFree(c->d_gains);
     cudaFree(c->d_in);
     cudaFree(c->d_out);
@@ -752,7 +770,6 @@ extern "C" int fcb_crossfade_new(fcb_crossfade **out, fcb_fftconv *convolver, si
     c->b = convolver; // :30
     c->max_buffer_size = max_buffer_size;
     c->stored_len = max_response_length;
-    c->stored_response.assign(c->C * (max_response_length ? max_response_length : 1), 0.f); // :26
     c->crossfader.init(crossfade_samples, max_buffer_size < max_response_length ? max_buffer_size : max_response_length); // :31-35
     int rc = FCB_OK;
     {
@@ -770,6 +787,7 @@ extern "C" int fcb_crossfade_new(fcb_crossfade **out, fcb_fftconv *convolver, si
     cu(cudaSetDevice(c->device));
     cu(cudaMalloc(&c->buffer_a, c->C * n * sizeof(float)));
     cu(cudaMalloc(&c->buffer_b, c->C * n * sizeof(float)));
+    cu(cudaMalloc(&c->stored_response, c->C * (max_response_length ? max_response_length : 1) * sizeof(float))); // :26
     cu(cudaMalloc(&c->d_gains, n * sizeof(float2)));
     cu(cudaHostAlloc(&c->h_gains, n * sizeof(float2), cudaHostAllocDefault));
     cu(cudaMalloc(&c->d_out, c->C * n * sizeof(float)));
@@ -805,17 +823,13 @@ extern "C" int fcb_crossfade_init(fcb_crossfade **out, const float *irs, size_t 
 
 extern "C" int fcb_crossfade_is_crossfading(const fcb_crossfade *c) { return c && c->crossfader.approaching; } // :85-92
 
-// :94-105
-static int crossfade_swap(fcb_crossfade *c, const float *irs, size_t len)
+// :94-105; `on_device`: irs is the device-resident stored_response
+static int crossfade_swap(fcb_crossfade *c, const float *irs, size_t len, bool on_device)
 {
     int rc;
-    if (c->crossfader.target == 0) {
-        rc = fcb_fftconv_update(c->b, irs, len);
-        c->crossfader.fade_into(1);
-    } else {
-        rc = fcb_fftconv_update(c->a, irs, len);
-        c->crossfader.fade_into(0);
-    }
+    fcb_fftconv *idle = c->crossfader.target == 0 ? c->b : c->a;
+    rc = on_device ? fftconv_update_dev(idle, irs, len, c->stored_len) : fcb_fftconv_update(idle, irs, len);
+    c->crossfader.fade_into(c->crossfader.target == 0 ? 1 : 0);
     return rc;
 }
 
@@ -824,16 +838,21 @@ extern "C" int fcb_crossfade_update(fcb_crossfade *c, const float *irs, size_t l
 {
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
     if (!fcb_crossfade_is_crossfading(c)) {
-        int rc = crossfade_swap(c, irs, len);
+        int rc = crossfade_swap(c, irs, len, false);
         c->response_pending = false;
         return rc;
     }
     if (!(len <= c->stored_len)) return fail(FCB_ERR_PANIC, "assertion failed: response_len <= self.stored_response.len()");
-    for (size_t ch = 0; ch < c->C; ch++) {
-        float *dst = &c->stored_response[ch * c->stored_len];
-        memcpy(dst, irs + ch * len, len * sizeof(float));
-        memset(dst + len, 0, (c->stored_len - len) * sizeof(float));
-    }
+    // :61-62 — copy + zero-fill the rest, straight into the device copy (stream-ordered after any
+    // kernel still reading a previous pending response)
+    FCB_CUDA(cudaSetDevice(c->device));
+    if (len)
+        FCB_CUDA(cudaMemcpy2DAsync(c->stored_response, c->stored_len * sizeof(float), irs, len * sizeof(float),
+                                   len * sizeof(float), c->C, cudaMemcpyHostToDevice, c->stream));
+    if (c->stored_len > len)
+        FCB_CUDA(cudaMemset2DAsync(c->stored_response + len, c->stored_len * sizeof(float), 0,
+                                   (c->stored_len - len) * sizeof(float), c->C, c->stream));
+    FCB_CUDA(cudaStreamSynchronize(c->stream)); // the caller's buffer is free to change on return
     c->response_pending = true;
     return FCB_OK;
 }
@@ -845,7 +864,7 @@ extern "C" int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in, size
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
     FCB_CUDA(cudaSetDevice(c->device));
     if (!fcb_crossfade_is_crossfading(c) && c->response_pending) { // :67-70
-        FCB_TRY(crossfade_swap(c, c->stored_response.data(), c->stored_len));
+        FCB_TRY(crossfade_swap(c, c->stored_response, c->stored_len, true));
         c->response_pending = false;
     }
     const size_t M = c->max_buffer_size;

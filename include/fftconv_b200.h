@@ -143,6 +143,8 @@ int fcb_engine_ifft_ola(fcb_engine *e, size_t current, size_t fill, size_t n, in
 /* a device buffer [C][B] (channel stride B) owned by the engine, for callers that have no device
  * allocator of their own: pass it as out_dev to ifft_ola, then fetch() it */
 float *fcb_engine_scratch(fcb_engine *e);
+/* the device input buffer [C][B] that push_input fills (src/fft_convolver.rs:114) */
+float *fcb_engine_input_buffer(fcb_engine *e);
 
 /* device -> host copy of a planar result (stream-ordered, then synchronised) */
 int fcb_engine_fetch(fcb_engine *e, float *out_host, size_t host_stride, const float *src_dev,
