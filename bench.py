@@ -418,6 +418,8 @@ def main():
     ap.add_argument("--fused", type=int, default=1, help="1: one fused K1+K2+K3 kernel per block (default), 0: three launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
+    args.steps = max(args.steps, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1,0 +1,105 @@
+"""Parity at BASELINE.json's full sizes (reduced only in channel count / run length where the
+check is size-independent): every run is long enough for the segment ring to wrap, outputs are
+compared with an f64 FFT convolution of the same synthetic inputs (<= 1e-5 * output RMS), and the
+linearity / shift properties of the operator are checked on the device path itself."""
+import numpy as np
+import pytest
+
+import bench
+from refsignals import rms
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def F():
+    import fft_convolution_b200 as f
+    return f
+
+
+def truth(x, h):
+    n = x.shape[-1]
+    nfft = 1 << int(np.ceil(np.log2(n + h.shape[-1])))
+    return np.fft.irfft(np.fft.rfft(x.astype(np.float64), nfft) * np.fft.rfft(h.astype(np.float64), nfft), nfft)[..., :n]
+
+
+def run_blocks(conv, x, B):
+    y = np.zeros_like(x)
+    blk = np.zeros(x.shape[:-1] + (B,), np.float32)
+    for b in range(x.shape[-1] // B):
+        conv.process(np.ascontiguousarray(x[..., b * B:(b + 1) * B]), blk)
+        y[..., b * B:(b + 1) * B] = blk
+    return y
+
+
+def test_config3_4_shape_full_ir_ring_wraps(F):
+    """configs[3]: 2 s IR (96 000 taps, S = 188), block 512 — 24 channels, 260 blocks (> S)"""
+    C, B, L, NB = 24, 512, 96000, 260
+    h = bench.synth_irs(0, C, 0, L)
+    x = bench.synth_noise(0, C, 0, B * NB)
+    conv = F.FFTConvolver.init(h, B, L)
+    assert conv.seg_count == 188
+    y = run_blocks(conv, x, B)
+    t = truth(x, h)
+    for c in range(C):
+        assert np.max(np.abs(y[c] - t[c])) <= TOL * rms(t[c]), c
+    assert conv.current == (188 - NB % 188) % 188
+
+
+def test_config3_4_linearity_and_shift_on_device(F):
+    """size-independent properties of the operator at the full IR length"""
+    C, B, L, NB = 3, 512, 96000, 40
+    h = bench.synth_irs(7, 1, 0, L)[0]
+    x1, x2 = bench.synth_noise(1, 1, 0, B * NB)[0], bench.synth_noise(2, 1, 0, B * NB)[0]
+    a, b = np.float32(0.75), np.float32(-1.5)
+    shifted = np.concatenate([np.zeros(B, np.float32), x1[:-B]])  # delayed by exactly one block
+    xs = np.stack([x1, x2, (a * x1 + b * x2).astype(np.float32), shifted])
+    y = run_blocks(F.FFTConvolver.init(h, B, L, channels=4), xs, B)  # shared IR, 4 channels
+    r = rms(y[2])
+    assert np.max(np.abs(y[2] - (a * y[0] + b * y[1]))) <= 4 * TOL * r            # linearity
+    assert np.max(np.abs(y[3][B:] - y[0][:-B])) <= 4 * TOL * rms(y[0]) and np.all(y[3][:B] == 0)  # time invariance
+
+
+def test_config0_shape_full_run_prefix(F):
+    """configs[0]: mono, block 256, 48 000-tap IR, white noise — 400 blocks (> S = 188)"""
+    B, L, NB = 256, 48000, 400
+    h = bench.synth_irs(0, 1, 0, L)[0]
+    x = bench.synth_noise(0, 1, 0, B * NB)[0]
+    y = run_blocks(F.FFTConvolver.init(h, B, L), x, B)
+    t = truth(x, h)
+    assert np.max(np.abs(y - t)) <= TOL * rms(t)
+
+
+def test_config1_shape_twostage_full_ir(F):
+    """configs[1]: head 128, 5 s IR (240 000 taps) -> T = 8192; 4 channels, 3 tail periods"""
+    C, H, L = 4, 128, 240000
+    h = bench.synth_irs(0, C, 0, L)
+    x = bench.synth_noise(0, C, 0, H * 64 * 3 + H * 5)
+    conv = F.TwoStageFFTConvolver.init(h, H, L, async_tail=True)
+    assert conv.tail_block_size == 8192
+    n = (x.shape[1] // H) * H
+    y = run_blocks(conv, x[:, :n], H)
+    t = truth(x[:, :n], h)
+    for c in range(C):
+        assert np.max(np.abs(y[c] - t[c])) <= TOL * rms(t[c]), c
+
+
+def test_config4_shape_mimo_full_matrix(F):
+    """configs[4]: 16 x 16 matrix, 10 s IRs (480 000 taps, S = 938), block 512; 960 blocks so the
+    ring wraps; two outputs checked against the f64 sum of 16 convolutions"""
+    N, B, L, NB = 16, 512, 480000, 960
+    h = bench.synth_irs(0, N * N, 0, L).reshape(N, N, L)
+    x = bench.synth_noise(0, N, 0, B * NB)
+    m = F.MimoConvolver.init(h, B, L)
+    assert m.seg_count == 938
+    y = np.zeros((N, B * NB), np.float32)
+    blk = np.zeros((N, B), np.float32)
+    for b in range(NB):
+        m.process(np.ascontiguousarray(x[:, b * B:(b + 1) * B]), blk)
+        y[:, b * B:(b + 1) * B] = blk
+    for o in (0, 11):
+        t = np.zeros(B * NB)
+        for i in range(N):
+            t += truth(x[i], h[o, i])
+        assert np.max(np.abs(y[o] - t)) <= TOL * rms(t), o
