@@ -71,6 +71,22 @@ struct fcb_engine {
 };
 
 // ---- launch helpers ---------------------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device)
+struct SmemOptIn {
+    bool done[64] = {};
+    template <typename K>
+    int ensure(K kernel, size_t bytes)
+    {
+        int dev = 0;
+        FCB_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            FCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+        return FCB_OK;
+    }
+};
+
 #define FCB_DISPATCH_LOGB(logb, CALL)                                                       \
     switch (logb) {                                                                         \
     case 0: { constexpr int LB = 0; CALL; } break;                                          \
@@ -96,12 +112,8 @@ static int launch_forward_t(const float2 *tw, cudaStream_t st, const float *src,
                             float2 *dst, long long dst_stride, int nseg, long long ntransforms)
 {
     using P = FftPlan<LOGB>;
-    static bool attr_done = false;
-    if (!attr_done && P::SMEM_BYTES > 48 * 1024) {
-        FCB_CUDA(cudaFuncSetAttribute(k_rfft_forward<LOGB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)P::SMEM_BYTES));
-        attr_done = true;
-    }
+    static SmemOptIn optin;
+    if (P::SMEM_BYTES > 48 * 1024) FCB_TRY(optin.ensure(k_rfft_forward<LOGB>, P::SMEM_BYTES));
     if (ntransforms <= 0) return FCB_OK;
     long long grid = (ntransforms + P::TPB - 1) / P::TPB;
     k_rfft_forward<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, st>>>(src, src_stride, len, dst, dst_stride, nseg,
@@ -115,12 +127,8 @@ template <int LOGB>
 static int launch_inverse_t(const float2 *tw, cudaStream_t st, const IfftArgs &a)
 {
     using P = FftPlan<LOGB>;
-    static bool attr_done = false;
-    if (!attr_done && P::SMEM_BYTES > 48 * 1024) {
-        FCB_CUDA(cudaFuncSetAttribute(k_irfft_ola<LOGB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)P::SMEM_BYTES));
-        attr_done = true;
-    }
+    static SmemOptIn optin;
+    if (P::SMEM_BYTES > 48 * 1024) FCB_TRY(optin.ensure(k_irfft_ola<LOGB>, P::SMEM_BYTES));
     long long grid = (a.nchan + P::TPB - 1) / P::TPB;
     k_irfft_ola<LOGB><<<(unsigned)grid, P::CTA, P::SMEM_BYTES, st>>>(a, tw);
     g_launches++;
@@ -184,18 +192,15 @@ static std::atomic<int> g_mac_stages{3}; // 2, 3, 4 or 6
 static std::atomic<int> g_pipe_group{512}; // channels per group of the end-to-end pipeline
 namespace fcb { std::atomic<bool> g_mimo_tile{true}; }
 static std::atomic<int> g_fused_stages{2}; // 2 stages (64 KB) -> 3 CTAs/SM: measured best (0.886 vs 0.890 ms)
+static std::atomic<int> g_fused_rows{4};
 static std::atomic<bool> g_fused_block{true}; // whole blocks with B in 32..512: one fused K1+K2+K3 kernel // matrix K2 with in-CTA reuse (0: generic K2)
 
 template <int B, int NST>
 static int launch_mac_bulk(const MacArgs &a, cudaStream_t st)
 {
     using Cfg = MacBulkCfg<B>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        FCB_CUDA(cudaFuncSetAttribute(k_mac_bulk<B, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)Cfg::smem_bytes(NST)));
-        attr_done = true;
-    }
+    static SmemOptIn optin;
+    FCB_TRY(optin.ensure(k_mac_bulk<B, NST>, Cfg::smem_bytes(NST)));
     long long groups = (a.nchan + Cfg::CPB - 1) / Cfg::CPB;
     k_mac_bulk<B, NST><<<(unsigned)(groups * Cfg::TILES), 256, Cfg::smem_bytes(NST), st>>>(a);
     return FCB_OK;
@@ -243,18 +248,14 @@ static int launch_mac_t(const MacArgs &a, cudaStream_t st)
 }
 
 // whole block, channels [c0, c0+nc): fused K1+K2+K3 (B in 32..512); false = not applicable
-template <int LOGB, int NST>
+template <int LOGB, int NST, int ROWS = 4>
 static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, size_t nc, const float *in_dev,
                               size_t in_stride, float *out_dev, size_t out_stride, size_t current, size_t active,
                               const fcb_epilogue *epi)
 {
-    using Cfg = FusedCfg<LOGB>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        FCB_CUDA(cudaFuncSetAttribute(k_block_fused<LOGB, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)Cfg::smem_bytes(NST)));
-        attr_done = true;
-    }
+    using Cfg = FusedCfg<LOGB, ROWS>;
+    static SmemOptIn optin;
+    FCB_TRY(optin.ensure(k_block_fused<LOGB, NST, ROWS>, Cfg::smem_bytes(NST)));
     const size_t B = e->B;
     FusedArgs fa{};
     fa.in = in_dev + c0 * in_stride;
@@ -280,7 +281,7 @@ static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, s
     cudaEvent_t prof_stop = nullptr;
     const bool profiled = prof_before(st, &prof_stop) != nullptr;
     const unsigned grid = (unsigned)((nc + Cfg::CPB - 1) / Cfg::CPB);
-    k_block_fused<LOGB, NST><<<grid, 256, Cfg::smem_bytes(NST), st>>>(fa, e->tw);
+    k_block_fused<LOGB, NST, ROWS><<<grid, 256, Cfg::smem_bytes(NST), st>>>(fa, e->tw);
     if (profiled) cudaEventRecord(prof_stop, st);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
@@ -296,6 +297,15 @@ static int run_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, size
                            size_t in_stride, float *out_dev, size_t out_stride, size_t current, size_t active,
                            const fcb_epilogue *epi)
 {
+    // experiment hook: B = 512 with other (rows per stage, stages) shapes
+    if (e->logb == 9 && g_fused_rows.load() != 4) {
+        const int r = g_fused_rows.load(), n = g_fused_stages.load();
+#define FCB_SHAPE(RR, NN)                                                                                      \
+    if (r == RR && n == NN)                                                                                    \
+        return launch_block_fused<9, NN, RR>(e, st, c0, nc, in_dev, in_stride, out_dev, out_stride, current, active, epi);
+        FCB_SHAPE(2, 2) FCB_SHAPE(2, 3) FCB_SHAPE(2, 4) FCB_SHAPE(2, 6) FCB_SHAPE(8, 2) FCB_SHAPE(1, 4) FCB_SHAPE(1, 8)
+#undef FCB_SHAPE
+    }
     const bool two = g_fused_stages.load() == 2; // 2 stages -> 3 CTAs/SM, 3 stages -> 2 CTAs/SM
 #define FCB_FUSED_CASE(LB)                                                                                       \
     case LB:                                                                                                     \
@@ -348,12 +358,8 @@ template <int B, int OT, int ST>
 static int launch_mac_tile(const MacTileArgs &a, cudaStream_t st)
 {
     using Cfg = MacTileCfg<B, OT, ST>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        FCB_CUDA(cudaFuncSetAttribute(k_mac_tile<B, OT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)Cfg::SMEM_BYTES));
-        attr_done = true;
-    }
+    static SmemOptIn optin;
+    FCB_TRY(optin.ensure(k_mac_tile<B, OT, ST>, Cfg::SMEM_BYTES));
     const long long OG = (a.n_out + OT - 1) / OT, SG = (a.n_streams + ST - 1) / ST;
     const long long grid = (long long)Cfg::TILES * a.zchunks * OG * a.n_in * SG;
     cudaEvent_t prof_stop = nullptr;
@@ -411,7 +417,8 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "pipe_group") && value >= 1) g_pipe_group = value;
     else if (!strcmp(key, "mimo_tile")) g_mimo_tile = value != 0;
     else if (!strcmp(key, "fused_block")) g_fused_block = value != 0;
-    else if (!strcmp(key, "fused_stages") && (value == 2 || value == 3)) g_fused_stages = value;
+    else if (!strcmp(key, "fused_stages") && value >= 2 && value <= 8) g_fused_stages = value;
+    else if (!strcmp(key, "fused_rows") && value >= 1 && value <= 8) g_fused_rows = value;
     else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);
     return FCB_OK;
 }

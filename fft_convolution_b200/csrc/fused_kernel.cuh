@@ -22,11 +22,11 @@ struct FusedArgs {
     IfftArgs ifft;        // overlap / out / out_stride / epilogue (fill = 0, n = B, complete)
 };
 
-template <int LOGB>
+template <int LOGB, int ROWS = 4>
 struct FusedCfg {
     static constexpr int B = 1 << LOGB;
     static constexpr int CPB = 512 / B;              // channels per CTA (B <= 512)
-    static constexpr int R = 4;                      // rows per stage
+    static constexpr int R = ROWS;                   // rows (segments) per stage
     static constexpr int ARR = CPB * R * B;          // float2 per array per stage (= 2048)
     static constexpr size_t STAGE_BYTES = 2 * (size_t)ARR * sizeof(float2);
     static constexpr int FFT_PER = (sidx(B) + 2) & ~1; // float2 per transform buffer (even: rows stay 16-byte aligned)
@@ -34,11 +34,11 @@ struct FusedCfg {
     __host__ __device__ static constexpr size_t smem_bytes(int nst) { return nst * STAGE_BYTES + 64 + ((FFT_BYTES + 15) / 16) * 16; }
 };
 
-template <int LOGB, int NST>
+template <int LOGB, int NST, int ROWS = 4>
 __global__ void __launch_bounds__(256)
 k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
 {
-    using Cfg = FusedCfg<LOGB>;
+    using Cfg = FusedCfg<LOGB, ROWS>;
     using P = FftPlan<LOGB>;
     constexpr int B = Cfg::B, CPB = Cfg::CPB, R = Cfg::R, ARR = Cfg::ARR;
     constexpr int TX = B / 2;             // MAC threads along a row (float4 each)

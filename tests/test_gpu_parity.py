@@ -348,3 +348,20 @@ def test_crossfade_config3_shape(F):
         g.process(blk, og); o.process(blk[1], oo)
         worst = max(worst, float(np.max(np.abs(og[1] - oo))) / max(rms(oo), 0.05))
     assert worst <= 2e-5
+
+
+def test_engine_on_second_device(F):
+    """every entry point selects its own device (skipped on a 1-GPU box)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    B, L = 8192, 20000  # a block size that needs the >48 KB shared-memory opt-in on each device
+    h = oracle.gen_ir(1, 0, L)
+    x = oracle.gen_noise(1, 0, B * 4)
+    y0 = _run(F.FFTConvolver.init(h, B, L, device=0), x, [B])
+    y1 = _run(F.FFTConvolver.init(h, B, L, device=1), x, [B])
+    assert np.array_equal(y0, y1)
+    h2 = oracle.gen_ir(2, 0, 3000)
+    x2 = oracle.gen_noise(2, 0, 512 * 6)
+    assert np.array_equal(_run(F.FFTConvolver.init(h2, 512, 3000, device=1), x2, [512]),
+                          _run(F.FFTConvolver.init(h2, 512, 3000, device=0), x2, [512]))
