@@ -193,6 +193,8 @@ static std::atomic<int> g_pipe_group{512}; // channels per group of the end-to-e
 namespace fcb { std::atomic<bool> g_mimo_tile{true}; }
 static std::atomic<int> g_fused_stages{2}; // 2 stages (64 KB) -> 3 CTAs/SM: measured best (0.886 vs 0.890 ms)
 static std::atomic<int> g_fused_rows{4};
+static std::atomic<int> g_l2_hint{0};
+static std::atomic<bool> g_shared_reuse{true}; // shared-IR engines: stage each IR tile once per CTA
 static std::atomic<bool> g_fused_block{true}; // whole blocks with B in 32..512: one fused K1+K2+K3 kernel // matrix K2 with in-CTA reuse (0: generic K2)
 
 template <int B, int NST>
@@ -247,6 +249,9 @@ static int launch_mac_t(const MacArgs &a, cudaStream_t st)
     return FCB_OK;
 }
 
+template <int LOGB>
+static int launch_block_fused_shared(const fcb_engine *e, cudaStream_t st, FusedArgs fa, size_t nc);
+
 // whole block, channels [c0, c0+nc): fused K1+K2+K3 (B in 32..512); false = not applicable
 template <int LOGB, int NST, int ROWS = 4>
 static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, size_t nc, const float *in_dev,
@@ -269,6 +274,7 @@ static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, s
     fa.mac.nchan = (long long)nc;
     fa.mac.seg_lo = 1;
     fa.mac.seg_hi = (int)active;
+    fa.l2_hint = (g_l2_hint.load() && !e->shared_ir) ? 1 : 0; // a shared IR wants to stay in L2
     fa.ifft.overlap = e->overlap + c0 * B;
     fa.ifft.out = out_dev + c0 * out_stride;
     fa.ifft.out_stride = (long long)out_stride;
@@ -278,10 +284,31 @@ static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, s
         if (fa.ifft.epi.add1) fa.ifft.epi.add1 += c0 * epi->add_stride;
         if (fa.ifft.epi.mix_other) fa.ifft.epi.mix_other += c0 * epi->mix_stride;
     }
+    if (e->shared_ir && g_shared_reuse.load() && ROWS == 4) {
+        if constexpr (LOGB >= 7) return launch_block_fused_shared<LOGB>(e, st, fa, nc);
+    }
     cudaEvent_t prof_stop = nullptr;
     const bool profiled = prof_before(st, &prof_stop) != nullptr;
     const unsigned grid = (unsigned)((nc + Cfg::CPB - 1) / Cfg::CPB);
     k_block_fused<LOGB, NST, ROWS><<<grid, 256, Cfg::smem_bytes(NST), st>>>(fa, e->tw);
+    if (profiled) cudaEventRecord(prof_stop, st);
+    g_launches++;
+    FCB_CUDA(cudaGetLastError());
+    return FCB_OK;
+}
+
+// shared-IR engines: G = 2 channels per thread group, one IR tile per CTA
+template <int LOGB>
+static int launch_block_fused_shared(const fcb_engine *e, cudaStream_t st, FusedArgs fa, size_t nc)
+{
+    constexpr int G = 2;
+    using Cfg = FusedSharedCfg<LOGB, G>;
+    static SmemOptIn optin;
+    FCB_TRY(optin.ensure(k_block_fused_shared<LOGB, G>, Cfg::SMEM_BYTES));
+    cudaEvent_t prof_stop = nullptr;
+    const bool profiled = prof_before(st, &prof_stop) != nullptr;
+    const unsigned grid = (unsigned)((nc + Cfg::NSLOT - 1) / Cfg::NSLOT);
+    k_block_fused_shared<LOGB, G><<<grid, 256, Cfg::SMEM_BYTES, st>>>(fa, e->tw);
     if (profiled) cudaEventRecord(prof_stop, st);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
@@ -419,6 +446,8 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "fused_block")) g_fused_block = value != 0;
     else if (!strcmp(key, "fused_stages") && value >= 2 && value <= 8) g_fused_stages = value;
     else if (!strcmp(key, "fused_rows") && value >= 1 && value <= 8) g_fused_rows = value;
+    else if (!strcmp(key, "l2_hint")) g_l2_hint = value != 0;
+    else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
     else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);
     return FCB_OK;
 }

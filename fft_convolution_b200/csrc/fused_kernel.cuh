@@ -20,6 +20,7 @@ struct FusedArgs {
     long long in_stride;
     MacArgs mac;          // ir / ring / strides / current / active / nchan (premul unused)
     IfftArgs ifft;        // overlap / out / out_stride / epilogue (fill = 0, n = B, complete)
+    int l2_hint;          // 1: bulk copies carry an L2 evict-first policy (streams are read once)
 };
 
 template <int LOGB, int ROWS = 4>
@@ -65,6 +66,11 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
     }
     __syncthreads();
 
+    const uint64_t pol = fa.l2_hint ? l2_evict_first_policy() : 0;
+    auto bulk = [&](void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+        if (fa.l2_hint) bulk_g2s_hint(dst, src, bytes, bar, pol);
+        else bulk_g2s(dst, src, bytes, bar);
+    };
     auto issue = [&](int it) {
         const int s = it % NST;
         const int i0 = lo + it * R;
@@ -77,9 +83,9 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
         for (int ch = 0; ch < nlive; ch++) {
             const float2 *irc = a.ir + a.ir_chan(c0 + ch) * a.ir_stride - (long long)a.ir_seg0 * B;
             const float2 *rgc = a.ring + a.ring_chan(c0 + ch) * a.ring_stride;
-            bulk_g2s(ir_s + ch * R * B, irc + (long long)i0 * B, cnt * B * sizeof(float2), &full[s]);
-            bulk_g2s(rg_s + ch * R * B, rgc + (long long)j0 * B, first * B * sizeof(float2), &full[s]);
-            if (first < cnt) bulk_g2s(rg_s + ch * R * B + first * B, rgc, (cnt - first) * B * sizeof(float2), &full[s]);
+            bulk(ir_s + ch * R * B, irc + (long long)i0 * B, cnt * B * sizeof(float2), &full[s]);
+            bulk(rg_s + ch * R * B, rgc + (long long)j0 * B, first * B * sizeof(float2), &full[s]);
+            if (first < cnt) bulk(rg_s + ch * R * B + first * B, rgc, (cnt - first) * B * sizeof(float2), &full[s]);
         }
     };
     // the MAC stream never touches ring[current]: start it before the forward FFT
@@ -263,6 +269,259 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
             if (2 * j >= B) {
                 float2 z = fs[sidx(j)];
                 *reinterpret_cast<float2 *>(o.overlap + c * B + (2 * j - B)) = make_float2(z.x * inv_n, z.y * inv_n);
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Shared-IR variant: all channels of the engine use ONE impulse response (fcb_engine_desc.shared_ir).
+// A CTA owns G channels per thread group (CPB*G channels) and stages each IR tile ONCE per CTA —
+// the IR spectra are "staged by TMA and reused across channels that share an IR": per complex MAC
+// the CTA moves 8 + 8/(CPB*G) bytes instead of 16.  Arithmetic and order per channel are those of
+// k_block_fused, so results are bit-identical to the unshared kernels.
+// ---------------------------------------------------------------------------------------------
+template <int LOGB, int G>
+struct FusedSharedCfg {
+    static constexpr int B = 1 << LOGB;
+    static constexpr int CPB = 512 / B;
+    static constexpr int NSLOT = CPB * G;            // channels per CTA
+    static constexpr int R = 4;
+    static constexpr int ROWS = R * B;               // float2 per tile
+    static constexpr size_t STAGE_BYTES = (size_t)(1 + NSLOT) * ROWS * sizeof(float2);
+    static constexpr int NST = 2;
+    static constexpr int FFT_PER = (sidx(B) + 2) & ~1;
+    static constexpr size_t FFT_BYTES = (size_t)NSLOT * FFT_PER * sizeof(float2);
+    static constexpr size_t SMEM_BYTES = NST * STAGE_BYTES + 64 + ((FFT_BYTES + 15) / 16) * 16;
+};
+
+template <int LOGB, int G>
+__global__ void __launch_bounds__(256)
+k_block_fused_shared(FusedArgs fa, const float2 *__restrict__ tw)
+{
+    using Cfg = FusedSharedCfg<LOGB, G>;
+    using P = FftPlan<LOGB>;
+    constexpr int B = Cfg::B, CPB = Cfg::CPB, NSLOT = Cfg::NSLOT, R = Cfg::R, ROWS = Cfg::ROWS, NST = Cfg::NST;
+    constexpr int TX = B / 2;
+    constexpr int T = P::T, E = P::E;
+    constexpr int FPASS = (NSLOT * T + 255) / 256; // FFT rounds when the transforms need more than 256 threads
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 *stages = reinterpret_cast<float2 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NST * Cfg::STAGE_BYTES);
+    float2 *fbuf = reinterpret_cast<float2 *>(smem_raw + NST * Cfg::STAGE_BYTES + 64);
+
+    const MacArgs &a = fa.mac;
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX; // MAC role: thread group ty owns slots ty*G .. ty*G+G-1
+    const long long c0 = (long long)blockIdx.x * NSLOT;
+    const int nlive = (int)((a.nchan - c0) < NSLOT ? (a.nchan - c0) : NSLOT);
+    const int cur = a.current, act = a.active, lo = a.seg_lo, hi = a.seg_hi;
+    const int niter = hi > lo ? (hi - lo + R - 1) / R : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int it) {
+        const int s = it % NST;
+        const int i0 = lo + it * R;
+        const int cnt = (hi - i0) < R ? (hi - i0) : R;
+        float2 *ir_s = stages + (size_t)s * (1 + NSLOT) * ROWS;
+        float2 *rg_s = ir_s + ROWS;
+        mbar_expect_tx(&full[s], (uint32_t)((1 + nlive) * cnt * B * sizeof(float2)));
+        const int j0 = (cur + i0) % act;
+        const int first = (act - j0) < cnt ? (act - j0) : cnt;
+        bulk_g2s(ir_s, a.ir + (long long)(i0 - a.ir_seg0) * B, cnt * B * sizeof(float2), &full[s]); // ONE IR tile
+        for (int ch = 0; ch < nlive; ch++) {
+            const float2 *rgc = a.ring + a.ring_chan(c0 + ch) * a.ring_stride;
+            bulk_g2s(rg_s + ch * ROWS, rgc + (long long)j0 * B, first * B * sizeof(float2), &full[s]);
+            if (first < cnt) bulk_g2s(rg_s + ch * ROWS + first * B, rgc, (cnt - first) * B * sizeof(float2), &full[s]);
+        }
+    };
+    if (tid == 0)
+        for (int it = 0; it < NST && it < niter; it++) issue(it);
+
+    const float4 h0 = __ldg(reinterpret_cast<const float4 *>(a.ir + (long long)(0 - a.ir_seg0) * B) + tx);
+
+    // ---- K1 for the CTA's NSLOT channels (FPASS rounds of up to 256/T transforms) ----------------
+#pragma unroll
+    for (int fp = 0; fp < FPASS; fp++) {
+        const int fslot = fp * (256 / T) + tid / T, flane = tid % T;
+        const bool fwork = fslot < NSLOT;
+        const bool flive = fwork && fslot < nlive;
+        float2 *fs = fbuf + (fwork ? fslot : 0) * Cfg::FFT_PER;
+        if (fwork) {
+            const float *x = fa.in + (c0 + fslot) * fa.in_stride;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                int j = flane + e * T;
+                float2 z = make_float2(0.f, 0.f);
+                if (flive && 2 * j < B) z.x = __ldg(x + 2 * j);
+                if (flive && 2 * j + 1 < B) z.y = __ldg(x + 2 * j + 1);
+                fs[sidx(j)] = z;
+            }
+        }
+        __syncthreads();
+        stockham_all<LOGB, -1, 0, 1>(fs, flane, tw, fwork);
+        float2 xk[E];
+        if (fwork) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                int k = flane + e * T;
+                float2 p = fs[sidx(k)];
+                if (k == 0) {
+                    xk[e] = make_float2(p.x + p.y, p.x - p.y);
+                } else {
+                    float2 q = cconj(fs[sidx(B - k)]);
+                    float2 ev = make_float2(0.5f * (p.x + q.x), 0.5f * (p.y + q.y));
+                    float2 d = make_float2(0.5f * (p.x - q.x), 0.5f * (p.y - q.y));
+                    float2 od = make_float2(d.y, -d.x);
+                    xk[e] = cadd(ev, cmul(od, __ldg(&tw[k])));
+                }
+            }
+        }
+        __syncthreads();
+        if (fwork) {
+            float2 *row = flive ? const_cast<float2 *>(a.ring) + a.ring_chan(c0 + fslot) * a.ring_stride + (long long)cur * B : nullptr;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                int k = flane + e * T;
+                fs[k] = xk[e];
+                if (flive) row[k] = xk[e];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- K2: G accumulators per thread, one IR tile per stage ------------------------------------
+    const bool packed = (tx == 0);
+    float4 acc[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < niter; it++) {
+        const int s = it % NST;
+        mbar_wait(&full[s], (it / NST) & 1);
+        const int i0 = lo + it * R;
+        const int cnt = (hi - i0) < R ? (hi - i0) : R;
+        const float4 *ir_s = reinterpret_cast<const float4 *>(stages + (size_t)s * (1 + NSLOT) * ROWS) + tx;
+        const float4 *rg_s = ir_s + ROWS / 2;
+        for (int r = 0; r < cnt; r++) {
+            const float4 h = ir_s[r * TX];
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int slot = ty * G + g;
+                if (slot < nlive) {
+                    const float4 x = rg_s[(slot * ROWS) / 2 + r * TX];
+                    cmac_ref(acc[g].x, acc[g].y, h.x, h.y, x.x, x.y, packed);
+                    cmac_ref(acc[g].z, acc[g].w, h.z, h.w, x.z, x.w, false);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && it + NST < niter) issue(it + NST);
+    }
+
+    // ---- K3 --------------------------------------------------------------------------------------
+    float4 conv[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int slot = ty * G + g;
+        conv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (slot < nlive) {
+            const float4 x = reinterpret_cast<const float4 *>(fbuf + slot * Cfg::FFT_PER)[tx];
+            conv[g] = acc[g];
+            cmac_ref(conv[g].x, conv[g].y, x.x, x.y, h0.x, h0.y, packed);
+            cmac_ref(conv[g].z, conv[g].w, x.z, x.w, h0.z, h0.w, false);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int slot = ty * G + g;
+        float2 *d = fbuf + slot * Cfg::FFT_PER;
+        d[sidx(2 * tx)] = make_float2(conv[g].x, conv[g].y);
+        d[sidx(2 * tx + 1)] = make_float2(conv[g].z, conv[g].w);
+    }
+    __syncthreads();
+    const IfftArgs &o = fa.ifft;
+    const float inv_n = 1.0f / (float)(2 * B);
+#pragma unroll
+    for (int fp = 0; fp < FPASS; fp++) {
+        const int fslot = fp * (256 / T) + tid / T, flane = tid % T;
+        const bool fwork = fslot < NSLOT;
+        const bool flive = fwork && fslot < nlive;
+        float2 *fs = fbuf + (fwork ? fslot : 0) * Cfg::FFT_PER;
+        if (fwork) {
+            constexpr int HALF = B / 2;
+            constexpr int PAIRS = HALF >= T ? HALF / T : 1;
+#pragma unroll
+            for (int e = 0; e < PAIRS; e++) {
+                int k = flane + e * T;
+                if (k < HALF) {
+                    if (k == 0) {
+                        float2 x = fs[0];
+                        fs[0] = make_float2(x.x + x.y, x.x - x.y);
+                        float2 m = fs[sidx(HALF)];
+                        fs[sidx(HALF)] = make_float2(2.f * m.x, -2.f * m.y);
+                    } else {
+                        float2 p = fs[sidx(k)], q = fs[sidx(B - k)];
+                        float2 w = __ldg(&tw[k]);
+                        w.y = -w.y;
+                        float2 sm = make_float2(p.x + q.x, p.y - q.y);
+                        float2 df = make_float2(p.x - q.x, p.y + q.y);
+                        float2 t = cmul(df, w);
+                        fs[sidx(k)] = make_float2(sm.x - t.y, sm.y + t.x);
+                        float2 sm2 = make_float2(sm.x, -sm.y);
+                        float2 df2 = make_float2(-df.x, df.y);
+                        float2 w2 = make_float2(-w.x, w.y);
+                        float2 t2 = cmul(df2, w2);
+                        fs[sidx(B - k)] = make_float2(sm2.x - t2.y, sm2.y + t2.x);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        stockham_all<LOGB, +1, 0, 1>(fs, flane, tw, fwork);
+        const long long c = c0 + fslot;
+        if (flive) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                int j = flane + e * T;
+                if (2 * j >= B) continue;
+                float2 z = fs[sidx(j)];
+                float y[2] = {z.x * inv_n, z.y * inv_n};
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    int i = 2 * j + h;
+                    float v = __fadd_rn(y[h], o.overlap[c * B + i]);
+                    if (o.epi.add0) v = __fadd_rn(v, __ldg(o.epi.add0 + c * (long long)o.epi.add_stride + i));
+                    if (o.epi.add1) v = __fadd_rn(v, __ldg(o.epi.add1 + c * (long long)o.epi.add_stride + i));
+                    if (o.epi.mix_other) {
+                        float2 gn = __ldg(reinterpret_cast<const float2 *>(o.epi.gains) + i);
+                        float ot = __ldg(o.epi.mix_other + c * (long long)o.epi.mix_stride + i);
+                        if (gn.x == 1.f && gn.y == 0.f) {
+                        } else if (gn.x == 0.f && gn.y == 1.f) {
+                            v = ot;
+                        } else {
+                            v = __fadd_rn(__fmul_rn(v, gn.x), __fmul_rn(ot, gn.y));
+                        }
+                    }
+                    o.out[c * o.out_stride + i] = v;
+                }
+            }
+        }
+        __syncthreads();
+        if (flive) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                int j = flane + e * T;
+                if (2 * j >= B) {
+                    float2 z = fs[sidx(j)];
+                    *reinterpret_cast<float2 *>(o.overlap + c * B + (2 * j - B)) = make_float2(z.x * inv_n, z.y * inv_n);
+                }
             }
         }
     }

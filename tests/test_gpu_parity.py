@@ -229,6 +229,38 @@ def test_shared_ir_matches_per_channel_ir(F):
     assert np.array_equal(ys, yp)
 
 
+@pytest.mark.parametrize("B,C", [(128, 13), (256, 7), (512, 5), (512, 2)])
+def test_shared_ir_reuse_kernel_bit_identical(F, B, C):
+    """shared-IR engines with B >= 128 stage every IR tile once per CTA (k_block_fused_shared);
+    same bits as one private copy of the IR per channel, and as the same engine with reuse off"""
+    from fft_convolution_b200 import _lib
+    lib = _lib.load()
+    L = B * 9 + 11
+    h = oracle.gen_ir(21, 0, L)
+    x = np.stack([oracle.gen_noise(c, 0, B * 12) for c in range(C)])
+    sizes = [B, B, B // 4, 3 * B // 4, B]
+    ys = _run(F.FFTConvolver.init(h, B, L, channels=C), x, sizes)
+    yp = _run(F.FFTConvolver.init(np.tile(h, (C, 1)), B, L), x, sizes)
+    _lib.check(lib.fcb_tune(b"shared_reuse", 0))
+    yn = _run(F.FFTConvolver.init(h, B, L, channels=C), x, sizes)
+    _lib.check(lib.fcb_tune(b"shared_reuse", 1))
+    assert np.array_equal(ys, yp) and np.array_equal(ys, yn)
+    yo = _run(oracle.FFTConvolver.init(h, B, L), x[C - 1], sizes)
+    assert np.max(np.abs(ys[C - 1] - yo)) <= TOL * rms(yo)
+
+
+def test_more_than_65535_channels(F):
+    """grid and pointer arithmetic beyond 16-bit channel counts"""
+    C, B, L = 70001, 32, 70
+    h = oracle.gen_ir(3, 0, L)
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, size=(C, B * 3)).astype(np.float32)
+    y = _run(F.FFTConvolver.init(h, B, L, channels=C), x, [B])
+    for c in (0, 65535, 65536, C - 1):
+        yo = _run(oracle.FFTConvolver.init(h, B, L), x[c], [B])
+        assert np.max(np.abs(y[c] - yo)) <= TOL * max(rms(yo), 1e-3), c
+
+
 def test_clone_is_deep(F):
     B, L = 64, 500
     h = oracle.gen_ir(3, 0, L)
