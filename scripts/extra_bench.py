@@ -33,22 +33,32 @@ def timed(step, steps=200, warm=20, stream=None):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"
+    steps_ts = int(sys.argv[2]) if len(sys.argv) > 2 else 320
+    import os
+    from fft_convolution_b200 import _lib
+    for kv in filter(None, os.environ.get("FCB_TUNE", "").split(",")):
+        k, v = kv.split("=")
+        _lib.check(_lib.load().fcb_tune(k.encode(), int(v)))
     st = torch.cuda.Stream()
     x = [torch.from_numpy(bench.synth_noise(0, C, B * i, B)).cuda() for i in range(8)]
     out = torch.empty((C, B), dtype=torch.float32, device="cuda")
     # (a) shared IR
-    conv = F.FFTConvolver.init(bench.synth_irs(0, 1, 0, L)[0], B, L, channels=C, stream=st.cuda_stream)
-    ms = timed(lambda i: conv.process_dev(x[i % 8].data_ptr(), B, B, out.data_ptr(), B, B), stream=st)
-    S, K = conv.seg_count, B + 1
-    print(json.dumps({"config": f"FFTConvolver x{C} channels sharing one IR (2 s, block 512)", "ms_per_block": ms,
-                      "channel_sec_per_sec": C * B / SR / (ms / 1e3),
-                      "ring_GBs": C * 8 * (S - 1) * K / (ms / 1e3) / 1e9}), flush=True)
-    conv.close()
+    if only in ("all", "shared"):
+      conv = F.FFTConvolver.init(bench.synth_irs(0, 1, 0, L)[0], B, L, channels=C, stream=st.cuda_stream)
+      ms = timed(lambda i: conv.process_dev(x[i % 8].data_ptr(), B, B, out.data_ptr(), B, B), stream=st)
+      S, K = conv.seg_count, B + 1
+      print(json.dumps({"config": f"FFTConvolver x{C} channels sharing one IR (2 s, block 512)", "ms_per_block": ms,
+                        "channel_sec_per_sec": C * B / SR / (ms / 1e3),
+                        "ring_GBs": C * 8 * (S - 1) * K / (ms / 1e3) / 1e9}), flush=True)
+      conv.close()
+    if only not in ("all", "twostage"):
+        return
     # (b) two-stage at scale
     irs = bench.synth_irs(0, C, 0, L)
     ts = F.TwoStageFFTConvolver.init(irs, B, L, stream=st.cuda_stream, async_tail=True)
     del irs
-    ms = timed(lambda i: ts.process_dev(x[i % 8].data_ptr(), B, B, out.data_ptr(), B, B), steps=320, warm=64, stream=st)
+    ms = timed(lambda i: ts.process_dev(x[i % 8].data_ptr(), B, B, out.data_ptr(), B, B), steps=steps_ts, warm=64, stream=st)
     ts.sync()
     print(json.dumps({"config": f"TwoStageFFTConvolver x{C} independent channels, head 512, T={ts.tail_block_size}, IR 2 s, async tail",
                       "ms_per_block_mean": ms, "channel_sec_per_sec": C * B / SR / (ms / 1e3)}), flush=True)
