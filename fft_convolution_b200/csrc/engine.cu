@@ -436,6 +436,8 @@ int run_mac_tile(int logb, cudaStream_t st, MacTileArgs a, int *zchunks_out)
 }
 } // namespace fcb
 
+extern "C" void fcb_host_mirror_set_mapped_io(int on);
+
 extern "C" int fcb_tune(const char *key, int value)
 {
     if (!key) return fail(FCB_ERR_ARG, "fcb_tune: NULL key");
@@ -448,6 +450,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "fused_rows") && value >= 1 && value <= 8) g_fused_rows = value;
     else if (!strcmp(key, "l2_hint")) g_l2_hint = value != 0;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
+    else if (!strcmp(key, "mapped_io")) fcb_host_mirror_set_mapped_io(value);
     else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);
     return FCB_OK;
 }
@@ -692,7 +695,7 @@ extern "C" int fcb_engine_push_input(fcb_engine *e, const float *in, size_t stri
 }
 extern "C" int fcb_engine_push_input_dev(fcb_engine *e, const float *in, size_t stride, size_t fill, size_t n)
 {
-    return push_common(e, in, stride, fill, n, cudaMemcpyDeviceToDevice);
+    return push_common(e, in, stride, fill, n, cudaMemcpyDefault); // device or mapped-host pointer
 }
 
 static int check_sched(const fcb_engine *e, size_t current, size_t active, const char *who)

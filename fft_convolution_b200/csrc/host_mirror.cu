@@ -74,7 +74,27 @@ struct fcb_fftconv {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     float *d_io = nullptr; // device staging for host-pointer process(): [C][B] (the engine's scratch)
+    // low-latency path for small batches: pinned host buffers mapped into the device address space
+    // ([C][B] each); the kernels read the input and write the output over PCIe themselves, so a
+    // single-chunk call is: CPU copy in, one launch (whole block) or three, one sync, CPU copy out
+    float *h_in = nullptr, *h_out = nullptr;   // host views
+    float *m_in = nullptr, *m_out = nullptr;   // the same memory as seen from the device
 };
+
+static void fftconv_alloc_mapped(fcb_fftconv *c)
+{
+    const size_t bytes = c->C * c->block_size * sizeof(float);
+    if (!c->eng || bytes == 0 || bytes > ((size_t)256 << 10)) return; // small batches only
+    if (cudaHostAlloc(&c->h_in, bytes, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc(&c->h_out, bytes, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&c->m_in, c->h_in, 0) != cudaSuccess ||
+        cudaHostGetDevicePointer(&c->m_out, c->h_out, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (c->h_in) cudaFreeHost(c->h_in);
+        if (c->h_out) cudaFreeHost(c->h_out);
+        c->h_in = c->h_out = c->m_in = c->m_out = nullptr;
+    }
+}
 
 static int fftconv_make_stream(fcb_fftconv *c)
 {
@@ -109,6 +129,8 @@ extern "C" void fcb_fftconv_free(fcb_fftconv *c)
     cudaSetDevice(c->opt.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     fcb_engine_destroy(c->eng);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -133,6 +155,7 @@ extern "C" int fcb_fftconv_init(fcb_fftconv **out, const float *irs, size_t chan
     // :145-156 — K5 over the zero-padded IR (rows past ir_len come out as zeros)
     if (rc == FCB_OK) rc = fcb_engine_set_ir(c->eng, 0, c->opt.shared_ir ? 1 : channels, irs, ir_len, ir_len, 0);
     if (rc == FCB_OK) c->d_io = fcb_engine_scratch(c->eng);
+    if (rc == FCB_OK) fftconv_alloc_mapped(c);
     if (rc == FCB_OK) rc = fcb_engine_sync(c->eng);
     if (rc != FCB_OK) {
         fcb_fftconv_free(c);
@@ -159,6 +182,7 @@ extern "C" int fcb_fftconv_clone(const fcb_fftconv *s, fcb_fftconv **out)
         rc = fcb_engine_clone(s->eng, &c->eng);
         if (rc == FCB_OK) rc = fcb_engine_set_stream(c->eng, (void *)c->stream);
         if (rc == FCB_OK) c->d_io = fcb_engine_scratch(c->eng);
+        if (rc == FCB_OK) fftconv_alloc_mapped(c);
     }
     if (rc != FCB_OK) {
         fcb_fftconv_free(c);
@@ -196,6 +220,10 @@ extern "C" int fcb_fftconv_reset(fcb_fftconv *c)
     return c->eng ? fcb_engine_reset(c->eng) : FCB_OK;
 }
 
+static bool g_mapped_io = true; // fcb_tune("mapped_io", 0) forces the copy-engine path
+
+extern "C" void fcb_host_mirror_set_mapped_io(int on) { g_mapped_io = on != 0; }
+
 static fcb_epilogue offset_epilogue(const fcb_epilogue *epi, size_t off)
 {
     fcb_epilogue e;
@@ -228,6 +256,15 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
     if (in_len < out_len) return fail(FCB_ERR_PANIC, "range end index %zu out of range for slice of length %zu", out_len, in_len);
     if (out_len && !in) return fail(FCB_ERR_ARG, "NULL input");
     const size_t B = c->block_size;
+    if (host && c->m_in && g_mapped_io && out_len > 0 && out_len <= B - c->input_buffer_fill) {
+        // one chunk, small batch: stage through mapped pinned memory and run the device path on it
+        const size_t n = out_len;
+        for (size_t ch = 0; ch < c->C; ch++) memcpy(c->h_in + ch * B, in + ch * in_stride, n * sizeof(float));
+        FCB_TRY(fftconv_run(c, c->m_in, n, B, c->m_out, n, B, nullptr, false));
+        FCB_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t ch = 0; ch < c->C; ch++) memcpy(out + ch * out_stride, c->h_out + ch * B, n * sizeof(float));
+        return FCB_OK;
+    }
     size_t processed = 0;
     while (processed < out_len) { // :236
         const bool was_empty = c->input_buffer_fill == 0; // :237

@@ -56,7 +56,8 @@ int fcb_device_count(void);
  * "mac_stages" (2, 3, 4, 6 pipeline stages of 32 KB), "pipe_group" (channels per group of the
  * end-to-end copy/compute pipeline, default 512), "mimo_tile" (1 = matrix K2 with in-CTA reuse of
  * IR and ring tiles, 0 = the per-channel K2), "fused_block" (1 = whole blocks with B in 32..512 run as
- * one fused K1+K2+K3 kernel, 0 = three launches; outputs are bit-identical), "fused_stages" (2 or 3) */
+ * one fused K1+K2+K3 kernel, 0 = three launches; outputs are bit-identical), "fused_stages" (2 or 3), "mapped_io" (1 = small-batch host
+ * calls go through mapped pinned memory instead of the copy engines) */
 int fcb_tune(const char *key, int value);
 
 /* live timing of the K2 launches: while enabled every K2 launch is bracketed by CUDA events on

@@ -249,6 +249,22 @@ def test_shared_ir_reuse_kernel_bit_identical(F, B, C):
     assert np.max(np.abs(ys[C - 1] - yo)) <= TOL * rms(yo)
 
 
+def test_mapped_io_path_matches_copy_path(F):
+    """small-batch host calls stage through mapped pinned memory; same bits as the copy-engine path"""
+    from fft_convolution_b200 import _lib
+    lib = _lib.load()
+    C, B, L = 3, 128, 900
+    irs = np.stack([oracle.gen_ir(c, 0, L) for c in range(C)])
+    x = np.stack([oracle.gen_noise(c, 0, B * 10) for c in range(C)])
+    sizes = [B, 50, 78, B, 200, 3]
+    ys = []
+    for on in (1, 0):
+        _lib.check(lib.fcb_tune(b"mapped_io", on))
+        ys.append(_run(F.FFTConvolver.init(irs, B, L), x, sizes))
+    _lib.check(lib.fcb_tune(b"mapped_io", 1))
+    assert np.array_equal(ys[0], ys[1])
+
+
 def test_more_than_65535_channels(F):
     """grid and pointer arithmetic beyond 16-bit channel counts"""
     C, B, L = 70001, 32, 70
