@@ -263,10 +263,6 @@ def run_b200(args) -> None:
     _lib.check(lib.fcb_tune(b"fused_block", 1 if fused else 0))
     if args.fused_stages is not None:
         _lib.check(lib.fcb_tune(b"fused_stages", args.fused_stages))
-    if args.l2_hint is not None:
-        _lib.check(lib.fcb_tune(b"l2_hint", args.l2_hint))
-    if args.fused_rows is not None:
-        _lib.check(lib.fcb_tune(b"fused_rows", args.fused_rows))
 
     Cn, B = args.channels, args.block
     L = int(args.ir_seconds * SAMPLE_RATE)
@@ -431,8 +427,6 @@ def main():
     ap.add_argument("--mac-stages", type=int, default=None)
     ap.add_argument("--pipe-group", type=int, default=None)
     ap.add_argument("--fused-stages", type=int, default=None)
-    ap.add_argument("--fused-rows", type=int, default=None)
-    ap.add_argument("--l2-hint", type=int, default=None)
     ap.add_argument("--fused", type=int, default=1, help="1: one fused K1+K2+K3 kernel per block (default), 0: three launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -192,8 +192,6 @@ static std::atomic<int> g_mac_stages{3}; // 2, 3, 4 or 6
 static std::atomic<int> g_pipe_group{512}; // channels per group of the end-to-end pipeline
 namespace fcb { std::atomic<bool> g_mimo_tile{true}; }
 static std::atomic<int> g_fused_stages{2}; // 2 stages (64 KB) -> 3 CTAs/SM: measured best (0.886 vs 0.890 ms)
-static std::atomic<int> g_fused_rows{4};
-static std::atomic<int> g_l2_hint{0};
 static std::atomic<bool> g_shared_reuse{true}; // shared-IR engines: stage each IR tile once per CTA
 static std::atomic<bool> g_fused_block{true}; // whole blocks with B in 32..512: one fused K1+K2+K3 kernel // matrix K2 with in-CTA reuse (0: generic K2)
 
@@ -274,7 +272,6 @@ static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, s
     fa.mac.nchan = (long long)nc;
     fa.mac.seg_lo = 1;
     fa.mac.seg_hi = (int)active;
-    fa.l2_hint = (g_l2_hint.load() && !e->shared_ir) ? 1 : 0; // a shared IR wants to stay in L2
     fa.ifft.overlap = e->overlap + c0 * B;
     fa.ifft.out = out_dev + c0 * out_stride;
     fa.ifft.out_stride = (long long)out_stride;
@@ -324,15 +321,6 @@ static int run_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, size
                            size_t in_stride, float *out_dev, size_t out_stride, size_t current, size_t active,
                            const fcb_epilogue *epi)
 {
-    // experiment hook: B = 512 with other (rows per stage, stages) shapes
-    if (e->logb == 9 && g_fused_rows.load() != 4) {
-        const int r = g_fused_rows.load(), n = g_fused_stages.load();
-#define FCB_SHAPE(RR, NN)                                                                                      \
-    if (r == RR && n == NN)                                                                                    \
-        return launch_block_fused<9, NN, RR>(e, st, c0, nc, in_dev, in_stride, out_dev, out_stride, current, active, epi);
-        FCB_SHAPE(2, 2) FCB_SHAPE(2, 3) FCB_SHAPE(2, 4) FCB_SHAPE(2, 6) FCB_SHAPE(8, 2) FCB_SHAPE(1, 4) FCB_SHAPE(1, 8)
-#undef FCB_SHAPE
-    }
     const bool two = g_fused_stages.load() == 2; // 2 stages -> 3 CTAs/SM, 3 stages -> 2 CTAs/SM
 #define FCB_FUSED_CASE(LB)                                                                                       \
     case LB:                                                                                                     \
@@ -446,9 +434,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "pipe_group") && value >= 1) g_pipe_group = value;
     else if (!strcmp(key, "mimo_tile")) g_mimo_tile = value != 0;
     else if (!strcmp(key, "fused_block")) g_fused_block = value != 0;
-    else if (!strcmp(key, "fused_stages") && value >= 2 && value <= 8) g_fused_stages = value;
-    else if (!strcmp(key, "fused_rows") && value >= 1 && value <= 8) g_fused_rows = value;
-    else if (!strcmp(key, "l2_hint")) g_l2_hint = value != 0;
+    else if (!strcmp(key, "fused_stages") && (value == 2 || value == 3)) g_fused_stages = value;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
     else if (!strcmp(key, "mapped_io")) fcb_host_mirror_set_mapped_io(value);
     else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);

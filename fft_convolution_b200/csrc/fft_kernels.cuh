@@ -167,6 +167,89 @@ __device__ __forceinline__ void stockham_all(float2 *s, int tid, const float2 *_
     }
 }
 
+
+// ---- pieces shared by k_rfft_forward / k_irfft_ola and the fused block kernels ---------------------
+
+// forward split of bin k from the B-point complex FFT Z of z[j] = x[2j] + i x[2j+1] (padded smem):
+// X[k] = Ev + w^k Od, Ev = (Z[k] + conj Z[B-k])/2, Od = (Z[k] - conj Z[B-k])/(2i); bin 0 is
+// packed {DC.re, Nyquist.re}
+template <int LOGB>
+__device__ __forceinline__ float2 rfft_split_bin(const float2 *s, int k, const float2 *__restrict__ tw)
+{
+    constexpr int B = 1 << LOGB;
+    float2 a = s[sidx(k)];
+    if (k == 0) return make_float2(a.x + a.y, a.x - a.y);
+    float2 b = cconj(s[sidx(B - k)]);
+    float2 ev = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
+    float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
+    float2 od = make_float2(d.y, -d.x);
+    return cadd(ev, cmul(od, __ldg(&tw[k])));
+}
+
+// inverse pre-split, in place on pairs (k, B-k) of a packed spectrum held in padded smem:
+// Z'[k] = (X[k] + conj X[B-k]) + i w^{-k} (X[k] - conj X[B-k]),  w = exp(-2 pi i / N).
+// Thread `tid` of the transform's T threads; caller synchronises before and after.
+template <int LOGB>
+__device__ __forceinline__ void irfft_presplit(float2 *s, int tid, const float2 *__restrict__ tw)
+{
+    using P = FftPlan<LOGB>;
+    constexpr int B = P::B, T = P::T, HALF = B / 2;
+    constexpr int PAIRS_PER_THREAD = HALF >= T ? HALF / T : 1; // pairs p = 0..HALF-1 (p = 0 also does k = B/2)
+#pragma unroll
+    for (int e = 0; e < PAIRS_PER_THREAD; e++) {
+        int k = tid + e * T;
+        if (B == 1) {
+            if (k == 0) {
+                float2 x = s[0];
+                s[0] = make_float2(x.x + x.y, x.x - x.y);
+            }
+        } else if (k < HALF) {
+            if (k == 0) {
+                float2 x = s[0]; // {DC, Nyquist}
+                s[0] = make_float2(x.x + x.y, x.x - x.y);
+                float2 m = s[sidx(HALF)];
+                s[sidx(HALF)] = make_float2(2.f * m.x, -2.f * m.y);
+            } else {
+                float2 p = s[sidx(k)], q = s[sidx(B - k)];
+                float2 w = __ldg(&tw[k]);
+                w.y = -w.y; // w^{-k}
+                // k:   (p + conj q) + i w^{-k} (p - conj q)
+                float2 sm = make_float2(p.x + q.x, p.y - q.y);
+                float2 df = make_float2(p.x - q.x, p.y + q.y);
+                float2 t = cmul(df, w);
+                s[sidx(k)] = make_float2(sm.x - t.y, sm.y + t.x);
+                // B-k: (q + conj p) + i w^{-(B-k)} (q - conj p),  w^{-(B-k)} = -conj(w^{-k})
+                float2 sm2 = make_float2(sm.x, -sm.y);
+                float2 df2 = make_float2(-df.x, df.y);
+                float2 w2 = make_float2(-w.x, w.y);
+                float2 t2 = cmul(df2, w2);
+                s[sidx(B - k)] = make_float2(sm2.x - t2.y, sm2.y + t2.x);
+            }
+        }
+    }
+}
+
+// output sample i of channel c: (y + overlap) then the optional fused epilogue, in the reference's
+// operation order — two-stage ((y+ov)+p0)+p1 (src/fft_convolver.rs:452-468), crossfade
+// a*g1 + b*g2 with separately rounded products (src/crossfade_convolver.rs:160-169, 242-278)
+__device__ __forceinline__ float apply_epilogue(float v, const fcb_epilogue &epi, long long c, int i)
+{
+    if (epi.add0) v = __fadd_rn(v, __ldg(epi.add0 + c * (long long)epi.add_stride + i));
+    if (epi.add1) v = __fadd_rn(v, __ldg(epi.add1 + c * (long long)epi.add_stride + i));
+    if (epi.mix_other) {
+        float2 g = __ldg(reinterpret_cast<const float2 *>(epi.gains) + i);
+        float o = __ldg(epi.mix_other + c * (long long)epi.mix_stride + i);
+        if (g.x == 1.f && g.y == 0.f) {
+            /* mine, untouched */
+        } else if (g.x == 0.f && g.y == 1.f) {
+            v = o;
+        } else {
+            v = __fadd_rn(__fmul_rn(v, g.x), __fmul_rn(o, g.y));
+        }
+    }
+    return v;
+}
+
 // ========================================================================================
 // K1 / K5: batched forward real FFT.
 // transform q -> (channel c = q / nseg, segment i = q % nseg); source = src + c*src_stride + i*B,
@@ -212,18 +295,7 @@ k_rfft_forward(const float *__restrict__ src, long long src_stride, int len, flo
 #pragma unroll
         for (int e = 0; e < E; e++) {
             int k = tid + e * T;
-            float2 a = s[sidx(k)];
-            float2 out;
-            if (k == 0) {
-                out = make_float2(a.x + a.y, a.x - a.y); // {DC.re, Nyquist.re}
-            } else {
-                float2 b = cconj(s[sidx(B - k)]);
-                float2 ev = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
-                float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
-                float2 od = make_float2(d.y, -d.x);
-                float2 w = __ldg(&tw[k]);
-                out = cadd(ev, cmul(od, w));
-            }
+            float2 out = rfft_split_bin<LOGB>(s, k, tw);
             row[k] = out;
         }
     }
@@ -286,44 +358,8 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
     }
     __syncthreads();
 
-    // 2. pre-split, in place on pairs (k, B-k):
-    //    Z'[k] = (X[k] + conj X[B-k]) + i w^{-k} (X[k] - conj X[B-k]),  w = exp(-2 pi i / N)
-    {
-        constexpr int HALF = B / 2;
-        constexpr int PAIRS_PER_THREAD = HALF >= T ? HALF / T : 1; // pairs p = 0..HALF-1 (p = 0 also does k = B/2)
-#pragma unroll
-        for (int e = 0; e < PAIRS_PER_THREAD; e++) {
-            int k = tid + e * T;
-            if (B == 1) {
-                if (k == 0) {
-                    float2 x = s[0];
-                    s[0] = make_float2(x.x + x.y, x.x - x.y);
-                }
-            } else if (k < HALF) {
-                if (k == 0) {
-                    float2 x = s[0]; // {DC, Nyquist}
-                    s[0] = make_float2(x.x + x.y, x.x - x.y);
-                    float2 m = s[sidx(HALF)];
-                    s[sidx(HALF)] = make_float2(2.f * m.x, -2.f * m.y);
-                } else {
-                    float2 p = s[sidx(k)], q = s[sidx(B - k)];
-                    float2 w = __ldg(&tw[k]);
-                    w.y = -w.y; // w^{-k}
-                    // k:   (p + conj q) + i w^{-k} (p - conj q)
-                    float2 sm = make_float2(p.x + q.x, p.y - q.y);
-                    float2 df = make_float2(p.x - q.x, p.y + q.y);
-                    float2 t = cmul(df, w);
-                    s[sidx(k)] = make_float2(sm.x - t.y, sm.y + t.x);
-                    // B-k: (q + conj p) + i w^{-(B-k)} (q - conj p),  w^{-(B-k)} = -conj(w^{-k})
-                    float2 sm2 = make_float2(sm.x, -sm.y);
-                    float2 df2 = make_float2(-df.x, df.y);
-                    float2 w2 = make_float2(-w.x, w.y);
-                    float2 t2 = cmul(df2, w2);
-                    s[sidx(B - k)] = make_float2(sm2.x - t2.y, sm2.y + t2.x);
-                }
-            }
-        }
-    }
+    // 2. pre-split, in place on pairs (k, B-k)
+    irfft_presplit<LOGB>(s, tid, tw);
     __syncthreads();
 
     // 3. unnormalised inverse complex FFT
@@ -344,20 +380,7 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
             int m = 2 * j + h;
             if (m >= lo && m < hi && m < B) {
                 int i = m - lo;
-                float v = __fadd_rn(y[h], a.overlap[c * B + m]);
-                if (a.epi.add0) v = __fadd_rn(v, __ldg(a.epi.add0 + c * (long long)a.epi.add_stride + i));
-                if (a.epi.add1) v = __fadd_rn(v, __ldg(a.epi.add1 + c * (long long)a.epi.add_stride + i));
-                if (a.epi.mix_other) {
-                    float2 g = __ldg(reinterpret_cast<const float2 *>(a.epi.gains) + i);
-                    float o = __ldg(a.epi.mix_other + c * (long long)a.epi.mix_stride + i);
-                    if (g.x == 1.f && g.y == 0.f) {
-                        /* v stays */
-                    } else if (g.x == 0.f && g.y == 1.f) {
-                        v = o;
-                    } else {
-                        v = __fadd_rn(__fmul_rn(v, g.x), __fmul_rn(o, g.y));
-                    }
-                }
+                float v = apply_epilogue(__fadd_rn(y[h], a.overlap[c * B + m]), a.epi, c, i);
                 a.out[c * a.out_stride + i] = v;
             }
         }

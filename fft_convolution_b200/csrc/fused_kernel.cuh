@@ -20,7 +20,6 @@ struct FusedArgs {
     long long in_stride;
     MacArgs mac;          // ir / ring / strides / current / active / nchan (premul unused)
     IfftArgs ifft;        // overlap / out / out_stride / epilogue (fill = 0, n = B, complete)
-    int l2_hint;          // 1: bulk copies carry an L2 evict-first policy (streams are read once)
 };
 
 template <int LOGB, int ROWS = 4>
@@ -66,11 +65,6 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
     }
     __syncthreads();
 
-    const uint64_t pol = fa.l2_hint ? l2_evict_first_policy() : 0;
-    auto bulk = [&](void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-        if (fa.l2_hint) bulk_g2s_hint(dst, src, bytes, bar, pol);
-        else bulk_g2s(dst, src, bytes, bar);
-    };
     auto issue = [&](int it) {
         const int s = it % NST;
         const int i0 = lo + it * R;
@@ -83,9 +77,9 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
         for (int ch = 0; ch < nlive; ch++) {
             const float2 *irc = a.ir + a.ir_chan(c0 + ch) * a.ir_stride - (long long)a.ir_seg0 * B;
             const float2 *rgc = a.ring + a.ring_chan(c0 + ch) * a.ring_stride;
-            bulk(ir_s + ch * R * B, irc + (long long)i0 * B, cnt * B * sizeof(float2), &full[s]);
-            bulk(rg_s + ch * R * B, rgc + (long long)j0 * B, first * B * sizeof(float2), &full[s]);
-            if (first < cnt) bulk(rg_s + ch * R * B + first * B, rgc, (cnt - first) * B * sizeof(float2), &full[s]);
+            bulk_g2s(ir_s + ch * R * B, irc + (long long)i0 * B, cnt * B * sizeof(float2), &full[s]);
+            bulk_g2s(rg_s + ch * R * B, rgc + (long long)j0 * B, first * B * sizeof(float2), &full[s]);
+            if (first < cnt) bulk_g2s(rg_s + ch * R * B + first * B, rgc, (cnt - first) * B * sizeof(float2), &full[s]);
         }
     };
     // the MAC stream never touches ring[current]: start it before the forward FFT
@@ -119,16 +113,7 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
 #pragma unroll
         for (int e = 0; e < E; e++) {
             int k = flane + e * T;
-            float2 p = fs[sidx(k)];
-            if (k == 0) {
-                xk[e] = make_float2(p.x + p.y, p.x - p.y);
-            } else {
-                float2 q = cconj(fs[sidx(B - k)]);
-                float2 ev = make_float2(0.5f * (p.x + q.x), 0.5f * (p.y + q.y));
-                float2 d = make_float2(0.5f * (p.x - q.x), 0.5f * (p.y - q.y));
-                float2 od = make_float2(d.y, -d.x);
-                xk[e] = cadd(ev, cmul(od, __ldg(&tw[k])));
-            }
+            xk[e] = rfft_split_bin<LOGB>(fs, k, tw);
         }
     }
     __syncthreads(); // every Z[k], Z[B-k] has been read
@@ -198,36 +183,7 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
         d[sidx(2 * tx + 1)] = make_float2(0.f, 0.f);
     }
     __syncthreads();
-    // pre-split in place (same code path as k_irfft_ola)
-    if (fwork) {
-        constexpr int HALF = B / 2;
-        constexpr int PAIRS = HALF >= T ? HALF / T : 1;
-#pragma unroll
-        for (int e = 0; e < PAIRS; e++) {
-            int k = flane + e * T;
-            if (k < HALF) {
-                if (k == 0) {
-                    float2 x = fs[0];
-                    fs[0] = make_float2(x.x + x.y, x.x - x.y);
-                    float2 m = fs[sidx(HALF)];
-                    fs[sidx(HALF)] = make_float2(2.f * m.x, -2.f * m.y);
-                } else {
-                    float2 p = fs[sidx(k)], q = fs[sidx(B - k)];
-                    float2 w = __ldg(&tw[k]);
-                    w.y = -w.y;
-                    float2 sm = make_float2(p.x + q.x, p.y - q.y);
-                    float2 df = make_float2(p.x - q.x, p.y + q.y);
-                    float2 t = cmul(df, w);
-                    fs[sidx(k)] = make_float2(sm.x - t.y, sm.y + t.x);
-                    float2 sm2 = make_float2(sm.x, -sm.y);
-                    float2 df2 = make_float2(-df.x, df.y);
-                    float2 w2 = make_float2(-w.x, w.y);
-                    float2 t2 = cmul(df2, w2);
-                    fs[sidx(B - k)] = make_float2(sm2.x - t2.y, sm2.y + t2.x);
-                }
-            }
-        }
-    }
+    if (fwork) irfft_presplit<LOGB>(fs, flane, tw);
     __syncthreads();
     stockham_all<LOGB, +1, 0, 1>(fs, flane, tw, fwork);
 
@@ -244,19 +200,7 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 int i = 2 * j + h;
-                float v = __fadd_rn(y[h], o.overlap[c * B + i]);
-                if (o.epi.add0) v = __fadd_rn(v, __ldg(o.epi.add0 + c * (long long)o.epi.add_stride + i));
-                if (o.epi.add1) v = __fadd_rn(v, __ldg(o.epi.add1 + c * (long long)o.epi.add_stride + i));
-                if (o.epi.mix_other) {
-                    float2 g = __ldg(reinterpret_cast<const float2 *>(o.epi.gains) + i);
-                    float ot = __ldg(o.epi.mix_other + c * (long long)o.epi.mix_stride + i);
-                    if (g.x == 1.f && g.y == 0.f) {
-                    } else if (g.x == 0.f && g.y == 1.f) {
-                        v = ot;
-                    } else {
-                        v = __fadd_rn(__fmul_rn(v, g.x), __fmul_rn(ot, g.y));
-                    }
-                }
+                float v = apply_epilogue(__fadd_rn(y[h], o.overlap[c * B + i]), o.epi, c, i);
                 o.out[c * o.out_stride + i] = v;
             }
         }
@@ -371,16 +315,7 @@ k_block_fused_shared(FusedArgs fa, const float2 *__restrict__ tw)
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 int k = flane + e * T;
-                float2 p = fs[sidx(k)];
-                if (k == 0) {
-                    xk[e] = make_float2(p.x + p.y, p.x - p.y);
-                } else {
-                    float2 q = cconj(fs[sidx(B - k)]);
-                    float2 ev = make_float2(0.5f * (p.x + q.x), 0.5f * (p.y + q.y));
-                    float2 d = make_float2(0.5f * (p.x - q.x), 0.5f * (p.y - q.y));
-                    float2 od = make_float2(d.y, -d.x);
-                    xk[e] = cadd(ev, cmul(od, __ldg(&tw[k])));
-                }
+                xk[e] = rfft_split_bin<LOGB>(fs, k, tw);
             }
         }
         __syncthreads();
@@ -454,35 +389,7 @@ k_block_fused_shared(FusedArgs fa, const float2 *__restrict__ tw)
         const bool fwork = fslot < NSLOT;
         const bool flive = fwork && fslot < nlive;
         float2 *fs = fbuf + (fwork ? fslot : 0) * Cfg::FFT_PER;
-        if (fwork) {
-            constexpr int HALF = B / 2;
-            constexpr int PAIRS = HALF >= T ? HALF / T : 1;
-#pragma unroll
-            for (int e = 0; e < PAIRS; e++) {
-                int k = flane + e * T;
-                if (k < HALF) {
-                    if (k == 0) {
-                        float2 x = fs[0];
-                        fs[0] = make_float2(x.x + x.y, x.x - x.y);
-                        float2 m = fs[sidx(HALF)];
-                        fs[sidx(HALF)] = make_float2(2.f * m.x, -2.f * m.y);
-                    } else {
-                        float2 p = fs[sidx(k)], q = fs[sidx(B - k)];
-                        float2 w = __ldg(&tw[k]);
-                        w.y = -w.y;
-                        float2 sm = make_float2(p.x + q.x, p.y - q.y);
-                        float2 df = make_float2(p.x - q.x, p.y + q.y);
-                        float2 t = cmul(df, w);
-                        fs[sidx(k)] = make_float2(sm.x - t.y, sm.y + t.x);
-                        float2 sm2 = make_float2(sm.x, -sm.y);
-                        float2 df2 = make_float2(-df.x, df.y);
-                        float2 w2 = make_float2(-w.x, w.y);
-                        float2 t2 = cmul(df2, w2);
-                        fs[sidx(B - k)] = make_float2(sm2.x - t2.y, sm2.y + t2.x);
-                    }
-                }
-            }
-        }
+        if (fwork) irfft_presplit<LOGB>(fs, flane, tw);
         __syncthreads();
         stockham_all<LOGB, +1, 0, 1>(fs, flane, tw, fwork);
         const long long c = c0 + fslot;
@@ -496,19 +403,7 @@ k_block_fused_shared(FusedArgs fa, const float2 *__restrict__ tw)
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     int i = 2 * j + h;
-                    float v = __fadd_rn(y[h], o.overlap[c * B + i]);
-                    if (o.epi.add0) v = __fadd_rn(v, __ldg(o.epi.add0 + c * (long long)o.epi.add_stride + i));
-                    if (o.epi.add1) v = __fadd_rn(v, __ldg(o.epi.add1 + c * (long long)o.epi.add_stride + i));
-                    if (o.epi.mix_other) {
-                        float2 gn = __ldg(reinterpret_cast<const float2 *>(o.epi.gains) + i);
-                        float ot = __ldg(o.epi.mix_other + c * (long long)o.epi.mix_stride + i);
-                        if (gn.x == 1.f && gn.y == 0.f) {
-                        } else if (gn.x == 0.f && gn.y == 1.f) {
-                            v = ot;
-                        } else {
-                            v = __fadd_rn(__fmul_rn(v, gn.x), __fmul_rn(ot, gn.y));
-                        }
-                    }
+                    float v = apply_epilogue(__fadd_rn(y[h], o.overlap[c * B + i]), o.epi, c, i);
                     o.out[c * o.out_stride + i] = v;
                 }
             }

@@ -146,21 +146,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "memory");
     } while (!done);
 }
-// L2 policy for data that is read exactly once per block (the IR / ring streams)
-__device__ __forceinline__ uint64_t l2_evict_first_policy()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-        : "memory");
-}
 // global -> shared bulk copy, completion counted in bytes on `bar`; bytes % 16 == 0, 16 B aligned
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {

@@ -194,6 +194,18 @@ def test_pipelined_host_path_large_batch(F):
         assert np.max(np.abs(yb[c] - yo)) <= TOL * rms(yo)
 
 
+def test_pipelined_host_path_three_kernel_engine(F):
+    """>= 1024 channels at B = 1024 (beyond the fused kernel): groups run K1, K2, K3 on the pipeline streams"""
+    C, B, L = 1030, 1024, 2100
+    h = oracle.gen_ir(8, 0, L)
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-1, 1, size=(C, B * 4)).astype(np.float32)
+    y = _run(F.FFTConvolver.init(h, B, L, channels=C), x, [B])
+    for c in (0, 511, 512, C - 1):
+        yo = _run(oracle.FFTConvolver.init(h, B, L), x[c], [B])
+        assert np.max(np.abs(y[c] - yo)) <= TOL * rms(yo), c
+
+
 @pytest.mark.parametrize("B,C", [(32, 19), (64, 9), (128, 5), (256, 3), (512, 2), (512, 1)])
 def test_fused_block_kernel_is_bit_identical_to_three_kernels(F, B, C):
     """whole blocks with B in 32..512 run as ONE fused K1+K2+K3 kernel; it must give the bits of
