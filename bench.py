@@ -261,6 +261,10 @@ def run_b200(args) -> None:
         _lib.check(lib.fcb_tune(b"pipe_group", args.pipe_group))
     fused = args.fused != 0 and args.block <= 512 and args.block >= 32
     _lib.check(lib.fcb_tune(b"fused_block", 1 if fused else 0))
+    if args.tma_io is not None:
+        _lib.check(lib.fcb_tune(b"tma_io", args.tma_io))
+    if args.zero_copy is not None:
+        _lib.check(lib.fcb_tune(b"zero_copy", args.zero_copy))
     if args.fused_stages is not None:
         _lib.check(lib.fcb_tune(b"fused_stages", args.fused_stages))
 
@@ -400,7 +404,11 @@ def run_b200(args) -> None:
                                          "ir_gen_s": round(t_gen, 1)}),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                    "ms_per_step": e2e_ms_max / args.steps},
+                    "ms_per_step": e2e_ms_max / args.steps,
+                    "path": "fcb_fftconv_process on pinned host buffers: the whole-block kernel pulls each channel's input "
+                            "block from host memory and pushes its output block back with cp.async.bulk (one launch per step)"
+                            if (fused and args.zero_copy != 0 and args.tma_io != 0) else
+                            "fcb_fftconv_process on pinned host buffers: H2D / kernel / D2H pipelined over channel groups"},
             "gpu_launches": int(launches), "clocks": clocks,
             "parity": {"max_abs_err_over_rms_vs_f64": worst, "tolerance": 1e-5},
             "realtime_headroom": {"block_period_ms": 1000.0 * B / SAMPLE_RATE,
@@ -427,6 +435,8 @@ def main():
     ap.add_argument("--mac-stages", type=int, default=None)
     ap.add_argument("--pipe-group", type=int, default=None)
     ap.add_argument("--fused-stages", type=int, default=None)
+    ap.add_argument("--zero-copy", type=int, default=None)
+    ap.add_argument("--tma-io", type=int, default=None)
     ap.add_argument("--fused", type=int, default=1, help="1: one fused K1+K2+K3 kernel per block (default), 0: three launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -192,6 +192,7 @@ static std::atomic<int> g_mac_stages{3}; // 2, 3, 4 or 6
 static std::atomic<int> g_pipe_group{512}; // channels per group of the end-to-end pipeline
 namespace fcb { std::atomic<bool> g_mimo_tile{true}; }
 static std::atomic<int> g_fused_stages{2}; // 2 stages (64 KB) -> 3 CTAs/SM: measured best (0.886 vs 0.890 ms)
+static std::atomic<bool> g_tma_io{true}; // whole-block kernel moves its input/output blocks with bulk copies
 static std::atomic<bool> g_shared_reuse{true}; // shared-IR engines: stage each IR tile once per CTA
 static std::atomic<bool> g_fused_block{true}; // whole blocks with B in 32..512: one fused K1+K2+K3 kernel // matrix K2 with in-CTA reuse (0: generic K2)
 
@@ -251,6 +252,12 @@ template <int LOGB>
 static int launch_block_fused_shared(const fcb_engine *e, cudaStream_t st, FusedArgs fa, size_t nc);
 
 // whole block, channels [c0, c0+nc): fused K1+K2+K3 (B in 32..512); false = not applicable
+// block I/O eligible for one bulk copy per channel: 16-byte aligned rows
+static bool tma_io_ok(const float *in, size_t in_stride, const float *out, size_t out_stride, size_t B)
+{
+    return B >= 4 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && in_stride % 4 == 0 && out_stride % 4 == 0;
+}
+
 template <int LOGB, int NST, int ROWS = 4>
 static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, size_t nc, const float *in_dev,
                               size_t in_stride, float *out_dev, size_t out_stride, size_t current, size_t active,
@@ -287,6 +294,11 @@ static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, s
     cudaEvent_t prof_stop = nullptr;
     const bool profiled = prof_before(st, &prof_stop) != nullptr;
     const unsigned grid = (unsigned)((nc + Cfg::CPB - 1) / Cfg::CPB);
+    if (g_tma_io.load() && tma_io_ok(fa.in, in_stride, fa.ifft.out, out_stride, e->B)) {
+        static SmemOptIn optin_io;
+        FCB_TRY(optin_io.ensure(k_block_fused<LOGB, NST, ROWS, true>, Cfg::smem_bytes(NST, true)));
+        k_block_fused<LOGB, NST, ROWS, true><<<grid, 256, Cfg::smem_bytes(NST, true), st>>>(fa, e->tw);
+    } else
     k_block_fused<LOGB, NST, ROWS><<<grid, 256, Cfg::smem_bytes(NST), st>>>(fa, e->tw);
     if (profiled) cudaEventRecord(prof_stop, st);
     g_launches++;
@@ -425,6 +437,7 @@ int run_mac_tile(int logb, cudaStream_t st, MacTileArgs a, int *zchunks_out)
 } // namespace fcb
 
 extern "C" void fcb_host_mirror_set_mapped_io(int on);
+extern "C" void fcb_host_mirror_set_zero_copy(int on);
 
 extern "C" int fcb_tune(const char *key, int value)
 {
@@ -436,7 +449,9 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "fused_block")) g_fused_block = value != 0;
     else if (!strcmp(key, "fused_stages") && (value == 2 || value == 3)) g_fused_stages = value;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
+    else if (!strcmp(key, "tma_io")) g_tma_io = value != 0;
     else if (!strcmp(key, "mapped_io")) fcb_host_mirror_set_mapped_io(value);
+    else if (!strcmp(key, "zero_copy")) fcb_host_mirror_set_zero_copy(value);
     else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);
     return FCB_OK;
 }

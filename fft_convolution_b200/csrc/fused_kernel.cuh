@@ -31,10 +31,27 @@ struct FusedCfg {
     static constexpr size_t STAGE_BYTES = 2 * (size_t)ARR * sizeof(float2);
     static constexpr int FFT_PER = (sidx(B) + 2) & ~1; // float2 per transform buffer (even: rows stay 16-byte aligned)
     static constexpr size_t FFT_BYTES = (size_t)CPB * FFT_PER * sizeof(float2);
-    __host__ __device__ static constexpr size_t smem_bytes(int nst) { return nst * STAGE_BYTES + 64 + ((FFT_BYTES + 15) / 16) * 16; }
+    static constexpr size_t FFT_BYTES_AL = ((FFT_BYTES + 15) / 16) * 16;
+    static constexpr size_t IO_BYTES = (size_t)CPB * B * sizeof(float); // one block of samples per channel
+    __host__ __device__ static constexpr size_t smem_bytes(int nst, bool tma_io = false)
+    {
+        return nst * STAGE_BYTES + 64 + FFT_BYTES_AL + (tma_io ? 2 * IO_BYTES : 0);
+    }
 };
 
-template <int LOGB, int NST, int ROWS = 4>
+// shared -> global bulk store (async proxy); the caller fences its generic-proxy smem writes first
+__device__ __forceinline__ void bulk_s2g(void *dst_global, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+// TMA_IO: the input block comes in and the output block goes out as ONE bulk copy per channel
+// (cp.async.bulk global<->shared).  Used when the caller's buffers are pinned HOST memory: a 2 KB
+// burst per channel crosses PCIe instead of hundreds of 4-byte accesses, so the kernel can work on
+// host buffers directly (no copy engines, no staging, one launch per step).  Same arithmetic.
+template <int LOGB, int NST, int ROWS = 4, bool TMA_IO = false>
 __global__ void __launch_bounds__(256)
 k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
 {
@@ -46,8 +63,12 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
     static_assert(CPB * T <= 256, "FFT lanes must fit the CTA");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2 *stages = reinterpret_cast<float2 *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NST * Cfg::STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NST * Cfg::STAGE_BYTES); // [NST] + in_bar at [7]
     float2 *fbuf = reinterpret_cast<float2 *>(smem_raw + NST * Cfg::STAGE_BYTES + 64);
+    float *in_s = reinterpret_cast<float *>(smem_raw + NST * Cfg::STAGE_BYTES + 64 + Cfg::FFT_BYTES_AL); // TMA_IO only
+    float *out_s = in_s + CPB * B;
+    uint64_t *in_bar = full + 7;
+    static_assert(NST <= 7, "barrier slots");
 
     const MacArgs &a = fa.mac;
     const int tid = threadIdx.x;
@@ -61,9 +82,15 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
 
     if (tid == 0) {
         for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
+        if (TMA_IO) mbar_init(in_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (TMA_IO && tid == 0) { // the new block of every live channel: one bulk copy each (host or device memory)
+        mbar_expect_tx(in_bar, (uint32_t)(nlive * B * sizeof(float)));
+        for (int ch = 0; ch < nlive; ch++)
+            bulk_g2s(in_s + ch * B, fa.in + (c0 + ch) * fa.in_stride, B * sizeof(float), in_bar);
+    }
 
     auto issue = [&](int it) {
         const int s = it % NST;
@@ -94,14 +121,19 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
     // ---- K1: forward real FFT of the new block (src/fft_convolver.rs:248-255) -------------------
     float2 *fs = fbuf + (fwork ? fslot : 0) * Cfg::FFT_PER;
     const bool flive = fwork && fslot < nlive;
+    if (TMA_IO) mbar_wait(in_bar, 0);
     if (fwork) {
-        const float *x = fa.in + (c0 + fslot) * fa.in_stride;
+        const float *x = TMA_IO ? in_s + fslot * B : fa.in + (c0 + fslot) * fa.in_stride;
 #pragma unroll
         for (int e = 0; e < E; e++) {
             int j = flane + e * T;
             float2 z = make_float2(0.f, 0.f);
-            if (flive && 2 * j < B) z.x = __ldg(x + 2 * j);
-            if (flive && 2 * j + 1 < B) z.y = __ldg(x + 2 * j + 1);
+            if (TMA_IO) {
+                if (flive && 2 * j + 1 < B) z = *reinterpret_cast<const float2 *>(x + 2 * j);
+            } else {
+                if (flive && 2 * j < B) z.x = __ldg(x + 2 * j);
+                if (flive && 2 * j + 1 < B) z.y = __ldg(x + 2 * j + 1);
+            }
             fs[sidx(j)] = z;
         }
     }
@@ -201,11 +233,18 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
             for (int h = 0; h < 2; h++) {
                 int i = 2 * j + h;
                 float v = apply_epilogue(__fadd_rn(y[h], o.overlap[c * B + i]), o.epi, c, i);
-                o.out[c * o.out_stride + i] = v;
+                if (TMA_IO) out_s[fslot * B + i] = v;
+                else o.out[c * o.out_stride + i] = v;
             }
         }
     }
-    __syncthreads(); // every reader of the old overlap is done
+    if (TMA_IO) asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // smem writes -> async proxy
+    __syncthreads(); // every reader of the old overlap is done (and every output sample is in out_s)
+    if (TMA_IO && tid == 0) {
+        for (int ch = 0; ch < nlive; ch++)
+            bulk_s2g(o.out + (c0 + ch) * o.out_stride, out_s + ch * B, B * sizeof(float));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
     if (flive) {
 #pragma unroll
         for (int e = 0; e < E; e++) {
@@ -216,6 +255,7 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
             }
         }
     }
+    if (TMA_IO && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // smem stays alive until read
 }
 
 

@@ -221,8 +221,21 @@ extern "C" int fcb_fftconv_reset(fcb_fftconv *c)
 }
 
 static bool g_mapped_io = true; // fcb_tune("mapped_io", 0) forces the copy-engine path
+static bool g_zero_copy = true; // fcb_tune("zero_copy", 0): never let kernels touch caller-pinned host buffers
 
 extern "C" void fcb_host_mirror_set_mapped_io(int on) { g_mapped_io = on != 0; }
+extern "C" void fcb_host_mirror_set_zero_copy(int on) { g_zero_copy = on != 0; }
+
+// device-visible alias of a pinned (page-locked) host pointer, or NULL for pageable / device memory
+static float *pinned_alias(const float *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? static_cast<float *>(a.devicePointer) : nullptr;
+}
 
 static fcb_epilogue offset_epilogue(const fcb_epilogue *epi, size_t off)
 {
@@ -275,6 +288,19 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
         fcb_epilogue e = offset_epilogue(epi, processed);
         float *dst = host ? c->d_io : out + processed;
         const size_t dst_stride = host ? B : out_stride;
+        if (host && was_empty && complete && g_zero_copy && c->C >= 1024) {
+            // caller's buffers are pinned: the whole-block kernel reads the input block and writes the
+            // output block over PCIe itself (every CTA its own channels, spread over the kernel's
+            // lifetime) — no copy engines, no staging, one launch per step
+            float *din = pinned_alias(in + processed), *dout = pinned_alias(out + processed);
+            if (din && dout) {
+                FCB_TRY(fcb_engine_process_block_dev(c->eng, din, in_stride, dout, out_stride, c->current,
+                                                     c->active_seg_count, &e));
+                c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1; // :301-305
+                processed += n;
+                continue;
+            }
+        }
         if (host && was_empty && complete && c->C >= 1024) {
             // many channels, whole block, host buffers: overlap the PCIe copies with K2
             FCB_TRY(fcb_engine_process_block_host(c->eng, in + processed, in_stride, out + processed, out_stride,

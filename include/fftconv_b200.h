@@ -57,7 +57,8 @@ int fcb_device_count(void);
  * end-to-end copy/compute pipeline, default 512), "mimo_tile" (1 = matrix K2 with in-CTA reuse of
  * IR and ring tiles, 0 = the per-channel K2), "fused_block" (1 = whole blocks with B in 32..512 run as
  * one fused K1+K2+K3 kernel, 0 = three launches; outputs are bit-identical), "fused_stages" (2 or 3), "mapped_io" (1 = small-batch host
- * calls go through mapped pinned memory instead of the copy engines) */
+ * calls go through mapped pinned memory instead of the copy engines), "zero_copy" (1 = when the caller's
+ * buffers are pinned, large-batch whole-block calls let the kernel read/write them over PCIe directly) */
 int fcb_tune(const char *key, int value);
 
 /* live timing of the K2 launches: while enabled every K2 launch is bracketed by CUDA events on

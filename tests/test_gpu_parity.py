@@ -261,6 +261,37 @@ def test_shared_ir_reuse_kernel_bit_identical(F, B, C):
     assert np.max(np.abs(ys[C - 1] - yo)) <= TOL * rms(yo)
 
 
+def test_zero_copy_pinned_buffers_match_copy_path(F):
+    """>= 1024 channels with PINNED caller buffers: the kernel reads/writes host memory directly;
+    same bits as the staged copy pipeline"""
+    import ctypes as C
+    from fft_convolution_b200 import _lib
+    lib = _lib.load()
+    Cn, B, L = 1100, 64, 300
+    h = oracle.gen_ir(4, 0, L)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, size=(Cn, B * 5)).astype(np.float32)
+    p_in, p_out = lib.fcb_host_alloc(Cn * B * 4), lib.fcb_host_alloc(Cn * B * 4)
+    h_in = np.ctypeslib.as_array(C.cast(p_in, C.POINTER(C.c_float)), shape=(Cn, B))
+    h_out = np.ctypeslib.as_array(C.cast(p_out, C.POINTER(C.c_float)), shape=(Cn, B))
+    ys = []
+    for on in (1, 0):
+        _lib.check(lib.fcb_tune(b"zero_copy", on))
+        conv = F.FFTConvolver.init(h, B, L, channels=Cn)
+        y = np.zeros_like(x)
+        for b in range(5):
+            h_in[:] = x[:, b * B:(b + 1) * B]
+            conv.process(h_in, h_out)
+            y[:, b * B:(b + 1) * B] = h_out
+        ys.append(y)
+    _lib.check(lib.fcb_tune(b"zero_copy", 1))
+    lib.fcb_host_free(p_in)
+    lib.fcb_host_free(p_out)
+    assert np.array_equal(ys[0], ys[1])
+    yo = _run(oracle.FFTConvolver.init(h, B, L), x[777], [B])
+    assert np.max(np.abs(ys[0][777] - yo)) <= TOL * rms(yo)
+
+
 def test_mapped_io_path_matches_copy_path(F):
     """small-batch host calls stage through mapped pinned memory; same bits as the copy-engine path"""
     from fft_convolution_b200 import _lib
