@@ -188,7 +188,7 @@ def run_reference(args) -> None:
     import oracle
     threads = host_threads()
     ir_len = int(args.ir_seconds * SAMPLE_RATE)
-    channels = max(threads * 4, 8)
+    channels = min(max(threads * 16, 16), 512)  # 16 channels per host thread, like the cpu_baseline leg
     calls = 94  # ~1 s of audio per channel per step
     # warm-up + timed steps, each step a bounded sample of the workload
     for _ in range(min(args.warmup, 3)):
@@ -391,10 +391,13 @@ def run_b200(args) -> None:
         if world == 1 and not args.no_cpu_baseline:
             import oracle  # noqa: F401  (cpu_baseline leg only)
             threads = host_threads()
-            ch, calls = max(threads * 4, 8), 188
+            # ~10 s of CPU work: 16 channels per host thread (each thread streams ~25 MB of state per
+            # block, like a real many-channel host), 4 s of audio per channel
+            ch, calls = min(max(threads * 16, 16), 512), 375
             v, secs = cpu_port_run(ch, B, L, calls, threads)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                            "sample": f"{ch} channels x {calls} blocks of {B} (2 s of audio each), block loop only, {secs:.2f} s",
+                            "sample": f"{ch} channels x {calls} blocks of {B} ({calls * B / SAMPLE_RATE:.1f} s of audio each), block loop only, "
+                                      f"{secs:.2f} s wall on {threads} threads",
                             "note": "CPU restatement of the reference algorithm, not rustfft (no Rust toolchain)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
