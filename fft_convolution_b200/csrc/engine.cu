@@ -186,15 +186,15 @@ extern "C" int fcb_profile_mac_read(double *total_ms, uint64_t *launches)
     return FCB_OK;
 }
 
-// tuning knobs (fcb_tune): which K2 implementation, how many pipeline stages
-static std::atomic<int> g_mac_impl{0};   // 0 = auto (TMA pipeline for B >= 32), 1 = LDG, 2 = TMA
-static std::atomic<int> g_mac_stages{3}; // 2, 3, 4 or 6
-static std::atomic<int> g_pipe_group{512}; // channels per group of the end-to-end pipeline
-namespace fcb { std::atomic<bool> g_mimo_tile{true}; }
-static std::atomic<int> g_fused_stages{2}; // 2 stages (64 KB) -> 3 CTAs/SM: measured best (0.886 vs 0.890 ms)
-static std::atomic<bool> g_tma_io{true}; // whole-block kernel moves its input/output blocks with bulk copies
+// ---- tuning knobs (fcb_tune); the defaults are the measured best (profiles/r01_*sweep*) -----------
+static std::atomic<int> g_mac_impl{0};         // K2: 0 = auto (TMA pipeline for B >= 32), 1 = LDG kernel, 2 = TMA
+static std::atomic<int> g_mac_stages{3};       // K2 pipeline stages: 2, 3, 4 or 6
+static std::atomic<int> g_pipe_group{512};     // channels per group of the copy pipeline (pageable host buffers)
+static std::atomic<bool> g_fused_block{true};  // whole blocks with B in 32..512: one fused K1+K2+K3 kernel
+static std::atomic<int> g_fused_stages{2};     // fused kernel: 2 stages (64 KB) -> 3 CTAs/SM; 3 -> 2 CTAs/SM
+static std::atomic<bool> g_tma_io{true};       // fused kernel moves its input/output blocks with bulk copies
 static std::atomic<bool> g_shared_reuse{true}; // shared-IR engines: stage each IR tile once per CTA
-static std::atomic<bool> g_fused_block{true}; // whole blocks with B in 32..512: one fused K1+K2+K3 kernel // matrix K2 with in-CTA reuse (0: generic K2)
+namespace fcb { std::atomic<bool> g_mimo_tile{true}; } // matrix K2 with in-CTA reuse (0: per-channel K2)
 
 template <int B, int NST>
 static int launch_mac_bulk(const MacArgs &a, cudaStream_t st)
@@ -251,13 +251,13 @@ static int launch_mac_t(const MacArgs &a, cudaStream_t st)
 template <int LOGB>
 static int launch_block_fused_shared(const fcb_engine *e, cudaStream_t st, FusedArgs fa, size_t nc);
 
-// whole block, channels [c0, c0+nc): fused K1+K2+K3 (B in 32..512); false = not applicable
 // block I/O eligible for one bulk copy per channel: 16-byte aligned rows
 static bool tma_io_ok(const float *in, size_t in_stride, const float *out, size_t out_stride, size_t B)
 {
     return B >= 4 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && in_stride % 4 == 0 && out_stride % 4 == 0;
 }
 
+// whole block for channels [c0, c0+nc): fused K1+K2+K3 (B in 32..512)
 template <int LOGB, int NST, int ROWS = 4>
 static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, size_t nc, const float *in_dev,
                               size_t in_stride, float *out_dev, size_t out_stride, size_t current, size_t active,
@@ -298,8 +298,9 @@ static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, s
         static SmemOptIn optin_io;
         FCB_TRY(optin_io.ensure(k_block_fused<LOGB, NST, ROWS, true>, Cfg::smem_bytes(NST, true)));
         k_block_fused<LOGB, NST, ROWS, true><<<grid, 256, Cfg::smem_bytes(NST, true), st>>>(fa, e->tw);
-    } else
-    k_block_fused<LOGB, NST, ROWS><<<grid, 256, Cfg::smem_bytes(NST), st>>>(fa, e->tw);
+    } else {
+        k_block_fused<LOGB, NST, ROWS><<<grid, 256, Cfg::smem_bytes(NST), st>>>(fa, e->tw);
+    }
     if (profiled) cudaEventRecord(prof_stop, st);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
