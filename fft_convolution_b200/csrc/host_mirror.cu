@@ -288,7 +288,11 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
         fcb_epilogue e = offset_epilogue(epi, processed);
         float *dst = host ? c->d_io : out + processed;
         const size_t dst_stride = host ? B : out_stride;
-        if (host && was_empty && complete && g_zero_copy && c->C >= 1024) {
+        // (only where the whole-block kernel moves its I/O with bulk copies: 32 <= B <= 512, 16-byte
+        // aligned rows — plain 4-byte accesses to host memory are 3x slower than staging)
+        const bool bulk_io = B >= 32 && B <= 512 && in_stride % 4 == 0 && out_stride % 4 == 0 &&
+                             (uintptr_t)(in + processed) % 16 == 0 && (uintptr_t)(out + processed) % 16 == 0;
+        if (host && was_empty && complete && g_zero_copy && bulk_io && c->C >= 1024) {
             // caller's buffers are pinned: the whole-block kernel reads the input block and writes the
             // output block over PCIe itself (every CTA its own channels, spread over the kernel's
             // lifetime) — no copy engines, no staging, one launch per step
