@@ -134,6 +134,7 @@ SIGNATURES = {
     "fcb_mimo_process": (_i, [_vp, _vp, _vp]),
     "fcb_mimo_sync": (_i, [_vp]),
     "fcb_mimo_stream": (_vp, [_vp]),
+    "fcb_mimo_uses_tensor_cores": (_i, [_vp]),
     "fcb_mimo_block_size": (_sz, [_vp]),
     "fcb_mimo_seg_count": (_sz, [_vp]),
     "fcb_mimo_segment_range": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),

@@ -276,7 +276,10 @@ class MimoConvolver:
 
     @classmethod
     def init(cls, responses, block_size: int, max_response_length: int, *, n_streams: int = 1,
-             shard_index: int = 0, shard_count: int = 1, device: int = 0, stream=None) -> "MimoConvolver":
+             shard_index: int = 0, shard_count: int = 1, device: int = 0, stream=None,
+             tensor_cores: bool | None = None) -> "MimoConvolver":
+        """tensor_cores: True / False force the tcgen05 matrix MAC (K4; 16 outputs, <= 128 streams) on /
+        off for this object; None keeps the library default (on from 32 streams)."""
         lib = _lib.load()
         _lib.require_gpu()
         r = np.ascontiguousarray(responses, dtype=np.float32)
@@ -286,7 +289,13 @@ class MimoConvolver:
         d = _lib.MimoDesc(n_in, n_out, n_streams, block_size, max_response_length, shard_index, shard_count,
                           device, stream)
         h = C.c_void_p()
-        check(lib.fcb_mimo_create(C.byref(d), C.byref(h)))
+        if tensor_cores is not None:
+            check(lib.fcb_tune(b"mimo_tc", 1 if tensor_cores else 0))
+        try:
+            check(lib.fcb_mimo_create(C.byref(d), C.byref(h)))
+        finally:
+            if tensor_cores is not None:
+                check(lib.fcb_tune(b"mimo_tc", 2))
         self = cls(h, n_in, n_out, n_streams)
         check(lib.fcb_mimo_set_ir(h, _ptr(r), length))
         check(lib.fcb_mimo_sync(h))
@@ -294,6 +303,7 @@ class MimoConvolver:
 
     block_size = property(lambda s: _lib.load().fcb_mimo_block_size(s._h))
     seg_count = property(lambda s: _lib.load().fcb_mimo_seg_count(s._h))
+    uses_tensor_cores = property(lambda s: bool(_lib.load().fcb_mimo_uses_tensor_cores(s._h)))
 
     @property
     def segment_range(self):

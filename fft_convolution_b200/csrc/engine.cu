@@ -195,6 +195,7 @@ static std::atomic<int> g_fused_stages{2};     // fused kernel: 2 stages (64 KB)
 static std::atomic<bool> g_tma_io{true};       // fused kernel moves its input/output blocks with bulk copies
 static std::atomic<bool> g_shared_reuse{true}; // shared-IR engines: stage each IR tile once per CTA
 namespace fcb { std::atomic<bool> g_mimo_tile{true}; } // matrix K2 with in-CTA reuse (0: per-channel K2)
+namespace fcb { std::atomic<int> g_mimo_tc{2}; }       // K4 tensor-core matrix MAC: 0 never, 1 when the shape fits, 2 + NS >= 32
 
 template <int B, int NST>
 static int launch_mac_bulk(const MacArgs &a, cudaStream_t st)
@@ -447,6 +448,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "mac_stages") && (value == 2 || value == 3 || value == 4 || value == 6)) g_mac_stages = value;
     else if (!strcmp(key, "pipe_group") && value >= 1) g_pipe_group = value;
     else if (!strcmp(key, "mimo_tile")) g_mimo_tile = value != 0;
+    else if (!strcmp(key, "mimo_tc") && value >= 0 && value <= 2) g_mimo_tc = value;
     else if (!strcmp(key, "fused_block")) g_fused_block = value != 0;
     else if (!strcmp(key, "fused_stages") && (value == 2 || value == 3)) g_fused_stages = value;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;

@@ -13,11 +13,40 @@
 #include <cstring>
 
 #include "engine_internal.cuh"
+#include "mimo_tc.cuh"
 
 using namespace fcb;
 
 namespace fcb {
 extern std::atomic<bool> g_mimo_tile;
+extern std::atomic<int> g_mimo_tc; // 0 never, 1 whenever the shape fits, 2 (default) when it fits and NS >= 32
+
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                           const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// f32 tensor [d2][d1][d0] (d0 contiguous, row pitch / plane pitch in bytes), box [1][b1][32] with the
+// 128-byte swizzle the K-major UMMA descriptors expect; out-of-bounds elements read as zero
+static int tc_encode_map(CUtensorMap *tm, void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1, uint64_t pitch2,
+                         uint32_t b1)
+{
+    static TensorMapEncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FCB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p) return fail(FCB_ERR_CUDA, "cuTensorMapEncodeTiled is not exported by this driver");
+        fn = (TensorMapEncodeTiledFn)p;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {pitch1, pitch2};
+    cuuint32_t box[3] = {2 * TC_KSEG, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FCB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return FCB_OK;
+}
 
 // conv[s][o][k] = sum_in sum_z part[z][s][o][in][k]  +  sum_in X[s][in][cur][k] * H[o][in][seg 0][k]
 // (the segment-0 product, src/fft_convolver.rs:270-275, only on the shard that owns segment 0).
@@ -95,6 +124,17 @@ struct fcb_mimo {
     float *stage = nullptr;
     size_t stage_floats = 0;
     const float2 *tw = nullptr;
+    // tensor-core path (K4, mimo_tc.cuh): transposed operands instead of ir / ring / premul
+    bool tc = false;
+    float2 *ring_t = nullptr;  // [B][IN][128][Sp]
+    float *ir_t = nullptr;     // [2 copies][B][IN][2*OUT][2*rowsP], copy 1 shifted by one position
+    float2 *xcur = nullptr;    // [NS*IN][B] spectra of the current block before the scatter
+    float2 *part_tc = nullptr; // [groups][NS*OUT][B]
+    float2 *ir_tmp = nullptr;  // [tmp_pairs][rows][B] K5 output before the transposition
+    size_t Sp = 0, rowsP = 0, tmp_pairs = 0;
+    int tc_groups = 1;
+    CUtensorMap tm_ring, tm_ir[2];
+    size_t ir_copy_floats() const { return B * n_in * 2 * n_out * 2 * rowsP; }
 
     size_t rows() const { return seg_hi - seg_lo; }
 };
@@ -112,6 +152,11 @@ extern "C" void fcb_mimo_destroy(fcb_mimo *m)
     cudaFree(m->io_in);
     cudaFree(m->io_out);
     cudaFree(m->stage);
+    cudaFree(m->ring_t);
+    cudaFree(m->ir_t);
+    cudaFree(m->xcur);
+    cudaFree(m->part_tc);
+    cudaFree(m->ir_tmp);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -155,13 +200,37 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
     }
     const size_t pairs = m->n_out * m->n_in;
     int rc = get_twiddles(m->device, 2 * B, &m->tw);
-    if (!rc) rc = mimo_alloc((void **)&m->ir, pairs * m->rows() * B * sizeof(float2), m->stream);
-    if (!rc) rc = mimo_alloc((void **)&m->ring, ns * m->n_in * m->S * B * sizeof(float2), m->stream);
-    {
+    const int tc_mode = g_mimo_tc.load();
+    m->tc = tc_mode != 0 && m->n_out == 16 && ns <= (size_t)TC_M && (tc_mode == 1 || ns >= 32) && m->rows() > 0 && B >= 2;
+    if (m->tc) {
+        m->Sp = (m->S + 1) & ~(size_t)1; // row pitches are multiples of 16 bytes
+        m->rowsP = (m->rows() + 2) & ~(size_t)1; // room for the shifted copy
+        size_t groups = (6 * 148 + B - 1) / B; // ~6 waves of CTAs
+        m->tc_groups = (int)(groups < 1 ? 1 : groups > m->n_in ? m->n_in : groups);
+        const size_t per_pair = m->rows() * B * sizeof(float2);
+        m->tmp_pairs = ((size_t)256 << 20) / per_pair;
+        if (m->tmp_pairs < 1) m->tmp_pairs = 1;
+        if (m->tmp_pairs > pairs) m->tmp_pairs = pairs;
+        if (!rc) rc = mimo_alloc((void **)&m->ring_t, B * m->n_in * TC_M * m->Sp * sizeof(float2), m->stream);
+        if (!rc) rc = mimo_alloc((void **)&m->ir_t, 2 * m->ir_copy_floats() * sizeof(float), m->stream);
+        if (!rc) rc = mimo_alloc((void **)&m->xcur, ns * m->n_in * B * sizeof(float2), m->stream);
+        if (!rc) rc = mimo_alloc((void **)&m->part_tc, (size_t)m->tc_groups * ns * m->n_out * B * sizeof(float2), m->stream);
+        if (!rc) rc = mimo_alloc((void **)&m->ir_tmp, m->tmp_pairs * per_pair, m->stream);
+        if (!rc)
+            rc = tc_encode_map(&m->tm_ring, m->ring_t, 2 * m->S, TC_M, B * m->n_in, m->Sp * sizeof(float2),
+                               TC_M * m->Sp * sizeof(float2), TC_M);
+        for (size_t sh = 0; sh < 2 && !rc; sh++)
+            rc = tc_encode_map(&m->tm_ir[sh], m->ir_t + sh * m->ir_copy_floats(), 2 * (m->rows() + sh), 2 * m->n_out, B * m->n_in,
+                               2 * m->rowsP * sizeof(float), 2 * m->n_out * 2 * m->rowsP * sizeof(float), (uint32_t)(2 * m->n_out));
+        if (!rc && cudaFuncSetAttribute(k_mimo_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<16>::SMEM) != cudaSuccess)
+            rc = fail(FCB_ERR_CUDA, "k_mimo_tc: cannot opt in to %zu bytes of shared memory", TcCfg<16>::SMEM);
+    } else {
+        if (!rc) rc = mimo_alloc((void **)&m->ir, pairs * m->rows() * B * sizeof(float2), m->stream);
+        if (!rc) rc = mimo_alloc((void **)&m->ring, ns * m->n_in * m->S * B * sizeof(float2), m->stream);
         int z = 1, zl = 1;
         if (mac_tile_plan(m->logb, (int)m->n_in, (int)m->n_out, (int)ns, (int)m->rows(), &z, &zl) == FCB_OK) m->zmax = z;
+        if (!rc) rc = mimo_alloc((void **)&m->premul, (size_t)m->zmax * ns * pairs * B * sizeof(float2), m->stream);
     }
-    if (!rc) rc = mimo_alloc((void **)&m->premul, (size_t)m->zmax * ns * pairs * B * sizeof(float2), m->stream);
     if (!rc) rc = mimo_alloc((void **)&m->conv, ns * m->n_out * B * sizeof(float2), m->stream);
     if (!rc) rc = mimo_alloc((void **)&m->overlap, ns * m->n_out * B * sizeof(float), m->stream);
     if (!rc) rc = mimo_alloc((void **)&m->io_in, ns * m->n_in * B * sizeof(float), m->stream);
@@ -191,16 +260,30 @@ extern "C" int fcb_mimo_set_ir(fcb_mimo *m, const float *irs, size_t len)
     const size_t off = m->seg_lo * B;                 // first sample of this shard's first segment
     const int rem = len > off ? (int)(len - off) : 0; // samples of the IR at or past it
     if (len == 0) {
+        if (m->tc) {
+            FCB_CUDA(cudaMemsetAsync(m->ir_t, 0, 2 * m->ir_copy_floats() * sizeof(float), m->stream));
+            return FCB_OK;
+        }
         return run_forward(m->logb, m->tw, m->stream, m->stage, 0, 0, m->ir, dst_stride, (int)m->rows(),
                            (long long)(pairs * m->rows()));
     }
-    const size_t per_group = m->stage_floats / len;
+    size_t per_group = m->stage_floats / len;
     if (per_group == 0) return fail(FCB_ERR_CUDA, "IR staging buffer too small");
+    if (m->tc && per_group > m->tmp_pairs) per_group = m->tmp_pairs;
     for (size_t g0 = 0; g0 < pairs; g0 += per_group) {
         const size_t g = pairs - g0 < per_group ? pairs - g0 : per_group;
         FCB_CUDA(cudaMemcpyAsync(m->stage, irs + g0 * len, g * len * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-        FCB_TRY(run_forward(m->logb, m->tw, m->stream, m->stage + off, (long long)len, rem, m->ir + g0 * dst_stride,
-                            dst_stride, (int)m->rows(), (long long)(g * m->rows())));
+        float2 *dst = m->tc ? m->ir_tmp : m->ir + g0 * dst_stride;
+        FCB_TRY(run_forward(m->logb, m->tw, m->stream, m->stage + off, (long long)len, rem, dst, dst_stride, (int)m->rows(),
+                            (long long)(g * m->rows())));
+        if (m->tc) {
+            const long long total = (long long)(g * m->rows() * B);
+            k_tc_build_ir<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->ir_tmp, m->ir_t, (int)B, (int)m->n_in,
+                                                                                   (int)m->n_out, (int)m->rows(), (long long)m->rowsP,
+                                                                                   (long long)g0, total, (long long)m->ir_copy_floats());
+            g_launches++;
+            FCB_CUDA(cudaGetLastError());
+        }
         if (g0 + per_group < pairs) FCB_CUDA(cudaStreamSynchronize(m->stream));
     }
     return FCB_OK;
@@ -211,7 +294,8 @@ extern "C" int fcb_mimo_reset(fcb_mimo *m)
     if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
     FCB_CUDA(cudaSetDevice(m->device));
     const size_t ns = m->n_streams, B = m->B;
-    FCB_CUDA(cudaMemsetAsync(m->ring, 0, ns * m->n_in * m->S * B * sizeof(float2), m->stream));
+    if (m->tc) FCB_CUDA(cudaMemsetAsync(m->ring_t, 0, B * m->n_in * TC_M * m->Sp * sizeof(float2), m->stream));
+    else FCB_CUDA(cudaMemsetAsync(m->ring, 0, ns * m->n_in * m->S * B * sizeof(float2), m->stream));
     FCB_CUDA(cudaMemsetAsync(m->overlap, 0, ns * m->n_out * B * sizeof(float), m->stream));
     m->current = 0;
     return FCB_OK;
@@ -224,6 +308,31 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
     if (m->S == 0) return FCB_OK;
     FCB_CUDA(cudaSetDevice(m->device));
     const size_t B = m->B, ns = m->n_streams, pairs = m->n_out * m->n_in;
+    if (m->tc) {
+        // K1 -> scatter into column `current` of the K-major ring -> K4 (every owned segment,
+        // segment 0 included) -> sum over input groups
+        FCB_TRY(run_forward(m->logb, m->tw, m->stream, in_dev, (long long)in_stride, (int)B, m->xcur, (long long)B, 1,
+                            (long long)(ns * m->n_in)));
+        const long long nx = (long long)(ns * m->n_in * B);
+        k_tc_scatter_ring<<<(unsigned)((nx + 255) / 256), 256, 0, m->stream>>>(m->xcur, m->ring_t, (int)B, (int)m->n_in, nx,
+                                                                                (long long)m->Sp, (int)m->current);
+        TcArgs t{};
+        t.part = m->part_tc;
+        t.B = (int)B;
+        t.n_in = (int)m->n_in;
+        t.n_streams = (int)ns;
+        t.S = (int)m->S;
+        t.current = (int)m->current;
+        t.seg_lo = (int)m->seg_lo;
+        t.seg_hi = (int)m->seg_hi;
+        t.groups = m->tc_groups;
+        k_mimo_tc<16><<<(unsigned)(B * m->tc_groups), TC_THREADS, TcCfg<16>::SMEM, m->stream>>>(t, m->tm_ring, m->tm_ir[0], m->tm_ir[1]);
+        const long long nc = (long long)(ns * m->n_out * B);
+        k_tc_reduce<<<(unsigned)((nc + 255) / 256), 256, 0, m->stream>>>(m->part_tc, m->conv, nc, m->tc_groups);
+        g_launches += 3;
+        FCB_CUDA(cudaGetLastError());
+        return FCB_OK;
+    }
     const long long ring_stride = (long long)(m->S * B);
     FCB_TRY(run_forward(m->logb, m->tw, m->stream, in_dev, (long long)in_stride, (int)B, m->ring + m->current * B,
                         ring_stride, 1, (long long)(ns * m->n_in)));
@@ -338,6 +447,7 @@ extern "C" int fcb_mimo_sync(fcb_mimo *m)
 }
 
 extern "C" void *fcb_mimo_stream(fcb_mimo *m) { return m ? (void *)m->stream : nullptr; }
+extern "C" int fcb_mimo_uses_tensor_cores(const fcb_mimo *m) { return m && m->tc ? 1 : 0; }
 extern "C" size_t fcb_mimo_block_size(const fcb_mimo *m) { return m->B; }
 extern "C" size_t fcb_mimo_seg_count(const fcb_mimo *m) { return m->S; }
 extern "C" int fcb_mimo_segment_range(const fcb_mimo *m, size_t *lo, size_t *hi)

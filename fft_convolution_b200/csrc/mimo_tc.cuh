@@ -1,0 +1,362 @@
+// mimo_tc.cuh — K4: the convolution-matrix delay-line MAC as per-bin complex GEMMs on the
+// sm_100a tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands staged by TMA).
+//
+// Replaces, for the OUT x IN matrix with NS streams sharing the IR matrix, the loops at
+// src/fft_convolver.rs:258-275 of all OUT*IN reference convolvers at once.  Per bin k
+//     D[s][o] = sum_in sum_i  X[s][in][(current+i) % S][k] * H[o][in][i][k]          (complex)
+// is a dense contraction over j = (in, i): M = streams, N = outputs, K = IN*S — the one place on
+// this path where the work really is a GEMM.  As a real GEMM (K doubles, N doubles):
+//     [D.re | D.im][s][n] = sum_{j,p}  A[s][(j,p)] * Bm[n][(j,p)],   A[s][(j,0)] = X.re, A[s][(j,1)] = X.im
+//     Bm[o][(j,0)] = H.re,  Bm[o][(j,1)] = -H.im        (n = o:        real part)
+//     Bm[OUT+o][(j,0)] = H.im, Bm[OUT+o][(j,1)] = H.re  (n = OUT + o:  imaginary part)
+// and for the packed bin 0 ({DC, Nyquist}: two real products) Bm[o] = {H.re, 0}, Bm[OUT+o] = {0, H.im}.
+//
+// HBM layout (K-major operands, so a tile is one TMA box and no transposition happens on chip):
+//     ring_t [bin][in][128 stream rows][Sp slots] float2      A: row = stream, K = (slot, re/im)
+//     ir_t   [2][bin][in][2*OUT rows][2*rowsP]    float       B: row = n,      K = (segment, plane)
+// The new block's spectrum is scattered into column `current` of ring_t by K1's epilogue kernel;
+// ir_t is built once per set_ir.  Slot s holds segment i = (s - current) mod S, so the K loop runs
+// over two contiguous slot ranges; ragged ends are covered by TMA out-of-bounds zero fill on one
+// of the two operands (tensor extents are exactly 2*S and 2*(rows + shift)).  A TMA box must start
+// on a 16-byte boundary in global memory, i.e. on an even slot AND an even IR position; slot and
+// segment differ by `current`, so ir_t is kept twice — copy 1 shifted by one (zero) position —
+// and each slot range reads the copy whose parity matches.
+//
+// Precision.  north_star asks for 1e-5 * RMS (f32); a tf32 product keeps 11 bits.  Every operand is
+// split on chip x = hi + lo (hi = the bits the tensor core reads, lo = x - hi, both exact) and
+// hi*hi, hi*lo, lo*hi are accumulated (3xTF32: error ~2^-22 per product).  TMEM accumulation
+// truncates (measured: a single K = 30016 accumulation drifts by 9e-4 * RMS toward zero), so the
+// accumulator is drained into f32 registers every 128 K-elements and the small cross terms go to
+// their own accumulator columns (scripts/tc_probe.cu, profiles/r01_tc_probe.txt).
+//
+// One CTA = one (bin, input group): 10 warps — TMA producer, MMA issuer, 4 splitter warps
+// (hi/lo), 4 drain warps (TMEM -> registers -> partial spectra).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mac_kernels.cuh"
+
+namespace fcb {
+
+constexpr int TC_M = 128;    // stream rows of one UMMA (streams are padded to this)
+constexpr int TC_KSEG = 16;  // segments per stage: 16 (re,im) pairs = 32 tf32 = one 128-byte swizzle row
+constexpr int TC_NST = 4;    // pipeline stages
+constexpr int TC_DRAIN = 4;  // stages per TMEM accumulation interval (K = 128 per drain)
+constexpr int TC_THREADS = 320;
+
+template <int NOUT>
+struct TcCfg {
+    static constexpr int N2 = 2 * NOUT;                    // GEMM N (re | im)
+    static constexpr int A_BYTES = TC_M * 128;             // 16 KB: 128 rows x 128 B
+    static constexpr int B_BYTES = N2 * 128;               // 4 KB at 16 outputs
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES; // A_hi | A_lo | B_hi | B_lo
+    static constexpr int TMEM_COLS = 4 * N2;               // 2 buffers x (main N2 | cross N2)
+    static constexpr size_t SMEM = (size_t)TC_NST * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(N2 % 16 == 0 && 2 * N2 <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32 && TMEM_COLS <= 512, "TMEM allocation is a power of two");
+};
+
+struct TcArgs {
+    float2 *part;        // [groups][NS][OUT][B] partial spectra (packed rows)
+    int B, n_in, n_streams;
+    int S;               // ring slots
+    int current;
+    int seg_lo, seg_hi;  // segments accumulated; IR position of segment i in copy sh = i - seg_lo + sh
+    int groups;          // input groups per bin; grid = B * groups
+};
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row groups 1024 B apart, version 1
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// D f32, A/B tf32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// chunk c of one input's K loop -> ring slot, IR copy and IR position of its first (re,im) pair.
+// Range 1: segments [seg_lo, min(seg_hi, S - current)) in slots current + i; range 2: segments
+// [max(seg_lo, S - current), seg_hi) in slots i - (S - current).  Each range starts on the even slot
+// at or below its first slot; the extra leading slot meets the zero pad of IR copy 1.
+struct TcSpan {
+    int n1, a1, sh1, n2, a2, sh2, pos2;
+    __device__ TcSpan(const TcArgs &a)
+    {
+        const int wrap = a.S - a.current;
+        const int p1_hi = a.seg_hi < wrap ? a.seg_hi : wrap;
+        const int first1 = a.current + a.seg_lo;
+        a1 = first1 & ~1;
+        sh1 = first1 & 1;
+        n1 = p1_hi > a.seg_lo ? (a.current + p1_hi - a1 + TC_KSEG - 1) / TC_KSEG : 0;
+        const int p2_lo = a.seg_lo > wrap ? a.seg_lo : wrap;
+        const int first2 = p2_lo - wrap;
+        a2 = first2 & ~1;
+        sh2 = (wrap - a.seg_lo) & 1;
+        pos2 = a2 + wrap - a.seg_lo + sh2; // even
+        n2 = a.seg_hi > p2_lo ? (a.seg_hi - wrap - a2 + TC_KSEG - 1) / TC_KSEG : 0;
+    }
+    __device__ int per_input() const { return n1 + n2; }
+    __device__ void chunk(int c, int &slot0, int &copy, int &pos0) const
+    {
+        if (c < n1) {
+            slot0 = a1 + c * TC_KSEG;
+            copy = sh1;
+            pos0 = c * TC_KSEG;
+        } else {
+            slot0 = a2 + (c - n1) * TC_KSEG;
+            copy = sh2;
+            pos0 = pos2 + (c - n1) * TC_KSEG;
+        }
+    }
+};
+
+template <int NOUT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_constant__ CUtensorMap tm_ir0,
+          const __grid_constant__ CUtensorMap tm_ir1)
+{
+    using Cfg = TcCfg<NOUT>;
+    constexpr int N2 = Cfg::N2;
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_NST * Cfg::STAGE_BYTES);
+    uint64_t *full_raw = bars, *full_ops = bars + TC_NST, *empty = bars + 2 * TC_NST;
+    uint64_t *acc_full = bars + 3 * TC_NST, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bin = blockIdx.x / a.groups, g = blockIdx.x % a.groups;
+    const int in_lo = a.n_in * g / a.groups, in_hi = a.n_in * (g + 1) / a.groups;
+    const TcSpan span(a);
+    const int cpi = span.per_input();
+    const int total = cpi * (in_hi - in_lo);
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_NST; s++) {
+            mbar_init(&full_raw[s], 1);
+            mbar_init(&full_ops[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- TMA producer -------------------------------------------------------------------
+        for (int t = 0; t < total; t++) {
+            if (lane == 0) {
+                const int s = t % TC_NST;
+                mbar_wait(&empty[s], ((t / TC_NST) & 1) ^ 1);
+                unsigned char *st = smem + s * Cfg::STAGE_BYTES;
+                const int in = in_lo + t / cpi;
+                int slot0, copy, pos0;
+                span.chunk(t % cpi, slot0, copy, pos0);
+                mbar_expect_tx(&full_raw[s], Cfg::A_BYTES + Cfg::B_BYTES);
+                tma_load_3d(st, &tm_ring, 2 * slot0, 0, bin * a.n_in + in, &full_raw[s]);
+                tma_load_3d(st + 2 * Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 2 * pos0, 0, bin * a.n_in + in, &full_raw[s]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer ---------------------------------------------------------------------
+        constexpr uint32_t idesc_wide = umma_idesc_tf32(2 * N2), idesc_narrow = umma_idesc_tf32(N2);
+        for (int t = 0; t < total; t++) {
+            if (lane == 0) {
+                const int s = t % TC_NST, iv = t / TC_DRAIN, b = iv & 1;
+                const bool first = (t % TC_DRAIN) == 0, last = (t % TC_DRAIN) == TC_DRAIN - 1 || t == total - 1;
+                if (first) mbar_wait(&acc_empty[b], ((iv >> 1) & 1) ^ 1);
+                mbar_wait(&full_ops[s], (t / TC_NST) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint32_t d_main = tmem + b * 2 * N2, d_cross = d_main + N2;
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    const uint64_t a_hi = umma_desc_k128(st + ks * 32), a_lo = umma_desc_k128(st + Cfg::A_BYTES + ks * 32);
+                    const uint64_t b_hl = umma_desc_k128(st + 2 * Cfg::A_BYTES + ks * 32);
+                    // [main | cross] (+)= A_hi * [B_hi | B_lo]^T ;  cross += A_lo * B_hi^T
+#ifndef TC_DBG_NO_WIDE
+                    umma_tf32(d_main, a_hi, b_hl, idesc_wide, (first && ks == 0) ? 0u : 1u);
+#endif
+#ifndef TC_DBG_NO_NARROW
+                    umma_tf32(d_cross, a_lo, b_hl, idesc_narrow, 1u);
+#endif
+                }
+                umma_commit(&empty[s]);
+                if (last) umma_commit(&acc_full[b]);
+            }
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // ---- splitters: lo = x - (the 19 bits the tensor core reads) ---------------------------
+        const int st_tid = tid - 64;
+        for (int t = 0; t < total; t++) {
+            const int s = t % TC_NST;
+            mbar_wait(&full_raw[s], (t / TC_NST) & 1);
+            float4 *hiA = reinterpret_cast<float4 *>(smem + s * Cfg::STAGE_BYTES);
+            float4 *loA = reinterpret_cast<float4 *>(smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES);
+            float4 *hiB = reinterpret_cast<float4 *>(smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES);
+            float4 *loB = reinterpret_cast<float4 *>(smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+            auto lo1 = [](float x) {
+                float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(r));
+                return __uint_as_float(u);
+            };
+#pragma unroll
+            for (int j = 0; j < Cfg::A_BYTES / 16 / 128; j++) {
+                float4 v = hiA[st_tid + 128 * j];
+                loA[st_tid + 128 * j] = make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w));
+            }
+            for (int i = st_tid; i < Cfg::B_BYTES / 16; i += 128) {
+                float4 v = hiB[i];
+                loB[i] = make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full_ops[s]);
+        }
+    } else {
+        // ---- drain warps: TMEM -> f32 registers every TC_DRAIN stages, then the partial spectra --
+        const int q = warp & 3; // TMEM lane quadrant this warp may touch
+        float acc[N2];
+#pragma unroll
+        for (int i = 0; i < N2; i++) acc[i] = 0.f;
+        const int nint = (total + TC_DRAIN - 1) / TC_DRAIN;
+        for (int iv = 0; iv < nint; iv++) {
+            const int b = iv & 1;
+            mbar_wait(&acc_full[b], (iv >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t base = tmem + ((uint32_t)(q * 32) << 16) + b * 2 * N2;
+#pragma unroll
+            for (int c = 0; c < N2; c += 16) {
+                uint32_t m[16], x[16];
+                tmem_ld16(base + c, m);
+                tmem_ld16(base + N2 + c, x);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; i++) acc[c + i] += __uint_as_float(m[i]) + __uint_as_float(x[i]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[b]);
+        }
+        const int s = q * 32 + lane;
+        if (s < a.n_streams) {
+            float2 *dst = a.part + (((size_t)g * a.n_streams + s) * NOUT) * a.B + bin;
+#pragma unroll
+            for (int o = 0; o < NOUT; o++) dst[(size_t)o * a.B] = make_float2(acc[o], acc[NOUT + o]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// K1 epilogue for the tensor-core layout: xcur [NS*IN][B] (packed spectra of the new block) -> column
+// `slot` of ring_t[bin][in][stream][Sp]
+__global__ void __launch_bounds__(256)
+k_tc_scatter_ring(const float2 *__restrict__ xcur, float2 *__restrict__ ring_t, int B, int n_in, long long total, long long Sp, int slot)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int bin = (int)(idx % B);
+    const long long c = idx / B; // stream * IN + in
+    const long long s = c / n_in, in = c % n_in;
+    ring_t[(((long long)bin * n_in + in) * TC_M + s) * Sp + slot] = xcur[idx];
+}
+
+// K5 epilogue: IR spectra of `npairs` (out, in) pairs starting at pair p0, src [npairs][rows][B] packed,
+// -> the B operand rows of both copies of ir_t[copy][bin][in][2*OUT][2*rowsP] (copy 1 shifted by one position)
+__global__ void __launch_bounds__(256)
+k_tc_build_ir(const float2 *__restrict__ src, float *__restrict__ ir_t, int B, int n_in, int n_out, int rows, long long rowsP,
+              long long p0, long long total, long long copy_stride)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int bin = (int)(idx % B);
+    const long long r = idx / B;
+    const int row = (int)(r % rows);
+    const long long p = p0 + r / rows;
+    const int out = (int)(p / n_in), in = (int)(p % n_in);
+    const float2 h = src[idx];
+    float2 re_row, im_row;
+    if (bin == 0) { // {DC, Nyquist}: two real products
+        re_row = make_float2(h.x, 0.f);
+        im_row = make_float2(0.f, h.y);
+    } else {
+        re_row = make_float2(h.x, -h.y);
+        im_row = make_float2(h.y, h.x);
+    }
+    float *base = ir_t + ((long long)bin * n_in + in) * (2 * n_out) * (2 * rowsP);
+    *reinterpret_cast<float2 *>(base + (long long)out * (2 * rowsP) + 2 * row) = re_row;
+    *reinterpret_cast<float2 *>(base + (long long)(n_out + out) * (2 * rowsP) + 2 * row) = im_row;
+    base += copy_stride;
+    *reinterpret_cast<float2 *>(base + (long long)out * (2 * rowsP) + 2 * (row + 1)) = re_row;
+    *reinterpret_cast<float2 *>(base + (long long)(n_out + out) * (2 * rowsP) + 2 * (row + 1)) = im_row;
+}
+
+// conv[so][k] = sum over input groups of part[g][so][k], ascending g
+__global__ void __launch_bounds__(256)
+k_tc_reduce(const float2 *__restrict__ part, float2 *__restrict__ conv, long long n, int groups)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n) return;
+    float2 t = part[idx];
+    for (int g = 1; g < groups; g++) {
+        float2 q = part[(long long)g * n + idx];
+        t.x += q.x;
+        t.y += q.y;
+    }
+    conv[idx] = t;
+}
+
+} // namespace fcb
