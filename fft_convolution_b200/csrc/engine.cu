@@ -162,6 +162,10 @@ static cudaEvent_t prof_before(cudaStream_t s, cudaEvent_t *stop)
     return ev.first;
 }
 
+namespace fcb {
+cudaEvent_t mac_profile_begin(cudaStream_t s, cudaEvent_t *stop) { return prof_before(s, stop); }
+} // namespace fcb
+
 extern "C" int fcb_profile_mac(int enable)
 {
     std::lock_guard<std::mutex> lock(g_prof.mu);

@@ -21,4 +21,8 @@ int run_mac_tile(int logb, cudaStream_t st, MacTileArgs a, int *zchunks_out);
 // part rows needed by run_mac_tile for this problem (upper bound on zchunks * NS * OUT * IN)
 int mac_tile_plan(int logb, int n_in, int n_out, int n_streams, int nsegs, int *zchunks, int *zlen);
 
+// fcb_profile_mac hook for MAC kernels launched outside engine.cu: returns nullptr when profiling is
+// off, else records the start event on `s` and hands back the stop event to record after the launch
+cudaEvent_t mac_profile_begin(cudaStream_t s, cudaEvent_t *stop);
+
 } // namespace fcb

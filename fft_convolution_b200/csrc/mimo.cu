@@ -25,10 +25,10 @@ typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, c
                                            const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// f32 tensor [d2][d1][d0] (d0 contiguous, row pitch / plane pitch in bytes), box [1][b1][32] with the
-// 128-byte swizzle the K-major UMMA descriptors expect; out-of-bounds elements read as zero
-static int tc_encode_map(CUtensorMap *tm, void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1, uint64_t pitch2,
-                         uint32_t b1)
+// f32 tensor [d3][d2][d1][d0] (d0 contiguous, pitches in bytes; rank 3 when d3 == 0), box [..1][b1][32] with
+// the 128-byte swizzle the K-major UMMA descriptors expect; out-of-bounds elements read as zero
+static int tc_encode_map(CUtensorMap *tm, void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t pitch1,
+                         uint64_t pitch2, uint64_t pitch3, uint32_t b1)
 {
     static TensorMapEncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -38,11 +38,11 @@ static int tc_encode_map(CUtensorMap *tm, void *base, uint64_t d0, uint64_t d1, 
         if (!p) return fail(FCB_ERR_CUDA, "cuTensorMapEncodeTiled is not exported by this driver");
         fn = (TensorMapEncodeTiledFn)p;
     }
-    cuuint64_t dims[3] = {d0, d1, d2};
-    cuuint64_t strides[2] = {pitch1, pitch2};
-    cuuint32_t box[3] = {2 * TC_KSEG, b1, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t dims[4] = {d0, d1, d2, d3};
+    cuuint64_t strides[3] = {pitch1, pitch2, pitch3};
+    cuuint32_t box[4] = {2 * TC_KSEG, b1, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d3 ? 4 : 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(FCB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return FCB_OK;
@@ -126,12 +126,13 @@ struct fcb_mimo {
     const float2 *tw = nullptr;
     // tensor-core path (K4, mimo_tc.cuh): transposed operands instead of ir / ring / premul
     bool tc = false;
-    float2 *ring_t = nullptr;  // [B][IN][128][Sp]
-    float *ir_t = nullptr;     // [2 copies][B][IN][2*OUT][2*rowsP], copy 1 shifted by one position
+    float2 *ring_t = nullptr;  // [B][IN][nblk][128][16], slot = 16 * block + column
+    float *ir_t = nullptr;     // [2 copies][B][IN][2*OUT][2*rowsP]; segment row r at position TC_LEAD + copy + r
     float2 *xcur = nullptr;    // [NS*IN][B] spectra of the current block before the scatter
     float2 *part_tc = nullptr; // [groups][NS*OUT][B]
     float2 *ir_tmp = nullptr;  // [tmp_pairs][rows][B] K5 output before the transposition
-    size_t Sp = 0, rowsP = 0, tmp_pairs = 0;
+    size_t nblk = 0, rowsP = 0, tmp_pairs = 0;
+    size_t ring_t_elems() const { return B * n_in * nblk * TC_M * TC_KSEG; }
     int tc_groups = 1;
     CUtensorMap tm_ring, tm_ir[2];
     size_t ir_copy_floats() const { return B * n_in * 2 * n_out * 2 * rowsP; }
@@ -203,25 +204,27 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
     const int tc_mode = g_mimo_tc.load();
     m->tc = tc_mode != 0 && m->n_out == 16 && ns <= (size_t)TC_M && (tc_mode == 1 || ns >= 32) && m->rows() > 0 && B >= 2;
     if (m->tc) {
-        m->Sp = (m->S + 1) & ~(size_t)1; // row pitches are multiples of 16 bytes
-        m->rowsP = (m->rows() + 2) & ~(size_t)1; // room for the shifted copy
+        m->nblk = (m->S + TC_KSEG - 1) / TC_KSEG;
+        m->rowsP = (TC_LEAD + 1 + m->rows() + 1) & ~(size_t)1; // positions per IR row; pitch a multiple of 16 bytes
         size_t groups = (6 * 148 + B - 1) / B; // ~6 waves of CTAs
         m->tc_groups = (int)(groups < 1 ? 1 : groups > m->n_in ? m->n_in : groups);
         const size_t per_pair = m->rows() * B * sizeof(float2);
         m->tmp_pairs = ((size_t)256 << 20) / per_pair;
         if (m->tmp_pairs < 1) m->tmp_pairs = 1;
         if (m->tmp_pairs > pairs) m->tmp_pairs = pairs;
-        if (!rc) rc = mimo_alloc((void **)&m->ring_t, B * m->n_in * TC_M * m->Sp * sizeof(float2), m->stream);
+        if (!rc) rc = mimo_alloc((void **)&m->ring_t, m->ring_t_elems() * sizeof(float2), m->stream);
         if (!rc) rc = mimo_alloc((void **)&m->ir_t, 2 * m->ir_copy_floats() * sizeof(float), m->stream);
         if (!rc) rc = mimo_alloc((void **)&m->xcur, ns * m->n_in * B * sizeof(float2), m->stream);
         if (!rc) rc = mimo_alloc((void **)&m->part_tc, (size_t)m->tc_groups * ns * m->n_out * B * sizeof(float2), m->stream);
         if (!rc) rc = mimo_alloc((void **)&m->ir_tmp, m->tmp_pairs * per_pair, m->stream);
+        const size_t tile = TC_M * TC_KSEG * sizeof(float2);
         if (!rc)
-            rc = tc_encode_map(&m->tm_ring, m->ring_t, 2 * m->S, TC_M, B * m->n_in, m->Sp * sizeof(float2),
-                               TC_M * m->Sp * sizeof(float2), TC_M);
+            rc = tc_encode_map(&m->tm_ring, m->ring_t, 2 * TC_KSEG, TC_M, m->nblk, B * m->n_in, TC_KSEG * sizeof(float2), tile,
+                               m->nblk * tile, TC_M);
         for (size_t sh = 0; sh < 2 && !rc; sh++)
-            rc = tc_encode_map(&m->tm_ir[sh], m->ir_t + sh * m->ir_copy_floats(), 2 * (m->rows() + sh), 2 * m->n_out, B * m->n_in,
-                               2 * m->rowsP * sizeof(float), 2 * m->n_out * 2 * m->rowsP * sizeof(float), (uint32_t)(2 * m->n_out));
+            rc = tc_encode_map(&m->tm_ir[sh], m->ir_t + sh * m->ir_copy_floats(), 2 * (TC_LEAD + sh + m->rows()), 2 * m->n_out,
+                               B * m->n_in, 0, 2 * m->rowsP * sizeof(float), 2 * m->n_out * 2 * m->rowsP * sizeof(float), 0,
+                               (uint32_t)(2 * m->n_out));
         if (!rc && cudaFuncSetAttribute(k_mimo_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<16>::SMEM) != cudaSuccess)
             rc = fail(FCB_ERR_CUDA, "k_mimo_tc: cannot opt in to %zu bytes of shared memory", TcCfg<16>::SMEM);
     } else {
@@ -294,7 +297,7 @@ extern "C" int fcb_mimo_reset(fcb_mimo *m)
     if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
     FCB_CUDA(cudaSetDevice(m->device));
     const size_t ns = m->n_streams, B = m->B;
-    if (m->tc) FCB_CUDA(cudaMemsetAsync(m->ring_t, 0, B * m->n_in * TC_M * m->Sp * sizeof(float2), m->stream));
+    if (m->tc) FCB_CUDA(cudaMemsetAsync(m->ring_t, 0, m->ring_t_elems() * sizeof(float2), m->stream));
     else FCB_CUDA(cudaMemsetAsync(m->ring, 0, ns * m->n_in * m->S * B * sizeof(float2), m->stream));
     FCB_CUDA(cudaMemsetAsync(m->overlap, 0, ns * m->n_out * B * sizeof(float), m->stream));
     m->current = 0;
@@ -315,7 +318,7 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
                             (long long)(ns * m->n_in)));
         const long long nx = (long long)(ns * m->n_in * B);
         k_tc_scatter_ring<<<(unsigned)((nx + 255) / 256), 256, 0, m->stream>>>(m->xcur, m->ring_t, (int)B, (int)m->n_in, nx,
-                                                                                (long long)m->Sp, (int)m->current);
+                                                                                (long long)m->nblk, (int)m->current);
         TcArgs t{};
         t.part = m->part_tc;
         t.B = (int)B;
@@ -326,7 +329,10 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
         t.seg_lo = (int)m->seg_lo;
         t.seg_hi = (int)m->seg_hi;
         t.groups = m->tc_groups;
+        cudaEvent_t prof_stop = nullptr;
+        const bool profiled = mac_profile_begin(m->stream, &prof_stop) != nullptr;
         k_mimo_tc<16><<<(unsigned)(B * m->tc_groups), TC_THREADS, TcCfg<16>::SMEM, m->stream>>>(t, m->tm_ring, m->tm_ir[0], m->tm_ir[1]);
+        if (profiled) cudaEventRecord(prof_stop, m->stream);
         const long long nc = (long long)(ns * m->n_out * B);
         k_tc_reduce<<<(unsigned)((nc + 255) / 256), 256, 0, m->stream>>>(m->part_tc, m->conv, nc, m->tc_groups);
         g_launches += 3;

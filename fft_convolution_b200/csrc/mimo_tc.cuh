@@ -12,15 +12,18 @@
 // and for the packed bin 0 ({DC, Nyquist}: two real products) Bm[o] = {H.re, 0}, Bm[OUT+o] = {0, H.im}.
 //
 // HBM layout (K-major operands, so a tile is one TMA box and no transposition happens on chip):
-//     ring_t [bin][in][128 stream rows][Sp slots] float2      A: row = stream, K = (slot, re/im)
-//     ir_t   [2][bin][in][2*OUT rows][2*rowsP]    float       B: row = n,      K = (segment, plane)
-// The new block's spectrum is scattered into column `current` of ring_t by K1's epilogue kernel;
-// ir_t is built once per set_ir.  Slot s holds segment i = (s - current) mod S, so the K loop runs
-// over two contiguous slot ranges; ragged ends are covered by TMA out-of-bounds zero fill on one
-// of the two operands (tensor extents are exactly 2*S and 2*(rows + shift)).  A TMA box must start
-// on a 16-byte boundary in global memory, i.e. on an even slot AND an even IR position; slot and
-// segment differ by `current`, so ir_t is kept twice — copy 1 shifted by one (zero) position —
-// and each slot range reads the copy whose parity matches.
+//     ring_t [bin][in][slot block][128 stream rows][16 slots] float2     A: row = stream, K = (slot, re/im)
+//     ir_t   [2][bin][in][2*OUT rows][2*posP]                 float      B: row = n,      K = (segment, plane)
+// ring_t is tile-major: the 16 slots x 128 streams one pipeline stage consumes are ONE contiguous
+// 16 KB run (DRAM-page friendly; a [stream][slot] matrix would be 128 separate 128-byte pieces).
+// The new block's spectrum is scattered into slot `current` of ring_t by K1's epilogue kernel;
+// ir_t is built once per set_ir.  Slot s holds segment i = (s - current) mod S, so the K loop walks
+// the slot blocks of two slot ranges and reads IR positions that start wherever `current` puts
+// them.  A TMA box must start on a 16-byte boundary, i.e. on an even IR position, so ir_t is kept
+// twice — copy 1 shifted by one position — and each range reads the copy whose parity matches.
+// Segment i sits at position TC_LEAD + copy + (i - seg_lo): the TC_LEAD zero positions in front
+// and TMA's out-of-bounds zero fill behind (the tensor extent is exact) blank the slots of a block
+// that belong to segments outside the range; ring slots >= S are never written and stay zero.
 //
 // Precision.  north_star asks for 1e-5 * RMS (f32); a tf32 product keeps 11 bits.  Every operand is
 // split on chip x = hi + lo (hi = the bits the tensor core reads, lo = x - hi, both exact) and
@@ -29,8 +32,13 @@
 // accumulator is drained into f32 registers every 128 K-elements and the small cross terms go to
 // their own accumulator columns (scripts/tc_probe.cu, profiles/r01_tc_probe.txt).
 //
-// One CTA = one (bin, input group): 10 warps — TMA producer, MMA issuer, 4 splitter warps
-// (hi/lo), 4 drain warps (TMEM -> registers -> partial spectra).
+// One CTA = one (bin, input group): 14 warps — TMA producer, MMA issuer, 8 splitter warps
+// (hi/lo), 4 drain warps (TMEM -> registers -> partial spectra).  Shared memory: TC_NR raw stages
+// (A 16 KB + B 4 KB, written by TMA) and TC_NL split stages of the small operand ([B_hi | B_lo],
+// 8 KB).  The big operand never returns to shared memory: a splitter thread owns one stream row,
+// reads its 128-byte swizzled row, and writes hi and lo straight into TMEM (tcgen05.st), from where
+// the MMAs take A — shared-memory bandwidth, not HBM, was the first version's limit (ncu: LSU
+// wavefronts 41 % + UMMA operand reads + TMA writes on one 128 B/clk port).
 #pragma once
 
 #include <cuda.h>
@@ -43,20 +51,28 @@ namespace fcb {
 
 constexpr int TC_M = 128;    // stream rows of one UMMA (streams are padded to this)
 constexpr int TC_KSEG = 16;  // segments per stage: 16 (re,im) pairs = 32 tf32 = one 128-byte swizzle row
-constexpr int TC_NST = 4;    // pipeline stages
+constexpr int TC_LEAD = 16;  // zero positions in front of every IR row
+constexpr int TC_NR = 8;     // raw (TMA) stages
+constexpr int TC_NL = 4;     // split-operand stages (A hi/lo in TMEM, [B_hi | B_lo] in shared memory)
 constexpr int TC_DRAIN = 4;  // stages per TMEM accumulation interval (K = 128 per drain)
-constexpr int TC_THREADS = 320;
+constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + 4);
 
 template <int NOUT>
 struct TcCfg {
     static constexpr int N2 = 2 * NOUT;                    // GEMM N (re | im)
     static constexpr int A_BYTES = TC_M * 128;             // 16 KB: 128 rows x 128 B
     static constexpr int B_BYTES = N2 * 128;               // 4 KB at 16 outputs
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES; // A_hi | A_lo | B_hi | B_lo
-    static constexpr int TMEM_COLS = 4 * N2;               // 2 buffers x (main N2 | cross N2)
-    static constexpr size_t SMEM = (size_t)TC_NST * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int RAW_BYTES = A_BYTES + B_BYTES;    // A | B as loaded
+    static constexpr int LO_BYTES = 2 * B_BYTES;           // B_hi | B_lo
+    static constexpr int ACC_COLS = 4 * N2;                // 2 buffers x (main N2 | cross N2)
+    static constexpr int A_COLS = 4 * TC_KSEG;             // per split stage: 32 columns of hi, 32 of lo
+    static constexpr int TMEM_NEED = ACC_COLS + TC_NL * A_COLS;
+    static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+    static constexpr size_t SMEM = (size_t)TC_NR * RAW_BYTES + (size_t)TC_NL * LO_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(N2 % 16 == 0 && 2 * N2 <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
-    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32 && TMEM_COLS <= 512, "TMEM allocation is a power of two");
+    static_assert(TMEM_NEED <= 512, "TMEM has 512 columns");
+    static_assert(RAW_BYTES % 1024 == 0 && LO_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 };
 
 struct TcArgs {
@@ -64,10 +80,18 @@ struct TcArgs {
     int B, n_in, n_streams;
     int S;               // ring slots
     int current;
-    int seg_lo, seg_hi;  // segments accumulated; IR position of segment i in copy sh = i - seg_lo + sh
+    int seg_lo, seg_hi;  // segments accumulated; IR position of segment i in copy sh = TC_LEAD + sh + i - seg_lo
     int groups;          // input groups per bin; grid = B * groups
 };
 
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar)
 {
     asm volatile(
@@ -98,6 +122,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A from TMEM (lanes = rows, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -111,36 +152,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
         : "r"(taddr));
 }
 
-// chunk c of one input's K loop -> ring slot, IR copy and IR position of its first (re,im) pair.
-// Range 1: segments [seg_lo, min(seg_hi, S - current)) in slots current + i; range 2: segments
-// [max(seg_lo, S - current), seg_hi) in slots i - (S - current).  Each range starts on the even slot
-// at or below its first slot; the extra leading slot meets the zero pad of IR copy 1.
+// chunk c of one input's K loop -> ring slot block, IR copy and IR position paired with the block's
+// first slot.  Range 1: segments [seg_lo, min(seg_hi, S - current)) in slots current + i; range 2:
+// segments [max(seg_lo, S - current), seg_hi) in slots i - (S - current).
 struct TcSpan {
-    int n1, a1, sh1, n2, a2, sh2, pos2;
+    int n1, blk1, sh1, pos1, n2, blk2, sh2, pos2;
     __device__ TcSpan(const TcArgs &a)
     {
         const int wrap = a.S - a.current;
-        const int p1_hi = a.seg_hi < wrap ? a.seg_hi : wrap;
-        const int first1 = a.current + a.seg_lo;
-        a1 = first1 & ~1;
-        sh1 = first1 & 1;
-        n1 = p1_hi > a.seg_lo ? (a.current + p1_hi - a1 + TC_KSEG - 1) / TC_KSEG : 0;
-        const int p2_lo = a.seg_lo > wrap ? a.seg_lo : wrap;
-        const int first2 = p2_lo - wrap;
-        a2 = first2 & ~1;
-        sh2 = (wrap - a.seg_lo) & 1;
-        pos2 = a2 + wrap - a.seg_lo + sh2; // even
-        n2 = a.seg_hi > p2_lo ? (a.seg_hi - wrap - a2 + TC_KSEG - 1) / TC_KSEG : 0;
+        const int hi1 = a.seg_hi < wrap ? a.seg_hi : wrap;
+        blk1 = (a.current + a.seg_lo) / TC_KSEG;
+        n1 = hi1 > a.seg_lo ? (a.current + hi1 - 1) / TC_KSEG - blk1 + 1 : 0;
+        sh1 = (a.current + a.seg_lo) & 1;
+        pos1 = TC_LEAD + sh1 + blk1 * TC_KSEG - a.current - a.seg_lo; // even, >= 1
+        const int lo2 = a.seg_lo > wrap ? a.seg_lo : wrap;
+        blk2 = (lo2 - wrap) / TC_KSEG;
+        n2 = a.seg_hi > lo2 ? (a.seg_hi - wrap - 1) / TC_KSEG - blk2 + 1 : 0;
+        sh2 = (wrap + a.seg_lo) & 1;
+        pos2 = TC_LEAD + sh2 + blk2 * TC_KSEG + wrap - a.seg_lo;
     }
     __device__ int per_input() const { return n1 + n2; }
-    __device__ void chunk(int c, int &slot0, int &copy, int &pos0) const
+    __device__ void chunk(int c, int &blk, int &copy, int &pos0) const
     {
         if (c < n1) {
-            slot0 = a1 + c * TC_KSEG;
+            blk = blk1 + c;
             copy = sh1;
-            pos0 = c * TC_KSEG;
+            pos0 = pos1 + c * TC_KSEG;
         } else {
-            slot0 = a2 + (c - n1) * TC_KSEG;
+            blk = blk2 + (c - n1);
             copy = sh2;
             pos0 = pos2 + (c - n1) * TC_KSEG;
         }
@@ -154,11 +193,13 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
 {
     using Cfg = TcCfg<NOUT>;
     constexpr int N2 = Cfg::N2;
+    constexpr int NSPLIT = 32 * TC_SPLIT_WARPS;
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_NST * Cfg::STAGE_BYTES);
-    uint64_t *full_raw = bars, *full_ops = bars + TC_NST, *empty = bars + 2 * TC_NST;
-    uint64_t *acc_full = bars + 3 * TC_NST, *acc_empty = acc_full + 2;
+    unsigned char *smem_lo = smem + TC_NR * Cfg::RAW_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_lo + TC_NL * Cfg::LO_BYTES);
+    uint64_t *full_raw = bars, *empty_raw = full_raw + TC_NR, *full_lo = empty_raw + TC_NR, *empty_lo = full_lo + TC_NL;
+    uint64_t *acc_full = empty_lo + TC_NL, *acc_empty = acc_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -169,10 +210,13 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
     const int total = cpi * (in_hi - in_lo);
 
     if (tid == 0) {
-        for (int s = 0; s < TC_NST; s++) {
+        for (int s = 0; s < TC_NR; s++) {
             mbar_init(&full_raw[s], 1);
-            mbar_init(&full_ops[s], 128);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty_raw[s], NSPLIT);
+        }
+        for (int s = 0; s < TC_NL; s++) {
+            mbar_init(&full_lo[s], NSPLIT);
+            mbar_init(&empty_lo[s], 1);
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(&acc_full[b], 1);
@@ -194,15 +238,15 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
         // ---- TMA producer -------------------------------------------------------------------
         for (int t = 0; t < total; t++) {
             if (lane == 0) {
-                const int s = t % TC_NST;
-                mbar_wait(&empty[s], ((t / TC_NST) & 1) ^ 1);
-                unsigned char *st = smem + s * Cfg::STAGE_BYTES;
+                const int s = t % TC_NR;
+                mbar_wait(&empty_raw[s], ((t / TC_NR) & 1) ^ 1);
+                unsigned char *st = smem + s * Cfg::RAW_BYTES;
                 const int in = in_lo + t / cpi;
-                int slot0, copy, pos0;
-                span.chunk(t % cpi, slot0, copy, pos0);
-                mbar_expect_tx(&full_raw[s], Cfg::A_BYTES + Cfg::B_BYTES);
-                tma_load_3d(st, &tm_ring, 2 * slot0, 0, bin * a.n_in + in, &full_raw[s]);
-                tma_load_3d(st + 2 * Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 2 * pos0, 0, bin * a.n_in + in, &full_raw[s]);
+                int blk, copy, pos0;
+                span.chunk(t % cpi, blk, copy, pos0);
+                mbar_expect_tx(&full_raw[s], Cfg::RAW_BYTES);
+                tma_load_4d(st, &tm_ring, 0, 0, blk, bin * a.n_in + in, &full_raw[s]);
+                tma_load_3d(st + Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 2 * pos0, 0, bin * a.n_in + in, &full_raw[s]);
             }
             __syncwarp();
         }
@@ -211,57 +255,76 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
         constexpr uint32_t idesc_wide = umma_idesc_tf32(2 * N2), idesc_narrow = umma_idesc_tf32(N2);
         for (int t = 0; t < total; t++) {
             if (lane == 0) {
-                const int s = t % TC_NST, iv = t / TC_DRAIN, b = iv & 1;
+                const int sl = t % TC_NL, iv = t / TC_DRAIN, b = iv & 1;
                 const bool first = (t % TC_DRAIN) == 0, last = (t % TC_DRAIN) == TC_DRAIN - 1 || t == total - 1;
                 if (first) mbar_wait(&acc_empty[b], ((iv >> 1) & 1) ^ 1);
-                mbar_wait(&full_ops[s], (t / TC_NST) & 1);
+                mbar_wait(&full_lo[sl], (t / TC_NL) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint32_t lo = smem_u32(smem_lo + sl * Cfg::LO_BYTES);
                 const uint32_t d_main = tmem + b * 2 * N2, d_cross = d_main + N2;
+                const uint32_t a_hi = tmem + Cfg::ACC_COLS + sl * Cfg::A_COLS, a_lo = a_hi + 2 * TC_KSEG;
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
-                    const uint64_t a_hi = umma_desc_k128(st + ks * 32), a_lo = umma_desc_k128(st + Cfg::A_BYTES + ks * 32);
-                    const uint64_t b_hl = umma_desc_k128(st + 2 * Cfg::A_BYTES + ks * 32);
+                    const uint64_t b_hl = umma_desc_k128(lo + ks * 32);
                     // [main | cross] (+)= A_hi * [B_hi | B_lo]^T ;  cross += A_lo * B_hi^T
-#ifndef TC_DBG_NO_WIDE
-                    umma_tf32(d_main, a_hi, b_hl, idesc_wide, (first && ks == 0) ? 0u : 1u);
-#endif
-#ifndef TC_DBG_NO_NARROW
-                    umma_tf32(d_cross, a_lo, b_hl, idesc_narrow, 1u);
-#endif
+                    umma_tf32_ts(d_main, a_hi + ks * 8, b_hl, idesc_wide, (first && ks == 0) ? 0u : 1u);
+                    umma_tf32_ts(d_cross, a_lo + ks * 8, b_hl, idesc_narrow, 1u);
                 }
-                umma_commit(&empty[s]);
+                umma_commit(&empty_lo[sl]);
                 if (last) umma_commit(&acc_full[b]);
             }
             __syncwarp();
         }
-    } else if (warp < 6) {
-        // ---- splitters: lo = x - (the 19 bits the tensor core reads) ---------------------------
+    } else if (warp < 2 + TC_SPLIT_WARPS) {
+        // ---- splitters: thread = (stream row, half of the 32 K-columns); hi = the 19 bits the
+        // tensor core reads, lo = x - hi; A goes to TMEM, [B_hi | B_lo] to shared memory ---------
         const int st_tid = tid - 64;
+        const int row = (warp & 3) * 32 + lane;  // TMEM lane quadrant of this warp
+        const int half = (warp - 2) >> 2;         // columns [16*half, 16*half + 16)
+        auto lo1 = [](float x) {
+            float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+            uint32_t u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(r));
+            return u;
+        };
         for (int t = 0; t < total; t++) {
-            const int s = t % TC_NST;
-            mbar_wait(&full_raw[s], (t / TC_NST) & 1);
-            float4 *hiA = reinterpret_cast<float4 *>(smem + s * Cfg::STAGE_BYTES);
-            float4 *loA = reinterpret_cast<float4 *>(smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES);
-            float4 *hiB = reinterpret_cast<float4 *>(smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES);
-            float4 *loB = reinterpret_cast<float4 *>(smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
-            auto lo1 = [](float x) {
-                float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-                uint32_t u;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(r));
-                return __uint_as_float(u);
-            };
+            const int sr = t % TC_NR, sl = t % TC_NL;
+            const unsigned char *rawA = smem + sr * Cfg::RAW_BYTES + row * 128;
+            const float4 *rawB = reinterpret_cast<const float4 *>(smem + sr * Cfg::RAW_BYTES + Cfg::A_BYTES);
+            float4 *hiB = reinterpret_cast<float4 *>(smem_lo + sl * Cfg::LO_BYTES);
+            float4 *loB = reinterpret_cast<float4 *>(smem_lo + sl * Cfg::LO_BYTES + Cfg::B_BYTES);
+            mbar_wait(&full_raw[sr], (t / TC_NR) & 1);
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < Cfg::A_BYTES / 16 / 128; j++) {
-                float4 v = hiA[st_tid + 128 * j];
-                loA[st_tid + 128 * j] = make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w));
+            for (int j = 0; j < 4; j++) { // logical 16-byte chunk c of a row sits at chunk c ^ (row & 7)
+                const float4 v = *reinterpret_cast<const float4 *>(rawA + ((((half * 4 + j) ^ (row & 7))) << 4));
+                hi[4 * j + 0] = __float_as_uint(v.x), hi[4 * j + 1] = __float_as_uint(v.y);
+                hi[4 * j + 2] = __float_as_uint(v.z), hi[4 * j + 3] = __float_as_uint(v.w);
+                lo[4 * j + 0] = lo1(v.x), lo[4 * j + 1] = lo1(v.y), lo[4 * j + 2] = lo1(v.z), lo[4 * j + 3] = lo1(v.w);
             }
-            for (int i = st_tid; i < Cfg::B_BYTES / 16; i += 128) {
-                float4 v = hiB[i];
-                loB[i] = make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w));
-            }
+            float4 w[(Cfg::B_BYTES / 16 + NSPLIT - 1) / NSPLIT];
+#pragma unroll
+            for (int j = 0; j < (Cfg::B_BYTES / 16 + NSPLIT - 1) / NSPLIT; j++)
+                if (st_tid + NSPLIT * j < Cfg::B_BYTES / 16) w[j] = rawB[st_tid + NSPLIT * j];
+            mbar_arrive(&empty_raw[sr]); // the raw stage is in registers now
+            mbar_wait(&empty_lo[sl], ((t / TC_NL) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::ACC_COLS + sl * Cfg::A_COLS + half * 16;
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 2 * TC_KSEG, lo);
+#pragma unroll
+            for (int j = 0; j < (Cfg::B_BYTES / 16 + NSPLIT - 1) / NSPLIT; j++)
+                if (st_tid + NSPLIT * j < Cfg::B_BYTES / 16) {
+                    hiB[st_tid + NSPLIT * j] = w[j];
+                    float4 l;
+                    l.x = __uint_as_float(lo1(w[j].x)), l.y = __uint_as_float(lo1(w[j].y));
+                    l.z = __uint_as_float(lo1(w[j].z)), l.w = __uint_as_float(lo1(w[j].w));
+                    loB[st_tid + NSPLIT * j] = l;
+                }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&full_ops[s]);
+            mbar_arrive(&full_lo[sl]);
         }
     } else {
         // ---- drain warps: TMEM -> f32 registers every TC_DRAIN stages, then the partial spectra --
@@ -301,21 +364,22 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
     }
 }
 
-// K1 epilogue for the tensor-core layout: xcur [NS*IN][B] (packed spectra of the new block) -> column
-// `slot` of ring_t[bin][in][stream][Sp]
+// K1 epilogue for the tensor-core layout: xcur [NS*IN][B] (packed spectra of the new block) -> slot
+// `slot` of ring_t[bin][in][slot block][stream][16]
 __global__ void __launch_bounds__(256)
-k_tc_scatter_ring(const float2 *__restrict__ xcur, float2 *__restrict__ ring_t, int B, int n_in, long long total, long long Sp, int slot)
+k_tc_scatter_ring(const float2 *__restrict__ xcur, float2 *__restrict__ ring_t, int B, int n_in, long long total, long long nblk, int slot)
 {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= total) return;
     const int bin = (int)(idx % B);
     const long long c = idx / B; // stream * IN + in
     const long long s = c / n_in, in = c % n_in;
-    ring_t[(((long long)bin * n_in + in) * TC_M + s) * Sp + slot] = xcur[idx];
+    ring_t[((((long long)bin * n_in + in) * nblk + slot / TC_KSEG) * TC_M + s) * TC_KSEG + slot % TC_KSEG] = xcur[idx];
 }
 
 // K5 epilogue: IR spectra of `npairs` (out, in) pairs starting at pair p0, src [npairs][rows][B] packed,
-// -> the B operand rows of both copies of ir_t[copy][bin][in][2*OUT][2*rowsP] (copy 1 shifted by one position)
+// -> the B operand rows of both copies of ir_t[copy][bin][in][2*OUT][2*posP]; segment row r sits at position
+// TC_LEAD + copy + r
 __global__ void __launch_bounds__(256)
 k_tc_build_ir(const float2 *__restrict__ src, float *__restrict__ ir_t, int B, int n_in, int n_out, int rows, long long rowsP,
               long long p0, long long total, long long copy_stride)
@@ -337,11 +401,11 @@ k_tc_build_ir(const float2 *__restrict__ src, float *__restrict__ ir_t, int B, i
         im_row = make_float2(h.y, h.x);
     }
     float *base = ir_t + ((long long)bin * n_in + in) * (2 * n_out) * (2 * rowsP);
-    *reinterpret_cast<float2 *>(base + (long long)out * (2 * rowsP) + 2 * row) = re_row;
-    *reinterpret_cast<float2 *>(base + (long long)(n_out + out) * (2 * rowsP) + 2 * row) = im_row;
+    *reinterpret_cast<float2 *>(base + (long long)out * (2 * rowsP) + 2 * (TC_LEAD + row)) = re_row;
+    *reinterpret_cast<float2 *>(base + (long long)(n_out + out) * (2 * rowsP) + 2 * (TC_LEAD + row)) = im_row;
     base += copy_stride;
-    *reinterpret_cast<float2 *>(base + (long long)out * (2 * rowsP) + 2 * (row + 1)) = re_row;
-    *reinterpret_cast<float2 *>(base + (long long)(n_out + out) * (2 * rowsP) + 2 * (row + 1)) = im_row;
+    *reinterpret_cast<float2 *>(base + (long long)out * (2 * rowsP) + 2 * (TC_LEAD + 1 + row)) = re_row;
+    *reinterpret_cast<float2 *>(base + (long long)(n_out + out) * (2 * rowsP) + 2 * (TC_LEAD + 1 + row)) = im_row;
 }
 
 // conv[so][k] = sum over input groups of part[g][so][k], ascending g

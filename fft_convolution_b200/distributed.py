@@ -24,13 +24,14 @@ class _DeviceBuffer:
 class ShardedMimoConvolver:
     """One IR-partition shard per rank of the default process group (NCCL on GPUs)."""
 
-    def __init__(self, responses, block_size: int, max_response_length: int, *, n_streams: int = 1, device: int = 0):
+    def __init__(self, responses, block_size: int, max_response_length: int, *, n_streams: int = 1, device: int = 0,
+                 tensor_cores: bool | None = None):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
         self.m = MimoConvolver.init(responses, block_size, max_response_length, n_streams=n_streams,
                                     shard_index=self.rank, shard_count=self.world, device=device,
-                                    stream=self.stream.cuda_stream)
+                                    stream=self.stream.cuda_stream, tensor_cores=tensor_cores)
         ptr, n = self.m.conv_buffer()
         self._keep = _DeviceBuffer(ptr, n)
         self.conv = torch.as_tensor(self._keep, device=f"cuda:{device}")

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--streams", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--tc", type=int, default=-1, help="1/0 force the tensor-core matrix MAC (K4) on/off, -1 library default")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -41,7 +42,7 @@ def main():
     lib = _lib.load()
     N, B, L, NS = a.n, a.block, int(a.ir_seconds * 48000), a.streams
     h = bench.synth_irs(0, N * N, 0, L).reshape(N, N, L)  # IR index c = out*N + in
-    m = ShardedMimoConvolver(h, B, L, n_streams=NS, device=local)
+    m = ShardedMimoConvolver(h, B, L, n_streams=NS, device=local, tensor_cores=None if a.tc < 0 else bool(a.tc))
     S = m.m.seg_count
     lo, hi = m.m.segment_range
     x = [torch.from_numpy(bench.synth_noise(0, NS * N, B * i, B)).cuda(local) for i in range(8)]
@@ -66,7 +67,7 @@ def main():
     t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    k2_ms = tot.value / max(nl.value, 1)
+    k2_ms = max(tot.value / max(nl.value, 1), 1e-9)
     K = B + 1
     rows = hi - max(lo, 1)
     ir_bytes = N * N * rows * K * 8  # IR matrix rows this shard streams from HBM per block
@@ -74,6 +75,8 @@ def main():
     if rank == 0:
         print(json.dumps({
             "config": f"MIMO {N}x{N}, IR {a.ir_seconds:g} s ({L} taps, S={S}), block {B}, streams {NS}, {world} GPU(s) (IR-partition shards)",
+            "tensor_cores": bool(m.m.uses_tensor_cores),
+            "T_cmac_per_s": NS * N * N * (hi - lo) * B / (float(t[0]) / 1e3) / 1e12,
             "ms_per_block": float(t[0]), "block_period_ms": 1000.0 * B / 48000, "realtime_factor": 1000.0 * B / 48000 / float(t[0]),
             "k2_ms": k2_ms, "k2_ir_GBs": ir_bytes / (k2_ms / 1e3) / 1e9, "k2_ir_plus_ring_GBs": (ir_bytes + ring_bytes) / (k2_ms / 1e3) / 1e9,
             "ir_bytes_per_block_this_shard": ir_bytes, "segments_this_shard": [lo, hi],

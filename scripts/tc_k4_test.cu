@@ -21,7 +21,8 @@ using namespace fcb;
 typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static CUtensorMap make_map(void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t p1, uint64_t p2, uint32_t b1)
+static CUtensorMap make_map(void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t p1, uint64_t p2, uint64_t p3,
+                            uint32_t b1)
 {
     static EncodeTiled enc = nullptr;
     if (!enc) {
@@ -31,9 +32,9 @@ static CUtensorMap make_map(void *base, uint64_t d0, uint64_t d1, uint64_t d2, u
         enc = (EncodeTiled)fn;
     }
     CUtensorMap tm;
-    cuuint64_t dims[3] = {d0, d1, d2}, strides[2] = {p1, p2};
-    cuuint32_t box[3] = {2 * TC_KSEG, b1, 1}, es[3] = {1, 1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t dims[4] = {d0, d1, d2, d3}, strides[3] = {p1, p2, p3};
+    cuuint32_t box[4] = {2 * TC_KSEG, b1, 1, 1}, es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d3 ? 4 : 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         printf("encode failed %d\n", (int)r);
@@ -53,22 +54,25 @@ int main(int argc, char **argv)
     const int NS = argc > 4 ? atoi(argv[4]) : 5, cur = argc > 5 ? atoi(argv[5]) : 7, groups = argc > 6 ? atoi(argv[6]) : 1;
     const int seg_lo = argc > 7 ? atoi(argv[7]) : 0, seg_hi = argc > 8 ? atoi(argv[8]) : S;
     const int OUT = 16, rows = seg_hi - seg_lo;
-    const size_t Sp = (S + 1) & ~1, rowsP = (rows + 2) & ~1;
+    const size_t nblk = (S + TC_KSEG - 1) / TC_KSEG, rowsP = (TC_LEAD + 1 + rows + 1) & ~1;
+    auto ring_at = [&](int b, int in, int s, int sl, int p) {
+        return (((((size_t)b * IN + in) * nblk + sl / TC_KSEG) * TC_M + s) * TC_KSEG + sl % TC_KSEG) * 2 + p;
+    };
     printf("B=%d IN=%d S=%d NS=%d cur=%d groups=%d segs [%d,%d)\n", B, IN, S, NS, cur, groups, seg_lo, seg_hi);
     const size_t copy = (size_t)B * IN * 2 * OUT * 2 * rowsP;
-    std::vector<float> ring((size_t)B * IN * TC_M * Sp * 2, 0.f), ir(2 * copy, 0.f);
+    std::vector<float> ring((size_t)B * IN * nblk * TC_M * TC_KSEG * 2, 0.f), ir(2 * copy, 0.f);
     uint64_t seed = 99;
     for (int b = 0; b < B; b++)
         for (int in = 0; in < IN; in++) {
             for (int s = 0; s < NS; s++)
                 for (int sl = 0; sl < S; sl++)
-                    for (int p = 0; p < 2; p++) ring[((((size_t)b * IN + in) * TC_M + s) * Sp + sl) * 2 + p] = (float)lcg(seed);
+                    for (int p = 0; p < 2; p++) ring[ring_at(b, in, s, sl, p)] = (float)lcg(seed);
             for (int n = 0; n < 2 * OUT; n++)
                 for (int r = 0; r < rows; r++)
                     for (int p = 0; p < 2; p++) {
                         const float v = (float)lcg(seed);
-                        ir[(((size_t)b * IN + in) * 2 * OUT + n) * 2 * rowsP + 2 * r + p] = v;
-                        ir[copy + (((size_t)b * IN + in) * 2 * OUT + n) * 2 * rowsP + 2 * (r + 1) + p] = v;
+                        ir[(((size_t)b * IN + in) * 2 * OUT + n) * 2 * rowsP + 2 * (TC_LEAD + r) + p] = v;
+                        ir[copy + (((size_t)b * IN + in) * 2 * OUT + n) * 2 * rowsP + 2 * (TC_LEAD + 1 + r) + p] = v;
                     }
         }
     float *d_ring, *d_ir;
@@ -79,9 +83,11 @@ int main(int argc, char **argv)
     CK(cudaMemcpy(d_ring, ring.data(), ring.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ir, ir.data(), ir.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(d_part, 0xFF, (size_t)groups * NS * OUT * B * 8));
-    CUtensorMap tmr = make_map(d_ring, 2 * S, TC_M, (uint64_t)B * IN, Sp * 8, TC_M * Sp * 8, TC_M);
-    CUtensorMap tmi = make_map(d_ir, 2 * rows, 2 * OUT, (uint64_t)B * IN, 2 * rowsP * 4, 2 * OUT * 2 * rowsP * 4, 2 * OUT);
-    CUtensorMap tmi1 = make_map(d_ir + copy, 2 * (rows + 1), 2 * OUT, (uint64_t)B * IN, 2 * rowsP * 4, 2 * OUT * 2 * rowsP * 4, 2 * OUT);
+    const uint64_t tile = (uint64_t)TC_M * TC_KSEG * 8;
+    CUtensorMap tmr = make_map(d_ring, 2 * TC_KSEG, TC_M, nblk, (uint64_t)B * IN, TC_KSEG * 8, tile, nblk * tile, TC_M);
+    CUtensorMap tmi = make_map(d_ir, 2 * (TC_LEAD + rows), 2 * OUT, (uint64_t)B * IN, 0, 2 * rowsP * 4, 2 * OUT * 2 * rowsP * 4, 0, 2 * OUT);
+    CUtensorMap tmi1 =
+        make_map(d_ir + copy, 2 * (TC_LEAD + 1 + rows), 2 * OUT, (uint64_t)B * IN, 0, 2 * rowsP * 4, 2 * OUT * 2 * rowsP * 4, 0, 2 * OUT);
     CK(cudaFuncSetAttribute(k_mimo_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<16>::SMEM));
     TcArgs a{};
     a.part = d_part;
@@ -108,8 +114,8 @@ int main(int argc, char **argv)
                     for (int i = seg_lo; i < seg_hi; i++) {
                         const int sl = (cur + i) % S;
                         for (int p = 0; p < 2; p++)
-                            ref += (double)ring[((((size_t)b * IN + in) * TC_M + s) * Sp + sl) * 2 + p] *
-                                   (double)ir[(((size_t)b * IN + in) * 2 * OUT + n) * 2 * rowsP + 2 * (i - seg_lo) + p];
+                            ref += (double)ring[ring_at(b, in, s, sl, p)] *
+                                   (double)ir[(((size_t)b * IN + in) * 2 * OUT + n) * 2 * rowsP + 2 * (TC_LEAD + i - seg_lo) + p];
                     }
                 double got = 0;
                 for (int g = 0; g < groups; g++) {
