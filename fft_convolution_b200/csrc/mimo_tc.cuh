@@ -53,7 +53,11 @@ constexpr int TC_M = 128;    // stream rows of one UMMA (streams are padded to t
 constexpr int TC_KSEG = 16;  // segments per stage: 16 (re,im) pairs = 32 tf32 = one 128-byte swizzle row
 constexpr int TC_LEAD = 16;  // zero positions in front of every IR row
 constexpr int TC_NR = 8;     // raw (TMA) stages
-constexpr int TC_NL = 4;     // split-operand stages (A hi/lo in TMEM, [B_hi | B_lo] in shared memory)
+#ifndef TC_NSETS
+#define TC_NSETS 1
+#endif
+constexpr int TC_SETS = TC_NSETS; // independent accumulator sets (K steps alternate between them: dependent MMAs expose the pipe latency)
+constexpr int TC_NL = TC_SETS == 1 ? 4 : 2; // split-operand stages (A hi/lo in TMEM, [B_hi | B_lo] in shared memory)
 constexpr int TC_DRAIN = 4;  // stages per TMEM accumulation interval (K = 128 per drain)
 constexpr int TC_SPLIT_WARPS = 8;
 constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + 4);
@@ -65,7 +69,9 @@ struct TcCfg {
     static constexpr int B_BYTES = N2 * 128;               // 4 KB at 16 outputs
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;    // A | B as loaded
     static constexpr int LO_BYTES = 2 * B_BYTES;           // B_hi | B_lo
-    static constexpr int ACC_COLS = 4 * N2;                // 2 buffers x (main N2 | cross N2)
+    static constexpr int SET_COLS = 3 * N2;                // main | cross (hi*lo) | cross (lo*hi)
+    static constexpr int BUF_COLS = TC_SETS * SET_COLS;
+    static constexpr int ACC_COLS = 2 * BUF_COLS;          // double-buffered against the drain
     static constexpr int A_COLS = 4 * TC_KSEG;             // per split stage: 32 columns of hi, 32 of lo
     static constexpr int TMEM_NEED = ACC_COLS + TC_NL * A_COLS;
     static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
@@ -98,6 +104,15 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, in
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
         "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+// one lane of a converged warp; ptxas then issues the single-thread tcgen05 / TMA instructions
+// directly instead of wrapping each one in an ELECT + R2UR + BRA.U.ANY lane-serialisation loop (~120 cycles per
+// MMA with a plain `if (lane == 0)`: measured, scripts/tc_mma_rate.cu)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -237,16 +252,20 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
     if (warp == 0) {
         // ---- TMA producer -------------------------------------------------------------------
         for (int t = 0; t < total; t++) {
-            if (lane == 0) {
-                const int s = t % TC_NR;
-                mbar_wait(&empty_raw[s], ((t / TC_NR) & 1) ^ 1);
-                unsigned char *st = smem + s * Cfg::RAW_BYTES;
-                const int in = in_lo + t / cpi;
-                int blk, copy, pos0;
-                span.chunk(t % cpi, blk, copy, pos0);
+            const int s = t % TC_NR;
+            mbar_wait(&empty_raw[s], ((t / TC_NR) & 1) ^ 1);
+            unsigned char *st = smem + s * Cfg::RAW_BYTES;
+            const int in = in_lo + t / cpi;
+            int blk, copy, pos0;
+            span.chunk(t % cpi, blk, copy, pos0);
+            if (elect_one()) {
                 mbar_expect_tx(&full_raw[s], Cfg::RAW_BYTES);
                 tma_load_4d(st, &tm_ring, 0, 0, blk, bin * a.n_in + in, &full_raw[s]);
+#ifndef TC_DBG_NO_IR
                 tma_load_3d(st + Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 2 * pos0, 0, bin * a.n_in + in, &full_raw[s]);
+#else
+                tma_load_3d(st + Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 0, 0, 0, &full_raw[s]);
+#endif
             }
             __syncwarp();
         }
@@ -254,21 +273,25 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
         // ---- MMA issuer ---------------------------------------------------------------------
         constexpr uint32_t idesc_wide = umma_idesc_tf32(2 * N2), idesc_narrow = umma_idesc_tf32(N2);
         for (int t = 0; t < total; t++) {
-            if (lane == 0) {
-                const int sl = t % TC_NL, iv = t / TC_DRAIN, b = iv & 1;
-                const bool first = (t % TC_DRAIN) == 0, last = (t % TC_DRAIN) == TC_DRAIN - 1 || t == total - 1;
-                if (first) mbar_wait(&acc_empty[b], ((iv >> 1) & 1) ^ 1);
-                mbar_wait(&full_lo[sl], (t / TC_NL) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int sl = t % TC_NL, iv = t / TC_DRAIN, b = iv & 1;
+            const bool first = (t % TC_DRAIN) == 0, last = (t % TC_DRAIN) == TC_DRAIN - 1 || t == total - 1;
+            if (first) mbar_wait(&acc_empty[b], ((iv >> 1) & 1) ^ 1);
+            mbar_wait(&full_lo[sl], (t / TC_NL) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
                 const uint32_t lo = smem_u32(smem_lo + sl * Cfg::LO_BYTES);
-                const uint32_t d_main = tmem + b * 2 * N2, d_cross = d_main + N2;
+                const uint32_t d_buf = tmem + b * Cfg::BUF_COLS;
                 const uint32_t a_hi = tmem + Cfg::ACC_COLS + sl * Cfg::A_COLS, a_lo = a_hi + 2 * TC_KSEG;
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
                     const uint64_t b_hl = umma_desc_k128(lo + ks * 32);
-                    // [main | cross] (+)= A_hi * [B_hi | B_lo]^T ;  cross += A_lo * B_hi^T
-                    umma_tf32_ts(d_main, a_hi + ks * 8, b_hl, idesc_wide, (first && ks == 0) ? 0u : 1u);
-                    umma_tf32_ts(d_cross, a_lo + ks * 8, b_hl, idesc_narrow, 1u);
+                    // [main | cross1] (+)= A_hi * [B_hi | B_lo]^T ;  cross2 (+)= A_lo * B_hi^T, in set ks % TC_SETS
+                    const uint32_t d_set = d_buf + (ks % TC_SETS) * Cfg::SET_COLS;
+                    const uint32_t acc_on = (first && ks < TC_SETS) ? 0u : 1u;
+#ifndef TC_DBG_NO_MMA
+                    umma_tf32_ts(d_set, a_hi + ks * 8, b_hl, idesc_wide, acc_on);
+                    umma_tf32_ts(d_set + 2 * N2, a_lo + ks * 8, b_hl, idesc_narrow, acc_on);
+#endif
                 }
                 umma_commit(&empty_lo[sl]);
                 if (last) umma_commit(&acc_full[b]);
@@ -310,8 +333,12 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
             mbar_wait(&empty_lo[sl], ((t / TC_NL) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::ACC_COLS + sl * Cfg::A_COLS + half * 16;
+#ifndef TC_DBG_NO_STTM
             tmem_st16(ta, hi);
             tmem_st16(ta + 2 * TC_KSEG, lo);
+#else
+            if (hi[0] == 0x12345678u && lo[3] == 0x9abcdefu) tmem_st16(ta, hi);
+#endif
 #pragma unroll
             for (int j = 0; j < (Cfg::B_BYTES / 16 + NSPLIT - 1) / NSPLIT; j++)
                 if (st_tid + NSPLIT * j < Cfg::B_BYTES / 16) {
@@ -337,15 +364,20 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
             const int b = iv & 1;
             mbar_wait(&acc_full[b], (iv >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t base = tmem + ((uint32_t)(q * 32) << 16) + b * 2 * N2;
+            const uint32_t base = tmem + ((uint32_t)(q * 32) << 16) + b * Cfg::BUF_COLS;
 #pragma unroll
-            for (int c = 0; c < N2; c += 16) {
-                uint32_t m[16], x[16];
-                tmem_ld16(base + c, m);
-                tmem_ld16(base + N2 + c, x);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int set = 0; set < TC_SETS; set++) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) acc[c + i] += __uint_as_float(m[i]) + __uint_as_float(x[i]);
+                for (int c = 0; c < N2; c += 16) {
+                    uint32_t m[16], x[16], y[16];
+                    tmem_ld16(base + set * Cfg::SET_COLS + c, m);
+                    tmem_ld16(base + set * Cfg::SET_COLS + N2 + c, x);
+                    tmem_ld16(base + set * Cfg::SET_COLS + 2 * N2 + c, y);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        acc[c + i] += __uint_as_float(m[i]) + (__uint_as_float(x[i]) + __uint_as_float(y[i]));
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[b]);

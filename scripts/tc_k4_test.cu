@@ -54,15 +54,17 @@ int main(int argc, char **argv)
     const int NS = argc > 4 ? atoi(argv[4]) : 5, cur = argc > 5 ? atoi(argv[5]) : 7, groups = argc > 6 ? atoi(argv[6]) : 1;
     const int seg_lo = argc > 7 ? atoi(argv[7]) : 0, seg_hi = argc > 8 ? atoi(argv[8]) : S;
     const int OUT = 16, rows = seg_hi - seg_lo;
+    const bool perf = getenv("TC_PERF") != nullptr; // device-filled operands, timing only
     const size_t nblk = (S + TC_KSEG - 1) / TC_KSEG, rowsP = (TC_LEAD + 1 + rows + 1) & ~1;
     auto ring_at = [&](int b, int in, int s, int sl, int p) {
         return (((((size_t)b * IN + in) * nblk + sl / TC_KSEG) * TC_M + s) * TC_KSEG + sl % TC_KSEG) * 2 + p;
     };
     printf("B=%d IN=%d S=%d NS=%d cur=%d groups=%d segs [%d,%d)\n", B, IN, S, NS, cur, groups, seg_lo, seg_hi);
     const size_t copy = (size_t)B * IN * 2 * OUT * 2 * rowsP;
-    std::vector<float> ring((size_t)B * IN * nblk * TC_M * TC_KSEG * 2, 0.f), ir(2 * copy, 0.f);
+    const size_t ring_n = (size_t)B * IN * nblk * TC_M * TC_KSEG * 2;
+    std::vector<float> ring(perf ? 1 : ring_n, 0.f), ir(perf ? 1 : 2 * copy, 0.f);
     uint64_t seed = 99;
-    for (int b = 0; b < B; b++)
+    for (int b = 0; b < (perf ? 0 : B); b++)
         for (int in = 0; in < IN; in++) {
             for (int s = 0; s < NS; s++)
                 for (int sl = 0; sl < S; sl++)
@@ -77,11 +79,17 @@ int main(int argc, char **argv)
         }
     float *d_ring, *d_ir;
     float2 *d_part;
-    CK(cudaMalloc(&d_ring, ring.size() * 4));
-    CK(cudaMalloc(&d_ir, ir.size() * 4));
+    CK(cudaMalloc(&d_ring, ring_n * 4));
+    CK(cudaMalloc(&d_ir, 2 * copy * 4));
+    if (perf) {
+        CK(cudaMemset(d_ring, 0x3c, ring_n * 4)); // 0x3c3c3c3c = 0.0115
+        CK(cudaMemset(d_ir, 0x3c, 2 * copy * 4));
+    }
     CK(cudaMalloc(&d_part, (size_t)groups * NS * OUT * B * 8));
-    CK(cudaMemcpy(d_ring, ring.data(), ring.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_ir, ir.data(), ir.size() * 4, cudaMemcpyHostToDevice));
+    if (!perf) {
+        CK(cudaMemcpy(d_ring, ring.data(), ring.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_ir, ir.data(), ir.size() * 4, cudaMemcpyHostToDevice));
+    }
     CK(cudaMemset(d_part, 0xFF, (size_t)groups * NS * OUT * B * 8));
     const uint64_t tile = (uint64_t)TC_M * TC_KSEG * 8;
     CUtensorMap tmr = make_map(d_ring, 2 * TC_KSEG, TC_M, nblk, (uint64_t)B * IN, TC_KSEG * 8, tile, nblk * tile, TC_M);
@@ -102,6 +110,26 @@ int main(int argc, char **argv)
     k_mimo_tc<16><<<B * groups, TC_THREADS, TcCfg<16>::SMEM>>>(a, tmr, tmi, tmi1);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
+    if (perf) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        const int reps = 10;
+        CK(cudaEventRecord(e0));
+        for (int r = 0; r < reps; r++) {
+            a.current = (cur + 37 * r) % S;
+            k_mimo_tc<16><<<B * groups, TC_THREADS, TcCfg<16>::SMEM>>>(a, tmr, tmi, tmi1);
+        }
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        ms /= reps;
+        const double bytes = (double)B * IN * ((double)nblk * TC_M * TC_KSEG * 8 + 2.0 * OUT * rows * 8);
+        printf("PERF %.4f ms per launch, %.0f GB/s of operand bytes, %.2f T cMAC/s (128 rows)\n", ms, bytes / ms / 1e6,
+               (double)B * IN * rows * 128 * OUT / ms / 1e9);
+        return 0;
+    }
     std::vector<float2> part((size_t)groups * NS * OUT * B);
     CK(cudaMemcpy(part.data(), d_part, part.size() * 8, cudaMemcpyDeviceToHost));
     double emax = 0, rms = 0;
