@@ -279,7 +279,7 @@ class MimoConvolver:
              shard_index: int = 0, shard_count: int = 1, device: int = 0, stream=None,
              tensor_cores: bool | None = None) -> "MimoConvolver":
         """tensor_cores: True / False force the tcgen05 matrix MAC (K4; 16 outputs, <= 128 streams) on /
-        off for this object; None keeps the library default (on from 32 streams)."""
+        off for this object; None keeps the library default (on from 16 streams)."""
         lib = _lib.load()
         _lib.require_gpu()
         r = np.ascontiguousarray(responses, dtype=np.float32)

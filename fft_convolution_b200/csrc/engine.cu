@@ -199,7 +199,7 @@ static std::atomic<int> g_fused_stages{2};     // fused kernel: 2 stages (64 KB)
 static std::atomic<bool> g_tma_io{true};       // fused kernel moves its input/output blocks with bulk copies
 static std::atomic<bool> g_shared_reuse{true}; // shared-IR engines: stage each IR tile once per CTA
 namespace fcb { std::atomic<bool> g_mimo_tile{true}; } // matrix K2 with in-CTA reuse (0: per-channel K2)
-namespace fcb { std::atomic<int> g_mimo_tc{2}; }       // K4 tensor-core matrix MAC: 0 never, 1 when the shape fits, 2 + NS >= 32
+namespace fcb { std::atomic<int> g_mimo_tc{2}; }       // K4 tensor-core matrix MAC: 0 never, 1 when the shape fits, 2 + NS >= 16
 
 template <int B, int NST>
 static int launch_mac_bulk(const MacArgs &a, cudaStream_t st)

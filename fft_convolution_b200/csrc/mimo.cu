@@ -19,7 +19,7 @@ using namespace fcb;
 
 namespace fcb {
 extern std::atomic<bool> g_mimo_tile;
-extern std::atomic<int> g_mimo_tc; // 0 never, 1 whenever the shape fits, 2 (default) when it fits and NS >= 32
+extern std::atomic<int> g_mimo_tc; // 0 never, 1 whenever the shape fits, 2 (default) when it fits and NS >= 16
 
 typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                            const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -131,8 +131,8 @@ struct fcb_mimo {
     float2 *xcur = nullptr;    // [NS*IN][B] spectra of the current block before the scatter
     float2 *part_tc = nullptr; // [groups][NS*OUT][B]
     float2 *ir_tmp = nullptr;  // [tmp_pairs][rows][B] K5 output before the transposition
-    size_t nblk = 0, rowsP = 0, tmp_pairs = 0;
-    size_t ring_t_elems() const { return B * n_in * nblk * TC_M * TC_KSEG; }
+    size_t nblk = 0, rowsP = 0, tmp_pairs = 0, nsp = 0; // nsp: stream rows per ring tile
+    size_t ring_t_elems() const { return B * n_in * nblk * nsp * TC_KSEG; }
     int tc_groups = 1;
     CUtensorMap tm_ring, tm_ir[2];
     size_t ir_copy_floats() const { return B * n_in * 2 * n_out * 2 * rowsP; }
@@ -202,9 +202,10 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
     const size_t pairs = m->n_out * m->n_in;
     int rc = get_twiddles(m->device, 2 * B, &m->tw);
     const int tc_mode = g_mimo_tc.load();
-    m->tc = tc_mode != 0 && m->n_out == 16 && ns <= (size_t)TC_M && (tc_mode == 1 || ns >= 32) && m->rows() > 0 && B >= 2;
+    m->tc = tc_mode != 0 && m->n_out == 16 && ns <= (size_t)TC_M && (tc_mode == 1 || ns >= 16) && m->rows() > 0 && B >= 2;
     if (m->tc) {
         m->nblk = (m->S + TC_KSEG - 1) / TC_KSEG;
+        m->nsp = (ns + 7) & ~(size_t)7;
         m->rowsP = (TC_LEAD + 1 + m->rows() + 1) & ~(size_t)1; // positions per IR row; pitch a multiple of 16 bytes
         size_t groups = (6 * 148 + B - 1) / B; // ~6 waves of CTAs
         m->tc_groups = (int)(groups < 1 ? 1 : groups > m->n_in ? m->n_in : groups);
@@ -217,10 +218,10 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
         if (!rc) rc = mimo_alloc((void **)&m->xcur, ns * m->n_in * B * sizeof(float2), m->stream);
         if (!rc) rc = mimo_alloc((void **)&m->part_tc, (size_t)m->tc_groups * ns * m->n_out * B * sizeof(float2), m->stream);
         if (!rc) rc = mimo_alloc((void **)&m->ir_tmp, m->tmp_pairs * per_pair, m->stream);
-        const size_t tile = TC_M * TC_KSEG * sizeof(float2);
+        const size_t tile = m->nsp * TC_KSEG * sizeof(float2);
         if (!rc)
-            rc = tc_encode_map(&m->tm_ring, m->ring_t, 2 * TC_KSEG, TC_M, m->nblk, B * m->n_in, TC_KSEG * sizeof(float2), tile,
-                               m->nblk * tile, TC_M);
+            rc = tc_encode_map(&m->tm_ring, m->ring_t, 2 * TC_KSEG, m->nsp, m->nblk, B * m->n_in, TC_KSEG * sizeof(float2), tile,
+                               m->nblk * tile, (uint32_t)m->nsp);
         for (size_t sh = 0; sh < 2 && !rc; sh++)
             rc = tc_encode_map(&m->tm_ir[sh], m->ir_t + sh * m->ir_copy_floats(), 2 * (TC_LEAD + sh + m->rows()), 2 * m->n_out,
                                B * m->n_in, 0, 2 * m->rowsP * sizeof(float), 2 * m->n_out * 2 * m->rowsP * sizeof(float), 0,
@@ -318,12 +319,13 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
                             (long long)(ns * m->n_in)));
         const long long nx = (long long)(ns * m->n_in * B);
         k_tc_scatter_ring<<<(unsigned)((nx + 255) / 256), 256, 0, m->stream>>>(m->xcur, m->ring_t, (int)B, (int)m->n_in, nx,
-                                                                                (long long)m->nblk, (int)m->current);
+                                                                                (long long)m->nblk, (int)m->current, (int)m->nsp);
         TcArgs t{};
         t.part = m->part_tc;
         t.B = (int)B;
         t.n_in = (int)m->n_in;
         t.n_streams = (int)ns;
+        t.rows_pad = (int)m->nsp;
         t.S = (int)m->S;
         t.current = (int)m->current;
         t.seg_lo = (int)m->seg_lo;

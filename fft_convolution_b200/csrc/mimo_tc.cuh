@@ -12,10 +12,13 @@
 // and for the packed bin 0 ({DC, Nyquist}: two real products) Bm[o] = {H.re, 0}, Bm[OUT+o] = {0, H.im}.
 //
 // HBM layout (K-major operands, so a tile is one TMA box and no transposition happens on chip):
-//     ring_t [bin][in][slot block][128 stream rows][16 slots] float2     A: row = stream, K = (slot, re/im)
+//     ring_t [bin][in][slot block][NSP stream rows][16 slots] float2     A: row = stream, K = (slot, re/im)
 //     ir_t   [2][bin][in][2*OUT rows][2*posP]                 float      B: row = n,      K = (segment, plane)
-// ring_t is tile-major: the 16 slots x 128 streams one pipeline stage consumes are ONE contiguous
-// 16 KB run (DRAM-page friendly; a [stream][slot] matrix would be 128 separate 128-byte pieces).
+// ring_t is tile-major: the 16 slots x NSP streams one pipeline stage consumes are ONE contiguous
+// run of NSP * 128 bytes (DRAM-page friendly; a [stream][slot] matrix would be NSP separate 128-byte
+// pieces).  NSP = streams rounded up to 8: the UMMA always works on 128 rows, but rows >= NSP of the
+// shared-memory tile are simply never loaded — their (stale) contents only reach accumulator rows
+// that no stream owns.
 // The new block's spectrum is scattered into slot `current` of ring_t by K1's epilogue kernel;
 // ir_t is built once per set_ir.  Slot s holds segment i = (s - current) mod S, so the K loop walks
 // the slot blocks of two slot ranges and reads IR positions that start wherever `current` puts
@@ -84,11 +87,24 @@ struct TcCfg {
 struct TcArgs {
     float2 *part;        // [groups][NS][OUT][B] partial spectra (packed rows)
     int B, n_in, n_streams;
+    int rows_pad;        // stream rows stored per ring tile (n_streams rounded up to 8); rows above are never loaded
     int S;               // ring slots
     int current;
     int seg_lo, seg_hi;  // segments accumulated; IR position of segment i in copy sh = TC_LEAD + sh + i - seg_lo
     int groups;          // input groups per bin; grid = B * groups
+#ifdef TC_DBG_CLOCK
+    long long *dbg;      // per-section cycle counts of CTA 0 (scripts/tc_k4_test.cu)
+#endif
 };
+#ifdef TC_DBG_CLOCK
+#define TC_CLK(i) { long long now_ = clock64(); clk_[i] += now_ - last_; last_ = now_; }
+#define TC_CLK_INIT long long clk_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long last_ = clock64();
+#define TC_CLK_DUMP(base) if (blockIdx.x == 0 && lane == 0) for (int i_ = 0; i_ < 8; i_++) a.dbg[(base) + i_] = clk_[i_];
+#else
+#define TC_CLK(i)
+#define TC_CLK_INIT
+#define TC_CLK_DUMP(base)
+#endif
 
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint64_t *bar)
 {
@@ -208,9 +224,11 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
 {
     using Cfg = TcCfg<NOUT>;
     constexpr int N2 = Cfg::N2;
-    constexpr int NSPLIT = 32 * TC_SPLIT_WARPS;
-    extern __shared__ unsigned char tc_smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+    static_assert(TC_SPLIT_WARPS % 4 == 0 && Cfg::B_BYTES % (16 * 128) == 0, "splitter groups are 4 warps; B tile in 2 KB units");
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    // swizzled tiles need 1024-byte alignment; index the __shared__ array (not a uintptr_t round trip) so
+    // every access below stays an LDS/STS instead of a generic LD/ST
+    unsigned char *smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     unsigned char *smem_lo = smem + TC_NR * Cfg::RAW_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_lo + TC_NL * Cfg::LO_BYTES);
     uint64_t *full_raw = bars, *empty_raw = full_raw + TC_NR, *full_lo = empty_raw + TC_NR, *empty_lo = full_lo + TC_NL;
@@ -227,10 +245,10 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
     if (tid == 0) {
         for (int s = 0; s < TC_NR; s++) {
             mbar_init(&full_raw[s], 1);
-            mbar_init(&empty_raw[s], NSPLIT);
+            mbar_init(&empty_raw[s], 128);
         }
         for (int s = 0; s < TC_NL; s++) {
-            mbar_init(&full_lo[s], NSPLIT);
+            mbar_init(&full_lo[s], 128);
             mbar_init(&empty_lo[s], 1);
         }
         for (int b = 0; b < 2; b++) {
@@ -259,7 +277,7 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
             int blk, copy, pos0;
             span.chunk(t % cpi, blk, copy, pos0);
             if (elect_one()) {
-                mbar_expect_tx(&full_raw[s], Cfg::RAW_BYTES);
+                mbar_expect_tx(&full_raw[s], a.rows_pad * 128 + Cfg::B_BYTES);
                 tma_load_4d(st, &tm_ring, 0, 0, blk, bin * a.n_in + in, &full_raw[s]);
 #ifndef TC_DBG_NO_IR
                 tma_load_3d(st + Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 2 * pos0, 0, bin * a.n_in + in, &full_raw[s]);
@@ -272,11 +290,14 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
     } else if (warp == 1) {
         // ---- MMA issuer ---------------------------------------------------------------------
         constexpr uint32_t idesc_wide = umma_idesc_tf32(2 * N2), idesc_narrow = umma_idesc_tf32(N2);
+        TC_CLK_INIT
         for (int t = 0; t < total; t++) {
             const int sl = t % TC_NL, iv = t / TC_DRAIN, b = iv & 1;
             const bool first = (t % TC_DRAIN) == 0, last = (t % TC_DRAIN) == TC_DRAIN - 1 || t == total - 1;
             if (first) mbar_wait(&acc_empty[b], ((iv >> 1) & 1) ^ 1);
+            TC_CLK(0)
             mbar_wait(&full_lo[sl], (t / TC_NL) & 1);
+            TC_CLK(1)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const uint32_t lo = smem_u32(smem_lo + sl * Cfg::LO_BYTES);
@@ -297,62 +318,78 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
                 if (last) umma_commit(&acc_full[b]);
             }
             __syncwarp();
+            TC_CLK(2)
         }
+        TC_CLK_DUMP(0)
     } else if (warp < 2 + TC_SPLIT_WARPS) {
-        // ---- splitters: thread = (stream row, half of the 32 K-columns); hi = the 19 bits the
-        // tensor core reads, lo = x - hi; A goes to TMEM, [B_hi | B_lo] to shared memory ---------
-        const int st_tid = tid - 64;
-        const int row = (warp & 3) * 32 + lane;  // TMEM lane quadrant of this warp
-        const int half = (warp - 2) >> 2;         // columns [16*half, 16*half + 16)
+        // ---- splitters: two groups of 4 warps take alternate stages (two stages in flight hide the
+        // wait -> LDS -> convert -> STTM -> arrive chain); thread = one stream row.  hi = the 19 bits the
+        // tensor core reads, lo = x - hi; A goes to TMEM, [B_hi | B_lo] to shared memory -----------
+        const int grp = (warp - 2) >> 2, gtid = (tid - 64) & 127;
+        const int row = (warp & 3) * 32 + lane; // TMEM lane quadrant of this warp
+        const bool live = (warp & 3) * 32 < a.rows_pad; // quadrants above the stored stream rows hold nothing
         auto lo1 = [](float x) {
             float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
             uint32_t u;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(r));
             return u;
         };
-        for (int t = 0; t < total; t++) {
+        TC_CLK_INIT
+        for (int t = grp; t < total; t += TC_SPLIT_WARPS / 4) {
             const int sr = t % TC_NR, sl = t % TC_NL;
             const unsigned char *rawA = smem + sr * Cfg::RAW_BYTES + row * 128;
             const float4 *rawB = reinterpret_cast<const float4 *>(smem + sr * Cfg::RAW_BYTES + Cfg::A_BYTES);
             float4 *hiB = reinterpret_cast<float4 *>(smem_lo + sl * Cfg::LO_BYTES);
             float4 *loB = reinterpret_cast<float4 *>(smem_lo + sl * Cfg::LO_BYTES + Cfg::B_BYTES);
             mbar_wait(&full_raw[sr], (t / TC_NR) & 1);
-            uint32_t hi[16], lo[16];
+            TC_CLK(0)
+            float4 v[8], w[Cfg::B_BYTES / 16 / 128];
+            if (live) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) { // logical 16-byte chunk c of a row sits at chunk c ^ (row & 7)
-                const float4 v = *reinterpret_cast<const float4 *>(rawA + ((((half * 4 + j) ^ (row & 7))) << 4));
-                hi[4 * j + 0] = __float_as_uint(v.x), hi[4 * j + 1] = __float_as_uint(v.y);
-                hi[4 * j + 2] = __float_as_uint(v.z), hi[4 * j + 3] = __float_as_uint(v.w);
-                lo[4 * j + 0] = lo1(v.x), lo[4 * j + 1] = lo1(v.y), lo[4 * j + 2] = lo1(v.z), lo[4 * j + 3] = lo1(v.w);
+                for (int j = 0; j < 8; j++) // logical 16-byte chunk c of a row sits at chunk c ^ (row & 7)
+                    v[j] = *reinterpret_cast<const float4 *>(rawA + ((j ^ (row & 7)) << 4));
             }
-            float4 w[(Cfg::B_BYTES / 16 + NSPLIT - 1) / NSPLIT];
 #pragma unroll
-            for (int j = 0; j < (Cfg::B_BYTES / 16 + NSPLIT - 1) / NSPLIT; j++)
-                if (st_tid + NSPLIT * j < Cfg::B_BYTES / 16) w[j] = rawB[st_tid + NSPLIT * j];
+            for (int j = 0; j < Cfg::B_BYTES / 16 / 128; j++) w[j] = rawB[gtid + 128 * j];
             mbar_arrive(&empty_raw[sr]); // the raw stage is in registers now
+            TC_CLK(1)
             mbar_wait(&empty_lo[sl], ((t / TC_NL) & 1) ^ 1);
+            TC_CLK(2)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::ACC_COLS + sl * Cfg::A_COLS + half * 16;
-#ifndef TC_DBG_NO_STTM
-            tmem_st16(ta, hi);
-            tmem_st16(ta + 2 * TC_KSEG, lo);
-#else
-            if (hi[0] == 0x12345678u && lo[3] == 0x9abcdefu) tmem_st16(ta, hi);
-#endif
+            const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::ACC_COLS + sl * Cfg::A_COLS;
+            if (live) {
 #pragma unroll
-            for (int j = 0; j < (Cfg::B_BYTES / 16 + NSPLIT - 1) / NSPLIT; j++)
-                if (st_tid + NSPLIT * j < Cfg::B_BYTES / 16) {
-                    hiB[st_tid + NSPLIT * j] = w[j];
-                    float4 l;
-                    l.x = __uint_as_float(lo1(w[j].x)), l.y = __uint_as_float(lo1(w[j].y));
-                    l.z = __uint_as_float(lo1(w[j].z)), l.w = __uint_as_float(lo1(w[j].w));
-                    loB[st_tid + NSPLIT * j] = l;
+                for (int h = 0; h < 2; h++) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const float4 x = v[4 * h + j];
+                        hi[4 * j + 0] = __float_as_uint(x.x), hi[4 * j + 1] = __float_as_uint(x.y);
+                        hi[4 * j + 2] = __float_as_uint(x.z), hi[4 * j + 3] = __float_as_uint(x.w);
+                        lo[4 * j + 0] = lo1(x.x), lo[4 * j + 1] = lo1(x.y), lo[4 * j + 2] = lo1(x.z), lo[4 * j + 3] = lo1(x.w);
+                    }
+                    tmem_st16(ta + 16 * h, hi);
+                    tmem_st16(ta + 2 * TC_KSEG + 16 * h, lo);
                 }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < Cfg::B_BYTES / 16 / 128; j++) {
+                hiB[gtid + 128 * j] = w[j];
+                float4 l;
+                l.x = __uint_as_float(lo1(w[j].x)), l.y = __uint_as_float(lo1(w[j].y));
+                l.z = __uint_as_float(lo1(w[j].z)), l.w = __uint_as_float(lo1(w[j].w));
+                loB[gtid + 128 * j] = l;
+            }
+            TC_CLK(3)
+            if (live) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            TC_CLK(4)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            TC_CLK(5)
             mbar_arrive(&full_lo[sl]);
+            TC_CLK(6)
         }
+        if (warp == 2) { TC_CLK_DUMP(8) }
     } else {
         // ---- drain warps: TMEM -> f32 registers every TC_DRAIN stages, then the partial spectra --
         const int q = warp & 3; // TMEM lane quadrant this warp may touch
@@ -399,14 +436,15 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
 // K1 epilogue for the tensor-core layout: xcur [NS*IN][B] (packed spectra of the new block) -> slot
 // `slot` of ring_t[bin][in][slot block][stream][16]
 __global__ void __launch_bounds__(256)
-k_tc_scatter_ring(const float2 *__restrict__ xcur, float2 *__restrict__ ring_t, int B, int n_in, long long total, long long nblk, int slot)
+k_tc_scatter_ring(const float2 *__restrict__ xcur, float2 *__restrict__ ring_t, int B, int n_in, long long total, long long nblk, int slot,
+                  int rows_pad)
 {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= total) return;
     const int bin = (int)(idx % B);
     const long long c = idx / B; // stream * IN + in
     const long long s = c / n_in, in = c % n_in;
-    ring_t[((((long long)bin * n_in + in) * nblk + slot / TC_KSEG) * TC_M + s) * TC_KSEG + slot % TC_KSEG] = xcur[idx];
+    ring_t[((((long long)bin * n_in + in) * nblk + slot / TC_KSEG) * rows_pad + s) * TC_KSEG + slot % TC_KSEG] = xcur[idx];
 }
 
 // K5 epilogue: IR spectra of `npairs` (out, in) pairs starting at pair p0, src [npairs][rows][B] packed,

@@ -55,13 +55,13 @@ int main(int argc, char **argv)
     const int seg_lo = argc > 7 ? atoi(argv[7]) : 0, seg_hi = argc > 8 ? atoi(argv[8]) : S;
     const int OUT = 16, rows = seg_hi - seg_lo;
     const bool perf = getenv("TC_PERF") != nullptr; // device-filled operands, timing only
-    const size_t nblk = (S + TC_KSEG - 1) / TC_KSEG, rowsP = (TC_LEAD + 1 + rows + 1) & ~1;
+    const size_t nblk = (S + TC_KSEG - 1) / TC_KSEG, rowsP = (TC_LEAD + 1 + rows + 1) & ~1, NSP = (NS + 7) & ~7;
     auto ring_at = [&](int b, int in, int s, int sl, int p) {
-        return (((((size_t)b * IN + in) * nblk + sl / TC_KSEG) * TC_M + s) * TC_KSEG + sl % TC_KSEG) * 2 + p;
+        return (((((size_t)b * IN + in) * nblk + sl / TC_KSEG) * NSP + s) * TC_KSEG + sl % TC_KSEG) * 2 + p;
     };
     printf("B=%d IN=%d S=%d NS=%d cur=%d groups=%d segs [%d,%d)\n", B, IN, S, NS, cur, groups, seg_lo, seg_hi);
     const size_t copy = (size_t)B * IN * 2 * OUT * 2 * rowsP;
-    const size_t ring_n = (size_t)B * IN * nblk * TC_M * TC_KSEG * 2;
+    const size_t ring_n = (size_t)B * IN * nblk * NSP * TC_KSEG * 2;
     std::vector<float> ring(perf ? 1 : ring_n, 0.f), ir(perf ? 1 : 2 * copy, 0.f);
     uint64_t seed = 99;
     for (int b = 0; b < (perf ? 0 : B); b++)
@@ -91,8 +91,8 @@ int main(int argc, char **argv)
         CK(cudaMemcpy(d_ir, ir.data(), ir.size() * 4, cudaMemcpyHostToDevice));
     }
     CK(cudaMemset(d_part, 0xFF, (size_t)groups * NS * OUT * B * 8));
-    const uint64_t tile = (uint64_t)TC_M * TC_KSEG * 8;
-    CUtensorMap tmr = make_map(d_ring, 2 * TC_KSEG, TC_M, nblk, (uint64_t)B * IN, TC_KSEG * 8, tile, nblk * tile, TC_M);
+    const uint64_t tile = (uint64_t)NSP * TC_KSEG * 8;
+    CUtensorMap tmr = make_map(d_ring, 2 * TC_KSEG, NSP, nblk, (uint64_t)B * IN, TC_KSEG * 8, tile, nblk * tile, (uint32_t)NSP);
     CUtensorMap tmi = make_map(d_ir, 2 * (TC_LEAD + rows), 2 * OUT, (uint64_t)B * IN, 0, 2 * rowsP * 4, 2 * OUT * 2 * rowsP * 4, 0, 2 * OUT);
     CUtensorMap tmi1 =
         make_map(d_ir + copy, 2 * (TC_LEAD + 1 + rows), 2 * OUT, (uint64_t)B * IN, 0, 2 * rowsP * 4, 2 * OUT * 2 * rowsP * 4, 0, 2 * OUT);
@@ -102,11 +102,16 @@ int main(int argc, char **argv)
     a.B = B;
     a.n_in = IN;
     a.n_streams = NS;
+    a.rows_pad = (int)NSP;
     a.S = S;
     a.current = cur;
     a.seg_lo = seg_lo;
     a.seg_hi = seg_hi;
     a.groups = groups;
+#ifdef TC_DBG_CLOCK
+    CK(cudaMalloc(&a.dbg, 16 * 8));
+    CK(cudaMemset(a.dbg, 0, 16 * 8));
+#endif
     k_mimo_tc<16><<<B * groups, TC_THREADS, TcCfg<16>::SMEM>>>(a, tmr, tmi, tmi1);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
@@ -125,9 +130,17 @@ int main(int argc, char **argv)
         float ms;
         CK(cudaEventElapsedTime(&ms, e0, e1));
         ms /= reps;
-        const double bytes = (double)B * IN * ((double)nblk * TC_M * TC_KSEG * 8 + 2.0 * OUT * rows * 8);
-        printf("PERF %.4f ms per launch, %.0f GB/s of operand bytes, %.2f T cMAC/s (128 rows)\n", ms, bytes / ms / 1e6,
-               (double)B * IN * rows * 128 * OUT / ms / 1e9);
+#ifdef TC_DBG_CLOCK
+        long long h[16];
+        CK(cudaMemcpy(h, a.dbg, sizeof h, cudaMemcpyDeviceToHost));
+        const double nch = (double)(nblk + 1) * (IN / groups);
+        printf("per chunk (CTA 0, ~%.0f chunks): MMA warp: wait acc_empty %.0f, wait full_lo %.0f, issue %.0f | splitter: wait full_raw %.0f, "
+               "LDS+split %.0f, wait empty_lo %.0f, STTM+STS issue %.0f, wait::st %.0f, fences %.0f, arrive %.0f\n",
+               nch, h[0] / nch, h[1] / nch, h[2] / nch, h[8] / nch, h[9] / nch, h[10] / nch, h[11] / nch, h[12] / nch, h[13] / nch, h[14] / nch);
+#endif
+        const double bytes = (double)B * IN * ((double)nblk * NSP * TC_KSEG * 8 + 2.0 * OUT * rows * 8);
+        printf("PERF %.4f ms per launch, %.0f GB/s of operand bytes, %.2f T cMAC/s (%d rows)\n", ms, bytes / ms / 1e6,
+               (double)B * IN * rows * NS * OUT / ms / 1e9, NS);
         return 0;
     }
     std::vector<float2> part((size_t)groups * NS * OUT * B);

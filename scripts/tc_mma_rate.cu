@@ -53,19 +53,23 @@ __global__ void __launch_bounds__(128) k_rate(int N, int mode, int kind, int nre
         const uint64_t ad = desc_k128(smem_u32(smem)), bd = desc_k128(smem_u32(smem + 16384));
         const uint32_t a_t = tmem + 480; // 32 columns at the top
         long long t0 = clock64();
-        for (int r = 0; r < nrep; r++) {
-            const uint32_t d = tmem + (r % nacc) * N; // nacc independent accumulators
-            if (!elect_one()) continue;
-            if (mode == 0) {
-                if (kind)
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
-                else
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
-            } else {
-                if (kind)
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_t), "l"(bd), "r"(idesc), "r"(1u) : "memory");
-                else
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_t), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+        if (elect_one()) {
+            for (int r = 0; r < nrep; r += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t d = tmem + (u % nacc) * N; // nacc independent accumulators
+                    if (mode == 0) {
+                        if (kind)
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+                        else
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+                    } else {
+                        if (kind)
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_t), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+                        else
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_t), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+                    }
+                }
             }
         }
         __syncwarp();
