@@ -135,6 +135,10 @@ SIGNATURES = {
     "fcb_mimo_sync": (_i, [_vp]),
     "fcb_mimo_stream": (_vp, [_vp]),
     "fcb_mimo_uses_tensor_cores": (_i, [_vp]),
+    "fcb_mimo_peer_export": (_i, [_vp, _vp]),
+    "fcb_mimo_peer_attach": (_i, [_vp, _vp]),
+    "fcb_mimo_peer_inbox": (_vp, [_vp]),
+    "fcb_mimo_peer_attach_ptrs": (_i, [_vp, _vp]),
     "fcb_mimo_block_size": (_sz, [_vp]),
     "fcb_mimo_seg_count": (_sz, [_vp]),
     "fcb_mimo_segment_range": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),

@@ -338,6 +338,23 @@ class MimoConvolver:
     def sync(self) -> None:
         check(_lib.load().fcb_mimo_sync(self._h))
 
+    # peer exchange of the partial spectra (IR-partition shards on one NVLink node)
+    def peer_export(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        check(_lib.load().fcb_mimo_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_attach(self, handles) -> None:
+        blob = b"".join(handles)
+        check(_lib.load().fcb_mimo_peer_attach(self._h, C.cast(C.c_char_p(blob), C.c_void_p)))
+
+    def peer_inbox(self) -> int:
+        return _lib.load().fcb_mimo_peer_inbox(self._h)
+
+    def peer_attach_ptrs(self, inboxes) -> None:
+        arr = (C.c_void_p * len(inboxes))(*inboxes)
+        check(_lib.load().fcb_mimo_peer_attach_ptrs(self._h, arr))
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.load().fcb_mimo_destroy(self._h)

@@ -319,7 +319,27 @@ struct IfftArgs {
     int fill, n, block_complete;
     long long nchan;
     fcb_epilogue epi;
+    // peer exchange (IR-partition shards on one NVLink node): conv = sum over g < gather_n of
+    // gather[g * gather_stride + c*B + k], ascending g, once gather_flags[g] == gather_seq for every g
+    // (written by the peers' reduce kernels with release/system scope)
+    const float2 *gather;
+    long long gather_stride;
+    const unsigned int *gather_flags;
+    unsigned int gather_seq;
+    int gather_n;
+    int *gather_err; // set to 1 when a flag never arrived (bounded spin)
 };
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 template <int LOGB>
 __global__ void __launch_bounds__(FftPlan<LOGB>::CTA, FftPlan<LOGB>::MIN_CTAS)
@@ -333,12 +353,32 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
     const long long c = (long long)blockIdx.x * P::TPB + slot;
     const bool live = c < a.nchan;
 
+    if (a.gather_n > 0) { // wait for every shard's partial spectra (peer stores + release flag)
+        if (threadIdx.x < a.gather_n) {
+            long long spins = 0;
+            while (ld_acquire_sys(a.gather_flags + threadIdx.x) != a.gather_seq) {
+                if (++spins > (1ll << 26)) {
+                    *a.gather_err = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
     // 1. conv, packed layout (bin 0 = {DC, Nyquist}: two real products)
 #pragma unroll
     for (int e = 0; e < E; e++) {
         int k = tid + e * T;
         float2 v = make_float2(0.f, 0.f);
-        if (live && !a.ir0) {
+        if (live && a.gather_n > 0) {
+            v = a.gather[c * B + k];
+            for (int g = 1; g < a.gather_n; g++) {
+                const float2 q = a.gather[g * a.gather_stride + c * B + k];
+                v.x = __fadd_rn(v.x, q.x);
+                v.y = __fadd_rn(v.y, q.y);
+            }
+        } else if (live && !a.ir0) {
             v = a.premul[c * B + k]; // conv already complete (MIMO: summed over inputs and shards)
         } else if (live) {
             float2 x = a.ring_cur[c * a.ring_stride + k];

@@ -48,6 +48,40 @@ static int tc_encode_map(CUtensorMap *tm, void *base, uint64_t d0, uint64_t d1, 
     return FCB_OK;
 }
 
+// ---- peer exchange of the partial spectra (replaces the NCCL all-reduce between the MAC and K3) ----
+// Every shard's reduce kernel stores its partial conv spectra straight into EVERY shard's inbox slot
+// [parity][me] over NVLink (plain peer stores), then the last CTA publishes a release/system-scope flag
+// per peer; K3 on each shard acquires the G flags and sums the G slots in rank order — every rank ends
+// with bit-identical spectra, no collective kernel, no host round trip.  Inboxes are double-buffered by
+// block parity: a peer can run at most one block ahead (it needs my flag to finish its block).
+struct PeerPub {
+    float2 *inbox[FCB_MAX_PEERS];       // peer g's inbox base ([2][G][n_conv] float2)
+    unsigned int *flags[FCB_MAX_PEERS]; // peer g's flags ([2][G])
+    unsigned int *done;                 // local CTA counter for the last-CTA pattern
+    long long n_conv;
+    unsigned int seq;                   // block counter, 1-based
+    int G, me;
+};
+
+__device__ __forceinline__ void peer_store(const PeerPub &p, long long idx, float2 v)
+{
+    const long long off = ((long long)(p.seq & 1) * p.G + p.me) * p.n_conv + idx;
+    for (int g = 0; g < p.G; g++) p.inbox[g][off] = v;
+}
+// after every thread of the grid has stored: the last CTA to arrive raises my flag on every peer
+__device__ __forceinline__ void peer_signal(const PeerPub &p, unsigned int ctas)
+{
+    __syncthreads(); // the CTA's stores happen-before thread 0's fences below (fences are cumulative)
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();
+        if (atomicAdd(p.done, 1u) == ctas - 1) {
+            *p.done = 0;
+            __threadfence_system();
+            for (int g = 0; g < p.G; g++) st_release_sys(p.flags[g] + (p.seq & 1) * p.G + p.me, p.seq);
+        }
+    }
+}
+
 // conv[s][o][k] = sum_in sum_z part[z][s][o][in][k]  +  sum_in X[s][in][cur][k] * H[o][in][seg 0][k]
 // (the segment-0 product, src/fft_convolver.rs:270-275, only on the shard that owns segment 0).
 // CTA = 32 bins x 8 input lanes of one (stream, out): lane y sums its inputs y, y+8, ... over all
@@ -56,7 +90,7 @@ static int tc_encode_map(CUtensorMap *tm, void *base, uint64_t d0, uint64_t d1, 
 __global__ void __launch_bounds__(256)
 k_mimo_reduce(const float2 *__restrict__ premul, const float2 *__restrict__ ring_cur, long long ring_stride,
               const float2 *__restrict__ ir0, long long ir_stride, float2 *__restrict__ conv, int B, int n_in,
-              int n_out, long long n_so, int zchunks)
+              int n_out, long long n_so, int zchunks, PeerPub pub)
 {
     __shared__ float2 lane_sum[8][32];
     const int kt = (B + 31) / 32;
@@ -100,8 +134,27 @@ k_mimo_reduce(const float2 *__restrict__ premul, const float2 *__restrict__ ring
             t.x = __fadd_rn(t.x, lane_sum[l][threadIdx.x].x);
             t.y = __fadd_rn(t.y, lane_sum[l][threadIdx.x].y);
         }
-        conv[so * B + k] = t;
+        if (pub.G > 0) peer_store(pub, so * B + k, t);
+        else conv[so * B + k] = t;
     }
+    if (pub.G > 0) peer_signal(pub, gridDim.x);
+}
+
+// tensor-core path: conv[so][k] = sum over input groups of part[g][so][k], ascending g (k_tc_reduce), peer variant
+__global__ void __launch_bounds__(256)
+k_tc_reduce_peer(const float2 *__restrict__ part, long long n, int groups, PeerPub pub)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx < n) {
+        float2 t = part[idx];
+        for (int g = 1; g < groups; g++) {
+            float2 q = part[(long long)g * n + idx];
+            t.x += q.x;
+            t.y += q.y;
+        }
+        peer_store(pub, idx, t);
+    }
+    peer_signal(pub, gridDim.x);
 }
 
 } // namespace fcb
@@ -135,6 +188,31 @@ struct fcb_mimo {
     size_t ring_t_elems() const { return B * n_in * nblk * nsp * TC_KSEG; }
     int tc_groups = 1;
     CUtensorMap tm_ring, tm_ir[2];
+    // peer exchange (see PeerPub)
+    size_t shard_index = 0, shard_count = 1;
+    unsigned char *inbox = nullptr;      // [2][G][n_conv] float2 then [2][G] flags, one allocation (IPC-exported)
+    unsigned int *peer_done = nullptr;   // CTA counter + error word
+    void *peer_base[FCB_MAX_PEERS] = {}; // every shard's inbox in my address space
+    bool peer_opened[FCB_MAX_PEERS] = {};
+    bool peer_on = false;
+    unsigned int peer_seq = 0;
+    size_t n_conv() const { return n_streams * n_out * B; }
+    size_t inbox_data_bytes() const { return 2 * shard_count * n_conv() * sizeof(float2); }
+    PeerPub pub() const
+    {
+        PeerPub p{};
+        if (!peer_on) return p;
+        for (size_t g = 0; g < shard_count; g++) {
+            p.inbox[g] = reinterpret_cast<float2 *>(peer_base[g]);
+            p.flags[g] = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(peer_base[g]) + inbox_data_bytes());
+        }
+        p.done = peer_done;
+        p.n_conv = (long long)n_conv();
+        p.seq = peer_seq;
+        p.G = (int)shard_count;
+        p.me = (int)shard_index;
+        return p;
+    }
     size_t ir_copy_floats() const { return B * n_in * 2 * n_out * 2 * rowsP; }
 
     size_t rows() const { return seg_hi - seg_lo; }
@@ -158,6 +236,10 @@ extern "C" void fcb_mimo_destroy(fcb_mimo *m)
     cudaFree(m->xcur);
     cudaFree(m->part_tc);
     cudaFree(m->ir_tmp);
+    for (size_t g = 0; g < FCB_MAX_PEERS; g++)
+        if (m->peer_opened[g]) cudaIpcCloseMemHandle(m->peer_base[g]);
+    cudaFree(m->inbox);
+    cudaFree(m->peer_done);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -188,6 +270,8 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
     m->logb = ilog2(B);
     m->L = d->max_response_length;
     m->S = (size_t)std::ceil((double)m->L / (double)B);
+    m->shard_index = d->shard_index;
+    m->shard_count = shards;
     m->seg_lo = m->S * d->shard_index / shards;
     m->seg_hi = m->S * (d->shard_index + 1) / shards;
     if (d->stream) m->stream = (cudaStream_t)d->stream;
@@ -312,6 +396,7 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
     if (m->S == 0) return FCB_OK;
     FCB_CUDA(cudaSetDevice(m->device));
     const size_t B = m->B, ns = m->n_streams, pairs = m->n_out * m->n_in;
+    if (m->peer_on) m->peer_seq++;
     if (m->tc) {
         // K1 -> scatter into column `current` of the K-major ring -> K4 (every owned segment,
         // segment 0 included) -> sum over input groups
@@ -336,7 +421,8 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
         k_mimo_tc<16><<<(unsigned)(B * m->tc_groups), TC_THREADS, TcCfg<16>::SMEM, m->stream>>>(t, m->tm_ring, m->tm_ir[0], m->tm_ir[1]);
         if (profiled) cudaEventRecord(prof_stop, m->stream);
         const long long nc = (long long)(ns * m->n_out * B);
-        k_tc_reduce<<<(unsigned)((nc + 255) / 256), 256, 0, m->stream>>>(m->part_tc, m->conv, nc, m->tc_groups);
+        if (m->peer_on) k_tc_reduce_peer<<<(unsigned)((nc + 255) / 256), 256, 0, m->stream>>>(m->part_tc, nc, m->tc_groups, m->pub());
+        else k_tc_reduce<<<(unsigned)((nc + 255) / 256), 256, 0, m->stream>>>(m->part_tc, m->conv, nc, m->tc_groups);
         g_launches += 3;
         FCB_CUDA(cudaGetLastError());
         return FCB_OK;
@@ -392,7 +478,7 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
     const long long n_so = (long long)(ns * m->n_out);
     k_mimo_reduce<<<(unsigned)(n_so * ((B + 31) / 32)), dim3(32, 8), 0, m->stream>>>(
         m->premul, m->ring + m->current * B, ring_stride, owns0 ? m->ir : nullptr, ir_stride, m->conv, (int)B,
-        (int)m->n_in, (int)m->n_out, n_so, zchunks);
+        (int)m->n_in, (int)m->n_out, n_so, zchunks, m->pub());
     g_launches++;
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;
@@ -425,6 +511,15 @@ extern "C" int fcb_mimo_finish_dev(fcb_mimo *m, float *out_dev, size_t out_strid
     a.n = (int)B;
     a.block_complete = 1;
     a.nchan = (long long)n_so;
+    if (m->peer_on) { // sum the G shards' partial spectra out of my inbox once their flags have arrived
+        const size_t G = m->shard_count, par = m->peer_seq & 1;
+        a.gather = reinterpret_cast<const float2 *>(m->inbox) + par * G * m->n_conv();
+        a.gather_stride = (long long)m->n_conv();
+        a.gather_flags = reinterpret_cast<const unsigned int *>(m->inbox + m->inbox_data_bytes()) + par * G;
+        a.gather_seq = m->peer_seq;
+        a.gather_n = (int)G;
+        a.gather_err = reinterpret_cast<int *>(m->peer_done + 1);
+    }
     FCB_TRY(run_inverse(m->logb, m->tw, m->stream, a));
     m->current = m->current > 0 ? m->current - 1 : m->S - 1; // src/fft_convolver.rs:301-305
     return FCB_OK;
@@ -451,6 +546,72 @@ extern "C" int fcb_mimo_sync(fcb_mimo *m)
     if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
     FCB_CUDA(cudaSetDevice(m->device));
     FCB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->peer_on) {
+        int err = 0;
+        FCB_CUDA(cudaMemcpy(&err, m->peer_done + 1, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) return fail(FCB_ERR_CUDA, "peer exchange: a shard's partial spectra never arrived (flag wait timed out)");
+    }
+    return FCB_OK;
+}
+
+// ---- peer exchange set-up -------------------------------------------------------------------
+static int peer_alloc(fcb_mimo *m)
+{
+    if (m->inbox) return FCB_OK;
+    if (m->shard_count > FCB_MAX_PEERS) return fail(FCB_ERR_UNSUPPORTED, "peer exchange supports up to %d shards", FCB_MAX_PEERS);
+    FCB_CUDA(cudaSetDevice(m->device));
+    const size_t bytes = m->inbox_data_bytes() + 256;
+    FCB_CUDA(cudaMalloc((void **)&m->inbox, bytes));
+    FCB_CUDA(cudaMemset(m->inbox, 0, bytes));
+    FCB_CUDA(cudaMalloc((void **)&m->peer_done, 2 * sizeof(unsigned int)));
+    FCB_CUDA(cudaMemset(m->peer_done, 0, 2 * sizeof(unsigned int)));
+    FCB_CUDA(cudaDeviceSynchronize());
+    return FCB_OK;
+}
+
+extern "C" int fcb_mimo_peer_export(fcb_mimo *m, unsigned char *handle_out)
+{
+    if (!m || !handle_out) return fail(FCB_ERR_ARG, "fcb_mimo_peer_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == FCB_PEER_HANDLE_BYTES, "IPC handle size");
+    FCB_TRY(peer_alloc(m));
+    cudaIpcMemHandle_t h;
+    FCB_CUDA(cudaIpcGetMemHandle(&h, m->inbox));
+    memcpy(handle_out, &h, sizeof h);
+    return FCB_OK;
+}
+
+extern "C" int fcb_mimo_peer_attach(fcb_mimo *m, const unsigned char *handles)
+{
+    if (!m || !handles) return fail(FCB_ERR_ARG, "fcb_mimo_peer_attach: NULL argument");
+    if (!m->inbox) return fail(FCB_ERR_ARG, "fcb_mimo_peer_attach: call fcb_mimo_peer_export first");
+    FCB_CUDA(cudaSetDevice(m->device));
+    for (size_t g = 0; g < m->shard_count; g++) {
+        if (g == m->shard_index) {
+            m->peer_base[g] = m->inbox;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + g * FCB_PEER_HANDLE_BYTES, sizeof h);
+        FCB_CUDA(cudaIpcOpenMemHandle(&m->peer_base[g], h, cudaIpcMemLazyEnablePeerAccess));
+        m->peer_opened[g] = true;
+    }
+    m->peer_on = true;
+    return FCB_OK;
+}
+
+extern "C" void *fcb_mimo_peer_inbox(fcb_mimo *m)
+{
+    if (!m || peer_alloc(m) != FCB_OK) return nullptr;
+    return m->inbox;
+}
+
+// same-process variant (tests: several shards of one job on one GPU): inboxes as plain device pointers
+extern "C" int fcb_mimo_peer_attach_ptrs(fcb_mimo *m, void *const *inboxes)
+{
+    if (!m || !inboxes) return fail(FCB_ERR_ARG, "fcb_mimo_peer_attach_ptrs: NULL argument");
+    FCB_TRY(peer_alloc(m));
+    for (size_t g = 0; g < m->shard_count; g++) m->peer_base[g] = g == m->shard_index ? (void *)m->inbox : inboxes[g];
+    m->peer_on = true;
     return FCB_OK;
 }
 

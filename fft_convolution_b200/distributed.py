@@ -3,8 +3,10 @@
 * Independent channels: every rank owns a disjoint channel range and its own FFTConvolver batch —
   no collective on the data path (bench.py does exactly this).
 * Convolution matrix with very long IRs: the IR is sharded by partition (contiguous ranges of IR
-  segments); each rank computes the partial spectra of its range and they are summed with one NCCL
-  all-reduce per block (16 x B complex = 64 KB at B = 512), after which every rank runs K3.
+  segments); each rank computes the partial spectra of its range.  exchange="peer" (default on one
+  node): the reduce kernel's epilogue stores them into every rank's inbox over NVLink and K3 sums the
+  G inboxes after an acquire on G flags — no collective kernel.  exchange="nccl": one NCCL all-reduce
+  per block (16 x B complex = 64 KB at B = 512), after which every rank runs K3.
 """
 from __future__ import annotations
 
@@ -25,7 +27,7 @@ class ShardedMimoConvolver:
     """One IR-partition shard per rank of the default process group (NCCL on GPUs)."""
 
     def __init__(self, responses, block_size: int, max_response_length: int, *, n_streams: int = 1, device: int = 0,
-                 tensor_cores: bool | None = None):
+                 tensor_cores: bool | None = None, exchange: str = "peer"):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
@@ -36,12 +38,19 @@ class ShardedMimoConvolver:
         self._keep = _DeviceBuffer(ptr, n)
         self.conv = torch.as_tensor(self._keep, device=f"cuda:{device}")
         self.B = self.m.block_size
+        self.exchange = exchange if self.world > 1 else "none"
+        if self.exchange == "peer":
+            mine = torch.frombuffer(bytearray(self.m.peer_export()), dtype=torch.uint8).to(f"cuda:{device}")
+            every = torch.empty((self.world, 64), dtype=torch.uint8, device=f"cuda:{device}")
+            dist.all_gather_into_tensor(every, mine)
+            self.m.peer_attach([bytes(row.tolist()) for row in every.cpu()])
+            dist.barrier()
 
     def process_dev(self, x: torch.Tensor, out: torch.Tensor) -> None:
         """x: [NS*IN, B] float32 on this rank's GPU (every rank is given the same block);
         out: [NS*OUT, B].  Every rank ends with the full result."""
         with torch.cuda.stream(self.stream):
             self.m.partial_dev(x.data_ptr(), x.stride(0))
-            if self.world > 1:
+            if self.exchange == "nccl":
                 dist.all_reduce(self.conv, op=dist.ReduceOp.SUM)
             self.m.finish_dev(out.data_ptr(), out.stride(0))

@@ -277,6 +277,19 @@ int fcb_mimo_finish_dev(fcb_mimo *m, float *out_dev, size_t out_stride);
 int fcb_mimo_process(fcb_mimo *m, const float *in, float *out);
 int fcb_mimo_sync(fcb_mimo *m);
 void *fcb_mimo_stream(fcb_mimo *m);
+/* Peer exchange for IR-partition shards on one NVLink node — replaces the all-reduce between partial and finish.
+ * Once attached, fcb_mimo_partial_dev's reduce kernel stores this shard's partial spectra straight into every
+ * shard's inbox (peer stores over NVLink) and raises a release flag; fcb_mimo_finish_dev's K3 acquires the G flags
+ * and sums the G inbox slots in shard order (bit-identical on every shard).  Set-up: every shard exports its inbox
+ * handle (cudaIpcMemHandle_t, FCB_PEER_HANDLE_BYTES bytes), the caller gathers the G handles in shard order and hands
+ * them to every shard.  All shards must step in lock-step (same number of partial/finish calls). */
+#define FCB_PEER_HANDLE_BYTES 64
+#define FCB_MAX_PEERS 16
+int fcb_mimo_peer_export(fcb_mimo *m, unsigned char *handle_out);
+int fcb_mimo_peer_attach(fcb_mimo *m, const unsigned char *handles /* [shard_count][FCB_PEER_HANDLE_BYTES] */);
+/* same-process variant: this shard's inbox as a device pointer / attach with the G inbox pointers */
+void *fcb_mimo_peer_inbox(fcb_mimo *m);
+int fcb_mimo_peer_attach_ptrs(fcb_mimo *m, void *const *inboxes);
 /* 1 when this object's delay-line MAC runs as per-bin complex GEMMs on the tensor cores (K4) */
 int fcb_mimo_uses_tensor_cores(const fcb_mimo *m);
 size_t fcb_mimo_block_size(const fcb_mimo *m);

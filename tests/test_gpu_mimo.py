@@ -98,8 +98,47 @@ def test_ir_partition_shards_sum_to_the_whole(F, shards):
         assert np.max(np.abs(outs[0] - out_w)) <= 2 * TOL * max(rms(ref), 0.05)
 
 
+@pytest.mark.parametrize("shards,tc", [(2, False), (3, False), (4, True)])
+def test_peer_exchange_shards_in_one_process(F, shards, tc):
+    """the NVLink peer exchange (reduce-kernel epilogue stores into every shard's inbox + release flag,
+    K3 acquires G flags and sums G slots) with all shards of a job on one GPU: every publish is issued
+    before any K3, so no kernel ever waits on a later one.  All shards end bit-identical and == oracle."""
+    import torch
+    n_out, n_in, B, L, NS = (16, 2, 64, 64 * 19 + 5, 3) if tc else (3, 2, 64, 64 * 11 + 5, 2)
+    h = _irs(n_out, n_in, L)
+    nblocks = 26
+    x = np.stack([oracle.gen_noise(900 + i, 0, B * nblocks) for i in range(NS * n_in)])
+    parts = [F.MimoConvolver.init(h, B, L, n_streams=NS, shard_index=g, shard_count=shards, tensor_cores=tc)
+             for g in range(shards)]
+    assert all(p.uses_tensor_cores == tc for p in parts)
+    inboxes = [p.peer_inbox() for p in parts]
+    for p in parts:
+        p.peer_attach_ptrs(inboxes)
+    refs = [MimoOracle(h, B, L) for _ in range(NS)]
+    d_in = torch.empty((NS * n_in, B), dtype=torch.float32, device="cuda")
+    d_out = [torch.empty((NS * n_out, B), dtype=torch.float32, device="cuda") for _ in parts]
+    for b in range(nblocks):
+        blk = np.ascontiguousarray(x[:, b * B:(b + 1) * B])
+        d_in.copy_(torch.from_numpy(blk))
+        torch.cuda.synchronize()
+        for p in parts:
+            p.partial_dev(d_in.data_ptr(), B)
+        for p in parts:
+            p.sync()
+        for p, o in zip(parts, d_out):
+            p.finish_dev(o.data_ptr(), B)
+        for p in parts:
+            p.sync()
+        outs = [o.cpu().numpy() for o in d_out]
+        for o in outs[1:]:
+            assert np.array_equal(o, outs[0])
+        for s_ in range(NS):
+            ref = refs[s_].process(blk[s_ * n_in:(s_ + 1) * n_in])
+            assert np.max(np.abs(outs[0][s_ * n_out:(s_ + 1) * n_out] - ref)) <= 2 * TOL * max(rms(ref), 0.05), b
+
+
 def test_nccl_sharded_mimo_two_gpus():
-    """real NCCL all-reduce of the partial spectra over 2 GPUs (skipped on a 1-GPU box)"""
+    """IR-partition shards on 2 GPUs, exchanged by NCCL all-reduce and by the NVLink peer exchange (skipped on a 1-GPU box)"""
     import subprocess
     import sys
     from pathlib import Path
