@@ -278,7 +278,7 @@ class MimoConvolver:
     def init(cls, responses, block_size: int, max_response_length: int, *, n_streams: int = 1,
              shard_index: int = 0, shard_count: int = 1, device: int = 0, stream=None,
              tensor_cores: bool | None = None) -> "MimoConvolver":
-        """tensor_cores: True / False force the tcgen05 matrix MAC (K4; 16 outputs, <= 128 streams) on /
+        """tensor_cores: True / False force the tcgen05 matrix MAC (K4) on /
         off for this object; None keeps the library default (on from 16 streams)."""
         lib = _lib.load()
         _lib.require_gpu()

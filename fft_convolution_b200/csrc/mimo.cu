@@ -185,7 +185,8 @@ struct fcb_mimo {
     float2 *part_tc = nullptr; // [groups][NS*OUT][B]
     float2 *ir_tmp = nullptr;  // [tmp_pairs][rows][B] K5 output before the transposition
     size_t nblk = 0, rowsP = 0, tmp_pairs = 0, nsp = 0; // nsp: stream rows per ring tile
-    size_t ring_t_elems() const { return B * n_in * nblk * nsp * TC_KSEG; }
+    size_t out_groups = 1, stream_groups = 1;           // groups of 16 outputs / 128 streams
+    size_t ring_t_elems() const { return B * n_in * stream_groups * nblk * nsp * TC_KSEG; }
     int tc_groups = 1;
     CUtensorMap tm_ring, tm_ir[2];
     // peer exchange (see PeerPub)
@@ -213,7 +214,7 @@ struct fcb_mimo {
         p.me = (int)shard_index;
         return p;
     }
-    size_t ir_copy_floats() const { return B * n_in * 2 * n_out * 2 * rowsP; }
+    size_t ir_copy_floats() const { return B * n_in * 32 * out_groups * 2 * rowsP; }
 
     size_t rows() const { return seg_hi - seg_lo; }
 };
@@ -286,12 +287,15 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
     const size_t pairs = m->n_out * m->n_in;
     int rc = get_twiddles(m->device, 2 * B, &m->tw);
     const int tc_mode = g_mimo_tc.load();
-    m->tc = tc_mode != 0 && m->n_out == 16 && ns <= (size_t)TC_M && (tc_mode == 1 || ns >= 16) && m->rows() > 0 && B >= 2;
+    m->tc = tc_mode != 0 && (tc_mode == 1 || ns >= 16) && m->rows() > 0 && B >= 2;
     if (m->tc) {
         m->nblk = (m->S + TC_KSEG - 1) / TC_KSEG;
-        m->nsp = (ns + 7) & ~(size_t)7;
+        m->stream_groups = (ns + TC_M - 1) / TC_M;
+        m->out_groups = (m->n_out + 15) / 16;
+        m->nsp = m->stream_groups > 1 ? (size_t)TC_M : (ns + 7) & ~(size_t)7;
         m->rowsP = (TC_LEAD + 1 + m->rows() + 1) & ~(size_t)1; // positions per IR row; pitch a multiple of 16 bytes
-        size_t groups = (6 * 148 + B - 1) / B; // ~6 waves of CTAs
+        const size_t per_bin = m->out_groups * m->stream_groups;
+        size_t groups = (6 * 148 + B * per_bin - 1) / (B * per_bin); // ~6 waves of CTAs
         m->tc_groups = (int)(groups < 1 ? 1 : groups > m->n_in ? m->n_in : groups);
         const size_t per_pair = m->rows() * B * sizeof(float2);
         m->tmp_pairs = ((size_t)256 << 20) / per_pair;
@@ -304,12 +308,11 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
         if (!rc) rc = mimo_alloc((void **)&m->ir_tmp, m->tmp_pairs * per_pair, m->stream);
         const size_t tile = m->nsp * TC_KSEG * sizeof(float2);
         if (!rc)
-            rc = tc_encode_map(&m->tm_ring, m->ring_t, 2 * TC_KSEG, m->nsp, m->nblk, B * m->n_in, TC_KSEG * sizeof(float2), tile,
-                               m->nblk * tile, (uint32_t)m->nsp);
+            rc = tc_encode_map(&m->tm_ring, m->ring_t, 2 * TC_KSEG, m->nsp, m->stream_groups * m->nblk, B * m->n_in,
+                               TC_KSEG * sizeof(float2), tile, m->stream_groups * m->nblk * tile, (uint32_t)m->nsp);
         for (size_t sh = 0; sh < 2 && !rc; sh++)
-            rc = tc_encode_map(&m->tm_ir[sh], m->ir_t + sh * m->ir_copy_floats(), 2 * (TC_LEAD + sh + m->rows()), 2 * m->n_out,
-                               B * m->n_in, 0, 2 * m->rowsP * sizeof(float), 2 * m->n_out * 2 * m->rowsP * sizeof(float), 0,
-                               (uint32_t)(2 * m->n_out));
+            rc = tc_encode_map(&m->tm_ir[sh], m->ir_t + sh * m->ir_copy_floats(), 2 * (TC_LEAD + sh + m->rows()), 32 * m->out_groups,
+                               B * m->n_in, 0, 2 * m->rowsP * sizeof(float), 32 * m->out_groups * 2 * m->rowsP * sizeof(float), 0, 32);
         if (!rc && cudaFuncSetAttribute(k_mimo_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<16>::SMEM) != cudaSuccess)
             rc = fail(FCB_ERR_CUDA, "k_mimo_tc: cannot opt in to %zu bytes of shared memory", TcCfg<16>::SMEM);
     } else {
@@ -404,12 +407,17 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
                             (long long)(ns * m->n_in)));
         const long long nx = (long long)(ns * m->n_in * B);
         k_tc_scatter_ring<<<(unsigned)((nx + 255) / 256), 256, 0, m->stream>>>(m->xcur, m->ring_t, (int)B, (int)m->n_in, nx,
-                                                                                (long long)m->nblk, (int)m->current, (int)m->nsp);
+                                                                                (long long)m->nblk, (int)m->current, (int)m->nsp,
+                                                                                (int)m->stream_groups);
         TcArgs t{};
         t.part = m->part_tc;
         t.B = (int)B;
         t.n_in = (int)m->n_in;
         t.n_streams = (int)ns;
+        t.n_out = (int)m->n_out;
+        t.out_groups = (int)m->out_groups;
+        t.stream_groups = (int)m->stream_groups;
+        t.nblk = (int)m->nblk;
         t.rows_pad = (int)m->nsp;
         t.S = (int)m->S;
         t.current = (int)m->current;
@@ -418,7 +426,7 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
         t.groups = m->tc_groups;
         cudaEvent_t prof_stop = nullptr;
         const bool profiled = mac_profile_begin(m->stream, &prof_stop) != nullptr;
-        k_mimo_tc<16><<<(unsigned)(B * m->tc_groups), TC_THREADS, TcCfg<16>::SMEM, m->stream>>>(t, m->tm_ring, m->tm_ir[0], m->tm_ir[1]);
+        k_mimo_tc<16><<<(unsigned)(B * m->tc_groups * m->out_groups * m->stream_groups), TC_THREADS, TcCfg<16>::SMEM, m->stream>>>(t, m->tm_ring, m->tm_ir[0], m->tm_ir[1]);
         if (profiled) cudaEventRecord(prof_stop, m->stream);
         const long long nc = (long long)(ns * m->n_out * B);
         if (m->peer_on) k_tc_reduce_peer<<<(unsigned)((nc + 255) / 256), 256, 0, m->stream>>>(m->part_tc, nc, m->tc_groups, m->pub());

@@ -12,8 +12,9 @@
 // and for the packed bin 0 ({DC, Nyquist}: two real products) Bm[o] = {H.re, 0}, Bm[OUT+o] = {0, H.im}.
 //
 // HBM layout (K-major operands, so a tile is one TMA box and no transposition happens on chip):
-//     ring_t [bin][in][slot block][NSP stream rows][16 slots] float2     A: row = stream, K = (slot, re/im)
-//     ir_t   [2][bin][in][2*OUT rows][2*posP]                 float      B: row = n,      K = (segment, plane)
+//     ring_t [bin][in][stream group][slot block][NSP rows][16 slots] float2   A: row = stream, K = (slot, re/im)
+//     ir_t   [2][bin][in][32 rows per 16 outputs][2*posP]              float    B: row = n,      K = (segment, plane)
+// (more than 128 streams / 16 outputs run as further CTAs over stream groups of 128 / output groups of 16)
 // ring_t is tile-major: the 16 slots x NSP streams one pipeline stage consumes are ONE contiguous
 // run of NSP * 128 bytes (DRAM-page friendly; a [stream][slot] matrix would be NSP separate 128-byte
 // pieces).  NSP = streams rounded up to 8: the UMMA always works on 128 rows, but rows >= NSP of the
@@ -86,12 +87,15 @@ struct TcCfg {
 
 struct TcArgs {
     float2 *part;        // [groups][NS][OUT][B] partial spectra (packed rows)
-    int B, n_in, n_streams;
-    int rows_pad;        // stream rows stored per ring tile (n_streams rounded up to 8); rows above are never loaded
+    int B, n_in, n_streams, n_out;
+    int rows_pad;        // stream rows stored per ring tile (streams rounded up to 8, 128 with several stream groups)
+    int out_groups;      // ceil(n_out / NOUT): outputs beyond NOUT run as further CTAs re-reading the ring
+    int stream_groups;   // ceil(n_streams / 128)
+    int nblk;            // slot blocks per ring row group
     int S;               // ring slots
     int current;
     int seg_lo, seg_hi;  // segments accumulated; IR position of segment i in copy sh = TC_LEAD + sh + i - seg_lo
-    int groups;          // input groups per bin; grid = B * groups
+    int groups;          // input groups per bin; grid = B * groups * out_groups * stream_groups
 #ifdef TC_DBG_CLOCK
     long long *dbg;      // per-section cycle counts of CTA 0 (scripts/tc_k4_test.cu)
 #endif
@@ -236,7 +240,12 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bin = blockIdx.x / a.groups, g = blockIdx.x % a.groups;
+    int bid = blockIdx.x;
+    const int sg = bid % a.stream_groups;
+    bid /= a.stream_groups;
+    const int og = bid % a.out_groups;
+    bid /= a.out_groups;
+    const int bin = bid / a.groups, g = bid % a.groups;
     const int in_lo = a.n_in * g / a.groups, in_hi = a.n_in * (g + 1) / a.groups;
     const TcSpan span(a);
     const int cpi = span.per_input();
@@ -278,12 +287,8 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
             span.chunk(t % cpi, blk, copy, pos0);
             if (elect_one()) {
                 mbar_expect_tx(&full_raw[s], a.rows_pad * 128 + Cfg::B_BYTES);
-                tma_load_4d(st, &tm_ring, 0, 0, blk, bin * a.n_in + in, &full_raw[s]);
-#ifndef TC_DBG_NO_IR
-                tma_load_3d(st + Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 2 * pos0, 0, bin * a.n_in + in, &full_raw[s]);
-#else
-                tma_load_3d(st + Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 0, 0, 0, &full_raw[s]);
-#endif
+                tma_load_4d(st, &tm_ring, 0, 0, sg * a.nblk + blk, bin * a.n_in + in, &full_raw[s]);
+                tma_load_3d(st + Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 2 * pos0, og * N2, bin * a.n_in + in, &full_raw[s]);
             }
             __syncwarp();
         }
@@ -419,11 +424,12 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[b]);
         }
-        const int s = q * 32 + lane;
+        const int s = sg * TC_M + q * 32 + lane;
         if (s < a.n_streams) {
-            float2 *dst = a.part + (((size_t)g * a.n_streams + s) * NOUT) * a.B + bin;
+            float2 *dst = a.part + (((size_t)g * a.n_streams + s) * a.n_out + og * NOUT) * a.B + bin;
 #pragma unroll
-            for (int o = 0; o < NOUT; o++) dst[(size_t)o * a.B] = make_float2(acc[o], acc[NOUT + o]);
+            for (int o = 0; o < NOUT; o++)
+                if (og * NOUT + o < a.n_out) dst[(size_t)o * a.B] = make_float2(acc[o], acc[NOUT + o]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -434,17 +440,18 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
 }
 
 // K1 epilogue for the tensor-core layout: xcur [NS*IN][B] (packed spectra of the new block) -> slot
-// `slot` of ring_t[bin][in][slot block][stream][16]
+// `slot` of ring_t[bin][in][stream group][slot block][stream row][16]
 __global__ void __launch_bounds__(256)
 k_tc_scatter_ring(const float2 *__restrict__ xcur, float2 *__restrict__ ring_t, int B, int n_in, long long total, long long nblk, int slot,
-                  int rows_pad)
+                  int rows_pad, int stream_groups)
 {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= total) return;
     const int bin = (int)(idx % B);
     const long long c = idx / B; // stream * IN + in
     const long long s = c / n_in, in = c % n_in;
-    ring_t[((((long long)bin * n_in + in) * nblk + slot / TC_KSEG) * rows_pad + s) * TC_KSEG + slot % TC_KSEG] = xcur[idx];
+    const long long tile = (((long long)bin * n_in + in) * stream_groups + s / TC_M) * nblk + slot / TC_KSEG;
+    ring_t[(tile * rows_pad + s % TC_M) * TC_KSEG + slot % TC_KSEG] = xcur[idx];
 }
 
 // K5 epilogue: IR spectra of `npairs` (out, in) pairs starting at pair p0, src [npairs][rows][B] packed,
@@ -470,12 +477,15 @@ k_tc_build_ir(const float2 *__restrict__ src, float *__restrict__ ir_t, int B, i
         re_row = make_float2(h.x, -h.y);
         im_row = make_float2(h.y, h.x);
     }
-    float *base = ir_t + ((long long)bin * n_in + in) * (2 * n_out) * (2 * rowsP);
-    *reinterpret_cast<float2 *>(base + (long long)out * (2 * rowsP) + 2 * (TC_LEAD + row)) = re_row;
-    *reinterpret_cast<float2 *>(base + (long long)(n_out + out) * (2 * rowsP) + 2 * (TC_LEAD + row)) = im_row;
+    // operand rows per (bin, in): out group og = out / 16 owns rows [32 og, 32 og + 32): 16 real-part rows, 16 imaginary
+    const int rows_all = 32 * ((n_out + 15) / 16);
+    const long long r_re = (out / 16) * 32 + out % 16, r_im = r_re + 16;
+    float *base = ir_t + ((long long)bin * n_in + in) * rows_all * (2 * rowsP);
+    *reinterpret_cast<float2 *>(base + r_re * (2 * rowsP) + 2 * (TC_LEAD + row)) = re_row;
+    *reinterpret_cast<float2 *>(base + r_im * (2 * rowsP) + 2 * (TC_LEAD + row)) = im_row;
     base += copy_stride;
-    *reinterpret_cast<float2 *>(base + (long long)out * (2 * rowsP) + 2 * (TC_LEAD + 1 + row)) = re_row;
-    *reinterpret_cast<float2 *>(base + (long long)(n_out + out) * (2 * rowsP) + 2 * (TC_LEAD + 1 + row)) = im_row;
+    *reinterpret_cast<float2 *>(base + r_re * (2 * rowsP) + 2 * (TC_LEAD + 1 + row)) = re_row;
+    *reinterpret_cast<float2 *>(base + r_im * (2 * rowsP) + 2 * (TC_LEAD + 1 + row)) = im_row;
 }
 
 // conv[so][k] = sum over input groups of part[g][so][k], ascending g

@@ -103,6 +103,10 @@ int main(int argc, char **argv)
     a.n_in = IN;
     a.n_streams = NS;
     a.rows_pad = (int)NSP;
+    a.n_out = OUT;
+    a.out_groups = 1;
+    a.stream_groups = 1;
+    a.nblk = (int)nblk;
     a.S = S;
     a.current = cur;
     a.seg_lo = seg_lo;

@@ -50,6 +50,24 @@ def test_tc_matches_oracle(F, n_in, B, L, NS, nblocks):
     assert worst <= TOL
 
 
+@pytest.mark.parametrize("n_out,n_in,B,L,NS,nblocks", [(5, 2, 64, 64 * 20 + 3, 3, 24),      # outputs padded to one group of 16
+                                                       (20, 2, 32, 32 * 18, 2, 21),        # two output groups
+                                                       (16, 1, 32, 32 * 17 + 1, 131, 19)])  # two stream groups of 128
+def test_tc_any_output_and_stream_count(F, n_out, n_in, B, L, NS, nblocks):
+    h = _irs(n_out, n_in, L)
+    rng = np.random.default_rng(NS)
+    x = (rng.random((NS * n_in, B * nblocks), dtype=np.float32) * 2 - 1).astype(np.float32)
+    g = F.MimoConvolver.init(h, B, L, n_streams=NS, tensor_cores=True)
+    assert g.uses_tensor_cores
+    y = _run(g, x, B, nblocks, NS * n_out)
+    worst = 0.0
+    for s in sorted({0, 1, NS // 2, NS - 1}):
+        ref = MimoOracle(h, B, L).process(x[s * n_in:(s + 1) * n_in])
+        err = np.max(np.abs(y[s * n_out:(s + 1) * n_out] - ref), axis=1) / np.array([rms(r) for r in ref])
+        worst = max(worst, float(err.max()))
+    assert worst <= TOL
+
+
 def test_tc_equals_cuda_core_matrix_kernel(F):
     n_out, n_in, B, L, NS, nblocks = 16, 4, 256, 256 * 21 + 3, 7, 30
     h = _irs(n_out, n_in, L)
