@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "engine_internal.cuh"
+#include "offline_kernels.cuh"
 
 namespace fcb {
 thread_local std::string g_last_error = "";
@@ -56,6 +57,11 @@ struct fcb_engine {
     float *stage = nullptr; // IR upload staging
     size_t stage_floats = 0;
     const float2 *tw = nullptr;
+    // multi-block calls (offline_kernels.cuh): workspace for up to mb_cap blocks per pass, allocated on first use
+    size_t mb_cap = 0;
+    float2 *mb_xnew = nullptr, *mb_premul = nullptr; // [C][mb_cap][B]
+    float *mb_y = nullptr;                           // [C][mb_cap][2B]
+    float *mb_in = nullptr, *mb_out = nullptr;       // [C][mb_cap*B] staging for host buffers
     // end-to-end pipeline (fcb_engine_process_block_host): channel groups round-robin over streams
     static constexpr int NPIPE = 4;
     cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr, nullptr};
@@ -199,7 +205,8 @@ static std::atomic<int> g_fused_stages{2};     // fused kernel: 2 stages (64 KB)
 static std::atomic<bool> g_tma_io{true};       // fused kernel moves its input/output blocks with bulk copies
 static std::atomic<bool> g_shared_reuse{true}; // shared-IR engines: stage each IR tile once per CTA
 namespace fcb { std::atomic<bool> g_mimo_tile{true}; } // matrix K2 with in-CTA reuse (0: per-channel K2)
-namespace fcb { std::atomic<int> g_mimo_tc{2}; }       // K4 tensor-core matrix MAC: 0 never, 1 when the shape fits, 2 + NS >= 16
+namespace fcb { std::atomic<int> g_mimo_tc{2}; }
+static std::atomic<bool> g_multi_block{true}; // calls spanning >= 2 whole blocks run as one time-batched pass       // K4 tensor-core matrix MAC: 0 never, 1 when the shape fits, 2 + NS >= 16
 
 template <int B, int NST>
 static int launch_mac_bulk(const MacArgs &a, cudaStream_t st)
@@ -453,6 +460,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "pipe_group") && value >= 1) g_pipe_group = value;
     else if (!strcmp(key, "mimo_tile")) g_mimo_tile = value != 0;
     else if (!strcmp(key, "mimo_tc") && value >= 0 && value <= 2) g_mimo_tc = value;
+    else if (!strcmp(key, "multi_block")) g_multi_block = value != 0;
     else if (!strcmp(key, "fused_block")) g_fused_block = value != 0;
     else if (!strcmp(key, "fused_stages") && (value == 2 || value == 3)) g_fused_stages = value;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
@@ -564,6 +572,11 @@ extern "C" void fcb_engine_destroy(fcb_engine *e)
     cudaFree(e->inbuf);
     cudaFree(e->scratch);
     cudaFree(e->stage);
+    cudaFree(e->mb_xnew);
+    cudaFree(e->mb_premul);
+    cudaFree(e->mb_y);
+    cudaFree(e->mb_in);
+    cudaFree(e->mb_out);
     for (int i = 0; i < fcb_engine::NPIPE; i++) {
         if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]);
         if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]);
@@ -797,6 +810,132 @@ extern "C" int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, 
                                                           (long long)e->C)));
     FCB_TRY(fcb_engine_mac(e, current, active));
     return fcb_engine_ifft_ola(e, current, 0, e->B, 1, out_dev, out_stride, epi);
+}
+
+// ---- multi-block calls: nblocks whole blocks of every channel in one time-batched pass -------------
+template <int LOGB, int T>
+static int launch_mac_time_t(const MacTimeArgs &a, cudaStream_t st)
+{
+    constexpr int B = 1 << LOGB, ROW4 = B / 2, TX = ROW4 < 256 ? ROW4 : 256, TILES = ROW4 / TX, CPB = 256 / TX;
+    const long long ngq = (a.nblocks + T - 1) / T, cgroups = (a.nchan + CPB - 1) / CPB;
+    k_mac_time<B, T><<<(unsigned)(TILES * ngq * cgroups), 256, 0, st>>>(a);
+    g_launches++;
+    FCB_CUDA(cudaGetLastError());
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_multi_block_ok(const fcb_engine *e, size_t current, size_t active)
+{
+    return e && g_multi_block.load() && e->logb >= 2 && active >= 1 && current < active;
+}
+
+static int mb_ensure(fcb_engine *e)
+{
+    if (e->mb_cap) return FCB_OK;
+    const size_t per_block = e->C * e->B * sizeof(float2);
+    size_t cap = ((size_t)256 << 20) / per_block;
+    cap = cap < 4 ? 4 : cap > 1024 ? 1024 : cap;
+    FCB_CUDA(cudaMalloc((void **)&e->mb_xnew, cap * per_block));
+    FCB_CUDA(cudaMalloc((void **)&e->mb_premul, cap * per_block));
+    FCB_CUDA(cudaMalloc((void **)&e->mb_y, cap * per_block));
+    FCB_CUDA(cudaMalloc((void **)&e->mb_in, cap * per_block / 2));
+    FCB_CUDA(cudaMalloc((void **)&e->mb_out, cap * per_block / 2));
+    e->mb_cap = cap;
+    return FCB_OK;
+}
+
+extern "C" size_t fcb_engine_multi_block_capacity(fcb_engine *e)
+{
+    if (!e || mb_ensure(e) != FCB_OK) return 0;
+    return e->mb_cap;
+}
+
+// in / out: device pointers, or host pointers when host_io (staged through the workspace).  Caller rotates
+// `current` nblocks times afterwards (src/fft_convolver.rs:301-305).  Output is bit-identical to nblocks calls of
+// fcb_engine_process_block_dev.
+extern "C" int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
+                                         size_t current, size_t active, size_t nblocks, const fcb_epilogue *epi,
+                                         int host_io)
+{
+    FCB_TRY(check_sched(e, current, active, "process_blocks"));
+    if (!in || !out) return fail(FCB_ERR_ARG, "process_blocks: NULL argument");
+    if (!fcb_engine_multi_block_ok(e, current, active)) return fail(FCB_ERR_UNSUPPORTED, "process_blocks: not applicable here");
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_TRY(mb_ensure(e));
+    if (nblocks == 0) return FCB_OK;
+    if (nblocks > e->mb_cap) return fail(FCB_ERR_ARG, "process_blocks: %zu blocks exceed the workspace (%zu)", nblocks, e->mb_cap);
+    const size_t B = e->B, C = e->C, NB = nblocks;
+    cudaStream_t st = e->stream;
+    const float *din = in;
+    float *dout = out;
+    size_t dstride_in = in_stride, dstride_out = out_stride;
+    if (host_io) {
+        FCB_CUDA(cudaMemcpy2DAsync(e->mb_in, NB * B * sizeof(float), in, in_stride * sizeof(float), NB * B * sizeof(float), C,
+                                   cudaMemcpyHostToDevice, st));
+        din = e->mb_in;
+        dout = e->mb_out;
+        dstride_in = dstride_out = NB * B;
+    }
+    // K1 for every (channel, block) -> xnew[c][d]
+    FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, din, (long long)dstride_in, (int)(NB * B), e->mb_xnew,
+                                                          (long long)(NB * B), (int)NB, (long long)(C * NB))));
+    MacTimeArgs m{};
+    m.ir = e->ir;
+    m.ir_stride = e->ir_stride();
+    m.ring = e->ring;
+    m.ring_stride = e->ring_stride();
+    m.xnew = e->mb_xnew;
+    m.premul = e->mb_premul;
+    m.current = (int)current;
+    m.active = (int)active;
+    m.nblocks = (int)NB;
+    m.nchan = (long long)C;
+    cudaEvent_t prof_stop = nullptr;
+    const bool profiled = prof_before(st, &prof_stop) != nullptr;
+#define FCB_MAC_TIME_CASE(LB)                                                      \
+    case LB:                                                                       \
+        if (NB >= 3) FCB_TRY((launch_mac_time_t<LB, 4>(m, st)));                   \
+        else FCB_TRY((launch_mac_time_t<LB, 2>(m, st)));                           \
+        break;
+    switch (e->logb) {
+        FCB_MAC_TIME_CASE(2) FCB_MAC_TIME_CASE(3) FCB_MAC_TIME_CASE(4) FCB_MAC_TIME_CASE(5) FCB_MAC_TIME_CASE(6)
+        FCB_MAC_TIME_CASE(7) FCB_MAC_TIME_CASE(8) FCB_MAC_TIME_CASE(9) FCB_MAC_TIME_CASE(10) FCB_MAC_TIME_CASE(11)
+        FCB_MAC_TIME_CASE(12) FCB_MAC_TIME_CASE(13) FCB_MAC_TIME_CASE(14)
+    default: return fail(FCB_ERR_UNSUPPORTED, "process_blocks: block size");
+    }
+#undef FCB_MAC_TIME_CASE
+    if (profiled) cudaEventRecord(prof_stop, st);
+    // K3 in raw mode: conv_d = pre_multiplied_d + X_d * H_0, inverse FFT, /N -> y[c][d][2B]
+    IfftArgs a{};
+    a.ring_cur = e->mb_xnew;
+    a.ring_stride = (long long)B;
+    a.ir0 = e->ir;
+    a.ir_stride = e->ir_stride();
+    a.ir_div = (long long)NB;
+    a.premul = e->mb_premul;
+    a.raw_out = e->mb_y;
+    a.nchan = (long long)(C * NB);
+    FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_inverse<LB>(e, a)));
+    // overlap-add across the call's blocks (+ epilogue), then the new overlap and the ring
+    fcb_epilogue ep;
+    memset(&ep, 0, sizeof ep);
+    if (epi) ep = *epi;
+    const long long nout = (long long)(C * NB * B);
+    k_ola_time<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(e->mb_y, e->overlap, dout, (long long)dstride_out, (int)B, (int)NB, nout, ep);
+    FCB_CUDA(cudaMemcpy2DAsync(e->overlap, B * sizeof(float), e->mb_y + (NB - 1) * 2 * B + B, NB * 2 * B * sizeof(float),
+                               B * sizeof(float), C, cudaMemcpyDeviceToDevice, st));
+    const size_t first = NB > active ? NB - active : 0;
+    const long long nring = (long long)(C * (NB - first) * (B / 2));
+    k_ring_update<<<(unsigned)((nring + 255) / 256), 256, 0, st>>>(e->mb_xnew, e->ring, e->ring_stride(), (int)B, (int)NB, (int)current,
+                                                                   (int)active, (int)first, nring);
+    g_launches += 2;
+    FCB_CUDA(cudaGetLastError());
+    if (host_io) {
+        FCB_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float), e->mb_out, NB * B * sizeof(float), NB * B * sizeof(float), C,
+                                   cudaMemcpyDeviceToHost, st));
+        FCB_CUDA(cudaStreamSynchronize(st));
+    }
+    return FCB_OK;
 }
 
 // Full block, host buffers, pipelined: the channels are cut into groups; each group's pinned H2D

@@ -328,6 +328,10 @@ struct IfftArgs {
     unsigned int gather_seq;
     int gather_n;
     int *gather_err; // set to 1 when a flag never arrived (bounded spin)
+    // multi-block calls (offline_kernels.cuh): `nchan` counts (channel, block) pairs, the IR channel is
+    // c / ir_div, and all 2B normalised samples go to raw_out[c][2B] — no overlap-add here
+    long long ir_div;
+    float *raw_out;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
@@ -382,7 +386,7 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
             v = a.premul[c * B + k]; // conv already complete (MIMO: summed over inputs and shards)
         } else if (live) {
             float2 x = a.ring_cur[c * a.ring_stride + k];
-            float2 h = __ldg(&a.ir0[c * a.ir_stride + k]);
+            float2 h = __ldg(&a.ir0[(a.ir_div ? c / a.ir_div : c) * a.ir_stride + k]);
             float2 p = a.premul[c * B + k];
             float pr, pi;
             if (k == 0) {
@@ -407,6 +411,17 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
 
     // 4. epilogue.  y[2j] = Re z[j] / N, y[2j+1] = Im z[j] / N (N = 2B: exact scaling).
     const float inv_n = 1.0f / (float)(2 * B);
+    if (a.raw_out) {
+        if (live) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                int j = tid + e * T;
+                float2 z = s[sidx(j)];
+                *reinterpret_cast<float2 *>(a.raw_out + c * 2 * B + 2 * j) = make_float2(z.x * inv_n, z.y * inv_n);
+            }
+        }
+        return;
+    }
     const int lo = a.fill, hi = a.fill + a.n;
     // 4a. first half -> output (+ overlap, + epilogue)
 #pragma unroll

@@ -286,6 +286,20 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
         const size_t pos = c->input_buffer_fill;
         const bool complete = pos + n == B;
         fcb_epilogue e = offset_epilogue(epi, processed);
+        if (was_empty && out_len - processed >= 2 * B && fcb_engine_multi_block_ok(c->eng, c->current, c->active_seg_count)) {
+            // the call spans several whole blocks: one time-batched pass over as many as the workspace holds
+            size_t nb = (out_len - processed) / B;
+            const size_t cap = fcb_engine_multi_block_capacity(c->eng);
+            if (cap >= 2) {
+                if (nb > cap) nb = cap;
+                FCB_TRY(fcb_engine_process_blocks(c->eng, in + processed, in_stride, out + processed, out_stride, c->current,
+                                                  c->active_seg_count, nb, &e, host ? 1 : 0));
+                for (size_t d = 0; d < nb; d++)
+                    c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1; // :301-305
+                processed += nb * B;
+                continue;
+            }
+        }
         float *dst = host ? c->d_io : out + processed;
         const size_t dst_stride = host ? B : out_stride;
         // (only where the whole-block kernel moves its I/O with bulk copies: 32 <= B <= 512, 16-byte

@@ -158,6 +158,17 @@ int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, size_t in_s
                                  size_t out_stride, size_t current, size_t active,
                                  const fcb_epilogue *epi);
 
+/* Multi-block calls (offline rendering, large host buffers): nblocks whole blocks of every channel in ONE
+ * time-batched pass — K1 for all blocks, a MAC kernel whose threads keep a sliding window of T input spectra in
+ * registers (one IR row + one spectrum row loaded per segment feed T output blocks: T blocks for the HBM traffic of
+ * one), independent inverse FFTs and a parallel overlap-add.  Same arithmetic and summation order per block as
+ * nblocks calls of fcb_engine_process_block_dev: bit-identical output.  in/out are device pointers, or host pointers
+ * when host_io != 0; the caller rotates `current` nblocks times afterwards.  The workspace (capacity in blocks) is
+ * allocated on first use.  fcb_tune("multi_block", 0) makes the host mirror process block by block. */
+int fcb_engine_multi_block_ok(const fcb_engine *e, size_t current, size_t active);
+size_t fcb_engine_multi_block_capacity(fcb_engine *e);
+int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
+                              size_t current, size_t active, size_t nblocks, const fcb_epilogue *epi, int host_io);
 /* the same with HOST buffers (pinned for full overlap), pipelined over channel groups of
  * `group_channels` (0 = 512) on internal streams so the PCIe copies overlap K2; synchronous */
 int fcb_engine_process_block_host(fcb_engine *e, const float *in, size_t in_stride, float *out,
