@@ -15,6 +15,12 @@
 // k_ring_update only after the MACs.  The NB inverse FFTs are independent (K3 in raw mode writes all 2B
 // samples); k_ola_time then forms out_d = y_d[0..B) + y_{d-1}[B..2B) (overlap-add, :284-288, :297-298)
 // with the epilogue, in parallel over d.
+//
+// Measured (B200, 4096 channels x 2 s IR x block 512, device buffers, profiles/r01_offline_multi_block.jsonl):
+// 1 / 2 / 4 / 8 / 16 blocks per call = 49.4 / 82.7 / 143 / 165 / 173 k channel-seconds per second; a window of
+// T = 4 (79 registers) with the second group of 4 re-reading IR rows from L2 beats T = 8 (165 registers: 144 k).
+// The reference example's shape (mono, 64-sample blocks, 128 000 taps, 1000 blocks): 0.58 ms in one call vs
+// 278 ms block by block, identical bits.
 #pragma once
 
 #include "fft_kernels.cuh"
