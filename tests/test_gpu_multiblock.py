@@ -93,3 +93,28 @@ def test_multi_block_shared_ir_and_state_carry_over(F):
         outs.append(y)
     _tune(b"multi_block", 1)
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("B,buf,fade", [(64, 256, 300), (32, 32 * 5, 40)])
+def test_crossfade_with_a_buffer_of_several_blocks(F, B, buf, fade):
+    """CrossfadeConvolver::new(conv, L, max_buffer_size = several blocks, fade): both inner convolvers take the
+    multi-block path, the second with the crossfade-mix epilogue over the whole call; vs the oracle incl. updates"""
+    L = B * 7 + 3
+    h = oracle.gen_ir(1, 0, L)
+    g = F.CrossfadeConvolver.new(F.FFTConvolver.init(h, B, L), L, buf, fade)
+    o = oracle.CrossfadeConvolver.new(oracle.FFTConvolver.init(h, B, L), L, buf, fade)
+    scale = 0.05
+    for step in range(24):
+        if step in (3, 4, 11, 17):
+            hn = oracle.gen_ir(1, step, L if step != 11 else L // 2)
+            g.update(hn)
+            o.update(hn)
+        x = oracle.gen_noise(5, step * buf, buf)
+        yg, yo = np.zeros(buf, np.float32), np.zeros(buf, np.float32)
+        g.process(x, yg)
+        o.process(x, yo)
+        scale = max(scale, rms(yo))
+        assert np.max(np.abs(yg - yo)) <= 1e-5 * scale, step
+        cnt, mix, appr, tgt = g.state()
+        s = o.crossfader
+        assert (cnt, appr, tgt, np.float32(mix)) == (s.counter, bool(s.approaching), s.target, np.float32(s.mix_value))
