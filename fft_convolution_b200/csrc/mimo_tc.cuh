@@ -57,11 +57,8 @@ constexpr int TC_M = 128;    // stream rows of one UMMA (streams are padded to t
 constexpr int TC_KSEG = 16;  // segments per stage: 16 (re,im) pairs = 32 tf32 = one 128-byte swizzle row
 constexpr int TC_LEAD = 16;  // zero positions in front of every IR row
 constexpr int TC_NR = 8;     // raw (TMA) stages
-#ifndef TC_NSETS
-#define TC_NSETS 1
-#endif
-constexpr int TC_SETS = TC_NSETS; // independent accumulator sets (K steps alternate between them: dependent MMAs expose the pipe latency)
-constexpr int TC_NL = TC_SETS == 1 ? 4 : 2; // split-operand stages (A hi/lo in TMEM, [B_hi | B_lo] in shared memory)
+constexpr int TC_SETS = 1;   // accumulator sets the K steps alternate between (2 measured no faster: MMAs are issue-paced, not dependency-paced)
+constexpr int TC_NL = 4;     // split-operand stages (A hi/lo in TMEM, [B_hi | B_lo] in shared memory)
 constexpr int TC_DRAIN = 4;  // stages per TMEM accumulation interval (K = 128 per drain)
 constexpr int TC_SPLIT_WARPS = 8;
 constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + 4);
@@ -96,19 +93,7 @@ struct TcArgs {
     int current;
     int seg_lo, seg_hi;  // segments accumulated; IR position of segment i in copy sh = TC_LEAD + sh + i - seg_lo
     int groups;          // input groups per bin; grid = B * groups * out_groups * stream_groups
-#ifdef TC_DBG_CLOCK
-    long long *dbg;      // per-section cycle counts of CTA 0 (scripts/tc_k4_test.cu)
-#endif
 };
-#ifdef TC_DBG_CLOCK
-#define TC_CLK(i) { long long now_ = clock64(); clk_[i] += now_ - last_; last_ = now_; }
-#define TC_CLK_INIT long long clk_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long last_ = clock64();
-#define TC_CLK_DUMP(base) if (blockIdx.x == 0 && lane == 0) for (int i_ = 0; i_ < 8; i_++) a.dbg[(base) + i_] = clk_[i_];
-#else
-#define TC_CLK(i)
-#define TC_CLK_INIT
-#define TC_CLK_DUMP(base)
-#endif
 
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint64_t *bar)
 {
@@ -148,14 +133,6 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr)
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int n)
 {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 // A from TMEM (lanes = rows, one 32-bit column per K element), B from shared memory
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
@@ -295,14 +272,11 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
     } else if (warp == 1) {
         // ---- MMA issuer ---------------------------------------------------------------------
         constexpr uint32_t idesc_wide = umma_idesc_tf32(2 * N2), idesc_narrow = umma_idesc_tf32(N2);
-        TC_CLK_INIT
         for (int t = 0; t < total; t++) {
             const int sl = t % TC_NL, iv = t / TC_DRAIN, b = iv & 1;
             const bool first = (t % TC_DRAIN) == 0, last = (t % TC_DRAIN) == TC_DRAIN - 1 || t == total - 1;
             if (first) mbar_wait(&acc_empty[b], ((iv >> 1) & 1) ^ 1);
-            TC_CLK(0)
             mbar_wait(&full_lo[sl], (t / TC_NL) & 1);
-            TC_CLK(1)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const uint32_t lo = smem_u32(smem_lo + sl * Cfg::LO_BYTES);
@@ -314,18 +288,14 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
                     // [main | cross1] (+)= A_hi * [B_hi | B_lo]^T ;  cross2 (+)= A_lo * B_hi^T, in set ks % TC_SETS
                     const uint32_t d_set = d_buf + (ks % TC_SETS) * Cfg::SET_COLS;
                     const uint32_t acc_on = (first && ks < TC_SETS) ? 0u : 1u;
-#ifndef TC_DBG_NO_MMA
                     umma_tf32_ts(d_set, a_hi + ks * 8, b_hl, idesc_wide, acc_on);
                     umma_tf32_ts(d_set + 2 * N2, a_lo + ks * 8, b_hl, idesc_narrow, acc_on);
-#endif
                 }
                 umma_commit(&empty_lo[sl]);
                 if (last) umma_commit(&acc_full[b]);
             }
             __syncwarp();
-            TC_CLK(2)
         }
-        TC_CLK_DUMP(0)
     } else if (warp < 2 + TC_SPLIT_WARPS) {
         // ---- splitters: two groups of 4 warps take alternate stages (two stages in flight hide the
         // wait -> LDS -> convert -> STTM -> arrive chain); thread = one stream row.  hi = the 19 bits the
@@ -339,7 +309,6 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(r));
             return u;
         };
-        TC_CLK_INIT
         for (int t = grp; t < total; t += TC_SPLIT_WARPS / 4) {
             const int sr = t % TC_NR, sl = t % TC_NL;
             const unsigned char *rawA = smem + sr * Cfg::RAW_BYTES + row * 128;
@@ -347,7 +316,6 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
             float4 *hiB = reinterpret_cast<float4 *>(smem_lo + sl * Cfg::LO_BYTES);
             float4 *loB = reinterpret_cast<float4 *>(smem_lo + sl * Cfg::LO_BYTES + Cfg::B_BYTES);
             mbar_wait(&full_raw[sr], (t / TC_NR) & 1);
-            TC_CLK(0)
             float4 v[8], w[Cfg::B_BYTES / 16 / 128];
             if (live) {
 #pragma unroll
@@ -357,9 +325,7 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
 #pragma unroll
             for (int j = 0; j < Cfg::B_BYTES / 16 / 128; j++) w[j] = rawB[gtid + 128 * j];
             mbar_arrive(&empty_raw[sr]); // the raw stage is in registers now
-            TC_CLK(1)
             mbar_wait(&empty_lo[sl], ((t / TC_NL) & 1) ^ 1);
-            TC_CLK(2)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::ACC_COLS + sl * Cfg::A_COLS;
             if (live) {
@@ -385,16 +351,11 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
                 l.z = __uint_as_float(lo1(w[j].z)), l.w = __uint_as_float(lo1(w[j].w));
                 loB[gtid + 128 * j] = l;
             }
-            TC_CLK(3)
             if (live) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            TC_CLK(4)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            TC_CLK(5)
             mbar_arrive(&full_lo[sl]);
-            TC_CLK(6)
         }
-        if (warp == 2) { TC_CLK_DUMP(8) }
     } else {
         // ---- drain warps: TMEM -> f32 registers every TC_DRAIN stages, then the partial spectra --
         const int q = warp & 3; // TMEM lane quadrant this warp may touch

@@ -112,10 +112,6 @@ int main(int argc, char **argv)
     a.seg_lo = seg_lo;
     a.seg_hi = seg_hi;
     a.groups = groups;
-#ifdef TC_DBG_CLOCK
-    CK(cudaMalloc(&a.dbg, 16 * 8));
-    CK(cudaMemset(a.dbg, 0, 16 * 8));
-#endif
     k_mimo_tc<16><<<B * groups, TC_THREADS, TcCfg<16>::SMEM>>>(a, tmr, tmi, tmi1);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
@@ -134,14 +130,6 @@ int main(int argc, char **argv)
         float ms;
         CK(cudaEventElapsedTime(&ms, e0, e1));
         ms /= reps;
-#ifdef TC_DBG_CLOCK
-        long long h[16];
-        CK(cudaMemcpy(h, a.dbg, sizeof h, cudaMemcpyDeviceToHost));
-        const double nch = (double)(nblk + 1) * (IN / groups);
-        printf("per chunk (CTA 0, ~%.0f chunks): MMA warp: wait acc_empty %.0f, wait full_lo %.0f, issue %.0f | splitter: wait full_raw %.0f, "
-               "LDS+split %.0f, wait empty_lo %.0f, STTM+STS issue %.0f, wait::st %.0f, fences %.0f, arrive %.0f\n",
-               nch, h[0] / nch, h[1] / nch, h[2] / nch, h[8] / nch, h[9] / nch, h[10] / nch, h[11] / nch, h[12] / nch, h[13] / nch, h[14] / nch);
-#endif
         const double bytes = (double)B * IN * ((double)nblk * NSP * TC_KSEG * 8 + 2.0 * OUT * rows * 8);
         printf("PERF %.4f ms per launch, %.0f GB/s of operand bytes, %.2f T cMAC/s (%d rows)\n", ms, bytes / ms / 1e6,
                (double)B * IN * rows * NS * OUT / ms / 1e9, NS);
