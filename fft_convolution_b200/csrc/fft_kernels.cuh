@@ -250,6 +250,45 @@ __device__ __forceinline__ float apply_epilogue(float v, const fcb_epilogue &epi
     return v;
 }
 
+
+// global -> shared: z[j] = x'[2j] + i x'[2j+1], x' = [x[0..valid) | zeros], for the T threads of one transform.
+// 16-byte loads (two complex points per thread and load) whenever the row is 16-byte aligned and the four
+// samples are real data; 4-byte loads at the ragged end of a partially filled block and for unaligned rows.
+template <int LOGB>
+__device__ __forceinline__ void load_block_as_complex(float2 *s, int tid, const float *__restrict__ x, int valid)
+{
+    using P = FftPlan<LOGB>;
+    constexpr int B = P::B, T = P::T, E = P::E;
+    if constexpr (E >= 2) {
+        if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+#pragma unroll
+            for (int e = 0; e < E / 2; e++) {
+                const int j2 = tid + e * T; // complex points 2*j2, 2*j2 + 1 = samples 4*j2 .. 4*j2 + 3
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (4 * j2 + 3 < valid) {
+                    v = __ldg(reinterpret_cast<const float4 *>(x) + j2);
+                } else {
+                    if (4 * j2 < valid) v.x = __ldg(x + 4 * j2);
+                    if (4 * j2 + 1 < valid) v.y = __ldg(x + 4 * j2 + 1);
+                    if (4 * j2 + 2 < valid) v.z = __ldg(x + 4 * j2 + 2);
+                }
+                s[sidx(2 * j2)] = make_float2(v.x, v.y);
+                s[sidx(2 * j2 + 1)] = make_float2(v.z, v.w);
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        int j = tid + e * T;
+        if (j >= B) continue;
+        float2 z = make_float2(0.f, 0.f);
+        if (2 * j < valid) z.x = __ldg(x + 2 * j);
+        if (2 * j + 1 < valid) z.y = __ldg(x + 2 * j + 1);
+        s[sidx(j)] = z;
+    }
+}
+
 // ========================================================================================
 // K1 / K5: batched forward real FFT.
 // transform q -> (channel c = q / nseg, segment i = q % nseg); source = src + c*src_stride + i*B,
@@ -278,14 +317,7 @@ k_rfft_forward(const float *__restrict__ src, long long src_stride, int len, flo
     if (!live) valid = 0;
 
     // z[j] = x'[2j] + i x'[2j+1], x' = [x[0..valid) | zeros]
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        int j = tid + e * T;
-        float2 z = make_float2(0.f, 0.f);
-        if (2 * j < valid) z.x = __ldg(x + 2 * j);
-        if (2 * j + 1 < valid) z.y = __ldg(x + 2 * j + 1);
-        s[sidx(j)] = z;
-    }
+    load_block_as_complex<LOGB>(s, tid, x, valid);
     __syncthreads();
     stockham_all<LOGB, -1, 0, 1>(s, tid, tw);
 
@@ -423,6 +455,36 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
         return;
     }
     const int lo = a.fill, hi = a.fill + a.n;
+    // whole block, plain overlap-add, 16-byte aligned rows: two complex points = four samples per access
+    const bool vec = E >= 2 && B >= 4 && a.fill == 0 && a.n == B && a.block_complete && !a.epi.add0 && !a.epi.add1 && !a.epi.mix_other &&
+                     (a.out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+    if (vec) {
+        float4 nov[E >= 2 ? E / 2 : 1];
+        if (live) {
+#pragma unroll
+            for (int e = 0; e < E / 2; e++) {
+                const int j2 = tid + e * T; // samples 4*j2 .. 4*j2 + 3 of the 2B-sample result
+                const float2 z0 = s[sidx(2 * j2)], z1 = s[sidx(2 * j2 + 1)];
+                const float4 y = make_float4(z0.x * inv_n, z0.y * inv_n, z1.x * inv_n, z1.y * inv_n);
+                if (4 * j2 < B) {
+                    const float4 ov = *reinterpret_cast<const float4 *>(a.overlap + c * B + 4 * j2);
+                    *reinterpret_cast<float4 *>(a.out + c * a.out_stride + 4 * j2) =
+                        make_float4(__fadd_rn(y.x, ov.x), __fadd_rn(y.y, ov.y), __fadd_rn(y.z, ov.z), __fadd_rn(y.w, ov.w));
+                } else {
+                    nov[e] = y;
+                }
+            }
+        }
+        __syncthreads(); // every reader of the old overlap is done
+        if (live) {
+#pragma unroll
+            for (int e = 0; e < E / 2; e++) {
+                const int j2 = tid + e * T;
+                if (4 * j2 >= B) *reinterpret_cast<float4 *>(a.overlap + c * B + (4 * j2 - B)) = nov[e];
+            }
+        }
+        return;
+    }
     // 4a. first half -> output (+ overlap, + epilogue)
 #pragma unroll
     for (int e = 0; e < E; e++) {

@@ -124,17 +124,16 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
     if (TMA_IO) mbar_wait(in_bar, 0);
     if (fwork) {
         const float *x = TMA_IO ? in_s + fslot * B : fa.in + (c0 + fslot) * fa.in_stride;
+        if (TMA_IO) {
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-            int j = flane + e * T;
-            float2 z = make_float2(0.f, 0.f);
-            if (TMA_IO) {
+            for (int e = 0; e < E; e++) {
+                int j = flane + e * T;
+                float2 z = make_float2(0.f, 0.f);
                 if (flive && 2 * j + 1 < B) z = *reinterpret_cast<const float2 *>(x + 2 * j);
-            } else {
-                if (flive && 2 * j < B) z.x = __ldg(x + 2 * j);
-                if (flive && 2 * j + 1 < B) z.y = __ldg(x + 2 * j + 1);
+                fs[sidx(j)] = z;
             }
-            fs[sidx(j)] = z;
+        } else {
+            load_block_as_complex<LOGB>(fs, flane, x, flive ? B : 0); // 16-byte loads when the row is aligned
         }
     }
     __syncthreads();
