@@ -201,6 +201,7 @@ static std::atomic<int> g_mac_impl{0};         // K2: 0 = auto (TMA pipeline for
 static std::atomic<int> g_mac_stages{3};       // K2 pipeline stages: 2, 3, 4 or 6
 static std::atomic<int> g_pipe_group{512};     // channels per group of the copy pipeline (pageable host buffers)
 static std::atomic<bool> g_fused_block{true};  // whole blocks with B in 32..512: one fused K1+K2+K3 kernel
+static std::atomic<int> g_fused_short{40};     // delay lines up to this many segments use 2-row stages (0 = off)
 static std::atomic<int> g_fused_stages{2};     // fused kernel: 2 stages (64 KB) -> 3 CTAs/SM; 3 -> 2 CTAs/SM
 static std::atomic<bool> g_tma_io{true};       // fused kernel moves its input/output blocks with bulk copies
 static std::atomic<bool> g_shared_reuse{true}; // shared-IR engines: stage each IR tile once per CTA
@@ -347,8 +348,13 @@ static int run_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, size
                            const fcb_epilogue *epi)
 {
     const bool two = g_fused_stages.load() == 2; // 2 stages -> 3 CTAs/SM, 3 stages -> 2 CTAs/SM
+    // short delay lines (two-stage head / tail0: 16 segments): the FFT latency is no longer hidden by the
+    // stream, so run 2-row stages (32 KB of stages per CTA) and let a fourth CTA per SM cover it
+    const bool short_line = active <= (size_t)g_fused_short.load();
 #define FCB_FUSED_CASE(LB)                                                                                       \
     case LB:                                                                                                     \
+        if (short_line)                                                                                          \
+            return launch_block_fused<LB, 2, 2>(e, st, c0, nc, in_dev, in_stride, out_dev, out_stride, current, active, epi); \
         return two ? launch_block_fused<LB, 2>(e, st, c0, nc, in_dev, in_stride, out_dev, out_stride, current, active, epi) \
                    : launch_block_fused<LB, 3>(e, st, c0, nc, in_dev, in_stride, out_dev, out_stride, current, active, epi);
     switch (e->logb) {
@@ -463,6 +469,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "multi_block")) g_multi_block = value != 0;
     else if (!strcmp(key, "fused_block")) g_fused_block = value != 0;
     else if (!strcmp(key, "fused_stages") && (value == 2 || value == 3)) g_fused_stages = value;
+    else if (!strcmp(key, "fused_short") && value >= 0) g_fused_short = value;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
     else if (!strcmp(key, "tma_io")) g_tma_io = value != 0;
     else if (!strcmp(key, "mapped_io")) fcb_host_mirror_set_mapped_io(value);

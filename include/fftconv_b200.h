@@ -57,7 +57,8 @@ int fcb_device_count(void);
  * end-to-end copy/compute pipeline, default 512), "mimo_tile" (1 = matrix K2 with in-CTA reuse of
  * IR and ring tiles, 0 = the per-channel K2), "mimo_tc" (the tensor-core matrix MAC K4: 0 = never, 1 = always,
  * 2 = when at least 16 streams share the matrix; read by fcb_mimo_create), "fused_block" (1 = whole blocks with B in 32..512 run as
- * one fused K1+K2+K3 kernel, 0 = three launches; outputs are bit-identical), "fused_stages" (2 or 3), "mapped_io" (1 = small-batch host
+ * one fused K1+K2+K3 kernel, 0 = three launches; outputs are bit-identical), "fused_stages" (2 or 3), "fused_short" (delay lines of up to this many segments run
+ * the fused kernel with 2-row stages so that a fourth CTA per SM hides the FFT latency; default 40, 0 = off), "mapped_io" (1 = small-batch host
  * calls go through mapped pinned memory instead of the copy engines), "zero_copy" (1 = when the caller's
  * buffers are pinned, large-batch whole-block calls let the kernel read/write them over PCIe directly) */
 int fcb_tune(const char *key, int value);
