@@ -21,6 +21,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra nvcc flags for A/B builds, e.g. FCB_NVCC_EXTRA="-DFCB_FFT_E16_FROM=12"
+NVCC_FLAGS += [f for f in os.environ.get("FCB_NVCC_EXTRA", "").split() if f]
+
+
 def nvcc_path() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and Path(cand).exists():

@@ -40,10 +40,13 @@ __device__ __forceinline__ float2 mul_dir_i(float2 a)
 __device__ __host__ __forceinline__ constexpr int sidx(int i) { return i + (i >> 4); }
 
 // ---- compile-time plan ----------------------------------------------------------------
+#ifndef FCB_FFT_E16_FROM
+#define FCB_FFT_E16_FROM 14 // block sizes from 2^this on: 16 points per thread (two radix-8 butterflies in flight)
+#endif
 template <int LOGB>
 struct FftPlan {
     static constexpr int B = 1 << LOGB;
-    static constexpr int E = LOGB >= 14 ? 16 : (LOGB >= 3 ? 8 : B); // points per thread
+    static constexpr int E = LOGB >= FCB_FFT_E16_FROM ? 16 : (LOGB >= 3 ? 8 : B); // points per thread
     static constexpr int T = B / E;                                 // threads per transform
     static constexpr int CTA = T >= 256 ? T : 256;                  // threads per CTA
     static constexpr int TPB = CTA / T;                             // transforms per CTA
