@@ -338,6 +338,78 @@ static int launch_block_fused_shared(const fcb_engine *e, cudaStream_t st, Fused
     return FCB_OK;
 }
 
+// two convolvers fed the same input (identical rings): one launch, one forward FFT, one ring stream
+static std::atomic<bool> g_fused_pair{true};
+static int check_sched(const fcb_engine *e, size_t current, size_t active, const char *who);
+
+template <int LOGB, int ROWS>
+static int launch_block_fused_pair(const fcb_engine *ea, const fcb_engine *eb, const FusedPairArgs &fa)
+{
+    using Cfg = FusedPairCfg<LOGB, ROWS>;
+    static SmemOptIn optin;
+    FCB_TRY(optin.ensure(k_block_fused_pair<LOGB, ROWS>, Cfg::SMEM_BYTES));
+    cudaEvent_t prof_stop = nullptr;
+    const bool profiled = prof_before(ea->stream, &prof_stop) != nullptr;
+    const unsigned grid = (unsigned)((ea->C + Cfg::CPB - 1) / Cfg::CPB);
+    k_block_fused_pair<LOGB, ROWS><<<grid, 256, Cfg::SMEM_BYTES, ea->stream>>>(fa, ea->tw);
+    if (profiled) cudaEventRecord(prof_stop, ea->stream);
+    g_launches++;
+    FCB_CUDA(cudaGetLastError());
+    (void)eb;
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_pair_ok(const fcb_engine *ea, const fcb_engine *eb, size_t active)
+{
+    return ea && eb && ea != eb && g_fused_pair.load() && g_fused_block.load() && ea->logb >= 5 && ea->logb <= 9 &&
+           ea->device == eb->device && ea->stream == eb->stream && ea->C == eb->C && ea->B == eb->B && ea->S == eb->S &&
+           !ea->shared_ir && !eb->shared_ir && active >= 1 && active <= ea->S;
+}
+
+extern "C" int fcb_engine_process_block_pair_dev(fcb_engine *ea, fcb_engine *eb, const float *in_dev, size_t in_stride,
+                                                 float *out_a, size_t stride_a, const fcb_epilogue *epi_a, float *out_b,
+                                                 size_t stride_b, const fcb_epilogue *epi_b, size_t current, size_t active)
+{
+    FCB_TRY(check_sched(ea, current, active, "process_block_pair"));
+    if (!fcb_engine_pair_ok(ea, eb, active)) return fail(FCB_ERR_UNSUPPORTED, "process_block_pair: engines do not pair");
+    if (!in_dev || !out_a || !out_b) return fail(FCB_ERR_ARG, "process_block_pair: NULL argument");
+    FCB_CUDA(cudaSetDevice(ea->device));
+    const size_t B = ea->B;
+    FusedPairArgs fa{};
+    fa.in = in_dev;
+    fa.in_stride = (long long)in_stride;
+    fa.mac.ir = ea->ir;
+    fa.mac.ir_stride = ea->ir_stride();
+    fa.mac.ring = ea->ring;
+    fa.mac.ring_stride = ea->ring_stride();
+    fa.mac.current = (int)current;
+    fa.mac.active = (int)active;
+    fa.mac.nchan = (long long)ea->C;
+    fa.mac.seg_lo = 1;
+    fa.mac.seg_hi = (int)active;
+    fa.ir_b = eb->ir;
+    fa.ir_b_stride = eb->ir_stride();
+    fa.ring_b = eb->ring;
+    fa.ifft_a.overlap = ea->overlap;
+    fa.ifft_a.out = out_a;
+    fa.ifft_a.out_stride = (long long)stride_a;
+    if (epi_a) fa.ifft_a.epi = *epi_a;
+    fa.ifft_b.overlap = eb->overlap;
+    fa.ifft_b.out = out_b;
+    fa.ifft_b.out_stride = (long long)stride_b;
+    if (epi_b) fa.ifft_b.epi = *epi_b;
+    (void)B;
+    const bool short_line = active <= (size_t)g_fused_short.load();
+#define FCB_PAIR_CASE(LB)                                                        \
+    case LB:                                                                     \
+        return short_line ? launch_block_fused_pair<LB, 2>(ea, eb, fa) : launch_block_fused_pair<LB, 4>(ea, eb, fa);
+    switch (ea->logb) {
+        FCB_PAIR_CASE(5) FCB_PAIR_CASE(6) FCB_PAIR_CASE(7) FCB_PAIR_CASE(8) FCB_PAIR_CASE(9)
+    default: return fail(FCB_ERR_UNSUPPORTED, "process_block_pair: block size not covered");
+    }
+#undef FCB_PAIR_CASE
+}
+
 static bool fused_applicable(const fcb_engine *e, size_t active)
 {
     return g_fused_block.load() && e->logb >= 5 && e->logb <= 9 && active >= 1;
@@ -470,6 +542,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "fused_block")) g_fused_block = value != 0;
     else if (!strcmp(key, "fused_stages") && (value == 2 || value == 3)) g_fused_stages = value;
     else if (!strcmp(key, "fused_short") && value >= 0) g_fused_short = value;
+    else if (!strcmp(key, "fused_pair")) g_fused_pair = value != 0;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
     else if (!strcmp(key, "tma_io")) g_tma_io = value != 0;
     else if (!strcmp(key, "mapped_io")) fcb_host_mirror_set_mapped_io(value);

@@ -257,6 +257,233 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
     if (TMA_IO && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // smem stays alive until read
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pair variant: TWO convolvers that are fed the same input — TwoStageFFTConvolver's head and
+// tail_convolver0 (src/fft_convolver.rs:431, :478-487) or CrossfadeConvolver's A and B
+// (src/crossfade_convolver.rs:72-73) — hold identical input-spectrum rings, so one CTA does ONE forward FFT,
+// streams the ring rows ONCE next to both IR row sets, and finishes with both inverse FFTs side by side
+// (threads 0..63 convolver A, 64..127 convolver B).  Per channel and block the stream is 24*S*K bytes instead
+// of 32*S*K and the pair is one launch instead of two.  Each convolver's sums are formed exactly as in
+// k_block_fused (same operands, same order): outputs are bit-identical to two separate launches.  The new
+// spectrum is written into BOTH rings, so either convolver can continue on its own afterwards.
+// B's epilogue may mix in A's output of this very block (crossfade): A's samples are stored first, and B reads
+// them back with ordinary (coherent) loads after a barrier.
+// ---------------------------------------------------------------------------------------------
+struct FusedPairArgs {
+    const float *in;
+    long long in_stride;
+    MacArgs mac;            // convolver A: ir / ring / strides / current / active / nchan
+    const float2 *ir_b;     // convolver B's IR rows, channel stride ir_b_stride (0 when shared)
+    long long ir_b_stride;
+    float2 *ring_b;         // convolver B's ring (same geometry as A's): receives the new spectrum as well
+    IfftArgs ifft_a, ifft_b; // overlap / out / out_stride / epilogue of each
+};
+
+template <int LOGB, int ROWS>
+struct FusedPairCfg {
+    static constexpr int B = 1 << LOGB;
+    static constexpr int CPB = 512 / B;
+    static constexpr int R = ROWS;
+    static constexpr int ARR = CPB * R * B;                                   // float2 per array per stage
+    static constexpr size_t STAGE_BYTES = 3 * (size_t)ARR * sizeof(float2);   // IR_A | IR_B | ring
+    static constexpr int NST = 2;
+    static constexpr int FFT_PER = (sidx(B) + 2) & ~1;
+    static constexpr size_t FFT_BYTES = (((size_t)2 * CPB * FFT_PER * sizeof(float2)) + 15) / 16 * 16; // A's and B's transforms
+    static constexpr size_t SMEM_BYTES = NST * STAGE_BYTES + 64 + FFT_BYTES;
+};
+
+// like apply_epilogue, but the mixed-in samples were written by this CTA a barrier ago: coherent loads
+__device__ __forceinline__ float apply_epilogue_pair(float v, const fcb_epilogue &epi, long long c, int i)
+{
+    if (epi.add0) v = __fadd_rn(v, __ldg(epi.add0 + c * (long long)epi.add_stride + i));
+    if (epi.add1) v = __fadd_rn(v, __ldg(epi.add1 + c * (long long)epi.add_stride + i));
+    if (epi.mix_other) {
+        float2 g = __ldg(reinterpret_cast<const float2 *>(epi.gains) + i);
+        float o = *(reinterpret_cast<const volatile float *>(epi.mix_other) + c * (long long)epi.mix_stride + i);
+        if (g.x == 1.f && g.y == 0.f) {
+            /* mine, untouched */
+        } else if (g.x == 0.f && g.y == 1.f) {
+            v = o;
+        } else {
+            v = __fadd_rn(__fmul_rn(v, g.x), __fmul_rn(o, g.y));
+        }
+    }
+    return v;
+}
+
+template <int LOGB, int ROWS>
+__global__ void __launch_bounds__(256)
+k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
+{
+    using Cfg = FusedPairCfg<LOGB, ROWS>;
+    using P = FftPlan<LOGB>;
+    constexpr int B = Cfg::B, CPB = Cfg::CPB, R = Cfg::R, ARR = Cfg::ARR, NST = Cfg::NST;
+    constexpr int TX = B / 2;
+    constexpr int T = P::T, E = P::E;
+    constexpr int FT = CPB * T; // FFT threads per convolver (64)
+    static_assert(2 * FT <= 256, "both inverse transforms must fit the CTA");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 *stages = reinterpret_cast<float2 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NST * Cfg::STAGE_BYTES);
+    float2 *fbuf = reinterpret_cast<float2 *>(smem_raw + NST * Cfg::STAGE_BYTES + 64); // [2][CPB][FFT_PER]
+
+    const MacArgs &a = fa.mac;
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    const int which = tid / FT;                              // FFT role: 0 = convolver A, 1 = B (threads 0 .. 2*FT-1)
+    const int fslot = (tid % FT) / T, flane = tid % T;
+    const bool fwork1 = tid < FT, fwork2 = tid < 2 * FT;
+    const long long c0 = (long long)blockIdx.x * CPB;
+    const int nlive = (int)((a.nchan - c0) < CPB ? (a.nchan - c0) : CPB);
+    const int cur = a.current, act = a.active, lo = a.seg_lo, hi = a.seg_hi;
+    const int niter = hi > lo ? (hi - lo + R - 1) / R : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int it) {
+        const int s = it % NST;
+        const int i0 = lo + it * R;
+        const int cnt = (hi - i0) < R ? (hi - i0) : R;
+        float2 *ira_s = stages + (size_t)s * 3 * ARR;
+        float2 *irb_s = ira_s + ARR, *rg_s = ira_s + 2 * ARR;
+        mbar_expect_tx(&full[s], (uint32_t)(3 * nlive * cnt * B * sizeof(float2)));
+        const int j0 = (cur + i0) % act;
+        const int first = (act - j0) < cnt ? (act - j0) : cnt;
+        for (int ch = 0; ch < nlive; ch++) {
+            const float2 *ira = a.ir + a.ir_chan(c0 + ch) * a.ir_stride;
+            const float2 *irb = fa.ir_b + (c0 + ch) * fa.ir_b_stride;
+            const float2 *rgc = a.ring + (c0 + ch) * a.ring_stride;
+            bulk_g2s(ira_s + ch * R * B, ira + (long long)i0 * B, cnt * B * sizeof(float2), &full[s]);
+            bulk_g2s(irb_s + ch * R * B, irb + (long long)i0 * B, cnt * B * sizeof(float2), &full[s]);
+            bulk_g2s(rg_s + ch * R * B, rgc + (long long)j0 * B, first * B * sizeof(float2), &full[s]);
+            if (first < cnt) bulk_g2s(rg_s + ch * R * B + first * B, rgc, (cnt - first) * B * sizeof(float2), &full[s]);
+        }
+    };
+    if (tid == 0)
+        for (int it = 0; it < NST && it < niter; it++) issue(it);
+
+    float4 h0a = make_float4(0.f, 0.f, 0.f, 0.f), h0b = h0a;
+    const bool mlive = ty < nlive;
+    if (mlive) {
+        h0a = __ldg(reinterpret_cast<const float4 *>(a.ir + a.ir_chan(c0 + ty) * a.ir_stride) + tx);
+        h0b = __ldg(reinterpret_cast<const float4 *>(fa.ir_b + (c0 + ty) * fa.ir_b_stride) + tx);
+    }
+
+    // ---- K1 once: forward real FFT of the new block, into both rings (src/fft_convolver.rs:248-255) ----
+    float2 *fs = fbuf + (fwork1 ? fslot : 0) * Cfg::FFT_PER;
+    const bool flive1 = fwork1 && fslot < nlive;
+    if (fwork1) load_block_as_complex<LOGB>(fs, flane, fa.in + (c0 + fslot) * fa.in_stride, flive1 ? B : 0);
+    __syncthreads();
+    stockham_all<LOGB, -1, 0, 1>(fs, flane, tw, fwork1);
+    float2 xk[E];
+    if (fwork1) {
+#pragma unroll
+        for (int e = 0; e < E; e++) xk[e] = rfft_split_bin<LOGB>(fs, flane + e * T, tw);
+    }
+    __syncthreads();
+    if (fwork1) {
+        float2 *row_a = flive1 ? const_cast<float2 *>(a.ring) + (c0 + fslot) * a.ring_stride + (long long)cur * B : nullptr;
+        float2 *row_b = flive1 ? fa.ring_b + (c0 + fslot) * a.ring_stride + (long long)cur * B : nullptr;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            int k = flane + e * T;
+            fs[k] = xk[e];
+            if (flive1) {
+                row_a[k] = xk[e];
+                row_b[k] = xk[e];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- K2 for both convolvers on one ring stream (src/fft_convolver.rs:258-269) ----------------
+    const bool packed = (tx == 0);
+    float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = acc_a;
+    for (int it = 0; it < niter; it++) {
+        const int s = it % NST;
+        mbar_wait(&full[s], (it / NST) & 1);
+        const int i0 = lo + it * R;
+        const int cnt = (hi - i0) < R ? (hi - i0) : R;
+        const float4 *ira_s = reinterpret_cast<const float4 *>(stages + (size_t)s * 3 * ARR + ty * R * B) + tx;
+        const float4 *irb_s = ira_s + ARR / 2, *rg_s = ira_s + ARR;
+        if (mlive) {
+            for (int r = 0; r < cnt; r++) {
+                const float4 ha = ira_s[r * TX], hb = irb_s[r * TX], x = rg_s[r * TX];
+                cmac_ref(acc_a.x, acc_a.y, ha.x, ha.y, x.x, x.y, packed);
+                cmac_ref(acc_a.z, acc_a.w, ha.z, ha.w, x.z, x.w, false);
+                cmac_ref(acc_b.x, acc_b.y, hb.x, hb.y, x.x, x.y, packed);
+                cmac_ref(acc_b.z, acc_b.w, hb.z, hb.w, x.z, x.w, false);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && it + NST < niter) issue(it + NST);
+    }
+
+    // ---- K3 twice, side by side: conv = pre_multiplied + X[current] * H[0] (:270-275), inverse FFT ------
+    float4 conv_a = make_float4(0.f, 0.f, 0.f, 0.f), conv_b = conv_a;
+    if (mlive) {
+        const float4 x = reinterpret_cast<const float4 *>(fbuf + ty * Cfg::FFT_PER)[tx];
+        conv_a = acc_a;
+        cmac_ref(conv_a.x, conv_a.y, x.x, x.y, h0a.x, h0a.y, packed);
+        cmac_ref(conv_a.z, conv_a.w, x.z, x.w, h0a.z, h0a.w, false);
+        conv_b = acc_b;
+        cmac_ref(conv_b.x, conv_b.y, x.x, x.y, h0b.x, h0b.y, packed);
+        cmac_ref(conv_b.z, conv_b.w, x.z, x.w, h0b.z, h0b.w, false);
+    }
+    __syncthreads();
+    if (ty < CPB) {
+        float2 *da = fbuf + ty * Cfg::FFT_PER, *db = fbuf + (CPB + ty) * Cfg::FFT_PER;
+        da[sidx(2 * tx)] = make_float2(conv_a.x, conv_a.y);
+        da[sidx(2 * tx + 1)] = make_float2(conv_a.z, conv_a.w);
+        db[sidx(2 * tx)] = make_float2(conv_b.x, conv_b.y);
+        db[sidx(2 * tx + 1)] = make_float2(conv_b.z, conv_b.w);
+    }
+    __syncthreads();
+    float2 *fs2 = fbuf + (fwork2 ? which * CPB + fslot : 0) * Cfg::FFT_PER;
+    if (fwork2) irfft_presplit<LOGB>(fs2, flane, tw);
+    __syncthreads();
+    stockham_all<LOGB, +1, 0, 1>(fs2, flane, tw, fwork2);
+
+    const float inv_n = 1.0f / (float)(2 * B);
+    const long long c = c0 + fslot;
+    const bool flive2 = fwork2 && fslot < nlive;
+    // A's samples first, then (after a barrier) B's: B's epilogue may read A's output of this block
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        if (flive2 && which == pass) {
+            const IfftArgs &o = pass == 0 ? fa.ifft_a : fa.ifft_b;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                int j = flane + e * T;
+                if (2 * j >= B) continue;
+                float2 z = fs2[sidx(j)];
+                float y[2] = {z.x * inv_n, z.y * inv_n};
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    int i = 2 * j + h;
+                    o.out[c * o.out_stride + i] = apply_epilogue_pair(__fadd_rn(y[h], o.overlap[c * B + i]), o.epi, c, i);
+                }
+            }
+        }
+        __syncthreads(); // pass 0: A's output visible to B's mix; pass 1: every reader of the old overlaps is done
+    }
+    if (flive2) {
+        const IfftArgs &o = which == 0 ? fa.ifft_a : fa.ifft_b;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            int j = flane + e * T;
+            if (2 * j >= B) {
+                float2 z = fs2[sidx(j)];
+                *reinterpret_cast<float2 *>(o.overlap + c * B + (2 * j - B)) = make_float2(z.x * inv_n, z.y * inv_n);
+            }
+        }
+    }
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // Shared-IR variant: all channels of the engine use ONE impulse response (fcb_engine_desc.shared_ir).

@@ -358,6 +358,28 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
     return FCB_OK;
 }
 
+
+// Both convolvers at a block boundary with the same ring position, one whole block of device samples: they have
+// seen the same input since creation / reset (head + tail0 of a two-stage convolver, A + B of a crossfade), so
+// one paired launch serves both (fcb_engine_process_block_pair_dev).
+static bool fftconv_pair_ok(const fcb_fftconv *a, const fcb_fftconv *b, size_t n)
+{
+    return a && b && a->eng && b->eng && n == a->block_size && a->block_size == b->block_size && a->input_buffer_fill == 0 &&
+           b->input_buffer_fill == 0 && a->current == b->current && a->active_seg_count == b->active_seg_count &&
+           a->active_seg_count >= 1 && a->current < a->active_seg_count && a->stream == b->stream &&
+           fcb_engine_pair_ok(a->eng, b->eng, a->active_seg_count);
+}
+static int fftconv_process_pair_dev(fcb_fftconv *a, fcb_fftconv *b, const float *in, size_t in_stride, float *out_a,
+                                    size_t stride_a, const fcb_epilogue *epi_a, float *out_b, size_t stride_b,
+                                    const fcb_epilogue *epi_b)
+{
+    FCB_TRY(fcb_engine_process_block_pair_dev(a->eng, b->eng, in, in_stride, out_a, stride_a, epi_a, out_b, stride_b, epi_b,
+                                              a->current, a->active_seg_count));
+    a->current = a->current > 0 ? a->current - 1 : a->active_seg_count - 1; // :301-305
+    b->current = a->current;
+    return FCB_OK;
+}
+
 extern "C" int fcb_fftconv_process(fcb_fftconv *c, const float *in, size_t in_len, size_t in_stride, float *out,
                                    size_t out_len, size_t out_stride)
 {
@@ -656,7 +678,14 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
         epi.add1 = c->tail_precalculated + c->precalculated_pos;
         epi.add_stride = T;
     }
-    FCB_TRY(fcb_fftconv_process_dev(c->head, in, in_len, in_stride, out, out_len, out_stride, fuse ? &epi : nullptr)); // :431
+    // head and tail_convolver0 see the same head blocks (:431 and :478-487): when this call is one whole head block
+    // both run in one paired launch, tail0 writing where :478-487 would have put its block
+    const bool paired = fuse && in_len == H && c->tail_input_fill % H == 0 && fftconv_pair_ok(c->head, c->tail0, in_len);
+    if (paired)
+        FCB_TRY(fftconv_process_pair_dev(c->head, c->tail0, in, in_stride, out, out_stride, &epi,
+                                         c->tail_output0 + c->tail_input_fill, T, nullptr));
+    else
+        FCB_TRY(fcb_fftconv_process_dev(c->head, in, in_len, in_stride, out, out_len, out_stride, fuse ? &epi : nullptr)); // :431
     if (T == 0) return FCB_OK; // :434-436
 
     size_t processed = 0;
@@ -682,7 +711,7 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
 
         if (c->tail_input_fill % H == 0) { // :478-490
             const size_t off = c->tail_input_fill - H;
-            FCB_TRY(fcb_fftconv_process_dev(c->tail0, tin + off, H, T, c->tail_output0 + off, H, T, nullptr));
+            if (!paired) FCB_TRY(fcb_fftconv_process_dev(c->tail0, tin + off, H, T, c->tail_output0 + off, H, T, nullptr));
             if (c->tail_input_fill == T) std::swap(c->tail_precalculated0, c->tail_output0);
         }
         if (c->tail_input_fill == T) { // :493-500
@@ -818,6 +847,11 @@ struct fcb_crossfade {
     cudaEvent_t ev_gains = nullptr;
     float *d_in = nullptr, *d_out = nullptr;        // host-call staging
     size_t d_in_cap = 0;
+    // A is a deep clone of B (:29) and both are fed the same samples, so their input-spectrum rings hold the same
+    // spectra in the same slots — until an update() with another segment count (:204) lets their `current` drift
+    // apart at the next wrap (:301-305); a call that starts with unequal segment counts or positions turns the
+    // paired launch off for good
+    bool rings_same = true;
 };
 
 extern "C" void fcb_crossfade_free(fcb_crossfade *c)
@@ -967,6 +1001,21 @@ extern "C" int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in, size
         return fcb_fftconv_process_dev(f, in, in_len, in_stride, dst, M, dst_stride, epi);
     };
     const bool whole = out_len == M && M > 0; // the mix can ride on the second convolver's K3
+    if (c->a->current != c->b->current || c->a->active_seg_count != c->b->active_seg_count) c->rings_same = false;
+    if (whole && in_len >= M && c->rings_same && fftconv_pair_ok(c->a, c->b, M)) {
+        // A and B are clones fed the same blocks (:29, :72-73): one paired launch, the mix fused into B's epilogue
+        if (all_a) return fftconv_process_pair_dev(c->a, c->b, in, in_stride, out, out_stride, nullptr, c->buffer_b, M, nullptr);
+        if (all_b) return fftconv_process_pair_dev(c->a, c->b, in, in_stride, c->buffer_a, M, nullptr, out, out_stride, nullptr);
+        for (size_t i = 0; i < out_len; i++) c->h_gains[i] = make_float2(c->h_gains[i].y, c->h_gains[i].x); // mine = B
+        FCB_CUDA(cudaMemcpyAsync(c->d_gains, c->h_gains, out_len * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+        FCB_CUDA(cudaEventRecord(c->ev_gains, c->stream));
+        fcb_epilogue epi;
+        memset(&epi, 0, sizeof epi);
+        epi.mix_other = c->buffer_a;
+        epi.mix_stride = M;
+        epi.gains = reinterpret_cast<const float *>(c->d_gains);
+        return fftconv_process_pair_dev(c->a, c->b, in, in_stride, c->buffer_a, M, nullptr, out, out_stride, &epi);
+    }
     if (whole && all_a) {
         FCB_TRY(run(c->b, c->buffer_b, M, nullptr));
         return run(c->a, out, out_stride, nullptr);

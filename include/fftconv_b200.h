@@ -57,7 +57,7 @@ int fcb_device_count(void);
  * end-to-end copy/compute pipeline, default 512), "mimo_tile" (1 = matrix K2 with in-CTA reuse of
  * IR and ring tiles, 0 = the per-channel K2), "mimo_tc" (the tensor-core matrix MAC K4: 0 = never, 1 = always,
  * 2 = when at least 16 streams share the matrix; read by fcb_mimo_create), "fused_block" (1 = whole blocks with B in 32..512 run as
- * one fused K1+K2+K3 kernel, 0 = three launches; outputs are bit-identical), "fused_stages" (2 or 3), "fused_short" (delay lines of up to this many segments run
+ * one fused K1+K2+K3 kernel, 0 = three launches; outputs are bit-identical), "fused_stages" (2 or 3), "fused_pair" (1 = convolvers fed the same input share one launch), "fused_short" (delay lines of up to this many segments run
  * the fused kernel with 2-row stages so that a fourth CTA per SM hides the FFT latency; default 40, 0 = off), "mapped_io" (1 = small-batch host
  * calls go through mapped pinned memory instead of the copy engines), "zero_copy" (1 = when the caller's
  * buffers are pinned, large-batch whole-block calls let the kernel read/write them over PCIe directly) */
@@ -159,6 +159,15 @@ int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, size_t in_s
                                  size_t out_stride, size_t current, size_t active,
                                  const fcb_epilogue *epi);
 
+/* Whole block for TWO engines that have been fed the same input since creation / reset (identical input-spectrum
+ * rings, same geometry, same stream): TwoStage's head + tail_convolver0, Crossfade's A + B.  One launch does one forward
+ * FFT (written into both rings), streams the ring rows once beside both IR row sets, and runs both inverse FFTs; each
+ * engine's output is bit-identical to its own fcb_engine_process_block_dev.  epi_b may mix in out_a of this block.
+ * fcb_tune("fused_pair", 0) disables the pairing in the host mirror. */
+int fcb_engine_pair_ok(const fcb_engine *ea, const fcb_engine *eb, size_t active);
+int fcb_engine_process_block_pair_dev(fcb_engine *ea, fcb_engine *eb, const float *in_dev, size_t in_stride, float *out_a,
+                                      size_t stride_a, const fcb_epilogue *epi_a, float *out_b, size_t stride_b,
+                                      const fcb_epilogue *epi_b, size_t current, size_t active);
 /* Multi-block calls (offline rendering, large host buffers): nblocks whole blocks of every channel in ONE
  * time-batched pass — K1 for all blocks, a MAC kernel whose threads keep a sliding window of T input spectra in
  * registers (one IR row + one spectrum row loaded per segment feed T output blocks: T blocks for the HBM traffic of
