@@ -28,14 +28,27 @@ int get_twiddles(int device, size_t N, const float2 **out)
         *out = it->second;
         return FCB_OK;
     }
-    std::vector<float2> h(N);
-    for (size_t t = 0; t < N; t++) {
+    auto root = [N](size_t t) {
         double a = -2.0 * M_PI * (double)t / (double)N;
-        h[t] = make_float2((float)cos(a), (float)sin(a));
+        return make_float2((float)cos(a), (float)sin(a));
+    };
+    std::vector<float2> h(N);
+    for (size_t t = 0; t < N; t++) h[t] = root(t);
+    // pass-ordered copies behind the base table: for Stockham pass p (stride NS, radix R) the factor of
+    // (r, k) sits at [off_p + (r-1)*NS + k] — the threads of a warp (consecutive k) then read consecutive
+    // entries instead of entries r*k*STEP apart.  Same values as h[r*k*STEP] (pass_tw_offset in fft_kernels.cuh).
+    const int logb = ilog2(N / 2);
+    size_t ns = 1;
+    for (int p = 0; radix_at(logb, p) > 0; p++) {
+        const size_t R = (size_t)radix_at(logb, p), step = N / (ns * R);
+        if (ns > 1)
+            for (size_t r = 1; r < R; r++)
+                for (size_t k = 0; k < ns; k++) h.push_back(root(r * k * step));
+        ns *= R;
     }
     float2 *d = nullptr;
-    FCB_CUDA(cudaMalloc(&d, N * sizeof(float2)));
-    FCB_CUDA(cudaMemcpy(d, h.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
+    FCB_CUDA(cudaMalloc(&d, h.size() * sizeof(float2)));
+    FCB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
     g_tw[key] = d;
     *out = d;
     return FCB_OK;

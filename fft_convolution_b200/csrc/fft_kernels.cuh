@@ -69,6 +69,19 @@ __host__ __device__ constexpr int radix_at(int logb, int p)
     return p < n8 - 1 ? 8 : (p < n8 + 1 ? 4 : 0);
 }
 
+// offset (in entries, from the end of the N-entry base table) of the pass-ordered twiddles of the pass with
+// stride `ns` (see get_twiddles): passes with ns > 1 store (R-1)*ns entries each
+__host__ __device__ constexpr int pass_tw_offset(int logb, int ns)
+{
+    int off = 0, n = 1;
+    for (int p = 0; n < ns; p++) {
+        const int r = radix_at(logb, p);
+        if (n > 1) off += (r - 1) * n;
+        n *= r;
+    }
+    return off;
+}
+
 // ---- in-register DFTs, natural order out ------------------------------------------------
 template <int DIR>
 __device__ __forceinline__ void dft2(float2 &a, float2 &b)
@@ -143,11 +156,12 @@ __device__ __forceinline__ void stockham_pass(float2 *s, int tid, const float2 *
         int j = tid + b * T;
         int k = j & (NS - 1);
         if constexpr (NS > 1) {
-            // twiddle v[r] *= w_{NS*R}^{r k} = tw[r * k * (N / (NS*R))], N = 2B
-            constexpr int STEP = (2 * B) / (NS * R);
+            // twiddle v[r] *= w_{NS*R}^{r k} = tw[r * k * (N / (NS*R))], N = 2B — read from the pass-ordered copy
+            // (coalesced over k) that get_twiddles appends to the base table
+            constexpr int OFF = 2 * B + pass_tw_offset(LOGB, NS);
 #pragma unroll
             for (int r = 1; r < R; r++) {
-                float2 w = __ldg(&tw[r * k * STEP]);
+                float2 w = __ldg(&tw[OFF + (r - 1) * NS + k]);
                 if (DIR > 0) w.y = -w.y;
                 v[b][r] = cmul(v[b][r], w);
             }
