@@ -516,6 +516,21 @@ int mac_tile_plan(int logb, int n_in, int n_out, int n_streams, int nsegs, int *
     const long long zmax = nsegs > 8 ? nsegs / 8 : 1;
     if (z > zmax) z = zmax;
     if (z < 1) z = 1;
+    // one CTA is resident per SM (its stages fill the shared memory): pick the chunk count near z whose CTA count
+    // fills whole waves of 148 best — 19 chunks of the 16 x 16 matrix are 608 CTAs = 4.1 waves (a fifth, nearly
+    // empty round), 18 are 576 = 3.9
+    {
+        double best = 0.0;
+        long long best_z = z;
+        for (long long c = z > 2 ? z - z / 3 : 1; c <= z + z / 3 && c <= zmax; c++) {
+            const double waves = (double)(base * c) / 148.0, eff = waves / (double)(long long)(waves + 0.999999);
+            if (eff > best + 1e-9) {
+                best = eff;
+                best_z = c;
+            }
+        }
+        z = best_z;
+    }
     const int len = (int)((nsegs + z - 1) / z);
     *zlen = len > 0 ? len : 1;
     *zchunks = nsegs > 0 ? (nsegs + *zlen - 1) / *zlen : 1;
