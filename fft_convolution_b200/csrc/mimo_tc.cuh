@@ -303,11 +303,14 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
         const int grp = (warp - 2) >> 2, gtid = (tid - 64) & 127;
         const int row = (warp & 3) * 32 + lane; // TMEM lane quadrant of this warp
         const bool live = (warp & 3) * 32 < a.rows_pad; // quadrants above the stored stream rows hold nothing
-        auto lo1 = [](float x) {
-            float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-            uint32_t u;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(r));
-            return u;
+        // lo = x - hi for two values at once: one LOP3 each for -hi = (x & 0xFFFFE000) ^ 0x80000000 and one packed
+        // add.f32x2 (exact: hi shares x's exponent).  The tensor core truncates lo to 11 bits itself.  The splitter
+        // warps' instruction count is what paces the kernel below 128 streams, hence 1.5 instead of 3 per value.
+        auto lo2 = [](float x0, float x1, uint32_t &l0, uint32_t &l1) {
+            const uint32_t n0 = (__float_as_uint(x0) & 0xFFFFE000u) ^ 0x80000000u, n1 = (__float_as_uint(x1) & 0xFFFFE000u) ^ 0x80000000u;
+            asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 c, a, b;\n\tmov.b64 {%0, %1}, c;\n\t}"
+                : "=r"(l0), "=r"(l1)
+                : "r"(__float_as_uint(x0)), "r"(__float_as_uint(x1)), "r"(n0), "r"(n1));
         };
         for (int t = grp; t < total; t += TC_SPLIT_WARPS / 4) {
             const int sr = t % TC_NR, sl = t % TC_NL;
@@ -337,7 +340,8 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
                         const float4 x = v[4 * h + j];
                         hi[4 * j + 0] = __float_as_uint(x.x), hi[4 * j + 1] = __float_as_uint(x.y);
                         hi[4 * j + 2] = __float_as_uint(x.z), hi[4 * j + 3] = __float_as_uint(x.w);
-                        lo[4 * j + 0] = lo1(x.x), lo[4 * j + 1] = lo1(x.y), lo[4 * j + 2] = lo1(x.z), lo[4 * j + 3] = lo1(x.w);
+                        lo2(x.x, x.y, lo[4 * j + 0], lo[4 * j + 1]);
+                        lo2(x.z, x.w, lo[4 * j + 2], lo[4 * j + 3]);
                     }
                     tmem_st16(ta + 16 * h, hi);
                     tmem_st16(ta + 2 * TC_KSEG + 16 * h, lo);
@@ -346,10 +350,10 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
 #pragma unroll
             for (int j = 0; j < Cfg::B_BYTES / 16 / 128; j++) {
                 hiB[gtid + 128 * j] = w[j];
-                float4 l;
-                l.x = __uint_as_float(lo1(w[j].x)), l.y = __uint_as_float(lo1(w[j].y));
-                l.z = __uint_as_float(lo1(w[j].z)), l.w = __uint_as_float(lo1(w[j].w));
-                loB[gtid + 128 * j] = l;
+                uint4 l;
+                lo2(w[j].x, w[j].y, l.x, l.y);
+                lo2(w[j].z, w[j].w, l.z, l.w);
+                reinterpret_cast<uint4 *>(loB)[gtid + 128 * j] = l;
             }
             if (live) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
