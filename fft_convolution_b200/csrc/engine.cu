@@ -921,12 +921,12 @@ extern "C" int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, 
 }
 
 // ---- multi-block calls: nblocks whole blocks of every channel in one time-batched pass -------------
-template <int LOGB, int T>
+template <int LOGB, int T, int P = (T < 4 ? T : 4)>
 static int launch_mac_time_t(const MacTimeArgs &a, cudaStream_t st)
 {
     constexpr int B = 1 << LOGB, ROW4 = B / 2, TX = ROW4 < 256 ? ROW4 : 256, TILES = ROW4 / TX, CPB = 256 / TX;
     const long long ngq = (a.nblocks + T - 1) / T, cgroups = (a.nchan + CPB - 1) / CPB;
-    k_mac_time<B, T><<<(unsigned)(TILES * ngq * cgroups), 256, 0, st>>>(a);
+    k_mac_time<B, T, P><<<(unsigned)(TILES * ngq * cgroups), 256, 0, st>>>(a);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;

@@ -18,7 +18,9 @@
 //
 // Measured (B200, 4096 channels x 2 s IR x block 512, device buffers, profiles/r01_offline_multi_block.jsonl):
 // 1 / 2 / 4 / 8 / 16 blocks per call = 49.4 / 82.7 / 143 / 165 / 173 k channel-seconds per second; a window of
-// T = 4 (79 registers) with the second group of 4 re-reading IR rows from L2 beats T = 8 (165 registers: 144 k).
+// T = 4 (79 registers) with the second group of 4 re-reading IR rows from L2 beats T = 8 (165 registers: 144 k; 127
+// registers with the prefetch bounded to 4 segments: 156 k) — at T = 4 the kernel is still HBM-bound (ncu: 6.6 TB/s,
+// FMA pipe 40 %), at T = 8 the arithmetic takes over.
 // The reference example's shape (mono, 64-sample blocks, 128 000 taps, 1000 blocks): 0.58 ms in one call vs
 // 278 ms block by block, identical bits.
 #pragma once
@@ -50,12 +52,14 @@ __device__ __forceinline__ float4 time_src(const MacTimeArgs &a, long long c, in
     return ld_stream4(reinterpret_cast<const float4 *>(a.ring + c * a.ring_stride) + (long long)slot * ROW4 + t4);
 }
 
-// One thread owns 2 adjacent bins (one float4) of one channel for T consecutive output blocks.
+// One thread owns 2 adjacent bins (one float4) of one channel for T consecutive output blocks; P = segments
+// whose IR / spectrum rows are loaded ahead of their MACs (2*P 16-byte loads in flight per thread).
 // grid.x = tiles * block groups * channel groups, block groups of one channel adjacent (IR rows re-read from L2).
-template <int B, int T>
+template <int B, int T, int P>
 __global__ void __launch_bounds__(256)
 k_mac_time(MacTimeArgs a)
 {
+    static_assert(T % P == 0, "the window rotation is unrolled over T segments in steps of P");
     constexpr int ROW4 = B / 2;
     constexpr int TX = ROW4 < 256 ? ROW4 : 256;
     constexpr int TILES = ROW4 / TX;
@@ -82,25 +86,28 @@ k_mac_time(MacTimeArgs a)
 #pragma unroll
     for (int d = 1; d < T; d++) w[d - 1] = time_src<B>(a, c, d0 + d - 1, t4);
     for (int i0 = 1; i0 < A; i0 += T) {
-        float4 h[T], e[T];
 #pragma unroll
-        for (int u = 0; u < T; u++) {
-            const int i = i0 + u;
-            if (i < A) {
-                h[u] = ld_stream4(ir + (long long)i * ROW4);
-                e[u] = time_src<B>(a, c, d0 - i, t4); // the spectrum that enters the window at segment i
+        for (int u0 = 0; u0 < T; u0 += P) {
+            float4 h[P], e[P];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const int i = i0 + u0 + p;
+                if (i < A) {
+                    h[p] = ld_stream4(ir + (long long)i * ROW4);
+                    e[p] = time_src<B>(a, c, d0 - i, t4); // the spectrum that enters the window at segment i
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < T; u++) {
-            const int i = i0 + u;
-            if (i < A) {
-                w[(T - 1 - u) % T] = e[u]; // (0 - i) mod T with i = i0 + u, (i0 - 1) % T == 0
+            for (int p = 0; p < P; p++) {
+                const int u = u0 + p, i = i0 + u;
+                if (i < A) {
+                    w[(T - 1 - u) % T] = e[p]; // (0 - i) mod T with i = i0 + u, (i0 - 1) % T == 0
 #pragma unroll
-                for (int d = 0; d < T; d++) {
-                    const float4 x = w[(d + T - 1 - u) % T]; // (d - i) mod T
-                    cmac_ref(acc[d].x, acc[d].y, h[u].x, h[u].y, x.x, x.y, packed);
-                    cmac_ref(acc[d].z, acc[d].w, h[u].z, h[u].w, x.z, x.w, false);
+                    for (int d = 0; d < T; d++) {
+                        const float4 x = w[(d + T - 1 - u) % T]; // (d - i) mod T
+                        cmac_ref(acc[d].x, acc[d].y, h[p].x, h[p].y, x.x, x.y, packed);
+                        cmac_ref(acc[d].z, acc[d].w, h[p].z, h[p].w, x.z, x.w, false);
+                    }
                 }
             }
         }
