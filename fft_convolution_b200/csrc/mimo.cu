@@ -624,6 +624,21 @@ extern "C" int fcb_mimo_peer_attach_ptrs(fcb_mimo *m, void *const *inboxes)
 }
 
 extern "C" void *fcb_mimo_stream(fcb_mimo *m) { return m ? (void *)m->stream : nullptr; }
+// K4's stage enumeration for one input (host copy of what the TMA producer computes): for stage c the ring slot
+// block, the IR copy and the IR position paired with the block's first slot.  No device needed (tests).
+extern "C" int fcb_debug_tc_stages(int S, int current, int seg_lo, int seg_hi, int max_stages, int *blk, int *copy, int *pos0)
+{
+    TcArgs a{};
+    a.S = S;
+    a.current = current;
+    a.seg_lo = seg_lo;
+    a.seg_hi = seg_hi;
+    const TcSpan span(a);
+    const int n = span.per_input();
+    for (int c = 0; c < n && c < max_stages; c++) span.chunk(c, blk[c], copy[c], pos0[c]);
+    return n;
+}
+
 extern "C" int fcb_mimo_uses_tensor_cores(const fcb_mimo *m) { return m && m->tc ? 1 : 0; }
 extern "C" size_t fcb_mimo_block_size(const fcb_mimo *m) { return m->B; }
 extern "C" size_t fcb_mimo_seg_count(const fcb_mimo *m) { return m->S; }

@@ -169,7 +169,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
 // segments [max(seg_lo, S - current), seg_hi) in slots i - (S - current).
 struct TcSpan {
     int n1, blk1, sh1, pos1, n2, blk2, sh2, pos2;
-    __device__ TcSpan(const TcArgs &a)
+    __host__ __device__ TcSpan(const TcArgs &a)
     {
         const int wrap = a.S - a.current;
         const int hi1 = a.seg_hi < wrap ? a.seg_hi : wrap;
@@ -183,8 +183,8 @@ struct TcSpan {
         sh2 = (wrap + a.seg_lo) & 1;
         pos2 = TC_LEAD + sh2 + blk2 * TC_KSEG + wrap - a.seg_lo;
     }
-    __device__ int per_input() const { return n1 + n2; }
-    __device__ void chunk(int c, int &blk, int &copy, int &pos0) const
+    __host__ __device__ int per_input() const { return n1 + n2; }
+    __host__ __device__ void chunk(int c, int &blk, int &copy, int &pos0) const
     {
         if (c < n1) {
             blk = blk1 + c;
