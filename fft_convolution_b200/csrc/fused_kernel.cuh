@@ -288,8 +288,11 @@ struct FusedPairCfg {
     static constexpr size_t STAGE_BYTES = 3 * (size_t)ARR * sizeof(float2);   // IR_A | IR_B | ring
     static constexpr int NST = 2;
     static constexpr int FFT_PER = (sidx(B) + 2) & ~1;
-    static constexpr size_t FFT_BYTES = (((size_t)2 * CPB * FFT_PER * sizeof(float2)) + 15) / 16 * 16; // A's and B's transforms
+    // one transform buffer per channel: X[current] during the stream, then convolver A's inverse transform;
+    // convolver B's inverse transform reuses stage memory (the stream has ended by then) — 4 CTAs per SM at B = 512
+    static constexpr size_t FFT_BYTES = (((size_t)CPB * FFT_PER * sizeof(float2)) + 15) / 16 * 16;
     static constexpr size_t SMEM_BYTES = NST * STAGE_BYTES + 64 + FFT_BYTES;
+    static_assert((size_t)CPB * FFT_PER * sizeof(float2) <= STAGE_BYTES, "B's transform buffer must fit one stage");
 };
 
 // like apply_epilogue, but the mixed-in samples were written by this CTA a barrier ago: coherent loads
@@ -325,7 +328,8 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2 *stages = reinterpret_cast<float2 *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NST * Cfg::STAGE_BYTES);
-    float2 *fbuf = reinterpret_cast<float2 *>(smem_raw + NST * Cfg::STAGE_BYTES + 64); // [2][CPB][FFT_PER]
+    float2 *fbuf = reinterpret_cast<float2 *>(smem_raw + NST * Cfg::STAGE_BYTES + 64); // [CPB][FFT_PER]
+    float2 *fbuf_b = stages;                                                            // [CPB][FFT_PER], after the stream
 
     const MacArgs &a = fa.mac;
     const int tid = threadIdx.x;
@@ -436,14 +440,14 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
     }
     __syncthreads();
     if (ty < CPB) {
-        float2 *da = fbuf + ty * Cfg::FFT_PER, *db = fbuf + (CPB + ty) * Cfg::FFT_PER;
+        float2 *da = fbuf + ty * Cfg::FFT_PER, *db = fbuf_b + ty * Cfg::FFT_PER;
         da[sidx(2 * tx)] = make_float2(conv_a.x, conv_a.y);
         da[sidx(2 * tx + 1)] = make_float2(conv_a.z, conv_a.w);
         db[sidx(2 * tx)] = make_float2(conv_b.x, conv_b.y);
         db[sidx(2 * tx + 1)] = make_float2(conv_b.z, conv_b.w);
     }
     __syncthreads();
-    float2 *fs2 = fbuf + (fwork2 ? which * CPB + fslot : 0) * Cfg::FFT_PER;
+    float2 *fs2 = (fwork2 && which ? fbuf_b : fbuf) + (fwork2 ? fslot : 0) * Cfg::FFT_PER;
     if (fwork2) irfft_presplit<LOGB>(fs2, flane, tw);
     __syncthreads();
     stockham_all<LOGB, +1, 0, 1>(fs2, flane, tw, fwork2);
