@@ -65,7 +65,7 @@ def main():
     # time (csrc/offline_kernels.cuh) and returns the same bits
     convolver_c = F.FFTConvolver.init(response, block_size, response.size)
     output_c = np.zeros_like(output_a)
-    convolver_c.process(x[:8 * block_size], output_c[:8 * block_size])  # first multi-block call allocates its workspace
+    convolver_c.process(x, output_c)  # the first call of this length sizes the multi-block workspace
     convolver_c.reset()
     t0 = time.perf_counter()
     convolver_c.process(x, output_c)

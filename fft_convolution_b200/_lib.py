@@ -87,6 +87,7 @@ SIGNATURES = {
     "fcb_engine_process_block_pair_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, C.POINTER(Epilogue), _vp, _sz, C.POINTER(Epilogue), _sz, _sz]),
     "fcb_engine_multi_block_ok": (_i, [_vp, _sz, _sz]),
     "fcb_engine_multi_block_capacity": (_sz, [_vp]),
+    "fcb_engine_multi_block_reserve": (_i, [_vp, _sz]),
     "fcb_engine_process_blocks": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz, _sz, C.POINTER(Epilogue), _i]),
     "fcb_engine_read_ir_segment": (_i, [_vp, _sz, _sz, _vp]),
     "fcb_engine_read_ring_segment": (_i, [_vp, _sz, _sz, _vp]),

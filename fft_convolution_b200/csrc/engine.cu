@@ -937,25 +937,50 @@ extern "C" int fcb_engine_multi_block_ok(const fcb_engine *e, size_t current, si
     return e && g_multi_block.load() && e->logb >= 2 && active >= 1 && current < active;
 }
 
-static int mb_ensure(fcb_engine *e)
+// most blocks one pass may hold: 256 MB per workspace buffer, at least 4, at most 1024
+static size_t mb_limit(const fcb_engine *e)
 {
-    if (e->mb_cap) return FCB_OK;
     const size_t per_block = e->C * e->B * sizeof(float2);
     size_t cap = ((size_t)256 << 20) / per_block;
-    cap = cap < 4 ? 4 : cap > 1024 ? 1024 : cap;
-    FCB_CUDA(cudaMalloc((void **)&e->mb_xnew, cap * per_block));
-    FCB_CUDA(cudaMalloc((void **)&e->mb_premul, cap * per_block));
-    FCB_CUDA(cudaMalloc((void **)&e->mb_y, cap * per_block));
-    FCB_CUDA(cudaMalloc((void **)&e->mb_in, cap * per_block / 2));
-    FCB_CUDA(cudaMalloc((void **)&e->mb_out, cap * per_block / 2));
-    e->mb_cap = cap;
+    return cap < 4 ? 4 : cap > 1024 ? 1024 : cap;
+}
+
+// workspace for `need` blocks per pass (grows when a longer call arrives; never shrinks)
+static int mb_ensure(fcb_engine *e, size_t need)
+{
+    if (need <= e->mb_cap) return FCB_OK;
+    if (need > mb_limit(e)) need = mb_limit(e);
+    if (need <= e->mb_cap) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(e->device));
+    if (e->mb_cap) {
+        FCB_CUDA(cudaStreamSynchronize(e->stream));
+        cudaFree(e->mb_xnew);
+        cudaFree(e->mb_premul);
+        cudaFree(e->mb_y);
+        cudaFree(e->mb_in);
+        cudaFree(e->mb_out);
+        e->mb_xnew = e->mb_premul = nullptr;
+        e->mb_y = e->mb_in = e->mb_out = nullptr;
+        e->mb_cap = 0;
+    }
+    const size_t per_block = e->C * e->B * sizeof(float2);
+    FCB_CUDA(cudaMalloc((void **)&e->mb_xnew, need * per_block));
+    FCB_CUDA(cudaMalloc((void **)&e->mb_premul, need * per_block));
+    FCB_CUDA(cudaMalloc((void **)&e->mb_y, need * per_block));
+    FCB_CUDA(cudaMalloc((void **)&e->mb_in, need * per_block / 2));
+    FCB_CUDA(cudaMalloc((void **)&e->mb_out, need * per_block / 2));
+    e->mb_cap = need;
     return FCB_OK;
 }
 
-extern "C" size_t fcb_engine_multi_block_capacity(fcb_engine *e)
+extern "C" size_t fcb_engine_multi_block_capacity(fcb_engine *e) { return e ? mb_limit(e) : 0; }
+
+// allocate the multi-block workspace ahead of time (a real-time caller whose buffers span several blocks calls this
+// once after create; otherwise the first multi-block call allocates)
+extern "C" int fcb_engine_multi_block_reserve(fcb_engine *e, size_t nblocks)
 {
-    if (!e || mb_ensure(e) != FCB_OK) return 0;
-    return e->mb_cap;
+    if (!e) return fail(FCB_ERR_ARG, "multi_block_reserve: NULL engine");
+    return mb_ensure(e, nblocks);
 }
 
 // in / out: device pointers, or host pointers when host_io (staged through the workspace).  Caller rotates
@@ -969,9 +994,9 @@ extern "C" int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t 
     if (!in || !out) return fail(FCB_ERR_ARG, "process_blocks: NULL argument");
     if (!fcb_engine_multi_block_ok(e, current, active)) return fail(FCB_ERR_UNSUPPORTED, "process_blocks: not applicable here");
     FCB_CUDA(cudaSetDevice(e->device));
-    FCB_TRY(mb_ensure(e));
     if (nblocks == 0) return FCB_OK;
-    if (nblocks > e->mb_cap) return fail(FCB_ERR_ARG, "process_blocks: %zu blocks exceed the workspace (%zu)", nblocks, e->mb_cap);
+    if (nblocks > mb_limit(e)) return fail(FCB_ERR_ARG, "process_blocks: %zu blocks exceed the workspace limit (%zu)", nblocks, mb_limit(e));
+    FCB_TRY(mb_ensure(e, nblocks));
     const size_t B = e->B, C = e->C, NB = nblocks;
     cudaStream_t st = e->stream;
     const float *din = in;

@@ -173,10 +173,12 @@ int fcb_engine_process_block_pair_dev(fcb_engine *ea, fcb_engine *eb, const floa
  * registers (one IR row + one spectrum row loaded per segment feed T output blocks: T blocks for the HBM traffic of
  * one), independent inverse FFTs and a parallel overlap-add.  Same arithmetic and summation order per block as
  * nblocks calls of fcb_engine_process_block_dev: bit-identical output.  in/out are device pointers, or host pointers
- * when host_io != 0; the caller rotates `current` nblocks times afterwards.  The workspace (capacity in blocks) is
- * allocated on first use.  fcb_tune("multi_block", 0) makes the host mirror process block by block. */
+ * when host_io != 0; the caller rotates `current` nblocks times afterwards.  The workspace grows to the longest
+ * call seen (first use allocates; fcb_engine_multi_block_reserve does it ahead of time for real-time callers) up to
+ * fcb_engine_multi_block_capacity blocks per pass.  fcb_tune("multi_block", 0) makes the host mirror process block by block. */
 int fcb_engine_multi_block_ok(const fcb_engine *e, size_t current, size_t active);
 size_t fcb_engine_multi_block_capacity(fcb_engine *e);
+int fcb_engine_multi_block_reserve(fcb_engine *e, size_t nblocks);
 int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
                               size_t current, size_t active, size_t nblocks, const fcb_epilogue *epi, int host_io);
 /* the same with HOST buffers (pinned for full overlap), pipelined over channel groups of
