@@ -70,7 +70,7 @@ struct TcCfg {
     static constexpr int B_BYTES = N2 * 128;               // 4 KB at 16 outputs
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;    // A | B as loaded
     static constexpr int LO_BYTES = 2 * B_BYTES;           // B_hi | B_lo
-    static constexpr int SET_COLS = 3 * N2;                // main | cross (hi*lo) | cross (lo*hi)
+    static constexpr int SET_COLS = 2 * N2;                // main | cross (hi*lo + lo*hi: both small, one accumulator)
     static constexpr int BUF_COLS = TC_SETS * SET_COLS;
     static constexpr int ACC_COLS = 2 * BUF_COLS;          // double-buffered against the drain
     static constexpr int A_COLS = 4 * TC_KSEG;             // per split stage: 32 columns of hi, 32 of lo
@@ -285,11 +285,11 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
                     const uint64_t b_hl = umma_desc_k128(lo + ks * 32);
-                    // [main | cross1] (+)= A_hi * [B_hi | B_lo]^T ;  cross2 (+)= A_lo * B_hi^T, in set ks % TC_SETS
+                    // [main | cross] (+)= A_hi * [B_hi | B_lo]^T ;  cross += A_lo * B_hi^T, in set ks % TC_SETS
                     const uint32_t d_set = d_buf + (ks % TC_SETS) * Cfg::SET_COLS;
                     const uint32_t acc_on = (first && ks < TC_SETS) ? 0u : 1u;
                     umma_tf32_ts(d_set, a_hi + ks * 8, b_hl, idesc_wide, acc_on);
-                    umma_tf32_ts(d_set + 2 * N2, a_lo + ks * 8, b_hl, idesc_narrow, acc_on);
+                    umma_tf32_ts(d_set + N2, a_lo + ks * 8, b_hl, idesc_narrow, 1u);
                 }
                 umma_commit(&empty_lo[sl]);
                 if (last) umma_commit(&acc_full[b]);
@@ -376,14 +376,12 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
             for (int set = 0; set < TC_SETS; set++) {
 #pragma unroll
                 for (int c = 0; c < N2; c += 16) {
-                    uint32_t m[16], x[16], y[16];
+                    uint32_t m[16], x[16];
                     tmem_ld16(base + set * Cfg::SET_COLS + c, m);
                     tmem_ld16(base + set * Cfg::SET_COLS + N2 + c, x);
-                    tmem_ld16(base + set * Cfg::SET_COLS + 2 * N2 + c, y);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int i = 0; i < 16; i++)
-                        acc[c + i] += __uint_as_float(m[i]) + (__uint_as_float(x[i]) + __uint_as_float(y[i]));
+                    for (int i = 0; i < 16; i++) acc[c + i] += __uint_as_float(m[i]) + __uint_as_float(x[i]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
