@@ -55,6 +55,19 @@ extern "C" {
     pub fn fcb_engine_fetch(e: *mut FcbEngine, out_host: *mut f32, host_stride: usize, src_dev: *const f32,
                             dev_stride: usize, n: usize) -> c_int;
     pub fn fcb_engine_scratch(e: *mut FcbEngine) -> *mut f32;
+    // several whole blocks in one time-batched pass (bit-identical to the block-by-block loop); host_io != 0: host pointers
+    pub fn fcb_engine_multi_block_ok(e: *const FcbEngine, current: usize, active: usize) -> c_int;
+    pub fn fcb_engine_multi_block_capacity(e: *mut FcbEngine) -> usize;
+    pub fn fcb_engine_multi_block_reserve(e: *mut FcbEngine, nblocks: usize) -> c_int;
+    pub fn fcb_engine_process_blocks(e: *mut FcbEngine, input: *const f32, in_stride: usize, output: *mut f32,
+                                     out_stride: usize, current: usize, active: usize, nblocks: usize,
+                                     epi: *const FcbEpilogue, host_io: c_int) -> c_int;
+    // two engines fed the same input (two-stage head + tail0, crossfade A + B) in one launch
+    pub fn fcb_engine_pair_ok(a: *const FcbEngine, b: *const FcbEngine, active: usize) -> c_int;
+    pub fn fcb_engine_process_block_pair_dev(a: *mut FcbEngine, b: *mut FcbEngine, in_dev: *const f32, in_stride: usize,
+                                             out_a: *mut f32, stride_a: usize, epi_a: *const FcbEpilogue,
+                                             out_b: *mut f32, stride_b: usize, epi_b: *const FcbEpilogue,
+                                             current: usize, active: usize) -> c_int;
 }
 
 fn check(rc: c_int) {
@@ -146,6 +159,24 @@ impl Convolution for CudaFFTConvolver {
         let mut processed = 0;
         while processed < output.len() {
             let input_buffer_was_empty = self.input_buffer_fill == 0;
+            // a call that spans several whole blocks: one time-batched pass over as many as the workspace holds
+            let whole = (output.len() - processed) / self.block_size;
+            if input_buffer_was_empty && whole >= 2
+                && unsafe { fcb_engine_multi_block_ok(self.engine, self.current, self.active_seg_count) } != 0
+            {
+                let nb = std::cmp::min(whole, unsafe { fcb_engine_multi_block_capacity(self.engine) });
+                let n = nb * self.block_size;
+                let chunk = &input[processed..processed + n]; // panics like the reference if too short
+                check(unsafe {
+                    fcb_engine_process_blocks(self.engine, chunk.as_ptr(), n, output[processed..].as_mut_ptr(), n,
+                                              self.current, self.active_seg_count, nb, std::ptr::null(), 1)
+                });
+                for _ in 0..nb {
+                    self.current = if self.current > 0 { self.current - 1 } else { self.active_seg_count - 1 };
+                }
+                processed += n;
+                continue;
+            }
             let processing = std::cmp::min(output.len() - processed, self.block_size - self.input_buffer_fill);
             let pos = self.input_buffer_fill;
             let chunk = &input[processed..processed + processing]; // panics like the reference if too short
