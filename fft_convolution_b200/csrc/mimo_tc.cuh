@@ -41,8 +41,9 @@
 // (A 16 KB + B 4 KB, written by TMA) and TC_NL split stages of the small operand ([B_hi | B_lo],
 // 8 KB).  The big operand never returns to shared memory: a splitter thread owns one stream row,
 // reads its 128-byte swizzled row, and writes hi and lo straight into TMEM (tcgen05.st), from where
-// the MMAs take A — shared-memory bandwidth, not HBM, was the first version's limit (ncu: LSU
-// wavefronts 41 % + UMMA operand reads + TMA writes on one 128 B/clk port).
+// the MMAs take A — with both operands in shared memory the one 128 B/clk port carried TMA writes, the split's
+// LDS/STS and the UMMA operand reads (ncu on the first version: LSU wavefronts alone 41 %).  The other early limit
+// was the issue path: see elect_one().  History and numbers: profiles/r01_k4_notes.txt.
 #pragma once
 
 #include <cuda.h>
