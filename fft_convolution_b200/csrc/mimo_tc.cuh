@@ -37,9 +37,10 @@
 // their own accumulator columns (scripts/tc_probe.cu, profiles/r01_tc_probe.txt).
 //
 // One CTA = one (bin, input group): 14 warps — TMA producer, MMA issuer, 8 splitter warps
-// (hi/lo), 4 drain warps (TMEM -> registers -> partial spectra).  Shared memory: TC_NR raw stages
-// (A 16 KB + B 4 KB, written by TMA) and TC_NL split stages of the small operand ([B_hi | B_lo],
-// 8 KB).  The big operand never returns to shared memory: a splitter thread owns one stream row,
+// (hi/lo), 4 drain warps (TMEM -> registers -> partial spectra).  A pipeline stage is TC_BOX = 2 boxes of 16
+// segments (one hand-off per 32 segments: 1.47 -> 1.44 ms at 128 streams, 1.03 -> 0.94 ms at 16).  Shared memory:
+// TC_NR raw stages (per box A 16 KB + B 4 KB, written by TMA) and TC_NL split stages of the small operand (per box
+// [B_hi | B_lo], 8 KB).  The big operand never returns to shared memory: a splitter thread owns one stream row,
 // reads its 128-byte swizzled row, and writes hi and lo straight into TMEM (tcgen05.st), from where
 // the MMAs take A — with both operands in shared memory the one 128 B/clk port carried TMA writes, the split's
 // LDS/STS and the UMMA operand reads (ncu on the first version: LSU wavefronts alone 41 %).  The other early limit
@@ -57,10 +58,14 @@ namespace fcb {
 constexpr int TC_M = 128;    // stream rows of one UMMA (streams are padded to this)
 constexpr int TC_KSEG = 16;  // segments per stage: 16 (re,im) pairs = 32 tf32 = one 128-byte swizzle row
 constexpr int TC_LEAD = 16;  // zero positions in front of every IR row
-constexpr int TC_NR = 8;     // raw (TMA) stages
+#ifndef TC_BOXES
+#define TC_BOXES 2
+#endif
+constexpr int TC_BOX = TC_BOXES;              // 16-segment TMA boxes per pipeline stage (one hand-off per stage)
+constexpr int TC_NR = 8 / TC_BOX;             // raw (TMA) stages
 constexpr int TC_SETS = 1;   // accumulator sets the K steps alternate between (2 measured no faster: MMAs are issue-paced, not dependency-paced)
-constexpr int TC_NL = 4;     // split-operand stages (A hi/lo in TMEM, [B_hi | B_lo] in shared memory)
-constexpr int TC_DRAIN = 4;  // stages per TMEM accumulation interval (K = 128 per drain)
+constexpr int TC_NL = TC_BOX == 1 ? 4 : 3;    // split-operand stages (A hi/lo in TMEM, [B_hi | B_lo] in shared memory)
+constexpr int TC_DRAIN = 4 / TC_BOX;          // stages per TMEM accumulation interval (K = 128 per drain)
 constexpr int TC_SPLIT_WARPS = 8;
 constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + 4);
 
@@ -69,12 +74,15 @@ struct TcCfg {
     static constexpr int N2 = 2 * NOUT;                    // GEMM N (re | im)
     static constexpr int A_BYTES = TC_M * 128;             // 16 KB: 128 rows x 128 B
     static constexpr int B_BYTES = N2 * 128;               // 4 KB at 16 outputs
-    static constexpr int RAW_BYTES = A_BYTES + B_BYTES;    // A | B as loaded
-    static constexpr int LO_BYTES = 2 * B_BYTES;           // B_hi | B_lo
+    static constexpr int BOX_RAW = A_BYTES + B_BYTES;      // one box as loaded: A | B
+    static constexpr int BOX_LO = 2 * B_BYTES;             // one box of the split small operand: B_hi | B_lo
+    static constexpr int RAW_BYTES = TC_BOX * BOX_RAW;
+    static constexpr int LO_BYTES = TC_BOX * BOX_LO;
     static constexpr int SET_COLS = 2 * N2;                // main | cross (hi*lo + lo*hi: both small, one accumulator)
     static constexpr int BUF_COLS = TC_SETS * SET_COLS;
     static constexpr int ACC_COLS = 2 * BUF_COLS;          // double-buffered against the drain
-    static constexpr int A_COLS = 4 * TC_KSEG;             // per split stage: 32 columns of hi, 32 of lo
+    static constexpr int BOX_COLS = 4 * TC_KSEG;           // per box: 32 columns of hi, 32 of lo
+    static constexpr int A_COLS = TC_BOX * BOX_COLS;
     static constexpr int TMEM_NEED = ACC_COLS + TC_NL * A_COLS;
     static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
     static constexpr size_t SMEM = (size_t)TC_NR * RAW_BYTES + (size_t)TC_NL * LO_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -227,7 +235,8 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
     const int in_lo = a.n_in * g / a.groups, in_hi = a.n_in * (g + 1) / a.groups;
     const TcSpan span(a);
     const int cpi = span.per_input();
-    const int total = cpi * (in_hi - in_lo);
+    const int chunks = cpi * (in_hi - in_lo);             // 16-segment boxes of this CTA
+    const int total = (chunks + TC_BOX - 1) / TC_BOX;     // pipeline stages
 
     if (tid == 0) {
         for (int s = 0; s < TC_NR; s++) {
@@ -260,13 +269,21 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
             const int s = t % TC_NR;
             mbar_wait(&empty_raw[s], ((t / TC_NR) & 1) ^ 1);
             unsigned char *st = smem + s * Cfg::RAW_BYTES;
-            const int in = in_lo + t / cpi;
-            int blk, copy, pos0;
-            span.chunk(t % cpi, blk, copy, pos0);
             if (elect_one()) {
-                mbar_expect_tx(&full_raw[s], a.rows_pad * 128 + Cfg::B_BYTES);
-                tma_load_4d(st, &tm_ring, 0, 0, sg * a.nblk + blk, bin * a.n_in + in, &full_raw[s]);
-                tma_load_3d(st + Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 2 * pos0, og * N2, bin * a.n_in + in, &full_raw[s]);
+                mbar_expect_tx(&full_raw[s], TC_BOX * (a.rows_pad * 128 + Cfg::B_BYTES));
+#pragma unroll
+                for (int bx = 0; bx < TC_BOX; bx++) {
+                    const int q = t * TC_BOX + bx;
+                    int in = in_lo, blk = a.stream_groups * a.nblk, copy = 0, pos0 = 1 << 20; // past both tensors: zero fill
+                    if (q < chunks) {
+                        in = in_lo + q / cpi;
+                        span.chunk(q % cpi, blk, copy, pos0);
+                        blk += sg * a.nblk;
+                    }
+                    tma_load_4d(st + bx * Cfg::BOX_RAW, &tm_ring, 0, 0, blk, bin * a.n_in + in, &full_raw[s]);
+                    tma_load_3d(st + bx * Cfg::BOX_RAW + Cfg::A_BYTES, copy ? &tm_ir1 : &tm_ir0, 2 * pos0, og * N2, bin * a.n_in + in,
+                                &full_raw[s]);
+                }
             }
             __syncwarp();
         }
@@ -282,15 +299,17 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
             if (elect_one()) {
                 const uint32_t lo = smem_u32(smem_lo + sl * Cfg::LO_BYTES);
                 const uint32_t d_buf = tmem + b * Cfg::BUF_COLS;
-                const uint32_t a_hi = tmem + Cfg::ACC_COLS + sl * Cfg::A_COLS, a_lo = a_hi + 2 * TC_KSEG;
 #pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                    const uint64_t b_hl = umma_desc_k128(lo + ks * 32);
-                    // [main | cross] (+)= A_hi * [B_hi | B_lo]^T ;  cross += A_lo * B_hi^T, in set ks % TC_SETS
-                    const uint32_t d_set = d_buf + (ks % TC_SETS) * Cfg::SET_COLS;
-                    const uint32_t acc_on = (first && ks < TC_SETS) ? 0u : 1u;
-                    umma_tf32_ts(d_set, a_hi + ks * 8, b_hl, idesc_wide, acc_on);
-                    umma_tf32_ts(d_set + N2, a_lo + ks * 8, b_hl, idesc_narrow, 1u);
+                for (int bx = 0; bx < TC_BOX; bx++) {
+                    const uint32_t a_hi = tmem + Cfg::ACC_COLS + sl * Cfg::A_COLS + bx * Cfg::BOX_COLS, a_lo = a_hi + 2 * TC_KSEG;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const uint64_t b_hl = umma_desc_k128(lo + bx * Cfg::BOX_LO + ks * 32);
+                        // [main | cross] (+)= A_hi * [B_hi | B_lo]^T ;  cross += A_lo * B_hi^T
+                        const uint32_t acc_on = (first && bx == 0 && ks == 0) ? 0u : 1u;
+                        umma_tf32_ts(d_buf, a_hi + ks * 8, b_hl, idesc_wide, acc_on);
+                        umma_tf32_ts(d_buf + N2, a_lo + ks * 8, b_hl, idesc_narrow, 1u);
+                    }
                 }
                 umma_commit(&empty_lo[sl]);
                 if (last) umma_commit(&acc_full[b]);
@@ -315,46 +334,51 @@ k_mimo_tc(TcArgs a, const __grid_constant__ CUtensorMap tm_ring, const __grid_co
         };
         for (int t = grp; t < total; t += TC_SPLIT_WARPS / 4) {
             const int sr = t % TC_NR, sl = t % TC_NL;
-            const unsigned char *rawA = smem + sr * Cfg::RAW_BYTES + row * 128;
-            const float4 *rawB = reinterpret_cast<const float4 *>(smem + sr * Cfg::RAW_BYTES + Cfg::A_BYTES);
-            float4 *hiB = reinterpret_cast<float4 *>(smem_lo + sl * Cfg::LO_BYTES);
-            float4 *loB = reinterpret_cast<float4 *>(smem_lo + sl * Cfg::LO_BYTES + Cfg::B_BYTES);
             mbar_wait(&full_raw[sr], (t / TC_NR) & 1);
-            float4 v[8], w[Cfg::B_BYTES / 16 / 128];
-            if (live) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) // logical 16-byte chunk c of a row sits at chunk c ^ (row & 7)
-                    v[j] = *reinterpret_cast<const float4 *>(rawA + ((j ^ (row & 7)) << 4));
-            }
+            for (int bx = 0; bx < TC_BOX; bx++) {
+                const unsigned char *rawA = smem + sr * Cfg::RAW_BYTES + bx * Cfg::BOX_RAW + row * 128;
+                const float4 *rawB = reinterpret_cast<const float4 *>(smem + sr * Cfg::RAW_BYTES + bx * Cfg::BOX_RAW + Cfg::A_BYTES);
+                float4 *hiB = reinterpret_cast<float4 *>(smem_lo + sl * Cfg::LO_BYTES + bx * Cfg::BOX_LO);
+                float4 *loB = reinterpret_cast<float4 *>(smem_lo + sl * Cfg::LO_BYTES + bx * Cfg::BOX_LO + Cfg::B_BYTES);
+                float4 v[8], w[Cfg::B_BYTES / 16 / 128];
+                if (live) {
 #pragma unroll
-            for (int j = 0; j < Cfg::B_BYTES / 16 / 128; j++) w[j] = rawB[gtid + 128 * j];
-            mbar_arrive(&empty_raw[sr]); // the raw stage is in registers now
-            mbar_wait(&empty_lo[sl], ((t / TC_NL) & 1) ^ 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::ACC_COLS + sl * Cfg::A_COLS;
-            if (live) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float4 x = v[4 * h + j];
-                        hi[4 * j + 0] = __float_as_uint(x.x), hi[4 * j + 1] = __float_as_uint(x.y);
-                        hi[4 * j + 2] = __float_as_uint(x.z), hi[4 * j + 3] = __float_as_uint(x.w);
-                        lo2(x.x, x.y, lo[4 * j + 0], lo[4 * j + 1]);
-                        lo2(x.z, x.w, lo[4 * j + 2], lo[4 * j + 3]);
-                    }
-                    tmem_st16(ta + 16 * h, hi);
-                    tmem_st16(ta + 2 * TC_KSEG + 16 * h, lo);
+                    for (int j = 0; j < 8; j++) // logical 16-byte chunk c of a row sits at chunk c ^ (row & 7)
+                        v[j] = *reinterpret_cast<const float4 *>(rawA + ((j ^ (row & 7)) << 4));
                 }
-            }
 #pragma unroll
-            for (int j = 0; j < Cfg::B_BYTES / 16 / 128; j++) {
-                hiB[gtid + 128 * j] = w[j];
-                uint4 l;
-                lo2(w[j].x, w[j].y, l.x, l.y);
-                lo2(w[j].z, w[j].w, l.z, l.w);
-                reinterpret_cast<uint4 *>(loB)[gtid + 128 * j] = l;
+                for (int j = 0; j < Cfg::B_BYTES / 16 / 128; j++) w[j] = rawB[gtid + 128 * j];
+                if (bx == TC_BOX - 1) mbar_arrive(&empty_raw[sr]); // the raw stage is in registers now
+                if (bx == 0) {
+                    mbar_wait(&empty_lo[sl], ((t / TC_NL) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::ACC_COLS + sl * Cfg::A_COLS + bx * Cfg::BOX_COLS;
+                if (live) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float4 x = v[4 * h + j];
+                            hi[4 * j + 0] = __float_as_uint(x.x), hi[4 * j + 1] = __float_as_uint(x.y);
+                            hi[4 * j + 2] = __float_as_uint(x.z), hi[4 * j + 3] = __float_as_uint(x.w);
+                            lo2(x.x, x.y, lo[4 * j + 0], lo[4 * j + 1]);
+                            lo2(x.z, x.w, lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                        tmem_st16(ta + 16 * h, hi);
+                        tmem_st16(ta + 2 * TC_KSEG + 16 * h, lo);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < Cfg::B_BYTES / 16 / 128; j++) {
+                    hiB[gtid + 128 * j] = w[j];
+                    uint4 l;
+                    lo2(w[j].x, w[j].y, l.x, l.y);
+                    lo2(w[j].z, w[j].w, l.z, l.w);
+                    reinterpret_cast<uint4 *>(loB)[gtid + 128 * j] = l;
+                }
             }
             if (live) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
