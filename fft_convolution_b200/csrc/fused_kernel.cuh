@@ -516,7 +516,7 @@ k_block_fused_shared(FusedArgs fa, const float2 *__restrict__ tw)
 {
     using Cfg = FusedSharedCfg<LOGB, G>;
     using P = FftPlan<LOGB>;
-    constexpr int B = Cfg::B, CPB = Cfg::CPB, NSLOT = Cfg::NSLOT, R = Cfg::R, ROWS = Cfg::ROWS, NST = Cfg::NST;
+    constexpr int B = Cfg::B, NSLOT = Cfg::NSLOT, R = Cfg::R, ROWS = Cfg::ROWS, NST = Cfg::NST;
     constexpr int TX = B / 2;
     constexpr int T = P::T, E = P::E;
     constexpr int FPASS = (NSLOT * T + 255) / 256; // FFT rounds when the transforms need more than 256 threads
