@@ -986,43 +986,29 @@ extern "C" int fcb_engine_multi_block_reserve(fcb_engine *e, size_t nblocks)
 // in / out: device pointers, or host pointers when host_io (staged through the workspace).  Caller rotates
 // `current` nblocks times afterwards (src/fft_convolver.rs:301-305).  Output is bit-identical to nblocks calls of
 // fcb_engine_process_block_dev.
-extern "C" int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
-                                         size_t current, size_t active, size_t nblocks, const fcb_epilogue *epi,
-                                         int host_io)
+// the time-batched pass for channels [c0, c0 + nc) on stream st; din / dout point at channel c0's first sample (device)
+static int process_blocks_range(fcb_engine *e, cudaStream_t st, size_t c0, size_t nc, const float *din, size_t dstride_in,
+                                float *dout, size_t dstride_out, size_t current, size_t active, size_t NB,
+                                const fcb_epilogue *epi)
 {
-    FCB_TRY(check_sched(e, current, active, "process_blocks"));
-    if (!in || !out) return fail(FCB_ERR_ARG, "process_blocks: NULL argument");
-    if (!fcb_engine_multi_block_ok(e, current, active)) return fail(FCB_ERR_UNSUPPORTED, "process_blocks: not applicable here");
-    FCB_CUDA(cudaSetDevice(e->device));
-    if (nblocks == 0) return FCB_OK;
-    if (nblocks > mb_limit(e)) return fail(FCB_ERR_ARG, "process_blocks: %zu blocks exceed the workspace limit (%zu)", nblocks, mb_limit(e));
-    FCB_TRY(mb_ensure(e, nblocks));
-    const size_t B = e->B, C = e->C, NB = nblocks;
-    cudaStream_t st = e->stream;
-    const float *din = in;
-    float *dout = out;
-    size_t dstride_in = in_stride, dstride_out = out_stride;
-    if (host_io) {
-        FCB_CUDA(cudaMemcpy2DAsync(e->mb_in, NB * B * sizeof(float), in, in_stride * sizeof(float), NB * B * sizeof(float), C,
-                                   cudaMemcpyHostToDevice, st));
-        din = e->mb_in;
-        dout = e->mb_out;
-        dstride_in = dstride_out = NB * B;
-    }
+    const size_t B = e->B;
+    const long long ir_off = e->shared_ir ? 0 : (long long)(c0 * e->S * B);
+    float2 *xnew = e->mb_xnew + c0 * NB * B, *premul = e->mb_premul + c0 * NB * B;
+    float *y = e->mb_y + c0 * NB * 2 * B;
     // K1 for every (channel, block) -> xnew[c][d]
-    FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, din, (long long)dstride_in, (int)(NB * B), e->mb_xnew,
-                                                          (long long)(NB * B), (int)NB, (long long)(C * NB))));
+    FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, din, (long long)dstride_in, (int)(NB * B), xnew, (long long)(NB * B),
+                                                          (int)NB, (long long)(nc * NB), st)));
     MacTimeArgs m{};
-    m.ir = e->ir;
+    m.ir = e->ir + ir_off;
     m.ir_stride = e->ir_stride();
-    m.ring = e->ring;
+    m.ring = e->ring + c0 * e->ring_stride();
     m.ring_stride = e->ring_stride();
-    m.xnew = e->mb_xnew;
-    m.premul = e->mb_premul;
+    m.xnew = xnew;
+    m.premul = premul;
     m.current = (int)current;
     m.active = (int)active;
     m.nblocks = (int)NB;
-    m.nchan = (long long)C;
+    m.nchan = (long long)nc;
     cudaEvent_t prof_stop = nullptr;
     const bool profiled = prof_before(st, &prof_stop) != nullptr;
 #define FCB_MAC_TIME_CASE(LB)                                                      \
@@ -1040,34 +1026,111 @@ extern "C" int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t 
     if (profiled) cudaEventRecord(prof_stop, st);
     // K3 in raw mode: conv_d = pre_multiplied_d + X_d * H_0, inverse FFT, /N -> y[c][d][2B]
     IfftArgs a{};
-    a.ring_cur = e->mb_xnew;
+    a.ring_cur = xnew;
     a.ring_stride = (long long)B;
-    a.ir0 = e->ir;
+    a.ir0 = e->ir + ir_off;
     a.ir_stride = e->ir_stride();
     a.ir_div = (long long)NB;
-    a.premul = e->mb_premul;
-    a.raw_out = e->mb_y;
-    a.nchan = (long long)(C * NB);
-    FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_inverse<LB>(e, a)));
+    a.premul = premul;
+    a.raw_out = y;
+    a.nchan = (long long)(nc * NB);
+    FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_inverse<LB>(e, a, st)));
     // overlap-add across the call's blocks (+ epilogue), then the new overlap and the ring
     fcb_epilogue ep;
     memset(&ep, 0, sizeof ep);
-    if (epi) ep = *epi;
-    const long long nout = (long long)(C * NB * B);
-    k_ola_time<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(e->mb_y, e->overlap, dout, (long long)dstride_out, (int)B, (int)NB, nout, ep);
-    FCB_CUDA(cudaMemcpy2DAsync(e->overlap, B * sizeof(float), e->mb_y + (NB - 1) * 2 * B + B, NB * 2 * B * sizeof(float),
-                               B * sizeof(float), C, cudaMemcpyDeviceToDevice, st));
+    if (epi) {
+        ep = *epi;
+        if (ep.add0) ep.add0 += c0 * epi->add_stride;
+        if (ep.add1) ep.add1 += c0 * epi->add_stride;
+        if (ep.mix_other) ep.mix_other += c0 * epi->mix_stride;
+    }
+    const long long nout = (long long)(nc * NB * B);
+    k_ola_time<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(y, e->overlap + c0 * B, dout, (long long)dstride_out, (int)B, (int)NB, nout, ep);
+    FCB_CUDA(cudaMemcpy2DAsync(e->overlap + c0 * B, B * sizeof(float), y + (NB - 1) * 2 * B + B, NB * 2 * B * sizeof(float),
+                               B * sizeof(float), nc, cudaMemcpyDeviceToDevice, st));
     const size_t first = NB > active ? NB - active : 0;
-    const long long nring = (long long)(C * (NB - first) * (B / 2));
-    k_ring_update<<<(unsigned)((nring + 255) / 256), 256, 0, st>>>(e->mb_xnew, e->ring, e->ring_stride(), (int)B, (int)NB, (int)current,
-                                                                   (int)active, (int)first, nring);
+    const long long nring = (long long)(nc * (NB - first) * (B / 2));
+    k_ring_update<<<(unsigned)((nring + 255) / 256), 256, 0, st>>>(xnew, e->ring + c0 * e->ring_stride(), e->ring_stride(), (int)B, (int)NB,
+                                                                   (int)current, (int)active, (int)first, nring);
     g_launches += 2;
     FCB_CUDA(cudaGetLastError());
-    if (host_io) {
-        FCB_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float), e->mb_out, NB * B * sizeof(float), NB * B * sizeof(float), C,
+    return FCB_OK;
+}
+
+static int pipe_streams_ensure(fcb_engine *e)
+{
+    if (e->pipe_start) return FCB_OK;
+    FCB_CUDA(cudaEventCreateWithFlags(&e->pipe_start, cudaEventDisableTiming));
+    for (int i = 0; i < fcb_engine::NPIPE; i++) {
+        FCB_CUDA(cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking));
+        FCB_CUDA(cudaEventCreateWithFlags(&e->pipe_done[i], cudaEventDisableTiming));
+    }
+    return FCB_OK;
+}
+
+// in / out: device pointers, or host pointers when host_io (staged through the workspace; with 1024 channels or more
+// the channels are cut into groups whose H2D copy, pass and D2H copy overlap on separate streams).  Caller rotates
+// `current` nblocks times afterwards (src/fft_convolver.rs:301-305).  Output is bit-identical to nblocks calls of
+// fcb_engine_process_block_dev.
+extern "C" int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
+                                         size_t current, size_t active, size_t nblocks, const fcb_epilogue *epi,
+                                         int host_io)
+{
+    FCB_TRY(check_sched(e, current, active, "process_blocks"));
+    if (!in || !out) return fail(FCB_ERR_ARG, "process_blocks: NULL argument");
+    if (!fcb_engine_multi_block_ok(e, current, active)) return fail(FCB_ERR_UNSUPPORTED, "process_blocks: not applicable here");
+    FCB_CUDA(cudaSetDevice(e->device));
+    if (nblocks == 0) return FCB_OK;
+    if (nblocks > mb_limit(e)) return fail(FCB_ERR_ARG, "process_blocks: %zu blocks exceed the workspace limit (%zu)", nblocks, mb_limit(e));
+    FCB_TRY(mb_ensure(e, nblocks));
+    const size_t B = e->B, C = e->C, NB = nblocks, row = NB * B;
+    cudaStream_t st = e->stream;
+    if (!host_io) return process_blocks_range(e, st, 0, C, in, in_stride, out, out_stride, current, active, NB, epi);
+    if (C < 1024) {
+        FCB_CUDA(cudaMemcpy2DAsync(e->mb_in, row * sizeof(float), in, in_stride * sizeof(float), row * sizeof(float), C,
+                                   cudaMemcpyHostToDevice, st));
+        FCB_TRY(process_blocks_range(e, st, 0, C, e->mb_in, row, e->mb_out, row, current, active, NB, epi));
+        FCB_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float), e->mb_out, row * sizeof(float), row * sizeof(float), C,
                                    cudaMemcpyDeviceToHost, st));
         FCB_CUDA(cudaStreamSynchronize(st));
+        return FCB_OK;
     }
+    // many channels: groups of channels, all H2D copies on one stream running ahead, the passes on two compute streams
+    // as their input lands, the D2H copies on a fourth stream — the PCIe traffic hides under the HBM-bound passes
+    FCB_TRY(pipe_streams_ensure(e));
+    const size_t ngroups = 8, per = (C + ngroups - 1) / ngroups;
+    while (e->pipe_in.size() < ngroups) { // grows on first use only
+        cudaEvent_t a = nullptr, b = nullptr;
+        FCB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        FCB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        e->pipe_in.push_back(a);
+        e->pipe_out.push_back(b);
+    }
+    cudaStream_t s_in = e->pipe[0], s_out = e->pipe[1];
+    FCB_CUDA(cudaEventRecord(e->pipe_start, st));
+    for (int i = 0; i < fcb_engine::NPIPE; i++) FCB_CUDA(cudaStreamWaitEvent(e->pipe[i], e->pipe_start, 0));
+    for (size_t g = 0; g < ngroups; g++) {
+        const size_t c0 = g * per;
+        if (c0 >= C) break;
+        const size_t nc = C - c0 < per ? C - c0 : per;
+        cudaStream_t sc = e->pipe[2 + g % (fcb_engine::NPIPE - 2)];
+        FCB_CUDA(cudaMemcpy2DAsync(e->mb_in + c0 * row, row * sizeof(float), in + c0 * in_stride, in_stride * sizeof(float),
+                                   row * sizeof(float), nc, cudaMemcpyHostToDevice, s_in));
+        FCB_CUDA(cudaEventRecord(e->pipe_in[g], s_in));
+        FCB_CUDA(cudaStreamWaitEvent(sc, e->pipe_in[g], 0));
+        FCB_TRY(process_blocks_range(e, sc, c0, nc, e->mb_in + c0 * row, row, e->mb_out + c0 * row, row, current, active, NB, epi));
+        FCB_CUDA(cudaEventRecord(e->pipe_out[g], sc));
+        FCB_CUDA(cudaStreamWaitEvent(s_out, e->pipe_out[g], 0));
+        FCB_CUDA(cudaMemcpy2DAsync(out + c0 * out_stride, out_stride * sizeof(float), e->mb_out + c0 * row, row * sizeof(float),
+                                   row * sizeof(float), nc, cudaMemcpyDeviceToHost, s_out));
+    }
+    FCB_CUDA(cudaEventRecord(e->pipe_done[1], s_out));
+    FCB_CUDA(cudaStreamWaitEvent(st, e->pipe_done[1], 0));
+    for (int i = 2; i < fcb_engine::NPIPE; i++) { // the engine stream also orders after the compute streams
+        FCB_CUDA(cudaEventRecord(e->pipe_done[i], e->pipe[i]));
+        FCB_CUDA(cudaStreamWaitEvent(st, e->pipe_done[i], 0));
+    }
+    FCB_CUDA(cudaStreamSynchronize(st));
     return FCB_OK;
 }
 
@@ -1082,13 +1145,7 @@ extern "C" int fcb_engine_process_block_host(fcb_engine *e, const float *in, siz
     if (!in || !out) return fail(FCB_ERR_ARG, "process_block_host: NULL argument");
     if (active == 0) return FCB_OK;
     FCB_CUDA(cudaSetDevice(e->device));
-    if (!e->pipe_start) { // created on first use, outside the steady state
-        FCB_CUDA(cudaEventCreateWithFlags(&e->pipe_start, cudaEventDisableTiming));
-        for (int i = 0; i < fcb_engine::NPIPE; i++) {
-            FCB_CUDA(cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking));
-            FCB_CUDA(cudaEventCreateWithFlags(&e->pipe_done[i], cudaEventDisableTiming));
-        }
-    }
+    FCB_TRY(pipe_streams_ensure(e)); // created on first use, outside the steady state
     const size_t B = e->B, C = e->C;
     size_t G = group_channels ? group_channels : (size_t)g_pipe_group.load();
     if (G > C) G = C;

@@ -43,6 +43,7 @@ def _run_calls(F, h, B, L, x, calls, multi):
     (1, 16, 16 * 40, [16 * 64, 16 * 3, 16 * 33]),                                    # small blocks, long calls
     (5, 512, 512 * 12 + 100, [512 * 4, 512 * 3, 512 * 2, 512, 512 * 5]),             # the headline block size
     (2, 1024, 1024 * 5, [1024 * 3, 1024 * 6]),                                       # above the fused-kernel range
+    (1100, 32, 32 * 6 + 1, [32 * 5, 32 * 2, 32 * 3]),                                # >= 1024 channels: grouped, copies overlap the passes
 ])
 def test_multi_block_calls_are_bit_identical_to_block_by_block(F, C, B, L, calls):
     h = np.stack([oracle.gen_ir(c, 0, L) for c in range(C)])
