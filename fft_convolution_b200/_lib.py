@@ -141,6 +141,7 @@ SIGNATURES = {
     "fcb_mimo_sync": (_i, [_vp]),
     "fcb_mimo_stream": (_vp, [_vp]),
     "fcb_debug_tc_stages": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "fcb_debug_mac_tile_plan": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "fcb_mimo_uses_tensor_cores": (_i, [_vp]),
     "fcb_mimo_peer_export": (_i, [_vp, _vp]),
     "fcb_mimo_peer_attach": (_i, [_vp, _vp]),

@@ -537,6 +537,14 @@ int mac_tile_plan(int logb, int n_in, int n_out, int n_streams, int nsegs, int *
     return FCB_OK;
 }
 
+} // namespace fcb
+// test hook (host only): the segment chunking the matrix kernel would use for this problem
+extern "C" int fcb_debug_mac_tile_plan(int logb, int n_in, int n_out, int n_streams, int nsegs, int *zchunks, int *zlen)
+{
+    return fcb::mac_tile_plan(logb, n_in, n_out, n_streams, nsegs, zchunks, zlen);
+}
+namespace fcb {
+
 int run_mac_tile(int logb, cudaStream_t st, MacTileArgs a, int *zchunks_out)
 {
     const int nsegs = a.seg_hi - a.seg_lo;

@@ -313,6 +313,8 @@ int fcb_mimo_peer_attach(fcb_mimo *m, const unsigned char *handles /* [shard_cou
 /* same-process variant: this shard's inbox as a device pointer / attach with the G inbox pointers */
 void *fcb_mimo_peer_inbox(fcb_mimo *m);
 int fcb_mimo_peer_attach_ptrs(fcb_mimo *m, void *const *inboxes);
+/* test hook (host only): segment chunks (count, segments per chunk) the CUDA-core matrix kernel uses for a problem */
+int fcb_debug_mac_tile_plan(int logb, int n_in, int n_out, int n_streams, int nsegs, int *zchunks, int *zlen);
 /* test hook (host only): K4's pipeline stages for one input — ring slot block, IR copy (0 / 1 = shifted by one
  * position) and IR position paired with the block's first slot; returns the stage count */
 int fcb_debug_tc_stages(int S, int current, int seg_lo, int seg_hi, int max_stages, int *blk, int *copy, int *pos0);
