@@ -189,6 +189,9 @@ struct fcb_mimo {
     size_t ring_t_elems() const { return B * n_in * stream_groups * nblk * nsp * TC_KSEG; }
     int tc_groups = 1;
     CUtensorMap tm_ring, tm_ir[2];
+    // K1 runs beside the MAC: the MAC only reads ring slots older than the current block (segments >= 1)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_k1 = nullptr;
     // peer exchange (see PeerPub)
     size_t shard_index = 0, shard_count = 1;
     unsigned char *inbox = nullptr;      // [2][G][n_conv] float2 then [2][G] flags, one allocation (IPC-exported)
@@ -241,6 +244,9 @@ extern "C" void fcb_mimo_destroy(fcb_mimo *m)
         if (m->peer_opened[g]) cudaIpcCloseMemHandle(m->peer_base[g]);
     cudaFree(m->inbox);
     cudaFree(m->peer_done);
+    if (m->side) cudaStreamDestroy(m->side);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_k1) cudaEventDestroy(m->ev_k1);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -329,6 +335,10 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
     const size_t per = m->L ? m->L : 1, cap = (size_t)16 << 20;
     m->stage_floats = pairs * per < cap ? pairs * per : (cap / per ? (cap / per) * per : per);
     if (!rc) rc = mimo_alloc((void **)&m->stage, m->stage_floats * sizeof(float), m->stream);
+    if (!rc && (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&m->ev_k1, cudaEventDisableTiming) != cudaSuccess))
+        rc = fail(FCB_ERR_CUDA, "mimo: side stream / events");
     if (!rc && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = fail(FCB_ERR_CUDA, "sync failed");
     if (rc) {
         fcb_mimo_destroy(m);
@@ -436,8 +446,13 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
         return FCB_OK;
     }
     const long long ring_stride = (long long)(m->S * B);
-    FCB_TRY(run_forward(m->logb, m->tw, m->stream, in_dev, (long long)in_stride, (int)B, m->ring + m->current * B,
+    // K1 writes ring slot `current`; the MAC below reads only the older slots (segments >= 1) and the reduce kernel is
+    // the first to need the new spectra (segment 0): K1 runs on a side stream beside the MAC and joins before the reduce
+    FCB_CUDA(cudaEventRecord(m->ev_fork, m->stream)); // after the previous block's last reader of that slot
+    FCB_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+    FCB_TRY(run_forward(m->logb, m->tw, m->side, in_dev, (long long)in_stride, (int)B, m->ring + m->current * B,
                         ring_stride, 1, (long long)(ns * m->n_in)));
+    FCB_CUDA(cudaEventRecord(m->ev_k1, m->side));
     const int seg_lo = (int)(m->seg_lo > 1 ? m->seg_lo : 1), seg_hi = (int)m->seg_hi;
     const long long ir_stride = (long long)(m->rows() * B);
     int zchunks = 1;
@@ -482,6 +497,7 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
         a.ring_mod = (long long)m->n_in;
         FCB_TRY(run_mac(m->logb, m->stream, a));
     }
+    FCB_CUDA(cudaStreamWaitEvent(m->stream, m->ev_k1, 0));
     const bool owns0 = m->seg_lo == 0 && m->seg_hi > 0;
     const long long n_so = (long long)(ns * m->n_out);
     k_mimo_reduce<<<(unsigned)(n_so * ((B + 31) / 32)), dim3(32, 8), 0, m->stream>>>(
