@@ -3,7 +3,7 @@
 Same names and argument meaning as the reference:
     X.init(response, max_block_size, max_response_length) -> X
     x.update(response); x.reset(); x.process(input, output)
-for X in FFTConvolver (src/fft_convolver.rs:100-321), TwoStageFFTConvolver (:337-540) and
+for X in FFTConvolver (src/fft_convolver.rs:86-307), TwoStageFFTConvolver (:323-526) and
 CrossfadeConvolver (src/crossfade_convolver.rs:3-105); contract violations that panic in the
 reference raise ConvolutionPanic, the two `todo!()` methods raise NotYetImplemented.
 
@@ -77,7 +77,7 @@ class _Base:
 
 
 class FFTConvolver(_Base):
-    """Uniformly partitioned convolver; reference: src/fft_convolver.rs:100-321."""
+    """Uniformly partitioned convolver; reference: src/fft_convolver.rs:86-307."""
     _free = "fcb_fftconv_free"
 
     @classmethod
@@ -158,7 +158,7 @@ class FFTConvolver(_Base):
 
 
 class TwoStageFFTConvolver(_Base):
-    """Two-stage (head/tail) partitioned convolver; reference: src/fft_convolver.rs:337-540."""
+    """Two-stage (head/tail) partitioned convolver; reference: src/fft_convolver.rs:323-526."""
     _free = "fcb_twostage_free"
 
     @classmethod
@@ -368,5 +368,5 @@ class MimoConvolver:
 
 
 def compute_tail_block_size(head_len: int, response_len: int) -> int:
-    """src/fft_convolver.rs:534-540 (f32 arithmetic)."""
+    """src/fft_convolver.rs:520-526 (f32 arithmetic)."""
     return _lib.load().fcb_compute_tail_block_size(head_len, response_len)

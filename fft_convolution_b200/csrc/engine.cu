@@ -1,7 +1,7 @@
 // engine.cu — layer 1 of the C ABI: device state of C lock-step FFTConvolver channels and the
 // stage launches K1 (forward FFT), K2 (delay-line MAC), K3 (inverse FFT + overlap-add +
 // epilogues), K5 (IR preparation).  The caller (Rust host or the C++ mirror in host_mirror.cu)
-// owns the scheduler scalars `current`, `fill`, `active` (src/fft_convolver.rs:113-115,105).
+// owns the scheduler scalars `current`, `fill`, `active` (src/fft_convolver.rs:99-101, :91).
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -237,7 +237,7 @@ template <int LOGB>
 static int launch_mac_t(const MacArgs &a, cudaStream_t st)
 {
     constexpr int B = 1 << LOGB;
-    if (a.seg_hi <= a.seg_lo) { // no segment to accumulate: pre_multiplied = 0 (src/fft_convolver.rs:259)
+    if (a.seg_hi <= a.seg_lo) { // no segment to accumulate: pre_multiplied = 0 (src/fft_convolver.rs:245)
         FCB_CUDA(cudaMemsetAsync(a.premul, 0, (size_t)a.nchan * B * sizeof(float2), st));
         return FCB_OK;
     }
@@ -645,7 +645,7 @@ extern "C" int fcb_engine_create(const fcb_engine_desc *d, fcb_engine **out)
     if (!d || !out) return fail(FCB_ERR_ARG, "fcb_engine_create: NULL argument");
     *out = nullptr;
     if (d->channels == 0) return fail(FCB_ERR_ARG, "fcb_engine_create: channels must be >= 1");
-    size_t B = next_power_of_two(d->block_size); // src/fft_convolver.rs:129
+    size_t B = next_power_of_two(d->block_size); // src/fft_convolver.rs:115
     if (B > 16384) return fail(FCB_ERR_UNSUPPORTED, "block size %zu > 16384 not supported", B);
     FCB_CUDA(cudaSetDevice(d->device));
     fcb_engine *e = new fcb_engine();
@@ -654,7 +654,7 @@ extern "C" int fcb_engine_create(const fcb_engine_desc *d, fcb_engine **out)
     e->B = B;
     e->logb = ilog2(B);
     e->L = d->max_response_length;
-    e->S = (size_t)std::ceil((double)e->L / (double)B); // :131
+    e->S = (size_t)std::ceil((double)e->L / (double)B); // :117
     e->shared_ir = d->shared_ir != 0;
     if (d->stream) {
         e->stream = (cudaStream_t)d->stream;
@@ -765,9 +765,9 @@ static int set_ir_common(fcb_engine *e, size_t chan0, size_t nchan, const float 
         return fail(FCB_ERR_ARG, "set_ir: channel range [%zu,%zu) outside %zu IR channels", chan0, chan0 + nchan,
                     e->ir_channels());
     if (len && !irs) return fail(FCB_ERR_ARG, "set_ir: NULL impulse response");
-    if (e->S == 0 || nchan == 0) return FCB_OK; // src/fft_convolver.rs:195-197
+    if (e->S == 0 || nchan == 0) return FCB_OK; // src/fft_convolver.rs:181-183
     FCB_CUDA(cudaSetDevice(e->device));
-    if (is_update) { // :199-202 (fft_buffer and conv are transient on the device)
+    if (is_update) { // :185-188 (fft_buffer and conv are transient on the device)
         size_t c0 = e->shared_ir ? 0 : chan0, nc = e->shared_ir ? e->C : nchan;
         FCB_CUDA(cudaMemsetAsync(e->premul + c0 * e->B, 0, nc * e->B * sizeof(float2), e->stream));
         FCB_CUDA(cudaMemsetAsync(e->overlap + c0 * e->B, 0, nc * e->B * sizeof(float), e->stream));
@@ -839,7 +839,7 @@ static int check_sched(const fcb_engine *e, size_t current, size_t active, const
 {
     if (!e) return fail(FCB_ERR_ARG, "%s: NULL engine", who);
     // `current` may legitimately exceed `active` after update() shrank the IR (quirk of
-    // src/fft_convolver.rs:204,262,301-305): ring slots are then re-read modulo `active`
+    // src/fft_convolver.rs:190, :248, :287-291): ring slots are then re-read modulo `active`
     if (active > e->S || (e->S && current >= e->S))
         return fail(FCB_ERR_ARG, "%s: current %zu / active %zu outside seg_count %zu", who, current, active, e->S);
     return FCB_OK;
@@ -918,7 +918,7 @@ extern "C" int fcb_engine_process_block_dev(fcb_engine *e, const float *in_dev, 
     FCB_CUDA(cudaSetDevice(e->device));
     if (fused_applicable(e, active))
         return run_block_fused(e, e->stream, 0, e->C, in_dev, in_stride, out_dev, out_stride, current, active, epi);
-    // K1 straight from the caller's block: a full block leaves the input buffer empty again (:294-295).
+    // K1 straight from the caller's block: a full block leaves the input buffer empty again (:280-281).
     // (Running K1 on a side stream underneath K2 was measured in round 1: no gain — K1 then competes
     // with the HBM-bound K2 for the same bandwidth.)
     FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, in_dev, (long long)in_stride, (int)e->B,
@@ -992,7 +992,7 @@ extern "C" int fcb_engine_multi_block_reserve(fcb_engine *e, size_t nblocks)
 }
 
 // in / out: device pointers, or host pointers when host_io (staged through the workspace).  Caller rotates
-// `current` nblocks times afterwards (src/fft_convolver.rs:301-305).  Output is bit-identical to nblocks calls of
+// `current` nblocks times afterwards (src/fft_convolver.rs:287-291).  Output is bit-identical to nblocks calls of
 // fcb_engine_process_block_dev.
 // the time-batched pass for channels [c0, c0 + nc) on stream st; din / dout point at channel c0's first sample (device)
 static int process_blocks_range(fcb_engine *e, cudaStream_t st, size_t c0, size_t nc, const float *din, size_t dstride_in,
@@ -1078,7 +1078,7 @@ static int pipe_streams_ensure(fcb_engine *e)
 
 // in / out: device pointers, or host pointers when host_io (staged through the workspace; with 1024 channels or more
 // the channels are cut into groups whose H2D copy, pass and D2H copy overlap on separate streams).  Caller rotates
-// `current` nblocks times afterwards (src/fft_convolver.rs:301-305).  Output is bit-identical to nblocks calls of
+// `current` nblocks times afterwards (src/fft_convolver.rs:287-291).  Output is bit-identical to nblocks calls of
 // fcb_engine_process_block_dev.
 extern "C" int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
                                          size_t current, size_t active, size_t nblocks, const fcb_epilogue *epi,

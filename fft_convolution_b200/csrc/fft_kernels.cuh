@@ -2,8 +2,8 @@
 // fused with the segment-0 MAC, 1/N normalisation, overlap-add, overlap save and the
 // two-stage / crossfade epilogues) for sm_100a.
 //
-// Replaces the reference's `Fft` adapter over realfft/rustfft (src/fft_convolver.rs:21-64) and
-// the per-chunk arithmetic of FFTConvolver::process (:248-255, :270-288, :297-298).
+// Replaces the reference's `Fft` adapter over realfft/rustfft (src/fft_convolver.rs:7-50) and
+// the per-chunk arithmetic of FFTConvolver::process (:234-241, :256-274, :283-284).
 //
 // Transform: a real FFT of N = 2B points is one B-point complex FFT plus a split pass
 // (z[j] = x[2j] + i x[2j+1]).  The complex FFT is a shared-memory Stockham autosort with
@@ -247,7 +247,7 @@ __device__ __forceinline__ void irfft_presplit(float2 *s, int tid, const float2 
 }
 
 // output sample i of channel c: (y + overlap) then the optional fused epilogue, in the reference's
-// operation order — two-stage ((y+ov)+p0)+p1 (src/fft_convolver.rs:452-468), crossfade
+// operation order — two-stage ((y+ov)+p0)+p1 (src/fft_convolver.rs:438-454), crossfade
 // a*g1 + b*g2 with separately rounded products (src/crossfade_convolver.rs:160-169, 242-278)
 __device__ __forceinline__ float apply_epilogue(float v, const fcb_epilogue &epi, long long c, int i)
 {
@@ -310,9 +310,9 @@ __device__ __forceinline__ void load_block_as_complex(float2 *s, int tid, const 
 // K1 / K5: batched forward real FFT.
 // transform q -> (channel c = q / nseg, segment i = q % nseg); source = src + c*src_stride + i*B,
 // of which only the first clamp(len - i*B, 0, B) samples are real data (copy_and_pad,
-// src/fft_convolver.rs:70-74); destination row = dst + c*dst_stride + i*B (packed bins).
-// K1 uses nseg = 1, len = fill + n, dst = ring + current*B  (:248-255);
-// K5 uses nseg = S,  len = IR length                         (:145-156, :207-226).
+// src/fft_convolver.rs:56-60); destination row = dst + c*dst_stride + i*B (packed bins).
+// K1 uses nseg = 1, len = fill + n, dst = ring + current*B  (:234-241);
+// K5 uses nseg = S,  len = IR length                         (:131-142, :193-212).
 // ========================================================================================
 template <int LOGB>
 __global__ void __launch_bounds__(FftPlan<LOGB>::CTA, FftPlan<LOGB>::MIN_CTAS)
@@ -351,9 +351,9 @@ k_rfft_forward(const float *__restrict__ src, long long src_stride, int len, flo
 }
 
 // ========================================================================================
-// K3: conv = pre_multiplied + ring[current] * ir[0]  (src/fft_convolver.rs:270-275, unfused
-// f32 like the reference), inverse real FFT, /N (:58-60), overlap-add into the output
-// (:284-288) with the two-stage (:452-468) or crossfade (src/crossfade_convolver.rs:75-77)
+// K3: conv = pre_multiplied + ring[current] * ir[0]  (src/fft_convolver.rs:256-261, unfused
+// f32 like the reference), inverse real FFT, /N (:44-46), overlap-add into the output
+// (:270-274) with the two-stage (:438-454) or crossfade (src/crossfade_convolver.rs:75-77)
 // epilogue, and overlap save on block completion (:297-298).
 // ========================================================================================
 struct IfftArgs {

@@ -6,7 +6,7 @@
 // cost ~5 % of the step.  Here a CTA starts its TMA pipeline first, does the forward FFT while the
 // first stages land, and runs the inverse FFT after its stream ends while the co-resident CTA keeps
 // the HBM pipes busy; the step becomes one launch and `pre_multiplied` never leaves the chip.
-// Same arithmetic, same order as the separate kernels (src/fft_convolver.rs:248-298): outputs are
+// Same arithmetic, same order as the separate kernels (src/fft_convolver.rs:234-284): outputs are
 // bit-identical to the K1 -> K2 -> K3 sequence.
 #pragma once
 
@@ -118,7 +118,7 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
     const bool mlive = ty < nlive;
     if (mlive) h0 = __ldg(reinterpret_cast<const float4 *>(a.ir + a.ir_chan(c0 + ty) * a.ir_stride + (long long)(0 - a.ir_seg0) * B) + tx);
 
-    // ---- K1: forward real FFT of the new block (src/fft_convolver.rs:248-255) -------------------
+    // ---- K1: forward real FFT of the new block (src/fft_convolver.rs:234-241) -------------------
     float2 *fs = fbuf + (fwork ? fslot : 0) * Cfg::FFT_PER;
     const bool flive = fwork && fslot < nlive;
     if (TMA_IO) mbar_wait(in_bar, 0);
@@ -159,7 +159,7 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
     }
     __syncthreads();
 
-    // ---- K2: delay-line MAC over segments lo..hi-1 (src/fft_convolver.rs:258-269) ---------------
+    // ---- K2: delay-line MAC over segments lo..hi-1 (src/fft_convolver.rs:244-255) ---------------
     const bool packed = (tx == 0);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int it = 0; it < niter; it++) {
@@ -194,7 +194,7 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
         if (tid == 0 && it + NST < niter) issue(it + NST);
     }
 
-    // ---- K3: conv = pre_multiplied + X[current] * H[0] (:270-275), inverse FFT, overlap-add ------
+    // ---- K3: conv = pre_multiplied + X[current] * H[0] (:256-261), inverse FFT, overlap-add ------
     float4 conv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (mlive) {
         const float4 x = reinterpret_cast<const float4 *>(fbuf + ty * Cfg::FFT_PER)[tx];
@@ -259,7 +259,7 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
 
 // ---------------------------------------------------------------------------------------------
 // Pair variant: TWO convolvers that are fed the same input — TwoStageFFTConvolver's head and
-// tail_convolver0 (src/fft_convolver.rs:431, :478-487) or CrossfadeConvolver's A and B
+// tail_convolver0 (src/fft_convolver.rs:417, :464-473) or CrossfadeConvolver's A and B
 // (src/crossfade_convolver.rs:72-73) — hold identical input-spectrum rings, so one CTA does ONE forward FFT,
 // streams the ring rows ONCE next to both IR row sets, and finishes with both inverse FFTs side by side
 // (threads 0..63 convolver A, 64..127 convolver B).  Per channel and block the stream is 24*S*K bytes instead
@@ -377,7 +377,7 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
         h0b = __ldg(reinterpret_cast<const float4 *>(fa.ir_b + (c0 + ty) * fa.ir_b_stride) + tx);
     }
 
-    // ---- K1 once: forward real FFT of the new block, into both rings (src/fft_convolver.rs:248-255) ----
+    // ---- K1 once: forward real FFT of the new block, into both rings (src/fft_convolver.rs:234-241) ----
     float2 *fs = fbuf + (fwork1 ? fslot : 0) * Cfg::FFT_PER;
     const bool flive1 = fwork1 && fslot < nlive;
     if (fwork1) load_block_as_complex<LOGB>(fs, flane, fa.in + (c0 + fslot) * fa.in_stride, flive1 ? B : 0);
@@ -404,7 +404,7 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
     }
     __syncthreads();
 
-    // ---- K2 for both convolvers on one ring stream (src/fft_convolver.rs:258-269) ----------------
+    // ---- K2 for both convolvers on one ring stream (src/fft_convolver.rs:244-255) ----------------
     const bool packed = (tx == 0);
     float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = acc_a;
     for (int it = 0; it < niter; it++) {
@@ -427,7 +427,7 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
         if (tid == 0 && it + NST < niter) issue(it + NST);
     }
 
-    // ---- K3 twice, side by side: conv = pre_multiplied + X[current] * H[0] (:270-275), inverse FFT ------
+    // ---- K3 twice, side by side: conv = pre_multiplied + X[current] * H[0] (:256-261), inverse FFT ------
     float4 conv_a = make_float4(0.f, 0.f, 0.f, 0.f), conv_b = conv_a;
     if (mlive) {
         const float4 x = reinterpret_cast<const float4 *>(fbuf + ty * Cfg::FFT_PER)[tx];

@@ -1,7 +1,7 @@
 // host_mirror.cu — layer 2 of the C ABI: a C++ mirror of the reference's three `Convolution`
 // implementors (src/lib.rs:5-14), batched over C lock-step channels.  It keeps exactly what
 // north_star leaves on the host — the block scheduler, the input-buffer fill, the segment-ring
-// rotation (src/fft_convolver.rs:236-245, 291-306), the two-stage bookkeeping (:438-508) and the
+// rotation (src/fft_convolver.rs:222-231, :277-292), the two-stage bookkeeping (:424-494) and the
 // crossfade state machine (src/crossfade_convolver.rs:51-105, 192-279) — and drives the device
 // stages of engine.cu.  All arithmetic on samples happens in CUDA kernels; there is no CPU path.
 #include <cmath>
@@ -16,7 +16,7 @@ using namespace fcb;
 // ---- small elementwise kernels for the unfused fall-backs of the K3 epilogues ----------------
 namespace fcb {
 
-// two-stage head/tail sum when a call does not map onto one K3 launch (src/fft_convolver.rs:452-468)
+// two-stage head/tail sum when a call does not map onto one K3 launch (src/fft_convolver.rs:438-454)
 __global__ void k_add2(float *out, long long out_stride, const float *p0, const float *p1, long long p_stride, int n,
                        long long nchan)
 {
@@ -63,13 +63,13 @@ static fcb_options default_options()
 } // namespace fcb
 
 // ==============================================================================================
-// FFTConvolver — src/fft_convolver.rs:100-321
+// FFTConvolver — src/fft_convolver.rs:86-307
 // ==============================================================================================
 struct fcb_fftconv {
     fcb_engine *eng = nullptr; // NULL = Default::default() (no segments)
     size_t C = 0;
-    size_t ir_len = 0, block_size = 0, seg_count = 0, active_seg_count = 0; // :102-105
-    size_t current = 0, input_buffer_fill = 0;                              // :113, :115
+    size_t ir_len = 0, block_size = 0, seg_count = 0, active_seg_count = 0; // :88-91
+    size_t current = 0, input_buffer_fill = 0;                              // :99, :101
     fcb_options opt{};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -135,24 +135,24 @@ extern "C" void fcb_fftconv_free(fcb_fftconv *c)
     delete c;
 }
 
-// :119-186
+// :105-172
 extern "C" int fcb_fftconv_init(fcb_fftconv **out, const float *irs, size_t channels, size_t ir_len,
                                 size_t block_size, size_t max_response_length, const fcb_options *opt)
 {
     if (!out) return fail(FCB_ERR_ARG, "NULL out");
     *out = nullptr;
     if (channels == 0) return fail(FCB_ERR_ARG, "channels must be >= 1");
-    if (max_response_length < ir_len) // :120-124
+    if (max_response_length < ir_len) // :106-110
         return fail(FCB_ERR_PANIC, "max_response_length must be at least the length of the initial impulse response");
     fcb_fftconv *c = nullptr;
     FCB_TRY(fcb_fftconv_default(&c, channels, opt));
-    c->ir_len = max_response_length;                 // :125-127
-    c->block_size = next_power_of_two(block_size);   // :129
-    c->seg_count = (size_t)std::ceil((double)c->ir_len / (double)c->block_size); // :131
-    c->active_seg_count = c->seg_count;              // :132
+    c->ir_len = max_response_length;                 // :111-113
+    c->block_size = next_power_of_two(block_size);   // :115
+    c->seg_count = (size_t)std::ceil((double)c->ir_len / (double)c->block_size); // :117
+    c->active_seg_count = c->seg_count;              // :118
     fcb_engine_desc d{channels, c->block_size, c->ir_len, c->opt.shared_ir, c->opt.device, (void *)c->stream};
     int rc = fcb_engine_create(&d, &c->eng);
-    // :145-156 — K5 over the zero-padded IR (rows past ir_len come out as zeros)
+    // :131-142 — K5 over the zero-padded IR (rows past ir_len come out as zeros)
     if (rc == FCB_OK) rc = fcb_engine_set_ir(c->eng, 0, c->opt.shared_ir ? 1 : channels, irs, ir_len, ir_len, 0);
     if (rc == FCB_OK) c->d_io = fcb_engine_scratch(c->eng);
     if (rc == FCB_OK) fftconv_alloc_mapped(c);
@@ -165,7 +165,7 @@ extern "C" int fcb_fftconv_init(fcb_fftconv **out, const float *irs, size_t chan
     return FCB_OK;
 }
 
-// #[derive(Clone)] :100
+// #[derive(Clone)] :86
 extern "C" int fcb_fftconv_clone(const fcb_fftconv *s, fcb_fftconv **out)
 {
     if (!s || !out) return fail(FCB_ERR_ARG, "NULL argument");
@@ -192,13 +192,13 @@ extern "C" int fcb_fftconv_clone(const fcb_fftconv *s, fcb_fftconv **out)
     return FCB_OK;
 }
 
-// :188-227
+// :174-213
 extern "C" int fcb_fftconv_update(fcb_fftconv *c, const float *irs, size_t new_ir_len)
 {
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
     if (new_ir_len > c->ir_len) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
-    if (c->ir_len == 0) return FCB_OK; // :195-197
-    c->active_seg_count = (size_t)std::ceil((double)new_ir_len / (double)c->block_size); // :204
+    if (c->ir_len == 0) return FCB_OK; // :181-183
+    c->active_seg_count = (size_t)std::ceil((double)new_ir_len / (double)c->block_size); // :190
     return fcb_engine_set_ir(c->eng, 0, c->opt.shared_ir ? 1 : c->C, irs, new_ir_len, new_ir_len, 1);
 }
 
@@ -211,7 +211,7 @@ static int fftconv_update_dev(fcb_fftconv *c, const float *irs_dev, size_t new_i
     return fcb_engine_set_ir_dev(c->eng, 0, c->opt.shared_ir ? 1 : c->C, irs_dev, new_ir_len, stride, 1);
 }
 
-// :310-320
+// :296-306
 extern "C" int fcb_fftconv_reset(fcb_fftconv *c)
 {
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
@@ -252,14 +252,14 @@ static fcb_epilogue offset_epilogue(const fcb_epilogue *epi, size_t off)
     return e;
 }
 
-// the block scheduler of :236-308; `host_in`/`host_out` select the H2D/D2H flavour of each chunk
+// the block scheduler of :222-294; `host_in`/`host_out` select the H2D/D2H flavour of each chunk
 static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in_stride, float *out, size_t out_len,
                        size_t out_stride, const fcb_epilogue *epi, bool host)
 {
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
     if (out_len && !out) return fail(FCB_ERR_ARG, "NULL output");
     FCB_CUDA(cudaSetDevice(c->opt.device));
-    if (c->active_seg_count == 0) { // :230-233
+    if (c->active_seg_count == 0) { // :216-219
         if (host) {
             for (size_t ch = 0; ch < c->C; ch++) memset(out + ch * out_stride, 0, out_len * sizeof(float));
             return FCB_OK;
@@ -279,9 +279,9 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
         return FCB_OK;
     }
     size_t processed = 0;
-    while (processed < out_len) { // :236
-        const bool was_empty = c->input_buffer_fill == 0; // :237
-        size_t n = out_len - processed;                   // :238-241
+    while (processed < out_len) { // :222
+        const bool was_empty = c->input_buffer_fill == 0; // :223
+        size_t n = out_len - processed;                   // :224-227
         if (B - c->input_buffer_fill < n) n = B - c->input_buffer_fill;
         const size_t pos = c->input_buffer_fill;
         const bool complete = pos + n == B;
@@ -295,7 +295,7 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
                 FCB_TRY(fcb_engine_process_blocks(c->eng, in + processed, in_stride, out + processed, out_stride, c->current,
                                                   c->active_seg_count, nb, &e, host ? 1 : 0));
                 for (size_t d = 0; d < nb; d++)
-                    c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1; // :301-305
+                    c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1; // :287-291
                 processed += nb * B;
                 continue;
             }
@@ -314,7 +314,7 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
             if (din && dout) {
                 FCB_TRY(fcb_engine_process_block_dev(c->eng, din, in_stride, dout, out_stride, c->current,
                                                      c->active_seg_count, &e));
-                c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1; // :301-305
+                c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1; // :287-291
                 processed += n;
                 continue;
             }
@@ -323,7 +323,7 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
             // many channels, whole block, host buffers: overlap the PCIe copies with K2
             FCB_TRY(fcb_engine_process_block_host(c->eng, in + processed, in_stride, out + processed, out_stride,
                                                   c->current, c->active_seg_count, 0));
-            c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1; // :301-305
+            c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1; // :287-291
             processed += n;
             continue;
         }
@@ -338,16 +338,16 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
             FCB_TRY(fcb_engine_process_block_dev(c->eng, in + processed, in_stride, dst, dst_stride, c->current,
                                                  c->active_seg_count, &e));
         } else {
-            if (host) FCB_TRY(fcb_engine_push_input(c->eng, in + processed, in_stride, pos, n)); // :243-245
+            if (host) FCB_TRY(fcb_engine_push_input(c->eng, in + processed, in_stride, pos, n)); // :229-231
             else FCB_TRY(fcb_engine_push_input_dev(c->eng, in + processed, in_stride, pos, n));
-            FCB_TRY(fcb_engine_fft_forward(c->eng, c->current, pos + n));                        // :248-255
-            if (was_empty) FCB_TRY(fcb_engine_mac(c->eng, c->current, c->active_seg_count));     // :258-269
-            FCB_TRY(fcb_engine_ifft_ola(c->eng, c->current, pos, n, complete, dst, dst_stride, &e)); // :270-288
+            FCB_TRY(fcb_engine_fft_forward(c->eng, c->current, pos + n));                        // :234-241
+            if (was_empty) FCB_TRY(fcb_engine_mac(c->eng, c->current, c->active_seg_count));     // :244-255
+            FCB_TRY(fcb_engine_ifft_ola(c->eng, c->current, pos, n, complete, dst, dst_stride, &e)); // :256-274
         }
         if (host)
             FCB_CUDA(cudaMemcpy2DAsync(out + processed, out_stride * sizeof(float), c->d_io, B * sizeof(float),
                                        n * sizeof(float), c->C, cudaMemcpyDeviceToHost, c->stream));
-        c->input_buffer_fill += n; // :291-306
+        c->input_buffer_fill += n; // :277-292
         if (c->input_buffer_fill == B) {
             c->input_buffer_fill = 0;
             c->current = c->current > 0 ? c->current - 1 : c->active_seg_count - 1;
@@ -375,7 +375,7 @@ static int fftconv_process_pair_dev(fcb_fftconv *a, fcb_fftconv *b, const float 
 {
     FCB_TRY(fcb_engine_process_block_pair_dev(a->eng, b->eng, in, in_stride, out_a, stride_a, epi_a, out_b, stride_b, epi_b,
                                               a->current, a->active_seg_count));
-    a->current = a->current > 0 ? a->current - 1 : a->active_seg_count - 1; // :301-305
+    a->current = a->current > 0 ? a->current - 1 : a->active_seg_count - 1; // :287-291
     b->current = a->current;
     return FCB_OK;
 }
@@ -405,9 +405,9 @@ extern "C" size_t fcb_fftconv_current(const fcb_fftconv *c) { return c->current;
 extern "C" size_t fcb_fftconv_fill(const fcb_fftconv *c) { return c->input_buffer_fill; }
 
 // ==============================================================================================
-// TwoStageFFTConvolver — src/fft_convolver.rs:337-540
+// TwoStageFFTConvolver — src/fft_convolver.rs:323-526
 // ==============================================================================================
-// :528-540, f32 arithmetic throughout
+// :514-526, f32 arithmetic throughout
 extern "C" size_t fcb_compute_tail_block_size(size_t head_len, size_t response_len)
 {
     const float FFT_K = 1.5f;
@@ -421,13 +421,13 @@ extern "C" size_t fcb_compute_tail_block_size(size_t head_len, size_t response_l
 }
 
 struct fcb_twostage {
-    size_t C = 0, head_block_size = 0, tail_block_size = 0; // :339-340
+    size_t C = 0, head_block_size = 0, tail_block_size = 0; // :325-326
     fcb_fftconv *head = nullptr, *tail0 = nullptr, *tail = nullptr;
-    // device [C][T] each (:343-348); tail_in is double-buffered for the asynchronous tail
+    // device [C][T] each (:329-334); tail_in is double-buffered for the asynchronous tail
     float *tail_output0 = nullptr, *tail_precalculated0 = nullptr, *tail_output = nullptr,
           *tail_precalculated = nullptr, *tail_input[2] = {nullptr, nullptr};
     int tail_in_sel = 0;
-    size_t tail_input_fill = 0, precalculated_pos = 0; // :349-350
+    size_t tail_input_fill = 0, precalculated_pos = 0; // :335-336
     fcb_options opt{};
     cudaStream_t stream = nullptr, tail_stream = nullptr;
     bool own_stream = false;
@@ -499,7 +499,7 @@ static int twostage_shell(fcb_twostage **out, size_t channels, const fcb_options
     return FCB_OK;
 }
 
-// :354-420
+// :340-406
 extern "C" int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t channels, size_t ir_len,
                                  size_t block_size, size_t max_response_length, const fcb_options *opt)
 {
@@ -508,13 +508,13 @@ extern "C" int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t ch
     if (channels == 0) return fail(FCB_ERR_ARG, "channels must be >= 1");
     fcb_options o = opt ? *opt : default_options();
     o.shared_ir = 0;
-    const size_t head = block_size; // :355 (kept unrounded for the bookkeeping)
+    const size_t head = block_size; // :341 (kept unrounded for the bookkeeping)
     const size_t T = o.forced_tail_block ? o.forced_tail_block : fcb_compute_tail_block_size(block_size, max_response_length);
-    if (max_response_length < ir_len) // :358-362
+    if (max_response_length < ir_len) // :344-348
         return fail(FCB_ERR_PANIC, "max_response_length must be at least the length of the initial impulse response");
-    if (head == 0) return fail(FCB_ERR_PANIC, "attempt to calculate the remainder with a divisor of zero"); // :445
+    if (head == 0) return fail(FCB_ERR_PANIC, "attempt to calculate the remainder with a divisor of zero"); // :431
     const size_t L = max_response_length;
-    // padded_ir (:363-364), channel-major
+    // padded_ir (:349-350), channel-major
     std::vector<float> padded(channels * (L ? L : 1), 0.f);
     for (size_t ch = 0; ch < channels; ch++)
         if (ir_len) memcpy(&padded[ch * L], irs + ch * ir_len, ir_len * sizeof(float));
@@ -532,12 +532,12 @@ extern "C" int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t ch
         return v;
     };
     {
-        const size_t head_ir_len = L < T ? L : T; // :366-368
+        const size_t head_ir_len = L < T ? L : T; // :352-354
         auto v = gather(0, head_ir_len);
         rc = fcb_fftconv_init(&c->head, v.data(), channels, head_ir_len, head, head_ir_len, &sub);
     }
     if (rc == FCB_OK) {
-        if (L > T) { // :370-382
+        if (L > T) { // :356-368
             const size_t tl = (L - T) < T ? (L - T) : T;
             auto v = gather(T, tl);
             rc = fcb_fftconv_init(&c->tail0, v.data(), channels, tl, head, tl, &sub);
@@ -548,7 +548,7 @@ extern "C" int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t ch
     if (rc == FCB_OK) {
         fcb_options tsub = sub;
         if (c->tail_stream) tsub.stream = (void *)c->tail_stream;
-        if (L > 2 * T) { // :387-398
+        if (L > 2 * T) { // :373-384
             const size_t tl = L - 2 * T;
             auto v = gather(2 * T, tl);
             rc = fcb_fftconv_init(&c->tail, v.data(), channels, tl, T, tl, &tsub);
@@ -624,14 +624,14 @@ extern "C" int fcb_twostage_clone(const fcb_twostage *s, fcb_twostage **out)
     return FCB_OK;
 }
 
-// :422-424
+// :408-410
 extern "C" int fcb_twostage_update(fcb_twostage *c, const float *irs, size_t ir_len)
 {
     (void)c; (void)irs; (void)ir_len;
     return fail(FCB_ERR_TODO, "not yet implemented");
 }
 
-// :511-525
+// :497-511
 extern "C" int fcb_twostage_reset(fcb_twostage *c)
 {
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
@@ -650,25 +650,25 @@ extern "C" int fcb_twostage_reset(fcb_twostage *c)
     return twostage_quiesce(c);
 }
 
-// :426-509 on device buffers
+// :412-495 on device buffers
 extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t in_len, size_t in_stride, float *out,
                                         size_t out_len, size_t out_stride)
 {
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
-    if (!(in_len <= c->head_block_size)) // assert! :428
+    if (!(in_len <= c->head_block_size)) // assert! :414
         return fail(FCB_ERR_PANIC, "assertion failed: input.len() <= self.head_block_size");
     // head.process slices input[..output.len()], the tail loop indexes output[..input.len()]
     if (in_len != out_len) return fail(FCB_ERR_PANIC, "index out of bounds: input and output lengths differ");
     FCB_CUDA(cudaSetDevice(c->opt.device));
     const size_t H = c->head_block_size, T = c->tail_block_size, C = c->C;
 
-    // Can the head/tail sum (:452-468) ride on the head's K3 launch?  Only when this call is one
+    // Can the head/tail sum (:438-454) ride on the head's K3 launch?  Only when this call is one
     // tail piece and one head chunk; otherwise the sum runs as a separate elementwise kernel.
     const bool one_piece = in_len <= H - (c->tail_input_fill % H);
     const bool one_chunk = c->head->active_seg_count == 0 ? false
                                                           : in_len <= c->head->block_size - c->head->input_buffer_fill;
     // a head block size that does not divide T runs off the end of tail_input: the reference's
-    // slice at :473 panics there (every non-power-of-two head size does, eventually)
+    // slice at :459 panics there (every non-power-of-two head size does, eventually)
     const bool overflow = c->tail_input_fill + (one_piece ? in_len : 0) > T;
     const bool fuse = T != 0 && in_len > 0 && one_piece && one_chunk && !overflow;
     fcb_epilogue epi;
@@ -678,22 +678,22 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
         epi.add1 = c->tail_precalculated + c->precalculated_pos;
         epi.add_stride = T;
     }
-    // head and tail_convolver0 see the same head blocks (:431 and :478-487): when this call is one whole head block
-    // both run in one paired launch, tail0 writing where :478-487 would have put its block
+    // head and tail_convolver0 see the same head blocks (:417 and :464-473): when this call is one whole head block
+    // both run in one paired launch, tail0 writing where :464-473 would have put its block
     const bool paired = fuse && in_len == H && c->tail_input_fill % H == 0 && fftconv_pair_ok(c->head, c->tail0, in_len);
     if (paired)
         FCB_TRY(fftconv_process_pair_dev(c->head, c->tail0, in, in_stride, out, out_stride, &epi,
                                          c->tail_output0 + c->tail_input_fill, T, nullptr));
     else
-        FCB_TRY(fcb_fftconv_process_dev(c->head, in, in_len, in_stride, out, out_len, out_stride, fuse ? &epi : nullptr)); // :431
-    if (T == 0) return FCB_OK; // :434-436
+        FCB_TRY(fcb_fftconv_process_dev(c->head, in, in_len, in_stride, out, out_len, out_stride, fuse ? &epi : nullptr)); // :417
+    if (T == 0) return FCB_OK; // :420-422
 
     size_t processed = 0;
-    while (processed < in_len) { // :441
+    while (processed < in_len) { // :427
         const size_t remaining = in_len - processed;
-        size_t n = H - (c->tail_input_fill % H); // :443-446
+        size_t n = H - (c->tail_input_fill % H); // :429-432
         if (remaining < n) n = remaining;
-        if (!fuse && c->precalculated_pos + n <= T) { // :452-468 (past T the reference panics at :456)
+        if (!fuse && c->precalculated_pos + n <= T) { // :438-454 (past T the reference panics at :442)
             long long total = (long long)C * (long long)n;
             k_add2<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
                 out + processed, (long long)out_stride, c->tail_precalculated0 + c->precalculated_pos,
@@ -701,20 +701,20 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
             g_launches++;
             FCB_CUDA(cudaGetLastError());
         }
-        c->precalculated_pos += n; // :470
-        if (c->tail_input_fill + n > T) // slice index panic at :473
+        c->precalculated_pos += n; // :456
+        if (c->tail_input_fill + n > T) // slice index panic at :459
             return fail(FCB_ERR_PANIC, "range end index %zu out of range for slice of length %zu", c->tail_input_fill + n, T);
         float *tin = c->tail_input[c->tail_in_sel];
         FCB_CUDA(cudaMemcpy2DAsync(tin + c->tail_input_fill, T * sizeof(float), in + processed, in_stride * sizeof(float),
-                                   n * sizeof(float), C, cudaMemcpyDeviceToDevice, c->stream)); // :473-475
+                                   n * sizeof(float), C, cudaMemcpyDeviceToDevice, c->stream)); // :459-461
         c->tail_input_fill += n;
 
-        if (c->tail_input_fill % H == 0) { // :478-490
+        if (c->tail_input_fill % H == 0) { // :464-476
             const size_t off = c->tail_input_fill - H;
             if (!paired) FCB_TRY(fcb_fftconv_process_dev(c->tail0, tin + off, H, T, c->tail_output0 + off, H, T, nullptr));
             if (c->tail_input_fill == T) std::swap(c->tail_precalculated0, c->tail_output0);
         }
-        if (c->tail_input_fill == T) { // :493-500
+        if (c->tail_input_fill == T) { // :479-486
             if (c->tail_stream) {
                 // the previous background tail must have produced tail_output before it becomes
                 // tail_precalculated, and must be done before we hand it new buffers
@@ -731,7 +731,7 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
                 FCB_TRY(fcb_fftconv_process_dev(c->tail, tin, T, T, c->tail_output, T, T, nullptr));
             }
         }
-        if (c->tail_input_fill == T) { // :502-505
+        if (c->tail_input_fill == T) { // :488-491
             c->tail_input_fill = 0;
             c->precalculated_pos = 0;
         }

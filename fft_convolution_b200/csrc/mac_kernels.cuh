@@ -1,7 +1,7 @@
 // mac_kernels.cuh — K2: the frequency-domain delay-line complex multiply-accumulate, fused with
 // the segment-ring indexing.  This is the HBM-bound kernel that carries >99 % of the bytes.
 //
-// Replaces src/fft_convolver.rs:258-269 (and complex_multiply_accumulate, :76-88):
+// Replaces src/fft_convolver.rs:244-255 (and complex_multiply_accumulate, :62-74):
 //     pre_multiplied[k] = sum_{i=1}^{active-1} ir[i][k] * ring[(current+i) % active][k]
 // accumulated in ascending i with every multiply / subtract / add rounded separately in f32
 // (Rust does not contract to FMA), so for identical spectra the result is bit-identical to the

@@ -3,10 +3,10 @@
 // optionally one IR-partition shard of a multi-GPU job.
 //
 // Semantics: y_out = sum_in FFTConvolver(h[out][in]).process(x_in), i.e. OUT*IN
-// reference convolvers (src/fft_convolver.rs:100-321) with outputs summed over `in`.  Because the
+// reference convolvers (src/fft_convolver.rs:86-307) with outputs summed over `in`.  Because the
 // inverse FFT and overlap-add are linear, the sum over `in` is taken in the frequency domain and
 // each output gets ONE inverse FFT and ONE overlap buffer; the delay-line sum over segments
-// (:258-269) is associative, so a shard may own only a contiguous range of IR segments and the
+// (:244-255) is associative, so a shard may own only a contiguous range of IR segments and the
 // partial spectra of all shards are summed (NCCL all-reduce, done by the caller) before K3.
 // Full blocks only (n == B per call).
 #include <cmath>
@@ -83,7 +83,7 @@ __device__ __forceinline__ void peer_signal(const PeerPub &p, unsigned int ctas)
 }
 
 // conv[s][o][k] = sum_in sum_z part[z][s][o][in][k]  +  sum_in X[s][in][cur][k] * H[o][in][seg 0][k]
-// (the segment-0 product, src/fft_convolver.rs:270-275, only on the shard that owns segment 0).
+// (the segment-0 product, src/fft_convolver.rs:256-261, only on the shard that owns segment 0).
 // CTA = 32 bins x 8 input lanes of one (stream, out): lane y sums its inputs y, y+8, ... over all
 // z chunks, then the 8 lane sums are added in fixed order — deterministic, and parallel enough
 // that the Z*IN partial rows (19 MB at 16x16, Z = 19) stream at memory speed.
@@ -166,7 +166,7 @@ struct fcb_mimo {
     size_t n_in = 0, n_out = 0, n_streams = 1, B = 0, L = 0, S = 0;
     int logb = 0;
     size_t seg_lo = 0, seg_hi = 0; // IR segments owned by this shard
-    size_t current = 0;            // ring slot of the next block (src/fft_convolver.rs:113)
+    size_t current = 0;            // ring slot of the next block (src/fft_convolver.rs:99)
     float2 *ir = nullptr;          // [OUT*IN][seg_hi-seg_lo][B]
     float2 *ring = nullptr;        // [NS*IN][S][B]
     float2 *premul = nullptr;      // [Z*NS*OUT*IN][B]  (Z segment chunks of the tile kernel, >= 1)
@@ -545,7 +545,7 @@ extern "C" int fcb_mimo_finish_dev(fcb_mimo *m, float *out_dev, size_t out_strid
         a.gather_err = reinterpret_cast<int *>(m->peer_done + 1);
     }
     FCB_TRY(run_inverse(m->logb, m->tw, m->stream, a));
-    m->current = m->current > 0 ? m->current - 1 : m->S - 1; // src/fft_convolver.rs:301-305
+    m->current = m->current > 0 ? m->current - 1 : m->S - 1; // src/fft_convolver.rs:287-291
     return FCB_OK;
 }
 

@@ -2,7 +2,7 @@
 // sm_100a tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands staged by TMA).
 //
 // Replaces, for the OUT x IN matrix with NS streams sharing the IR matrix, the loops at
-// src/fft_convolver.rs:258-275 of all OUT*IN reference convolvers at once.  Per bin k
+// src/fft_convolver.rs:244-261 of all OUT*IN reference convolvers at once.  Per bin k
 //     D[s][o] = sum_in sum_i  X[s][in][(current+i) % S][k] * H[o][in][i][k]          (complex)
 // is a dense contraction over j = (in, i): M = streams, N = outputs, K = IN*S — the one place on
 // this path where the work really is a GEMM.  As a real GEMM (K doubles, N doubles):

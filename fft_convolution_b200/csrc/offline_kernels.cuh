@@ -1,8 +1,8 @@
 // offline_kernels.cuh — multi-block calls: NB whole blocks of every channel in one pass.
 //
-// FFTConvolver::process accepts any call length (src/fft_convolver.rs:236); a caller that hands over
+// FFTConvolver::process accepts any call length (src/fft_convolver.rs:222); a caller that hands over
 // several blocks at once (offline rendering, large host buffers) lets the engine look at time, too.
-// For output block d the delay-line sum (:258-269) is
+// For output block d the delay-line sum (:244-255) is
 //     pre_multiplied_d = sum_{i=1}^{A-1} H_i * X_{t+d-i}
 // — the same IR row H_i meets T consecutive input spectra for T consecutive output blocks.  A thread of
 // k_mac_time keeps that window of T spectra bins in registers (it slides by one row per segment), so per
@@ -13,7 +13,7 @@
 // Spectra of the call's own blocks (time index m >= 0) come from `xnew` [C][NB][B]; older ones (m < 0)
 // from the ring slot (current - m) mod A, which this pass does not modify — the ring is updated by
 // k_ring_update only after the MACs.  The NB inverse FFTs are independent (K3 in raw mode writes all 2B
-// samples); k_ola_time then forms out_d = y_d[0..B) + y_{d-1}[B..2B) (overlap-add, :284-288, :297-298)
+// samples); k_ola_time then forms out_d = y_d[0..B) + y_{d-1}[B..2B) (overlap-add, :270-274, :283-284)
 // with the epilogue, in parallel over d.
 //
 // Measured (B200, 4096 channels x 2 s IR x block 512, device buffers, profiles/r01_offline_multi_block.jsonl):
@@ -118,7 +118,7 @@ k_mac_time(MacTimeArgs a)
 }
 
 // ring slot of block d <- xnew[c][d] for the last min(NB, A) blocks (older ones would be overwritten anyway);
-// slot_0 = current, slot_{d+1} = slot_d > 0 ? slot_d - 1 : A - 1  (src/fft_convolver.rs:301-305)
+// slot_0 = current, slot_{d+1} = slot_d > 0 ? slot_d - 1 : A - 1  (src/fft_convolver.rs:287-291)
 __global__ void __launch_bounds__(256)
 k_ring_update(const float2 *__restrict__ xnew, float2 *__restrict__ ring, long long ring_stride, int B, int nblocks, int current,
               int active, int first_block, long long total)

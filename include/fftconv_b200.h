@@ -3,7 +3,7 @@
  *
  * This is the drop-in boundary for the hot path of Sin-tel/fft-convolution
  * (/root/reference): the per-block inner loop of FFTConvolver::process
- * (src/fft_convolver.rs:229-309) as reused by TwoStageFFTConvolver (:426-509) and
+ * (src/fft_convolver.rs:215-295) as reused by TwoStageFFTConvolver (:412-495) and
  * CrossfadeConvolver (src/crossfade_convolver.rs:66-78).  Plain pointers and sizes only.
  *
  * Two layers are exported from libfftconv_b200.so:
@@ -73,15 +73,15 @@ void *fcb_host_alloc(size_t bytes);
 void fcb_host_free(void *p);
 
 /* ============================================================================================
- * Layer 1: device stages (replaces the arithmetic of src/fft_convolver.rs:21-98 and the loop
- * bodies at :145-156, :207-226, :248-288, :297-298).
+ * Layer 1: device stages (replaces the arithmetic of src/fft_convolver.rs:7-84 and the loop
+ * bodies at :131-142, :193-212, :234-274, :283-284).
  * ========================================================================================== */
 typedef struct fcb_engine fcb_engine;
 
 typedef struct {
     size_t channels;            /* C >= 1 lock-step channels */
-    size_t block_size;          /* rounded up to a power of two like :129; 1..16384 */
-    size_t max_response_length; /* ir_len of :125-127; seg_count = ceil(len / B) (:131) */
+    size_t block_size;          /* rounded up to a power of two like :115; 1..16384 */
+    size_t max_response_length; /* ir_len of :111-113; seg_count = ceil(len / B) (:117) */
     int shared_ir;              /* 1: all channels use one IR (spectra stored once, reused on chip) */
     int device;                 /* CUDA device ordinal */
     void *stream;               /* cudaStream_t to run on, NULL = a private non-blocking stream */
@@ -89,7 +89,7 @@ typedef struct {
 
 int fcb_engine_create(const fcb_engine_desc *desc, fcb_engine **out);
 void fcb_engine_destroy(fcb_engine *e);
-/* #[derive(Clone)] (src/fft_convolver.rs:100): deep copy of ring, spectra, overlap, input buffer */
+/* #[derive(Clone)] (src/fft_convolver.rs:86): deep copy of ring, spectra, overlap, input buffer */
 int fcb_engine_clone(const fcb_engine *e, fcb_engine **out);
 int fcb_engine_set_stream(fcb_engine *e, void *stream);
 void *fcb_engine_stream(const fcb_engine *e);
@@ -99,34 +99,34 @@ size_t fcb_engine_channels(const fcb_engine *e);
 size_t fcb_engine_block_size(const fcb_engine *e); /* rounded B */
 size_t fcb_engine_seg_count(const fcb_engine *e);  /* S */
 
-/* K5 — IR preparation (src/fft_convolver.rs:145-156 for init, :199-226 for update).
+/* K5 — IR preparation (src/fft_convolver.rs:131-142 for init, :185-212 for update).
  * irs: [nchan][len] f32 with channel stride `stride` samples, host or device memory.
  * Rows >= ceil(len/B) are zeroed.  is_update != 0 additionally zeroes pre_multiplied and
- * overlap of those channels (:199-202).  With shared_ir the call must cover chan0 = 0, nchan = 1.
+ * overlap of those channels (:185-188).  With shared_ir the call must cover chan0 = 0, nchan = 1.
  * No allocation happens here (the staging buffer is created with the engine). */
 int fcb_engine_set_ir(fcb_engine *e, size_t chan0, size_t nchan, const float *irs, size_t len,
                       size_t stride, int is_update);
 int fcb_engine_set_ir_dev(fcb_engine *e, size_t chan0, size_t nchan, const float *irs_dev, size_t len,
                           size_t stride, int is_update);
 
-/* reset() (:310-320): zero ring, overlap, input buffer, pre_multiplied.  IR spectra kept. */
+/* reset() (:296-306): zero ring, overlap, input buffer, pre_multiplied.  IR spectra kept. */
 int fcb_engine_reset(fcb_engine *e);
 
-/* :243-245 — copy n new samples per channel into the device input buffer at [fill, fill+n) */
+/* :229-231 — copy n new samples per channel into the device input buffer at [fill, fill+n) */
 int fcb_engine_push_input(fcb_engine *e, const float *in, size_t stride, size_t fill, size_t n);
 int fcb_engine_push_input_dev(fcb_engine *e, const float *in_dev, size_t stride, size_t fill, size_t n);
 
-/* K1 (:248-255): forward real FFT of [input_buffer[0..valid) | zeros] into ring slot `current` */
+/* K1 (:234-241): forward real FFT of [input_buffer[0..valid) | zeros] into ring slot `current` */
 int fcb_engine_fft_forward(fcb_engine *e, size_t current, size_t valid);
 
-/* K2 (:258-269): pre_multiplied = sum_{i=1}^{active-1} ir[i] * ring[(current+i) % active],
+/* K2 (:244-255): pre_multiplied = sum_{i=1}^{active-1} ir[i] * ring[(current+i) % active],
  * ascending i, every multiply/add rounded separately like the reference.  Only touches ring
  * slots older than `current`, so it may be issued before the block's input arrives. */
 int fcb_engine_mac(fcb_engine *e, size_t current, size_t active);
 
 /* fused output epilogues for K3 */
 typedef struct {
-    /* two-stage head/tail sum (:452-468): out = ((y + overlap) + add0[i]) + add1[i]; device
+    /* two-stage head/tail sum (:438-454): out = ((y + overlap) + add0[i]) + add1[i]; device
      * pointers already offset to this call's first sample, channel stride add_stride; may be NULL */
     const float *add0, *add1;
     size_t add_stride;
@@ -147,7 +147,7 @@ int fcb_engine_ifft_ola(fcb_engine *e, size_t current, size_t fill, size_t n, in
 /* a device buffer [C][B] (channel stride B) owned by the engine, for callers that have no device
  * allocator of their own: pass it as out_dev to ifft_ola, then fetch() it */
 float *fcb_engine_scratch(fcb_engine *e);
-/* the device input buffer [C][B] that push_input fills (src/fft_convolver.rs:114) */
+/* the device input buffer [C][B] that push_input fills (src/fft_convolver.rs:100) */
 float *fcb_engine_input_buffer(fcb_engine *e);
 
 /* device -> host copy of a planar result (stream-ordered, then synchronised) */
@@ -210,11 +210,11 @@ typedef struct {
     void *stream;   /* cudaStream_t or NULL */
     int shared_ir;  /* FFTConvolver only */
     int async_tail; /* TwoStage: run the big tail convolver on a second stream (the reference's
-                       "might be done in some background thread", src/fft_convolver.rs:492) */
-    size_t forced_tail_block; /* TwoStage: 0 = derive like the reference (:534-540) */
+                       "might be done in some background thread", src/fft_convolver.rs:478) */
+    size_t forced_tail_block; /* TwoStage: 0 = derive like the reference (:520-526) */
 } fcb_options;
 
-/* ---- FFTConvolver (src/fft_convolver.rs:100-321) ---- */
+/* ---- FFTConvolver (src/fft_convolver.rs:86-307) ---- */
 int fcb_fftconv_init(fcb_fftconv **out, const float *irs, size_t channels, size_t ir_len,
                      size_t block_size, size_t max_response_length, const fcb_options *opt);
 int fcb_fftconv_default(fcb_fftconv **out, size_t channels, const fcb_options *opt); /* Default::default() */
@@ -228,15 +228,15 @@ int fcb_fftconv_process_dev(fcb_fftconv *c, const float *in_dev, size_t in_len, 
                             float *out_dev, size_t out_len, size_t out_stride, const fcb_epilogue *epi);
 int fcb_fftconv_sync(fcb_fftconv *c);
 fcb_engine *fcb_fftconv_engine(fcb_fftconv *c); /* NULL for a default (empty) convolver */
-/* scheduler scalars the host keeps (src/fft_convolver.rs:103-105, :113, :115) */
+/* scheduler scalars the host keeps (src/fft_convolver.rs:89-91, :99, :101) */
 size_t fcb_fftconv_block_size(const fcb_fftconv *c);
 size_t fcb_fftconv_seg_count(const fcb_fftconv *c);
 size_t fcb_fftconv_active_seg_count(const fcb_fftconv *c);
 size_t fcb_fftconv_current(const fcb_fftconv *c);
 size_t fcb_fftconv_fill(const fcb_fftconv *c);
 
-/* ---- TwoStageFFTConvolver (src/fft_convolver.rs:337-540) ---- */
-size_t fcb_compute_tail_block_size(size_t head_len, size_t response_len); /* :534-540, f32 */
+/* ---- TwoStageFFTConvolver (src/fft_convolver.rs:323-526) ---- */
+size_t fcb_compute_tail_block_size(size_t head_len, size_t response_len); /* :520-526, f32 */
 int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t channels, size_t ir_len,
                       size_t block_size, size_t max_response_length, const fcb_options *opt);
 int fcb_twostage_clone(const fcb_twostage *c, fcb_twostage **out);

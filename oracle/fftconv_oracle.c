@@ -23,7 +23,7 @@
 #endif
 
 /* ------------------------------------------------------------------------------------------
- * real FFT stand-in.  Contract mirrored from the call sites src/fft_convolver.rs:50-63:
+ * real FFT stand-in.  Contract mirrored from the call sites src/fft_convolver.rs:36-49:
  * forward = unnormalised R2C (n reals -> n/2+1 bins, DC/Nyquist imaginary parts exactly 0),
  * inverse = unnormalised C2R then every sample divided by n.
  * ---------------------------------------------------------------------------------------- */
@@ -42,7 +42,7 @@ orc_plan *orc_plan_new(size_t n)
     p->n = n;
     p->m = n / 2;
     p->refs = 1;
-    if (n == 0) return p; /* Fft::default() plans length 0 (src/fft_convolver.rs:27-35) */
+    if (n == 0) return p; /* Fft::default() plans length 0 (src/fft_convolver.rs:13-21) */
     size_t m = p->m;
     int lg = 0;
     while (((size_t)1 << lg) < m) lg++;
@@ -190,7 +190,7 @@ void orc_rfft_inverse(const orc_plan *p, const orc_cpx *in, float *out)
         im[r] = ei + tr;
     }
     cfft_stages(p, re, im, +1.0f);
-    /* FFT normalisation, src/fft_convolver.rs:58-60: `*bin /= len as f32` */
+    /* FFT normalisation, src/fft_convolver.rs:44-46: `*bin /= len as f32` */
     float len = (float)n;
     for (size_t j = 0; j < m; j++) {
         out[2 * j] = re[j] / len;
@@ -199,10 +199,10 @@ void orc_rfft_inverse(const orc_plan *p, const orc_cpx *in, float *out)
     if (re != sre) free(re);
 }
 
-/* src/fft_convolver.rs:66-68 */
+/* src/fft_convolver.rs:52-54 */
 size_t orc_complex_size(size_t n) { return n / 2 + 1; }
 
-/* src/fft_convolver.rs:76-88: result[i] += a[i] * b[i]; Complex<f32> multiply =
+/* src/fft_convolver.rs:62-74: result[i] += a[i] * b[i]; Complex<f32> multiply =
  * (ar*br - ai*bi, ar*bi + ai*br), every operation rounded separately */
 void orc_complex_multiply_accumulate(orc_cpx *result, const orc_cpx *a, const orc_cpx *b, size_t len)
 {
@@ -239,20 +239,20 @@ static size_t next_power_of_two(size_t v)
 }
 
 /* ------------------------------------------------------------------------------------------
- * FFTConvolver — src/fft_convolver.rs:100-321
+ * FFTConvolver — src/fft_convolver.rs:86-307
  * ---------------------------------------------------------------------------------------- */
 struct orc_fftconv {
-    size_t ir_len, block_size, seg_count, active_seg_count; /* :102-105 */
+    size_t ir_len, block_size, seg_count, active_seg_count; /* :88-91 */
     size_t fft_complex_size;
-    orc_cpx *segments;    /* seg_count x K  (input spectra ring, :106) */
-    orc_cpx *segments_ir; /* seg_count x K  (:107) */
-    float *fft_buffer;    /* 2B (:108) */
-    orc_plan *fft;        /* :109 */
-    orc_cpx *pre_multiplied, *conv; /* K each (:110-111) */
-    float *overlap;       /* B (:112) */
-    size_t current;       /* :113 */
-    float *input_buffer;  /* B (:114) */
-    size_t input_buffer_fill; /* :115 */
+    orc_cpx *segments;    /* seg_count x K  (input spectra ring, :92) */
+    orc_cpx *segments_ir; /* seg_count x K  (:93) */
+    float *fft_buffer;    /* 2B (:94) */
+    orc_plan *fft;        /* :95 */
+    orc_cpx *pre_multiplied, *conv; /* K each (:96-97) */
+    float *overlap;       /* B (:98) */
+    size_t current;       /* :99 */
+    float *input_buffer;  /* B (:100) */
+    size_t input_buffer_fill; /* :101 */
 };
 
 /* #[derive(Default)]: everything empty / zero, Fft::default() */
@@ -263,36 +263,36 @@ orc_fftconv *orc_fftconv_default(void)
     return c;
 }
 
-/* src/fft_convolver.rs:119-186 */
+/* src/fft_convolver.rs:105-172 */
 orc_fftconv *orc_fftconv_init(const float *ir, size_t n_ir, size_t block_size, size_t max_response_length)
 {
-    if (max_response_length < n_ir) return NULL; /* panic! :120-124 */
-    size_t ir_len = max_response_length;          /* padded_ir.resize(max_response_length, 0.) :125-127 */
+    if (max_response_length < n_ir) return NULL; /* panic! :106-110 */
+    size_t ir_len = max_response_length;          /* padded_ir.resize(max_response_length, 0.) :111-113 */
     float *padded = (float *)calloc(ir_len ? ir_len : 1, sizeof(float));
     if (n_ir) memcpy(padded, ir, n_ir * sizeof(float));
 
     orc_fftconv *c = (orc_fftconv *)calloc(1, sizeof *c);
     c->ir_len = ir_len;
-    c->block_size = next_power_of_two(block_size); /* :129 */
-    size_t B = c->block_size, seg_size = 2 * B;    /* :130 */
-    c->seg_count = (size_t)ceil((double)ir_len / (double)B); /* :131 */
-    c->active_seg_count = c->seg_count;            /* :132 */
-    size_t K = c->fft_complex_size = orc_complex_size(seg_size); /* :133 */
-    c->fft = orc_plan_new(seg_size);               /* :136-137 */
+    c->block_size = next_power_of_two(block_size); /* :115 */
+    size_t B = c->block_size, seg_size = 2 * B;    /* :116 */
+    c->seg_count = (size_t)ceil((double)ir_len / (double)B); /* :117 */
+    c->active_seg_count = c->seg_count;            /* :118 */
+    size_t K = c->fft_complex_size = orc_complex_size(seg_size); /* :119 */
+    c->fft = orc_plan_new(seg_size);               /* :122-123 */
     c->fft_buffer = (float *)calloc(seg_size, sizeof(float));
-    c->segments = (orc_cpx *)calloc(c->seg_count * K + 1, sizeof(orc_cpx));    /* :141 */
-    c->segments_ir = (orc_cpx *)calloc(c->seg_count * K + 1, sizeof(orc_cpx)); /* :142 */
-    for (size_t i = 0; i < c->seg_count; i++) {    /* :145-156 */
+    c->segments = (orc_cpx *)calloc(c->seg_count * K + 1, sizeof(orc_cpx));    /* :127 */
+    c->segments_ir = (orc_cpx *)calloc(c->seg_count * K + 1, sizeof(orc_cpx)); /* :128 */
+    for (size_t i = 0; i < c->seg_count; i++) {    /* :131-142 */
         size_t remaining = ir_len - i * B;
         size_t size_copy = remaining >= B ? B : remaining;
-        memcpy(c->fft_buffer, padded + i * B, size_copy * sizeof(float)); /* copy_and_pad :70-74 */
+        memcpy(c->fft_buffer, padded + i * B, size_copy * sizeof(float)); /* copy_and_pad :56-60 */
         memset(c->fft_buffer + size_copy, 0, (seg_size - size_copy) * sizeof(float));
         orc_rfft_forward(c->fft, c->fft_buffer, c->segments_ir + i * K);
     }
-    c->pre_multiplied = (orc_cpx *)calloc(K, sizeof(orc_cpx)); /* :159-161 */
+    c->pre_multiplied = (orc_cpx *)calloc(K, sizeof(orc_cpx)); /* :145-147 */
     c->conv = (orc_cpx *)calloc(K, sizeof(orc_cpx));
     c->overlap = (float *)calloc(B, sizeof(float));
-    c->input_buffer = (float *)calloc(B, sizeof(float));       /* :164-168 */
+    c->input_buffer = (float *)calloc(B, sizeof(float));       /* :150-154 */
     c->input_buffer_fill = 0;
     c->current = 0;
     free(padded);
@@ -307,7 +307,7 @@ static void *dup_mem(const void *src, size_t bytes)
     return d;
 }
 
-/* #[derive(Clone)] (:100): deep copy of all Vec state, Arc-shared plans (:23-24) */
+/* #[derive(Clone)] (:86): deep copy of all Vec state, Arc-shared plans (:9-10) */
 orc_fftconv *orc_fftconv_clone(const orc_fftconv *s)
 {
     orc_fftconv *c = (orc_fftconv *)malloc(sizeof *c);
@@ -333,52 +333,52 @@ void orc_fftconv_free(orc_fftconv *c)
     free(c);
 }
 
-/* src/fft_convolver.rs:188-227 */
+/* src/fft_convolver.rs:174-213 */
 int orc_fftconv_update(orc_fftconv *c, const float *response, size_t new_ir_len)
 {
-    if (new_ir_len > c->ir_len) return ORC_PANIC; /* :191-193 */
-    if (c->ir_len == 0) return ORC_OK;            /* :195-197 */
+    if (new_ir_len > c->ir_len) return ORC_PANIC; /* :177-179 */
+    if (c->ir_len == 0) return ORC_OK;            /* :181-183 */
     size_t B = c->block_size, K = c->fft_complex_size;
-    memset(c->fft_buffer, 0, 2 * B * sizeof(float));  /* :199-202 */
+    memset(c->fft_buffer, 0, 2 * B * sizeof(float));  /* :185-188 */
     memset(c->conv, 0, K * sizeof(orc_cpx));
     memset(c->pre_multiplied, 0, K * sizeof(orc_cpx));
     memset(c->overlap, 0, B * sizeof(float));
-    c->active_seg_count = (size_t)ceil((double)new_ir_len / (double)B); /* :204 */
-    for (size_t i = 0; i < c->active_seg_count; i++) { /* :207-221 */
+    c->active_seg_count = (size_t)ceil((double)new_ir_len / (double)B); /* :190 */
+    for (size_t i = 0; i < c->active_seg_count; i++) { /* :193-207 */
         size_t remaining = new_ir_len - i * B;
         size_t size_copy = remaining >= B ? B : remaining;
         memcpy(c->fft_buffer, response + i * B, size_copy * sizeof(float));
         memset(c->fft_buffer + size_copy, 0, (2 * B - size_copy) * sizeof(float));
         orc_rfft_forward(c->fft, c->fft_buffer, c->segments_ir + i * K);
     }
-    for (size_t i = c->active_seg_count; i < c->seg_count; i++) /* :224-226 */
+    for (size_t i = c->active_seg_count; i < c->seg_count; i++) /* :210-212 */
         memset(c->segments_ir + i * K, 0, K * sizeof(orc_cpx));
     return ORC_OK;
 }
 
-/* src/fft_convolver.rs:229-309 */
+/* src/fft_convolver.rs:215-295 */
 int orc_fftconv_process(orc_fftconv *c, const float *input, size_t in_len, float *output, size_t out_len)
 {
-    if (c->active_seg_count == 0) { /* :230-233 */
+    if (c->active_seg_count == 0) { /* :216-219 */
         memset(output, 0, out_len * sizeof(float));
         return ORC_OK;
     }
-    if (in_len < out_len) return ORC_PANIC; /* slice index at :245 would panic */
+    if (in_len < out_len) return ORC_PANIC; /* slice index at :231 would panic */
     size_t B = c->block_size, K = c->fft_complex_size;
     size_t processed = 0;
-    while (processed < out_len) { /* :236 */
-        int input_buffer_was_empty = c->input_buffer_fill == 0; /* :237 */
-        size_t processing = out_len - processed;                  /* :238-241 */
+    while (processed < out_len) { /* :222 */
+        int input_buffer_was_empty = c->input_buffer_fill == 0; /* :223 */
+        size_t processing = out_len - processed;                  /* :224-227 */
         if (B - c->input_buffer_fill < processing) processing = B - c->input_buffer_fill;
-        size_t pos = c->input_buffer_fill;                        /* :243-245 */
+        size_t pos = c->input_buffer_fill;                        /* :229-231 */
         memcpy(c->input_buffer + pos, input + processed, processing * sizeof(float));
 
-        /* forward FFT of [input_buffer | zeros] into segments[current] (:248-255) */
+        /* forward FFT of [input_buffer | zeros] into segments[current] (:234-241) */
         memcpy(c->fft_buffer, c->input_buffer, B * sizeof(float));
         memset(c->fft_buffer + B, 0, B * sizeof(float));
         orc_rfft_forward(c->fft, c->fft_buffer, c->segments + c->current * K);
 
-        if (input_buffer_was_empty) { /* :258-269 */
+        if (input_buffer_was_empty) { /* :244-255 */
             memset(c->pre_multiplied, 0, K * sizeof(orc_cpx));
             for (size_t i = 1; i < c->active_seg_count; i++) {
                 size_t index_ir = i;
@@ -387,15 +387,15 @@ int orc_fftconv_process(orc_fftconv *c, const float *input, size_t in_len, float
                                                 c->segments + index_audio * K, K);
             }
         }
-        memcpy(c->conv, c->pre_multiplied, K * sizeof(orc_cpx)); /* :270-275 */
+        memcpy(c->conv, c->pre_multiplied, K * sizeof(orc_cpx)); /* :256-261 */
         orc_complex_multiply_accumulate(c->conv, c->segments + c->current * K, c->segments_ir, K);
 
-        orc_rfft_inverse(c->fft, c->conv, c->fft_buffer);        /* :278-281 */
+        orc_rfft_inverse(c->fft, c->conv, c->fft_buffer);        /* :264-267 */
 
-        for (size_t i = 0; i < processing; i++)                  /* sum(), :284-288 and :90-98 */
+        for (size_t i = 0; i < processing; i++)                  /* sum(), :270-274 and :76-84 */
             output[processed + i] = c->fft_buffer[pos + i] + c->overlap[pos + i];
 
-        c->input_buffer_fill += processing;                      /* :291-306 */
+        c->input_buffer_fill += processing;                      /* :277-292 */
         if (c->input_buffer_fill == B) {
             memset(c->input_buffer, 0, B * sizeof(float));
             c->input_buffer_fill = 0;
@@ -407,7 +407,7 @@ int orc_fftconv_process(orc_fftconv *c, const float *input, size_t in_len, float
     return ORC_OK;
 }
 
-/* src/fft_convolver.rs:310-320 */
+/* src/fft_convolver.rs:296-306 */
 void orc_fftconv_reset(orc_fftconv *c)
 {
     size_t B = c->block_size, K = c->fft_complex_size;
@@ -431,9 +431,9 @@ const orc_cpx *orc_fftconv_premul(const orc_fftconv *c) { return c->pre_multipli
 const float *orc_fftconv_overlap(const orc_fftconv *c) { return c->overlap; }
 
 /* ------------------------------------------------------------------------------------------
- * TwoStageFFTConvolver — src/fft_convolver.rs:337-540
+ * TwoStageFFTConvolver — src/fft_convolver.rs:323-526
  * ---------------------------------------------------------------------------------------- */
-/* :528-540, all arithmetic in f32 */
+/* :514-526, all arithmetic in f32 */
 size_t orc_compute_tail_block_size(size_t head_len, size_t response_len)
 {
     const float FFT_K = 1.5f;
@@ -450,13 +450,13 @@ struct orc_twostage {
     size_t tail_input_fill, precalculated_pos;
 };
 
-/* :354-420 */
+/* :340-406 */
 orc_twostage *orc_twostage_init_tail(const float *ir, size_t n_ir, size_t block_size,
                                      size_t max_response_length, size_t forced_tail)
 {
     size_t head = block_size;
     size_t T = forced_tail ? forced_tail : orc_compute_tail_block_size(block_size, max_response_length);
-    if (max_response_length < n_ir) return NULL; /* panic! :358-362 */
+    if (max_response_length < n_ir) return NULL; /* panic! :344-348 */
     size_t L = max_response_length;
     float *padded = (float *)calloc(L ? L : 1, sizeof(float));
     if (n_ir) memcpy(padded, ir, n_ir * sizeof(float));
@@ -464,23 +464,23 @@ orc_twostage *orc_twostage_init_tail(const float *ir, size_t n_ir, size_t block_
     orc_twostage *c = (orc_twostage *)calloc(1, sizeof *c);
     c->head_block_size = head;
     c->tail_block_size = T;
-    size_t head_ir_len = L < T ? L : T; /* :366-368 */
+    size_t head_ir_len = L < T ? L : T; /* :352-354 */
     c->head_convolver = orc_fftconv_init(padded, head_ir_len, head, head_ir_len);
-    if (L > T) { /* :370-382 */
+    if (L > T) { /* :356-368 */
         size_t tail_ir_len = (L - T) < T ? (L - T) : T;
         c->tail_convolver0 = orc_fftconv_init(padded + T, tail_ir_len, head, tail_ir_len);
     } else {
         c->tail_convolver0 = orc_fftconv_default();
     }
-    if (L > 2 * T) { /* :387-398 */
+    if (L > 2 * T) { /* :373-384 */
         size_t tail_ir_len = L - 2 * T;
         c->tail_convolver = orc_fftconv_init(padded + 2 * T, tail_ir_len, T, tail_ir_len);
     } else {
         c->tail_convolver = orc_fftconv_default();
     }
-    c->tail_output0 = (float *)calloc(T, sizeof(float));        /* :384-385 */
+    c->tail_output0 = (float *)calloc(T, sizeof(float));        /* :370-371 */
     c->tail_precalculated0 = (float *)calloc(T, sizeof(float));
-    c->tail_output = (float *)calloc(T, sizeof(float));         /* :400-402 */
+    c->tail_output = (float *)calloc(T, sizeof(float));         /* :386-388 */
     c->tail_precalculated = (float *)calloc(T, sizeof(float));
     c->tail_input = (float *)calloc(T, sizeof(float));
     free(padded);
@@ -517,7 +517,7 @@ void orc_twostage_free(orc_twostage *c)
     free(c);
 }
 
-/* :422-424 — todo!() */
+/* :408-410 — todo!() */
 int orc_twostage_update(orc_twostage *c, const float *ir, size_t len)
 {
     (void)c; (void)ir; (void)len;
@@ -526,51 +526,51 @@ int orc_twostage_update(orc_twostage *c, const float *ir, size_t len)
 
 static void swap_ptr(float **a, float **b) { float *t = *a; *a = *b; *b = t; }
 
-/* :426-509 */
+/* :412-495 */
 int orc_twostage_process(orc_twostage *c, const float *input, size_t in_len, float *output, size_t out_len)
 {
-    if (!(in_len <= c->head_block_size)) return ORC_PANIC; /* assert! :428 */
+    if (!(in_len <= c->head_block_size)) return ORC_PANIC; /* assert! :414 */
     /* head.process slices input[..output.len()] (needs in_len >= out_len) and the tail loop
      * indexes output[..input.len()] (needs out_len >= in_len): anything else panics */
     if (in_len != out_len) return ORC_PANIC;
     size_t H = c->head_block_size, T = c->tail_block_size;
 
-    orc_fftconv_process(c->head_convolver, input, in_len, output, out_len); /* :431 */
-    if (T == 0) return ORC_OK; /* tail_input.is_empty() :434-436 */
+    orc_fftconv_process(c->head_convolver, input, in_len, output, out_len); /* :417 */
+    if (T == 0) return ORC_OK; /* tail_input.is_empty() :420-422 */
 
     size_t len = in_len, processed = 0;
-    while (processed < len) { /* :441 */
+    while (processed < len) { /* :427 */
         size_t remaining = len - processed;
-        size_t processing = H - (c->tail_input_fill % H); /* :443-446 */
+        size_t processing = H - (c->tail_input_fill % H); /* :429-432 */
         if (remaining < processing) processing = remaining;
         size_t sum_begin = processed, sum_end = processed + processing;
 
         if (c->precalculated_pos + processing > T || c->tail_input_fill + processing > T)
-            return ORC_PANIC; /* index / slice panic at :456 / :473 (head size not dividing T) */
-        { /* :453-459 */
+            return ORC_PANIC; /* index / slice panic at :442 / :459 (head size not dividing T) */
+        { /* :439-445 */
             size_t pp = c->precalculated_pos;
             for (size_t i = sum_begin; i < sum_end; i++) output[i] += c->tail_precalculated0[pp++];
         }
-        { /* :462-468 */
+        { /* :448-454 */
             size_t pp = c->precalculated_pos;
             for (size_t i = sum_begin; i < sum_end; i++) output[i] += c->tail_precalculated[pp++];
         }
-        c->precalculated_pos += processing; /* :470 */
+        c->precalculated_pos += processing; /* :456 */
 
-        memcpy(c->tail_input + c->tail_input_fill, input + processed, processing * sizeof(float)); /* :473-475 */
+        memcpy(c->tail_input + c->tail_input_fill, input + processed, processing * sizeof(float)); /* :459-461 */
         c->tail_input_fill += processing;
 
-        if (c->tail_input_fill % H == 0) { /* :478-490 */
+        if (c->tail_input_fill % H == 0) { /* :464-476 */
             size_t block_offset = c->tail_input_fill - H;
             orc_fftconv_process(c->tail_convolver0, c->tail_input + block_offset, H,
                                 c->tail_output0 + block_offset, H);
             if (c->tail_input_fill == T) swap_ptr(&c->tail_precalculated0, &c->tail_output0);
         }
-        if (c->tail_input_fill == T) { /* :493-500 */
+        if (c->tail_input_fill == T) { /* :479-486 */
             swap_ptr(&c->tail_precalculated, &c->tail_output);
             orc_fftconv_process(c->tail_convolver, c->tail_input, T, c->tail_output, T);
         }
-        if (c->tail_input_fill == T) { /* :502-505 */
+        if (c->tail_input_fill == T) { /* :488-491 */
             c->tail_input_fill = 0;
             c->precalculated_pos = 0;
         }
@@ -579,7 +579,7 @@ int orc_twostage_process(orc_twostage *c, const float *input, size_t in_len, flo
     return ORC_OK;
 }
 
-/* :511-525 */
+/* :497-511 */
 void orc_twostage_reset(orc_twostage *c)
 {
     size_t T = c->tail_block_size;

@@ -6,8 +6,8 @@
  * --impl reference legs (as the checker / the reported CPU baseline, never as the product).
  *
  * It restates, in plain C, the algorithm of the reference crate Sin-tel/fft-convolution:
- *   FFTConvolver          src/fft_convolver.rs:100-321
- *   TwoStageFFTConvolver  src/fft_convolver.rs:337-540
+ *   FFTConvolver          src/fft_convolver.rs:86-307
+ *   TwoStageFFTConvolver  src/fft_convolver.rs:323-526
  *   CrossfadeConvolver    src/crossfade_convolver.rs:3-105
  *   Crossfader / mixer    src/crossfade_convolver.rs:126-279
  *
@@ -36,20 +36,20 @@ typedef struct { float re, im; } orc_cpx;
 #define ORC_OK 0
 #define ORC_PANIC 1
 
-/* ---- real FFT stand-in for realfft/rustfft (src/fft_convolver.rs:21-64) ---- */
+/* ---- real FFT stand-in for realfft/rustfft (src/fft_convolver.rs:7-50) ---- */
 typedef struct orc_plan orc_plan;
 orc_plan *orc_plan_new(size_t n);            /* n = real length, power of two >= 2, or 0 */
 void orc_plan_free(orc_plan *p);
 /* unnormalised forward: n reals -> n/2+1 complex.  `in` is NOT clobbered here. */
 void orc_rfft_forward(const orc_plan *p, const float *in, orc_cpx *out);
-/* Fft::inverse: unnormalised C2R followed by division of every sample by n (:55-63) */
+/* Fft::inverse: unnormalised C2R followed by division of every sample by n (:41-49) */
 void orc_rfft_inverse(const orc_plan *p, const orc_cpx *in, float *out);
 
-/* free helpers (src/fft_convolver.rs:66-98) */
+/* free helpers (src/fft_convolver.rs:52-84) */
 size_t orc_complex_size(size_t n);
 void orc_complex_multiply_accumulate(orc_cpx *result, const orc_cpx *a, const orc_cpx *b, size_t len);
 
-/* ---- FFTConvolver (src/fft_convolver.rs:100-321) ---- */
+/* ---- FFTConvolver (src/fft_convolver.rs:86-307) ---- */
 typedef struct orc_fftconv orc_fftconv;
 orc_fftconv *orc_fftconv_init(const float *ir, size_t ir_len, size_t block_size, size_t max_response_length);
 orc_fftconv *orc_fftconv_default(void);
@@ -69,7 +69,7 @@ const orc_cpx *orc_fftconv_segment(const orc_fftconv *c, size_t i);
 const orc_cpx *orc_fftconv_premul(const orc_fftconv *c);
 const float *orc_fftconv_overlap(const orc_fftconv *c);
 
-/* ---- TwoStageFFTConvolver (src/fft_convolver.rs:337-540) ---- */
+/* ---- TwoStageFFTConvolver (src/fft_convolver.rs:323-526) ---- */
 size_t orc_compute_tail_block_size(size_t head_len, size_t response_len);
 typedef struct orc_twostage orc_twostage;
 orc_twostage *orc_twostage_init(const float *ir, size_t ir_len, size_t block_size, size_t max_response_length);

@@ -121,7 +121,7 @@ def _check(rc: int, what: str):
 
 
 class FFTConvolver:
-    """Oracle mirror of the reference FFTConvolver (src/fft_convolver.rs:100-321)."""
+    """Oracle mirror of the reference FFTConvolver (src/fft_convolver.rs:86-307)."""
 
     def __init__(self, handle, lib: OracleLib):
         self._h, self._lib = handle, lib
@@ -190,7 +190,7 @@ class FFTConvolver:
 
 
 class TwoStageFFTConvolver:
-    """Oracle mirror of TwoStageFFTConvolver (src/fft_convolver.rs:337-540)."""
+    """Oracle mirror of TwoStageFFTConvolver (src/fft_convolver.rs:323-526)."""
 
     def __init__(self, handle, lib):
         self._h, self._lib = handle, lib

@@ -32,7 +32,7 @@ def rfft_f32(x: np.ndarray) -> np.ndarray:
 
 
 def irfft_f32(X: np.ndarray, n: int) -> np.ndarray:
-    """Fft::inverse (:55-63): unnormalised C2R then `/= len as f32`.  numpy's irfft already
+    """Fft::inverse (:41-49): unnormalised C2R then `/= len as f32`.  numpy's irfft already
     normalises by 1/n; for power-of-two n that is the same scaling up to the last bit."""
     out = np.fft.irfft(X.astype(np.complex64, copy=False), n=n)
     assert out.dtype == np.float32
@@ -40,7 +40,7 @@ def irfft_f32(X: np.ndarray, n: int) -> np.ndarray:
 
 
 def cmac(result: np.ndarray, a: np.ndarray, b: np.ndarray) -> None:
-    """complex_multiply_accumulate (:76-88), each operation rounded to f32 separately."""
+    """complex_multiply_accumulate (:62-74), each operation rounded to f32 separately."""
     ar, ai, br, bi = a.real, a.imag, b.real, b.imag
     pr = (ar * br).astype(np.float32) - (ai * bi).astype(np.float32)
     pi = (ar * bi).astype(np.float32) + (ai * br).astype(np.float32)
@@ -49,7 +49,7 @@ def cmac(result: np.ndarray, a: np.ndarray, b: np.ndarray) -> None:
 
 
 class FFTConvolverNP:
-    """:100-321"""
+    """:86-307"""
 
     def __init__(self):
         self.ir_len = self.block_size = self.seg_count = self.active_seg_count = 0
@@ -151,7 +151,7 @@ class FFTConvolverNP:
 
 
 def compute_tail_block_size(head_len: int, response_len: int) -> int:
-    """:528-540 in f32."""
+    """:514-526 in f32."""
     f = np.float32
     kn = (f(1.5) * f(head_len)) / (f(2.0) * np.log(f(2.0)))
     b = -kn + np.sqrt(kn * kn + f(response_len) * f(head_len), dtype=np.float32)
@@ -160,7 +160,7 @@ def compute_tail_block_size(head_len: int, response_len: int) -> int:
 
 
 class TwoStageNP:
-    """:337-526"""
+    """:323-512"""
 
     @classmethod
     def init(cls, ir, block_size, max_response_length, forced_tail=0):

@@ -2,7 +2,7 @@
 //!
 //! The Rust host keeps exactly what the reference keeps on the host: the block scheduler, the
 //! input-buffer fill and the segment-ring rotation of `FFTConvolver::process`
-//! (reference src/fft_convolver.rs:236-245, 291-306); the arithmetic of every chunk
+//! (reference src/fft_convolver.rs:222-231, :277-292); the arithmetic of every chunk
 //! (forward FFT, delay-line MAC, inverse FFT + overlap-add) is the four `fcb_engine_*` stage
 //! calls.  Contract violations surface as `panic!`, like the reference.
 //!
@@ -87,7 +87,7 @@ pub trait Convolution: Clone {
 }
 
 /// Drop-in for `fft_convolver::FFTConvolver` (mono).  Host state = the reference's scalars
-/// (src/fft_convolver.rs:102-105, 113, 115); everything else lives on the device.
+/// (src/fft_convolver.rs:88-91, :99, :101); everything else lives on the device.
 pub struct CudaFFTConvolver {
     engine: *mut FcbEngine,
     ir_len: usize,
@@ -115,7 +115,7 @@ impl Convolution for CudaFFTConvolver {
         };
         let mut engine = std::ptr::null_mut();
         check(unsafe { fcb_engine_create(&desc, &mut engine) });
-        // K5: segment FFTs of the zero-padded IR (src/fft_convolver.rs:145-156)
+        // K5: segment FFTs of the zero-padded IR (src/fft_convolver.rs:131-142)
         check(unsafe {
             fcb_engine_set_ir(engine, 0, 1, impulse_response.as_ptr(), impulse_response.len(),
                               impulse_response.len(), 0)

@@ -53,7 +53,7 @@ def test_multi_block_calls_are_bit_identical_to_block_by_block(F, C, B, L, calls
     b = _run_calls(F, h, B, L, x, calls, multi=False)
     assert np.array_equal(a, b)
     # and the same signal cut block by block: identical bits when every call was whole blocks, f32 rounding
-    # otherwise (a partially filled block is transformed as it stands, src/fft_convolver.rs:248-255)
+    # otherwise (a partially filled block is transformed as it stands, src/fft_convolver.rs:234-241)
     blocks = [B] * (n // B) + ([n % B] if n % B else [])
     c = _run_calls(F, h, B, L, x, blocks, multi=False)
     if all(k % B == 0 for k in calls):

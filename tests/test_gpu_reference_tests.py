@@ -25,7 +25,7 @@ def _delta(n=1024):
 
 
 def test_fft_convolver_passthrough(F):
-    """src/fft_convolver.rs:323-335"""
+    """src/fft_convolver.rs:309-321"""
     conv = F.FFTConvolver.init(_delta(), 1024, 1024)
     out = np.zeros(1024, np.float32)
     conv.process(np.ones(1024, np.float32), out)
@@ -33,7 +33,7 @@ def test_fft_convolver_passthrough(F):
 
 
 def test_fft_twostage_convolver_passthrough(F):
-    """src/fft_convolver.rs:542-554"""
+    """src/fft_convolver.rs:528-540"""
     conv = F.TwoStageFFTConvolver.init(_delta(), 1024, 1024)
     assert conv.tail_block_size == 1024
     out = np.zeros(1024, np.float32)

@@ -1,6 +1,6 @@
 """IR-partition sharding of the convolution matrix, CPU side: the segment-range rule partitions
 [0, S), and per-rank partial spectra summed with a gloo all-reduce (world size 2) equal the
-unsharded delay-line sum (src/fft_convolver.rs:258-275 is associative over segments)."""
+unsharded delay-line sum (src/fft_convolver.rs:244-261 is associative over segments)."""
 import os
 import socket
 

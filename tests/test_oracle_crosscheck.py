@@ -56,7 +56,7 @@ def test_rfft_matches_numpy_f64():
 
 
 def test_chunk_size_invariance():
-    """zero added latency / arbitrary call sizes (src/fft_convolver.rs:236-245): random
+    """zero added latency / arbitrary call sizes (src/fft_convolver.rs:222-231): random
     chunk sizes 1..99 give the block-sized result up to f32 rounding."""
     B, L = 64, 1000
     h = oracle.gen_ir(1, 0, L)
@@ -88,7 +88,7 @@ def test_twostage_vs_truth_partial_calls():
 
 
 def test_twostage_non_power_of_two_head_panics():
-    """head 48, T = 512: tail_input overflows on the 11th block (src/fft_convolver.rs:473)"""
+    """head 48, T = 512: tail_input overflows on the 11th block (src/fft_convolver.rs:459)"""
     h = oracle.gen_ir(0, 0, 5000)
     o = oracle.TwoStageFFTConvolver.init(h, 48, 5000)
     blk, out = np.zeros(48, np.float32), np.zeros(48, np.float32)
@@ -103,14 +103,14 @@ def test_twostage_non_power_of_two_head_panics():
                                       (256, 48000, 4096), (512, 480000, 16384), (128, 140002, 4096),
                                       (128, 140003, 8192)])
 def test_tail_block_size_table(head, L, T):
-    """src/fft_convolver.rs:528-540 evaluated in f32."""
+    """src/fft_convolver.rs:514-526 evaluated in f32."""
     assert oracle.compute_tail_block_size(head, L) == T
     assert oracle_np.compute_tail_block_size(head, L) == T
 
 
 def test_update_changes_segment_count_literal():
     """update() with a shorter IR re-interprets the ring modulo the new count
-    (src/fft_convolver.rs:204,262,301-305); C and numpy restatements must agree."""
+    (src/fft_convolver.rs:190, :248, :287-291); C and numpy restatements must agree."""
     B, L = 32, 320
     h0, h1 = oracle.gen_ir(5, 0, L), oracle.gen_ir(5, 1, 100)
     x = oracle.gen_noise(5, 0, 32 * 40)

@@ -29,7 +29,7 @@ def _delta(n=1024):
 
 
 def test_fft_convolver_passthrough(impl):
-    """src/fft_convolver.rs:323-335"""
+    """src/fft_convolver.rs:309-321"""
     conv = impl[0].init(_delta(), 1024, 1024)
     out = np.zeros(1024, np.float32)
     conv.process(np.ones(1024, np.float32), out)
@@ -37,7 +37,7 @@ def test_fft_convolver_passthrough(impl):
 
 
 def test_fft_twostage_convolver_passthrough(impl):
-    """src/fft_convolver.rs:542-554"""
+    """src/fft_convolver.rs:528-540"""
     conv = impl[1].init(_delta(), 1024, 1024)
     out = np.zeros(1024, np.float32)
     conv.process(np.ones(1024, np.float32), out)
@@ -174,7 +174,7 @@ def test_reset(kind):
 
 
 def test_reference_panics():
-    """contract violations that panic in the reference (src/fft_convolver.rs:120-124,
+    """contract violations that panic in the reference (src/fft_convolver.rs:106-110,
     191-193, 422-424, 428; src/crossfade_convolver.rs:80-82)"""
     with pytest.raises(oracle.OraclePanic):
         oracle.FFTConvolver.init(np.zeros(10, np.float32), 4, 5)
