@@ -14,6 +14,9 @@ namespace fcb {
 
 extern thread_local std::string g_last_error;
 extern std::atomic<uint64_t> g_launches;
+// every device / pinned allocation, stream or event creation and their releases made by this library
+// (fcb_debug_alloc_count): update() and process() must not move it in the steady state (src/lib.rs:8)
+extern std::atomic<uint64_t> g_resource_calls;
 
 inline int fail(int code, const char *fmt, ...)
 {
@@ -25,6 +28,18 @@ inline int fail(int code, const char *fmt, ...)
     g_last_error = buf;
     return code;
 }
+
+// count the resource calls where they are made (a function-like macro is not re-expanded inside itself)
+#define cudaMalloc(...) (++::fcb::g_resource_calls, cudaMalloc(__VA_ARGS__))
+#define cudaFree(...) (++::fcb::g_resource_calls, cudaFree(__VA_ARGS__))
+#define cudaHostAlloc(...) (++::fcb::g_resource_calls, cudaHostAlloc(__VA_ARGS__))
+#define cudaFreeHost(...) (++::fcb::g_resource_calls, cudaFreeHost(__VA_ARGS__))
+#define cudaStreamCreateWithFlags(...) (++::fcb::g_resource_calls, cudaStreamCreateWithFlags(__VA_ARGS__))
+#define cudaStreamCreateWithPriority(...) (++::fcb::g_resource_calls, cudaStreamCreateWithPriority(__VA_ARGS__))
+#define cudaStreamDestroy(...) (++::fcb::g_resource_calls, cudaStreamDestroy(__VA_ARGS__))
+#define cudaEventCreateWithFlags(...) (++::fcb::g_resource_calls, cudaEventCreateWithFlags(__VA_ARGS__))
+#define cudaEventCreate(...) (++::fcb::g_resource_calls, cudaEventCreate(__VA_ARGS__))
+#define cudaEventDestroy(...) (++::fcb::g_resource_calls, cudaEventDestroy(__VA_ARGS__))
 
 #define FCB_CUDA(expr)                                                                              \
     do {                                                                                            \

@@ -407,16 +407,27 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
     const bool live = c < a.nchan;
 
     if (a.gather_n > 0) { // wait for every shard's partial spectra (peer stores + release flag)
+        __shared__ int s_timed_out;
+        if (threadIdx.x == 0) s_timed_out = 0;
+        __syncthreads();
         if (threadIdx.x < a.gather_n) {
             long long spins = 0;
             while (ld_acquire_sys(a.gather_flags + threadIdx.x) != a.gather_seq) {
                 if (++spins > (1ll << 26)) {
-                    *a.gather_err = 1;
+                    *reinterpret_cast<volatile int *>(a.gather_err) = 1; // mapped host word: the next call fails loudly
+                    s_timed_out = 1;
                     break;
                 }
             }
         }
         __syncthreads();
+        if (s_timed_out) {
+            // a shard never published: the inbox holds a stale or partial sum.  Never turn that into audio —
+            // this block is silence, the overlap is left alone, and the host sees the error word.
+            if (live)
+                for (int i = tid; i < a.n; i += T) a.out[c * a.out_stride + i] = 0.f;
+            return;
+        }
     }
 
     // 1. conv, packed layout (bin 0 = {DC, Nyquist}: two real products)

@@ -961,12 +961,14 @@ extern "C" int fcb_crossfade_update(fcb_crossfade *c, const float *irs, size_t l
     // :61-62 — copy + zero-fill the rest, straight into the device copy (stream-ordered after any
     // kernel still reading a previous pending response)
     FCB_CUDA(cudaSetDevice(c->device));
+    // a convolver built over ONE shared response (fcb_crossfade_new on a shared_ir FFTConvolver) is handed one row
+    const size_t rows = c->b->opt.shared_ir ? 1 : c->C;
     if (len)
         FCB_CUDA(cudaMemcpy2DAsync(c->stored_response, c->stored_len * sizeof(float), irs, len * sizeof(float),
-                                   len * sizeof(float), c->C, cudaMemcpyHostToDevice, c->stream));
+                                   len * sizeof(float), rows, cudaMemcpyHostToDevice, c->stream));
     if (c->stored_len > len)
         FCB_CUDA(cudaMemset2DAsync(c->stored_response + len, c->stored_len * sizeof(float), 0,
-                                   (c->stored_len - len) * sizeof(float), c->C, c->stream));
+                                   (c->stored_len - len) * sizeof(float), rows, c->stream));
     FCB_CUDA(cudaStreamSynchronize(c->stream)); // the caller's buffer is free to change on return
     c->response_pending = true;
     return FCB_OK;

@@ -195,7 +195,9 @@ struct fcb_mimo {
     // peer exchange (see PeerPub)
     size_t shard_index = 0, shard_count = 1;
     unsigned char *inbox = nullptr;      // [2][G][n_conv] float2 then [2][G] flags, one allocation (IPC-exported)
-    unsigned int *peer_done = nullptr;   // CTA counter + error word
+    unsigned int *peer_done = nullptr;   // CTA counter of the last-CTA pattern
+    int *peer_err_h = nullptr, *peer_err_d = nullptr; // error word in mapped pinned memory (host view / device alias):
+                                                      // K3 sets it when a flag never arrives, every later call reads it
     void *peer_base[FCB_MAX_PEERS] = {}; // every shard's inbox in my address space
     bool peer_opened[FCB_MAX_PEERS] = {};
     bool peer_on = false;
@@ -244,6 +246,7 @@ extern "C" void fcb_mimo_destroy(fcb_mimo *m)
         if (m->peer_opened[g]) cudaIpcCloseMemHandle(m->peer_base[g]);
     cudaFree(m->inbox);
     cudaFree(m->peer_done);
+    if (m->peer_err_h) cudaFreeHost(m->peer_err_h);
     if (m->side) cudaStreamDestroy(m->side);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_k1) cudaEventDestroy(m->ev_k1);
@@ -402,11 +405,23 @@ extern "C" int fcb_mimo_reset(fcb_mimo *m)
     return FCB_OK;
 }
 
+// Peer exchange health: K3 raises the mapped error word when a shard's flag never arrives (it then emits silence for
+// that block instead of summing a stale inbox).  Reading it is one host load, so every partial / finish / sync call
+// checks it and fails loudly from the first call after the fault on — no synchronisation needed.
+static int peer_check(const fcb_mimo *m)
+{
+    if (m->peer_on && m->peer_err_h && *reinterpret_cast<volatile int *>(m->peer_err_h))
+        return fail(FCB_ERR_CUDA, "peer exchange: a shard's partial spectra never arrived (flag wait timed out); "
+                                  "output blocks since then are silence");
+    return FCB_OK;
+}
+
 // K1 on the NS*IN input blocks, K2 over this shard's segments, reduction over `in` -> conv
 extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_stride)
 {
     if (!m || !in_dev) return fail(FCB_ERR_ARG, "fcb_mimo_partial_dev: NULL argument");
     if (m->S == 0) return FCB_OK;
+    FCB_TRY(peer_check(m));
     FCB_CUDA(cudaSetDevice(m->device));
     const size_t B = m->B, ns = m->n_streams, pairs = m->n_out * m->n_in;
     if (m->peer_on) m->peer_seq++;
@@ -519,6 +534,7 @@ extern "C" float *fcb_mimo_conv_buffer(fcb_mimo *m, size_t *n_floats)
 extern "C" int fcb_mimo_finish_dev(fcb_mimo *m, float *out_dev, size_t out_stride)
 {
     if (!m || !out_dev) return fail(FCB_ERR_ARG, "fcb_mimo_finish_dev: NULL argument");
+    FCB_TRY(peer_check(m));
     FCB_CUDA(cudaSetDevice(m->device));
     const size_t B = m->B, n_so = m->n_streams * m->n_out;
     if (m->S == 0) {
@@ -542,7 +558,7 @@ extern "C" int fcb_mimo_finish_dev(fcb_mimo *m, float *out_dev, size_t out_strid
         a.gather_flags = reinterpret_cast<const unsigned int *>(m->inbox + m->inbox_data_bytes()) + par * G;
         a.gather_seq = m->peer_seq;
         a.gather_n = (int)G;
-        a.gather_err = reinterpret_cast<int *>(m->peer_done + 1);
+        a.gather_err = m->peer_err_d;
     }
     FCB_TRY(run_inverse(m->logb, m->tw, m->stream, a));
     m->current = m->current > 0 ? m->current - 1 : m->S - 1; // src/fft_convolver.rs:287-291
@@ -570,12 +586,7 @@ extern "C" int fcb_mimo_sync(fcb_mimo *m)
     if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
     FCB_CUDA(cudaSetDevice(m->device));
     FCB_CUDA(cudaStreamSynchronize(m->stream));
-    if (m->peer_on) {
-        int err = 0;
-        FCB_CUDA(cudaMemcpy(&err, m->peer_done + 1, sizeof err, cudaMemcpyDeviceToHost));
-        if (err) return fail(FCB_ERR_CUDA, "peer exchange: a shard's partial spectra never arrived (flag wait timed out)");
-    }
-    return FCB_OK;
+    return peer_check(m);
 }
 
 // ---- peer exchange set-up -------------------------------------------------------------------
@@ -589,6 +600,9 @@ static int peer_alloc(fcb_mimo *m)
     FCB_CUDA(cudaMemset(m->inbox, 0, bytes));
     FCB_CUDA(cudaMalloc((void **)&m->peer_done, 2 * sizeof(unsigned int)));
     FCB_CUDA(cudaMemset(m->peer_done, 0, 2 * sizeof(unsigned int)));
+    FCB_CUDA(cudaHostAlloc((void **)&m->peer_err_h, sizeof(int), cudaHostAllocMapped));
+    *m->peer_err_h = 0;
+    FCB_CUDA(cudaHostGetDevicePointer((void **)&m->peer_err_d, m->peer_err_h, 0));
     FCB_CUDA(cudaDeviceSynchronize());
     return FCB_OK;
 }

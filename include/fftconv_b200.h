@@ -310,7 +310,12 @@ void *fcb_mimo_stream(fcb_mimo *m);
 #define FCB_MAX_PEERS 16
 int fcb_mimo_peer_export(fcb_mimo *m, unsigned char *handle_out);
 int fcb_mimo_peer_attach(fcb_mimo *m, const unsigned char *handles /* [shard_count][FCB_PEER_HANDLE_BYTES] */);
-/* same-process variant: this shard's inbox as a device pointer / attach with the G inbox pointers */
+/* Failure behaviour: K3 waits a bounded time for the G flags.  If one never arrives it writes SILENCE for that block
+ * (never a sum over a stale inbox), leaves the overlap alone and raises an error word in mapped host memory; every
+ * later fcb_mimo_partial_dev / fcb_mimo_finish_dev / fcb_mimo_sync call returns FCB_ERR_CUDA.
+ * same-process variant: this shard's inbox as a device pointer / attach with the G inbox pointers.  Shards that share
+ * ONE GPU must all enqueue fcb_mimo_partial_dev before any of them enqueues fcb_mimo_finish_dev: a K3 spinning on a
+ * flag can otherwise hold the SMs its peer's producer kernel is waiting for. */
 void *fcb_mimo_peer_inbox(fcb_mimo *m);
 int fcb_mimo_peer_attach_ptrs(fcb_mimo *m, void *const *inboxes);
 /* test hook (host only): segment chunks (count, segments per chunk) the CUDA-core matrix kernel uses for a problem */

@@ -7,4 +7,5 @@ from .oracle_c import (  # noqa: F401
     OracleLib, load, build,
     FFTConvolver, TwoStageFFTConvolver, CrossfadeConvolver, Crossfader,
     compute_tail_block_size, gen_noise, gen_ir, direct_conv_f64, OraclePanic,
+    batch_twostage, batch_crossfade, batch_fftconv,
 )

@@ -448,6 +448,7 @@ struct orc_twostage {
     orc_fftconv *head_convolver, *tail_convolver0, *tail_convolver;
     float *tail_output0, *tail_precalculated0, *tail_output, *tail_precalculated, *tail_input;
     size_t tail_input_fill, precalculated_pos;
+    size_t max_response_length; /* not a field of the reference struct; only orc_twostage_update_ext reads it */
 };
 
 /* :340-406 */
@@ -464,6 +465,7 @@ orc_twostage *orc_twostage_init_tail(const float *ir, size_t n_ir, size_t block_
     orc_twostage *c = (orc_twostage *)calloc(1, sizeof *c);
     c->head_block_size = head;
     c->tail_block_size = T;
+    c->max_response_length = L;
     size_t head_ir_len = L < T ? L : T; /* :352-354 */
     c->head_convolver = orc_fftconv_init(padded, head_ir_len, head, head_ir_len);
     if (L > T) { /* :356-368 */
@@ -522,6 +524,29 @@ int orc_twostage_update(orc_twostage *c, const float *ir, size_t len)
 {
     (void)c; (void)ir; (void)len;
     return ORC_PANIC;
+}
+
+/* EXTENSION — not in the reference (its method is todo!(), :408-410; SURVEY.md §8(f)2 asks for it).
+ * Defined as the per-stage FFTConvolver::update (:174-213) on the re-sliced response, sliced exactly
+ * like init slices it (:349-384): the response is zero-padded to max_response_length, head gets
+ * [0, min(L,T)), tail0 [T, T + min(L-T,T)) when L > T, tail [2T, L) when L > 2T.  Every stage is
+ * handed its FULL slice length, so active_seg_count stays seg_count and no ring slot is re-read
+ * modulo a new count.  Like FFTConvolver::update it keeps everything already heard: the input
+ * rings, the partially filled blocks, tail_input and the tail outputs computed with the old
+ * response (tail_output*, tail_precalculated* — audio already in flight); it zeroes each stage's
+ * overlap and pre_multiplied (:185-188).  Panics like FFTConvolver::update (:177-179) when the
+ * response is longer than max_response_length. */
+int orc_twostage_update_ext(orc_twostage *c, const float *ir, size_t len)
+{
+    size_t L = c->max_response_length, T = c->tail_block_size;
+    if (len > L) return ORC_PANIC;
+    float *padded = (float *)calloc(L ? L : 1, sizeof(float));
+    if (len) memcpy(padded, ir, len * sizeof(float));
+    int rc = orc_fftconv_update(c->head_convolver, padded, L < T ? L : T);
+    if (!rc && L > T) rc = orc_fftconv_update(c->tail_convolver0, padded + T, (L - T) < T ? (L - T) : T);
+    if (!rc && L > 2 * T) rc = orc_fftconv_update(c->tail_convolver, padded + 2 * T, L - 2 * T);
+    free(padded);
+    return rc;
 }
 
 static void swap_ptr(float **a, float **b) { float *t = *a; *a = *b; *b = t; }
@@ -756,6 +781,28 @@ int orc_crossfade_process(orc_crossfade *c, const float *input, size_t in_len, f
 /* :80-82 — todo!() */
 int orc_crossfade_reset(orc_crossfade *c) { (void)c; return ORC_PANIC; }
 
+/* EXTENSION — not in the reference (its method is todo!(), :80-82; SURVEY.md §8(f)2 asks for it).
+ * Defined by analogy with FFTConvolver::reset (src/fft_convolver.rs:296-306: forget all audio,
+ * keep the responses): both convolvers are reset, buffer_a / buffer_b are zeroed, and a fade in
+ * progress is completed at once — the crossfader lands where `mix` would have left it when
+ * counter == fading_samples (:261-273: Reached(target), mix_value 0.0 for A / 1.0 for B; the step
+ * keeps the sign fade_into gave it), so the most recently requested response is the one heard.
+ * A response still pending (stored_response, :58-63) stays pending and is swapped in by the next
+ * process() exactly as :67-70 does when no fade is running. */
+int orc_crossfade_reset_ext(orc_crossfade *c)
+{
+    orc_fftconv_reset(c->convolver_a);
+    orc_fftconv_reset(c->convolver_b);
+    memset(c->buffer_a, 0, (c->max_buffer_size ? c->max_buffer_size : 1) * sizeof(float));
+    memset(c->buffer_b, 0, (c->max_buffer_size ? c->max_buffer_size : 1) * sizeof(float));
+    if (c->crossfader.approaching) {
+        c->crossfader.approaching = 0;
+        c->crossfader.mix_value = c->crossfader.target == 0 ? 0.0f : 1.0f;
+    }
+    c->crossfader.counter = 0;
+    return ORC_OK;
+}
+
 /* ------------------------------------------------------------------------------------------
  * synthetic data
  * ---------------------------------------------------------------------------------------- */
@@ -854,4 +901,52 @@ double orc_batch_fftconv_run(size_t channels, size_t block_size, size_t ir_len, 
     for (size_t c = 0; c < channels; c++) orc_fftconv_free(cv[c]);
     free(cv);
     return t1 - t0;
+}
+
+/* C independent TwoStageFFTConvolvers (BASELINE configs[1]); calls of n_per_call <= head samples.
+ * update_every > 0: orc_twostage_update_ext with irs_upd[(k / update_every - 1) % n_upd] before call k */
+double orc_batch_twostage_run(size_t channels, size_t head_block, size_t ir_len, size_t forced_tail,
+                              const float *irs, const float *irs_upd, size_t n_upd, size_t update_every,
+                              const float *in, float *out, size_t n_per_call, size_t calls, int threads)
+{
+    orc_twostage **cv = (orc_twostage **)malloc(sizeof(*cv) * channels);
+    if (threads < 1) threads = 1;
+    size_t total = n_per_call * calls;
+    double t0 = now_s();
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (long c = 0; c < (long)channels; c++) {
+        cv[c] = orc_twostage_init_tail(irs + (size_t)c * ir_len, ir_len, head_block, ir_len, forced_tail);
+        for (size_t k = 0; k < calls; k++) {
+            if (update_every && n_upd && k && k % update_every == 0)
+                orc_twostage_update_ext(cv[c], irs_upd + (((k / update_every - 1) % n_upd) * channels + (size_t)c) * ir_len, ir_len);
+            orc_twostage_process(cv[c], in + (size_t)c * total + k * n_per_call, n_per_call,
+                                 out + (size_t)c * total + k * n_per_call, n_per_call);
+        }
+        orc_twostage_free(cv[c]);
+    }
+    double t1 = now_s();
+    free(cv);
+    return t1 - t0;
+}
+
+/* C independent CrossfadeConvolver::init(h, block, ir_len) (BASELINE configs[2]); every call is one
+ * whole block; update(irs_upd[(k / update_every - 1) % n_upd]) before call k for k = update_every, 2*update_every, ... */
+double orc_batch_crossfade_run(size_t channels, size_t block, size_t ir_len, const float *irs,
+                               const float *irs_upd, size_t n_upd, size_t update_every, const float *in,
+                               float *out, size_t calls, int threads)
+{
+    if (threads < 1) threads = 1;
+    size_t total = block * calls;
+    double t0 = now_s();
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (long c = 0; c < (long)channels; c++) {
+        orc_crossfade *x = orc_crossfade_init(irs + (size_t)c * ir_len, ir_len, block, ir_len);
+        for (size_t k = 0; k < calls; k++) {
+            if (update_every && n_upd && k && k % update_every == 0)
+                orc_crossfade_update(x, irs_upd + (((k / update_every - 1) % n_upd) * channels + (size_t)c) * ir_len, ir_len);
+            orc_crossfade_process(x, in + (size_t)c * total + k * block, block, out + (size_t)c * total + k * block, block);
+        }
+        orc_crossfade_free(x);
+    }
+    return now_s() - t0;
 }

@@ -80,6 +80,9 @@ orc_twostage *orc_twostage_init_tail(const float *ir, size_t ir_len, size_t bloc
 orc_twostage *orc_twostage_clone(const orc_twostage *c);
 void orc_twostage_free(orc_twostage *c);
 int orc_twostage_update(orc_twostage *c, const float *ir, size_t len); /* todo!() => ORC_PANIC */
+/* EXTENSION beyond the reference (which leaves it todo!()): per-stage FFTConvolver::update on the
+ * response re-sliced like init does; semantics written out above its definition */
+int orc_twostage_update_ext(orc_twostage *c, const float *ir, size_t len);
 void orc_twostage_reset(orc_twostage *c);
 int orc_twostage_process(orc_twostage *c, const float *in, size_t in_len, float *out, size_t out_len);
 size_t orc_twostage_tail_block_size(const orc_twostage *c);
@@ -109,6 +112,9 @@ void orc_crossfade_free(orc_crossfade *c);
 int orc_crossfade_update(orc_crossfade *c, const float *ir, size_t len);
 int orc_crossfade_process(orc_crossfade *c, const float *in, size_t in_len, float *out, size_t out_len);
 int orc_crossfade_reset(orc_crossfade *c); /* todo!() => ORC_PANIC */
+/* EXTENSION beyond the reference (which leaves it todo!()): forget all audio, finish a running fade
+ * at once, keep the responses and a pending update; semantics written out above its definition */
+int orc_crossfade_reset_ext(orc_crossfade *c);
 int orc_crossfade_is_crossfading(const orc_crossfade *c);
 const orc_crossfader *orc_crossfade_crossfader(const orc_crossfade *c);
 
@@ -127,6 +133,14 @@ double orc_batch_fftconv_run(size_t channels, size_t block_size, size_t ir_len,
                              const float *irs /* [C][ir_len] */, const float *in, float *out,
                              size_t n_per_call, size_t calls, int threads);
 int orc_max_threads(void);
+/* the same for C TwoStageFFTConvolvers / C CrossfadeConvolver::init (full-count parity of BASELINE
+ * configs[1] and configs[2]); irs_upd: [n_upd][C][ir_len], applied every `update_every` calls */
+double orc_batch_twostage_run(size_t channels, size_t head_block, size_t ir_len, size_t forced_tail,
+                              const float *irs, const float *irs_upd, size_t n_upd, size_t update_every,
+                              const float *in, float *out, size_t n_per_call, size_t calls, int threads);
+double orc_batch_crossfade_run(size_t channels, size_t block, size_t ir_len, const float *irs,
+                               const float *irs_upd, size_t n_upd, size_t update_every, const float *in,
+                               float *out, size_t calls, int threads);
 
 #ifdef __cplusplus
 }

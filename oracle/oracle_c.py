@@ -75,6 +75,7 @@ class OracleLib:
         sig("orc_twostage_clone", _vp, _vp)
         sig("orc_twostage_free", None, _vp)
         sig("orc_twostage_update", C.c_int, _vp, _f32p, _sz)
+        sig("orc_twostage_update_ext", C.c_int, _vp, _f32p, _sz)
         sig("orc_twostage_reset", None, _vp)
         sig("orc_twostage_process", C.c_int, _vp, _f32p, _sz, _f32p, _sz)
         sig("orc_twostage_tail_block_size", _sz, _vp)
@@ -88,6 +89,7 @@ class OracleLib:
         sig("orc_crossfade_update", C.c_int, _vp, _f32p, _sz)
         sig("orc_crossfade_process", C.c_int, _vp, _f32p, _sz, _f32p, _sz)
         sig("orc_crossfade_reset", C.c_int, _vp)
+        sig("orc_crossfade_reset_ext", C.c_int, _vp)
         sig("orc_crossfade_is_crossfading", C.c_int, _vp)
         sig("orc_crossfade_crossfader", C.POINTER(_CrossfaderStruct), _vp)
         sig("orc_mix64", C.c_uint64, C.c_uint64)
@@ -96,6 +98,8 @@ class OracleLib:
         sig("orc_direct_conv_f64", None, _f32p, _sz, _f32p, _sz, _f64p)
         sig("orc_batch_fftconv_run", C.c_double, _sz, _sz, _sz, _f32p, _f32p, _f32p, _sz, _sz, C.c_int)
         sig("orc_max_threads", C.c_int)
+        sig("orc_batch_twostage_run", C.c_double, _sz, _sz, _sz, _sz, _f32p, _vp, _sz, _sz, _f32p, _f32p, _sz, _sz, C.c_int)
+        sig("orc_batch_crossfade_run", C.c_double, _sz, _sz, _sz, _f32p, _vp, _sz, _sz, _f32p, _f32p, _sz, C.c_int)
 
 
 _LIB: OracleLib | None = None
@@ -211,6 +215,12 @@ class TwoStageFFTConvolver:
         r = _f32(response)
         _check(self._lib.lib.orc_twostage_update(self._h, r, r.size), "not yet implemented")
 
+    def update_ext(self, response):
+        """EXTENSION beyond the reference (todo!() there): per-stage FFTConvolver::update on the re-sliced response."""
+        r = _f32(response)
+        _check(self._lib.lib.orc_twostage_update_ext(self._h, r, r.size),
+               "New impulse response is longer than initialized length")
+
     def reset(self):
         self._lib.lib.orc_twostage_reset(self._h)
 
@@ -283,6 +293,10 @@ class CrossfadeConvolver:
     def reset(self):
         _check(self._lib.lib.orc_crossfade_reset(self._h), "not yet implemented")
 
+    def reset_ext(self):
+        """EXTENSION beyond the reference (todo!() there): forget all audio, finish a running fade at once."""
+        _check(self._lib.lib.orc_crossfade_reset_ext(self._h), "reset failed")
+
     def is_crossfading(self) -> bool:
         return bool(self._lib.lib.orc_crossfade_is_crossfading(self._h))
 
@@ -317,3 +331,46 @@ def direct_conv_f64(x, h) -> np.ndarray:
     y = np.empty(x.size, dtype=np.float64)
     load().lib.orc_direct_conv_f64(x, x.size, h, h.size, y)
     return y
+
+
+def batch_twostage(irs, head_block: int, x, n_per_call: int, *, forced_tail: int = 0, irs_upd=None,
+                   update_every: int = 0, threads: int | None = None) -> np.ndarray:
+    """C independent TwoStageFFTConvolvers over x [C, calls*n_per_call] (OpenMP over channels)."""
+    lib = load()
+    irs, x = _f32(irs), _f32(x)
+    Cn, L = irs.shape
+    calls = x.shape[1] // n_per_call
+    out = np.zeros((Cn, calls * n_per_call), np.float32)
+    xin = np.ascontiguousarray(x[:, :calls * n_per_call])
+    upd = _f32(irs_upd) if irs_upd is not None else None
+    lib.lib.orc_batch_twostage_run(Cn, head_block, L, forced_tail, irs, upd.ctypes.data if upd is not None else None,
+                                   upd.shape[0] if upd is not None else 0, update_every, xin, out, n_per_call, calls,
+                                   threads or lib.lib.orc_max_threads())
+    return out
+
+
+def batch_crossfade(irs, block: int, x, *, irs_upd=None, update_every: int = 0, threads: int | None = None) -> np.ndarray:
+    """C independent CrossfadeConvolver::init(h, block, len) over x [C, calls*block] (OpenMP over channels)."""
+    lib = load()
+    irs, x = _f32(irs), _f32(x)
+    Cn, L = irs.shape
+    calls = x.shape[1] // block
+    out = np.zeros((Cn, calls * block), np.float32)
+    xin = np.ascontiguousarray(x[:, :calls * block])
+    upd = _f32(irs_upd) if irs_upd is not None else None
+    lib.lib.orc_batch_crossfade_run(Cn, block, L, irs, upd.ctypes.data if upd is not None else None,
+                                    upd.shape[0] if upd is not None else 0, update_every, xin, out, calls,
+                                    threads or lib.lib.orc_max_threads())
+    return out
+
+
+def batch_fftconv(irs, block: int, x, n_per_call: int, threads: int | None = None) -> np.ndarray:
+    """C independent FFTConvolvers over x [C, calls*n_per_call] (OpenMP over channels)."""
+    lib = load()
+    irs, x = _f32(irs), _f32(x)
+    Cn, L = irs.shape
+    calls = x.shape[1] // n_per_call
+    out = np.zeros((Cn, calls * n_per_call), np.float32)
+    lib.lib.orc_batch_fftconv_run(Cn, block, L, irs, np.ascontiguousarray(x[:, :calls * n_per_call]), out, n_per_call,
+                                  calls, threads or lib.lib.orc_max_threads())
+    return out
