@@ -56,6 +56,7 @@ SIGNATURES = {
     "fcb_version": (C.c_char_p, []),
     "fcb_launch_count": (C.c_uint64, []),
     "fcb_device_count": (_i, []),
+    "fcb_debug_alloc_count": (C.c_uint64, []),
     "fcb_tune": (_i, [C.c_char_p, _i]),
     "fcb_profile_mac": (_i, [_i]),
     "fcb_profile_mac_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -72,6 +73,13 @@ SIGNATURES = {
     "fcb_engine_seg_count": (_sz, [_vp]),
     "fcb_engine_set_ir": (_i, [_vp, _sz, _sz, _vp, _sz, _sz, _i]),
     "fcb_engine_set_ir_dev": (_i, [_vp, _sz, _sz, _vp, _sz, _sz, _i]),
+    "fcb_engine_update_reserve": (_i, [_vp]),
+    "fcb_engine_update_reserved": (_i, [_vp]),
+    "fcb_engine_update_begin": (_i, [_vp, _vp, _sz, _sz, _i]),
+    "fcb_engine_update_ready": (_i, [_vp]),
+    "fcb_engine_update_commit": (_i, [_vp]),
+    "fcb_engine_update_wait": (_i, [_vp]),
+    "fcb_engine_update_join": (_i, [_vp, _vp]),
     "fcb_engine_reset": (_i, [_vp]),
     "fcb_engine_push_input": (_i, [_vp, _vp, _sz, _sz, _sz]),
     "fcb_engine_push_input_dev": (_i, [_vp, _vp, _sz, _sz, _sz]),
@@ -87,6 +95,7 @@ SIGNATURES = {
     "fcb_engine_process_block_pair_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, C.POINTER(Epilogue), _vp, _sz, C.POINTER(Epilogue), _sz, _sz]),
     "fcb_engine_multi_block_ok": (_i, [_vp, _sz, _sz]),
     "fcb_engine_multi_block_capacity": (_sz, [_vp]),
+    "fcb_engine_multi_block_reserved": (_sz, [_vp]),
     "fcb_engine_multi_block_reserve": (_i, [_vp, _sz]),
     "fcb_engine_process_blocks": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz, _sz, C.POINTER(Epilogue), _i]),
     "fcb_engine_read_ir_segment": (_i, [_vp, _sz, _sz, _vp]),
@@ -100,6 +109,10 @@ SIGNATURES = {
     "fcb_fftconv_clone": (_i, [_vp, _pp]),
     "fcb_fftconv_free": (None, [_vp]),
     "fcb_fftconv_update": (_i, [_vp, _vp, _sz]),
+    "fcb_fftconv_update_reserve": (_i, [_vp]),
+    "fcb_fftconv_update_begin": (_i, [_vp, _vp, _sz, _i]),
+    "fcb_fftconv_update_pending": (_i, [_vp]),
+    "fcb_fftconv_reserve": (_i, [_vp, _sz]),
     "fcb_fftconv_reset": (_i, [_vp]),
     "fcb_fftconv_process": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz]),
     "fcb_fftconv_process_dev": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, C.POINTER(Epilogue)]),
@@ -127,6 +140,9 @@ SIGNATURES = {
     "fcb_crossfade_process": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz]),
     "fcb_crossfade_process_dev": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz]),
     "fcb_crossfade_reset": (_i, [_vp]),
+    "fcb_crossfade_clone": (_i, [_vp, _pp]),
+    "fcb_crossfade_update_begin": (_i, [_vp, _vp, _sz]),
+    "fcb_crossfade_update_pending": (_i, [_vp]),
     "fcb_crossfade_is_crossfading": (_i, [_vp]),
     "fcb_crossfade_sync": (_i, [_vp]),
     "fcb_crossfade_state": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(_i), C.POINTER(_i)]),

@@ -5,7 +5,9 @@ Same names and argument meaning as the reference:
     x.update(response); x.reset(); x.process(input, output)
 for X in FFTConvolver (src/fft_convolver.rs:86-307), TwoStageFFTConvolver (:323-526) and
 CrossfadeConvolver (src/crossfade_convolver.rs:3-105); contract violations that panic in the
-reference raise ConvolutionPanic, the two `todo!()` methods raise NotYetImplemented.
+reference raise ConvolutionPanic.  The two methods the reference leaves `todo!()` (TwoStageFFTConvolver.update,
+CrossfadeConvolver.reset) are implemented as documented extensions; `strict_todo(True)` makes them raise
+NotYetImplemented like the reference.
 
 Batched entry point: pass a 2-D response [channels, len]; input/output are then [channels, n]
 (planar).  A 1-D response gives the reference's mono convolver.  All sample arithmetic runs in
@@ -109,6 +111,22 @@ class FFTConvolver(_Base):
 
     def reset(self) -> None:
         check(_lib.load().fcb_fftconv_reset(self._h))
+
+    # real-time extras (no reference counterpart): process() and update() never allocate, so the workspace of
+    # multi-block calls and the shadow spectra of background updates are reserved ahead of time
+    def reserve(self, max_call_samples: int) -> None:
+        """calls of up to this many samples may run as one time-batched pass"""
+        check(_lib.load().fcb_fftconv_reserve(self._h, max_call_samples))
+
+    def update_reserve(self) -> None:
+        check(_lib.load().fcb_fftconv_update_reserve(self._h))
+
+    def update_begin(self, response_ptr: int, ir_len: int, *, wait: bool = False) -> None:
+        """background update from a raw pointer ([ir_channels][ir_len] f32, page-locked for a non-blocking call)"""
+        check(_lib.load().fcb_fftconv_update_begin(self._h, response_ptr, ir_len, 1 if wait else 0))
+
+    def update_pending(self) -> bool:
+        return bool(_lib.load().fcb_fftconv_update_pending(self._h))
 
     def process(self, input, output) -> None:
         x, n_in, s_in, y, n_out, s_out = self._io(input, output)
@@ -254,6 +272,20 @@ class CrossfadeConvolver(_Base):
     def is_crossfading(self) -> bool:
         return bool(_lib.load().fcb_crossfade_is_crossfading(self._h))
 
+    def clone(self) -> "CrossfadeConvolver":
+        h = C.c_void_p()
+        check(_lib.load().fcb_crossfade_clone(self._h, C.byref(h)))
+        c = CrossfadeConvolver(h, self.channels, self._mono)
+        c._ir_channels = self._ir_channels
+        return c
+
+    def update_begin(self, response_ptr: int, ir_len: int) -> None:
+        """update() that never waits: raw pointer to page-locked [ir_channels][ir_len] f32, kept alive by the caller"""
+        check(_lib.load().fcb_crossfade_update_begin(self._h, response_ptr, ir_len))
+
+    def update_pending(self) -> bool:
+        return bool(_lib.load().fcb_crossfade_update_pending(self._h))
+
     def state(self):
         counter, mix, appr, tgt = C.c_int64(), C.c_float(), C.c_int(), C.c_int()
         check(_lib.load().fcb_crossfade_state(self._h, C.byref(counter), C.byref(mix), C.byref(appr), C.byref(tgt)))
@@ -370,3 +402,13 @@ class MimoConvolver:
 def compute_tail_block_size(head_len: int, response_len: int) -> int:
     """src/fft_convolver.rs:520-526 (f32 arithmetic)."""
     return _lib.load().fcb_compute_tail_block_size(head_len, response_len)
+
+
+def strict_todo(on: bool) -> None:
+    """True: TwoStageFFTConvolver.update / CrossfadeConvolver.reset raise NotYetImplemented like the reference's todo!()."""
+    check(_lib.load().fcb_tune(b"strict_todo", 1 if on else 0))
+
+
+def alloc_count() -> int:
+    """allocations / stream and event creations / releases made by the library so far (real-time tests)"""
+    return _lib.load().fcb_debug_alloc_count()

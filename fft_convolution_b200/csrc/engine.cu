@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <utility>
 #include <mutex>
 #include <vector>
 
@@ -14,6 +15,7 @@
 namespace fcb {
 thread_local std::string g_last_error = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_resource_calls{0};
 
 // ---- twiddle tables: tw[t] = exp(-2 pi i t / N), t < N, rounded from f64; one per (device, N)
 static std::mutex g_tw_mutex;
@@ -70,6 +72,11 @@ struct fcb_engine {
     float *stage = nullptr; // IR upload staging
     size_t stage_floats = 0;
     const float2 *tw = nullptr;
+    // background IR update (fcb_engine_update_reserve): K5 writes `ir_shadow` on `upd_stream` while the blocks keep
+    // reading `ir`; fcb_engine_update_commit swaps the two pointers
+    float2 *ir_shadow = nullptr;
+    cudaStream_t upd_stream = nullptr;
+    cudaEvent_t upd_done = nullptr, upd_fence = nullptr;
     // multi-block calls (offline_kernels.cuh): workspace for up to mb_cap blocks per pass, allocated on first use
     size_t mb_cap = 0;
     float2 *mb_xnew = nullptr, *mb_premul = nullptr; // [C][mb_cap][B]
@@ -565,6 +572,7 @@ int run_mac_tile(int logb, cudaStream_t st, MacTileArgs a, int *zchunks_out)
 
 extern "C" void fcb_host_mirror_set_mapped_io(int on);
 extern "C" void fcb_host_mirror_set_zero_copy(int on);
+extern "C" void fcb_host_mirror_set_strict_todo(int on);
 
 extern "C" int fcb_tune(const char *key, int value)
 {
@@ -583,6 +591,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "tma_io")) g_tma_io = value != 0;
     else if (!strcmp(key, "mapped_io")) fcb_host_mirror_set_mapped_io(value);
     else if (!strcmp(key, "zero_copy")) fcb_host_mirror_set_zero_copy(value);
+    else if (!strcmp(key, "strict_todo")) fcb_host_mirror_set_strict_todo(value);
     else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);
     return FCB_OK;
 }
@@ -591,6 +600,7 @@ extern "C" int fcb_tune(const char *key, int value)
 extern "C" const char *fcb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *fcb_version(void) { return "fftconv_b200 0.1.0 sm_100a"; }
 extern "C" uint64_t fcb_launch_count(void) { return g_launches.load(); }
+extern "C" uint64_t fcb_debug_alloc_count(void) { return g_resource_calls.load(); }
 extern "C" int fcb_device_count(void)
 {
     int n = 0;
@@ -640,6 +650,37 @@ static int engine_alloc(fcb_engine *e)
     return FCB_OK;
 }
 
+static size_t mb_limit(const fcb_engine *e);
+static int mb_ensure(fcb_engine *e, size_t need);
+static int pipe_streams_ensure(fcb_engine *e);
+
+// everything a process call may need later is created here, so that the audio path never allocates:
+// a default multi-block workspace (as many blocks as fit 32 MB, when that is at least 2) and, for batches that take
+// the grouped host-buffer pipelines (C >= 1024), their streams and events
+static int engine_prepare_process(fcb_engine *e)
+{
+    if (e->S == 0) return FCB_OK;
+    const size_t per_block = e->C * e->B * sizeof(float2) * 4, budget = (size_t)32 << 20;
+    size_t nb = budget / per_block;
+    if (nb > mb_limit(e)) nb = mb_limit(e);
+    if (nb >= 2 && e->logb >= 2) FCB_TRY(mb_ensure(e, nb));
+    if (e->C >= 1024) {
+        FCB_TRY(pipe_streams_ensure(e));
+        const size_t G = (size_t)g_pipe_group.load();
+        size_t ngroups = e->C / (G ? G : 1) + 4;
+        if (ngroups < 8) ngroups = 8;
+        while (e->pipe_in.size() < ngroups) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            FCB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            FCB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            e->pipe_in.push_back(a);
+            e->pipe_out.push_back(b);
+        }
+        e->pipe_cut.reserve(ngroups + 2);
+    }
+    return FCB_OK;
+}
+
 extern "C" int fcb_engine_create(const fcb_engine_desc *d, fcb_engine **out)
 {
     if (!d || !out) return fail(FCB_ERR_ARG, "fcb_engine_create: NULL argument");
@@ -668,6 +709,7 @@ extern "C" int fcb_engine_create(const fcb_engine_desc *d, fcb_engine **out)
     }
     int rc = get_twiddles(e->device, 2 * B, &e->tw);
     if (rc == FCB_OK) rc = engine_alloc(e);
+    if (rc == FCB_OK) rc = engine_prepare_process(e);
     if (rc != FCB_OK) {
         fcb_engine_destroy(e);
         return rc;
@@ -681,6 +723,13 @@ extern "C" void fcb_engine_destroy(fcb_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->upd_stream) {
+        cudaStreamSynchronize(e->upd_stream);
+        cudaStreamDestroy(e->upd_stream);
+    }
+    if (e->upd_done) cudaEventDestroy(e->upd_done);
+    if (e->upd_fence) cudaEventDestroy(e->upd_fence);
+    cudaFree(e->ir_shadow);
     cudaFree(e->ir);
     cudaFree(e->ring);
     cudaFree(e->premul);
@@ -724,6 +773,8 @@ extern "C" int fcb_engine_clone(const fcb_engine *s, fcb_engine **out)
     FCB_CUDA(cudaMemcpyAsync(e->inbuf, s->inbuf, s->C * s->B * sizeof(float), cudaMemcpyDeviceToDevice, st));
     FCB_CUDA(cudaStreamSynchronize(st));
     cudaEventDestroy(ev);
+    if (s->mb_cap > e->mb_cap) FCB_TRY(mb_ensure(e, s->mb_cap));
+    if (s->ir_shadow) FCB_TRY(fcb_engine_update_reserve(e));
     *out = e;
     return FCB_OK;
 }
@@ -756,6 +807,42 @@ extern "C" size_t fcb_engine_block_size(const fcb_engine *e) { return e->B; }
 extern "C" size_t fcb_engine_seg_count(const fcb_engine *e) { return e->S; }
 
 // ---- K5: IR preparation -----------------------------------------------------------------------
+// 1 = page-locked host memory (a DMA from it is still in flight when the copy call returns)
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// K5 of `nchan` responses into `dst` (ir or ir_shadow) on stream `st`.  Host sources are staged through e->stage in
+// groups; the groups need no host synchronisation between them — the next group's copy into the staging buffer is
+// ordered behind the previous group's K5 by the stream itself.
+static int k5_into(fcb_engine *e, float2 *dst, cudaStream_t st, size_t chan0, size_t nchan, const float *irs, size_t len,
+                   size_t stride, bool on_device)
+{
+    const long long rows = (long long)(e->S * e->B);
+    if (on_device || len == 0) {
+        FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, irs, (long long)stride, (int)len, dst + chan0 * rows, rows,
+                                                              (int)e->S, (long long)(nchan * e->S), st)));
+        return FCB_OK;
+    }
+    size_t per_group = e->stage_floats / len;
+    if (per_group == 0) return fail(FCB_ERR_CUDA, "IR staging buffer too small");
+    for (size_t g0 = 0; g0 < nchan; g0 += per_group) {
+        size_t g = nchan - g0 < per_group ? nchan - g0 : per_group;
+        FCB_CUDA(cudaMemcpy2DAsync(e->stage, len * sizeof(float), irs + (g0)*stride, stride * sizeof(float),
+                                   len * sizeof(float), g, cudaMemcpyHostToDevice, st));
+        FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, e->stage, (long long)len, (int)len,
+                                                              dst + (chan0 + g0) * rows, rows, (int)e->S,
+                                                              (long long)(g * e->S), st)));
+    }
+    return FCB_OK;
+}
+
 static int set_ir_common(fcb_engine *e, size_t chan0, size_t nchan, const float *irs, size_t len, size_t stride,
                          int is_update, bool on_device)
 {
@@ -772,24 +859,14 @@ static int set_ir_common(fcb_engine *e, size_t chan0, size_t nchan, const float 
         FCB_CUDA(cudaMemsetAsync(e->premul + c0 * e->B, 0, nc * e->B * sizeof(float2), e->stream));
         FCB_CUDA(cudaMemsetAsync(e->overlap + c0 * e->B, 0, nc * e->B * sizeof(float), e->stream));
     }
-    const long long rows = (long long)(e->S * e->B);
-    if (on_device || len == 0) {
-        FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, irs, (long long)stride, (int)len,
-                                                              e->ir + chan0 * rows, rows, (int)e->S,
-                                                              (long long)(nchan * e->S))));
-        return FCB_OK;
+    if (e->upd_stream) { // the staging buffer is shared with a background update that may still be running
+        FCB_CUDA(cudaEventRecord(e->upd_fence, e->upd_stream));
+        FCB_CUDA(cudaStreamWaitEvent(e->stream, e->upd_fence, 0));
     }
-    size_t per_group = e->stage_floats / len;
-    if (per_group == 0) return fail(FCB_ERR_CUDA, "IR staging buffer too small");
-    for (size_t g0 = 0; g0 < nchan; g0 += per_group) {
-        size_t g = nchan - g0 < per_group ? nchan - g0 : per_group;
-        FCB_CUDA(cudaMemcpy2DAsync(e->stage, len * sizeof(float), irs + (g0)*stride, stride * sizeof(float),
-                                   len * sizeof(float), g, cudaMemcpyHostToDevice, e->stream));
-        FCB_DISPATCH_LOGB(e->logb, FCB_TRY(launch_forward<LB>(e, e->stage, (long long)len, (int)len,
-                                                              e->ir + (chan0 + g0) * rows, rows, (int)e->S,
-                                                              (long long)(g * e->S))));
-        if (g0 + per_group < nchan) FCB_CUDA(cudaStreamSynchronize(e->stream)); // staging reuse
-    }
+    FCB_TRY(k5_into(e, e->ir, e->stream, chan0, nchan, irs, len, stride, on_device));
+    // the reference's caller may drop or overwrite `response` as soon as update() returns: a DMA out of page-locked
+    // memory is still in flight at this point, so wait for it (pageable sources were staged by the driver already)
+    if (!on_device && len && is_pinned_host(irs)) FCB_CUDA(cudaStreamSynchronize(e->stream));
     return FCB_OK;
 }
 
@@ -802,6 +879,83 @@ extern "C" int fcb_engine_set_ir_dev(fcb_engine *e, size_t chan0, size_t nchan, 
                                      size_t stride, int is_update)
 {
     return set_ir_common(e, chan0, nchan, irs, len, stride, is_update, true);
+}
+
+// ---- background IR update: K5 into a second copy of the spectra while the blocks keep running ----------------
+// fcb_engine_update_reserve   once, outside the audio path: the second IR buffer, a side stream, two events
+// fcb_engine_update_begin     queue copy + K5 of ALL responses into the shadow buffer on the side stream; returns at
+//                             once when `irs` is page-locked or device memory (it must then stay untouched until
+//                             fcb_engine_update_ready says 1); pageable memory is staged by the driver during the call
+// fcb_engine_update_ready     1 when the shadow buffer is complete (cudaEventQuery, never blocks)
+// fcb_engine_update_commit    swap the buffers and zero pre_multiplied / overlap like update() does (:185-188); the
+//                             blocks queued after it wait ON THE DEVICE for the K5 if it is still running
+extern "C" int fcb_engine_update_reserve(fcb_engine *e)
+{
+    if (!e) return fail(FCB_ERR_ARG, "NULL engine");
+    if (e->ir_shadow || e->S == 0) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_TRY(alloc_zero((void **)&e->ir_shadow, e->ir_channels() * e->S * e->B * sizeof(float2), e->stream));
+    int lo = 0, hi = 0;
+    FCB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    FCB_CUDA(cudaStreamCreateWithPriority(&e->upd_stream, cudaStreamNonBlocking, lo)); // lowest priority: blocks first
+    FCB_CUDA(cudaEventCreateWithFlags(&e->upd_done, cudaEventDisableTiming));
+    FCB_CUDA(cudaEventCreateWithFlags(&e->upd_fence, cudaEventDisableTiming));
+    FCB_CUDA(cudaEventRecord(e->upd_done, e->upd_stream));
+    return FCB_OK;
+}
+extern "C" int fcb_engine_update_reserved(const fcb_engine *e) { return e && e->ir_shadow ? 1 : 0; }
+
+extern "C" int fcb_engine_update_begin(fcb_engine *e, const float *irs, size_t len, size_t stride, int on_device)
+{
+    if (!e) return fail(FCB_ERR_ARG, "NULL engine");
+    if (!e->ir_shadow) return fail(FCB_ERR_ARG, "update_begin: call fcb_engine_update_reserve first");
+    if (len > e->L) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
+    if (len && !irs) return fail(FCB_ERR_ARG, "update_begin: NULL impulse response");
+    FCB_CUDA(cudaSetDevice(e->device));
+    // the shadow buffer was the active one until the last commit: kernels queued before that commit may still read it
+    FCB_CUDA(cudaEventRecord(e->upd_fence, e->stream));
+    FCB_CUDA(cudaStreamWaitEvent(e->upd_stream, e->upd_fence, 0));
+    FCB_TRY(k5_into(e, e->ir_shadow, e->upd_stream, 0, e->ir_channels(), irs, len, stride, on_device != 0));
+    FCB_CUDA(cudaEventRecord(e->upd_done, e->upd_stream));
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_update_ready(fcb_engine *e)
+{
+    if (!e || !e->ir_shadow) return 0;
+    cudaError_t q = cudaEventQuery(e->upd_done);
+    if (q == cudaErrorNotReady) return 0;
+    return q == cudaSuccess ? 1 : -1;
+}
+
+// host-blocking wait for the background K5 (a caller that wants its page-locked source buffer back)
+extern "C" int fcb_engine_update_wait(fcb_engine *e)
+{
+    if (!e || !e->upd_stream) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_CUDA(cudaStreamSynchronize(e->upd_stream));
+    return FCB_OK;
+}
+
+// make `stream` wait (on the device) for the background K5 queued so far, e.g. before its source buffer is rewritten
+extern "C" int fcb_engine_update_join(fcb_engine *e, void *stream)
+{
+    if (!e || !e->upd_done) return FCB_OK;
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, e->upd_done, 0));
+    return FCB_OK;
+}
+
+extern "C" int fcb_engine_update_commit(fcb_engine *e)
+{
+    if (!e) return fail(FCB_ERR_ARG, "NULL engine");
+    if (!e->ir_shadow) return fail(FCB_ERR_ARG, "update_commit: nothing reserved");
+    FCB_CUDA(cudaSetDevice(e->device));
+    FCB_CUDA(cudaStreamWaitEvent(e->stream, e->upd_done, 0));
+    std::swap(e->ir, e->ir_shadow);
+    FCB_CUDA(cudaMemsetAsync(e->premul, 0, e->C * e->B * sizeof(float2), e->stream));
+    FCB_CUDA(cudaMemsetAsync(e->overlap, 0, e->C * e->B * sizeof(float), e->stream));
+    return FCB_OK;
 }
 
 extern "C" int fcb_engine_reset(fcb_engine *e)
@@ -953,38 +1107,48 @@ static size_t mb_limit(const fcb_engine *e)
     return cap < 4 ? 4 : cap > 1024 ? 1024 : cap;
 }
 
-// workspace for `need` blocks per pass (grows when a longer call arrives; never shrinks)
+static void mb_release(fcb_engine *e)
+{
+    cudaFree(e->mb_xnew);
+    cudaFree(e->mb_premul);
+    cudaFree(e->mb_y);
+    cudaFree(e->mb_in);
+    cudaFree(e->mb_out);
+    e->mb_xnew = e->mb_premul = nullptr;
+    e->mb_y = e->mb_in = e->mb_out = nullptr;
+    e->mb_cap = 0;
+}
+
+// workspace for `need` blocks per pass.  Called from fcb_engine_create (a small default) and from
+// fcb_engine_multi_block_reserve only — never from a process call (src/lib.rs:8: no allocation on the audio path).
 static int mb_ensure(fcb_engine *e, size_t need)
 {
-    if (need <= e->mb_cap) return FCB_OK;
     if (need > mb_limit(e)) need = mb_limit(e);
     if (need <= e->mb_cap) return FCB_OK;
     FCB_CUDA(cudaSetDevice(e->device));
     if (e->mb_cap) {
         FCB_CUDA(cudaStreamSynchronize(e->stream));
-        cudaFree(e->mb_xnew);
-        cudaFree(e->mb_premul);
-        cudaFree(e->mb_y);
-        cudaFree(e->mb_in);
-        cudaFree(e->mb_out);
-        e->mb_xnew = e->mb_premul = nullptr;
-        e->mb_y = e->mb_in = e->mb_out = nullptr;
-        e->mb_cap = 0;
+        mb_release(e);
     }
     const size_t per_block = e->C * e->B * sizeof(float2);
-    FCB_CUDA(cudaMalloc((void **)&e->mb_xnew, need * per_block));
-    FCB_CUDA(cudaMalloc((void **)&e->mb_premul, need * per_block));
-    FCB_CUDA(cudaMalloc((void **)&e->mb_y, need * per_block));
-    FCB_CUDA(cudaMalloc((void **)&e->mb_in, need * per_block / 2));
-    FCB_CUDA(cudaMalloc((void **)&e->mb_out, need * per_block / 2));
+    if (cudaMalloc((void **)&e->mb_xnew, need * per_block) != cudaSuccess ||
+        cudaMalloc((void **)&e->mb_premul, need * per_block) != cudaSuccess ||
+        cudaMalloc((void **)&e->mb_y, need * per_block) != cudaSuccess ||
+        cudaMalloc((void **)&e->mb_in, need * per_block / 2) != cudaSuccess ||
+        cudaMalloc((void **)&e->mb_out, need * per_block / 2) != cudaSuccess) {
+        cudaGetLastError();
+        mb_release(e); // nothing half-allocated survives a failure
+        return fail(FCB_ERR_CUDA, "multi-block workspace for %zu blocks (%zu MB) does not fit", need, need * per_block * 4 >> 20);
+    }
     e->mb_cap = need;
     return FCB_OK;
 }
 
 extern "C" size_t fcb_engine_multi_block_capacity(fcb_engine *e) { return e ? mb_limit(e) : 0; }
+extern "C" size_t fcb_engine_multi_block_reserved(const fcb_engine *e) { return e ? e->mb_cap : 0; }
 
-// allocate the multi-block workspace ahead of time (a real-time caller whose buffers span several blocks calls this
-// once after create; otherwise the first multi-block call allocates)
+// size the multi-block workspace (create reserves what fits FCB_MB_DEFAULT_BYTES; callers whose buffers span more
+// blocks call this once, outside the audio path)
 extern "C" int fcb_engine_multi_block_reserve(fcb_engine *e, size_t nblocks)
 {
     if (!e) return fail(FCB_ERR_ARG, "multi_block_reserve: NULL engine");
@@ -1089,8 +1253,9 @@ extern "C" int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t 
     if (!fcb_engine_multi_block_ok(e, current, active)) return fail(FCB_ERR_UNSUPPORTED, "process_blocks: not applicable here");
     FCB_CUDA(cudaSetDevice(e->device));
     if (nblocks == 0) return FCB_OK;
-    if (nblocks > mb_limit(e)) return fail(FCB_ERR_ARG, "process_blocks: %zu blocks exceed the workspace limit (%zu)", nblocks, mb_limit(e));
-    FCB_TRY(mb_ensure(e, nblocks));
+    if (nblocks > e->mb_cap)
+        return fail(FCB_ERR_ARG, "process_blocks: %zu blocks exceed the reserved workspace (%zu; fcb_engine_multi_block_reserve)",
+                    nblocks, e->mb_cap);
     const size_t B = e->B, C = e->C, NB = nblocks, row = NB * B;
     cudaStream_t st = e->stream;
     if (!host_io) return process_blocks_range(e, st, 0, C, in, in_stride, out, out_stride, current, active, NB, epi);
@@ -1105,9 +1270,9 @@ extern "C" int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t 
     }
     // many channels: groups of channels, all H2D copies on one stream running ahead, the passes on two compute streams
     // as their input lands, the D2H copies on a fourth stream — the PCIe traffic hides under the HBM-bound passes
-    FCB_TRY(pipe_streams_ensure(e));
+    FCB_TRY(pipe_streams_ensure(e)); // created with the engine (C >= 1024)
     const size_t ngroups = 8, per = (C + ngroups - 1) / ngroups;
-    while (e->pipe_in.size() < ngroups) { // grows on first use only
+    while (e->pipe_in.size() < ngroups) { // sized in fcb_engine_create; grows only after fcb_tune("pipe_group")
         cudaEvent_t a = nullptr, b = nullptr;
         FCB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
         FCB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
@@ -1153,7 +1318,7 @@ extern "C" int fcb_engine_process_block_host(fcb_engine *e, const float *in, siz
     if (!in || !out) return fail(FCB_ERR_ARG, "process_block_host: NULL argument");
     if (active == 0) return FCB_OK;
     FCB_CUDA(cudaSetDevice(e->device));
-    FCB_TRY(pipe_streams_ensure(e)); // created on first use, outside the steady state
+    FCB_TRY(pipe_streams_ensure(e)); // created with the engine (C >= 1024)
     const size_t B = e->B, C = e->C;
     size_t G = group_channels ? group_channels : (size_t)g_pipe_group.load();
     if (G > C) G = C;

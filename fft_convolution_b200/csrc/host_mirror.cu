@@ -79,7 +79,13 @@ struct fcb_fftconv {
     // single-chunk call is: CPU copy in, one launch (whole block) or three, one sync, CPU copy out
     float *h_in = nullptr, *h_out = nullptr;   // host views
     float *m_in = nullptr, *m_out = nullptr;   // the same memory as seen from the device
+    // fcb_fftconv_update_begin: the new spectra are being built in the engine's shadow buffer
+    bool upd_pending = false, upd_wait = false;
+    size_t upd_active = 0; // active_seg_count once the update is committed
 };
+
+static int fftconv_commit_update(fcb_fftconv *c);
+static int fftconv_commit_wait(fcb_fftconv *c);
 
 static void fftconv_alloc_mapped(fcb_fftconv *c)
 {
@@ -178,7 +184,11 @@ extern "C" int fcb_fftconv_clone(const fcb_fftconv *s, fcb_fftconv **out)
     c->current = s->current;
     c->input_buffer_fill = s->input_buffer_fill;
     int rc = FCB_OK;
-    if (s->eng) {
+    if (s->upd_pending) { // #[derive(Clone)] copies a value whose update() has returned: finish the background one first
+        rc = fftconv_commit_wait(const_cast<fcb_fftconv *>(s));
+        c->active_seg_count = s->active_seg_count;
+    }
+    if (rc == FCB_OK && s->eng) {
         rc = fcb_engine_clone(s->eng, &c->eng);
         if (rc == FCB_OK) rc = fcb_engine_set_stream(c->eng, (void *)c->stream);
         if (rc == FCB_OK) c->d_io = fcb_engine_scratch(c->eng);
@@ -198,6 +208,7 @@ extern "C" int fcb_fftconv_update(fcb_fftconv *c, const float *irs, size_t new_i
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
     if (new_ir_len > c->ir_len) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
     if (c->ir_len == 0) return FCB_OK; // :181-183
+    c->upd_pending = false; // supersedes an update still in the background
     c->active_seg_count = (size_t)std::ceil((double)new_ir_len / (double)c->block_size); // :190
     return fcb_engine_set_ir(c->eng, 0, c->opt.shared_ir ? 1 : c->C, irs, new_ir_len, new_ir_len, 1);
 }
@@ -207,6 +218,7 @@ static int fftconv_update_dev(fcb_fftconv *c, const float *irs_dev, size_t new_i
 {
     if (new_ir_len > c->ir_len) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
     if (c->ir_len == 0) return FCB_OK;
+    c->upd_pending = false;
     c->active_seg_count = (size_t)std::ceil((double)new_ir_len / (double)c->block_size);
     return fcb_engine_set_ir_dev(c->eng, 0, c->opt.shared_ir ? 1 : c->C, irs_dev, new_ir_len, stride, 1);
 }
@@ -219,6 +231,80 @@ extern "C" int fcb_fftconv_reset(fcb_fftconv *c)
     c->input_buffer_fill = 0;
     return c->eng ? fcb_engine_reset(c->eng) : FCB_OK;
 }
+
+// update() with the new response zero-padded to `full_len` samples: `valid` samples are read from `irs`, the segment
+// count follows full_len (used by the two-stage update, whose stages always keep their whole slice active)
+static int fftconv_update_padded(fcb_fftconv *c, const float *irs, size_t valid, size_t stride, size_t full_len)
+{
+    if (full_len > c->ir_len) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
+    if (c->ir_len == 0) return FCB_OK;
+    c->upd_pending = false; // a synchronous update supersedes one still in the background
+    c->active_seg_count = (size_t)std::ceil((double)full_len / (double)c->block_size);
+    return fcb_engine_set_ir(c->eng, 0, c->opt.shared_ir ? 1 : c->C, irs, valid, stride, 1);
+}
+
+// ---- real-time update: returns at once, the blocks keep running, the new response is swapped in between two calls ----
+extern "C" int fcb_fftconv_update_reserve(fcb_fftconv *c)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    return c->eng ? fcb_engine_update_reserve(c->eng) : FCB_OK;
+}
+
+static int fftconv_update_begin(fcb_fftconv *c, const float *irs, size_t valid, size_t stride, size_t full_len, bool on_device,
+                                bool wait)
+{
+    if (full_len > c->ir_len) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
+    if (c->ir_len == 0) return FCB_OK;
+    FCB_TRY(fcb_engine_update_begin(c->eng, irs, valid, stride, on_device ? 1 : 0));
+    c->upd_pending = true;
+    c->upd_wait = wait;
+    c->upd_active = (size_t)std::ceil((double)full_len / (double)c->block_size);
+    return FCB_OK;
+}
+
+extern "C" int fcb_fftconv_update_begin(fcb_fftconv *c, const float *irs, size_t ir_len, int flags)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    if (c->eng && !fcb_engine_update_reserved(c->eng)) return fail(FCB_ERR_ARG, "update_begin: call fcb_fftconv_update_reserve first");
+    return fftconv_update_begin(c, irs, ir_len, ir_len, ir_len, false, (flags & FCB_UPDATE_WAIT) != 0);
+}
+
+extern "C" int fcb_fftconv_update_pending(const fcb_fftconv *c) { return c && c->upd_pending ? 1 : 0; }
+
+// called at the top of every process call: swap a finished (or, in wait mode, any) background update in
+static int fftconv_commit_update(fcb_fftconv *c)
+{
+    if (!c->upd_pending) return FCB_OK;
+    if (!c->upd_wait) {
+        const int ready = fcb_engine_update_ready(c->eng);
+        if (ready < 0) return fail(FCB_ERR_CUDA, "background IR update failed");
+        if (!ready) return FCB_OK; // keep playing the old response; look again at the next call
+    }
+    FCB_TRY(fcb_engine_update_commit(c->eng));
+    c->active_seg_count = c->upd_active;
+    c->upd_pending = false;
+    return FCB_OK;
+}
+
+// the same, but always: whatever update() has accepted becomes the active response now (device-side wait)
+static int fftconv_commit_wait(fcb_fftconv *c)
+{
+    if (!c || !c->upd_pending) return FCB_OK;
+    c->upd_wait = true;
+    return fftconv_commit_update(c);
+}
+
+// multi-block calls never allocate: reserve the workspace for calls of up to `max_call_samples` samples ahead of time
+extern "C" int fcb_fftconv_reserve(fcb_fftconv *c, size_t max_call_samples)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    if (!c->eng) return FCB_OK;
+    const size_t nb = max_call_samples / c->block_size;
+    return nb >= 2 ? fcb_engine_multi_block_reserve(c->eng, nb) : FCB_OK;
+}
+
+static bool g_strict_todo = false; // fcb_tune("strict_todo", 1): TwoStage::update / Crossfade::reset answer FCB_ERR_TODO like the reference
+extern "C" void fcb_host_mirror_set_strict_todo(int on) { g_strict_todo = on != 0; }
 
 static bool g_mapped_io = true; // fcb_tune("mapped_io", 0) forces the copy-engine path
 static bool g_zero_copy = true; // fcb_tune("zero_copy", 0): never let kernels touch caller-pinned host buffers
@@ -259,6 +345,7 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
     if (out_len && !out) return fail(FCB_ERR_ARG, "NULL output");
     FCB_CUDA(cudaSetDevice(c->opt.device));
+    FCB_TRY(fftconv_commit_update(c));
     if (c->active_seg_count == 0) { // :216-219
         if (host) {
             for (size_t ch = 0; ch < c->C; ch++) memset(out + ch * out_stride, 0, out_len * sizeof(float));
@@ -289,7 +376,7 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
         if (was_empty && out_len - processed >= 2 * B && fcb_engine_multi_block_ok(c->eng, c->current, c->active_seg_count)) {
             // the call spans several whole blocks: one time-batched pass over as many as the workspace holds
             size_t nb = (out_len - processed) / B;
-            const size_t cap = fcb_engine_multi_block_capacity(c->eng);
+            const size_t cap = fcb_engine_multi_block_reserved(c->eng); // never allocates here (fcb_fftconv_reserve)
             if (cap >= 2) {
                 if (nb > cap) nb = cap;
                 FCB_TRY(fcb_engine_process_blocks(c->eng, in + processed, in_stride, out + processed, out_stride, c->current,
@@ -422,6 +509,7 @@ extern "C" size_t fcb_compute_tail_block_size(size_t head_len, size_t response_l
 
 struct fcb_twostage {
     size_t C = 0, head_block_size = 0, tail_block_size = 0; // :325-326
+    size_t max_response_length = 0; // not a field of the reference struct; fcb_twostage_update re-slices with it
     fcb_fftconv *head = nullptr, *tail0 = nullptr, *tail = nullptr;
     // device [C][T] each (:329-334); tail_in is double-buffered for the asynchronous tail
     float *tail_output0 = nullptr, *tail_precalculated0 = nullptr, *tail_output = nullptr,
@@ -523,6 +611,7 @@ extern "C" int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t ch
     FCB_TRY(twostage_shell(&c, channels, &o));
     c->head_block_size = head;
     c->tail_block_size = T;
+    c->max_response_length = L;
     fcb_options sub = o;
     sub.stream = (void *)c->stream;
     int rc = FCB_OK;
@@ -582,6 +671,7 @@ extern "C" int fcb_twostage_clone(const fcb_twostage *s, fcb_twostage **out)
     FCB_TRY(twostage_shell(&c, s->C, &s->opt));
     c->head_block_size = s->head_block_size;
     c->tail_block_size = s->tail_block_size;
+    c->max_response_length = s->max_response_length;
     c->tail_input_fill = s->tail_input_fill;
     c->precalculated_pos = s->precalculated_pos;
     c->tail_in_sel = s->tail_in_sel;
@@ -624,11 +714,29 @@ extern "C" int fcb_twostage_clone(const fcb_twostage *s, fcb_twostage **out)
     return FCB_OK;
 }
 
-// :408-410
+// :408-410 is todo!() in the reference.  EXTENSION (semantics written down in DESIGN.md §9 and
+// pinned by the CPU restatement the tests check against): the per-stage FFTConvolver::update (:174-213) on the response
+// re-sliced the way init slices it (:349-384) — zero-padded to max_response_length, head [0, min(L,T)), tail0
+// [T, T + min(L-T,T)), tail [2T, L); every stage keeps its whole slice active.  Input rings, partially filled blocks,
+// tail_input and the tail outputs already computed with the old response are kept (audio in flight), each stage's
+// overlap and pre_multiplied are zeroed (:185-188).  No allocation: the slices are read in place with the caller's
+// stride.  fcb_tune("strict_todo", 1) restores the reference's answer (FCB_ERR_TODO).
 extern "C" int fcb_twostage_update(fcb_twostage *c, const float *irs, size_t ir_len)
 {
-    (void)c; (void)irs; (void)ir_len;
-    return fail(FCB_ERR_TODO, "not yet implemented");
+    if (g_strict_todo) return fail(FCB_ERR_TODO, "not yet implemented");
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    const size_t L = c->max_response_length, T = c->tail_block_size;
+    if (ir_len > L) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
+    if (ir_len && !irs) return fail(FCB_ERR_ARG, "NULL impulse response");
+    FCB_CUDA(cudaSetDevice(c->opt.device));
+    auto stage = [&](fcb_fftconv *f, size_t off, size_t slice) { // `slice` samples of the padded response from `off`
+        const size_t valid = ir_len > off ? (ir_len - off < slice ? ir_len - off : slice) : 0;
+        return fftconv_update_padded(f, valid ? irs + off : irs, valid, ir_len, slice);
+    };
+    FCB_TRY(stage(c->head, 0, L < T ? L : T));
+    if (L > T) FCB_TRY(stage(c->tail0, T, (L - T) < T ? (L - T) : T));
+    if (L > 2 * T) FCB_TRY(stage(c->tail, 2 * T, L - 2 * T));
+    return FCB_OK;
 }
 
 // :497-511
@@ -845,8 +953,13 @@ struct fcb_crossfade {
     int device = 0;
     float2 *h_gains = nullptr, *d_gains = nullptr;  // pinned / device, max_buffer_size each
     cudaEvent_t ev_gains = nullptr;
-    float *d_in = nullptr, *d_out = nullptr;        // host-call staging
-    size_t d_in_cap = 0;
+    float *d_in = nullptr, *d_out = nullptr;        // host-call staging, [C][max_buffer_size] each (allocated in new())
+    size_t max_response_length = 0;                 // as given to new() (= stored_len)
+    size_t crossfade_samples = 0;
+    // update() while a fade runs (:58-63) also starts K5 of the stored response into the shadow buffer of the
+    // convolver that will take it when the fade ends, so the deferred swap inside process() (:67-70) is a pointer flip
+    bool stored_staged = false;
+    bool update_nowait = false; // inside fcb_crossfade_update_begin: the caller keeps the source buffer alive
     // A is a deep clone of B (:29) and both are fed the same samples, so their input-spectrum rings hold the same
     // spectra in the same slots — until an update() with another segment count (:204) lets their `current` drift
     // apart at the next wrap (:301-305); a call that starts with unequal segment counts or positions turns the
@@ -885,6 +998,8 @@ extern "C" int fcb_crossfade_new(fcb_crossfade **out, fcb_fftconv *convolver, si
     c->b = convolver; // :30
     c->max_buffer_size = max_buffer_size;
     c->stored_len = max_response_length;
+    c->max_response_length = max_response_length;
+    c->crossfade_samples = crossfade_samples;
     c->crossfader.init(crossfade_samples, max_buffer_size < max_response_length ? max_buffer_size : max_response_length); // :31-35
     int rc = FCB_OK;
     {
@@ -906,7 +1021,12 @@ extern "C" int fcb_crossfade_new(fcb_crossfade **out, fcb_fftconv *convolver, si
     cu(cudaMalloc(&c->d_gains, n * sizeof(float2)));
     cu(cudaHostAlloc(&c->h_gains, n * sizeof(float2), cudaHostAllocDefault));
     cu(cudaMalloc(&c->d_out, c->C * n * sizeof(float)));
+    cu(cudaMalloc(&c->d_in, c->C * n * sizeof(float)));
     cu(cudaEventCreateWithFlags(&c->ev_gains, cudaEventDisableTiming));
+    // live response changes are what this type is for: both convolvers get a shadow copy of their spectra so that
+    // update() never makes a block wait for K5 (fcb_engine_update_*)
+    if (rc == FCB_OK && c->a && c->a->eng) rc = fcb_engine_update_reserve(c->a->eng);
+    if (rc == FCB_OK && c->b->eng) rc = fcb_engine_update_reserve(c->b->eng);
     if (rc == FCB_OK) {
         cu(cudaMemsetAsync(c->buffer_a, 0, c->C * n * sizeof(float), c->stream));
         cu(cudaMemsetAsync(c->buffer_b, 0, c->C * n * sizeof(float), c->stream));
@@ -938,12 +1058,31 @@ extern "C" int fcb_crossfade_init(fcb_crossfade **out, const float *irs, size_t 
 
 extern "C" int fcb_crossfade_is_crossfading(const fcb_crossfade *c) { return c && c->crossfader.approaching; } // :85-92
 
-// :94-105; `on_device`: irs is the device-resident stored_response
-static int crossfade_swap(fcb_crossfade *c, const float *irs, size_t len, bool on_device)
+// :94-105.  The idle convolver's update() runs in the background (K5 into its shadow spectra on the update stream);
+// it is committed by that convolver's next process call, which waits for it ON THE DEVICE if it is still running —
+// same result as the synchronous update, and the host never blocks on K5.
+static int crossfade_swap(fcb_crossfade *c, const float *irs, size_t len, bool from_stored)
 {
-    int rc;
+    int rc = FCB_OK;
     fcb_fftconv *idle = c->crossfader.target == 0 ? c->b : c->a;
-    rc = on_device ? fftconv_update_dev(idle, irs, len, c->stored_len) : fcb_fftconv_update(idle, irs, len);
+    if (!idle->eng || !fcb_engine_update_reserved(idle->eng)) {
+        rc = from_stored ? fftconv_update_dev(idle, irs, len, c->stored_len) : fcb_fftconv_update(idle, irs, len);
+    } else if (from_stored) {
+        // stored_response (:58-63), staged into the shadow buffer when update() arrived; `len` == stored_len
+        if (!c->stored_staged) rc = fftconv_update_begin(idle, c->stored_response, len, c->stored_len, len, true, true);
+        else {
+            idle->upd_pending = true; // the K5 queued by fcb_crossfade_update: commit it at the next process call
+            idle->upd_wait = true;
+            idle->upd_active = (size_t)std::ceil((double)len / (double)idle->block_size);
+        }
+    } else {
+        if (len > idle->ir_len) return fail(FCB_ERR_PANIC, "New impulse response is longer than initialized length");
+        rc = fftconv_update_begin(idle, irs, len, len, len, false, true);
+        // the caller may drop `irs` when update() returns: a DMA out of page-locked memory is still in flight, wait for
+        // it (pageable sources were staged by the driver during the call); fcb_crossfade_update_begin skips this wait
+        if (rc == FCB_OK && len && !c->update_nowait && pinned_alias(irs)) rc = fcb_engine_update_wait(idle->eng);
+    }
+    c->stored_staged = false;
     c->crossfader.fade_into(c->crossfader.target == 0 ? 1 : 0);
     return rc;
 }
@@ -963,15 +1102,44 @@ extern "C" int fcb_crossfade_update(fcb_crossfade *c, const float *irs, size_t l
     FCB_CUDA(cudaSetDevice(c->device));
     // a convolver built over ONE shared response (fcb_crossfade_new on a shared_ir FFTConvolver) is handed one row
     const size_t rows = c->b->opt.shared_ir ? 1 : c->C;
+    fcb_fftconv *next = c->crossfader.target == 0 ? c->b : c->a; // takes the stored response when the fade ends (:67-70)
+    const bool shadow = next->eng && fcb_engine_update_reserved(next->eng) && len <= next->ir_len && c->stored_len <= next->ir_len;
+    cudaStream_t st = c->stream;
+    if (shadow) FCB_TRY(fcb_engine_update_join(next->eng, (void *)st)); // an earlier pending response may still be read by its K5
     if (len)
         FCB_CUDA(cudaMemcpy2DAsync(c->stored_response, c->stored_len * sizeof(float), irs, len * sizeof(float),
-                                   len * sizeof(float), rows, cudaMemcpyHostToDevice, c->stream));
+                                   len * sizeof(float), rows, cudaMemcpyHostToDevice, st));
     if (c->stored_len > len)
         FCB_CUDA(cudaMemset2DAsync(c->stored_response + len, c->stored_len * sizeof(float), 0,
-                                   (c->stored_len - len) * sizeof(float), rows, c->stream));
-    FCB_CUDA(cudaStreamSynchronize(c->stream)); // the caller's buffer is free to change on return
+                                   (c->stored_len - len) * sizeof(float), rows, st));
+    if (!c->update_nowait) FCB_CUDA(cudaStreamSynchronize(st)); // the caller's buffer is free to change on return
+    c->stored_staged = false;
+    if (shadow) {
+        // K5 now, in the background, into the spectra that are not playing; latest update wins (same stream order)
+        FCB_TRY(fcb_engine_update_begin(next->eng, c->stored_response, c->stored_len, c->stored_len, 1));
+        c->stored_staged = true;
+    }
     c->response_pending = true;
     return FCB_OK;
+}
+
+// update() for real-time callers: identical state changes, but never waits for a copy or a kernel.  `irs` must be
+// page-locked (fcb_host_alloc) or the call degrades to fcb_crossfade_update, and must stay untouched until
+// fcb_crossfade_update_pending() returns 0.
+extern "C" int fcb_crossfade_update_begin(fcb_crossfade *c, const float *irs, size_t len)
+{
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    c->update_nowait = len == 0 || pinned_alias(irs) != nullptr;
+    const int rc = fcb_crossfade_update(c, irs, len);
+    c->update_nowait = false;
+    return rc;
+}
+extern "C" int fcb_crossfade_update_pending(fcb_crossfade *c)
+{
+    if (!c) return 0;
+    for (fcb_fftconv *f : {c->a, c->b})
+        if (f && f->eng && fcb_engine_update_reserved(f->eng) && fcb_engine_update_ready(f->eng) == 0) return 1;
+    return cudaStreamQuery(c->stream) == cudaErrorNotReady ? 1 : 0; // the copy into stored_response rides on the main stream
 }
 
 // :66-78 on device buffers
@@ -980,9 +1148,13 @@ extern "C" int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in, size
 {
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
     FCB_CUDA(cudaSetDevice(c->device));
+    FCB_TRY(fftconv_commit_update(c->a)); // background updates accepted by update() take effect here (the paired launch
+    FCB_TRY(fftconv_commit_update(c->b)); // below does not go through the convolvers' own process)
     if (!fcb_crossfade_is_crossfading(c) && c->response_pending) { // :67-70
         FCB_TRY(crossfade_swap(c, c->stored_response, c->stored_len, true));
         c->response_pending = false;
+        FCB_TRY(fftconv_commit_update(c->a));
+        FCB_TRY(fftconv_commit_update(c->b));
     }
     const size_t M = c->max_buffer_size;
     if (out_len > M) return fail(FCB_ERR_PANIC, "index out of bounds: the len is %zu but the index is %zu", M, M); // :76
@@ -1062,19 +1234,15 @@ extern "C" int fcb_crossfade_process(fcb_crossfade *c, const float *in, size_t i
 {
     if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
     FCB_CUDA(cudaSetDevice(c->device));
-    if (in_len > c->d_in_cap) { // grow the input staging (outside the steady state: sizes repeat)
-        FCB_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_in);
-        c->d_in = nullptr;
-        FCB_CUDA(cudaMalloc(&c->d_in, c->C * in_len * sizeof(float)));
-        c->d_in_cap = in_len;
-    }
-    if (in_len)
-        FCB_CUDA(cudaMemcpy2DAsync(c->d_in, in_len * sizeof(float), in, in_stride * sizeof(float), in_len * sizeof(float),
-                                   c->C, cudaMemcpyHostToDevice, c->stream));
     const size_t M = c->max_buffer_size;
     if (out_len > M) return fail(FCB_ERR_PANIC, "index out of bounds: the len is %zu but the index is %zu", M, M);
-    FCB_TRY(fcb_crossfade_process_dev(c, c->d_in, in_len, in_len, c->d_out, out_len, M ? M : 1));
+    // both convolvers consume input[..max_buffer_size] (:72-73): a longer input is never read past that, a shorter
+    // one panics inside FFTConvolver::process — either way at most M samples are staged (buffer made in new())
+    const size_t n_in = in_len < M ? in_len : M;
+    if (n_in)
+        FCB_CUDA(cudaMemcpy2DAsync(c->d_in, (M ? M : 1) * sizeof(float), in, in_stride * sizeof(float), n_in * sizeof(float),
+                                   c->C, cudaMemcpyHostToDevice, c->stream));
+    FCB_TRY(fcb_crossfade_process_dev(c, c->d_in, n_in, M ? M : 1, c->d_out, out_len, M ? M : 1));
     if (out_len)
         FCB_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float), c->d_out, (M ? M : 1) * sizeof(float),
                                    out_len * sizeof(float), c->C, cudaMemcpyDeviceToHost, c->stream));
@@ -1082,11 +1250,82 @@ extern "C" int fcb_crossfade_process(fcb_crossfade *c, const float *in, size_t i
     return FCB_OK;
 }
 
-// :80-82
+// :80-82 is todo!() in the reference.  EXTENSION (semantics written down in DESIGN.md §9 and
+// pinned by the CPU restatement the tests check against): forget all audio like FFTConvolver::reset (src/fft_convolver.rs:296-306)
+// — both convolvers reset, buffer_a / buffer_b zeroed — and finish a running fade at once: the crossfader lands where
+// `mix` leaves it at counter == fading_samples (:261-273), so the response asked for last is the one heard.  A response
+// still pending stays pending (:67-70 applies it at the next process()).  fcb_tune("strict_todo", 1): FCB_ERR_TODO.
 extern "C" int fcb_crossfade_reset(fcb_crossfade *c)
 {
-    (void)c;
-    return fail(FCB_ERR_TODO, "not yet implemented");
+    if (g_strict_todo) return fail(FCB_ERR_TODO, "not yet implemented");
+    if (!c) return fail(FCB_ERR_ARG, "NULL convolver");
+    FCB_CUDA(cudaSetDevice(c->device));
+    FCB_TRY(fftconv_commit_wait(c->a)); // an update whose update() call has returned is part of the state that is kept
+    FCB_TRY(fftconv_commit_wait(c->b));
+    FCB_TRY(fcb_fftconv_reset(c->a));
+    FCB_TRY(fcb_fftconv_reset(c->b));
+    const size_t n = c->max_buffer_size ? c->max_buffer_size : 1;
+    FCB_CUDA(cudaMemsetAsync(c->buffer_a, 0, c->C * n * sizeof(float), c->stream));
+    FCB_CUDA(cudaMemsetAsync(c->buffer_b, 0, c->C * n * sizeof(float), c->stream));
+    if (c->crossfader.approaching) {
+        c->crossfader.approaching = false;
+        c->crossfader.mix_value = c->crossfader.target == 0 ? 0.f : 1.f;
+    }
+    c->crossfader.counter = 0;
+    c->rings_same = c->a->active_seg_count == c->b->active_seg_count; // both rings are all-zero again, current = 0
+    return FCB_OK;
+}
+
+// #[derive(Clone)] (src/crossfade_convolver.rs:10): deep copy of both convolvers, the crossfader and the buffers
+extern "C" int fcb_crossfade_clone(const fcb_crossfade *s, fcb_crossfade **out)
+{
+    if (!s || !out) return fail(FCB_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    FCB_CUDA(cudaSetDevice(s->device));
+    FCB_TRY(fftconv_commit_wait(s->a)); // updates already accepted are part of the value being cloned
+    FCB_TRY(fftconv_commit_wait(s->b));
+    FCB_CUDA(cudaStreamSynchronize(s->stream));
+    fcb_fftconv *b = nullptr;
+    FCB_TRY(fcb_fftconv_clone(s->b, &b)); // a private stream of its own when the source's was private
+    fcb_crossfade *c = nullptr;
+    int rc = fcb_crossfade_new(&c, b, s->max_response_length, s->max_buffer_size, s->crossfade_samples);
+    if (rc != FCB_OK) {
+        fcb_fftconv_free(b);
+        return rc;
+    }
+    // new() made A a clone of B; A must be a clone of the source's A
+    fcb_fftconv *a = nullptr;
+    {
+        fcb_fftconv tmp = *s->a;
+        tmp.opt.stream = (void *)c->stream;
+        rc = fcb_fftconv_clone(&tmp, &a);
+    }
+    if (rc == FCB_OK && a->eng) rc = fcb_engine_update_reserve(a->eng);
+    if (rc != FCB_OK) {
+        fcb_fftconv_free(a);
+        fcb_crossfade_free(c);
+        return rc;
+    }
+    fcb_fftconv_free(c->a);
+    c->a = a;
+    c->crossfader = s->crossfader;
+    c->response_pending = s->response_pending;
+    c->rings_same = s->rings_same;
+    const size_t n = s->max_buffer_size ? s->max_buffer_size : 1, rows = s->b->opt.shared_ir ? 1 : s->C;
+    auto cp = [&](void *d, const void *src, size_t bytes) {
+        if (rc == FCB_OK && bytes && cudaMemcpyAsync(d, src, bytes, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess)
+            rc = fail(FCB_ERR_CUDA, "crossfade clone copy failed");
+    };
+    cp(c->buffer_a, s->buffer_a, s->C * n * sizeof(float));
+    cp(c->buffer_b, s->buffer_b, s->C * n * sizeof(float));
+    cp(c->stored_response, s->stored_response, rows * (s->stored_len ? s->stored_len : 0) * sizeof(float));
+    if (rc == FCB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(FCB_ERR_CUDA, "sync failed");
+    if (rc != FCB_OK) {
+        fcb_crossfade_free(c);
+        return rc;
+    }
+    *out = c;
+    return FCB_OK;
 }
 
 extern "C" int fcb_crossfade_sync(fcb_crossfade *c)

@@ -51,6 +51,10 @@ const char *fcb_version(void);
 uint64_t fcb_launch_count(void);
 /* number of visible CUDA devices, or -1 */
 int fcb_device_count(void);
+/* test hook: device / pinned allocations, stream and event creations and their releases made by this library so far.
+ * update() and process() must leave it unchanged in the steady state (the reference's real-time rule, src/lib.rs:8);
+ * tests/test_gpu_realtime.py pins that. */
+uint64_t fcb_debug_alloc_count(void);
 
 /* tuning knobs for benchmarking sweeps: "mac_impl" (0 auto, 1 LDG kernel, 2 TMA pipeline),
  * "mac_stages" (2, 3, 4, 6 pipeline stages of 32 KB), "pipe_group" (channels per group of the
@@ -60,7 +64,9 @@ int fcb_device_count(void);
  * one fused K1+K2+K3 kernel, 0 = three launches; outputs are bit-identical), "fused_stages" (2 or 3), "fused_pair" (1 = convolvers fed the same input share one launch), "fused_short" (delay lines of up to this many segments run
  * the fused kernel with 2-row stages so that a fourth CTA per SM hides the FFT latency; default 40, 0 = off), "mapped_io" (1 = small-batch host
  * calls go through mapped pinned memory instead of the copy engines), "zero_copy" (1 = when the caller's
- * buffers are pinned, large-batch whole-block calls let the kernel read/write them over PCIe directly) */
+ * buffers are pinned, large-batch whole-block calls let the kernel read/write them over PCIe directly), "strict_todo"
+ * (1 = fcb_twostage_update and fcb_crossfade_reset answer FCB_ERR_TODO like the reference's todo!(); default 0 = the
+ * extensions documented at those entry points) */
 int fcb_tune(const char *key, int value);
 
 /* live timing of the K2 launches: while enabled every K2 launch is bracketed by CUDA events on
@@ -108,6 +114,25 @@ int fcb_engine_set_ir(fcb_engine *e, size_t chan0, size_t nchan, const float *ir
                       size_t stride, int is_update);
 int fcb_engine_set_ir_dev(fcb_engine *e, size_t chan0, size_t nchan, const float *irs_dev, size_t len,
                           size_t stride, int is_update);
+
+/* Background IR update — update() that never makes a block wait.  A second copy of the IR spectra
+ * (the "shadow") is filled by K5 on a low-priority side stream while the blocks keep reading the active copy; commit
+ * swaps the two pointers and zeroes pre_multiplied / overlap exactly like update() (:185-188).
+ *   reserve  once after create, outside the audio path (the only call here that allocates: S*B*8 bytes per IR channel)
+ *   begin    irs: [ir_channels][len], stride in samples; host memory (on_device = 0) or device memory (1).  Returns at
+ *            once when irs is page-locked or device memory — it must then stay untouched until ready() answers 1;
+ *            pageable memory is staged by the driver during the call.  A second begin before commit overwrites the first.
+ *   ready    1 = the shadow copy is complete, 0 = K5 still running, -1 = error; never blocks
+ *   commit   swap.  Blocks queued afterwards wait ON THE DEVICE for K5 if it has not finished — the host never does.
+ *   wait     host-blocking wait for the copy + K5 (to get a page-locked source buffer back)
+ *   join     make `stream` wait on the device for the K5 queued so far */
+int fcb_engine_update_reserve(fcb_engine *e);
+int fcb_engine_update_reserved(const fcb_engine *e);
+int fcb_engine_update_begin(fcb_engine *e, const float *irs, size_t len, size_t stride, int on_device);
+int fcb_engine_update_ready(fcb_engine *e);
+int fcb_engine_update_commit(fcb_engine *e);
+int fcb_engine_update_wait(fcb_engine *e);
+int fcb_engine_update_join(fcb_engine *e, void *stream);
 
 /* reset() (:296-306): zero ring, overlap, input buffer, pre_multiplied.  IR spectra kept. */
 int fcb_engine_reset(fcb_engine *e);
@@ -173,11 +198,14 @@ int fcb_engine_process_block_pair_dev(fcb_engine *ea, fcb_engine *eb, const floa
  * registers (one IR row + one spectrum row loaded per segment feed T output blocks: T blocks for the HBM traffic of
  * one), independent inverse FFTs and a parallel overlap-add.  Same arithmetic and summation order per block as
  * nblocks calls of fcb_engine_process_block_dev: bit-identical output.  in/out are device pointers, or host pointers
- * when host_io != 0; the caller rotates `current` nblocks times afterwards.  The workspace grows to the longest
- * call seen (first use allocates; fcb_engine_multi_block_reserve does it ahead of time for real-time callers) up to
- * fcb_engine_multi_block_capacity blocks per pass.  fcb_tune("multi_block", 0) makes the host mirror process block by block. */
+ * when host_io != 0; the caller rotates `current` nblocks times afterwards.  No process call allocates: the workspace
+ * holds fcb_engine_multi_block_reserved blocks — fcb_engine_create reserves as many as fit 32 MB (when that is at
+ * least 2), fcb_engine_multi_block_reserve resizes it outside the audio path, up to fcb_engine_multi_block_capacity —
+ * and fcb_engine_process_blocks refuses more (the host mirror then splits the call, block by block if need be).
+ * fcb_tune("multi_block", 0) makes the host mirror process block by block. */
 int fcb_engine_multi_block_ok(const fcb_engine *e, size_t current, size_t active);
 size_t fcb_engine_multi_block_capacity(fcb_engine *e);
+size_t fcb_engine_multi_block_reserved(const fcb_engine *e);
 int fcb_engine_multi_block_reserve(fcb_engine *e, size_t nblocks);
 int fcb_engine_process_blocks(fcb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
                               size_t current, size_t active, size_t nblocks, const fcb_epilogue *epi, int host_io);
@@ -221,6 +249,18 @@ int fcb_fftconv_default(fcb_fftconv **out, size_t channels, const fcb_options *o
 int fcb_fftconv_clone(const fcb_fftconv *c, fcb_fftconv **out);
 void fcb_fftconv_free(fcb_fftconv *c);
 int fcb_fftconv_update(fcb_fftconv *c, const float *irs, size_t ir_len);
+/* update() for real-time callers (fcb_engine_update_*): reserve once after init; begin queues the copy + K5 in the
+ * background and returns (irs page-locked: untouched until pending() answers 0; pageable: staged during the call);
+ * the new response is swapped in between two process calls — with FCB_UPDATE_WAIT at the very next one (the device
+ * waits for K5 if need be: same output as fcb_fftconv_update), otherwise at the first one that finds K5 finished
+ * (no block ever waits; the old response plays until then). */
+#define FCB_UPDATE_WAIT 1
+int fcb_fftconv_update_reserve(fcb_fftconv *c);
+int fcb_fftconv_update_begin(fcb_fftconv *c, const float *irs, size_t ir_len, int flags);
+int fcb_fftconv_update_pending(const fcb_fftconv *c);
+/* calls of several whole blocks run as one time-batched pass only within the reserved workspace (process never
+ * allocates): reserve it for calls of up to max_call_samples samples, outside the audio path */
+int fcb_fftconv_reserve(fcb_fftconv *c, size_t max_call_samples);
 int fcb_fftconv_reset(fcb_fftconv *c);
 int fcb_fftconv_process(fcb_fftconv *c, const float *in, size_t in_len, size_t in_stride, float *out,
                         size_t out_len, size_t out_stride);
@@ -241,7 +281,11 @@ int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t channels, siz
                       size_t block_size, size_t max_response_length, const fcb_options *opt);
 int fcb_twostage_clone(const fcb_twostage *c, fcb_twostage **out);
 void fcb_twostage_free(fcb_twostage *c);
-int fcb_twostage_update(fcb_twostage *c, const float *irs, size_t ir_len); /* FCB_ERR_TODO */
+/* todo!() in the reference (:408-410).  EXTENSION, default: the per-stage FFTConvolver::update (:174-213) on the
+ * response zero-padded to max_response_length and re-sliced like init (:349-384); rings, partial blocks and tail
+ * outputs already computed are kept, each stage's overlap and pre_multiplied are zeroed; panics (FCB_ERR_PANIC) when
+ * ir_len > max_response_length; allocation-free.  With fcb_tune("strict_todo", 1): FCB_ERR_TODO. */
+int fcb_twostage_update(fcb_twostage *c, const float *irs, size_t ir_len);
 int fcb_twostage_reset(fcb_twostage *c);
 int fcb_twostage_process(fcb_twostage *c, const float *in, size_t in_len, size_t in_stride, float *out,
                          size_t out_len, size_t out_stride);
@@ -263,7 +307,17 @@ int fcb_crossfade_process(fcb_crossfade *c, const float *in, size_t in_len, size
                           size_t out_len, size_t out_stride);
 int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in_dev, size_t in_len, size_t in_stride,
                               float *out_dev, size_t out_len, size_t out_stride);
-int fcb_crossfade_reset(fcb_crossfade *c); /* FCB_ERR_TODO */
+/* todo!() in the reference (src/crossfade_convolver.rs:80-82).  EXTENSION, default: both convolvers reset
+ * (src/fft_convolver.rs:296-306), buffer_a / buffer_b zeroed, a running fade finished at once (the crossfader lands
+ * where `mix` leaves it when counter == fading_samples, :261-273), a pending response stays pending.
+ * With fcb_tune("strict_todo", 1): FCB_ERR_TODO. */
+int fcb_crossfade_reset(fcb_crossfade *c);
+/* #[derive(Clone)] (src/crossfade_convolver.rs:10) */
+int fcb_crossfade_clone(const fcb_crossfade *c, fcb_crossfade **out);
+/* update() that never waits for a copy or a kernel: irs must be page-locked (else this is fcb_crossfade_update) and
+ * stay untouched until fcb_crossfade_update_pending answers 0.  State changes and output are those of update(). */
+int fcb_crossfade_update_begin(fcb_crossfade *c, const float *irs, size_t ir_len);
+int fcb_crossfade_update_pending(fcb_crossfade *c);
 int fcb_crossfade_is_crossfading(const fcb_crossfade *c);
 int fcb_crossfade_sync(fcb_crossfade *c);
 /* crossfader state for tests: counter, mix_value, approaching(0/1), target(0=A,1=B) */

@@ -24,6 +24,7 @@ def main():
     C, B, L = 4096, 512, 96000
     st = torch.cuda.Stream()
     conv = F.FFTConvolver.init(bench.synth_irs(0, C, 0, L), B, L, stream=st.cuda_stream)
+    conv.reserve(B * 16)  # process() never allocates: the multi-block workspace is sized here
     import os
     from fft_convolution_b200 import _lib
     for kv in filter(None, os.environ.get("FCB_TUNE", "").split(",")):

@@ -103,3 +103,39 @@ def test_config4_shape_mimo_full_matrix(F):
         for i in range(N):
             t += truth(x[i], h[o, i])
         assert np.max(np.abs(y[o] - t)) <= TOL * rms(t), o
+
+
+def test_config1_full_channel_count_vs_oracle(F):
+    """configs[1] at its full 64 channels: TwoStage head 128 / T = 8192 (derived), 5 s IRs, 200 head blocks (three tail
+    periods and a bit) — every channel against its own oracle convolver (OpenMP over channels on the CPU side)"""
+    import oracle
+    C, H, L, NB = 64, 128, 240000, 200
+    h = bench.synth_irs(0, C, 0, L)
+    x = bench.synth_noise(0, C, 0, H * NB)
+    conv = F.TwoStageFFTConvolver.init(h, H, L, async_tail=True)
+    assert conv.tail_block_size == 8192
+    y = run_blocks(conv, x, H)
+    ref = oracle.batch_twostage(h, H, x, H)
+    worst = max(float(np.max(np.abs(y[c] - ref[c]))) / rms(ref[c]) for c in range(C))
+    assert worst <= TOL, f"configs[1] x 64 channels: {worst:.3e} x RMS"
+
+
+def test_config2_full_channel_count_vs_oracle(F):
+    """configs[2] at its full 256 channels: CrossfadeConvolver::init(h, 512, 96 000) — a 96 000-sample fade after a
+    512-sample hold — with update() every 50 blocks, 120 blocks, every channel against its own oracle convolver"""
+    import oracle
+    C, B, L, NB = 256, 512, 96000, 120
+    h = bench.synth_irs(0, C, 0, L)
+    upd = np.stack([bench.synth_irs(0, C, u, L) for u in (1, 2)])
+    x = bench.synth_noise(0, C, 0, B * NB)
+    conv = F.CrossfadeConvolver.init(h, B, L)
+    y = np.zeros_like(x)
+    blk = np.zeros((C, B), np.float32)
+    for b in range(NB):
+        if b and b % 50 == 0:
+            conv.update(upd[(b // 50 - 1) % 2])
+        conv.process(np.ascontiguousarray(x[:, b * B:(b + 1) * B]), blk)
+        y[:, b * B:(b + 1) * B] = blk
+    ref = oracle.batch_crossfade(h, B, x, irs_upd=upd, update_every=50)
+    worst = max(float(np.max(np.abs(y[c] - ref[c]))) / rms(ref[c]) for c in range(C))
+    assert worst <= TOL, f"configs[2] x 256 channels: {worst:.3e} x RMS"

@@ -6,7 +6,7 @@ import pytest
 
 import oracle
 from oracle import oracle_np
-from refsignals import rms
+from refsignals import rms, WholeRun
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -137,6 +137,7 @@ def test_update_changes_segment_count(F):
     x = oracle.gen_noise(5, 0, B * 60)
     g, o = F.FFTConvolver.init(h0, B, L), oracle.FFTConvolver.init(h0, B, L)
     og, oo = np.zeros(B, np.float32), np.zeros(B, np.float32)
+    run = WholeRun()
     for i in range(60):
         if i == 13:
             g.update(h1); o.update(h1)
@@ -150,7 +151,8 @@ def test_update_changes_segment_count(F):
         else:
             g.process(x[i * B:(i + 1) * B], og); o.process(x[i * B:(i + 1) * B], oo)
         assert g.current == o.current
-        assert np.max(np.abs(og - oo)) <= 2e-5 * max(rms(oo), 0.05)
+        run.add(og, oo)
+    run.check(TOL, "update with changing segment counts")
 
 
 def test_empty_ir_and_zero_length(F):
@@ -363,6 +365,7 @@ def test_twostage_non_power_of_two_head_panics_like_reference(F):
     assert g.tail_block_size == o.tail_block_size == 512
     og, oo = np.zeros(H, np.float32), np.zeros(H, np.float32)
     failed_at = None
+    run = WholeRun()
     for i in range(12):
         blk = x[i * H:(i + 1) * H]
         try:
@@ -373,7 +376,8 @@ def test_twostage_non_power_of_two_head_panics_like_reference(F):
             failed_at = i
             break
         g.process(blk, og)
-        assert np.max(np.abs(og - oo)) <= 2e-5 * max(rms(oo), 0.05)
+        run.add(og, oo)
+    run.check(TOL, "two-stage, head size not dividing T")
     assert failed_at == 10
 
 
@@ -402,6 +406,7 @@ def test_crossfade_sequences_vs_oracle(F):
     og = np.zeros((C, B), np.float32)
     oo = np.zeros(B, np.float32)
     upd = {5: 1, 7: 2, 8: 3, 30: 1, 50: 2}
+    runs = [WholeRun() for _ in range(C)]
     for i in range(80):
         if i in upd:
             g.update(irs[upd[i]])
@@ -414,12 +419,14 @@ def test_crossfade_sequences_vs_oracle(F):
         for c in range(C):
             oo[:] = 0
             os_[c].process(blk[c], oo[:n_out])
-            assert np.max(np.abs(og[c] - oo[:n_out])) <= 2e-5 * max(rms(oo[:n_out]), 0.05), (i, c)
+            runs[c].add(og[c], oo[:n_out])
             assert g.is_crossfading() == os_[c].is_crossfading()
             cnt, mix, appr, tgt = g.state()
             s = os_[c].crossfader
             assert (cnt, appr, tgt) == (s.counter, bool(s.approaching), s.target)
             assert np.float32(mix) == np.float32(s.mix_value)
+    for c in range(C):
+        runs[c].check(TOL, f"crossfade sequence, channel {c}")
 
 
 def test_crossfade_config3_shape(F):
@@ -431,14 +438,14 @@ def test_crossfade_config3_shape(F):
     g = F.CrossfadeConvolver.init(ir(0), B, L)
     o = oracle.CrossfadeConvolver.init(ir(0)[1], B, L)
     og, oo = np.zeros((C, B), np.float32), np.zeros(B, np.float32)
-    worst = 0.0
+    run = WholeRun()
     for i in range(120):
         if i and i % 50 == 0:
             g.update(ir(i // 50)); o.update(ir(i // 50)[1])
         blk = np.ascontiguousarray(x[:, i * B:(i + 1) * B])
         g.process(blk, og); o.process(blk[1], oo)
-        worst = max(worst, float(np.max(np.abs(og[1] - oo))) / max(rms(oo), 0.05))
-    assert worst <= 2e-5
+        run.add(og[1], oo)
+    run.check(TOL, "configs[2] shape")
 
 
 def test_engine_on_second_device(F):

@@ -168,12 +168,18 @@ def test_reference_panics(F):
     with pytest.raises(F.ConvolutionPanic):
         c.process(np.zeros(3, np.float32), np.zeros(4, np.float32))
     t = F.TwoStageFFTConvolver.init(np.zeros(100, np.float32), 8, 100)
-    with pytest.raises(F.NotYetImplemented):
-        t.update(np.zeros(10, np.float32))
+    x = F.CrossfadeConvolver.init(np.ones(16, np.float32), 8, 16)
+    F.strict_todo(True)  # the reference's two todo!() methods (src/fft_convolver.rs:408-410, src/crossfade_convolver.rs:80-82)
+    try:
+        with pytest.raises(F.NotYetImplemented):
+            t.update(np.zeros(10, np.float32))
+        with pytest.raises(F.NotYetImplemented):
+            x.reset()
+    finally:
+        F.strict_todo(False)
+    with pytest.raises(F.ConvolutionPanic):
+        t.update(np.zeros(101, np.float32))  # the extension panics like FFTConvolver::update (:177-179)
     with pytest.raises(F.ConvolutionPanic):
         t.process(np.zeros(9, np.float32), np.zeros(9, np.float32))
-    x = F.CrossfadeConvolver.init(np.ones(16, np.float32), 8, 16)
-    with pytest.raises(F.NotYetImplemented):
-        x.reset()
     with pytest.raises(F.ConvolutionPanic):
         x.process(np.zeros(8, np.float32), np.zeros(9, np.float32))
