@@ -58,7 +58,14 @@ extern "C" {
     // several whole blocks in one time-batched pass (bit-identical to the block-by-block loop); host_io != 0: host pointers
     pub fn fcb_engine_multi_block_ok(e: *const FcbEngine, current: usize, active: usize) -> c_int;
     pub fn fcb_engine_multi_block_capacity(e: *mut FcbEngine) -> usize;
+    pub fn fcb_engine_multi_block_reserved(e: *const FcbEngine) -> usize;
     pub fn fcb_engine_multi_block_reserve(e: *mut FcbEngine, nblocks: usize) -> c_int;
+    // background IR update: K5 into a shadow copy of the spectra, pointer flip at commit (no block ever waits)
+    pub fn fcb_engine_update_reserve(e: *mut FcbEngine) -> c_int;
+    pub fn fcb_engine_update_begin(e: *mut FcbEngine, irs: *const f32, len: usize, stride: usize, on_device: c_int) -> c_int;
+    pub fn fcb_engine_update_ready(e: *mut FcbEngine) -> c_int;
+    pub fn fcb_engine_update_commit(e: *mut FcbEngine) -> c_int;
+    pub fn fcb_engine_update_wait(e: *mut FcbEngine) -> c_int;
     pub fn fcb_engine_process_blocks(e: *mut FcbEngine, input: *const f32, in_stride: usize, output: *mut f32,
                                      out_stride: usize, current: usize, active: usize, nblocks: usize,
                                      epi: *const FcbEpilogue, host_io: c_int) -> c_int;
@@ -164,7 +171,9 @@ impl Convolution for CudaFFTConvolver {
             if input_buffer_was_empty && whole >= 2
                 && unsafe { fcb_engine_multi_block_ok(self.engine, self.current, self.active_seg_count) } != 0
             {
-                let nb = std::cmp::min(whole, unsafe { fcb_engine_multi_block_capacity(self.engine) });
+                // process() never allocates: only as many blocks as the workspace reserved at create / by reserve_blocks()
+                let nb = std::cmp::min(whole, unsafe { fcb_engine_multi_block_reserved(self.engine) });
+                if nb >= 2 {
                 let n = nb * self.block_size;
                 let chunk = &input[processed..processed + n]; // panics like the reference if too short
                 check(unsafe {
@@ -176,6 +185,7 @@ impl Convolution for CudaFFTConvolver {
                 }
                 processed += n;
                 continue;
+                }
             }
             let processing = std::cmp::min(output.len() - processed, self.block_size - self.input_buffer_fill);
             let pos = self.input_buffer_fill;
@@ -202,6 +212,13 @@ impl Convolution for CudaFFTConvolver {
     }
 }
 
+impl CudaFFTConvolver {
+    /// size the multi-block workspace for calls of up to `nblocks` whole blocks (outside the audio path)
+    pub fn reserve_blocks(&mut self, nblocks: usize) {
+        check(unsafe { fcb_engine_multi_block_reserve(self.engine, nblocks) });
+    }
+}
+
 impl Clone for CudaFFTConvolver {
     fn clone(&self) -> Self {
         let mut engine = std::ptr::null_mut();
@@ -213,5 +230,389 @@ impl Clone for CudaFFTConvolver {
 impl Drop for CudaFFTConvolver {
     fn drop(&mut self) {
         unsafe { fcb_engine_destroy(self.engine) };
+    }
+}
+
+
+// =================================================================================================
+// Layer 2 — the three reference types with their scheduler on the C++ side (host_mirror.cu), batched
+// over C lock-step channels.  These bindings give the fused paths (head + tail0 and A + B in one
+// launch, head/tail sum and crossfade gains in the K3 epilogue, the big tail on its own stream) that
+// a composition of mono `CudaFFTConvolver`s cannot: the reference's `TwoStageFFTConvolver` holds
+// three CONCRETE `FFTConvolver` fields (reference src/fft_convolver.rs:323-337), it is not generic
+// over `Convolution`, so it cannot be re-instantiated over `CudaFFTConvolver`.
+// =================================================================================================
+#[repr(C)]
+pub struct FcbFftconv {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct FcbTwostage {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct FcbCrossfade {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+pub struct FcbOptions {
+    pub device: c_int,
+    pub stream: *mut c_void,
+    pub shared_ir: c_int,
+    pub async_tail: c_int,
+    pub forced_tail_block: usize,
+}
+
+impl FcbOptions {
+    pub fn new(device: c_int) -> Self {
+        Self { device, stream: std::ptr::null_mut(), shared_ir: 0, async_tail: 0, forced_tail_block: 0 }
+    }
+}
+
+extern "C" {
+    pub fn fcb_fftconv_init(out: *mut *mut FcbFftconv, irs: *const f32, channels: usize, ir_len: usize, block_size: usize,
+                            max_response_length: usize, opt: *const FcbOptions) -> c_int;
+    pub fn fcb_fftconv_clone(c: *const FcbFftconv, out: *mut *mut FcbFftconv) -> c_int;
+    pub fn fcb_fftconv_free(c: *mut FcbFftconv);
+    pub fn fcb_fftconv_update(c: *mut FcbFftconv, irs: *const f32, ir_len: usize) -> c_int;
+    pub fn fcb_fftconv_update_reserve(c: *mut FcbFftconv) -> c_int;
+    pub fn fcb_fftconv_update_begin(c: *mut FcbFftconv, irs: *const f32, ir_len: usize, flags: c_int) -> c_int;
+    pub fn fcb_fftconv_update_pending(c: *const FcbFftconv) -> c_int;
+    pub fn fcb_fftconv_reserve(c: *mut FcbFftconv, max_call_samples: usize) -> c_int;
+    pub fn fcb_fftconv_reset(c: *mut FcbFftconv) -> c_int;
+    pub fn fcb_fftconv_process(c: *mut FcbFftconv, input: *const f32, in_len: usize, in_stride: usize, output: *mut f32,
+                               out_len: usize, out_stride: usize) -> c_int;
+
+    pub fn fcb_twostage_init(out: *mut *mut FcbTwostage, irs: *const f32, channels: usize, ir_len: usize, block_size: usize,
+                             max_response_length: usize, opt: *const FcbOptions) -> c_int;
+    pub fn fcb_twostage_clone(c: *const FcbTwostage, out: *mut *mut FcbTwostage) -> c_int;
+    pub fn fcb_twostage_free(c: *mut FcbTwostage);
+    pub fn fcb_twostage_update(c: *mut FcbTwostage, irs: *const f32, ir_len: usize) -> c_int;
+    pub fn fcb_twostage_reset(c: *mut FcbTwostage) -> c_int;
+    pub fn fcb_twostage_process(c: *mut FcbTwostage, input: *const f32, in_len: usize, in_stride: usize, output: *mut f32,
+                                out_len: usize, out_stride: usize) -> c_int;
+
+    pub fn fcb_crossfade_new(out: *mut *mut FcbCrossfade, convolver: *mut FcbFftconv, max_response_length: usize,
+                             max_buffer_size: usize, crossfade_samples: usize) -> c_int;
+    pub fn fcb_crossfade_init(out: *mut *mut FcbCrossfade, irs: *const f32, channels: usize, ir_len: usize,
+                              max_block_size: usize, max_response_length: usize, opt: *const FcbOptions) -> c_int;
+    pub fn fcb_crossfade_clone(c: *const FcbCrossfade, out: *mut *mut FcbCrossfade) -> c_int;
+    pub fn fcb_crossfade_free(c: *mut FcbCrossfade);
+    pub fn fcb_crossfade_update(c: *mut FcbCrossfade, irs: *const f32, ir_len: usize) -> c_int;
+    pub fn fcb_crossfade_update_begin(c: *mut FcbCrossfade, irs: *const f32, ir_len: usize) -> c_int;
+    pub fn fcb_crossfade_update_pending(c: *mut FcbCrossfade) -> c_int;
+    pub fn fcb_crossfade_reset(c: *mut FcbCrossfade) -> c_int;
+    pub fn fcb_crossfade_is_crossfading(c: *const FcbCrossfade) -> c_int;
+    pub fn fcb_crossfade_process(c: *mut FcbCrossfade, input: *const f32, in_len: usize, in_stride: usize, output: *mut f32,
+                                 out_len: usize, out_stride: usize) -> c_int;
+}
+
+/// The batched multi-channel entry point north_star adds: C independent `FFTConvolver`s in lock step.
+/// Buffers are planar, `[channel][sample]`, channel stride = samples per call.
+pub struct CudaFFTConvolverBatch {
+    handle: *mut FcbFftconv,
+    channels: usize,
+}
+
+unsafe impl Send for CudaFFTConvolverBatch {}
+
+impl CudaFFTConvolverBatch {
+    /// `responses`: `[channels][ir_len]` flattened.  Panics like `FFTConvolver::init` (reference :106-110).
+    pub fn init(responses: &[f32], channels: usize, block_size: usize, max_response_length: usize) -> Self {
+        assert!(channels > 0 && responses.len() % channels == 0);
+        let mut handle = std::ptr::null_mut();
+        let opt = FcbOptions::new(0);
+        check(unsafe {
+            fcb_fftconv_init(&mut handle, responses.as_ptr(), channels, responses.len() / channels, block_size,
+                             max_response_length, &opt)
+        });
+        Self { handle, channels }
+    }
+    pub fn channels(&self) -> usize {
+        self.channels
+    }
+    /// `responses`: `[channels][len]` flattened; every channel gets a response of the same length
+    pub fn update(&mut self, responses: &[f32]) {
+        check(unsafe { fcb_fftconv_update(self.handle, responses.as_ptr(), responses.len() / self.channels) });
+    }
+    pub fn reset(&mut self) {
+        check(unsafe { fcb_fftconv_reset(self.handle) });
+    }
+    /// `input`, `output`: `[channels][n]` flattened, n = samples per channel in this call
+    pub fn process(&mut self, input: &[f32], output: &mut [f32]) {
+        let (n_in, n_out) = (input.len() / self.channels, output.len() / self.channels);
+        check(unsafe {
+            fcb_fftconv_process(self.handle, input.as_ptr(), n_in, n_in, output.as_mut_ptr(), n_out, n_out)
+        });
+    }
+    /// calls of up to this many samples per channel may run as one time-batched pass (process never allocates)
+    pub fn reserve(&mut self, max_call_samples: usize) {
+        check(unsafe { fcb_fftconv_reserve(self.handle, max_call_samples) });
+    }
+    /// real-time update: `reserve_update()` once, then `update_begin()` returns at once (page-locked `responses`, kept
+    /// alive until `update_pending()` is false) and the new responses are swapped in between two blocks
+    pub fn reserve_update(&mut self) {
+        check(unsafe { fcb_fftconv_update_reserve(self.handle) });
+    }
+    /// # Safety
+    /// `responses` must point to `[channels][len]` f32 that stay valid and unchanged while `update_pending()`.
+    pub unsafe fn update_begin(&mut self, responses: *const f32, len: usize, wait_for_it: bool) {
+        check(fcb_fftconv_update_begin(self.handle, responses, len, wait_for_it as c_int));
+    }
+    pub fn update_pending(&self) -> bool {
+        unsafe { fcb_fftconv_update_pending(self.handle) != 0 }
+    }
+}
+
+impl Clone for CudaFFTConvolverBatch {
+    fn clone(&self) -> Self {
+        let mut handle = std::ptr::null_mut();
+        check(unsafe { fcb_fftconv_clone(self.handle, &mut handle) });
+        Self { handle, channels: self.channels }
+    }
+}
+
+impl Drop for CudaFFTConvolverBatch {
+    fn drop(&mut self) {
+        unsafe { fcb_fftconv_free(self.handle) };
+    }
+}
+
+/// Drop-in for `fft_convolver::TwoStageFFTConvolver` (reference src/fft_convolver.rs:323-526), mono.
+/// `update` is `todo!()` in the reference; here it is the documented extension of `fcb_twostage_update`
+/// (`fcb_tune("strict_todo", 1)` restores the panic).
+pub struct CudaTwoStageFFTConvolver {
+    handle: *mut FcbTwostage,
+}
+
+unsafe impl Send for CudaTwoStageFFTConvolver {}
+
+impl CudaTwoStageFFTConvolver {
+    /// the reference computes the tail block in the audio call (:478-486); `async_tail` runs it on a second stream
+    pub fn init_with(impulse_response: &[f32], block_size: usize, max_response_length: usize, async_tail: bool) -> Self {
+        let mut handle = std::ptr::null_mut();
+        let mut opt = FcbOptions::new(0);
+        opt.async_tail = async_tail as c_int;
+        check(unsafe {
+            fcb_twostage_init(&mut handle, impulse_response.as_ptr(), 1, impulse_response.len(), block_size,
+                              max_response_length, &opt)
+        });
+        Self { handle }
+    }
+}
+
+impl Convolution for CudaTwoStageFFTConvolver {
+    fn init(impulse_response: &[f32], block_size: usize, max_response_length: usize) -> Self {
+        Self::init_with(impulse_response, block_size, max_response_length, false)
+    }
+    fn update(&mut self, response: &[f32]) {
+        check(unsafe { fcb_twostage_update(self.handle, response.as_ptr(), response.len()) });
+    }
+    fn reset(&mut self) {
+        check(unsafe { fcb_twostage_reset(self.handle) });
+    }
+    fn process(&mut self, input: &[f32], output: &mut [f32]) {
+        check(unsafe {
+            fcb_twostage_process(self.handle, input.as_ptr(), input.len(), input.len(), output.as_mut_ptr(), output.len(),
+                                 output.len())
+        });
+    }
+}
+
+impl Clone for CudaTwoStageFFTConvolver {
+    fn clone(&self) -> Self {
+        let mut handle = std::ptr::null_mut();
+        check(unsafe { fcb_twostage_clone(self.handle, &mut handle) });
+        Self { handle }
+    }
+}
+
+impl Drop for CudaTwoStageFFTConvolver {
+    fn drop(&mut self) {
+        unsafe { fcb_twostage_free(self.handle) };
+    }
+}
+
+/// Drop-in for `crossfade_convolver::CrossfadeConvolver<FFTConvolver>` (reference
+/// src/crossfade_convolver.rs:3-105), mono; `CudaCrossfadeConvolver::batch_*` give the batched form.
+/// A and B run as ONE launch per block with the gain ramp in B's epilogue, and `update` builds the new spectra in
+/// the background.  (`CrossfadeConvolver<CudaFFTConvolver>` — the reference's generic type over the layer-1 binding —
+/// also works, at five FFI calls and a synchronisation per chunk per convolver and without those fusions.)
+pub struct CudaCrossfadeConvolver {
+    handle: *mut FcbCrossfade,
+    channels: usize,
+}
+
+unsafe impl Send for CudaCrossfadeConvolver {}
+
+impl CudaCrossfadeConvolver {
+    /// `CrossfadeConvolver::new` (reference :20-42); consumes `convolver`
+    pub fn new(convolver: CudaFFTConvolverBatch, max_response_length: usize, max_buffer_size: usize,
+               crossfade_samples: usize) -> Self {
+        let mut handle = std::ptr::null_mut();
+        let channels = convolver.channels;
+        check(unsafe { fcb_crossfade_new(&mut handle, convolver.handle, max_response_length, max_buffer_size, crossfade_samples) });
+        std::mem::forget(convolver); // ownership moved into the crossfade object
+        Self { handle, channels }
+    }
+    pub fn is_crossfading(&self) -> bool {
+        unsafe { fcb_crossfade_is_crossfading(self.handle) != 0 }
+    }
+    pub fn batch_update(&mut self, responses: &[f32]) {
+        check(unsafe { fcb_crossfade_update(self.handle, responses.as_ptr(), responses.len() / self.channels) });
+    }
+    pub fn batch_process(&mut self, input: &[f32], output: &mut [f32]) {
+        let (n_in, n_out) = (input.len() / self.channels, output.len() / self.channels);
+        check(unsafe { fcb_crossfade_process(self.handle, input.as_ptr(), n_in, n_in, output.as_mut_ptr(), n_out, n_out) });
+    }
+    /// # Safety
+    /// `responses`: page-locked `[channels][len]` f32, valid and unchanged while `update_pending()`.
+    pub unsafe fn update_begin(&mut self, responses: *const f32, len: usize) {
+        check(fcb_crossfade_update_begin(self.handle, responses, len));
+    }
+    pub fn update_pending(&mut self) -> bool {
+        unsafe { fcb_crossfade_update_pending(self.handle) != 0 }
+    }
+}
+
+impl Convolution for CudaCrossfadeConvolver {
+    // reference :46-49 — response.len() is both the stored capacity and the fade length
+    fn init(response: &[f32], max_block_size: usize, max_response_length: usize) -> Self {
+        let mut handle = std::ptr::null_mut();
+        let opt = FcbOptions::new(0);
+        check(unsafe {
+            fcb_crossfade_init(&mut handle, response.as_ptr(), 1, response.len(), max_block_size, max_response_length, &opt)
+        });
+        Self { handle, channels: 1 }
+    }
+    fn update(&mut self, response: &[f32]) {
+        check(unsafe { fcb_crossfade_update(self.handle, response.as_ptr(), response.len()) });
+    }
+    // todo!() in the reference (:80-82); the documented extension of fcb_crossfade_reset
+    fn reset(&mut self) {
+        check(unsafe { fcb_crossfade_reset(self.handle) });
+    }
+    fn process(&mut self, input: &[f32], output: &mut [f32]) {
+        check(unsafe {
+            fcb_crossfade_process(self.handle, input.as_ptr(), input.len(), input.len(), output.as_mut_ptr(), output.len(),
+                                  output.len())
+        });
+    }
+}
+
+impl Clone for CudaCrossfadeConvolver {
+    fn clone(&self) -> Self {
+        let mut handle = std::ptr::null_mut();
+        check(unsafe { fcb_crossfade_clone(self.handle, &mut handle) });
+        Self { handle, channels: self.channels }
+    }
+}
+
+impl Drop for CudaCrossfadeConvolver {
+    fn drop(&mut self) {
+        unsafe { fcb_crossfade_free(self.handle) };
+    }
+}
+
+/// The reference's own test scenarios (reference src/tests.rs:18-257 and the three passthrough tests), written
+/// against the trait so that they run over the CUDA types unchanged: `cargo test --release` on a B200 box.
+#[cfg(test)]
+mod tests {
+    use super::*;
+
+    const SAMPLE_RATE: f32 = 44100.0;
+
+    fn generate_sinusoid(length: usize, frequency: f32, sample_rate: f32, gain: f32) -> Vec<f32> {
+        (0..length).map(|i| gain * (2.0 * std::f32::consts::PI * frequency * i as f32 / sample_rate).sin()).collect()
+    }
+
+    fn passthrough<C: Convolution>() {
+        let mut response = [0.0_f32; 1024];
+        response[0] = 1.0;
+        let mut convolver = C::init(&response, 1024, response.len());
+        let input = vec![1.0_f32; 1024];
+        let mut output = vec![0.0_f32; 1024];
+        convolver.process(&input, &mut output);
+        for i in 0..1024 {
+            assert!((output[i] - 1.0).abs() < 1e-6);
+        }
+    }
+
+    #[test]
+    fn passthrough_all_types() {
+        passthrough::<CudaFFTConvolver>();
+        passthrough::<CudaTwoStageFFTConvolver>();
+        passthrough::<CudaCrossfadeConvolver>();
+    }
+
+    fn update_is_reset<C: Convolution>() {
+        let block_size = 512;
+        let response_a = generate_sinusoid(block_size, 1000.0, SAMPLE_RATE, 1.0);
+        let response_b = generate_sinusoid(block_size, 2000.0, SAMPLE_RATE, 0.7);
+        let mut convolver_a = C::init(&response_a, block_size, response_a.len());
+        let mut convolver_b = C::init(&response_b, block_size, response_b.len());
+        let mut convolver_update = C::init(&response_a, block_size, response_a.len());
+        let (mut out_a, mut out_b, mut out_u) = (vec![0.0; block_size], vec![0.0; block_size], vec![0.0; block_size]);
+        let input = generate_sinusoid(16 * block_size, 1300.0, SAMPLE_RATE, 1.0);
+        for i in 0..16 {
+            if i == 8 {
+                convolver_update.update(&response_b);
+            }
+            let blk = &input[i * block_size..(i + 1) * block_size];
+            convolver_update.process(blk, &mut out_u);
+            let reference = if i < 8 {
+                convolver_a.process(blk, &mut out_a);
+                &out_a
+            } else {
+                convolver_b.process(blk, &mut out_b);
+                &out_b
+            };
+            for j in 0..block_size {
+                assert!((reference[j] - out_u[j]).abs() < 1e-6 * 16.0); // outputs have RMS ~ 15: 1e-6 absolute is below f32 resolution there
+            }
+        }
+    }
+
+    #[test]
+    fn fft_convolver_update_is_reset() {
+        update_is_reset::<CudaFFTConvolver>();
+    }
+
+    #[test]
+    fn twostage_equal() {
+        let block_size = 64;
+        let response = generate_sinusoid(12000, 1000.0, SAMPLE_RATE, 0.1);
+        let mut convolver_a = CudaFFTConvolver::init(&response, block_size / 2, response.len());
+        let mut convolver_b = CudaTwoStageFFTConvolver::init(&response, block_size, response.len());
+        let (mut out_a, mut out_b) = (vec![0.0; block_size], vec![0.0; block_size]);
+        let input = generate_sinusoid(1000 * block_size, 1300.0, SAMPLE_RATE, 0.1);
+        for i in 0..1000 {
+            let blk = &input[i * block_size..(i + 1) * block_size];
+            convolver_a.process(blk, &mut out_a);
+            convolver_b.process(blk, &mut out_b);
+            for j in 0..block_size {
+                assert!((out_a[j] - out_b[j]).abs() < 1e-5);
+            }
+        }
+    }
+
+    #[test]
+    fn batch_equals_mono() {
+        let (channels, block, len) = (3usize, 64usize, 1000usize);
+        let responses: Vec<f32> = (0..channels).flat_map(|c| generate_sinusoid(len, 500.0 + 300.0 * c as f32, SAMPLE_RATE, 0.05)).collect();
+        let mut batch = CudaFFTConvolverBatch::init(&responses, channels, block, len);
+        let mut monos: Vec<CudaFFTConvolver> =
+            (0..channels).map(|c| CudaFFTConvolver::init(&responses[c * len..(c + 1) * len], block, len)).collect();
+        let input: Vec<f32> = (0..channels).flat_map(|c| generate_sinusoid(block, 900.0 + 50.0 * c as f32, SAMPLE_RATE, 1.0)).collect();
+        let mut out = vec![0.0_f32; channels * block];
+        let mut one = vec![0.0_f32; block];
+        for _ in 0..40 {
+            batch.process(&input, &mut out);
+            for c in 0..channels {
+                monos[c].process(&input[c * block..(c + 1) * block], &mut one);
+                assert_eq!(&out[c * block..(c + 1) * block], &one[..]);
+            }
+        }
     }
 }

@@ -102,11 +102,10 @@ static void conv_process(conv_t *c, const float *input, size_t in_len, float *ou
         const int was_empty = c->input_buffer_fill == 0;
         const size_t whole = (out_len - processed) / B;
         if (was_empty && whole >= 2 && fcb_engine_multi_block_ok(c->engine, c->current, c->active_seg_count)) {
-            size_t nb = whole, cap = fcb_engine_multi_block_capacity(c->engine);
+            size_t nb = whole, cap = fcb_engine_multi_block_reserved(c->engine); /* process never allocates */
             if (nb > cap) nb = cap;
             if (nb >= 2) {
                 const size_t n = nb * B;
-                CHECK(fcb_engine_multi_block_reserve(c->engine, nb));
                 CHECK(fcb_engine_process_blocks(c->engine, input + processed, n, output + processed, n, c->current,
                                                 c->active_seg_count, nb, NULL, 1));
                 for (size_t d = 0; d < nb; d++) rotate(c);
@@ -148,6 +147,7 @@ int main(int argc, char **argv)
 
     conv_t c;
     conv_init(&c, h0, n_h0, block, max_len);
+    CHECK(fcb_engine_multi_block_reserve(c.engine, 3)); /* CudaFFTConvolver::reserve_blocks(3): a 4-block call runs as 3 + 1 */
     size_t p = 0;
     long call = 0;
     while (p < n_x) {
