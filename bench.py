@@ -12,6 +12,15 @@ One "step" = one 512-sample block for every channel (K1 -> K2 -> K3).
 
 Prints ONE JSON line (rank 0).  Synthetic data per SURVEY.md §8(d) (splitmix64 white noise,
 random-decay unit-energy IRs), generated here with numpy — the product arm never touches oracle/.
+
+Beside the headline (`value`, `e2e`, `roofline`, `cpu_baseline`, unchanged in meaning) the line carries:
+  sustained   the same step timed over a >= 1 s window (the driver's K may be 20 steps = 18 ms)
+  strong      BASELINE configs[3] read as "4096 channels sharded across N GPUs": 4096 / N channels per GPU
+  realtime    the >= 1e5-channel claim measured, not extrapolated: 12 500 channels per GPU (1e5 / 8) and the largest
+              channel count whose block still fits the 10.667 ms period, 1000 consecutive blocks each through the
+              end-to-end host path, with p50 / p99 / max block time and the deadlines missed
+  mimo        (N > 1) BASELINE configs[4]: the 16 x 16 matrix with 10 s IRs sharded by IR partition over the N GPUs,
+              1 and 128 streams, peer exchange and NCCL all-reduce, checked in-run against the unsharded engine
 """
 from __future__ import annotations
 
@@ -199,12 +208,14 @@ def run_reference(args) -> None:
         t_tot += secs
         work += channels * calls * args.block / SAMPLE_RATE
     value = work / t_tot
-    sample = f"{channels} channels x {calls} blocks of {args.block} per step, {args.steps} steps"
+    sample = (f"{channels} of the workload's {args.channels} channels x {calls} blocks of {args.block} per step, {args.steps} steps; "
+              "throughput is per channel, so the figure stands for the whole workload (working set "
+              f"{channels * 2 * 188 * 513 * 8 / 1e6:.0f} MB >> LLC)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, None),
+        "config": config_dict(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "CPU restatement of the reference algorithm (oracle/), not rustfft: no Rust toolchain in the image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -213,15 +224,168 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
-def config_dict(args, extra):
-    d = {"workload": f"FFTConvolver x {args.channels} independent channels per GPU, IR {args.ir_seconds:g} s "
-                     f"({int(args.ir_seconds * SAMPLE_RATE)} taps, one IR per channel), block {args.block}, 48 kHz "
-                     "(BASELINE configs[3])",
-         "channels_per_gpu": args.channels, "block": args.block, "ir_taps": int(args.ir_seconds * SAMPLE_RATE),
-         "l2": "working set 6.3 GB/GPU per step >> 126 MB L2, no flush needed"}
-    if extra:
-        d.update(extra)
-    return d
+def config_dict(args):
+    """the workload both arms are quoted on — the same dict on the CUDA arm and on the reference arm (what each arm
+    actually timed per step is in `cpu_baseline.sample` / `tuning`, not here)"""
+    return {"workload": f"FFTConvolver x {args.channels} independent channels per GPU, IR {args.ir_seconds:g} s "
+                        f"({int(args.ir_seconds * SAMPLE_RATE)} taps, one IR per channel), block {args.block}, 48 kHz "
+                        "(BASELINE configs[3])",
+            "channels_per_gpu": args.channels, "block": args.block, "ir_taps": int(args.ir_seconds * SAMPLE_RATE),
+            "l2": "working set 6.3 GB/GPU per step >> 126 MB L2, no flush needed"}
+
+
+
+# ---------------------------------------------------------------------------------------------
+def kernel_source_hash() -> str:
+    """sha256 of the kernel sources the dominant kernel is built from: an ncu traffic figure is only quoted while the
+    kernels it was captured from are the ones being timed (scripts/capture_traffic.sh re-captures and re-stamps it)"""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("fused_kernel.cuh", "mac_kernels.cuh", "fft_kernels.cuh", "common.cuh"):
+        h.update((ROOT / "fft_convolution_b200" / "csrc" / name).read_bytes())
+    return h.hexdigest()[:16]
+
+
+def bind_to_gpu_numa_node(local: int) -> dict:
+    """Pin this rank's threads (and so the first-touch placement of the pinned buffers it allocates next) to the NUMA
+    node its GPU hangs off, when the box exposes more than one node.  Returns what was found, for the bench line."""
+    info = {"nodes_visible": None, "gpu_node": None, "bound": False}
+    try:
+        import torch
+        nodes = sorted(int(p.name[4:]) for p in Path("/sys/devices/system/node").glob("node[0-9]*"))
+        info["nodes_visible"] = len(nodes)
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int((Path("/sys/bus/pci/devices") / bdf / "numa_node").read_text())
+        info["gpu_node"] = node
+        if node >= 0 and len(nodes) > 1:
+            cpus = set()
+            for part in (Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(",")):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound"] = True
+    except Exception as e:  # sysfs not there (containers): nothing to bind
+        info["error"] = type(e).__name__
+    return info
+
+
+def percentile_ms(v, q):
+    return float(np.percentile(np.asarray(v), q) * 1000.0)
+
+
+def run_realtime(F, lib, local, rank, world, chan0, Cn_head, ms_e2e_per_block_head, B, L, blocks, barrier):
+    """The real-time claim, measured: C channels per GPU through the END-TO-END host path (pinned host buffers in and
+    out, synchronous call per block) for `blocks` consecutive blocks; every block's wall time against the block period.
+    Two sizes: 12 500 channels (1e5 / 8 GPUs) and the largest count whose block is expected to fit the period.  The IRs
+    of channel c are those of channel c mod 4096 of this rank (each channel still owns and streams its own copy)."""
+    import torch
+    from fft_convolution_b200 import _lib
+    period = B / SAMPLE_RATE
+    free_b, _ = torch.cuda.mem_get_info(local)
+    per_ch = 2 * ((L + B - 1) // B) * B * 8 + 64 * B
+    c_fit = int(0.90 * period * 1000.0 / ms_e2e_per_block_head * Cn_head) // 256 * 256
+    c_mem = int(0.85 * free_b / per_ch) // 256 * 256
+    sizes = [("1e5_over_8_gpus", 12500), ("largest_that_fits_the_period", max(256, min(c_fit, c_mem)))]
+    base = synth_irs(chan0, min(4096, max(s for _, s in sizes)), 0, L)
+    out = {}
+    for name, Cn in sizes:
+        if Cn * per_ch > 0.9 * free_b:
+            out[name] = {"channels_per_gpu": Cn, "skipped": "does not fit the free HBM"}
+            continue
+        conv = F.FFTConvolver.init(np.zeros((Cn, 1), np.float32), B, L, device=local)
+        eng = conv.engine
+        for c0 in range(0, Cn, base.shape[0]):  # K5 in slabs of 4096 channels (layer 1: any channel range)
+            n = min(base.shape[0], Cn - c0)
+            _lib.check(lib.fcb_engine_set_ir(eng, c0, n, base.ctypes.data_as(C.c_void_p), L, L, 0))
+        conv.sync()
+        nbytes = Cn * B * 4
+        p_in, p_out = lib.fcb_host_alloc(nbytes), lib.fcb_host_alloc(nbytes)
+        h_in = np.ctypeslib.as_array(C.cast(p_in, C.POINTER(C.c_float)), shape=(Cn, B))
+        h_out = np.ctypeslib.as_array(C.cast(p_out, C.POINTER(C.c_float)), shape=(Cn, B))
+        h_in[:] = np.tile(synth_noise(chan0, min(Cn, 1024), 0, B), ((Cn + 1023) // 1024, 1))[:Cn]
+        for _ in range(20):
+            conv.process(h_in, h_out)
+        barrier()
+        times = np.empty(blocks)
+        t_all = time.perf_counter()
+        for i in range(blocks):
+            t0 = time.perf_counter()
+            conv.process(h_in, h_out)
+            times[i] = time.perf_counter() - t0
+        t_all = time.perf_counter() - t_all
+        barrier()
+        stats = reduce_max([percentile_ms(times, 50), percentile_ms(times, 99), float(times.max() * 1000.0),
+                            float((times > period).sum()), t_all * 1000.0], device=f"cuda:{local}")
+        out[name] = {"channels_per_gpu": Cn, "channels_all_gpus": Cn * world, "blocks": blocks,
+                     "block_period_ms": period * 1000.0, "p50_ms": stats[0], "p99_ms": stats[1], "max_ms": stats[2],
+                     "missed_deadlines": int(stats[3]), "utilisation": stats[4] / 1000.0 / (blocks * period),
+                     "state_GB_per_gpu": Cn * per_ch / 1e9,
+                     "path": "fcb_fftconv_process, pinned host buffers, one synchronous call per block, back to back "
+                             "(max over ranks of every figure)"}
+        lib.fcb_host_free(p_in)
+        lib.fcb_host_free(p_out)
+        conv.close()
+    return out
+
+
+def run_mimo(local, rank, world, steps, warmup):
+    """BASELINE configs[4] under the driver's eyes (N > 1): 16 x 16 matrix, 10 s IRs, block 512, the IR partitions
+    sharded over the N GPUs; 1 stream (CUDA-core matrix kernel) and 128 streams (tcgen05 K4); partial spectra exchanged
+    by peer stores over NVLink and by an NCCL all-reduce; the first blocks are checked against the unsharded engine."""
+    import torch
+    import torch.distributed as dist
+    import fft_convolution_b200 as F
+    from fft_convolution_b200.distributed import ShardedMimoConvolver
+    N, B, L = 16, 512, 10 * SAMPLE_RATE
+    h = synth_irs(0, N * N, 0, L).reshape(N, N, L)
+    res = {"config": f"MIMO {N}x{N}, IR 10 s ({L} taps, S = {(L + B - 1) // B}), block {B}, IR partitions sharded over {world} GPUs"}
+    for NS in (1, 128):
+        x = [torch.from_numpy(synth_noise(0, NS * N, B * i, B)).cuda(local) for i in range(8)]
+        ref = None
+        if rank == 0:  # the unsharded engine, first blocks only
+            whole = F.MimoConvolver.init(h, B, L, n_streams=NS, device=local)
+            ref = []
+            o = torch.empty((NS * N, B), dtype=torch.float32, device=f"cuda:{local}")
+            for i in range(4):
+                whole.partial_dev(x[i].data_ptr(), B)
+                whole.finish_dev(o.data_ptr(), B)
+                whole.sync()
+                ref.append(o.cpu().numpy().copy())
+            whole.close()
+            del whole
+        for exchange in ("peer", "nccl"):
+            m = ShardedMimoConvolver(h, B, L, n_streams=NS, device=local, exchange=exchange)
+            out = torch.empty((NS * N, B), dtype=torch.float32, device=f"cuda:{local}")
+            err = 0.0
+            for i in range(4):
+                m.process_dev(x[i], out)
+                torch.cuda.synchronize()
+                if ref is not None:
+                    r = ref[i]
+                    err = max(err, float(np.max(np.abs(out.cpu().numpy() - r))) / max(float(np.sqrt(np.mean(r.astype(np.float64) ** 2))), 1e-9))
+            for i in range(warmup):
+                m.process_dev(x[i % 8], out)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(m.stream)
+            for i in range(steps):
+                m.process_dev(x[i % 8], out)
+            e1.record(m.stream)
+            torch.cuda.synchronize()
+            m.m.sync()  # surfaces a peer-exchange timeout
+            ms = reduce_max([e0.elapsed_time(e1) / steps], device=f"cuda:{local}")[0]
+            res[f"streams{NS}_{exchange}"] = {
+                "ms_per_block": ms, "realtime_factor": 1000.0 * B / SAMPLE_RATE / ms, "tensor_cores": bool(m.m.uses_tensor_cores),
+                "T_cmac_per_s": NS * N * N * ((L + B - 1) // B) * B / (ms / 1e3) / 1e12,
+                "max_abs_err_over_rms_vs_unsharded": err if rank == 0 else None}
+            m.m.close()
+            del m
+            dist.barrier()
+    return res
 
 
 # ---------------------------------------------------------------------------------------------
@@ -235,6 +399,7 @@ def run_b200(args) -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         # NCCL prints its version banner on stdout when the communicator comes up; stdout must carry
         # the ONE JSON line only, so route fd 1 to stderr until the first collective has run
@@ -331,6 +496,39 @@ def run_b200(args) -> None:
     launches = lib.fcb_launch_count() - launches0
     clocks = sampler.stop()
 
+    # ---- the same step over a window of at least a second (the driver's K may be 20 steps = 18 ms) ----
+    n_sus = max(args.steps, int(1200.0 / max(ms / args.steps, 1e-3)))
+    barrier()
+    ev0.record(stream)
+    for i in range(n_sus):
+        step_dev(i)
+    ev1.record(stream)
+    barrier()
+    sus_ms = reduce_max([ev0.elapsed_time(ev1)], device=f"cuda:{local}")[0]
+    sustained = {"steps": n_sus, "window_ms": sus_ms, "ms_per_step": sus_ms / n_sus,
+                 "value": aggregate_value(world, Cn, n_sus, B, sus_ms), "unit": UNIT}
+    launches += n_sus
+
+    # ---- strong scaling: BASELINE configs[3] read as 4096 channels in total, sharded over the N GPUs ----
+    strong = None
+    if world > 1 and Cn % world == 0:
+        Cs = Cn // world
+        conv_s = F.FFTConvolver.init(synth_irs(rank * Cs, Cs, 0, L), B, L, device=local, stream=stream.cuda_stream)
+        n_str = max(args.steps, 200)
+        for i in range(args.warmup):
+            conv_s.process_dev(d_in[i % NIN].data_ptr(), B, B, d_out.data_ptr(), B, B)
+        barrier()
+        ev0.record(stream)
+        for i in range(n_str):
+            conv_s.process_dev(d_in[i % NIN].data_ptr(), B, B, d_out.data_ptr(), B, B)
+        ev1.record(stream)
+        barrier()
+        st_ms = reduce_max([ev0.elapsed_time(ev1)], device=f"cuda:{local}")[0]
+        strong = {"channels_total": Cn, "channels_per_gpu": Cs, "steps": n_str, "ms_per_step": st_ms / n_str,
+                  "value": Cn * n_str * B / SAMPLE_RATE / (st_ms / 1000.0), "unit": UNIT, "scaling": "strong"}
+        launches += n_str + args.warmup
+        conv_s.close()
+
     # ---- end to end through the host-pointer API: pinned H2D + K1..K3 + D2H every step ---------
     nbytes = Cn * B * 4
     p_in, p_out = lib.fcb_host_alloc(nbytes), lib.fcb_host_alloc(nbytes)
@@ -376,7 +574,8 @@ def run_b200(args) -> None:
     if tp.exists():
         try:
             t = json.loads(tp.read_text())
-            if t.get("channels") == Cn:
+            # an ncu capture is only quoted for the kernels it was taken from (scripts/capture_traffic.sh stamps the hash)
+            if t.get("channels") == Cn and t.get("kernel_source_sha256_16") == kernel_source_hash():
                 traffic = t.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
@@ -385,6 +584,22 @@ def run_b200(args) -> None:
                 "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": k2_ms, "launches_timed": int(nl.value),
                 "kernel_share_of_step": tot_ms.value / ms if ms > 0 else None}
+
+    realtime = None
+    if args.realtime:
+        lib.fcb_host_free(p_in)
+        lib.fcb_host_free(p_out)
+        p_in = p_out = None
+        conv.close()
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        realtime = run_realtime(F, lib, local, rank, world, chan0, Cn, e2e_ms_max / args.steps, B, L, args.realtime_blocks, barrier)
+    mimo = None
+    if world > 1 and args.mimo:
+        if conv._h:
+            conv.close()
+        torch.cuda.empty_cache()
+        mimo = run_mimo(local, rank, world, 200, 20)
 
     if rank == 0:
         cpu_baseline = None
@@ -403,8 +618,9 @@ def run_b200(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, {"segments": S, "mac_impl": args.mac_impl, "mac_stages": args.mac_stages, "fused_block": bool(fused),
-                                         "ir_gen_s": round(t_gen, 1)}),
+            "config": config_dict(args),
+            "tuning": {"segments": S, "mac_impl": args.mac_impl, "mac_stages": args.mac_stages, "fused_block": bool(fused),
+                       "ir_gen_s": round(t_gen, 1), "numa": numa},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "ms_per_step": e2e_ms_max / args.steps,
@@ -416,11 +632,15 @@ def run_b200(args) -> None:
             "parity": {"max_abs_err_over_rms_vs_f64": worst, "tolerance": 1e-5},
             "realtime_headroom": {"block_period_ms": 1000.0 * B / SAMPLE_RATE,
                                   "block_time_ms": ms_max / args.steps},
+            "sustained": sustained, "strong": strong, "realtime": realtime, "mimo": mimo,
+            "scaling_note": "headline = weak (4096 channels PER GPU); `strong` = 4096 channels in total over the N GPUs",
         }
         print(json.dumps(line), flush=True)
-    lib.fcb_host_free(p_in)
-    lib.fcb_host_free(p_out)
-    conv.close()
+    if p_in:
+        lib.fcb_host_free(p_in)
+        lib.fcb_host_free(p_out)
+    if conv._h:
+        conv.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -442,6 +662,9 @@ def main():
     ap.add_argument("--tma-io", type=int, default=None)
     ap.add_argument("--fused", type=int, default=1, help="1: one fused K1+K2+K3 kernel per block (default), 0: three launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--realtime", type=int, default=1, help="1: also run the measured real-time block (12 500 channels and the largest fitting count)")
+    ap.add_argument("--realtime-blocks", type=int, default=1000)
+    ap.add_argument("--mimo", type=int, default=1, help="1: with N > 1 also run BASELINE configs[4] sharded over the N GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
     args.steps = max(args.steps, 1)
