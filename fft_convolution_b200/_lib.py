@@ -93,6 +93,7 @@ SIGNATURES = {
     "fcb_engine_process_block_host": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz, _sz]),
     "fcb_engine_pair_ok": (_i, [_vp, _vp, _sz]),
     "fcb_engine_process_block_pair_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, C.POINTER(Epilogue), _vp, _sz, C.POINTER(Epilogue), _sz, _sz]),
+    "fcb_engine_process_block_pair_copy_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, C.POINTER(Epilogue), _vp, _sz, C.POINTER(Epilogue), _sz, _sz, _vp, _sz]),
     "fcb_engine_multi_block_ok": (_i, [_vp, _sz, _sz]),
     "fcb_engine_multi_block_capacity": (_sz, [_vp]),
     "fcb_engine_multi_block_reserved": (_sz, [_vp]),

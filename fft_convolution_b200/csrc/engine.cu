@@ -74,6 +74,10 @@ struct fcb_engine {
     const float2 *tw = nullptr;
     // background IR update (fcb_engine_update_reserve): K5 writes `ir_shadow` on `upd_stream` while the blocks keep
     // reading `ir`; fcb_engine_update_commit swaps the two pointers
+    // small batches: partial sums and arrival counters of the split whole-block kernels (fused_kernel.cuh SplitArgs)
+    float4 *zpart = nullptr;
+    unsigned int *zcount = nullptr;
+    size_t zslices = 0; // capacity of zpart in (group, slice) entries of 2 x 256 float4
     float2 *ir_shadow = nullptr;
     cudaStream_t upd_stream = nullptr;
     cudaEvent_t upd_done = nullptr, upd_fence = nullptr;
@@ -227,6 +231,7 @@ static std::atomic<bool> g_tma_io{true};       // fused kernel moves its input/o
 static std::atomic<bool> g_shared_reuse{true}; // shared-IR engines: stage each IR tile once per CTA
 namespace fcb { std::atomic<bool> g_mimo_tile{true}; } // matrix K2 with in-CTA reuse (0: per-channel K2)
 namespace fcb { std::atomic<int> g_mimo_tc{2}; }
+static std::atomic<bool> g_split{true};        // small batches: cut the delay line of a whole block over several CTAs
 static std::atomic<bool> g_multi_block{true}; // calls spanning >= 2 whole blocks run as one time-batched pass       // K4 tensor-core matrix MAC: 0 never, 1 when the shape fits, 2 + NS >= 16
 
 template <int B, int NST>
@@ -284,6 +289,31 @@ static int launch_mac_t(const MacArgs &a, cudaStream_t st)
 template <int LOGB>
 static int launch_block_fused_shared(const fcb_engine *e, cudaStream_t st, FusedArgs fa, size_t nc);
 
+// Small batches (fewer channel groups than the machine has CTA slots): how many CTAs share one delay line.
+// Aim at ~3 CTAs per SM over the whole grid, at least two pipeline stages of `rows` segments per CTA; slices are whole
+// stages.  Returns zsplit = 1 when the split does not apply.
+static constexpr size_t kSplitTargetCtas = 3 * 148;
+static SplitArgs split_plan(const fcb_engine *e, size_t groups, int seg_lo, int seg_hi, int rows)
+{
+    SplitArgs sp{};
+    sp.zsplit = 1;
+    const int nseg = seg_hi - seg_lo;
+    if (!g_split.load() || !e->zpart || groups == 0 || groups * 2 > kSplitTargetCtas || nseg < 4 * rows) return sp;
+    size_t z = (kSplitTargetCtas + groups - 1) / groups;
+    const size_t zmax = (size_t)nseg / (2 * (size_t)rows);
+    if (z > zmax) z = zmax;
+    if (z < 2) return sp;
+    int zlen = (int)((nseg + z - 1) / z);
+    zlen = (zlen + rows - 1) / rows * rows;
+    z = (size_t)(nseg + zlen - 1) / zlen;
+    if (z < 2 || groups * z > e->zslices) return sp;
+    sp.zsplit = (int)z;
+    sp.zlen = zlen;
+    sp.part = e->zpart;
+    sp.count = e->zcount;
+    return sp;
+}
+
 // block I/O eligible for one bulk copy per channel: 16-byte aligned rows
 static bool tma_io_ok(const float *in, size_t in_stride, const float *out, size_t out_stride, size_t B)
 {
@@ -321,12 +351,15 @@ static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, s
         if (fa.ifft.epi.add1) fa.ifft.epi.add1 += c0 * epi->add_stride;
         if (fa.ifft.epi.mix_other) fa.ifft.epi.mix_other += c0 * epi->mix_stride;
     }
-    if (e->shared_ir && g_shared_reuse.load() && ROWS == 4) {
+    const size_t groups = (nc + Cfg::CPB - 1) / Cfg::CPB;
+    fa.split.zsplit = 1;
+    if (c0 == 0 && nc == e->C) fa.split = split_plan(e, groups, fa.mac.seg_lo, fa.mac.seg_hi, ROWS);
+    if (e->shared_ir && g_shared_reuse.load() && ROWS == 4 && fa.split.zsplit == 1) {
         if constexpr (LOGB >= 7) return launch_block_fused_shared<LOGB>(e, st, fa, nc);
     }
     cudaEvent_t prof_stop = nullptr;
     const bool profiled = prof_before(st, &prof_stop) != nullptr;
-    const unsigned grid = (unsigned)((nc + Cfg::CPB - 1) / Cfg::CPB);
+    const unsigned grid = (unsigned)(groups * (size_t)fa.split.zsplit);
     if (g_tma_io.load() && tma_io_ok(fa.in, in_stride, fa.ifft.out, out_stride, e->B)) {
         static SmemOptIn optin_io;
         FCB_TRY(optin_io.ensure(k_block_fused<LOGB, NST, ROWS, true>, Cfg::smem_bytes(NST, true)));
@@ -363,14 +396,16 @@ static std::atomic<bool> g_fused_pair{true};
 static int check_sched(const fcb_engine *e, size_t current, size_t active, const char *who);
 
 template <int LOGB, int ROWS>
-static int launch_block_fused_pair(const fcb_engine *ea, const fcb_engine *eb, const FusedPairArgs &fa)
+static int launch_block_fused_pair(const fcb_engine *ea, const fcb_engine *eb, FusedPairArgs fa)
 {
     using Cfg = FusedPairCfg<LOGB, ROWS>;
     static SmemOptIn optin;
     FCB_TRY(optin.ensure(k_block_fused_pair<LOGB, ROWS>, Cfg::SMEM_BYTES));
+    const size_t groups = (ea->C + Cfg::CPB - 1) / Cfg::CPB;
+    fa.split = split_plan(ea, groups, fa.mac.seg_lo, fa.mac.seg_hi, ROWS);
     cudaEvent_t prof_stop = nullptr;
     const bool profiled = prof_before(ea->stream, &prof_stop) != nullptr;
-    const unsigned grid = (unsigned)((ea->C + Cfg::CPB - 1) / Cfg::CPB);
+    const unsigned grid = (unsigned)(groups * (size_t)fa.split.zsplit);
     k_block_fused_pair<LOGB, ROWS><<<grid, 256, Cfg::SMEM_BYTES, ea->stream>>>(fa, ea->tw);
     if (profiled) cudaEventRecord(prof_stop, ea->stream);
     g_launches++;
@@ -389,6 +424,17 @@ extern "C" int fcb_engine_pair_ok(const fcb_engine *ea, const fcb_engine *eb, si
 extern "C" int fcb_engine_process_block_pair_dev(fcb_engine *ea, fcb_engine *eb, const float *in_dev, size_t in_stride,
                                                  float *out_a, size_t stride_a, const fcb_epilogue *epi_a, float *out_b,
                                                  size_t stride_b, const fcb_epilogue *epi_b, size_t current, size_t active)
+{
+    return fcb_engine_process_block_pair_copy_dev(ea, eb, in_dev, in_stride, out_a, stride_a, epi_a, out_b, stride_b, epi_b,
+                                                  current, active, nullptr, 0);
+}
+
+// the same, and the input block is also stored to copy_to (channel stride copy_stride, rows 8-byte aligned): TwoStage's
+// append to tail_input (src/fft_convolver.rs:459-461) rides on the launch instead of costing a copy of its own
+extern "C" int fcb_engine_process_block_pair_copy_dev(fcb_engine *ea, fcb_engine *eb, const float *in_dev, size_t in_stride,
+                                                      float *out_a, size_t stride_a, const fcb_epilogue *epi_a, float *out_b,
+                                                      size_t stride_b, const fcb_epilogue *epi_b, size_t current,
+                                                      size_t active, float *copy_to, size_t copy_stride)
 {
     FCB_TRY(check_sched(ea, current, active, "process_block_pair"));
     if (!fcb_engine_pair_ok(ea, eb, active)) return fail(FCB_ERR_UNSUPPORTED, "process_block_pair: engines do not pair");
@@ -418,6 +464,9 @@ extern "C" int fcb_engine_process_block_pair_dev(fcb_engine *ea, fcb_engine *eb,
     fa.ifft_b.out = out_b;
     fa.ifft_b.out_stride = (long long)stride_b;
     if (epi_b) fa.ifft_b.epi = *epi_b;
+    if (copy_to && ((uintptr_t)copy_to % 8 || copy_stride % 2)) return fail(FCB_ERR_ARG, "process_block_pair: copy_to rows must be 8-byte aligned");
+    fa.copy_in = copy_to;
+    fa.copy_stride = (long long)copy_stride;
     (void)B;
     const bool short_line = active <= (size_t)g_fused_short.load();
 #define FCB_PAIR_CASE(LB)                                                        \
@@ -587,6 +636,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "fused_stages") && (value == 2 || value == 3)) g_fused_stages = value;
     else if (!strcmp(key, "fused_short") && value >= 0) g_fused_short = value;
     else if (!strcmp(key, "fused_pair")) g_fused_pair = value != 0;
+    else if (!strcmp(key, "split")) g_split = value != 0;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
     else if (!strcmp(key, "tma_io")) g_tma_io = value != 0;
     else if (!strcmp(key, "mapped_io")) fcb_host_mirror_set_mapped_io(value);
@@ -664,6 +714,14 @@ static int engine_prepare_process(fcb_engine *e)
     size_t nb = budget / per_block;
     if (nb > mb_limit(e)) nb = mb_limit(e);
     if (nb >= 2 && e->logb >= 2) FCB_TRY(mb_ensure(e, nb));
+    if (e->logb >= 5 && e->logb <= 9) { // whole-block kernels: split buffers for small batches
+        const size_t groups = (e->C + (512 >> e->logb) - 1) / (512 >> e->logb);
+        if (groups * 2 <= kSplitTargetCtas) {
+            e->zslices = kSplitTargetCtas + groups;
+            FCB_TRY(alloc_zero((void **)&e->zpart, e->zslices * 2 * 256 * sizeof(float4), e->stream));
+            FCB_TRY(alloc_zero((void **)&e->zcount, groups * sizeof(unsigned int), e->stream));
+        }
+    }
     if (e->C >= 1024) {
         FCB_TRY(pipe_streams_ensure(e));
         const size_t G = (size_t)g_pipe_group.load();
@@ -730,6 +788,8 @@ extern "C" void fcb_engine_destroy(fcb_engine *e)
     if (e->upd_done) cudaEventDestroy(e->upd_done);
     if (e->upd_fence) cudaEventDestroy(e->upd_fence);
     cudaFree(e->ir_shadow);
+    cudaFree(e->zpart);
+    cudaFree(e->zcount);
     cudaFree(e->ir);
     cudaFree(e->ring);
     cudaFree(e->premul);

@@ -15,12 +15,63 @@
 
 namespace fcb {
 
+// Small batches: with fewer channel groups than SMs one CTA per group would stream a whole delay line by itself
+// (770 KB for a 2 s response) while most of the machine idles.  `split` cuts the segment range into zsplit slices of
+// zlen segments, one CTA each (grid = groups * zsplit).  Slice 0 also runs K1 and writes ring[current]; every CTA
+// publishes its partial pre_multiplied (one float4 per thread) and the LAST one to arrive (one atomic per CTA) adds the
+// zsplit partials in slice order — deterministic — and runs K3.  zsplit == 1 is the unsplit kernel, bit for bit.
+struct SplitArgs {
+    int zsplit, zlen;        // slices per channel group, segments per slice (a multiple of the stage rows)
+    float4 *part;            // [groups][zsplit][arrays][256] partial sums
+    unsigned int *count;     // [groups] arrival counters, zero between launches
+};
+
 struct FusedArgs {
     const float *in;      // [C][B] new block, channel stride in_stride
     long long in_stride;
     MacArgs mac;          // ir / ring / strides / current / active / nchan (premul unused)
     IfftArgs ifft;        // overlap / out / out_stride / epilogue (fill = 0, n = B, complete)
+    SplitArgs split;
 };
+
+// publish this CTA's partial accumulator(s); returns true in the one CTA of the group that arrives last
+template <int NACC>
+__device__ __forceinline__ bool split_arrive(const SplitArgs &sp, long long group, int z, const float4 (&acc)[NACC])
+{
+    __shared__ int s_last;
+    float4 *mine = sp.part + ((size_t)(group * sp.zsplit + z) * NACC) * 256;
+#pragma unroll
+    for (int n = 0; n < NACC; n++) mine[n * 256 + threadIdx.x] = acc[n];
+    __threadfence(); // partials (and slice 0's ring row) before the arrival
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(sp.count + group, 1u);
+        s_last = prev == (unsigned int)(sp.zsplit - 1);
+        if (s_last) sp.count[group] = 0; // ready for the next launch
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// sum of the zsplit partials in slice order (every CTA of the group has arrived)
+template <int NACC>
+__device__ __forceinline__ void split_gather(const SplitArgs &sp, long long group, float4 (&acc)[NACC])
+{
+    const float4 *base = sp.part + (size_t)group * sp.zsplit * NACC * 256;
+#pragma unroll
+    for (int n = 0; n < NACC; n++) acc[n] = __ldcg(base + n * 256 + threadIdx.x);
+    for (int z = 1; z < sp.zsplit; z++) {
+#pragma unroll
+        for (int n = 0; n < NACC; n++) {
+            const float4 p = __ldcg(base + ((size_t)z * NACC + n) * 256 + threadIdx.x);
+            acc[n].x = __fadd_rn(acc[n].x, p.x);
+            acc[n].y = __fadd_rn(acc[n].y, p.y);
+            acc[n].z = __fadd_rn(acc[n].z, p.z);
+            acc[n].w = __fadd_rn(acc[n].w, p.w);
+        }
+    }
+}
 
 template <int LOGB, int ROWS = 4>
 struct FusedCfg {
@@ -74,10 +125,16 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;                 // MAC role
     const int fslot = tid / T, flane = tid % T;             // FFT role (threads 0 .. CPB*T-1)
-    const bool fwork = tid < CPB * T;
-    const long long c0 = (long long)blockIdx.x * CPB;
+    const int Z = fa.split.zsplit > 1 ? fa.split.zsplit : 1;
+    const long long group = Z > 1 ? blockIdx.x / Z : blockIdx.x;
+    const int zs = Z > 1 ? (int)(blockIdx.x % Z) : 0;
+    const bool k1 = zs == 0;                                // this CTA transforms the new block
+    const bool fwork = tid < CPB * T && k1;
+    const long long c0 = group * CPB;
     const int nlive = (int)((a.nchan - c0) < CPB ? (a.nchan - c0) : CPB);
-    const int cur = a.current, act = a.active, lo = a.seg_lo, hi = a.seg_hi;
+    const int cur = a.current, act = a.active;
+    const int lo = Z > 1 ? a.seg_lo + zs * fa.split.zlen : a.seg_lo;
+    const int hi = Z > 1 ? (lo + fa.split.zlen < a.seg_hi ? lo + fa.split.zlen : a.seg_hi) : a.seg_hi;
     const int niter = hi > lo ? (hi - lo + R - 1) / R : 0;
 
     if (tid == 0) {
@@ -86,7 +143,7 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (TMA_IO && tid == 0) { // the new block of every live channel: one bulk copy each (host or device memory)
+    if (TMA_IO && tid == 0 && k1) { // the new block of every live channel: one bulk copy each (host or device memory)
         mbar_expect_tx(in_bar, (uint32_t)(nlive * B * sizeof(float)));
         for (int ch = 0; ch < nlive; ch++)
             bulk_g2s(in_s + ch * B, fa.in + (c0 + ch) * fa.in_stride, B * sizeof(float), in_bar);
@@ -120,8 +177,8 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
 
     // ---- K1: forward real FFT of the new block (src/fft_convolver.rs:234-241) -------------------
     float2 *fs = fbuf + (fwork ? fslot : 0) * Cfg::FFT_PER;
-    const bool flive = fwork && fslot < nlive;
-    if (TMA_IO) mbar_wait(in_bar, 0);
+    bool flive = fwork && fslot < nlive;
+    if (TMA_IO && k1) mbar_wait(in_bar, 0);
     if (fwork) {
         const float *x = TMA_IO ? in_s + fslot * B : fa.in + (c0 + fslot) * fa.in_stride;
         if (TMA_IO) {
@@ -194,10 +251,25 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
         if (tid == 0 && it + NST < niter) issue(it + NST);
     }
 
+    // ---- small batches: the delay line was cut over Z CTAs; the last one to arrive finishes the block ----
+    bool fwork3 = fwork;
+    if (Z > 1) {
+        float4 part[1] = {acc};
+        if (!split_arrive<1>(fa.split, group, zs, part)) return;
+        split_gather<1>(fa.split, group, part);
+        acc = part[0];
+        fwork3 = tid < CPB * T;
+        flive = fwork3 && fslot < nlive;
+        fs = fbuf + (fwork3 ? fslot : 0) * Cfg::FFT_PER;
+    }
+
     // ---- K3: conv = pre_multiplied + X[current] * H[0] (:256-261), inverse FFT, overlap-add ------
     float4 conv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (mlive) {
-        const float4 x = reinterpret_cast<const float4 *>(fbuf + ty * Cfg::FFT_PER)[tx];
+        // X[current]: this CTA's own transform, or (split, another CTA did K1) the ring row slice 0 wrote before it arrived
+        const float4 x = Z > 1 && !k1
+                             ? __ldcg(reinterpret_cast<const float4 *>(a.ring + a.ring_chan(c0 + ty) * a.ring_stride + (long long)cur * B) + tx)
+                             : reinterpret_cast<const float4 *>(fbuf + ty * Cfg::FFT_PER)[tx];
         conv = acc;
         // the reference multiplies segments[current] (a) by segments_ir[0] (b): im = a.re*b.im + a.im*b.re
         cmac_ref(conv.x, conv.y, x.x, x.y, h0.x, h0.y, packed);
@@ -214,9 +286,9 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
         d[sidx(2 * tx + 1)] = make_float2(0.f, 0.f);
     }
     __syncthreads();
-    if (fwork) irfft_presplit<LOGB>(fs, flane, tw);
+    if (fwork3) irfft_presplit<LOGB>(fs, flane, tw);
     __syncthreads();
-    stockham_all<LOGB, +1, 0, 1>(fs, flane, tw, fwork);
+    stockham_all<LOGB, +1, 0, 1>(fs, flane, tw, fwork3);
 
     const IfftArgs &o = fa.ifft;
     const float inv_n = 1.0f / (float)(2 * B);
@@ -277,6 +349,9 @@ struct FusedPairArgs {
     long long ir_b_stride;
     float2 *ring_b;         // convolver B's ring (same geometry as A's): receives the new spectrum as well
     IfftArgs ifft_a, ifft_b; // overlap / out / out_stride / epilogue of each
+    SplitArgs split;        // small batches: the delay line cut over zsplit CTAs (see FusedArgs)
+    float *copy_in;         // optional: the input block is also stored here (TwoStage's tail_input, :459-461), stride copy_stride
+    long long copy_stride;
 };
 
 template <int LOGB, int ROWS>
@@ -336,10 +411,16 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
     const int tx = tid % TX, ty = tid / TX;
     const int which = tid / FT;                              // FFT role: 0 = convolver A, 1 = B (threads 0 .. 2*FT-1)
     const int fslot = (tid % FT) / T, flane = tid % T;
-    const bool fwork1 = tid < FT, fwork2 = tid < 2 * FT;
-    const long long c0 = (long long)blockIdx.x * CPB;
+    const int Z = fa.split.zsplit > 1 ? fa.split.zsplit : 1;
+    const long long group = Z > 1 ? blockIdx.x / Z : blockIdx.x;
+    const int zs = Z > 1 ? (int)(blockIdx.x % Z) : 0;
+    const bool k1 = zs == 0;
+    const bool fwork1 = tid < FT && k1, fwork2 = tid < 2 * FT;
+    const long long c0 = group * CPB;
     const int nlive = (int)((a.nchan - c0) < CPB ? (a.nchan - c0) : CPB);
-    const int cur = a.current, act = a.active, lo = a.seg_lo, hi = a.seg_hi;
+    const int cur = a.current, act = a.active;
+    const int lo = Z > 1 ? a.seg_lo + zs * fa.split.zlen : a.seg_lo;
+    const int hi = Z > 1 ? (lo + fa.split.zlen < a.seg_hi ? lo + fa.split.zlen : a.seg_hi) : a.seg_hi;
     const int niter = hi > lo ? (hi - lo + R - 1) / R : 0;
 
     if (tid == 0) {
@@ -382,6 +463,11 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
     const bool flive1 = fwork1 && fslot < nlive;
     if (fwork1) load_block_as_complex<LOGB>(fs, flane, fa.in + (c0 + fslot) * fa.in_stride, flive1 ? B : 0);
     __syncthreads();
+    if (fa.copy_in && flive1) { // the block as it was fed, for the caller's own buffer (z[j] = x[2j] + i x[2j+1])
+        float2 *dst = reinterpret_cast<float2 *>(fa.copy_in + (c0 + fslot) * fa.copy_stride);
+#pragma unroll
+        for (int e = 0; e < E; e++) dst[flane + e * T] = fs[sidx(flane + e * T)];
+    }
     stockham_all<LOGB, -1, 0, 1>(fs, flane, tw, fwork1);
     float2 xk[E];
     if (fwork1) {
@@ -427,10 +513,19 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
         if (tid == 0 && it + NST < niter) issue(it + NST);
     }
 
+    if (Z > 1) { // small batches: the last CTA of the group to arrive adds the partials in slice order and finishes
+        float4 part[2] = {acc_a, acc_b};
+        if (!split_arrive<2>(fa.split, group, zs, part)) return;
+        split_gather<2>(fa.split, group, part);
+        acc_a = part[0];
+        acc_b = part[1];
+    }
+
     // ---- K3 twice, side by side: conv = pre_multiplied + X[current] * H[0] (:256-261), inverse FFT ------
     float4 conv_a = make_float4(0.f, 0.f, 0.f, 0.f), conv_b = conv_a;
     if (mlive) {
-        const float4 x = reinterpret_cast<const float4 *>(fbuf + ty * Cfg::FFT_PER)[tx];
+        const float4 x = Z > 1 && !k1 ? __ldcg(reinterpret_cast<const float4 *>(a.ring + (c0 + ty) * a.ring_stride + (long long)cur * B) + tx)
+                                      : reinterpret_cast<const float4 *>(fbuf + ty * Cfg::FFT_PER)[tx];
         conv_a = acc_a;
         cmac_ref(conv_a.x, conv_a.y, x.x, x.y, h0a.x, h0a.y, packed);
         cmac_ref(conv_a.z, conv_a.w, x.z, x.w, h0a.z, h0a.w, false);

@@ -458,10 +458,10 @@ static bool fftconv_pair_ok(const fcb_fftconv *a, const fcb_fftconv *b, size_t n
 }
 static int fftconv_process_pair_dev(fcb_fftconv *a, fcb_fftconv *b, const float *in, size_t in_stride, float *out_a,
                                     size_t stride_a, const fcb_epilogue *epi_a, float *out_b, size_t stride_b,
-                                    const fcb_epilogue *epi_b)
+                                    const fcb_epilogue *epi_b, float *copy_to = nullptr, size_t copy_stride = 0)
 {
-    FCB_TRY(fcb_engine_process_block_pair_dev(a->eng, b->eng, in, in_stride, out_a, stride_a, epi_a, out_b, stride_b, epi_b,
-                                              a->current, a->active_seg_count));
+    FCB_TRY(fcb_engine_process_block_pair_copy_dev(a->eng, b->eng, in, in_stride, out_a, stride_a, epi_a, out_b, stride_b, epi_b,
+                                                   a->current, a->active_seg_count, copy_to, copy_stride));
     a->current = a->current > 0 ? a->current - 1 : a->active_seg_count - 1; // :287-291
     b->current = a->current;
     return FCB_OK;
@@ -522,6 +522,9 @@ struct fcb_twostage {
     cudaEvent_t ev_in = nullptr, ev_tail_done = nullptr;
     bool tail_pending = false;
     float *d_in = nullptr, *d_out = nullptr; // host-call staging [C][head_block_size]
+    // small batches: the staging is pinned host memory mapped into the device address space (h_* host views, m_* the
+    // device aliases) — a host call is CPU copy in, the launches, one sync, CPU copy out; no copy-engine round trips
+    float *h_in = nullptr, *h_out = nullptr, *m_in = nullptr, *m_out = nullptr;
 };
 
 extern "C" void fcb_twostage_free(fcb_twostage *c)
@@ -541,6 +544,8 @@ extern "C" void fcb_twostage_free(fcb_twostage *c)
     cudaFree(c->tail_input[1]);
     cudaFree(c->d_in);
     cudaFree(c->d_out);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->ev_tail_done) cudaEventDestroy(c->ev_tail_done);
     if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
@@ -560,6 +565,15 @@ static int twostage_alloc(fcb_twostage *c)
     const size_t io = c->C * (c->head_block_size ? c->head_block_size : 1) * sizeof(float);
     FCB_CUDA(cudaMalloc(&c->d_in, io));
     FCB_CUDA(cudaMalloc(&c->d_out, io));
+    if (io <= ((size_t)256 << 10)) { // small batches only
+        if (cudaHostAlloc(&c->h_in, io, cudaHostAllocMapped) != cudaSuccess || cudaHostAlloc(&c->h_out, io, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&c->m_in, c->h_in, 0) != cudaSuccess || cudaHostGetDevicePointer(&c->m_out, c->h_out, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (c->h_in) cudaFreeHost(c->h_in);
+            if (c->h_out) cudaFreeHost(c->h_out);
+            c->h_in = c->h_out = c->m_in = c->m_out = nullptr;
+        }
+    }
     FCB_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
     FCB_CUDA(cudaEventCreateWithFlags(&c->ev_tail_done, cudaEventDisableTiming));
     return FCB_OK;
@@ -789,9 +803,12 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
     // head and tail_convolver0 see the same head blocks (:417 and :464-473): when this call is one whole head block
     // both run in one paired launch, tail0 writing where :464-473 would have put its block
     const bool paired = fuse && in_len == H && c->tail_input_fill % H == 0 && fftconv_pair_ok(c->head, c->tail0, in_len);
+    // ... and the append of the input block to tail_input (:459-461) rides on the same launch
+    const bool copy_fused = paired && T % 2 == 0 && c->tail_input_fill % 2 == 0;
     if (paired)
         FCB_TRY(fftconv_process_pair_dev(c->head, c->tail0, in, in_stride, out, out_stride, &epi,
-                                         c->tail_output0 + c->tail_input_fill, T, nullptr));
+                                         c->tail_output0 + c->tail_input_fill, T, nullptr,
+                                         copy_fused ? c->tail_input[c->tail_in_sel] + c->tail_input_fill : nullptr, T));
     else
         FCB_TRY(fcb_fftconv_process_dev(c->head, in, in_len, in_stride, out, out_len, out_stride, fuse ? &epi : nullptr)); // :417
     if (T == 0) return FCB_OK; // :420-422
@@ -813,8 +830,9 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
         if (c->tail_input_fill + n > T) // slice index panic at :459
             return fail(FCB_ERR_PANIC, "range end index %zu out of range for slice of length %zu", c->tail_input_fill + n, T);
         float *tin = c->tail_input[c->tail_in_sel];
-        FCB_CUDA(cudaMemcpy2DAsync(tin + c->tail_input_fill, T * sizeof(float), in + processed, in_stride * sizeof(float),
-                                   n * sizeof(float), C, cudaMemcpyDeviceToDevice, c->stream)); // :459-461
+        if (!copy_fused)
+            FCB_CUDA(cudaMemcpy2DAsync(tin + c->tail_input_fill, T * sizeof(float), in + processed, in_stride * sizeof(float),
+                                       n * sizeof(float), C, cudaMemcpyDefault, c->stream)); // :459-461
         c->tail_input_fill += n;
 
         if (c->tail_input_fill % H == 0) { // :464-476
@@ -856,6 +874,14 @@ extern "C" int fcb_twostage_process(fcb_twostage *c, const float *in, size_t in_
     if (in_len != out_len) return fail(FCB_ERR_PANIC, "index out of bounds: input and output lengths differ");
     if (in_len == 0) return FCB_OK;
     FCB_CUDA(cudaSetDevice(c->opt.device));
+    if (c->m_in && g_mapped_io) { // small batch: the kernels read and write mapped pinned staging themselves
+        const size_t H = c->head_block_size;
+        for (size_t ch = 0; ch < c->C; ch++) memcpy(c->h_in + ch * H, in + ch * in_stride, in_len * sizeof(float));
+        FCB_TRY(fcb_twostage_process_dev(c, c->m_in, in_len, H, c->m_out, out_len, H));
+        FCB_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t ch = 0; ch < c->C; ch++) memcpy(out + ch * out_stride, c->h_out + ch * H, out_len * sizeof(float));
+        return FCB_OK;
+    }
     FCB_CUDA(cudaMemcpy2DAsync(c->d_in, in_len * sizeof(float), in, in_stride * sizeof(float), in_len * sizeof(float),
                                c->C, cudaMemcpyHostToDevice, c->stream));
     FCB_TRY(fcb_twostage_process_dev(c, c->d_in, in_len, in_len, c->d_out, out_len, out_len));
@@ -954,6 +980,7 @@ struct fcb_crossfade {
     float2 *h_gains = nullptr, *d_gains = nullptr;  // pinned / device, max_buffer_size each
     cudaEvent_t ev_gains = nullptr;
     float *d_in = nullptr, *d_out = nullptr;        // host-call staging, [C][max_buffer_size] each (allocated in new())
+    float *h_in = nullptr, *h_out = nullptr, *m_in = nullptr, *m_out = nullptr; // small batches: mapped pinned staging
     size_t max_response_length = 0;                 // as given to new() (= stored_len)
     size_t crossfade_samples = 0;
     // update() while a fade runs (:58-63) also starts K5 of the stored response into the shadow buffer of the
@@ -978,6 +1005,8 @@ extern "C" void fcb_crossfade_free(fcb_crossfade *c)
     cudaFree(c->d_gains);
     cudaFree(c->d_in);
     cudaFree(c->d_out);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
     if (c->h_gains) cudaFreeHost(c->h_gains);
     if (c->ev_gains) cudaEventDestroy(c->ev_gains);
     fcb_fftconv_free(c->a); // b owns the shared stream when it is private, so free it last
@@ -1022,6 +1051,16 @@ extern "C" int fcb_crossfade_new(fcb_crossfade **out, fcb_fftconv *convolver, si
     cu(cudaHostAlloc(&c->h_gains, n * sizeof(float2), cudaHostAllocDefault));
     cu(cudaMalloc(&c->d_out, c->C * n * sizeof(float)));
     cu(cudaMalloc(&c->d_in, c->C * n * sizeof(float)));
+    if (rc == FCB_OK && c->C * n * sizeof(float) <= ((size_t)1 << 20)) { // small batches: mapped pinned staging
+        const size_t io = c->C * n * sizeof(float);
+        if (cudaHostAlloc(&c->h_in, io, cudaHostAllocMapped) != cudaSuccess || cudaHostAlloc(&c->h_out, io, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&c->m_in, c->h_in, 0) != cudaSuccess || cudaHostGetDevicePointer(&c->m_out, c->h_out, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (c->h_in) cudaFreeHost(c->h_in);
+            if (c->h_out) cudaFreeHost(c->h_out);
+            c->h_in = c->h_out = c->m_in = c->m_out = nullptr;
+        }
+    }
     cu(cudaEventCreateWithFlags(&c->ev_gains, cudaEventDisableTiming));
     // live response changes are what this type is for: both convolvers get a shadow copy of their spectra so that
     // update() never makes a block wait for K5 (fcb_engine_update_*)
@@ -1239,6 +1278,13 @@ extern "C" int fcb_crossfade_process(fcb_crossfade *c, const float *in, size_t i
     // both convolvers consume input[..max_buffer_size] (:72-73): a longer input is never read past that, a shorter
     // one panics inside FFTConvolver::process — either way at most M samples are staged (buffer made in new())
     const size_t n_in = in_len < M ? in_len : M;
+    if (c->m_in && g_mapped_io && M) { // small batch: the kernels read and write mapped pinned staging themselves
+        for (size_t ch = 0; ch < c->C; ch++) memcpy(c->h_in + ch * M, in + ch * in_stride, n_in * sizeof(float));
+        FCB_TRY(fcb_crossfade_process_dev(c, c->m_in, n_in, M, c->m_out, out_len, M));
+        FCB_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t ch = 0; ch < c->C; ch++) memcpy(out + ch * out_stride, c->h_out + ch * M, out_len * sizeof(float));
+        return FCB_OK;
+    }
     if (n_in)
         FCB_CUDA(cudaMemcpy2DAsync(c->d_in, (M ? M : 1) * sizeof(float), in, in_stride * sizeof(float), n_in * sizeof(float),
                                    c->C, cudaMemcpyHostToDevice, c->stream));

@@ -64,7 +64,9 @@ uint64_t fcb_debug_alloc_count(void);
  * one fused K1+K2+K3 kernel, 0 = three launches; outputs are bit-identical), "fused_stages" (2 or 3), "fused_pair" (1 = convolvers fed the same input share one launch), "fused_short" (delay lines of up to this many segments run
  * the fused kernel with 2-row stages so that a fourth CTA per SM hides the FFT latency; default 40, 0 = off), "mapped_io" (1 = small-batch host
  * calls go through mapped pinned memory instead of the copy engines), "zero_copy" (1 = when the caller's
- * buffers are pinned, large-batch whole-block calls let the kernel read/write them over PCIe directly), "strict_todo"
+ * buffers are pinned, large-batch whole-block calls let the kernel read/write them over PCIe directly), "split" (1 = small
+ * batches cut each delay line of a whole-block launch over several CTAs, partial sums added in slice order by the last
+ * CTA to arrive: deterministic, within tolerance, not bit-equal to the unsplit order; 0 = never), "strict_todo"
  * (1 = fcb_twostage_update and fcb_crossfade_reset answer FCB_ERR_TODO like the reference's todo!(); default 0 = the
  * extensions documented at those entry points) */
 int fcb_tune(const char *key, int value);
@@ -193,6 +195,12 @@ int fcb_engine_pair_ok(const fcb_engine *ea, const fcb_engine *eb, size_t active
 int fcb_engine_process_block_pair_dev(fcb_engine *ea, fcb_engine *eb, const float *in_dev, size_t in_stride, float *out_a,
                                       size_t stride_a, const fcb_epilogue *epi_a, float *out_b, size_t stride_b,
                                       const fcb_epilogue *epi_b, size_t current, size_t active);
+/* the same; the input block is also stored to copy_to ([C][B], channel stride copy_stride, 8-byte aligned rows) — TwoStage's
+ * append to tail_input (:459-461) without a copy of its own */
+int fcb_engine_process_block_pair_copy_dev(fcb_engine *ea, fcb_engine *eb, const float *in_dev, size_t in_stride, float *out_a,
+                                           size_t stride_a, const fcb_epilogue *epi_a, float *out_b, size_t stride_b,
+                                           const fcb_epilogue *epi_b, size_t current, size_t active, float *copy_to,
+                                           size_t copy_stride);
 /* Multi-block calls (offline rendering, large host buffers): nblocks whole blocks of every channel in ONE
  * time-batched pass — K1 for all blocks, a MAC kernel whose threads keep a sliding window of T input spectra in
  * registers (one IR row + one spectrum row loaded per segment feed T output blocks: T blocks for the HBM traffic of

@@ -38,7 +38,8 @@ def cfg0():
     dto = timed(lambda i: o.process(x[(i % 1800) * B:(i % 1800 + 1) * B], out), 1500)
     return {"config": "configs[0] FFTConvolver mono, block 256, IR 48000", "us_per_block_gpu_host_api": dt * 1e6,
             "us_per_block_cpu_port_1core": dto * 1e6, "block_period_us": 1e6 * B / SR,
-            "note": "one channel: latency-bound on the GPU (3 launches + 2 PCIe copies per block), state fits L2"}
+            "note": "one channel, state fits L2: one launch per block, the delay line cut over ~20 CTAs (fcb_tune split), I/O through "
+                    "mapped pinned staging"}
 
 
 def cfg1(async_tail, forced=0):
@@ -56,7 +57,13 @@ def cfg1(async_tail, forced=0):
         if i >= 64:
             per.append(time.perf_counter() - t0)
     per = np.array(per)
+    import oracle  # CPU restatement beside it (baseline only): all host threads over the 64 channels
+    xo = bench.synth_noise(0, C, 0, H * 256)
+    t0 = time.perf_counter()
+    oracle.batch_twostage(h, H, xo, H, forced_tail=forced)
+    cpu_us = (time.perf_counter() - t0) / 256 * 1e6
     return {"config": f"configs[1] TwoStage x{C} ch, head 128, IR 240000, T={conv.tail_block_size}, async_tail={async_tail}",
+            "us_per_head_block_cpu_port_all_threads": cpu_us, "cpu_threads": oracle.load().lib.orc_max_threads(),
             "us_per_head_block_mean": float(per.mean() * 1e6), "us_per_head_block_max": float(per.max() * 1e6),
             "us_per_head_block_p99": float(np.percentile(per, 99) * 1e6), "block_period_us": 1e6 * H / SR,
             "channel_sec_per_sec": C * H / SR / float(per.mean())}
@@ -80,7 +87,14 @@ def cfg2():
         if i >= 10:
             per.append(time.perf_counter() - t0)
     per = np.array(per)
+    import oracle  # CPU restatement beside it (baseline only)
+    h0 = bench.synth_irs(0, C, 0, L)
+    xo = bench.synth_noise(0, C, 0, B * 100)
+    t0 = time.perf_counter()
+    oracle.batch_crossfade(h0, B, xo, irs_upd=np.stack(upd), update_every=50)
+    cpu_us = (time.perf_counter() - t0) / 100 * 1e6
     return {"config": f"configs[2] CrossfadeConvolver::init x{C} ch, block 512, IR 96000, update every 50 blocks",
+            "us_per_block_cpu_port_all_threads": cpu_us, "cpu_threads": oracle.load().lib.orc_max_threads(),
             "us_per_block_mean": float(per.mean() * 1e6), "us_per_block_max": float(per.max() * 1e6),
             "ms_per_update_call": float(np.mean(per_upd) * 1e3), "block_period_us": 1e6 * B / SR,
             "channel_sec_per_sec": C * B / SR / float(per.mean()),

@@ -66,6 +66,7 @@ def test_layer1_sequence_matches_oracle_and_goldens(replay_bin, tmp_path, case):
 
 
 @pytest.mark.gpu
+@pytest.mark.usefixtures("exact_paths")
 def test_layer1_sequence_equals_the_host_mirror_bit_for_bit(replay_bin, tmp_path):
     """ragged calls (partial blocks: K1 + K3 per chunk, K2 only at block start) and one multi-block call"""
     import fft_convolution_b200 as F

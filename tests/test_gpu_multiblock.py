@@ -7,7 +7,7 @@ import pytest
 import oracle
 from refsignals import rms
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_paths")]
 
 
 @pytest.fixture(scope="module")

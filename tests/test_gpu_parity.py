@@ -8,7 +8,7 @@ import oracle
 from oracle import oracle_np
 from refsignals import rms, WholeRun
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_paths")]
 TOL = 1e-5
 
 

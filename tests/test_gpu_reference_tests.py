@@ -7,7 +7,7 @@ import pytest
 import oracle
 from refsignals import generate_sinusoid, rms
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_paths")]
 
 TOL = 1e-5  # max-abs error relative to output RMS (BASELINE.json north_star)
 
