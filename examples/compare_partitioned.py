@@ -61,15 +61,18 @@ def main():
 
     print(f"max_abs_diff = {float(np.max(np.abs(output_a - output_b)))!r}")
 
-    # the same uniform convolver handed the whole input in ONE call: the engine batches the 1000 blocks over
-    # time (csrc/offline_kernels.cuh) and returns the same bits
+    # the same uniform convolver handed the whole input in ONE call: the engine batches the 1000 blocks over time
+    # (csrc/offline_kernels.cuh).  Same arithmetic per block; the block-by-block run above cut each delay line over
+    # several CTAs (one channel cannot fill the GPU otherwise), so the f32 sums are associated differently
     convolver_c = F.FFTConvolver.init(response, block_size, response.size)
+    convolver_c.reserve(x.size)  # process() never allocates: size the multi-block workspace ahead of the call
     output_c = np.zeros_like(output_a)
-    convolver_c.process(x, output_c)  # the first call of this length sizes the multi-block workspace
+    convolver_c.process(x, output_c)
     convolver_c.reset()
     t0 = time.perf_counter()
     convolver_c.process(x, output_c)
-    print(f"Uniform, one call = {(time.perf_counter() - t0) * 1000.0:.2f} ms (identical: {bool(np.array_equal(output_a, output_c))})")
+    rel = float(np.max(np.abs(output_a - output_c))) / float(np.sqrt(np.mean(output_a.astype(np.float64) ** 2)))
+    print(f"Uniform, one call = {(time.perf_counter() - t0) * 1000.0:.2f} ms (max abs diff vs block by block: {rel:.2e} x RMS)")
     out = Path(a.outdir)
     save_wav(str(out / "output_a.wav"), output_a, SAMPLE_RATE)
     save_wav(str(out / "output_b.wav"), output_b, SAMPLE_RATE)

@@ -466,7 +466,8 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
     if (fa.copy_in && flive1) { // the block as it was fed, for the caller's own buffer (z[j] = x[2j] + i x[2j+1])
         float2 *dst = reinterpret_cast<float2 *>(fa.copy_in + (c0 + fslot) * fa.copy_stride);
 #pragma unroll
-        for (int e = 0; e < E; e++) dst[flane + e * T] = fs[sidx(flane + e * T)];
+        for (int e = 0; e < E; e++) // the block is the first B/2 complex points; the rest of the transform is zero padding
+            if (flane + e * T < B / 2) dst[flane + e * T] = fs[sidx(flane + e * T)];
     }
     stockham_all<LOGB, -1, 0, 1>(fs, flane, tw, fwork1);
     float2 xk[E];
