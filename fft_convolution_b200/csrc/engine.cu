@@ -292,14 +292,14 @@ static int launch_block_fused_shared(const fcb_engine *e, cudaStream_t st, Fused
 // Small batches (fewer channel groups than the machine has CTA slots): how many CTAs share one delay line.
 // Aim at ~3 CTAs per SM over the whole grid, at least two pipeline stages of `rows` segments per CTA; slices are whole
 // stages.  Returns zsplit = 1 when the split does not apply.
-static constexpr size_t kSplitTargetCtas = 3 * 148;
+static constexpr size_t kSplitTargetCtas = 4 * 148; // CTA slots of the whole-block kernels (4 per SM at 54 KB each)
 static SplitArgs split_plan(const fcb_engine *e, size_t groups, int seg_lo, int seg_hi, int rows)
 {
     SplitArgs sp{};
     sp.zsplit = 1;
     const int nseg = seg_hi - seg_lo;
     if (!g_split.load() || !e->zpart || groups == 0 || groups * 2 > kSplitTargetCtas || nseg < 4 * rows) return sp;
-    size_t z = (kSplitTargetCtas + groups - 1) / groups;
+    size_t z = kSplitTargetCtas / groups; // whole waves only: never a nearly empty second round
     const size_t zmax = (size_t)nseg / (2 * (size_t)rows);
     if (z > zmax) z = zmax;
     if (z < 2) return sp;
@@ -406,7 +406,18 @@ static int launch_block_fused_pair(const fcb_engine *ea, const fcb_engine *eb, F
     cudaEvent_t prof_stop = nullptr;
     const bool profiled = prof_before(ea->stream, &prof_stop) != nullptr;
     const unsigned grid = (unsigned)(groups * (size_t)fa.split.zsplit);
-    k_block_fused_pair<LOGB, ROWS><<<grid, 256, Cfg::SMEM_BYTES, ea->stream>>>(fa, ea->tw);
+    // block I/O as bulk copies whenever every row is 16-byte aligned (device buffers or mapped pinned host staging); a mix
+    // that reads another buffer than this launch's out_a keeps the plain-store kernel
+    const bool mix_ok = !fa.ifft_b.epi.mix_other || (fa.ifft_b.epi.mix_other == fa.ifft_a.out && (long long)fa.ifft_b.epi.mix_stride == fa.ifft_a.out_stride);
+    if (g_tma_io.load() && mix_ok && !fa.ifft_a.epi.mix_other && tma_io_ok(fa.in, (size_t)fa.in_stride, fa.ifft_a.out, (size_t)fa.ifft_a.out_stride, ea->B) &&
+        tma_io_ok(fa.in, (size_t)fa.in_stride, fa.ifft_b.out, (size_t)fa.ifft_b.out_stride, ea->B)) {
+        static SmemOptIn optin_io;
+        FCB_TRY(optin_io.ensure(k_block_fused_pair<LOGB, ROWS, true>, Cfg::SMEM_BYTES));
+        fa.mix_from_a = fa.ifft_b.epi.mix_other ? 1 : 0;
+        k_block_fused_pair<LOGB, ROWS, true><<<grid, 256, Cfg::SMEM_BYTES, ea->stream>>>(fa, ea->tw);
+    } else {
+        k_block_fused_pair<LOGB, ROWS><<<grid, 256, Cfg::SMEM_BYTES, ea->stream>>>(fa, ea->tw);
+    }
     if (profiled) cudaEventRecord(prof_stop, ea->stream);
     g_launches++;
     FCB_CUDA(cudaGetLastError());

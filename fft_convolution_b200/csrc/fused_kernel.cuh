@@ -350,6 +350,7 @@ struct FusedPairArgs {
     float2 *ring_b;         // convolver B's ring (same geometry as A's): receives the new spectrum as well
     IfftArgs ifft_a, ifft_b; // overlap / out / out_stride / epilogue of each
     SplitArgs split;        // small batches: the delay line cut over zsplit CTAs (see FusedArgs)
+    int mix_from_a;         // ifft_b.epi.mix_other is out_a of this very launch (crossfade): TMA_IO reads it from shared memory
     float *copy_in;         // optional: the input block is also stored here (TwoStage's tail_input, :459-461), stride copy_stride
     long long copy_stride;
 };
@@ -389,7 +390,10 @@ __device__ __forceinline__ float apply_epilogue_pair(float v, const fcb_epilogue
     return v;
 }
 
-template <int LOGB, int ROWS>
+// TMA_IO (16-byte aligned rows): the input block comes in as ONE bulk copy per channel and both output blocks leave as
+// one bulk store per channel — the form that works on pinned HOST buffers (small-batch host calls go through mapped
+// staging; a 512 B .. 2 KB burst per channel crosses PCIe instead of hundreds of 4-byte accesses).  Same arithmetic.
+template <int LOGB, int ROWS, bool TMA_IO = false>
 __global__ void __launch_bounds__(256)
 k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
 {
@@ -405,6 +409,10 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NST * Cfg::STAGE_BYTES);
     float2 *fbuf = reinterpret_cast<float2 *>(smem_raw + NST * Cfg::STAGE_BYTES + 64); // [CPB][FFT_PER]
     float2 *fbuf_b = stages;                                                            // [CPB][FFT_PER], after the stream
+    // TMA_IO: output staging of A and B, in stage memory behind fbuf_b (the stream has ended by then)
+    float *out_sa = reinterpret_cast<float *>(stages + CPB * Cfg::FFT_PER), *out_sb = out_sa + CPB * B;
+    uint64_t *in_bar = full + 7;
+    static_assert((size_t)CPB * Cfg::FFT_PER * sizeof(float2) + 2 * (size_t)CPB * B * sizeof(float) <= Cfg::STAGE_BYTES, "output staging must fit a stage");
 
     const MacArgs &a = fa.mac;
     const int tid = threadIdx.x;
@@ -425,9 +433,15 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
 
     if (tid == 0) {
         for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
+        if (TMA_IO) mbar_init(in_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (TMA_IO && tid == 0 && k1) { // the new block of every live channel lands (raw) at the head of its transform buffer
+        mbar_expect_tx(in_bar, (uint32_t)(nlive * B * sizeof(float)));
+        for (int ch = 0; ch < nlive; ch++)
+            bulk_g2s(fbuf + ch * Cfg::FFT_PER, fa.in + (c0 + ch) * fa.in_stride, B * sizeof(float), in_bar);
+    }
 
     auto issue = [&](int it) {
         const int s = it % NST;
@@ -461,7 +475,24 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
     // ---- K1 once: forward real FFT of the new block, into both rings (src/fft_convolver.rs:234-241) ----
     float2 *fs = fbuf + (fwork1 ? fslot : 0) * Cfg::FFT_PER;
     const bool flive1 = fwork1 && fslot < nlive;
-    if (fwork1) load_block_as_complex<LOGB>(fs, flane, fa.in + (c0 + fslot) * fa.in_stride, flive1 ? B : 0);
+    if (TMA_IO) {
+        if (k1) mbar_wait(in_bar, 0);
+        float2 z[E]; // raw block -> padded transform layout, in place through registers
+        if (fwork1) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const int j = flane + e * T;
+                z[e] = flive1 && j < B / 2 ? fs[j] : make_float2(0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        if (fwork1) {
+#pragma unroll
+            for (int e = 0; e < E; e++) fs[sidx(flane + e * T)] = z[e];
+        }
+    } else if (fwork1) {
+        load_block_as_complex<LOGB>(fs, flane, fa.in + (c0 + fslot) * fa.in_stride, flive1 ? B : 0);
+    }
     __syncthreads();
     if (fa.copy_in && flive1) { // the block as it was fed, for the caller's own buffer (z[j] = x[2j] + i x[2j+1])
         float2 *dst = reinterpret_cast<float2 *>(fa.copy_in + (c0 + fslot) * fa.copy_stride);
@@ -565,11 +596,33 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     int i = 2 * j + h;
-                    o.out[c * o.out_stride + i] = apply_epilogue_pair(__fadd_rn(y[h], o.overlap[c * B + i]), o.epi, c, i);
+                    float v = __fadd_rn(y[h], o.overlap[c * B + i]);
+                    if (TMA_IO && pass == 1 && fa.mix_from_a && o.epi.mix_other) {
+                        // B mixes in A's sample of this block: it sits in A's output staging (same rule as apply_epilogue)
+                        const float2 g = __ldg(reinterpret_cast<const float2 *>(o.epi.gains) + i);
+                        const float other = out_sa[fslot * B + i];
+                        if (o.epi.add0) v = __fadd_rn(v, __ldg(o.epi.add0 + c * (long long)o.epi.add_stride + i));
+                        if (o.epi.add1) v = __fadd_rn(v, __ldg(o.epi.add1 + c * (long long)o.epi.add_stride + i));
+                        if (g.x == 1.f && g.y == 0.f) {
+                        } else if (g.x == 0.f && g.y == 1.f) v = other;
+                        else v = __fadd_rn(__fmul_rn(v, g.x), __fmul_rn(other, g.y));
+                    } else {
+                        v = apply_epilogue_pair(v, o.epi, c, i);
+                    }
+                    if (TMA_IO) (pass == 0 ? out_sa : out_sb)[fslot * B + i] = v;
+                    else o.out[c * o.out_stride + i] = v;
                 }
             }
         }
+        if (TMA_IO && pass == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // staging -> async proxy
         __syncthreads(); // pass 0: A's output visible to B's mix; pass 1: every reader of the old overlaps is done
+    }
+    if (TMA_IO && tid == 0) {
+        for (int ch = 0; ch < nlive; ch++) {
+            bulk_s2g(fa.ifft_a.out + (c0 + ch) * fa.ifft_a.out_stride, out_sa + ch * B, B * sizeof(float));
+            bulk_s2g(fa.ifft_b.out + (c0 + ch) * fa.ifft_b.out_stride, out_sb + ch * B, B * sizeof(float));
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if (flive2) {
         const IfftArgs &o = which == 0 ? fa.ifft_a : fa.ifft_b;
@@ -582,6 +635,7 @@ k_block_fused_pair(FusedPairArgs fa, const float2 *__restrict__ tw)
             }
         }
     }
+    if (TMA_IO && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // staging stays alive until read
 }
 
 

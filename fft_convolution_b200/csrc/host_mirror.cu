@@ -356,6 +356,15 @@ static int fftconv_run(fcb_fftconv *c, const float *in, size_t in_len, size_t in
     if (in_len < out_len) return fail(FCB_ERR_PANIC, "range end index %zu out of range for slice of length %zu", out_len, in_len);
     if (out_len && !in) return fail(FCB_ERR_ARG, "NULL input");
     const size_t B = c->block_size;
+    if (host && g_zero_copy && c->C < 1024 && out_len > 0 && out_len <= B - c->input_buffer_fill) {
+        // one chunk, small batch, caller's buffers page-locked: the device path works on them in place
+        float *din = pinned_alias(in), *dout = pinned_alias(out);
+        if (din && dout) {
+            FCB_TRY(fftconv_run(c, din, out_len, in_stride, dout, out_len, out_stride, nullptr, false));
+            FCB_CUDA(cudaStreamSynchronize(c->stream));
+            return FCB_OK;
+        }
+    }
     if (host && c->m_in && g_mapped_io && out_len > 0 && out_len <= B - c->input_buffer_fill) {
         // one chunk, small batch: stage through mapped pinned memory and run the device path on it
         const size_t n = out_len;
@@ -874,6 +883,14 @@ extern "C" int fcb_twostage_process(fcb_twostage *c, const float *in, size_t in_
     if (in_len != out_len) return fail(FCB_ERR_PANIC, "index out of bounds: input and output lengths differ");
     if (in_len == 0) return FCB_OK;
     FCB_CUDA(cudaSetDevice(c->opt.device));
+    if (g_zero_copy) { // the caller's own buffers are page-locked (fcb_host_alloc): the kernels read and write them in place
+        float *din = pinned_alias(in), *dout = pinned_alias(out);
+        if (din && dout) {
+            FCB_TRY(fcb_twostage_process_dev(c, din, in_len, in_stride, dout, out_len, out_stride));
+            FCB_CUDA(cudaStreamSynchronize(c->stream));
+            return FCB_OK;
+        }
+    }
     if (c->m_in && g_mapped_io) { // small batch: the kernels read and write mapped pinned staging themselves
         const size_t H = c->head_block_size;
         for (size_t ch = 0; ch < c->C; ch++) memcpy(c->h_in + ch * H, in + ch * in_stride, in_len * sizeof(float));
@@ -1051,7 +1068,8 @@ extern "C" int fcb_crossfade_new(fcb_crossfade **out, fcb_fftconv *convolver, si
     cu(cudaHostAlloc(&c->h_gains, n * sizeof(float2), cudaHostAllocDefault));
     cu(cudaMalloc(&c->d_out, c->C * n * sizeof(float)));
     cu(cudaMalloc(&c->d_in, c->C * n * sizeof(float)));
-    if (rc == FCB_OK && c->C * n * sizeof(float) <= ((size_t)1 << 20)) { // small batches: mapped pinned staging
+    if (rc == FCB_OK && c->C * n * sizeof(float) <= ((size_t)1 << 20)) { // small batches: mapped pinned staging, read and
+        // written by the paired kernel's bulk copies (one burst per channel); fcb_tune("mapped_io", 0) = copy engines
         const size_t io = c->C * n * sizeof(float);
         if (cudaHostAlloc(&c->h_in, io, cudaHostAllocMapped) != cudaSuccess || cudaHostAlloc(&c->h_out, io, cudaHostAllocMapped) != cudaSuccess ||
             cudaHostGetDevicePointer(&c->m_in, c->h_in, 0) != cudaSuccess || cudaHostGetDevicePointer(&c->m_out, c->h_out, 0) != cudaSuccess) {
@@ -1278,6 +1296,15 @@ extern "C" int fcb_crossfade_process(fcb_crossfade *c, const float *in, size_t i
     // both convolvers consume input[..max_buffer_size] (:72-73): a longer input is never read past that, a shorter
     // one panics inside FFTConvolver::process — either way at most M samples are staged (buffer made in new())
     const size_t n_in = in_len < M ? in_len : M;
+    if (g_zero_copy && M && out_len) {
+        // the caller's own buffers are page-locked (fcb_host_alloc): the kernels read and write them in place
+        float *din = pinned_alias(in), *dout = pinned_alias(out);
+        if (din && dout) {
+            FCB_TRY(fcb_crossfade_process_dev(c, din, n_in, in_stride, dout, out_len, out_stride));
+            FCB_CUDA(cudaStreamSynchronize(c->stream));
+            return FCB_OK;
+        }
+    }
     if (c->m_in && g_mapped_io && M) { // small batch: the kernels read and write mapped pinned staging themselves
         for (size_t ch = 0; ch < c->C; ch++) memcpy(c->h_in + ch * M, in + ch * in_stride, n_in * sizeof(float));
         FCB_TRY(fcb_crossfade_process_dev(c, c->m_in, n_in, M, c->m_out, out_len, M));
