@@ -286,7 +286,7 @@ def run_realtime(F, lib, local, rank, world, chan0, Cn_head, ms_e2e_per_block_he
     period = B / SAMPLE_RATE
     free_b, _ = torch.cuda.mem_get_info(local)
     per_ch = 2 * ((L + B - 1) // B) * B * 8 + 64 * B
-    c_fit = int(0.90 * period * 1000.0 / ms_e2e_per_block_head * Cn_head) // 256 * 256
+    c_fit = int(0.85 * period * 1000.0 / ms_e2e_per_block_head * Cn_head) // 256 * 256  # 15 % headroom for host jitter
     c_mem = int(0.85 * free_b / per_ch) // 256 * 256
     sizes = [("1e5_over_8_gpus", 12500), ("largest_that_fits_the_period", max(256, min(c_fit, c_mem)))]
     base = synth_irs(chan0, min(4096, max(s for _, s in sizes)), 0, L)
@@ -345,27 +345,28 @@ def run_mimo(local, rank, world, steps, warmup):
     for NS in (1, 128):
         x = [torch.from_numpy(synth_noise(0, NS * N, B * i, B)).cuda(local) for i in range(8)]
         ref = None
-        if rank == 0:  # the unsharded engine, first blocks only
+        NCHK = 520  # past half of the 938-slot ring: every shard's segment range has met real input spectra
+        if rank == 0:  # the unsharded engine on the same blocks; the last one is compared
             whole = F.MimoConvolver.init(h, B, L, n_streams=NS, device=local)
-            ref = []
             o = torch.empty((NS * N, B), dtype=torch.float32, device=f"cuda:{local}")
-            for i in range(4):
-                whole.partial_dev(x[i].data_ptr(), B)
+            for i in range(NCHK):
+                whole.partial_dev(x[i % 8].data_ptr(), B)
                 whole.finish_dev(o.data_ptr(), B)
-                whole.sync()
-                ref.append(o.cpu().numpy().copy())
+            whole.sync()
+            ref = o.cpu().numpy().copy()
             whole.close()
             del whole
         for exchange in ("peer", "nccl"):
             m = ShardedMimoConvolver(h, B, L, n_streams=NS, device=local, exchange=exchange)
             out = torch.empty((NS * N, B), dtype=torch.float32, device=f"cuda:{local}")
-            err = 0.0
-            for i in range(4):
-                m.process_dev(x[i], out)
-                torch.cuda.synchronize()
-                if ref is not None:
-                    r = ref[i]
-                    err = max(err, float(np.max(np.abs(out.cpu().numpy() - r))) / max(float(np.sqrt(np.mean(r.astype(np.float64) ** 2))), 1e-9))
+            err = None
+            for i in range(NCHK):
+                m.process_dev(x[i % 8], out)
+            torch.cuda.synchronize()
+            if ref is not None:
+                err = float(np.max(np.abs(out.cpu().numpy() - ref))) / max(float(np.sqrt(np.mean(ref.astype(np.float64) ** 2))), 1e-9)
+                if err > 1e-5:
+                    raise SystemExit(f"bench.py: sharded matrix differs from the unsharded engine: {err:.3e} x RMS")
             for i in range(warmup):
                 m.process_dev(x[i % 8], out)
             torch.cuda.synchronize()
@@ -381,7 +382,7 @@ def run_mimo(local, rank, world, steps, warmup):
             res[f"streams{NS}_{exchange}"] = {
                 "ms_per_block": ms, "realtime_factor": 1000.0 * B / SAMPLE_RATE / ms, "tensor_cores": bool(m.m.uses_tensor_cores),
                 "T_cmac_per_s": NS * N * N * ((L + B - 1) // B) * B / (ms / 1e3) / 1e12,
-                "max_abs_err_over_rms_vs_unsharded": err if rank == 0 else None}
+                "max_abs_err_over_rms_vs_unsharded_after_520_blocks": err}
             m.m.close()
             del m
             dist.barrier()
