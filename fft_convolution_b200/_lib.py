@@ -28,7 +28,7 @@ class CudaError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("shared_ir", C.c_int),
-                ("async_tail", C.c_int), ("forced_tail_block", C.c_size_t)]
+                ("async_tail", C.c_int), ("forced_tail_block", C.c_size_t), ("stages", C.c_size_t)]
 
 
 class EngineDesc(C.Structure):
@@ -134,6 +134,7 @@ SIGNATURES = {
     "fcb_twostage_process_dev": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz]),
     "fcb_twostage_sync": (_i, [_vp]),
     "fcb_twostage_tail_block_size": (_sz, [_vp]),
+    "fcb_twostage_stage_blocks": (_sz, [_vp, C.POINTER(_sz), _sz]),
     "fcb_crossfade_new": (_i, [_pp, _vp, _sz, _sz, _sz]),
     "fcb_crossfade_init": (_i, [_pp, _vp, _sz, _sz, _sz, _sz, C.POINTER(Options)]),
     "fcb_crossfade_free": (None, [_vp]),

@@ -36,8 +36,8 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def _opts(device=0, stream=None, shared_ir=False, async_tail=False, forced_tail_block=0) -> Options:
-    return Options(device, stream, int(shared_ir), int(async_tail), forced_tail_block)
+def _opts(device=0, stream=None, shared_ir=False, async_tail=False, forced_tail_block=0, stages=0) -> Options:
+    return Options(device, stream, int(shared_ir), int(async_tail), forced_tail_block, stages)
 
 
 class _Base:
@@ -181,12 +181,13 @@ class TwoStageFFTConvolver(_Base):
 
     @classmethod
     def init(cls, response, block_size: int, max_response_length: int, *, device: int = 0, stream=None,
-             async_tail: bool = False, forced_tail_block: int = 0) -> "TwoStageFFTConvolver":
+             async_tail: bool = False, forced_tail_block: int = 0, stages: int = 2) -> "TwoStageFFTConvolver":
+        """stages > 2 (extension): the partition nested — the tail is again a two-stage convolver (block sizes B, T1, T2, ...)"""
         lib = _lib.load()
         _lib.require_gpu()
         r, mono = _as_ir(response)
         h = C.c_void_p()
-        o = _opts(device, stream, async_tail=async_tail, forced_tail_block=forced_tail_block)
+        o = _opts(device, stream, async_tail=async_tail, forced_tail_block=forced_tail_block, stages=stages)
         check(lib.fcb_twostage_init(C.byref(h), _ptr(r), r.shape[0], r.shape[1], block_size, max_response_length,
                                     C.byref(o)))
         self = cls(h, r.shape[0], mono)
@@ -220,6 +221,12 @@ class TwoStageFFTConvolver(_Base):
     @property
     def tail_block_size(self) -> int:
         return _lib.load().fcb_twostage_tail_block_size(self._h)
+
+    @property
+    def stage_blocks(self) -> list:
+        buf = (C.c_size_t * 16)()
+        n = _lib.load().fcb_twostage_stage_blocks(self._h, buf, 16)
+        return [int(buf[i]) for i in range(min(n, 16))]
 
 
 class CrossfadeConvolver(_Base):

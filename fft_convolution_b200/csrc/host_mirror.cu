@@ -519,6 +519,10 @@ extern "C" size_t fcb_compute_tail_block_size(size_t head_len, size_t response_l
 struct fcb_twostage {
     size_t C = 0, head_block_size = 0, tail_block_size = 0; // :325-326
     size_t max_response_length = 0; // not a field of the reference struct; fcb_twostage_update re-slices with it
+    // EXTENSION (fcb_options.stages > 2): the tail [2T, L) is itself a two-stage convolver whose head block is T — the
+    // reference's partition applied recursively (Gardner-style non-uniform partition).  It lives on
+    // the tail stream; `tail` is then a Default convolver.
+    fcb_twostage *nested = nullptr;
     fcb_fftconv *head = nullptr, *tail0 = nullptr, *tail = nullptr;
     // device [C][T] each (:329-334); tail_in is double-buffered for the asynchronous tail
     float *tail_output0 = nullptr, *tail_precalculated0 = nullptr, *tail_output = nullptr,
@@ -542,6 +546,7 @@ extern "C" void fcb_twostage_free(fcb_twostage *c)
     cudaSetDevice(c->opt.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
+    fcb_twostage_free(c->nested);
     fcb_fftconv_free(c->head);
     fcb_fftconv_free(c->tail0);
     fcb_fftconv_free(c->tail);
@@ -620,7 +625,9 @@ extern "C" int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t ch
     fcb_options o = opt ? *opt : default_options();
     o.shared_ir = 0;
     const size_t head = block_size; // :341 (kept unrounded for the bookkeeping)
-    const size_t T = o.forced_tail_block ? o.forced_tail_block : fcb_compute_tail_block_size(block_size, max_response_length);
+    size_t T = o.forced_tail_block ? o.forced_tail_block : fcb_compute_tail_block_size(block_size, max_response_length);
+    const size_t stages = o.stages < 2 ? 2 : o.stages;
+    if (stages > 2 && !o.forced_tail_block && T > 16384) T = 16384; // nested levels: stay within the engine's block limit
     if (max_response_length < ir_len) // :344-348
         return fail(FCB_ERR_PANIC, "max_response_length must be at least the length of the initial impulse response");
     if (head == 0) return fail(FCB_ERR_PANIC, "attempt to calculate the remainder with a divisor of zero"); // :431
@@ -660,7 +667,16 @@ extern "C" int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t ch
     if (rc == FCB_OK) {
         fcb_options tsub = sub;
         if (c->tail_stream) tsub.stream = (void *)c->tail_stream;
-        if (L > 2 * T) { // :373-384
+        if (L > 2 * T && stages > 2) { // EXTENSION: the tail is again a two-stage convolver, fed T samples per call
+            const size_t tl = L - 2 * T;
+            auto v = gather(2 * T, tl);
+            fcb_options nsub = tsub;
+            nsub.stages = stages - 1;
+            nsub.async_tail = 0; // everything of the tail stays in order on the tail stream
+            nsub.forced_tail_block = 0;
+            rc = fcb_twostage_init(&c->nested, v.data(), channels, tl, T, tl, &nsub);
+            if (rc == FCB_OK) rc = fcb_fftconv_default(&c->tail, channels, &tsub);
+        } else if (L > 2 * T) { // :373-384
             const size_t tl = L - 2 * T;
             auto v = gather(2 * T, tl);
             rc = fcb_fftconv_init(&c->tail, v.data(), channels, tl, T, tl, &tsub);
@@ -683,7 +699,25 @@ static int twostage_quiesce(const fcb_twostage *c)
     FCB_CUDA(cudaSetDevice(c->opt.device));
     FCB_CUDA(cudaStreamSynchronize(c->stream));
     if (c->tail_stream) FCB_CUDA(cudaStreamSynchronize(c->tail_stream));
-    return FCB_OK;
+    return c->nested ? twostage_quiesce(c->nested) : FCB_OK;
+}
+
+// move a (nested) two-stage convolver and everything under it onto stream `st`
+static int twostage_rehome(fcb_twostage *n, cudaStream_t st)
+{
+    FCB_TRY(twostage_quiesce(n));
+    for (fcb_fftconv *f : {n->head, n->tail0, n->tail}) {
+        if (f->eng) FCB_TRY(fcb_engine_set_stream(f->eng, (void *)st));
+        if (f->own_stream) cudaStreamDestroy(f->stream);
+        f->own_stream = false;
+        f->stream = st;
+        f->opt.stream = (void *)st;
+    }
+    if (n->own_stream && n->stream) cudaStreamDestroy(n->stream);
+    n->own_stream = false;
+    n->stream = st;
+    n->opt.stream = (void *)st;
+    return n->nested ? twostage_rehome(n->nested, st) : FCB_OK;
 }
 
 extern "C" int fcb_twostage_clone(const fcb_twostage *s, fcb_twostage **out)
@@ -701,6 +735,10 @@ extern "C" int fcb_twostage_clone(const fcb_twostage *s, fcb_twostage **out)
     int rc = fcb_fftconv_clone(s->head, &c->head);
     if (rc == FCB_OK) rc = fcb_fftconv_clone(s->tail0, &c->tail0);
     if (rc == FCB_OK) rc = fcb_fftconv_clone(s->tail, &c->tail);
+    if (rc == FCB_OK && s->nested) {
+        rc = fcb_twostage_clone(s->nested, &c->nested);
+        if (rc == FCB_OK) rc = twostage_rehome(c->nested, c->tail_stream ? c->tail_stream : c->stream);
+    }
     if (rc == FCB_OK) rc = twostage_alloc(c);
     if (rc == FCB_OK) {
         // the clones carry their own private streams; re-home them onto this object's streams
@@ -758,7 +796,15 @@ extern "C" int fcb_twostage_update(fcb_twostage *c, const float *irs, size_t ir_
     };
     FCB_TRY(stage(c->head, 0, L < T ? L : T));
     if (L > T) FCB_TRY(stage(c->tail0, T, (L - T) < T ? (L - T) : T));
-    if (L > 2 * T) FCB_TRY(stage(c->tail, 2 * T, L - 2 * T));
+    if (L > 2 * T) {
+        if (c->nested) {
+            const size_t off = 2 * T, valid = ir_len > off ? ir_len - off : 0;
+            if (c->C > 1 && valid) return fail(FCB_ERR_UNSUPPORTED, "update of a nested partition: batched responses need a contiguous slice per channel");
+            FCB_TRY(fcb_twostage_update(c->nested, valid ? irs + off : irs, valid));
+        } else {
+            FCB_TRY(stage(c->tail, 2 * T, L - 2 * T));
+        }
+    }
     return FCB_OK;
 }
 
@@ -771,6 +817,7 @@ extern "C" int fcb_twostage_reset(fcb_twostage *c)
     FCB_TRY(fcb_fftconv_reset(c->head));
     FCB_TRY(fcb_fftconv_reset(c->tail0));
     FCB_TRY(fcb_fftconv_reset(c->tail));
+    if (c->nested) FCB_TRY(fcb_twostage_reset(c->nested));
     const size_t bytes = c->C * c->tail_block_size * sizeof(float);
     float *bufs[] = {c->tail_output0, c->tail_precalculated0, c->tail_output, c->tail_precalculated,
                      c->tail_input[0], c->tail_input[1]};
@@ -779,6 +826,14 @@ extern "C" int fcb_twostage_reset(fcb_twostage *c)
     c->tail_input_fill = 0;
     c->precalculated_pos = 0;
     return twostage_quiesce(c);
+}
+
+// :479-486 — the big tail block: one FFTConvolver call of T samples, or (nested partition) one two-stage call
+static int twostage_run_tail(fcb_twostage *c, const float *tin)
+{
+    const size_t T = c->tail_block_size;
+    if (c->nested) return fcb_twostage_process_dev(c->nested, tin, T, T, c->tail_output, T, T);
+    return fcb_fftconv_process_dev(c->tail, tin, T, T, c->tail_output, T, T, nullptr);
 }
 
 // :412-495 on device buffers
@@ -857,13 +912,13 @@ extern "C" int fcb_twostage_process_dev(fcb_twostage *c, const float *in, size_t
                 std::swap(c->tail_precalculated, c->tail_output);
                 FCB_CUDA(cudaEventRecord(c->ev_in, c->stream));
                 FCB_CUDA(cudaStreamWaitEvent(c->tail_stream, c->ev_in, 0));
-                FCB_TRY(fcb_fftconv_process_dev(c->tail, tin, T, T, c->tail_output, T, T, nullptr));
+                FCB_TRY(twostage_run_tail(c, tin));
                 FCB_CUDA(cudaEventRecord(c->ev_tail_done, c->tail_stream));
                 c->tail_pending = true;
                 c->tail_in_sel ^= 1; // the tail stream may still be reading `tin`
             } else {
                 std::swap(c->tail_precalculated, c->tail_output);
-                FCB_TRY(fcb_fftconv_process_dev(c->tail, tin, T, T, c->tail_output, T, T, nullptr));
+                FCB_TRY(twostage_run_tail(c, tin));
             }
         }
         if (c->tail_input_fill == T) { // :488-491
@@ -914,6 +969,19 @@ extern "C" int fcb_twostage_sync(fcb_twostage *c)
     return twostage_quiesce(c);
 }
 extern "C" size_t fcb_twostage_tail_block_size(const fcb_twostage *c) { return c->tail_block_size; }
+// block sizes of the (nested) partition, outermost first: head, T1, T2, ...; returns how many there are
+extern "C" size_t fcb_twostage_stage_blocks(const fcb_twostage *c, size_t *out, size_t cap)
+{
+    size_t n = 0;
+    if (!c) return 0;
+    if (n < cap) out[n] = c->head_block_size;
+    n++;
+    for (; c; c = c->nested) {
+        if (n < cap) out[n] = c->tail_block_size;
+        n++;
+    }
+    return n;
+}
 
 // ==============================================================================================
 // Crossfader<RaisedCosineMixer> — src/crossfade_convolver.rs:160-279, run on the host one sample

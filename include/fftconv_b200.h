@@ -248,6 +248,10 @@ typedef struct {
     int async_tail; /* TwoStage: run the big tail convolver on a second stream (the reference's
                        "might be done in some background thread", src/fft_convolver.rs:478) */
     size_t forced_tail_block; /* TwoStage: 0 = derive like the reference (:520-526) */
+    size_t stages;  /* TwoStage: 0 or 2 = the reference's two stages.  N > 2 (EXTENSION): the partition
+                       nested N-1 deep — the tail [2T, L) of every level but the last is again a two-stage convolver with
+                       head block T and its own T from the same formula (capped at 16384): block sizes B, T1, T2, ...
+                       grow geometrically with the distance into the response, Gardner-style */
 } fcb_options;
 
 /* ---- FFTConvolver (src/fft_convolver.rs:86-307) ---- */
@@ -301,6 +305,8 @@ int fcb_twostage_process_dev(fcb_twostage *c, const float *in_dev, size_t in_len
                              float *out_dev, size_t out_len, size_t out_stride);
 int fcb_twostage_sync(fcb_twostage *c);
 size_t fcb_twostage_tail_block_size(const fcb_twostage *c);
+/* block sizes of the (nested) partition, outermost first: head, T1, T2, ...; returns how many there are */
+size_t fcb_twostage_stage_blocks(const fcb_twostage *c, size_t *out, size_t cap);
 
 /* ---- CrossfadeConvolver<FFTConvolver> (src/crossfade_convolver.rs:3-105) ---- */
 /* CrossfadeConvolver::new (:20-42): takes ownership of `convolver` */

@@ -449,14 +449,37 @@ struct orc_twostage {
     float *tail_output0, *tail_precalculated0, *tail_output, *tail_precalculated, *tail_input;
     size_t tail_input_fill, precalculated_pos;
     size_t max_response_length; /* not a field of the reference struct; only orc_twostage_update_ext reads it */
+    /* EXTENSION (orc_twostage_init_multi): when not NULL the tail [2T, L) is itself a two-stage convolver whose head
+     * block is T — the reference's partition applied recursively (Gardner-style non-uniform partition, SURVEY.md
+     * §8(f)4); tail_convolver is then a Default convolver and unused */
+    struct orc_twostage *tail_nested;
 };
+
+static orc_twostage *twostage_init_impl(const float *ir, size_t n_ir, size_t block_size, size_t max_response_length,
+                                        size_t forced_tail, size_t stages, size_t max_block);
 
 /* :340-406 */
 orc_twostage *orc_twostage_init_tail(const float *ir, size_t n_ir, size_t block_size,
                                      size_t max_response_length, size_t forced_tail)
 {
+    return twostage_init_impl(ir, n_ir, block_size, max_response_length, forced_tail, 2, 0);
+}
+
+/* EXTENSION: `stages` > 2 nests the partition — the tail of every level but the last is again a two-stage convolver
+ * (head block = this level's T, its own T from the same formula on what is left, capped at max_block when that is not
+ * 0).  stages <= 2 is the reference's TwoStageFFTConvolver. */
+orc_twostage *orc_twostage_init_multi(const float *ir, size_t n_ir, size_t block_size, size_t max_response_length,
+                                      size_t stages, size_t max_block)
+{
+    return twostage_init_impl(ir, n_ir, block_size, max_response_length, 0, stages < 2 ? 2 : stages, max_block);
+}
+
+static orc_twostage *twostage_init_impl(const float *ir, size_t n_ir, size_t block_size, size_t max_response_length,
+                                        size_t forced_tail, size_t stages, size_t max_block)
+{
     size_t head = block_size;
     size_t T = forced_tail ? forced_tail : orc_compute_tail_block_size(block_size, max_response_length);
+    if (!forced_tail && max_block && T > max_block) T = max_block;
     if (max_response_length < n_ir) return NULL; /* panic! :344-348 */
     size_t L = max_response_length;
     float *padded = (float *)calloc(L ? L : 1, sizeof(float));
@@ -474,7 +497,11 @@ orc_twostage *orc_twostage_init_tail(const float *ir, size_t n_ir, size_t block_
     } else {
         c->tail_convolver0 = orc_fftconv_default();
     }
-    if (L > 2 * T) { /* :373-384 */
+    if (L > 2 * T && stages > 2) { /* EXTENSION: the tail is again a two-stage convolver fed T samples per call */
+        size_t tail_ir_len = L - 2 * T;
+        c->tail_nested = twostage_init_impl(padded + 2 * T, tail_ir_len, T, tail_ir_len, 0, stages - 1, max_block);
+        c->tail_convolver = orc_fftconv_default();
+    } else if (L > 2 * T) { /* :373-384 */
         size_t tail_ir_len = L - 2 * T;
         c->tail_convolver = orc_fftconv_init(padded + 2 * T, tail_ir_len, T, tail_ir_len);
     } else {
@@ -502,6 +529,7 @@ orc_twostage *orc_twostage_clone(const orc_twostage *s)
     c->head_convolver = orc_fftconv_clone(s->head_convolver);
     c->tail_convolver0 = orc_fftconv_clone(s->tail_convolver0);
     c->tail_convolver = orc_fftconv_clone(s->tail_convolver);
+    c->tail_nested = s->tail_nested ? orc_twostage_clone(s->tail_nested) : NULL;
     c->tail_output0 = (float *)dup_mem(s->tail_output0, T * sizeof(float));
     c->tail_precalculated0 = (float *)dup_mem(s->tail_precalculated0, T * sizeof(float));
     c->tail_output = (float *)dup_mem(s->tail_output, T * sizeof(float));
@@ -514,6 +542,7 @@ void orc_twostage_free(orc_twostage *c)
 {
     if (!c) return;
     orc_fftconv_free(c->head_convolver); orc_fftconv_free(c->tail_convolver0); orc_fftconv_free(c->tail_convolver);
+    orc_twostage_free(c->tail_nested);
     free(c->tail_output0); free(c->tail_precalculated0); free(c->tail_output);
     free(c->tail_precalculated); free(c->tail_input);
     free(c);
@@ -544,7 +573,9 @@ int orc_twostage_update_ext(orc_twostage *c, const float *ir, size_t len)
     if (len) memcpy(padded, ir, len * sizeof(float));
     int rc = orc_fftconv_update(c->head_convolver, padded, L < T ? L : T);
     if (!rc && L > T) rc = orc_fftconv_update(c->tail_convolver0, padded + T, (L - T) < T ? (L - T) : T);
-    if (!rc && L > 2 * T) rc = orc_fftconv_update(c->tail_convolver, padded + 2 * T, L - 2 * T);
+    if (!rc && L > 2 * T)
+        rc = c->tail_nested ? orc_twostage_update_ext(c->tail_nested, padded + 2 * T, L - 2 * T)
+                            : orc_fftconv_update(c->tail_convolver, padded + 2 * T, L - 2 * T);
     free(padded);
     return rc;
 }
@@ -593,7 +624,8 @@ int orc_twostage_process(orc_twostage *c, const float *input, size_t in_len, flo
         }
         if (c->tail_input_fill == T) { /* :479-486 */
             swap_ptr(&c->tail_precalculated, &c->tail_output);
-            orc_fftconv_process(c->tail_convolver, c->tail_input, T, c->tail_output, T);
+            if (c->tail_nested) orc_twostage_process(c->tail_nested, c->tail_input, T, c->tail_output, T);
+            else orc_fftconv_process(c->tail_convolver, c->tail_input, T, c->tail_output, T);
         }
         if (c->tail_input_fill == T) { /* :488-491 */
             c->tail_input_fill = 0;
@@ -613,6 +645,7 @@ void orc_twostage_reset(orc_twostage *c)
     memset(c->tail_output0, 0, T * sizeof(float));
     memset(c->tail_precalculated0, 0, T * sizeof(float));
     orc_fftconv_reset(c->tail_convolver);
+    if (c->tail_nested) orc_twostage_reset(c->tail_nested);
     memset(c->tail_output, 0, T * sizeof(float));
     memset(c->tail_precalculated, 0, T * sizeof(float));
     memset(c->tail_input, 0, T * sizeof(float));
@@ -621,6 +654,18 @@ void orc_twostage_reset(orc_twostage *c)
 }
 
 size_t orc_twostage_tail_block_size(const orc_twostage *c) { return c->tail_block_size; }
+/* block sizes of the nested partition, outermost first: head, T1, T2, ...; returns how many */
+size_t orc_twostage_stage_blocks(const orc_twostage *c, size_t *out, size_t cap)
+{
+    size_t n = 0;
+    if (n < cap) out[n] = c->head_block_size;
+    n++;
+    for (; c; c = c->tail_nested) {
+        if (n < cap) out[n] = c->tail_block_size;
+        n++;
+    }
+    return n;
+}
 
 /* ------------------------------------------------------------------------------------------
  * Crossfader<RaisedCosineMixer> — src/crossfade_convolver.rs:160-279

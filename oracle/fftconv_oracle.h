@@ -77,6 +77,12 @@ orc_twostage *orc_twostage_init(const float *ir, size_t ir_len, size_t block_siz
  * BASELINE.json "tail 4096" wording, see SURVEY.md §8 config-2 note */
 orc_twostage *orc_twostage_init_tail(const float *ir, size_t ir_len, size_t block_size,
                                      size_t max_response_length, size_t forced_tail);
+/* EXTENSION beyond the reference: `stages` > 2 nests the two-stage partition (the tail of every level but the last is
+ * again a two-stage convolver with head block T; each level's T from the reference's own formula, capped at
+ * max_block when non-zero) — a Gardner-style non-uniform partition built from the reference's scheme */
+orc_twostage *orc_twostage_init_multi(const float *ir, size_t ir_len, size_t block_size, size_t max_response_length,
+                                      size_t stages, size_t max_block);
+size_t orc_twostage_stage_blocks(const orc_twostage *c, size_t *out, size_t cap);
 orc_twostage *orc_twostage_clone(const orc_twostage *c);
 void orc_twostage_free(orc_twostage *c);
 int orc_twostage_update(orc_twostage *c, const float *ir, size_t len); /* todo!() => ORC_PANIC */

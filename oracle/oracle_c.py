@@ -72,6 +72,8 @@ class OracleLib:
         sig("orc_compute_tail_block_size", _sz, _sz, _sz)
         sig("orc_twostage_init", _vp, _f32p, _sz, _sz, _sz)
         sig("orc_twostage_init_tail", _vp, _f32p, _sz, _sz, _sz, _sz)
+        sig("orc_twostage_init_multi", _vp, _f32p, _sz, _sz, _sz, _sz, _sz)
+        sig("orc_twostage_stage_blocks", _sz, _vp, C.POINTER(_sz), _sz)
         sig("orc_twostage_clone", _vp, _vp)
         sig("orc_twostage_free", None, _vp)
         sig("orc_twostage_update", C.c_int, _vp, _f32p, _sz)
@@ -200,10 +202,14 @@ class TwoStageFFTConvolver:
         self._h, self._lib = handle, lib
 
     @classmethod
-    def init(cls, response, block_size, max_response_length, forced_tail: int = 0):
+    def init(cls, response, block_size, max_response_length, forced_tail: int = 0, stages: int = 2, max_block: int = 0):
+        """stages > 2: EXTENSION, the partition nested (the tail is again a two-stage convolver)"""
         lib = load()
         r = _f32(response)
-        h = lib.lib.orc_twostage_init_tail(r, r.size, block_size, max_response_length, forced_tail)
+        if stages > 2:
+            h = lib.lib.orc_twostage_init_multi(r, r.size, block_size, max_response_length, stages, max_block)
+        else:
+            h = lib.lib.orc_twostage_init_tail(r, r.size, block_size, max_response_length, forced_tail)
         if not h:
             raise OraclePanic("max_response_length must be at least the length of the initial impulse response")
         return cls(h, lib)
@@ -232,6 +238,12 @@ class TwoStageFFTConvolver:
     @property
     def tail_block_size(self):
         return self._lib.lib.orc_twostage_tail_block_size(self._h)
+
+    @property
+    def stage_blocks(self):
+        buf = (_sz * 16)()
+        n = self._lib.lib.orc_twostage_stage_blocks(self._h, buf, 16)
+        return [int(buf[i]) for i in range(min(n, 16))]
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -262,11 +262,12 @@ pub struct FcbOptions {
     pub shared_ir: c_int,
     pub async_tail: c_int,
     pub forced_tail_block: usize,
+    pub stages: usize, // 0 / 2 = the reference's two stages; N > 2 nests the partition (extension)
 }
 
 impl FcbOptions {
     pub fn new(device: c_int) -> Self {
-        Self { device, stream: std::ptr::null_mut(), shared_ir: 0, async_tail: 0, forced_tail_block: 0 }
+        Self { device, stream: std::ptr::null_mut(), shared_ir: 0, async_tail: 0, forced_tail_block: 0, stages: 0 }
     }
 }
 

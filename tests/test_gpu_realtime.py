@@ -313,3 +313,34 @@ def test_small_batch_calls_on_caller_pinned_buffers_work_in_place(F):
             assert np.array_equal(np.asarray(yout), ref), (type(a).__name__, i)
     lib.fcb_host_free(pin)
     lib.fcb_host_free(pout)
+
+
+@pytest.mark.parametrize("head,L,stages,async_tail", [(32, 40000, 3, False), (32, 40000, 4, True), (64, 150000, 3, True)])
+def test_nested_partition_matches_oracle_and_truth(F, head, L, stages, async_tail):
+    """fcb_options.stages > 2 (extension): the tail of the two-stage partition is again a two-stage
+    convolver — block sizes head, T1, T2, ... — against the oracle's nested convolver and an f64 convolution"""
+    from oracle import oracle_np
+    from refsignals import WholeRun
+    h = oracle.gen_ir(2, 0, L)
+    g = F.TwoStageFFTConvolver.init(h, head, L, stages=stages, async_tail=async_tail)
+    o = oracle.TwoStageFFTConvolver.init(h, head, L, stages=stages, max_block=16384)
+    assert g.stage_blocks == o.stage_blocks and len(g.stage_blocks) >= 3 and g.stage_blocks[2] > g.stage_blocks[1] >= head
+    n = 3 * g.stage_blocks[2] // head + 40
+    x = oracle.gen_noise(2, 0, head * n)
+    yg, yo = np.zeros_like(x), np.zeros_like(x)
+    a, b = np.zeros(head, np.float32), np.zeros(head, np.float32)
+    for i in range(n):
+        g.process(x[i * head:(i + 1) * head], a)
+        o.process(x[i * head:(i + 1) * head], b)
+        yg[i * head:(i + 1) * head], yo[i * head:(i + 1) * head] = a, b
+    assert np.max(np.abs(yg - yo)) <= 1e-5 * rms(yo)
+    yt = oracle_np.truth_f64(x, h)
+    assert np.max(np.abs(yg - yt)) <= 1e-5 * rms(yt)
+    # reset and clone carry the nested state
+    k = g.clone()
+    g.process(x[:head], a); k.process(x[:head], b)
+    assert np.array_equal(a, b)
+    g.reset(); o.reset()
+    for i in range(20):
+        g.process(x[i * head:(i + 1) * head], a); o.process(x[i * head:(i + 1) * head], b)
+    assert np.max(np.abs(a - b)) <= 1e-5 * rms(yo)
