@@ -673,7 +673,9 @@ extern "C" int fcb_twostage_init(fcb_twostage **out, const float *irs, size_t ch
             fcb_options nsub = tsub;
             nsub.stages = stages - 1;
             nsub.async_tail = 0; // everything of the tail stays in order on the tail stream
-            nsub.forced_tail_block = 0;
+            // the nested level's own T: the reference's formula on what is left, within the engine's block limit
+            const size_t tn = fcb_compute_tail_block_size(T, tl);
+            nsub.forced_tail_block = tn > 16384 ? 16384 : tn;
             rc = fcb_twostage_init(&c->nested, v.data(), channels, tl, T, tl, &nsub);
             if (rc == FCB_OK) rc = fcb_fftconv_default(&c->tail, channels, &tsub);
         } else if (L > 2 * T) { // :373-384
