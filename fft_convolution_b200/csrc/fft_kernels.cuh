@@ -43,24 +43,36 @@ __device__ __host__ __forceinline__ constexpr int sidx(int i) { return i + (i >>
 #ifndef FCB_FFT_E16_FROM
 #define FCB_FFT_E16_FROM 14 // block sizes from 2^this on: 16 points per thread (two radix-8 butterflies in flight)
 #endif
+// Large transforms (B >= 4096: the two-stage tail, K5 of long segments) use the "wide" plan: 32 points per thread — two
+// ADJACENT radix-16 butterflies — so that every shared-memory access of a Stockham pass is 16 bytes (LDS.128 / STS.128:
+// butterflies j and j+1 read neighbouring points and, from the second pass on, write neighbouring points; in the first
+// pass a butterfly's own 16 outputs are neighbours), three radix-16 passes plus one radix-2 / radix-4 pass instead of
+// five radix-8/4 passes, and half the threads.  ncu on the round-1 kernel (profiles/r02_tailfft_before_*): the top stall
+// was mio_throttle — the shared-memory instruction queue — at one 1024-thread CTA per SM; the wide plan issues 2.5x
+// fewer shared-memory instructions per transform and fits two CTAs per SM.
 template <int LOGB>
 struct FftPlan {
     static constexpr int B = 1 << LOGB;
-    static constexpr int E = LOGB >= FCB_FFT_E16_FROM ? 16 : (LOGB >= 3 ? 8 : B); // points per thread
+    static constexpr bool WIDE = LOGB >= 12;
+    static constexpr int E = WIDE ? 32 : (LOGB >= FCB_FFT_E16_FROM ? 16 : (LOGB >= 3 ? 8 : B)); // points per thread
     static constexpr int T = B / E;                                 // threads per transform
     static constexpr int CTA = T >= 256 ? T : 256;                  // threads per CTA
     static constexpr int TPB = CTA / T;                             // transforms per CTA
-    static constexpr int SMEM_PER = sidx(B) + 1;                    // float2 per transform
+    // padded shared-memory index of point i: one float2 per 16 (narrow plan), two per 32 (wide plan: even indices stay
+    // even, so pairs of points stay 16-byte aligned)
+    __host__ __device__ static constexpr int pidx(int i) { return WIDE ? i + 2 * (i >> 5) : sidx(i); }
+    static constexpr int SMEM_PER = WIDE ? pidx(B) + 2 : sidx(B) + 1; // float2 per transform
     static constexpr size_t SMEM_BYTES = (size_t)TPB * SMEM_PER * sizeof(float2);
     // (tried in round 1: capping at 32 registers for 8 CTAs/SM — spills made K1/K5 slower, K3 only
     // 12 % faster; left at the natural 40 registers / 6 CTAs per SM)
-    static constexpr int MIN_CTAS = 1;
+    static constexpr int MIN_CTAS = WIDE && LOGB < 14 ? 2 : 1; // B = 16384: one 139 KB transform per SM anyway
 };
 
 // radix of pass `p` for a 2^LOGB-point transform, 0 when past the last pass
 __host__ __device__ constexpr int radix_at(int logb, int p)
 {
     int n8 = logb / 3, rem = logb % 3;
+    if (logb >= 12) return p < 3 ? 16 : (p == 3 ? (logb == 12 ? 0 : (logb == 13 ? 2 : 4)) : 0); // wide plan
     if (logb == 0) return 0;
     if (logb == 1) return p == 0 ? 2 : 0;
     if (rem == 0) return p < n8 ? 8 : 0;
@@ -127,12 +139,49 @@ __device__ __forceinline__ void dft8(float2 (&v)[8])
     v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
 }
 
+// 16-point DFT as 4 x 4: n = n1 + 4 n2, k = 4 k1 + k2:  X[4 k1 + k2] = sum_n1 w4^(n1 k1) [ w16^(n1 k2) sum_n2 x[n1 + 4 n2] w4^(n2 k2) ].
+// In place; output X[r] ends up in v[(r >> 2) + 4 (r & 3)] (dft16_out).
+template <int DIR>
+__device__ __forceinline__ float2 mul_w16(float2 a, int m)
+{
+    // a * exp(DIR * 2 pi i m / 16) for the exponents that occur (m = n1 * k2: 1, 2, 3, 4, 6, 9)
+    constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    float wr = 1.f, wi = 0.f;
+    if (m == 1) { wr = c1; wi = s1; }
+    else if (m == 2) { wr = h; wi = h; }
+    else if (m == 3) { wr = s1; wi = c1; }
+    else if (m == 4) { wr = 0.f; wi = 1.f; }
+    else if (m == 6) { wr = -h; wi = h; }
+    else if (m == 9) { wr = -c1; wi = -s1; }
+    if (DIR < 0) wi = -wi;
+    return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+}
+template <int DIR>
+__device__ __forceinline__ void dft16(float2 (&v)[16])
+{
+#pragma unroll
+    for (int n1 = 0; n1 < 4; n1++) dft4<DIR>(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]); // v[n1 + 4 k2] = y[n1][k2]
+#pragma unroll
+    for (int n1 = 1; n1 < 4; n1++)
+#pragma unroll
+        for (int k2 = 1; k2 < 4; k2++) v[n1 + 4 * k2] = mul_w16<DIR>(v[n1 + 4 * k2], n1 * k2);
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) dft4<DIR>(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]); // v[k1 + 4 k2] = X[4 k1 + k2]
+}
+
 template <int R, int DIR>
 __device__ __forceinline__ void dftR(float2 (&v)[R])
 {
     if constexpr (R == 2) dft2<DIR>(v[0], v[1]);
     else if constexpr (R == 4) dft4<DIR>(v[0], v[1], v[2], v[3]);
+    else if constexpr (R == 16) dft16<DIR>(v);
     else dft8<DIR>(v);
+}
+// where output r of dftR sits in the array
+template <int R>
+__device__ __forceinline__ constexpr int dft_out(int r)
+{
+    return R == 16 ? (r >> 2) + 4 * (r & 3) : r;
 }
 
 // ---- one Stockham pass over a transform resident in shared memory ------------------------
@@ -174,12 +223,72 @@ __device__ __forceinline__ void stockham_pass(float2 *s, int tid, const float2 *
     __syncthreads();
 }
 
+// the same pass in the wide plan: a thread owns pairs of adjacent butterflies (j, j + 1), j even; every shared-memory
+// access and every twiddle load is 16 bytes
+template <int LOGB, int R, int DIR, int NS>
+__device__ __forceinline__ void stockham_pass_wide(float2 *s, int tid, const float2 *__restrict__ tw)
+{
+    using P = FftPlan<LOGB>;
+    constexpr int B = P::B, T = P::T, NP = P::E / (2 * R), Q = B / R; // butterfly pairs per thread, input stride
+    float4 v[NP][R];
+#pragma unroll
+    for (int b = 0; b < NP; b++) {
+        const int j = 2 * (tid + b * T);
+#pragma unroll
+        for (int r = 0; r < R; r++) v[b][r] = *reinterpret_cast<const float4 *>(&s[P::pidx(j + r * Q)]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NP; b++) {
+        const int j = 2 * (tid + b * T);
+        const int k = j & (NS - 1);
+        float2 a[R], c[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            a[r] = make_float2(v[b][r].x, v[b][r].y);
+            c[r] = make_float2(v[b][r].z, v[b][r].w);
+        }
+        if constexpr (NS > 1) {
+            constexpr int OFF = 2 * B + pass_tw_offset(LOGB, NS);
+#pragma unroll
+            for (int r = 1; r < R; r++) {
+                float4 w = __ldg(reinterpret_cast<const float4 *>(&tw[OFF + (r - 1) * NS + k])); // factors of (r, k), (r, k + 1)
+                if (DIR > 0) {
+                    w.y = -w.y;
+                    w.w = -w.w;
+                }
+                a[r] = cmul(a[r], make_float2(w.x, w.y));
+                c[r] = cmul(c[r], make_float2(w.z, w.w));
+            }
+        }
+        dftR<R, DIR>(a);
+        dftR<R, DIR>(c);
+        if constexpr (NS > 1) {
+            const int j0 = (j - k) * R + k;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const float2 x = a[dft_out<R>(r)], y = c[dft_out<R>(r)];
+                *reinterpret_cast<float4 *>(&s[P::pidx(j0 + r * NS)]) = make_float4(x.x, x.y, y.x, y.y);
+            }
+        } else { // first pass: a butterfly's own outputs are neighbours
+#pragma unroll
+            for (int r = 0; r < R; r += 2) {
+                const float2 x0 = a[dft_out<R>(r)], x1 = a[dft_out<R>(r + 1)], y0 = c[dft_out<R>(r)], y1 = c[dft_out<R>(r + 1)];
+                *reinterpret_cast<float4 *>(&s[P::pidx(j * R + r)]) = make_float4(x0.x, x0.y, x1.x, x1.y);
+                *reinterpret_cast<float4 *>(&s[P::pidx((j + 1) * R + r)]) = make_float4(y0.x, y0.y, y1.x, y1.y);
+            }
+        }
+    }
+    __syncthreads();
+}
+
 template <int LOGB, int DIR, int PASS, int NS>
 __device__ __forceinline__ void stockham_all(float2 *s, int tid, const float2 *__restrict__ tw, bool work = true)
 {
     constexpr int R = radix_at(LOGB, PASS);
     if constexpr (R > 0) {
-        stockham_pass<LOGB, R, DIR, NS>(s, tid, tw, work);
+        if constexpr (FftPlan<LOGB>::WIDE) stockham_pass_wide<LOGB, R, DIR, NS>(s, tid, tw);
+        else stockham_pass<LOGB, R, DIR, NS>(s, tid, tw, work);
         stockham_all<LOGB, DIR, PASS + 1, NS * R>(s, tid, tw, work);
     }
 }
@@ -193,10 +302,11 @@ __device__ __forceinline__ void stockham_all(float2 *s, int tid, const float2 *_
 template <int LOGB>
 __device__ __forceinline__ float2 rfft_split_bin(const float2 *s, int k, const float2 *__restrict__ tw)
 {
+    using P = FftPlan<LOGB>;
     constexpr int B = 1 << LOGB;
-    float2 a = s[sidx(k)];
+    float2 a = s[P::pidx(k)];
     if (k == 0) return make_float2(a.x + a.y, a.x - a.y);
-    float2 b = cconj(s[sidx(B - k)]);
+    float2 b = cconj(s[P::pidx(B - k)]);
     float2 ev = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
     float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
     float2 od = make_float2(d.y, -d.x);
@@ -224,23 +334,23 @@ __device__ __forceinline__ void irfft_presplit(float2 *s, int tid, const float2 
             if (k == 0) {
                 float2 x = s[0]; // {DC, Nyquist}
                 s[0] = make_float2(x.x + x.y, x.x - x.y);
-                float2 m = s[sidx(HALF)];
-                s[sidx(HALF)] = make_float2(2.f * m.x, -2.f * m.y);
+                float2 m = s[P::pidx(HALF)];
+                s[P::pidx(HALF)] = make_float2(2.f * m.x, -2.f * m.y);
             } else {
-                float2 p = s[sidx(k)], q = s[sidx(B - k)];
+                float2 p = s[P::pidx(k)], q = s[P::pidx(B - k)];
                 float2 w = __ldg(&tw[k]);
                 w.y = -w.y; // w^{-k}
                 // k:   (p + conj q) + i w^{-k} (p - conj q)
                 float2 sm = make_float2(p.x + q.x, p.y - q.y);
                 float2 df = make_float2(p.x - q.x, p.y + q.y);
                 float2 t = cmul(df, w);
-                s[sidx(k)] = make_float2(sm.x - t.y, sm.y + t.x);
+                s[P::pidx(k)] = make_float2(sm.x - t.y, sm.y + t.x);
                 // B-k: (q + conj p) + i w^{-(B-k)} (q - conj p),  w^{-(B-k)} = -conj(w^{-k})
                 float2 sm2 = make_float2(sm.x, -sm.y);
                 float2 df2 = make_float2(-df.x, df.y);
                 float2 w2 = make_float2(-w.x, w.y);
                 float2 t2 = cmul(df2, w2);
-                s[sidx(B - k)] = make_float2(sm2.x - t2.y, sm2.y + t2.x);
+                s[P::pidx(B - k)] = make_float2(sm2.x - t2.y, sm2.y + t2.x);
             }
         }
     }
@@ -289,8 +399,8 @@ __device__ __forceinline__ void load_block_as_complex(float2 *s, int tid, const 
                     if (4 * j2 + 1 < valid) v.y = __ldg(x + 4 * j2 + 1);
                     if (4 * j2 + 2 < valid) v.z = __ldg(x + 4 * j2 + 2);
                 }
-                s[sidx(2 * j2)] = make_float2(v.x, v.y);
-                s[sidx(2 * j2 + 1)] = make_float2(v.z, v.w);
+                s[P::pidx(2 * j2)] = make_float2(v.x, v.y);
+                s[P::pidx(2 * j2 + 1)] = make_float2(v.z, v.w);
             }
             return;
         }
@@ -302,7 +412,7 @@ __device__ __forceinline__ void load_block_as_complex(float2 *s, int tid, const 
         float2 z = make_float2(0.f, 0.f);
         if (2 * j < valid) z.x = __ldg(x + 2 * j);
         if (2 * j + 1 < valid) z.y = __ldg(x + 2 * j + 1);
-        s[sidx(j)] = z;
+        s[P::pidx(j)] = z;
     }
 }
 
@@ -341,11 +451,20 @@ k_rfft_forward(const float *__restrict__ src, long long src_stride, int len, flo
     // split: X[k] = Ev + w^k Od, Ev = (Z[k] + conj Z[B-k])/2, Od = (Z[k] - conj Z[B-k])/(2i)
     if (live) {
         float2 *row = dst + c * dst_stride + (long long)i * B;
+        if constexpr (P::WIDE) { // two bins per 16-byte store
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-            int k = tid + e * T;
-            float2 out = rfft_split_bin<LOGB>(s, k, tw);
-            row[k] = out;
+            for (int e = 0; e < E / 2; e++) {
+                const int k = 2 * (tid + e * T);
+                const float2 o0 = rfft_split_bin<LOGB>(s, k, tw), o1 = rfft_split_bin<LOGB>(s, k + 1, tw);
+                *reinterpret_cast<float4 *>(row + k) = make_float4(o0.x, o0.y, o1.x, o1.y);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                int k = tid + e * T;
+                float2 out = rfft_split_bin<LOGB>(s, k, tw);
+                row[k] = out;
+            }
         }
     }
 }
@@ -431,6 +550,44 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
     }
 
     // 1. conv, packed layout (bin 0 = {DC, Nyquist}: two real products)
+    if constexpr (P::WIDE) {
+        if (a.gather_n == 0 && a.ir0) {
+            // wide plan, plain case: two bins per 16-byte load, four loads of each array in flight per thread — with 32
+            // points per thread and two CTAs per SM the latency has to be covered by loads in flight, not by warps
+            const float4 *xr = reinterpret_cast<const float4 *>(a.ring_cur + c * a.ring_stride);
+            const float4 *hr = reinterpret_cast<const float4 *>(a.ir0 + (a.ir_div ? c / a.ir_div : c) * a.ir_stride);
+            const float4 *pr4 = reinterpret_cast<const float4 *>(a.premul + c * B);
+            constexpr int U = 4;
+#pragma unroll
+            for (int e0 = 0; e0 < E / 2; e0 += U) {
+                float4 x[U], h[U], q[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int k2 = tid + (e0 + u) * T; // bins 2*k2, 2*k2 + 1
+                    x[u] = live ? xr[k2] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    h[u] = live ? __ldg(hr + k2) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    q[u] = live ? pr4[k2] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int k2 = tid + (e0 + u) * T;
+                    float r0, i0;
+                    if (k2 == 0) {
+                        r0 = __fmul_rn(x[u].x, h[u].x);
+                        i0 = __fmul_rn(x[u].y, h[u].y);
+                    } else {
+                        r0 = __fsub_rn(__fmul_rn(x[u].x, h[u].x), __fmul_rn(x[u].y, h[u].y));
+                        i0 = __fadd_rn(__fmul_rn(x[u].x, h[u].y), __fmul_rn(x[u].y, h[u].x));
+                    }
+                    const float r1 = __fsub_rn(__fmul_rn(x[u].z, h[u].z), __fmul_rn(x[u].w, h[u].w));
+                    const float i1 = __fadd_rn(__fmul_rn(x[u].z, h[u].w), __fmul_rn(x[u].w, h[u].z));
+                    *reinterpret_cast<float4 *>(&s[P::pidx(2 * k2)]) =
+                        make_float4(__fadd_rn(q[u].x, r0), __fadd_rn(q[u].y, i0), __fadd_rn(q[u].z, r1), __fadd_rn(q[u].w, i1));
+                }
+            }
+            goto conv_done;
+        }
+    }
 #pragma unroll
     for (int e = 0; e < E; e++) {
         int k = tid + e * T;
@@ -458,8 +615,9 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
             }
             v = make_float2(__fadd_rn(p.x, pr), __fadd_rn(p.y, pi));
         }
-        s[sidx(k)] = v;
+        s[P::pidx(k)] = v;
     }
+conv_done:
     __syncthreads();
 
     // 2. pre-split, in place on pairs (k, B-k)
@@ -476,7 +634,7 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 int j = tid + e * T;
-                float2 z = s[sidx(j)];
+                float2 z = s[P::pidx(j)];
                 *reinterpret_cast<float2 *>(a.raw_out + c * 2 * B + 2 * j) = make_float2(z.x * inv_n, z.y * inv_n);
             }
         }
@@ -487,19 +645,16 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
     const bool vec = E >= 2 && B >= 4 && a.fill == 0 && a.n == B && a.block_complete && !a.epi.add0 && !a.epi.add1 && !a.epi.mix_other &&
                      (a.out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
     if (vec) {
-        float4 nov[E >= 2 ? E / 2 : 1];
         if (live) {
 #pragma unroll
             for (int e = 0; e < E / 2; e++) {
                 const int j2 = tid + e * T; // samples 4*j2 .. 4*j2 + 3 of the 2B-sample result
-                const float2 z0 = s[sidx(2 * j2)], z1 = s[sidx(2 * j2 + 1)];
-                const float4 y = make_float4(z0.x * inv_n, z0.y * inv_n, z1.x * inv_n, z1.y * inv_n);
                 if (4 * j2 < B) {
+                    const float2 z0 = s[P::pidx(2 * j2)], z1 = s[P::pidx(2 * j2 + 1)];
+                    const float4 y = make_float4(z0.x * inv_n, z0.y * inv_n, z1.x * inv_n, z1.y * inv_n);
                     const float4 ov = *reinterpret_cast<const float4 *>(a.overlap + c * B + 4 * j2);
                     *reinterpret_cast<float4 *>(a.out + c * a.out_stride + 4 * j2) =
                         make_float4(__fadd_rn(y.x, ov.x), __fadd_rn(y.y, ov.y), __fadd_rn(y.z, ov.z), __fadd_rn(y.w, ov.w));
-                } else {
-                    nov[e] = y;
                 }
             }
         }
@@ -508,7 +663,11 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
 #pragma unroll
             for (int e = 0; e < E / 2; e++) {
                 const int j2 = tid + e * T;
-                if (4 * j2 >= B) *reinterpret_cast<float4 *>(a.overlap + c * B + (4 * j2 - B)) = nov[e];
+                if (4 * j2 >= B) { // second half of the result (still in shared memory) -> the new overlap
+                    const float2 z0 = s[P::pidx(2 * j2)], z1 = s[P::pidx(2 * j2 + 1)];
+                    *reinterpret_cast<float4 *>(a.overlap + c * B + (4 * j2 - B)) =
+                        make_float4(z0.x * inv_n, z0.y * inv_n, z1.x * inv_n, z1.y * inv_n);
+                }
             }
         }
         return;
@@ -518,7 +677,7 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
     for (int e = 0; e < E; e++) {
         int j = tid + e * T;
         if (!live || 2 * j >= B) continue;
-        float2 z = s[sidx(j)];
+        float2 z = s[P::pidx(j)];
         float y[2] = {z.x * inv_n, z.y * inv_n};
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -540,7 +699,7 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
             if (B == 1) {
                 a.overlap[c] = s[0].y * inv_n; // y[1]
             } else if (2 * j >= B) {
-                float2 z = s[sidx(j)];
+                float2 z = s[P::pidx(j)];
                 *reinterpret_cast<float2 *>(a.overlap + c * B + (2 * j - B)) = make_float2(z.x * inv_n, z.y * inv_n);
             }
         }
