@@ -7,7 +7,7 @@ set -e
 mkdir -p gpurun_out
 CMD="python bench.py --steps 3 --warmup 3 --realtime 0 --no-cpu-baseline"
 $CMD > gpurun_out/traffic_plain.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_block_fused -s 12 -c 2 -f -o gpurun_out/r02_fused $CMD > gpurun_out/traffic_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_block_fused -s 100 -c 2 -f -o gpurun_out/r02_fused $CMD > gpurun_out/traffic_ncu.log 2>&1
 ncu -i gpurun_out/r02_fused.ncu-rep --page raw --csv > gpurun_out/r02_fused_raw.csv
 python - <<'PY'
 import csv, json, sys
@@ -27,3 +27,4 @@ out = {"kernel": rows[2][hdr.index('Kernel Name')], "channels": 4096, "dram_byte
 json.dump(out, open('gpurun_out/fused_traffic.json', 'w'), indent=1)
 print(json.dumps(out))
 PY
+rm -f gpurun_out/r02_fused.ncu-rep gpurun_out/r02_fused_raw.csv  # gpurun brings back at most 64 MiB
