@@ -289,17 +289,26 @@ static int launch_mac_t(const MacArgs &a, cudaStream_t st)
 template <int LOGB>
 static int launch_block_fused_shared(const fcb_engine *e, cudaStream_t st, FusedArgs fa, size_t nc);
 
-// Small batches (fewer channel groups than the machine has CTA slots): how many CTAs share one delay line.
-// Aim at ~3 CTAs per SM over the whole grid, at least two pipeline stages of `rows` segments per CTA; slices are whole
-// stages.  Returns zsplit = 1 when the split does not apply.
+// Small batches: how many CTAs share one delay line (SplitArgs).  Measured on the B200 (scripts/r02_split_sweep.py,
+// 2 s responses, block 512): with fewer channel groups than SMs the split wins by 2x and more (mono: 48 -> 20 us per block);
+// at 256 groups it LOSES (0.065 -> 0.076 ms: a full first wave already streams, the partial sums are pure overhead); at 512
+// groups — one wave that starts and ends in step, so every CTA is in its FFT phase at the same time — three slices per line
+// de-synchronise the phases and win 9 % (0.137 -> 0.125 ms).  Hence: groups <= 148 fill the 4 x 148 CTA slots in whole
+// waves; 296 < groups <= 592 take three slices; everything else runs unsplit.  At least two pipeline stages per CTA,
+// slices are whole stages.  Returns zsplit = 1 when the split does not apply.
 static constexpr size_t kSplitTargetCtas = 4 * 148; // CTA slots of the whole-block kernels (4 per SM at 54 KB each)
+static std::atomic<int> g_split_slots{(int)kSplitTargetCtas}; // fcb_tune("split_slots"): CTAs the split aims at (sweeps)
 static SplitArgs split_plan(const fcb_engine *e, size_t groups, int seg_lo, int seg_hi, int rows)
 {
     SplitArgs sp{};
     sp.zsplit = 1;
     const int nseg = seg_hi - seg_lo;
-    if (!g_split.load() || !e->zpart || groups == 0 || groups * 2 > kSplitTargetCtas || nseg < 4 * rows) return sp;
-    size_t z = kSplitTargetCtas / groups; // whole waves only: never a nearly empty second round
+    const size_t slots = (size_t)g_split_slots.load();
+    if (!g_split.load() || !e->zpart || groups == 0 || nseg < 4 * rows) return sp;
+    size_t z = 1;
+    if (groups <= slots / 4) z = slots / groups; // whole waves only: never a nearly empty second round
+    else if (groups > slots / 2 && groups <= slots) z = 3;
+    else return sp;
     const size_t zmax = (size_t)nseg / (2 * (size_t)rows);
     if (z > zmax) z = zmax;
     if (z < 2) return sp;
@@ -648,6 +657,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "fused_short") && value >= 0) g_fused_short = value;
     else if (!strcmp(key, "fused_pair")) g_fused_pair = value != 0;
     else if (!strcmp(key, "split")) g_split = value != 0;
+    else if (!strcmp(key, "split_slots") && value >= 1) g_split_slots = value;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
     else if (!strcmp(key, "tma_io")) g_tma_io = value != 0;
     else if (!strcmp(key, "mapped_io")) fcb_host_mirror_set_mapped_io(value);
@@ -727,8 +737,8 @@ static int engine_prepare_process(fcb_engine *e)
     if (nb >= 2 && e->logb >= 2) FCB_TRY(mb_ensure(e, nb));
     if (e->logb >= 5 && e->logb <= 9) { // whole-block kernels: split buffers for small batches
         const size_t groups = (e->C + (512 >> e->logb) - 1) / (512 >> e->logb);
-        if (groups * 2 <= kSplitTargetCtas) {
-            e->zslices = kSplitTargetCtas + groups;
+        if (groups <= 2 * kSplitTargetCtas) {
+            e->zslices = 3 * kSplitTargetCtas + groups;
             FCB_TRY(alloc_zero((void **)&e->zpart, e->zslices * 2 * 256 * sizeof(float4), e->stream));
             FCB_TRY(alloc_zero((void **)&e->zcount, groups * sizeof(unsigned int), e->stream));
         }
