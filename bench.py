@@ -433,6 +433,8 @@ def run_b200(args) -> None:
         _lib.check(lib.fcb_tune(b"zero_copy", args.zero_copy))
     if args.fused_stages is not None:
         _lib.check(lib.fcb_tune(b"fused_stages", args.fused_stages))
+    if args.k1_late is not None:
+        _lib.check(lib.fcb_tune(b"k1_late", args.k1_late))
 
     Cn, B = args.channels, args.block
     L = int(args.ir_seconds * SAMPLE_RATE)
@@ -661,6 +663,7 @@ def main():
     ap.add_argument("--fused-stages", type=int, default=None)
     ap.add_argument("--zero-copy", type=int, default=None)
     ap.add_argument("--tma-io", type=int, default=None)
+    ap.add_argument("--k1-late", type=int, default=None, help="0: forward FFT before the MAC stream even when the block comes from host memory")
     ap.add_argument("--fused", type=int, default=1, help="1: one fused K1+K2+K3 kernel per block (default), 0: three launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--realtime", type=int, default=1, help="1: also run the measured real-time block (12 500 channels and the largest fitting count)")

@@ -74,6 +74,9 @@ struct fcb_engine {
     const float2 *tw = nullptr;
     // background IR update (fcb_engine_update_reserve): K5 writes `ir_shadow` on `upd_stream` while the blocks keep
     // reading `ir`; fcb_engine_update_commit swaps the two pointers
+    // where the caller's input block lives, remembered per pointer (a driver query per launch would cost the small batches)
+    mutable const void *io_probe_ptr = nullptr;
+    mutable bool io_probe_host = false;
     // small batches: partial sums and arrival counters of the split whole-block kernels (fused_kernel.cuh SplitArgs)
     float4 *zpart = nullptr;
     unsigned int *zcount = nullptr;
@@ -323,6 +326,20 @@ static SplitArgs split_plan(const fcb_engine *e, size_t groups, int seg_lo, int 
     return sp;
 }
 
+// fcb_tune("k1_late", 1): K1 after the MAC stream when the input block sits in host memory, so that the PCIe pull issued at
+// the top of the kernel has the whole stream to land.  Measured on 8 GPUs (profiles/r02_e2e_8gpu_k1_late.jsonl): no
+// effect on the end-to-end step (0.98-1.02 ms either way) — the pull is not what the 8-GPU host path pays for.  Off.
+static std::atomic<bool> g_k1_late{false};
+static bool input_is_host_memory(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 // block I/O eligible for one bulk copy per channel: 16-byte aligned rows
 static bool tma_io_ok(const float *in, size_t in_stride, const float *out, size_t out_stride, size_t B)
 {
@@ -371,6 +388,11 @@ static int launch_block_fused(const fcb_engine *e, cudaStream_t st, size_t c0, s
     const unsigned grid = (unsigned)(groups * (size_t)fa.split.zsplit);
     if (g_tma_io.load() && tma_io_ok(fa.in, in_stride, fa.ifft.out, out_stride, e->B)) {
         static SmemOptIn optin_io;
+        if (e->io_probe_ptr != (const void *)in_dev) {
+            e->io_probe_ptr = (const void *)in_dev;
+            e->io_probe_host = input_is_host_memory(in_dev);
+        }
+        fa.k1_late = g_k1_late.load() && e->io_probe_host ? 1 : 0;
         FCB_TRY(optin_io.ensure(k_block_fused<LOGB, NST, ROWS, true>, Cfg::smem_bytes(NST, true)));
         k_block_fused<LOGB, NST, ROWS, true><<<grid, 256, Cfg::smem_bytes(NST, true), st>>>(fa, e->tw);
     } else {
@@ -657,6 +679,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "fused_short") && value >= 0) g_fused_short = value;
     else if (!strcmp(key, "fused_pair")) g_fused_pair = value != 0;
     else if (!strcmp(key, "split")) g_split = value != 0;
+    else if (!strcmp(key, "k1_late")) g_k1_late = value != 0;
     else if (!strcmp(key, "split_slots") && value >= 1) g_split_slots = value;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
     else if (!strcmp(key, "tma_io")) g_tma_io = value != 0;

@@ -32,6 +32,7 @@ struct FusedArgs {
     MacArgs mac;          // ir / ring / strides / current / active / nchan (premul unused)
     IfftArgs ifft;        // overlap / out / out_stride / epilogue (fill = 0, n = B, complete)
     SplitArgs split;
+    int k1_late;          // TMA_IO only: run K1 after the MAC stream (the input block is still crossing PCIe)
 };
 
 // publish this CTA's partial accumulator(s); returns true in the one CTA of the group that arrives last
@@ -176,45 +177,53 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
     if (mlive) h0 = __ldg(reinterpret_cast<const float4 *>(a.ir + a.ir_chan(c0 + ty) * a.ir_stride + (long long)(0 - a.ir_seg0) * B) + tx);
 
     // ---- K1: forward real FFT of the new block (src/fft_convolver.rs:234-241) -------------------
+    // K2 below only reads ring slots OLDER than the current block, so K1 may run before or after it.  Before is the
+    // default (its latency hides under the first stages' flight).  With the block still crossing PCIe (zero-copy on
+    // pinned host buffers, fa.k1_late) K1 runs AFTER the MAC stream: the pull that was issued at the top of the kernel has
+    // the whole stream to land instead of stalling every CTA at its start.
     float2 *fs = fbuf + (fwork ? fslot : 0) * Cfg::FFT_PER;
     bool flive = fwork && fslot < nlive;
-    if (TMA_IO && k1) mbar_wait(in_bar, 0);
-    if (fwork) {
-        const float *x = TMA_IO ? in_s + fslot * B : fa.in + (c0 + fslot) * fa.in_stride;
-        if (TMA_IO) {
+    auto k1_stage = [&]() {
+        if (TMA_IO && k1) mbar_wait(in_bar, 0);
+        if (fwork) {
+            const float *x = TMA_IO ? in_s + fslot * B : fa.in + (c0 + fslot) * fa.in_stride;
+            if (TMA_IO) {
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    int j = flane + e * T;
+                    float2 z = make_float2(0.f, 0.f);
+                    if (flive && 2 * j + 1 < B) z = *reinterpret_cast<const float2 *>(x + 2 * j);
+                    fs[sidx(j)] = z;
+                }
+            } else {
+                load_block_as_complex<LOGB>(fs, flane, x, flive ? B : 0); // 16-byte loads when the row is aligned
+            }
+        }
+        __syncthreads();
+        stockham_all<LOGB, -1, 0, 1>(fs, flane, tw, fwork);
+        // split -> packed spectrum; written to ring[current] and kept in shared memory for segment 0
+        float2 xk[E];
+        if (fwork) {
 #pragma unroll
             for (int e = 0; e < E; e++) {
-                int j = flane + e * T;
-                float2 z = make_float2(0.f, 0.f);
-                if (flive && 2 * j + 1 < B) z = *reinterpret_cast<const float2 *>(x + 2 * j);
-                fs[sidx(j)] = z;
+                int k = flane + e * T;
+                xk[e] = rfft_split_bin<LOGB>(fs, k, tw);
             }
-        } else {
-            load_block_as_complex<LOGB>(fs, flane, x, flive ? B : 0); // 16-byte loads when the row is aligned
         }
-    }
-    __syncthreads();
-    stockham_all<LOGB, -1, 0, 1>(fs, flane, tw, fwork);
-    // split -> packed spectrum; written to ring[current] and kept in shared memory for segment 0
-    float2 xk[E];
-    if (fwork) {
+        __syncthreads(); // every Z[k], Z[B-k] has been read
+        if (fwork) {
+            float2 *row = flive ? const_cast<float2 *>(a.ring) + a.ring_chan(c0 + fslot) * a.ring_stride + (long long)cur * B : nullptr;
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-            int k = flane + e * T;
-            xk[e] = rfft_split_bin<LOGB>(fs, k, tw);
+            for (int e = 0; e < E; e++) {
+                int k = flane + e * T;
+                fs[k] = xk[e]; // unpadded packed row: the MAC threads read it as float4
+                if (flive) row[k] = xk[e];
+            }
         }
-    }
-    __syncthreads(); // every Z[k], Z[B-k] has been read
-    if (fwork) {
-        float2 *row = flive ? const_cast<float2 *>(a.ring) + a.ring_chan(c0 + fslot) * a.ring_stride + (long long)cur * B : nullptr;
-#pragma unroll
-        for (int e = 0; e < E; e++) {
-            int k = flane + e * T;
-            fs[k] = xk[e]; // unpadded packed row: the MAC threads read it as float4
-            if (flive) row[k] = xk[e];
-        }
-    }
-    __syncthreads();
+        __syncthreads();
+    };
+    const bool k1_late = TMA_IO && fa.k1_late != 0;
+    if (!k1_late) k1_stage();
 
     // ---- K2: delay-line MAC over segments lo..hi-1 (src/fft_convolver.rs:244-255) ---------------
     const bool packed = (tx == 0);
@@ -250,6 +259,8 @@ k_block_fused(FusedArgs fa, const float2 *__restrict__ tw)
         __syncthreads();
         if (tid == 0 && it + NST < niter) issue(it + NST);
     }
+
+    if (k1_late) k1_stage();
 
     // ---- small batches: the delay line was cut over Z CTAs; the last one to arrive finishes the block ----
     bool fwork3 = fwork;
