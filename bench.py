@@ -596,13 +596,19 @@ def run_b200(args) -> None:
         conv.close()
         del d_in, d_out
         torch.cuda.empty_cache()
-        realtime = run_realtime(F, lib, local, rank, world, chan0, Cn, e2e_ms_max / args.steps, B, L, args.realtime_blocks, barrier)
+        try:  # an optional block must never cost the headline line
+            realtime = run_realtime(F, lib, local, rank, world, chan0, Cn, e2e_ms_max / args.steps, B, L, args.realtime_blocks, barrier)
+        except Exception as exc:  # e.g. another tenant holding HBM: report, do not die
+            realtime = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     mimo = None
     if world > 1 and args.mimo:
         if conv._h:
             conv.close()
         torch.cuda.empty_cache()
-        mimo = run_mimo(local, rank, world, 200, 20)
+        try:
+            mimo = run_mimo(local, rank, world, 200, 20)
+        except Exception as exc:
+            mimo = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank == 0:
         cpu_baseline = None
