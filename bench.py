@@ -552,7 +552,19 @@ def run_b200(args) -> None:
     launches += lib.fcb_launch_count() - launches_e0
     barrier()
 
-    ms_max, e2e_ms_max = reduce_max([ms, e2e_s * 1000.0], device=f"cuda:{local}")
+    # ---- where the end-to-end overhead sits: the same synchronous call pattern on DEVICE buffers (launch + kernel + host
+    # sync per step, no PCIe data): the difference to `ms_per_step` is the host's launch/sync cost, the rest of the e2e gap is
+    # the data path
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_dev(i)
+        conv.sync()
+    sync_s = time.perf_counter() - t0
+    launches += args.steps
+    barrier()
+
+    ms_max, e2e_ms_max, sync_ms_max = reduce_max([ms, e2e_s * 1000.0, sync_s * 1000.0], device=f"cuda:{local}")
     value = aggregate_value(world, Cn, args.steps, B, ms_max)
     e2e_value = aggregate_value(world, Cn, args.steps, B, e2e_ms_max)
 
@@ -633,6 +645,7 @@ def run_b200(args) -> None:
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "ms_per_step": e2e_ms_max / args.steps,
+                    "ms_per_step_same_calls_on_device_buffers": sync_ms_max / args.steps,
                     "path": "fcb_fftconv_process on pinned host buffers: the whole-block kernel pulls each channel's input "
                             "block from host memory and pushes its output block back with cp.async.bulk (one launch per step)"
                             if (fused and args.zero_copy != 0 and args.tma_io != 0) else
