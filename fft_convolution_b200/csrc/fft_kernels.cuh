@@ -416,6 +416,84 @@ __device__ __forceinline__ void load_block_as_complex(float2 *s, int tid, const 
     }
 }
 
+// ---- wide plan, forward direction: the two ends of the transform without a trip through shared memory ----------
+// First Stockham pass (Ns = 1, no twiddles) straight from global memory: butterflies (j, j + 1) read z[j + r Q], z[j + 1 + r Q]
+// = four consecutive samples x'[2 (j + r Q) ..], one 16-byte load; inputs past B / 2 are the zero padding of the block
+// (src/fft_convolver.rs:56-60) and cost nothing.  Saves the store + load of the whole input (128 KB per 16384-point transform).
+template <int LOGB>
+__device__ __forceinline__ void stockham_pass0_from_global(float2 *s, int tid, const float *__restrict__ x, int valid)
+{
+    using P = FftPlan<LOGB>;
+    constexpr int B = P::B, R = 16, Q = B / R;
+    static_assert(P::WIDE && P::E == 2 * R, "one pair of radix-16 butterflies per thread");
+    const int j = 2 * tid;
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    float2 a[R], c[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < R / 2) { // points j + r Q < B / 2: real samples; the rest is zero padding
+            const int n0 = 2 * (j + r * Q);
+            if (aligned && n0 + 3 < valid) {
+                v = __ldg(reinterpret_cast<const float4 *>(x + n0));
+            } else {
+                if (n0 < valid) v.x = __ldg(x + n0);
+                if (n0 + 1 < valid) v.y = __ldg(x + n0 + 1);
+                if (n0 + 2 < valid) v.z = __ldg(x + n0 + 2);
+                if (n0 + 3 < valid) v.w = __ldg(x + n0 + 3);
+            }
+        }
+        a[r] = make_float2(v.x, v.y);
+        c[r] = make_float2(v.z, v.w);
+    }
+    dft16<-1>(a);
+    dft16<-1>(c);
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+        const float2 x0 = a[dft_out<R>(r)], x1 = a[dft_out<R>(r + 1)], y0 = c[dft_out<R>(r)], y1 = c[dft_out<R>(r + 1)];
+        *reinterpret_cast<float4 *>(&s[P::pidx(j * R + r)]) = make_float4(x0.x, x0.y, x1.x, x1.y);
+        *reinterpret_cast<float4 *>(&s[P::pidx((j + 1) * R + r)]) = make_float4(y0.x, y0.y, y1.x, y1.y);
+    }
+    __syncthreads();
+}
+
+// B = 8192: the last pass is radix 2 (Z[k] = u[k] + W^k u[k + B/2], Z[k + B/2] = u[k] - W^k u[k + B/2], W = exp(-2 pi i / B)).
+// The real-FFT split of bins k and B - k needs exactly Z[k] and Z[B - k]: both come from four points of u, so the pass and
+// the split run as one step from shared memory straight to the spectrum row — no store + load of Z (256 KB per transform).
+template <int LOGB>
+__device__ __forceinline__ void radix2_split_to_global(const float2 *s, int tid, const float2 *__restrict__ tw, float2 *__restrict__ row)
+{
+    using P = FftPlan<LOGB>;
+    constexpr int B = P::B, T = P::T, H = B / 2;
+    constexpr int OFF = 2 * B + pass_tw_offset(LOGB, H); // pass-ordered twiddles of the radix-2 pass: W^k at [OFF + k]
+    auto split = [](float2 zk, float2 zm, float2 w) { // X[k] from Z[k], Z[B - k] and w = exp(-2 pi i k / 2B)
+        const float2 b = cconj(zm);
+        const float2 ev = make_float2(0.5f * (zk.x + b.x), 0.5f * (zk.y + b.y));
+        const float2 d = make_float2(0.5f * (zk.x - b.x), 0.5f * (zk.y - b.y));
+        return cadd(ev, cmul(make_float2(d.y, -d.x), w));
+    };
+#pragma unroll
+    for (int e = 0; e < H / T; e++) {
+        const int k = tid + e * T; // 0 .. B/2 - 1
+        const float2 u0 = s[P::pidx(k)], u1 = s[P::pidx(k + H)];
+        if (k == 0) {
+            const float2 z0 = cadd(u0, u1), zh = csub(u0, u1);        // Z[0], Z[B/2]
+            row[0] = make_float2(z0.x + z0.y, z0.x - z0.y);          // packed {DC, Nyquist}
+            row[H] = split(zh, zh, __ldg(&tw[H]));                   // bin B/2 is its own mirror
+        } else {
+            const int m = H - k;
+            const float2 v0 = s[P::pidx(m)], v1 = s[P::pidx(m + H)];
+            const float2 wk = __ldg(&tw[OFF + k]);
+            const float2 wm = make_float2(-wk.x, wk.y);              // W^(B/2 - k) = -conj(W^k)
+            const float2 zk = cadd(u0, cmul(u1, wk));                // Z[k]
+            const float2 zm = csub(v0, cmul(v1, wm));                // Z[B - k] = Z[(B/2 - k) + B/2]
+            const float2 tk = __ldg(&tw[k]);
+            row[k] = split(zk, zm, tk);
+            row[B - k] = split(zm, zk, make_float2(-tk.x, tk.y));    // exp(-2 pi i (B - k) / 2B) = -conj(exp(-2 pi i k / 2B))
+        }
+    }
+}
+
 // ========================================================================================
 // K1 / K5: batched forward real FFT.
 // transform q -> (channel c = q / nseg, segment i = q % nseg); source = src + c*src_stride + i*B,
@@ -444,9 +522,21 @@ k_rfft_forward(const float *__restrict__ src, long long src_stride, int len, flo
     if (!live) valid = 0;
 
     // z[j] = x'[2j] + i x'[2j+1], x' = [x[0..valid) | zeros]
-    load_block_as_complex<LOGB>(s, tid, x, valid);
-    __syncthreads();
-    stockham_all<LOGB, -1, 0, 1>(s, tid, tw);
+    if constexpr (P::WIDE) {
+        stockham_pass0_from_global<LOGB>(s, tid, x, valid);
+        if constexpr (LOGB == 13) {
+            stockham_pass_wide<LOGB, 16, -1, 16>(s, tid, tw);
+            stockham_pass_wide<LOGB, 16, -1, 256>(s, tid, tw);
+            if (live) radix2_split_to_global<LOGB>(s, tid, tw, dst + c * dst_stride + (long long)i * B);
+            return;
+        } else {
+            stockham_all<LOGB, -1, 1, 16>(s, tid, tw);
+        }
+    } else {
+        load_block_as_complex<LOGB>(s, tid, x, valid);
+        __syncthreads();
+        stockham_all<LOGB, -1, 0, 1>(s, tid, tw);
+    }
 
     // split: X[k] = Ev + w^k Od, Ev = (Z[k] + conj Z[B-k])/2, Od = (Z[k] - conj Z[B-k])/(2i)
     if (live) {
