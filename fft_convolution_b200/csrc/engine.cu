@@ -301,6 +301,7 @@ static int launch_block_fused_shared(const fcb_engine *e, cudaStream_t st, Fused
 // slices are whole stages.  Returns zsplit = 1 when the split does not apply.
 static constexpr size_t kSplitTargetCtas = 4 * 148; // CTA slots of the whole-block kernels (4 per SM at 54 KB each)
 static std::atomic<int> g_split_slots{(int)kSplitTargetCtas}; // fcb_tune("split_slots"): CTAs the split aims at (sweeps)
+static std::atomic<int> g_split_min_stages{2};                 // fcb_tune("split_min_stages"): pipeline stages per CTA at least
 static SplitArgs split_plan(const fcb_engine *e, size_t groups, int seg_lo, int seg_hi, int rows)
 {
     SplitArgs sp{};
@@ -312,7 +313,7 @@ static SplitArgs split_plan(const fcb_engine *e, size_t groups, int seg_lo, int 
     if (groups <= slots / 4) z = slots / groups; // whole waves only: never a nearly empty second round
     else if (groups > slots / 2 && groups <= slots) z = 3;
     else return sp;
-    const size_t zmax = (size_t)nseg / (2 * (size_t)rows);
+    const size_t zmax = (size_t)nseg / ((size_t)g_split_min_stages.load() * (size_t)rows);
     if (z > zmax) z = zmax;
     if (z < 2) return sp;
     int zlen = (int)((nseg + z - 1) / z);
@@ -681,6 +682,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "split")) g_split = value != 0;
     else if (!strcmp(key, "k1_late")) g_k1_late = value != 0;
     else if (!strcmp(key, "split_slots") && value >= 1) g_split_slots = value;
+    else if (!strcmp(key, "split_min_stages") && value >= 1) g_split_min_stages = value;
     else if (!strcmp(key, "shared_reuse")) g_shared_reuse = value != 0;
     else if (!strcmp(key, "tma_io")) g_tma_io = value != 0;
     else if (!strcmp(key, "mapped_io")) fcb_host_mirror_set_mapped_io(value);

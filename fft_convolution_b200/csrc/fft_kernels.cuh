@@ -65,7 +65,10 @@ struct FftPlan {
     static constexpr size_t SMEM_BYTES = (size_t)TPB * SMEM_PER * sizeof(float2);
     // (tried in round 1: capping at 32 registers for 8 CTAs/SM — spills made K1/K5 slower, K3 only
     // 12 % faster; left at the natural 40 registers / 6 CTAs per SM)
-    static constexpr int MIN_CTAS = WIDE && LOGB < 14 ? 2 : 1; // B = 16384: one 139 KB transform per SM anyway
+#ifndef FCB_WIDE_MIN_CTAS
+#define FCB_WIDE_MIN_CTAS 2
+#endif
+    static constexpr int MIN_CTAS = WIDE && LOGB < 14 ? FCB_WIDE_MIN_CTAS : 1; // B = 16384: one 139 KB transform per SM anyway
 };
 
 // radix of pass `p` for a 2^LOGB-point transform, 0 when past the last pass
@@ -715,10 +718,44 @@ conv_done:
     __syncthreads();
 
     // 3. unnormalised inverse complex FFT
+    const float inv_n = 1.0f / (float)(2 * B);
+    if constexpr (LOGB == 13) {
+        // B = 8192, whole block, plain overlap-add: the last pass is a radix 2 — y[k] = u[k] + conj(W^k) u[k + B/2] is sample
+        // pair (2k, 2k+1) of the FIRST half of the result, y[k + B/2] = u[k] - ... the same pair of the SECOND half — so it
+        // is folded into the overlap-add: a thread adds the old overlap to the first-half samples and writes the
+        // second-half samples over the very overlap samples it has just read (no barrier, no store + load of y: 256 KB of
+        // shared-memory traffic per transform less)
+        const bool whole = !a.raw_out && a.fill == 0 && a.n == B && a.block_complete && !a.epi.add0 && !a.epi.add1 && !a.epi.mix_other &&
+                           (a.out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+        if (whole) {
+            constexpr int H = B / 2, OFF = 2 * B + pass_tw_offset(LOGB, H);
+            stockham_pass_wide<LOGB, 16, +1, 1>(s, tid, tw);
+            stockham_pass_wide<LOGB, 16, +1, 16>(s, tid, tw);
+            stockham_pass_wide<LOGB, 16, +1, 256>(s, tid, tw);
+            if (live) {
+#pragma unroll
+                for (int e = 0; e < H / 2 / T; e++) {
+                    const int k = 2 * (tid + e * T); // points k, k + 1 and their partners k + H, k + 1 + H
+                    const float4 u0 = *reinterpret_cast<const float4 *>(&s[P::pidx(k)]);
+                    const float4 u1 = *reinterpret_cast<const float4 *>(&s[P::pidx(k + H)]);
+                    const float4 w = __ldg(reinterpret_cast<const float4 *>(&tw[OFF + k]));
+                    const float2 t0 = cmul(make_float2(u1.x, u1.y), make_float2(w.x, -w.y));
+                    const float2 t1 = cmul(make_float2(u1.z, u1.w), make_float2(w.z, -w.w));
+                    float *ov = a.overlap + c * B + 2 * k;
+                    const float4 old = *reinterpret_cast<const float4 *>(ov);
+                    *reinterpret_cast<float4 *>(a.out + c * a.out_stride + 2 * k) =
+                        make_float4(__fadd_rn((u0.x + t0.x) * inv_n, old.x), __fadd_rn((u0.y + t0.y) * inv_n, old.y),
+                                    __fadd_rn((u0.z + t1.x) * inv_n, old.z), __fadd_rn((u0.w + t1.y) * inv_n, old.w));
+                    *reinterpret_cast<float4 *>(ov) =
+                        make_float4((u0.x - t0.x) * inv_n, (u0.y - t0.y) * inv_n, (u0.z - t1.x) * inv_n, (u0.w - t1.y) * inv_n);
+                }
+            }
+            return;
+        }
+    }
     stockham_all<LOGB, +1, 0, 1>(s, tid, tw);
 
     // 4. epilogue.  y[2j] = Re z[j] / N, y[2j+1] = Im z[j] / N (N = 2B: exact scaling).
-    const float inv_n = 1.0f / (float)(2 * B);
     if (a.raw_out) {
         if (live) {
 #pragma unroll
