@@ -643,6 +643,7 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
     }
 
     // 1. conv, packed layout (bin 0 = {DC, Nyquist}: two real products)
+    bool conv_done = false;
     if constexpr (P::WIDE) {
         if (a.gather_n == 0 && a.ir0) {
             // wide plan, plain case: two bins per 16-byte load, four loads of each array in flight per thread — with 32
@@ -678,11 +679,12 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
                         make_float4(__fadd_rn(q[u].x, r0), __fadd_rn(q[u].y, i0), __fadd_rn(q[u].z, r1), __fadd_rn(q[u].w, i1));
                 }
             }
-            goto conv_done;
+            conv_done = true;
         }
     }
 #pragma unroll
     for (int e = 0; e < E; e++) {
+        if (conv_done) break;
         int k = tid + e * T;
         float2 v = make_float2(0.f, 0.f);
         if (live && a.gather_n > 0) {
@@ -710,7 +712,6 @@ k_irfft_ola(IfftArgs a, const float2 *__restrict__ tw)
         }
         s[P::pidx(k)] = v;
     }
-conv_done:
     __syncthreads();
 
     // 2. pre-split, in place on pairs (k, B-k)
