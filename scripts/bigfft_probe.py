@@ -8,6 +8,11 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import fft_convolution_b200 as F
 
+import os
+from fft_convolution_b200 import _lib
+for kv in filter(None, os.environ.get("FCB_TUNE", "").split(",")):
+    k, v = kv.split("=")
+    _lib.check(_lib.load().fcb_tune(k.encode(), int(v)))
 C, B, S = 4096, int(sys.argv[1]) if len(sys.argv) > 1 else 8192, 10
 rng = np.random.default_rng(0)
 h = (rng.standard_normal((C, B * S)) * 0.01).astype(np.float32)
