@@ -139,3 +139,33 @@ def test_config2_full_channel_count_vs_oracle(F):
     ref = oracle.batch_crossfade(h, B, x, irs_upd=upd, update_every=50)
     worst = max(float(np.max(np.abs(y[c] - ref[c]))) / rms(ref[c]) for c in range(C))
     assert worst <= TOL, f"configs[2] x 256 channels: {worst:.3e} x RMS"
+
+
+def test_config3_full_channel_count_through_the_headline_path(F):
+    """configs[3] at its FULL size: 4096 channels x 2 s IR x block 512, 190 blocks (the 188-slot ring wraps), through the
+    very path bench.py times end to end — fcb_fftconv_process on page-locked host buffers (the whole-block kernel pulls and
+    pushes the blocks itself) — every channel against its own oracle convolver (OpenMP over channels)."""
+    import ctypes as C
+    import oracle
+    from fft_convolution_b200 import _lib
+    Cn, B, L, NB = 4096, 512, 96000, 190
+    lib = F.load_library()
+    h = bench.synth_irs(0, Cn, 0, L)                             # 4096 different responses
+    x = np.tile(bench.synth_noise(0, 256, 0, B * NB), (Cn // 256, 1))  # 256 different inputs, each met by 16 responses
+    conv = F.FFTConvolver.init(h, B, L)
+    p_in, p_out = lib.fcb_host_alloc(Cn * B * 4), lib.fcb_host_alloc(Cn * B * 4)
+    h_in = np.ctypeslib.as_array(C.cast(p_in, C.POINTER(C.c_float)), shape=(Cn, B))
+    h_out = np.ctypeslib.as_array(C.cast(p_out, C.POINTER(C.c_float)), shape=(Cn, B))
+    y = np.zeros_like(x)
+    launches0 = lib.fcb_launch_count()
+    for b in range(NB):
+        h_in[...] = x[:, b * B:(b + 1) * B]
+        _lib.check(lib.fcb_fftconv_process(conv._h, p_in, B, B, p_out, B, B))
+        y[:, b * B:(b + 1) * B] = h_out
+    assert lib.fcb_launch_count() - launches0 == NB  # one fused launch per block: the zero-copy path was taken
+    assert conv.current == (188 - NB % 188) % 188
+    ref = oracle.batch_fftconv(h, B, x, B)
+    err = np.max(np.abs(y - ref), axis=1) / np.sqrt(np.mean(ref.astype(np.float64) ** 2, axis=1))
+    assert float(err.max()) <= TOL, f"configs[3] x 4096 channels: worst channel {int(err.argmax())} at {float(err.max()):.3e} x RMS"
+    lib.fcb_host_free(p_in)
+    lib.fcb_host_free(p_out)
