@@ -66,7 +66,9 @@ uint64_t fcb_debug_alloc_count(void);
  * calls go through mapped pinned memory instead of the copy engines), "zero_copy" (1 = when the caller's
  * buffers are pinned, large-batch whole-block calls let the kernel read/write them over PCIe directly), "split" (1 = small
  * batches cut each delay line of a whole-block launch over several CTAs, partial sums added in slice order by the last
- * CTA to arrive: deterministic, within tolerance, not bit-equal to the unsplit order; 0 = never), "strict_todo"
+ * CTA to arrive: deterministic, within tolerance, not bit-equal to the unsplit order; 0 = never; sweeps: "split_slots" = CTAs
+ * the split aims at, "split_min_stages" = pipeline stages per CTA at least), "k1_late" (1 = the fused kernel transforms a block
+ * that sits in host memory AFTER its MAC stream; measured without effect, default 0), "strict_todo"
  * (1 = fcb_twostage_update and fcb_crossfade_reset answer FCB_ERR_TODO like the reference's todo!(); default 0 = the
  * extensions documented at those entry points) */
 int fcb_tune(const char *key, int value);
