@@ -310,12 +310,17 @@ def run_realtime(F, lib, local, rank, world, chan0, Cn_head, ms_e2e_per_block_he
             conv.process(h_in, h_out)
         barrier()
         times = np.empty(blocks)
-        t_all = time.perf_counter()
-        for i in range(blocks):
-            t0 = time.perf_counter()
-            conv.process(h_in, h_out)
-            times[i] = time.perf_counter() - t0
-        t_all = time.perf_counter() - t_all
+        import gc
+        gc.disable()  # an audio thread does not collect garbage; neither should the loop that stands in for one
+        try:
+            t_all = time.perf_counter()
+            for i in range(blocks):
+                t0 = time.perf_counter()
+                conv.process(h_in, h_out)
+                times[i] = time.perf_counter() - t0
+            t_all = time.perf_counter() - t_all
+        finally:
+            gc.enable()
         barrier()
         stats = reduce_max([percentile_ms(times, 50), percentile_ms(times, 99), float(times.max() * 1000.0),
                             float((times > period).sum()), t_all * 1000.0], device=f"cuda:{local}")

@@ -52,6 +52,19 @@ def main():
                         "channel_sec_per_sec": C * B / SR / (ms / 1e3),
                         "ring_GBs": C * 8 * (S - 1) * K / (ms / 1e3) / 1e9}), flush=True)
       conv.close()
+    if only in ("all", "crossfade"):
+        # (c) configs[2] at scale: CrossfadeConvolver x 4096 channels, fading all the time (update every 50 blocks, 2 s fade)
+        irs = bench.synth_irs(0, C, 0, L)
+        xf = F.CrossfadeConvolver.init(irs, B, L, stream=st.cuda_stream)
+        upd = bench.synth_irs(0, C, 1, L)
+        xf.update(upd)  # starts the 96 000-sample fade: A and B both audible from the second block on
+        del irs, upd
+        ms = timed(lambda i: xf.process_dev(x[i % 8].data_ptr(), B, B, out.data_ptr(), B, B), steps=100, warm=10, stream=st)
+        S, K = 188, B + 1
+        print(json.dumps({"config": f"CrossfadeConvolver::init x{C} channels, 2 s IRs, block 512, mid-fade (A + B in one paired launch)",
+                          "ms_per_block": ms, "channel_sec_per_sec": C * B / SR / (ms / 1e3),
+                          "GBs_of_24SK_bytes": C * 24 * (S - 1) * K / (ms / 1e3) / 1e9}), flush=True)
+        xf.close()
     if only not in ("all", "twostage"):
         return
     # (b) two-stage at scale
