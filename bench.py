@@ -361,15 +361,21 @@ def run_mimo(local, rank, world, steps, warmup):
             ref = o.cpu().numpy().copy()
             whole.close()
             del whole
-        for exchange in ("peer", "nccl"):
-            m = ShardedMimoConvolver(h, B, L, n_streams=NS, device=local, exchange=exchange)
+        R = NS * N
+        modes = [("peer", False), ("nccl", False)]
+        if NS > 1 and R % world == 0:
+            modes += [("peer", True), ("nccl", True)]  # reduce-scatter: every rank finishes its own R / N output rows
+        for exchange, scatter in modes:
+            m = ShardedMimoConvolver(h, B, L, n_streams=NS, device=local, exchange=exchange, scatter=scatter)
             out = torch.empty((NS * N, B), dtype=torch.float32, device=f"cuda:{local}")
             err = None
             for i in range(NCHK):
                 m.process_dev(x[i % 8], out)
             torch.cuda.synchronize()
             if ref is not None:
-                err = float(np.max(np.abs(out.cpu().numpy() - ref))) / max(float(np.sqrt(np.mean(ref.astype(np.float64) ** 2))), 1e-9)
+                lo, hi = m.rows  # every row, or this rank's rows in the reduce-scatter form
+                got = out.cpu().numpy()[lo:hi]
+                err = float(np.max(np.abs(got - ref[lo:hi]))) / max(float(np.sqrt(np.mean(ref[lo:hi].astype(np.float64) ** 2))), 1e-9)
                 if err > 1e-5:
                     raise SystemExit(f"bench.py: sharded matrix differs from the unsharded engine: {err:.3e} x RMS")
             for i in range(warmup):
@@ -384,8 +390,9 @@ def run_mimo(local, rank, world, steps, warmup):
             torch.cuda.synchronize()
             m.m.sync()  # surfaces a peer-exchange timeout
             ms = reduce_max([e0.elapsed_time(e1) / steps], device=f"cuda:{local}")[0]
-            res[f"streams{NS}_{exchange}"] = {
+            res[f"streams{NS}_{exchange}" + ("_reduce_scatter" if scatter else "")] = {
                 "ms_per_block": ms, "realtime_factor": 1000.0 * B / SAMPLE_RATE / ms, "tensor_cores": bool(m.m.uses_tensor_cores),
+                "output": "sharded by row over the ranks" if scatter else "complete on every rank",
                 "T_cmac_per_s": NS * N * N * ((L + B - 1) // B) * B / (ms / 1e3) / 1e12,
                 "max_abs_err_over_rms_vs_unsharded_after_520_blocks": err}
             m.m.close()

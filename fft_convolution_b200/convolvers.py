@@ -390,6 +390,19 @@ class MimoConvolver:
     def peer_inbox(self) -> int:
         return _lib.load().fcb_mimo_peer_inbox(self._h)
 
+    def peer_set_scatter(self, on: bool) -> None:
+        """reduce-scatter form of the peer exchange: this shard finishes (and outputs) only its own rows"""
+        check(_lib.load().fcb_mimo_peer_set_scatter(self._h, 1 if on else 0))
+
+    @property
+    def owned_rows(self):
+        lo, hi = C.c_size_t(), C.c_size_t()
+        check(_lib.load().fcb_mimo_owned_rows(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def finish_rows_dev(self, out_ptr: int, out_stride: int, row_lo: int, row_hi: int) -> None:
+        check(_lib.load().fcb_mimo_finish_rows_dev(self._h, out_ptr, out_stride, row_lo, row_hi))
+
     def peer_attach_ptrs(self, inboxes) -> None:
         arr = (C.c_void_p * len(inboxes))(*inboxes)
         check(_lib.load().fcb_mimo_peer_attach_ptrs(self._h, arr))

@@ -61,10 +61,22 @@ struct PeerPub {
     long long n_conv;
     unsigned int seq;                   // block counter, 1-based
     int G, me;
+    // reduce-scatter form (fcb_mimo_peer_set_scatter): shard g finishes rows [rows*g/G, rows*(g+1)/G) only, so a partial
+    // row travels to its owner alone — 1/G of the all-gather form's NVLink bytes — and lands in the owner's slot
+    // [parity][source][row - first owned row]
+    int scatter, B;
+    long long rows, slot_stride;        // rows = NS*OUT; slot_stride = float2 per (parity, source) slot
 };
 
 __device__ __forceinline__ void peer_store(const PeerPub &p, long long idx, float2 v)
 {
+    if (p.scatter) {
+        const long long row = idx / p.B;
+        const int g = (int)(((row + 1) * p.G - 1) / p.rows);          // owner of `row`
+        const long long local = (row - p.rows * g / p.G) * p.B + idx % p.B;
+        p.inbox[g][((long long)(p.seq & 1) * p.G + p.me) * p.slot_stride + local] = v;
+        return;
+    }
     const long long off = ((long long)(p.seq & 1) * p.G + p.me) * p.n_conv + idx;
     for (int g = 0; g < p.G; g++) p.inbox[g][off] = v;
 }
@@ -201,7 +213,12 @@ struct fcb_mimo {
     void *peer_base[FCB_MAX_PEERS] = {}; // every shard's inbox in my address space
     bool peer_opened[FCB_MAX_PEERS] = {};
     bool peer_on = false;
+    bool peer_scatter = false;           // reduce-scatter form: this shard finishes (and outputs) its own rows only
     unsigned int peer_seq = 0;
+    size_t rows_total() const { return n_streams * n_out; }
+    size_t row_lo() const { return rows_total() * shard_index / shard_count; }
+    size_t row_hi() const { return rows_total() * (shard_index + 1) / shard_count; }
+    size_t slot_stride() const { return peer_scatter ? ((rows_total() + shard_count - 1) / shard_count) * B : n_conv(); }
     size_t n_conv() const { return n_streams * n_out * B; }
     size_t inbox_data_bytes() const { return 2 * shard_count * n_conv() * sizeof(float2); }
     PeerPub pub() const
@@ -217,6 +234,10 @@ struct fcb_mimo {
         p.seq = peer_seq;
         p.G = (int)shard_count;
         p.me = (int)shard_index;
+        p.scatter = peer_scatter ? 1 : 0;
+        p.B = (int)B;
+        p.rows = (long long)rows_total();
+        p.slot_stride = (long long)slot_stride();
         return p;
     }
     size_t ir_copy_floats() const { return B * n_in * 32 * out_groups * 2 * rowsP; }
@@ -530,38 +551,74 @@ extern "C" float *fcb_mimo_conv_buffer(fcb_mimo *m, size_t *n_floats)
     return reinterpret_cast<float *>(m->conv);
 }
 
-// K3 on the (all-reduced) conv: inverse FFT, /N, overlap-add, overlap save; rotates `current`
+// K3 on rows [row_lo, row_hi) of the (reduced) conv: inverse FFT, /N, overlap-add, overlap save; rotates `current`.
+// out_dev is the base of the FULL [NS*OUT][B] output (row r lands at out_dev + r*out_stride).
+static int mimo_finish_rows(fcb_mimo *m, float *out_dev, size_t out_stride, size_t row_lo, size_t row_hi)
+{
+    FCB_TRY(peer_check(m));
+    FCB_CUDA(cudaSetDevice(m->device));
+    const size_t B = m->B;
+    if (m->S == 0) {
+        if (row_hi > row_lo)
+            FCB_CUDA(cudaMemset2DAsync(out_dev + row_lo * out_stride, out_stride * sizeof(float), 0, B * sizeof(float), row_hi - row_lo, m->stream));
+        return FCB_OK;
+    }
+    if (row_hi > row_lo) {
+        IfftArgs a{};
+        a.ir0 = nullptr; // conv is complete
+        a.premul = m->conv + row_lo * B;
+        a.overlap = m->overlap + row_lo * B;
+        a.out = out_dev + row_lo * out_stride;
+        a.out_stride = (long long)out_stride;
+        a.fill = 0;
+        a.n = (int)B;
+        a.block_complete = 1;
+        a.nchan = (long long)(row_hi - row_lo);
+        if (m->peer_on) { // sum the G shards' partial spectra out of my inbox once their flags have arrived
+            const size_t G = m->shard_count, par = m->peer_seq & 1, stride = m->slot_stride();
+            a.gather = reinterpret_cast<const float2 *>(m->inbox) + par * G * stride + (m->peer_scatter ? 0 : row_lo * B);
+            a.gather_stride = (long long)stride;
+            a.gather_flags = reinterpret_cast<const unsigned int *>(m->inbox + m->inbox_data_bytes()) + par * G;
+            a.gather_seq = m->peer_seq;
+            a.gather_n = (int)G;
+            a.gather_err = m->peer_err_d;
+        }
+        FCB_TRY(run_inverse(m->logb, m->tw, m->stream, a));
+    }
+    m->current = m->current > 0 ? m->current - 1 : m->S - 1; // src/fft_convolver.rs:287-291
+    return FCB_OK;
+}
+
+// every row — or, in the reduce-scatter form of the peer exchange, the rows this shard owns
 extern "C" int fcb_mimo_finish_dev(fcb_mimo *m, float *out_dev, size_t out_stride)
 {
     if (!m || !out_dev) return fail(FCB_ERR_ARG, "fcb_mimo_finish_dev: NULL argument");
-    FCB_TRY(peer_check(m));
-    FCB_CUDA(cudaSetDevice(m->device));
-    const size_t B = m->B, n_so = m->n_streams * m->n_out;
-    if (m->S == 0) {
-        FCB_CUDA(cudaMemset2DAsync(out_dev, out_stride * sizeof(float), 0, B * sizeof(float), n_so, m->stream));
-        return FCB_OK;
-    }
-    IfftArgs a{};
-    a.ir0 = nullptr; // conv is complete
-    a.premul = m->conv;
-    a.overlap = m->overlap;
-    a.out = out_dev;
-    a.out_stride = (long long)out_stride;
-    a.fill = 0;
-    a.n = (int)B;
-    a.block_complete = 1;
-    a.nchan = (long long)n_so;
-    if (m->peer_on) { // sum the G shards' partial spectra out of my inbox once their flags have arrived
-        const size_t G = m->shard_count, par = m->peer_seq & 1;
-        a.gather = reinterpret_cast<const float2 *>(m->inbox) + par * G * m->n_conv();
-        a.gather_stride = (long long)m->n_conv();
-        a.gather_flags = reinterpret_cast<const unsigned int *>(m->inbox + m->inbox_data_bytes()) + par * G;
-        a.gather_seq = m->peer_seq;
-        a.gather_n = (int)G;
-        a.gather_err = m->peer_err_d;
-    }
-    FCB_TRY(run_inverse(m->logb, m->tw, m->stream, a));
-    m->current = m->current > 0 ? m->current - 1 : m->S - 1; // src/fft_convolver.rs:287-291
+    if (m->peer_on && m->peer_scatter) return mimo_finish_rows(m, out_dev, out_stride, m->row_lo(), m->row_hi());
+    return mimo_finish_rows(m, out_dev, out_stride, 0, m->rows_total());
+}
+
+// K3 for rows [row_lo, row_hi) only (the caller reduce-scattered the conv buffer: NCCL reduce_scatter in place of all-reduce)
+extern "C" int fcb_mimo_finish_rows_dev(fcb_mimo *m, float *out_dev, size_t out_stride, size_t row_lo, size_t row_hi)
+{
+    if (!m || !out_dev) return fail(FCB_ERR_ARG, "fcb_mimo_finish_rows_dev: NULL argument");
+    if (row_lo > row_hi || row_hi > m->rows_total()) return fail(FCB_ERR_ARG, "fcb_mimo_finish_rows_dev: rows [%zu, %zu) of %zu", row_lo, row_hi, m->rows_total());
+    if (m->peer_on) return fail(FCB_ERR_ARG, "fcb_mimo_finish_rows_dev: the peer exchange picks the rows itself (fcb_mimo_peer_set_scatter)");
+    return mimo_finish_rows(m, out_dev, out_stride, row_lo, row_hi);
+}
+
+// reduce-scatter form of the peer exchange: set on EVERY shard before the first block
+extern "C" int fcb_mimo_peer_set_scatter(fcb_mimo *m, int on)
+{
+    if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
+    if (m->peer_seq != 0) return fail(FCB_ERR_ARG, "fcb_mimo_peer_set_scatter: set before the first block");
+    m->peer_scatter = on != 0;
+    return FCB_OK;
+}
+extern "C" int fcb_mimo_owned_rows(const fcb_mimo *m, size_t *lo, size_t *hi)
+{
+    if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
+    if (lo) *lo = m->row_lo();
+    if (hi) *hi = m->row_hi();
     return FCB_OK;
 }
 

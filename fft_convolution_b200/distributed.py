@@ -27,7 +27,9 @@ class ShardedMimoConvolver:
     """One IR-partition shard per rank of the default process group (NCCL on GPUs)."""
 
     def __init__(self, responses, block_size: int, max_response_length: int, *, n_streams: int = 1, device: int = 0,
-                 tensor_cores: bool | None = None, exchange: str = "peer"):
+                 tensor_cores: bool | None = None, exchange: str = "peer", scatter: bool = False):
+        """scatter=True: reduce-scatter instead of all-gather / all-reduce — every rank FINISHES only its own output rows
+        (`self.rows`), the result is sharded by row over the ranks (1/G of the exchange bytes, 1/G of the K3 work)"""
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
@@ -39,7 +41,13 @@ class ShardedMimoConvolver:
         self.conv = torch.as_tensor(self._keep, device=f"cuda:{device}")
         self.B = self.m.block_size
         self.exchange = exchange if self.world > 1 else "none"
+        self.scatter = bool(scatter) and self.world > 1
+        self.rows = self.m.owned_rows if self.scatter else (0, n_streams * self.m.n_out)
+        if self.scatter and self.exchange == "nccl" and (n_streams * self.m.n_out) % self.world:
+            raise ValueError("reduce_scatter needs the output rows to divide evenly over the ranks")
         if self.exchange == "peer":
+            if self.scatter:
+                self.m.peer_set_scatter(True)
             mine = torch.frombuffer(bytearray(self.m.peer_export()), dtype=torch.uint8).to(f"cuda:{device}")
             every = torch.empty((self.world, 64), dtype=torch.uint8, device=f"cuda:{device}")
             dist.all_gather_into_tensor(every, mine)
@@ -51,6 +59,12 @@ class ShardedMimoConvolver:
         out: [NS*OUT, B].  Every rank ends with the full result."""
         with torch.cuda.stream(self.stream):
             self.m.partial_dev(x.data_ptr(), x.stride(0))
+            if self.exchange == "nccl" and self.scatter:
+                lo, hi = self.rows
+                mine = self.conv[lo * 2 * self.B:hi * 2 * self.B]  # my rows of the conv buffer, reduced in place
+                dist.reduce_scatter_tensor(mine, self.conv, op=dist.ReduceOp.SUM)
+                self.m.finish_rows_dev(out.data_ptr(), out.stride(0), lo, hi)
+                return
             if self.exchange == "nccl":
                 dist.all_reduce(self.conv, op=dist.ReduceOp.SUM)
             self.m.finish_dev(out.data_ptr(), out.stride(0))

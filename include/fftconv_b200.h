@@ -387,6 +387,14 @@ int fcb_mimo_peer_attach(fcb_mimo *m, const unsigned char *handles /* [shard_cou
  * ONE GPU must all enqueue fcb_mimo_partial_dev before any of them enqueues fcb_mimo_finish_dev: a K3 spinning on a
  * flag can otherwise hold the SMs its peer's producer kernel is waiting for. */
 void *fcb_mimo_peer_inbox(fcb_mimo *m);
+/* Reduce-scatter form of the exchange (large payloads: many streams).  Shard g FINISHES rows [R*g/G, R*(g+1)/G) of the
+ * R = NS*OUT output rows only (fcb_mimo_owned_rows), so a partial row travels to its owner alone — 1/G of the all-gather
+ * form's NVLink bytes — and fcb_mimo_finish_dev writes just those rows of out_dev (the full-size buffer's other rows are
+ * left alone: the output is sharded by row over the GPUs).  Set on EVERY shard before the first block.
+ * NCCL callers get the same with a reduce_scatter of fcb_mimo_conv_buffer followed by fcb_mimo_finish_rows_dev. */
+int fcb_mimo_peer_set_scatter(fcb_mimo *m, int on);
+int fcb_mimo_owned_rows(const fcb_mimo *m, size_t *lo, size_t *hi);
+int fcb_mimo_finish_rows_dev(fcb_mimo *m, float *out_dev, size_t out_stride, size_t row_lo, size_t row_hi);
 int fcb_mimo_peer_attach_ptrs(fcb_mimo *m, void *const *inboxes);
 /* test hook (host only): segment chunks (count, segments per chunk) the CUDA-core matrix kernel uses for a problem */
 int fcb_debug_mac_tile_plan(int logb, int n_in, int n_out, int n_streams, int nsegs, int *zchunks, int *zlen);

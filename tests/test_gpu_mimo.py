@@ -141,6 +141,49 @@ def test_peer_exchange_shards_in_one_process(F, shards, tc):
     run.check(TOL, "peer-exchange shards vs oracle")
 
 
+@pytest.mark.parametrize("shards,tc,NS,n_out", [(2, False, 2, 3), (3, False, 1, 4), (4, True, 3, 16), (3, True, 5, 16)])
+def test_peer_exchange_reduce_scatter_form(F, shards, tc, NS, n_out):
+    """reduce-scatter form of the peer exchange: a partial row travels to its owner only and every shard finishes just
+    its own rows [R g / G, R (g+1) / G) of the R = NS * OUT output rows (uneven splits included); the rows of all shards
+    together are the full result.  All shards in one process on one GPU, every publish issued before any K3."""
+    import torch
+    n_in, B = 2, 64
+    L = B * (19 if tc else 11) + 5
+    h = _irs(n_out, n_in, L)
+    nblocks = 24
+    x = np.stack([oracle.gen_noise(700 + i, 0, B * nblocks) for i in range(NS * n_in)])
+    parts = [F.MimoConvolver.init(h, B, L, n_streams=NS, shard_index=g, shard_count=shards, tensor_cores=tc) for g in range(shards)]
+    inboxes = [p.peer_inbox() for p in parts]
+    for p in parts:
+        p.peer_attach_ptrs(inboxes)
+        p.peer_set_scatter(True)
+    rows = [p.owned_rows for p in parts]
+    R = NS * n_out
+    assert rows[0][0] == 0 and rows[-1][1] == R and all(rows[i][1] == rows[i + 1][0] for i in range(shards - 1))
+    refs = [MimoOracle(h, B, L) for _ in range(NS)]
+    d_in = torch.empty((NS * n_in, B), dtype=torch.float32, device="cuda")
+    d_out = torch.full((R, B), float("nan"), dtype=torch.float32, device="cuda")  # ONE buffer: every shard writes its rows
+    run = WholeRun()
+    for b in range(nblocks):
+        blk = np.ascontiguousarray(x[:, b * B:(b + 1) * B])
+        d_in.copy_(torch.from_numpy(blk))
+        d_out.fill_(float("nan"))
+        torch.cuda.synchronize()
+        for p in parts:
+            p.partial_dev(d_in.data_ptr(), B)
+        for p in parts:
+            p.sync()
+        for p in parts:
+            p.finish_dev(d_out.data_ptr(), B)
+        for p in parts:
+            p.sync()
+        out = d_out.cpu().numpy()
+        assert not np.isnan(out).any()  # the shards' rows cover the output exactly
+        for s_ in range(NS):
+            run.add(out[s_ * n_out:(s_ + 1) * n_out], refs[s_].process(blk[s_ * n_in:(s_ + 1) * n_in]))
+    run.check(TOL, "reduce-scatter peer exchange vs oracle")
+
+
 def test_nccl_sharded_mimo_two_gpus():
     """IR-partition shards on 2 GPUs, exchanged by NCCL all-reduce and by the NVLink peer exchange (skipped on a 1-GPU box)"""
     import subprocess
