@@ -11,7 +11,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 SO = PKG / "libfftconv_b200.so"
 SOURCES = ["engine.cu", "host_mirror.cu", "mimo.cu"]
-HEADERS = ["common.cuh", "engine_internal.cuh", "fft_kernels.cuh", "mac_kernels.cuh", "fused_kernel.cuh", "mimo_tc.cuh", "offline_kernels.cuh", "../../include/fftconv_b200.h"]
+HEADERS = ["common.cuh", "engine_internal.cuh", "fft_kernels.cuh", "mac_kernels.cuh", "fused_kernel.cuh", "mimo_tc.cuh", "mimo_rt.cuh", "offline_kernels.cuh", "../../include/fftconv_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

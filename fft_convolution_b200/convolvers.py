@@ -342,7 +342,9 @@ class MimoConvolver:
 
     block_size = property(lambda s: _lib.load().fcb_mimo_block_size(s._h))
     seg_count = property(lambda s: _lib.load().fcb_mimo_seg_count(s._h))
-    uses_tensor_cores = property(lambda s: bool(_lib.load().fcb_mimo_uses_tensor_cores(s._h)))
+    uses_tensor_cores = property(lambda s: _lib.load().fcb_mimo_uses_tensor_cores(s._h) == 1)
+    #: which delay-line MAC this object runs: "tensor" (K4, tcgen05), "register_tile" (k_mac_rt) or "tile" (k_mac_tile / K2)
+    mac_kernel = property(lambda s: {1: "tensor", 2: "register_tile"}.get(_lib.load().fcb_mimo_uses_tensor_cores(s._h), "tile"))
 
     @property
     def segment_range(self):
@@ -362,6 +364,14 @@ class MimoConvolver:
 
     def reset(self) -> None:
         check(_lib.load().fcb_mimo_reset(self._h))
+
+    def set_ir(self, responses) -> None:
+        """replace the whole matrix ([OUT, IN, len], len <= max_response_length); input history is kept like update()"""
+        r = np.ascontiguousarray(responses, dtype=np.float32)
+        if r.ndim != 3 or r.shape[:2] != (self.n_out, self.n_in):
+            raise ValueError("responses must be [out, in, len]")
+        check(_lib.load().fcb_mimo_set_ir(self._h, _ptr(r), r.shape[2]))
+        check(_lib.load().fcb_mimo_sync(self._h))
 
     def partial_dev(self, in_ptr: int, in_stride: int) -> None:
         check(_lib.load().fcb_mimo_partial_dev(self._h, in_ptr, in_stride))

@@ -14,12 +14,15 @@
 
 #include "engine_internal.cuh"
 #include "mimo_tc.cuh"
+#include "mimo_rt.cuh"
 
 using namespace fcb;
 
 namespace fcb {
 extern std::atomic<bool> g_mimo_tile;
-extern std::atomic<int> g_mimo_tc; // 0 never, 1 whenever the shape fits, 2 (default) when it fits and NS >= 16
+extern std::atomic<int> g_mimo_tc; // 0 never, 1 whenever the shape fits, 2 (default) when it fits and NS >= g_mimo_tc_min
+extern std::atomic<int> g_mimo_tc_min; // fewer streams than this run on the FP32 pipes (k_mac_rt)
+extern std::atomic<bool> g_mimo_rt;    // register-tiled matrix MAC for 2+ streams (0: the shared-memory tile kernel)
 
 typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                            const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -46,6 +49,89 @@ static int tc_encode_map(CUtensorMap *tm, void *base, uint64_t d0, uint64_t d1, 
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(FCB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return FCB_OK;
+}
+
+// f32 tensor [d3][d2][d1][d0] (d0 contiguous, pitches in bytes), box [b3][1][b1][b0], no swizzle; out-of-bounds reads as zero
+static int rt_encode_map(CUtensorMap *tm, void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t pitch1,
+                         uint64_t pitch2, uint64_t pitch3, uint32_t b0, uint32_t b1, uint32_t b3)
+{
+    static TensorMapEncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FCB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p) return fail(FCB_ERR_CUDA, "cuTensorMapEncodeTiled is not exported by this driver");
+        fn = (TensorMapEncodeTiledFn)p;
+    }
+    cuuint64_t dims[4] = {d0, d1, d2, d3};
+    cuuint64_t strides[3] = {pitch1, pitch2, pitch3};
+    cuuint32_t box[4] = {b0, b1, 1, b3};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FCB_ERR_CUDA, "cuTensorMapEncodeTiled (matrix operands) failed (%d)", (int)r);
+    return FCB_OK;
+}
+
+// k_mac_rt: CTA shape by problem (8 or 16 outputs x 4, 8 or 16 streams) and the segment chunking that fills ONE wave of
+// resident CTAs (the partial spectra have no input dimension, so a chunk is cheap: Z * NS * OUT rows)
+struct RtPlan {
+    int wo = 1, ws = 1, zchunks = 1, zlen = 1, out_groups = 1, stream_groups = 1;
+    size_t smem = 0;
+    int threads = 32, per_sm = 1;
+};
+template <int WO, int WS>
+static void rt_shape(RtPlan &p)
+{
+    using Cfg = RtCfg<WO, WS>;
+    p.wo = WO;
+    p.ws = WS;
+    p.smem = Cfg::SMEM;
+    p.threads = Cfg::THREADS;
+    const int by_smem = (int)((227 * 1024) / (Cfg::SMEM + 1024));
+    p.per_sm = Cfg::MIN_CTAS < by_smem ? Cfg::MIN_CTAS : by_smem;
+}
+static RtPlan rt_plan(int B, int n_out, int n_streams, int nsegs)
+{
+    RtPlan p;
+    const bool o16 = n_out > 8;
+    const int sw = n_streams > 8 ? 4 : n_streams > 4 ? 2 : 1;
+    if (o16) sw == 4 ? rt_shape<2, 4>(p) : sw == 2 ? rt_shape<2, 2>(p) : rt_shape<2, 1>(p);
+    else sw == 4 ? rt_shape<1, 4>(p) : sw == 2 ? rt_shape<1, 2>(p) : rt_shape<1, 1>(p);
+    p.out_groups = (n_out + 8 * p.wo - 1) / (8 * p.wo);
+    p.stream_groups = (n_streams + 4 * p.ws - 1) / (4 * p.ws);
+    const long long base = (long long)((B + RT_BINS - 1) / RT_BINS) * p.out_groups * p.stream_groups;
+    const long long slots = 148LL * p.per_sm;
+    long long z = slots / base;
+    const long long zmax = nsegs / (2 * RT_R) > 0 ? nsegs / (2 * RT_R) : 1; // at least two stages of segments per chunk
+    z = z > zmax ? zmax : z < 1 ? 1 : z;
+    p.zlen = nsegs > 0 ? (int)((nsegs + z - 1) / z) : 1;
+    p.zchunks = nsegs > 0 ? (nsegs + p.zlen - 1) / p.zlen : 0;
+    return p;
+}
+template <int WO, int WS>
+static int rt_launch_t(const RtArgs &a, const CUtensorMap &tm_ir, const CUtensorMap &tm_ring, cudaStream_t st)
+{
+    using Cfg = RtCfg<WO, WS>;
+    static bool opted = false;
+    if (!opted) {
+        if (cudaFuncSetAttribute(k_mac_rt<WO, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
+            return fail(FCB_ERR_CUDA, "k_mac_rt: cannot opt in to %zu bytes of shared memory", (size_t)Cfg::SMEM);
+        opted = true;
+    }
+    const long long grid = (long long)((a.B + RT_BINS - 1) / RT_BINS) * a.zchunks * a.out_groups * a.stream_groups;
+    cudaEvent_t prof_stop = nullptr;
+    const bool profiled = mac_profile_begin(st, &prof_stop) != nullptr;
+    k_mac_rt<WO, WS><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(a, tm_ir, tm_ring);
+    if (profiled) cudaEventRecord(prof_stop, st);
+    g_launches++;
+    FCB_CUDA(cudaGetLastError());
+    return FCB_OK;
+}
+static int rt_launch(const RtPlan &p, const RtArgs &a, const CUtensorMap &tm_ir, const CUtensorMap &tm_ring, cudaStream_t st)
+{
+    if (p.wo == 2) return p.ws == 4 ? rt_launch_t<2, 4>(a, tm_ir, tm_ring, st) : p.ws == 2 ? rt_launch_t<2, 2>(a, tm_ir, tm_ring, st) : rt_launch_t<2, 1>(a, tm_ir, tm_ring, st);
+    return p.ws == 4 ? rt_launch_t<1, 4>(a, tm_ir, tm_ring, st) : p.ws == 2 ? rt_launch_t<1, 2>(a, tm_ir, tm_ring, st) : rt_launch_t<1, 1>(a, tm_ir, tm_ring, st);
 }
 
 // ---- peer exchange of the partial spectra (replaces the NCCL all-reduce between the MAC and K3) ----
@@ -96,13 +182,14 @@ __device__ __forceinline__ void peer_signal(const PeerPub &p, unsigned int ctas)
 
 // conv[s][o][k] = sum_in sum_z part[z][s][o][in][k]  +  sum_in X[s][in][cur][k] * H[o][in][seg 0][k]
 // (the segment-0 product, src/fft_convolver.rs:256-261, only on the shard that owns segment 0).
+// part_in == 0: the partial rows are already summed over `in` (k_mac_rt): part[z][s][o][k], added by lane 0.
 // CTA = 32 bins x 8 input lanes of one (stream, out): lane y sums its inputs y, y+8, ... over all
 // z chunks, then the 8 lane sums are added in fixed order — deterministic, and parallel enough
 // that the Z*IN partial rows (19 MB at 16x16, Z = 19) stream at memory speed.
 __global__ void __launch_bounds__(256)
 k_mimo_reduce(const float2 *__restrict__ premul, const float2 *__restrict__ ring_cur, long long ring_stride,
               const float2 *__restrict__ ir0, long long ir_stride, float2 *__restrict__ conv, int B, int n_in,
-              int n_out, long long n_so, int zchunks, PeerPub pub)
+              int n_out, long long n_so, int zchunks, int part_in, PeerPub pub)
 {
     __shared__ float2 lane_sum[8][32];
     const int kt = (B + 31) / 32;
@@ -113,11 +200,14 @@ k_mimo_reduce(const float2 *__restrict__ premul, const float2 *__restrict__ ring
     float ar = 0.f, ai = 0.f;
     if (k < B) {
         for (int in = y; in < n_in; in += 8) {
-            float2 p = premul[(so * n_in + in) * B + k];
-            for (int z = 1; z < zchunks; z++) {
-                float2 q = premul[(((long long)z * n_so + so) * n_in + in) * B + k];
-                p.x += q.x;
-                p.y += q.y;
+            float2 p = make_float2(0.f, 0.f);
+            if (part_in) {
+                p = premul[(so * n_in + in) * B + k];
+                for (int z = 1; z < zchunks; z++) {
+                    float2 q = premul[(((long long)z * n_so + so) * n_in + in) * B + k];
+                    p.x += q.x;
+                    p.y += q.y;
+                }
             }
             if (ir0) {
                 float2 x = ring_cur[(s * n_in + in) * ring_stride + k];
@@ -136,6 +226,12 @@ k_mimo_reduce(const float2 *__restrict__ premul, const float2 *__restrict__ ring
             ar = __fadd_rn(ar, p.x);
             ai = __fadd_rn(ai, p.y);
         }
+        if (!part_in && y == 0)
+            for (int z = 0; z < zchunks; z++) {
+                float2 q = premul[((long long)z * n_so + so) * B + k];
+                ar = __fadd_rn(ar, q.x);
+                ai = __fadd_rn(ai, q.y);
+            }
     }
     lane_sum[y][threadIdx.x] = make_float2(ar, ai);
     __syncthreads();
@@ -183,6 +279,10 @@ struct fcb_mimo {
     float2 *ring = nullptr;        // [NS*IN][S][B]
     float2 *premul = nullptr;      // [Z*NS*OUT*IN][B]  (Z segment chunks of the tile kernel, >= 1)
     int zmax = 1;
+    // register-tiled matrix MAC (k_mac_rt, mimo_rt.cuh): 2+ streams below the tensor-core threshold
+    bool rt = false;
+    RtPlan rt_plan_;
+    CUtensorMap tm_rt_ir, tm_rt_ring;
     float2 *conv = nullptr;        // [NS*OUT][B]  (this shard's partial until all-reduced)
     float *overlap = nullptr;      // [NS*OUT][B]
     float *io_in = nullptr, *io_out = nullptr; // staging for the host-pointer call
@@ -317,7 +417,7 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
     const size_t pairs = m->n_out * m->n_in;
     int rc = get_twiddles(m->device, 2 * B, &m->tw);
     const int tc_mode = g_mimo_tc.load();
-    m->tc = tc_mode != 0 && (tc_mode == 1 || ns >= 16) && m->rows() > 0 && B >= 2;
+    m->tc = tc_mode != 0 && (tc_mode == 1 || ns >= (size_t)g_mimo_tc_min.load()) && m->rows() > 0 && B >= 2;
     if (m->tc) {
         m->nblk = (m->S + TC_KSEG - 1) / TC_KSEG;
         m->stream_groups = (ns + TC_M - 1) / TC_M;
@@ -350,7 +450,23 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
         if (!rc) rc = mimo_alloc((void **)&m->ring, ns * m->n_in * m->S * B * sizeof(float2), m->stream);
         int z = 1, zl = 1;
         if (mac_tile_plan(m->logb, (int)m->n_in, (int)m->n_out, (int)ns, (int)m->rows(), &z, &zl) == FCB_OK) m->zmax = z;
-        if (!rc) rc = mimo_alloc((void **)&m->premul, (size_t)m->zmax * ns * pairs * B * sizeof(float2), m->stream);
+        size_t part_rows = (size_t)m->zmax * ns * pairs;
+        const size_t first = m->seg_lo > 1 ? m->seg_lo : 1; // segment 0 belongs to the reduce kernel
+        m->rt = g_mimo_rt.load() && ns >= 2 && B >= (size_t)RT_BINS && m->seg_hi > first;
+        if (m->rt) {
+            m->rt_plan_ = rt_plan((int)B, (int)m->n_out, (int)ns, (int)(m->seg_hi - first));
+            const size_t need = (size_t)m->rt_plan_.zchunks * ns * m->n_out;
+            if (need > part_rows) part_rows = need;
+        }
+        if (!rc) rc = mimo_alloc((void **)&m->premul, part_rows * B * sizeof(float2), m->stream);
+        if (!rc && m->rt) {
+            const uint64_t row = B * sizeof(float2), per_pair = m->rows() * row, per_ring = m->S * row;
+            rc = rt_encode_map(&m->tm_rt_ir, m->ir + (first - m->seg_lo) * B, 2 * B, m->seg_hi - first, m->n_in, m->n_out, row,
+                               per_pair, m->n_in * per_pair, 2 * RT_BINS, RT_R, 8 * m->rt_plan_.wo);
+            if (!rc)
+                rc = rt_encode_map(&m->tm_rt_ring, m->ring, 2 * B, m->S, m->n_in, ns, row, per_ring, m->n_in * per_ring,
+                                   2 * RT_BINS, RT_R, 4 * m->rt_plan_.ws);
+        }
     }
     if (!rc) rc = mimo_alloc((void **)&m->conv, ns * m->n_out * B * sizeof(float2), m->stream);
     if (!rc) rc = mimo_alloc((void **)&m->overlap, ns * m->n_out * B * sizeof(float), m->stream);
@@ -491,9 +607,30 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
     FCB_CUDA(cudaEventRecord(m->ev_k1, m->side));
     const int seg_lo = (int)(m->seg_lo > 1 ? m->seg_lo : 1), seg_hi = (int)m->seg_hi;
     const long long ir_stride = (long long)(m->rows() * B);
-    int zchunks = 1;
+    int zchunks = 1, part_in = 1;
     bool done = false;
-    if (g_mimo_tile.load() && m->zmax >= 1 && seg_hi > seg_lo) {
+    if (m->rt) {
+        RtArgs t{};
+        t.part = m->premul;
+        t.B = (int)B;
+        t.n_in = (int)m->n_in;
+        t.n_out = (int)m->n_out;
+        t.n_streams = (int)ns;
+        t.S = (int)m->S;
+        t.current = (int)m->current;
+        t.seg_lo = seg_lo;
+        t.seg_hi = seg_hi;
+        t.seg_base = seg_lo;
+        t.zchunks = m->rt_plan_.zchunks;
+        t.zlen = m->rt_plan_.zlen;
+        t.out_groups = m->rt_plan_.out_groups;
+        t.stream_groups = m->rt_plan_.stream_groups;
+        FCB_TRY(rt_launch(m->rt_plan_, t, m->tm_rt_ir, m->tm_rt_ring, m->stream));
+        zchunks = t.zchunks;
+        part_in = 0;
+        done = true;
+    }
+    if (!done && g_mimo_tile.load() && m->zmax >= 1 && seg_hi > seg_lo) {
         MacTileArgs t{};
         t.ir = m->ir;
         t.ir_stride = ir_stride;
@@ -538,7 +675,7 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
     const long long n_so = (long long)(ns * m->n_out);
     k_mimo_reduce<<<(unsigned)(n_so * ((B + 31) / 32)), dim3(32, 8), 0, m->stream>>>(
         m->premul, m->ring + m->current * B, ring_stride, owns0 ? m->ir : nullptr, ir_stride, m->conv, (int)B,
-        (int)m->n_in, (int)m->n_out, n_so, zchunks, m->pub());
+        (int)m->n_in, (int)m->n_out, n_so, zchunks, part_in, m->pub());
     g_launches++;
     FCB_CUDA(cudaGetLastError());
     return FCB_OK;
@@ -726,7 +863,7 @@ extern "C" int fcb_debug_tc_stages(int S, int current, int seg_lo, int seg_hi, i
     return n;
 }
 
-extern "C" int fcb_mimo_uses_tensor_cores(const fcb_mimo *m) { return m && m->tc ? 1 : 0; }
+extern "C" int fcb_mimo_uses_tensor_cores(const fcb_mimo *m) { return !m ? 0 : m->tc ? 1 : m->rt ? 2 : 0; }
 extern "C" size_t fcb_mimo_block_size(const fcb_mimo *m) { return m->B; }
 extern "C" size_t fcb_mimo_seg_count(const fcb_mimo *m) { return m->S; }
 extern "C" int fcb_mimo_segment_range(const fcb_mimo *m, size_t *lo, size_t *hi)

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="how IR-partition shards exchange partial spectra")
     ap.add_argument("--tc", type=int, default=-1, help="1/0 force the tensor-core matrix MAC (K4) on/off, -1 library default")
+    ap.add_argument("--rt", type=int, default=1, help="0: the shared-memory tile kernel instead of the register-tiled MAC (k_mac_rt) below the tensor-core threshold")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -41,6 +42,7 @@ def main():
     from fft_convolution_b200.distributed import ShardedMimoConvolver
     from fft_convolution_b200 import _lib
     lib = _lib.load()
+    _lib.check(lib.fcb_tune(b"mimo_rt", a.rt))
     N, B, L, NS = a.n, a.block, int(a.ir_seconds * 48000), a.streams
     h = bench.synth_irs(0, N * N, 0, L).reshape(N, N, L)  # IR index c = out*N + in
     m = ShardedMimoConvolver(h, B, L, n_streams=NS, device=local, tensor_cores=None if a.tc < 0 else bool(a.tc), exchange=a.exchange)
@@ -76,7 +78,7 @@ def main():
     if rank == 0:
         print(json.dumps({
             "config": f"MIMO {N}x{N}, IR {a.ir_seconds:g} s ({L} taps, S={S}), block {B}, streams {NS}, {world} GPU(s) (IR-partition shards)",
-            "tensor_cores": bool(m.m.uses_tensor_cores), "exchange": m.exchange,
+            "tensor_cores": bool(m.m.uses_tensor_cores), "mac_kernel": m.m.mac_kernel, "exchange": m.exchange,
             "T_cmac_per_s": NS * N * N * (hi - lo) * B / (float(t[0]) / 1e3) / 1e12,
             "ms_per_block": float(t[0]), "block_period_ms": 1000.0 * B / 48000, "realtime_factor": 1000.0 * B / 48000 / float(t[0]),
             "k2_ms": k2_ms, "k2_ir_GBs": ir_bytes / (k2_ms / 1e3) / 1e9, "k2_ir_plus_ring_GBs": (ir_bytes + ring_bytes) / (k2_ms / 1e3) / 1e9,
