@@ -23,6 +23,9 @@ extern std::atomic<bool> g_mimo_tile;
 extern std::atomic<int> g_mimo_tc; // 0 never, 1 whenever the shape fits, 2 (default) when it fits and NS >= g_mimo_tc_min
 extern std::atomic<int> g_mimo_tc_min; // fewer streams than this run on the FP32 pipes (k_mac_rt)
 extern std::atomic<bool> g_mimo_rt;    // register-tiled matrix MAC for 2+ streams (0: the shared-memory tile kernel)
+extern std::atomic<int> g_mimo_rt_wb;  // warps side by side along the bins in k_mac_rt (1 or 2)
+extern std::atomic<int> g_mimo_rt_r;   // segments per pipeline stage (4: 3 stages, 2: 6 stages)
+extern std::atomic<int> g_mimo_rt_waves; // waves of resident CTAs the segment chunking aims at
 
 typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                            const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -76,16 +79,18 @@ static int rt_encode_map(CUtensorMap *tm, void *base, uint64_t d0, uint64_t d1, 
 // k_mac_rt: CTA shape by problem (8 or 16 outputs x 4, 8 or 16 streams) and the segment chunking that fills ONE wave of
 // resident CTAs (the partial spectra have no input dimension, so a chunk is cheap: Z * NS * OUT rows)
 struct RtPlan {
-    int wo = 1, ws = 1, zchunks = 1, zlen = 1, out_groups = 1, stream_groups = 1;
+    int wo = 1, ws = 1, wb = 1, r = 4, zchunks = 1, out_groups = 1, stream_groups = 1;
     size_t smem = 0;
     int threads = 32, per_sm = 1;
 };
-template <int WO, int WS>
+template <int WO, int WS, int WB, int R>
 static void rt_shape(RtPlan &p)
 {
-    using Cfg = RtCfg<WO, WS>;
+    using Cfg = RtCfg<WO, WS, WB, R>;
+    p.r = R;
     p.wo = WO;
     p.ws = WS;
+    p.wb = WB;
     p.smem = Cfg::SMEM;
     p.threads = Cfg::THREADS;
     const int by_smem = (int)((227 * 1024) / (Cfg::SMEM + 1024));
@@ -95,34 +100,52 @@ static RtPlan rt_plan(int B, int n_out, int n_streams, int nsegs)
 {
     RtPlan p;
     const bool o16 = n_out > 8;
-    const int sw = n_streams > 8 ? 4 : n_streams > 4 ? 2 : 1;
-    if (o16) sw == 4 ? rt_shape<2, 4>(p) : sw == 2 ? rt_shape<2, 2>(p) : rt_shape<2, 1>(p);
-    else sw == 4 ? rt_shape<1, 4>(p) : sw == 2 ? rt_shape<1, 2>(p) : rt_shape<1, 1>(p);
+    // streams per CTA: 16, 8 or 4 — the widest shape whose padding (stream rows that exist only as zeros) stays under a
+    // quarter of the work: 24 streams run as 3 groups of 8, not as 2 groups of 16
+    int sw = 1;
+    for (int c = 4; c >= 1; c /= 2) {
+        const int padded = (n_streams + 4 * c - 1) / (4 * c) * (4 * c);
+        if (4 * (padded - n_streams) <= padded || c == 1) {
+            sw = c;
+            break;
+        }
+    }
+    // two warps side by side along the bins (512-byte runs per TMA row instead of 256) when the block has the bins
+    const bool wide = B >= 2 * RT_BINS && g_mimo_rt_wb.load() >= 2;
+    const int wo = o16 ? 2 : 1, wb = wide ? 2 : 1, r = g_mimo_rt_r.load();
+#define FCB_RT_SHAPE(WO, WS, WB)                                                      \
+    if (wo == WO && sw == WS && wb == WB) {                                           \
+        if (r == 2) rt_shape<WO, WS, WB, 2>(p);                                       \
+        else rt_shape<WO, WS, WB, 4>(p);                                              \
+    }
+    FCB_RT_SHAPE(2, 4, 1) FCB_RT_SHAPE(2, 2, 1) FCB_RT_SHAPE(2, 1, 1) FCB_RT_SHAPE(1, 4, 1) FCB_RT_SHAPE(1, 2, 1) FCB_RT_SHAPE(1, 1, 1)
+    FCB_RT_SHAPE(2, 4, 2) FCB_RT_SHAPE(2, 2, 2) FCB_RT_SHAPE(2, 1, 2) FCB_RT_SHAPE(1, 4, 2) FCB_RT_SHAPE(1, 2, 2) FCB_RT_SHAPE(1, 1, 2)
+#undef FCB_RT_SHAPE
     p.out_groups = (n_out + 8 * p.wo - 1) / (8 * p.wo);
     p.stream_groups = (n_streams + 4 * p.ws - 1) / (4 * p.ws);
-    const long long base = (long long)((B + RT_BINS - 1) / RT_BINS) * p.out_groups * p.stream_groups;
+    const int bins = RT_BINS * p.wb;
+    const long long base = (long long)((B + bins - 1) / bins) * p.out_groups * p.stream_groups;
     const long long slots = 148LL * p.per_sm;
-    long long z = slots / base;
-    const long long zmax = nsegs / (2 * RT_R) > 0 ? nsegs / (2 * RT_R) : 1; // at least two stages of segments per chunk
+    long long z = slots * g_mimo_rt_waves.load() / base;
+    const long long zmax = nsegs / 8 > 0 ? nsegs / 8 : 1; // at least eight segments per chunk
     z = z > zmax ? zmax : z < 1 ? 1 : z;
-    p.zlen = nsegs > 0 ? (int)((nsegs + z - 1) / z) : 1;
-    p.zchunks = nsegs > 0 ? (nsegs + p.zlen - 1) / p.zlen : 0;
+    p.zchunks = nsegs > 0 ? (int)z : 0;
     return p;
 }
-template <int WO, int WS>
+template <int WO, int WS, int WB, int R>
 static int rt_launch_t(const RtArgs &a, const CUtensorMap &tm_ir, const CUtensorMap &tm_ring, cudaStream_t st)
 {
-    using Cfg = RtCfg<WO, WS>;
+    using Cfg = RtCfg<WO, WS, WB, R>;
     static bool opted = false;
     if (!opted) {
-        if (cudaFuncSetAttribute(k_mac_rt<WO, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_mac_rt<WO, WS, WB, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
             return fail(FCB_ERR_CUDA, "k_mac_rt: cannot opt in to %zu bytes of shared memory", (size_t)Cfg::SMEM);
         opted = true;
     }
-    const long long grid = (long long)((a.B + RT_BINS - 1) / RT_BINS) * a.zchunks * a.out_groups * a.stream_groups;
+    const long long grid = (long long)((a.B + Cfg::BINS - 1) / Cfg::BINS) * a.zchunks * a.out_groups * a.stream_groups;
     cudaEvent_t prof_stop = nullptr;
     const bool profiled = mac_profile_begin(st, &prof_stop) != nullptr;
-    k_mac_rt<WO, WS><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(a, tm_ir, tm_ring);
+    k_mac_rt<WO, WS, WB, R><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(a, tm_ir, tm_ring);
     if (profiled) cudaEventRecord(prof_stop, st);
     g_launches++;
     FCB_CUDA(cudaGetLastError());
@@ -130,8 +153,13 @@ static int rt_launch_t(const RtArgs &a, const CUtensorMap &tm_ir, const CUtensor
 }
 static int rt_launch(const RtPlan &p, const RtArgs &a, const CUtensorMap &tm_ir, const CUtensorMap &tm_ring, cudaStream_t st)
 {
-    if (p.wo == 2) return p.ws == 4 ? rt_launch_t<2, 4>(a, tm_ir, tm_ring, st) : p.ws == 2 ? rt_launch_t<2, 2>(a, tm_ir, tm_ring, st) : rt_launch_t<2, 1>(a, tm_ir, tm_ring, st);
-    return p.ws == 4 ? rt_launch_t<1, 4>(a, tm_ir, tm_ring, st) : p.ws == 2 ? rt_launch_t<1, 2>(a, tm_ir, tm_ring, st) : rt_launch_t<1, 1>(a, tm_ir, tm_ring, st);
+#define FCB_RT_CASE(WO, WS, WB)                                                                                              \
+    if (p.wo == WO && p.ws == WS && p.wb == WB)                                                                              \
+        return p.r == 2 ? rt_launch_t<WO, WS, WB, 2>(a, tm_ir, tm_ring, st) : rt_launch_t<WO, WS, WB, 4>(a, tm_ir, tm_ring, st);
+    FCB_RT_CASE(2, 4, 1) FCB_RT_CASE(2, 2, 1) FCB_RT_CASE(2, 1, 1) FCB_RT_CASE(1, 4, 1) FCB_RT_CASE(1, 2, 1) FCB_RT_CASE(1, 1, 1)
+    FCB_RT_CASE(2, 4, 2) FCB_RT_CASE(2, 2, 2) FCB_RT_CASE(2, 1, 2) FCB_RT_CASE(1, 4, 2) FCB_RT_CASE(1, 2, 2) FCB_RT_CASE(1, 1, 2)
+#undef FCB_RT_CASE
+    return fail(FCB_ERR_ARG, "k_mac_rt: no such shape");
 }
 
 // ---- peer exchange of the partial spectra (replaces the NCCL all-reduce between the MAC and K3) ----
@@ -462,10 +490,10 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
         if (!rc && m->rt) {
             const uint64_t row = B * sizeof(float2), per_pair = m->rows() * row, per_ring = m->S * row;
             rc = rt_encode_map(&m->tm_rt_ir, m->ir + (first - m->seg_lo) * B, 2 * B, m->seg_hi - first, m->n_in, m->n_out, row,
-                               per_pair, m->n_in * per_pair, 2 * RT_BINS, RT_R, 8 * m->rt_plan_.wo);
+                               per_pair, m->n_in * per_pair, 2 * RT_BINS * m->rt_plan_.wb, m->rt_plan_.r, 8 * m->rt_plan_.wo);
             if (!rc)
                 rc = rt_encode_map(&m->tm_rt_ring, m->ring, 2 * B, m->S, m->n_in, ns, row, per_ring, m->n_in * per_ring,
-                                   2 * RT_BINS, RT_R, 4 * m->rt_plan_.ws);
+                                   2 * RT_BINS * m->rt_plan_.wb, m->rt_plan_.r, 4 * m->rt_plan_.ws);
         }
     }
     if (!rc) rc = mimo_alloc((void **)&m->conv, ns * m->n_out * B * sizeof(float2), m->stream);
@@ -622,7 +650,6 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
         t.seg_hi = seg_hi;
         t.seg_base = seg_lo;
         t.zchunks = m->rt_plan_.zchunks;
-        t.zlen = m->rt_plan_.zlen;
         t.out_groups = m->rt_plan_.out_groups;
         t.stream_groups = m->rt_plan_.stream_groups;
         FCB_TRY(rt_launch(m->rt_plan_, t, m->tm_rt_ir, m->tm_rt_ring, m->stream));

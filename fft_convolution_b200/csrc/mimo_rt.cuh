@@ -29,17 +29,24 @@
 
 namespace fcb {
 
-constexpr int RT_BINS = 32; // bins per CTA: one lane each
-constexpr int RT_R = 4;     // segments per pipeline stage
-constexpr int RT_NST = 3;   // stages
+// Packed FP32 (fma.rn.f32x2, FFMA2) halves the issue slots but not the time: measured on the B200 the FFMA2 form of this
+// loop is math-pipe throttled at one FFMA2 per 4 cycles per scheduler — the same FLOP rate the scalar FFMAs reach — and
+// 16 streams take 0.420 ms instead of 0.406 (profiles/r02_k_mac_rt_notes.txt).  Kept for the record, off.
+#ifndef RT_FFMA2
+#define RT_FFMA2 0
+#endif
+constexpr int RT_BINS = 32; // bins per warp: one lane each
+// segments per pipeline stage R and stages NST = 12 / R: the same bytes in flight as 3 stages of 4 or 6 stages of 2
 
-template <int WO, int WS>
+template <int WO, int WS, int WB, int R_>
 struct RtCfg {
-    static constexpr int OUTS = 8 * WO, STREAMS = 4 * WS, WARPS = WO * WS, THREADS = 32 * WARPS;
-    static constexpr int ROW = 2 * RT_BINS;                       // floats of one (row, segment) piece
-    static constexpr int H_FLOATS = OUTS * RT_R * ROW, X_FLOATS = STREAMS * RT_R * ROW;
+    static constexpr int R = R_, NST = 12 / R_;
+    static constexpr int OUTS = 8 * WO, STREAMS = 4 * WS, WARPS = WO * WS * WB, THREADS = 32 * WARPS;
+    static constexpr int BINS = RT_BINS * WB;                     // bins per CTA: WB warps side by side
+    static constexpr int ROW = 2 * BINS;                          // floats of one (row, segment) piece
+    static constexpr int H_FLOATS = OUTS * R * ROW, X_FLOATS = STREAMS * R * ROW;
     static constexpr int STAGE_BYTES = (H_FLOATS + X_FLOATS) * 4;
-    static constexpr size_t SMEM = (size_t)RT_NST * STAGE_BYTES + 2 * RT_NST * sizeof(uint64_t);
+    static constexpr size_t SMEM = (size_t)NST * STAGE_BYTES + NST * (sizeof(uint64_t) + sizeof(unsigned int));
     static constexpr int MIN_CTAS = 512 / THREADS > 8 ? 8 : 512 / THREADS; // <= 128 registers per thread
     static_assert(STAGE_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
 };
@@ -50,20 +57,42 @@ struct RtArgs {
     int S, current;        // ring length and the slot of the current block
     int seg_lo, seg_hi;    // segments accumulated, seg_lo >= 1
     int seg_base;          // the segment at coordinate 0 of the IR tensor map
-    int zchunks, zlen;     // segment chunks and their length
+    int zchunks;           // segment chunks, cut in units of R segments (see the kernel)
     int out_groups, stream_groups;
 };
 
 // acc[o][s] += h[o] * x[s] for RT_R (or cnt) segments of one stage.  PACKED: the CTA holds bin 0 = {DC, Nyquist},
 // two real products for the one lane `p0` (x.y is replaced by 0 in both cross terms and x.x by x.y in the last one).
-template <bool PACKED>
+template <bool PACKED, int ROW, int RT_R>
 __device__ __forceinline__ void rt_row(float2 (&acc)[8][4], const float *hs, const float *xs, int r, bool p0)
 {
     float2 x[4], h[8];
 #pragma unroll
-    for (int s = 0; s < 4; s++) x[s] = *reinterpret_cast<const float2 *>(xs + (s * RT_R + r) * (2 * RT_BINS));
+    for (int s = 0; s < 4; s++) x[s] = *reinterpret_cast<const float2 *>(xs + (s * RT_R + r) * ROW);
 #pragma unroll
-    for (int o = 0; o < 8; o++) h[o] = *reinterpret_cast<const float2 *>(hs + (o * RT_R + r) * (2 * RT_BINS));
+    for (int o = 0; o < 8; o++) h[o] = *reinterpret_cast<const float2 *>(hs + (o * RT_R + r) * ROW);
+#if RT_FFMA2
+    // packed FP32 (fma.rn.f32x2: one issue slot for the two FMAs of an accumulator's (re, im) pair):
+    //     acc += (x.x, x.x) * (h.x, h.y);   acc += (x.y, x.y) * (-h.y, h.x)
+    // FFMA2 takes a broadcast scalar, a swapped pair and a per-half negation as operand forms, so no operand needs
+    // preparing.  Bin-0 lane: (x.x, x.y) * (h.x, h.y) and nothing else.
+    float2 xa[4], xb[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        xa[s] = make_float2(x[s].x, (PACKED && p0) ? x[s].y : x[s].x);
+        const float t = (PACKED && p0) ? 0.f : x[s].y;
+        xb[s] = make_float2(t, t);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; o++) {
+        const float2 hj = make_float2(-h[o].y, h[o].x);
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            acc[o][s] = __ffma2_rn(xa[s], h[o], acc[o][s]);
+            acc[o][s] = __ffma2_rn(xb[s], hj, acc[o][s]);
+        }
+    }
+#else
     float xt[4], xq[4];
 #pragma unroll
     for (int s = 0; s < 4; s++) {
@@ -77,110 +106,118 @@ __device__ __forceinline__ void rt_row(float2 (&acc)[8][4], const float *hs, con
             acc[o][s].x = fmaf(h[o].x, x[s].x, fmaf(-h[o].y, xt[s], acc[o][s].x));
             acc[o][s].y = fmaf(h[o].x, xt[s], fmaf(h[o].y, xq[s], acc[o][s].y));
         }
+#endif
 }
 
-template <bool PACKED>
-__device__ __forceinline__ void rt_stage(float2 (&acc)[8][4], const float *hs, const float *xs, int cnt, bool p0)
-{
-    if (cnt == RT_R) {
-#pragma unroll
-        for (int r = 0; r < RT_R; r++) rt_row<PACKED>(acc, hs, xs, r, p0);
-    } else {
-        for (int r = 0; r < cnt; r++) rt_row<PACKED>(acc, hs, xs, r, p0);
-    }
-}
-
-template <int WO, int WS>
-__global__ void __launch_bounds__(RtCfg<WO, WS>::THREADS, RtCfg<WO, WS>::MIN_CTAS)
+template <int WO, int WS, int WB, int R>
+__global__ void __launch_bounds__(RtCfg<WO, WS, WB, R>::THREADS, RtCfg<WO, WS, WB, R>::MIN_CTAS)
 k_mac_rt(RtArgs a, const __grid_constant__ CUtensorMap tm_ir, const __grid_constant__ CUtensorMap tm_ring)
 {
-    using Cfg = RtCfg<WO, WS>;
+    using Cfg = RtCfg<WO, WS, WB, R>;
     extern __shared__ __align__(1024) unsigned char rt_smem[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(rt_smem + RT_NST * Cfg::STAGE_BYTES), *empty = full + RT_NST;
+    uint64_t *full = reinterpret_cast<uint64_t *>(rt_smem + Cfg::NST * Cfg::STAGE_BYTES);
+    unsigned int *left = reinterpret_cast<unsigned int *>(full + Cfg::NST); // warps that have left a stage
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // blockIdx.x = tile + TILES*(z + Z*(og + OG*sg))
-    const int tiles = (a.B + RT_BINS - 1) / RT_BINS;
+    // blockIdx.x = sg + SG*(og + OG*(tile + TILES*z)): the CTAs that read the same IR tiles (stream groups) and the same
+    // ring tiles (output groups) are neighbours in launch order, so the second reader finds them in L2
+    const int tiles = (a.B + Cfg::BINS - 1) / Cfg::BINS;
     int bid = blockIdx.x;
-    const int tile = bid % tiles;
-    bid /= tiles;
-    const int z = bid % a.zchunks;
-    bid /= a.zchunks;
-    const int og = bid % a.out_groups, sg = bid / a.out_groups;
-    const int lo = a.seg_lo + z * a.zlen;
-    const int hi = (lo + a.zlen) < a.seg_hi ? (lo + a.zlen) : a.seg_hi;
-    // slots run upwards with the segments and wrap once: runs [lo, w) and [w, hi)
+    const int sg = bid % a.stream_groups;
+    bid /= a.stream_groups;
+    const int og = bid % a.out_groups;
+    bid /= a.out_groups;
+    const int tile = bid % tiles, z = bid / tiles;
+    // Chunk z owns the R-segment units [U*z/Z, U*(z+1)/Z) of the range: every chunk but the last is a whole number of
+    // boxes long, and the last one ends where the IR tensor ends.
+    const int units = (a.seg_hi - a.seg_lo + R - 1) / R;
+    const int lo = a.seg_lo + R * (int)((long long)units * z / a.zchunks);
+    int hi = a.seg_lo + R * (int)((long long)units * (z + 1) / a.zchunks);
+    hi = hi < a.seg_hi ? hi : a.seg_hi;
+    // Slots run upwards with the segments and wrap once inside [lo, hi) at most: run A = [lo, w) takes its boxes from
+    // lo upwards, run B = [w, hi) from hi downwards.  Every box is a full R rows; the rows a box has too many are rows
+    // the TMA unit fills with zeros in one of the two operands, so they add nothing: past the end of run A the ring
+    // slots are >= S, before the start of run B they are < 0, and past the end of the last chunk the IR rows are past
+    // the tensor.
     int w = lo + (a.S - (a.current + lo) % a.S);
     w = w < hi ? w : hi;
-    const int nA = hi > lo ? (w - lo + RT_R - 1) / RT_R : 0, nB = hi > w ? (hi - w + RT_R - 1) / RT_R : 0;
+    const int nA = hi > lo ? (w - lo + R - 1) / R : 0, nB = hi > w ? (hi - w + R - 1) / R : 0;
     const int per_in = nA + nB, total = per_in * a.n_in;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < RT_NST; s++) {
+        for (int s = 0; s < Cfg::NST; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], Cfg::WARPS);
+            left[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    auto first_seg = [&](int c) { return c < nA ? lo + c * RT_R : w + (c - nA) * RT_R; };
-    // producer state (warp 0, kept by every lane; one elected lane issues): the next stage to fill is (p_in, p_c)
-    int p_in = 0, p_c = 0, p_left = total;
-    auto issue = [&](int s) {
-        const int i0 = first_seg(p_c);
-        if (elect_one()) {
-            unsigned char *st = rt_smem + s * Cfg::STAGE_BYTES;
-            mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-            tma_load_4d(st, &tm_ir, 2 * tile * RT_BINS, i0 - a.seg_base, p_in, og * Cfg::OUTS, &full[s]);
-            int j0 = a.current + i0;
-            j0 = j0 >= a.S ? j0 - a.S : j0; // current < S and i0 < S
-            tma_load_4d(st + Cfg::H_FLOATS * 4, &tm_ring, 2 * tile * RT_BINS, j0, p_in, sg * Cfg::STREAMS, &full[s]);
-        }
-        __syncwarp();
-        if (++p_c == per_in) {
-            p_c = 0;
-            p_in++;
-        }
-        p_left--;
+    // fill stage s with box c of input `in` (one thread)
+    auto issue = [&](int s, int in, int c) {
+        const int i0 = c < nA ? lo + c * R : hi - (per_in - c) * R;
+        const int j0 = c < nA ? (a.current + lo) % a.S + c * R : i0 - w;
+        unsigned char *st = rt_smem + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        tma_load_4d(st, &tm_ir, 2 * tile * Cfg::BINS, i0 - a.seg_base, in, og * Cfg::OUTS, &full[s]);
+        tma_load_4d(st + Cfg::H_FLOATS * 4, &tm_ring, 2 * tile * Cfg::BINS, j0, in, sg * Cfg::STREAMS, &full[s]);
     };
-    if (warp == 0)
-        for (int s = 0; s < RT_NST && p_left > 0; s++) issue(s);
+    // the box NST iterations ahead of the current one (kept by every thread; whoever refills a stage uses it)
+    int n_in = 0, n_c = 0;
+    auto advance = [&]() {
+        if (++n_c == per_in) {
+            n_c = 0;
+            n_in++;
+        }
+    };
+    for (int s = 0; s < Cfg::NST; s++) {
+        if (threadIdx.x == 0 && s < total) issue(s, n_in, n_c);
+        advance();
+    }
 
-    const int wo = warp / WS, ws = warp % WS;
-    const bool p0 = tile == 0 && lane == 0;
-    const float *hs0 = reinterpret_cast<const float *>(rt_smem) + wo * 8 * RT_R * Cfg::ROW + 2 * lane;
-    const float *xs0 = reinterpret_cast<const float *>(rt_smem) + Cfg::H_FLOATS + ws * 4 * RT_R * Cfg::ROW + 2 * lane;
+    const int wb = warp % WB, wo = (warp / WB) / WS, ws = (warp / WB) % WS;
+    const bool p0 = tile == 0 && wb == 0 && lane == 0;
+    const float *hs0 = reinterpret_cast<const float *>(rt_smem) + wo * 8 * R * Cfg::ROW + 2 * (wb * RT_BINS + lane);
+    const float *xs0 = reinterpret_cast<const float *>(rt_smem) + Cfg::H_FLOATS + ws * 4 * R * Cfg::ROW + 2 * (wb * RT_BINS + lane);
     float2 acc[8][4];
 #pragma unroll
     for (int o = 0; o < 8; o++)
 #pragma unroll
         for (int s = 0; s < 4; s++) acc[o][s] = make_float2(0.f, 0.f);
 
-    int s = 0, ph = 0, c = 0, prev_s = 0, prev_ph = 0; // stage and phase of this iteration and of the one before
+    // No producer warp and no warp waiting for the others: the LAST warp to leave a stage refills it (a counter in shared
+    // memory, one atomic per warp and stage), so the load for iteration it + NST starts the moment stage it % NST is free.
+    int s = 0, ph = 0;
     for (int it = 0; it < total; it++) {
-        if (warp == 0 && it >= 1 && p_left > 0) { // refill the stage every warp left at it - 1
-            mbar_wait(&empty[prev_s], prev_ph);
-            issue(prev_s);
-        }
         mbar_wait(&full[s], ph);
-        const int i0 = first_seg(c), end = c < nA ? w : hi;
-        const int cnt = (end - i0) < RT_R ? (end - i0) : RT_R;
         const float *hs = hs0 + s * (Cfg::STAGE_BYTES / 4), *xs = xs0 + s * (Cfg::STAGE_BYTES / 4);
-        if (tile == 0) rt_stage<true>(acc, hs, xs, cnt, p0);
-        else rt_stage<false>(acc, hs, xs, cnt, false);
+        if (tile == 0 && wb == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r++) rt_row<true, Cfg::ROW, R>(acc, hs, xs, r, p0);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) rt_row<false, Cfg::ROW, R>(acc, hs, xs, r, false);
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        prev_s = s;
-        prev_ph = ph;
-        if (++s == RT_NST) {
+        if (lane == 0) {
+            __threadfence_block(); // this warp's reads of the stage are done before the count says so
+            if (atomicAdd(&left[s], 1u) == Cfg::WARPS - 1) {
+                left[s] = 0; // nobody counts on this stage again before the refill below has landed
+                __threadfence_block();
+                if (it + Cfg::NST < total) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(s, n_in, n_c);
+                }
+            }
+        }
+        advance();
+        if (++s == Cfg::NST) {
             s = 0;
             ph ^= 1;
         }
-        if (++c == per_in) c = 0;
     }
 
-    const int k = tile * RT_BINS + lane;
+    const int k = tile * Cfg::BINS + wb * RT_BINS + lane;
     if (k < a.B) {
 #pragma unroll
         for (int s = 0; s < 4; s++) {

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="how IR-partition shards exchange partial spectra")
     ap.add_argument("--tc", type=int, default=-1, help="1/0 force the tensor-core matrix MAC (K4) on/off, -1 library default")
     ap.add_argument("--rt", type=int, default=1, help="0: the shared-memory tile kernel instead of the register-tiled MAC (k_mac_rt) below the tensor-core threshold")
+    ap.add_argument("--tune", default="", help="extra fcb_tune settings, e.g. mimo_rt_wb=1,mimo_tc_min=40")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -43,6 +44,9 @@ def main():
     from fft_convolution_b200 import _lib
     lib = _lib.load()
     _lib.check(lib.fcb_tune(b"mimo_rt", a.rt))
+    for kv in filter(None, a.tune.split(",")):
+        k, v = kv.split("=")
+        _lib.check(lib.fcb_tune(k.encode(), int(v)))
     N, B, L, NS = a.n, a.block, int(a.ir_seconds * 48000), a.streams
     h = bench.synth_irs(0, N * N, 0, L).reshape(N, N, L)  # IR index c = out*N + in
     m = ShardedMimoConvolver(h, B, L, n_streams=NS, device=local, tensor_cores=None if a.tc < 0 else bool(a.tc), exchange=a.exchange)
