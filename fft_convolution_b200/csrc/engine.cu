@@ -237,7 +237,8 @@ namespace fcb { std::atomic<int> g_mimo_tc{2}; }
 namespace fcb { std::atomic<int> g_mimo_tc_min{33}; }  // streams from which mimo_tc == 2 picks the tensor cores
 namespace fcb { std::atomic<int> g_mimo_rt_wb{1}; }
 namespace fcb { std::atomic<int> g_mimo_rt_r{4}; }
-namespace fcb { std::atomic<int> g_mimo_rt_waves{2}; }
+namespace fcb { std::atomic<int> g_mimo_rt_min{1}; }
+namespace fcb { std::atomic<int> g_mimo_rt_waves{0}; }
 namespace fcb { std::atomic<bool> g_mimo_rt{true}; }   // register-tiled matrix MAC (k_mac_rt) for 2+ streams below that
 static std::atomic<bool> g_split{true};        // small batches: cut the delay line of a whole block over several CTAs
 static std::atomic<bool> g_multi_block{true}; // calls spanning >= 2 whole blocks run as one time-batched pass       // K4 tensor-core matrix MAC: 0 never, 1 when the shape fits, 2 + NS >= 16
@@ -682,8 +683,9 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "mimo_tc_min") && value >= 1) g_mimo_tc_min = value;
     else if (!strcmp(key, "mimo_rt")) g_mimo_rt = value != 0;
     else if (!strcmp(key, "mimo_rt_wb") && (value == 1 || value == 2)) g_mimo_rt_wb = value;
+    else if (!strcmp(key, "mimo_rt_min") && value >= 1) g_mimo_rt_min = value;
     else if (!strcmp(key, "mimo_rt_r") && (value == 2 || value == 4)) g_mimo_rt_r = value;
-    else if (!strcmp(key, "mimo_rt_waves") && value >= 1 && value <= 16) g_mimo_rt_waves = value;
+    else if (!strcmp(key, "mimo_rt_waves") && value >= 0 && value <= 16) g_mimo_rt_waves = value;
     else if (!strcmp(key, "multi_block")) g_multi_block = value != 0;
     else if (!strcmp(key, "fused_block")) g_fused_block = value != 0;
     else if (!strcmp(key, "fused_stages") && (value == 2 || value == 3)) g_fused_stages = value;

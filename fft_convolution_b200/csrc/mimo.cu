@@ -24,6 +24,7 @@ extern std::atomic<int> g_mimo_tc; // 0 never, 1 whenever the shape fits, 2 (def
 extern std::atomic<int> g_mimo_tc_min; // fewer streams than this run on the FP32 pipes (k_mac_rt)
 extern std::atomic<bool> g_mimo_rt;    // register-tiled matrix MAC for 2+ streams (0: the shared-memory tile kernel)
 extern std::atomic<int> g_mimo_rt_wb;  // warps side by side along the bins in k_mac_rt (1 or 2)
+extern std::atomic<int> g_mimo_rt_min; // streams from which k_mac_rt replaces the tile kernel
 extern std::atomic<int> g_mimo_rt_r;   // segments per pipeline stage (4: 3 stages, 2: 6 stages)
 extern std::atomic<int> g_mimo_rt_waves; // waves of resident CTAs the segment chunking aims at
 
@@ -126,7 +127,10 @@ static RtPlan rt_plan(int B, int n_out, int n_streams, int nsegs)
     const int bins = RT_BINS * p.wb;
     const long long base = (long long)((B + bins - 1) / bins) * p.out_groups * p.stream_groups;
     const long long slots = 148LL * p.per_sm;
-    long long z = slots * g_mimo_rt_waves.load() / base;
+    // one wave of CTAs while the operands' HBM time dominates (up to 8 streams: fewer partial rows), two from there on
+    // (the FP32 pipes dominate and the second wave evens out the CTAs' finishing times); measured, profiles/r02_k_mac_rt_notes.txt
+    const int waves = g_mimo_rt_waves.load() > 0 ? g_mimo_rt_waves.load() : n_streams <= 8 ? 1 : 2;
+    long long z = slots * waves / base;
     const long long zmax = nsegs / 8 > 0 ? nsegs / 8 : 1; // at least eight segments per chunk
     z = z > zmax ? zmax : z < 1 ? 1 : z;
     p.zchunks = nsegs > 0 ? (int)z : 0;
@@ -480,7 +484,7 @@ extern "C" int fcb_mimo_create(const fcb_mimo_desc *d, fcb_mimo **out)
         if (mac_tile_plan(m->logb, (int)m->n_in, (int)m->n_out, (int)ns, (int)m->rows(), &z, &zl) == FCB_OK) m->zmax = z;
         size_t part_rows = (size_t)m->zmax * ns * pairs;
         const size_t first = m->seg_lo > 1 ? m->seg_lo : 1; // segment 0 belongs to the reduce kernel
-        m->rt = g_mimo_rt.load() && ns >= 2 && B >= (size_t)RT_BINS && m->seg_hi > first;
+        m->rt = g_mimo_rt.load() && ns >= (size_t)g_mimo_rt_min.load() && B >= (size_t)RT_BINS && m->seg_hi > first;
         if (m->rt) {
             m->rt_plan_ = rt_plan((int)B, (int)m->n_out, (int)ns, (int)(m->seg_hi - first));
             const size_t need = (size_t)m->rt_plan_.zchunks * ns * m->n_out;

@@ -60,8 +60,9 @@ uint64_t fcb_debug_alloc_count(void);
  * "mac_stages" (2, 3, 4, 6 pipeline stages of 32 KB), "pipe_group" (channels per group of the
  * end-to-end copy/compute pipeline, default 512), "mimo_tile" (1 = matrix K2 with in-CTA reuse of
  * IR and ring tiles, 0 = the per-channel K2), "mimo_tc" (the tensor-core matrix MAC K4: 0 = never, 1 = always,
- * 2 = when at least "mimo_tc_min" streams share the matrix; read by fcb_mimo_create), "mimo_rt" (1 = 2+ streams below that threshold run
- * the register-tiled matrix MAC k_mac_rt, 0 = the shared-memory tile kernel), "fused_block" (1 = whole blocks with B in 32..512 run as
+ * 2 = when at least "mimo_tc_min" streams share the matrix; read by fcb_mimo_create), "mimo_rt" (1 = fewer streams than that run
+ * the register-tiled matrix MAC k_mac_rt, 0 = the shared-memory tile kernel; sweeps: "mimo_rt_min" = streams from which it is used, "mimo_rt_waves" = waves
+ * of CTAs its segment chunking aims at (0 = by stream count), "mimo_rt_r" = segments per pipeline stage (4 or 2), "mimo_rt_wb" = warps side by side along the bins), "fused_block" (1 = whole blocks with B in 32..512 run as
  * one fused K1+K2+K3 kernel, 0 = three launches; outputs are bit-identical), "fused_stages" (2 or 3), "fused_pair" (1 = convolvers fed the same input share one launch), "fused_short" (delay lines of up to this many segments run
  * the fused kernel with 2-row stages so that a fourth CTA per SM hides the FFT latency; default 40, 0 = off), "mapped_io" (1 = small-batch host
  * calls go through mapped pinned memory instead of the copy engines), "zero_copy" (1 = when the caller's
@@ -403,7 +404,7 @@ int fcb_debug_mac_tile_plan(int logb, int n_in, int n_out, int n_streams, int ns
  * position) and IR position paired with the block's first slot; returns the stage count */
 int fcb_debug_tc_stages(int S, int current, int seg_lo, int seg_hi, int max_stages, int *blk, int *copy, int *pos0);
 /* 1 when this object's delay-line MAC runs as per-bin complex GEMMs on the tensor cores (K4), 2 when it runs as the
- * register-tiled per-bin GEMM on the FP32 pipes (k_mac_rt: 2+ streams below the tensor-core threshold), else 0 */
+ * register-tiled per-bin GEMM on the FP32 pipes (k_mac_rt: stream counts below the tensor-core threshold, blocks of 32+), else 0 */
 int fcb_mimo_uses_tensor_cores(const fcb_mimo *m);
 size_t fcb_mimo_block_size(const fcb_mimo *m);
 size_t fcb_mimo_seg_count(const fcb_mimo *m);

@@ -15,7 +15,7 @@ sys.path.insert(0, str(ROOT))
 import bench  # noqa: E402
 from fft_convolution_b200 import _lib, MimoConvolver  # noqa: E402
 
-DEFAULTS = {"mimo_rt": 1, "mimo_rt_wb": 1, "mimo_rt_r": 4, "mimo_rt_waves": 2, "mimo_tc": 0}
+DEFAULTS = {"mimo_rt": 1, "mimo_rt_wb": 1, "mimo_rt_r": 4, "mimo_rt_waves": 0, "mimo_rt_min": 1, "mimo_tc": 0}
 
 
 def main():

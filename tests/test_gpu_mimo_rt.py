@@ -39,6 +39,7 @@ def _worst(y, ref):
 # several bin tiles, delay lines shorter and longer than a stage, nblocks > S so `current` takes every value (the ring
 # wrap falls into every position of a box)
 @pytest.mark.parametrize("n_out,n_in,B,L,NS,nblocks", [
+    (16, 3, 64, 64 * 25 + 1, 1, 29),     # one stream (BASELINE configs[4] as worded): <2,1>
     (3, 2, 64, 64 * 13 + 5, 2, 20),      # <1,1>
     (8, 3, 32, 32 * 9, 5, 14),           # <1,2>
     (5, 1, 128, 128 * 6 + 1, 11, 10),    # <1,4>
