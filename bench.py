@@ -338,8 +338,9 @@ def run_realtime(F, lib, local, rank, world, chan0, Cn_head, ms_e2e_per_block_he
 
 def run_mimo(local, rank, world, steps, warmup):
     """BASELINE configs[4] under the driver's eyes (N > 1): 16 x 16 matrix, 10 s IRs, block 512, the IR partitions
-    sharded over the N GPUs; 1 stream (CUDA-core matrix kernel) and 128 streams (tcgen05 K4); partial spectra exchanged
-    by peer stores over NVLink and by an NCCL all-reduce; the first blocks are checked against the unsharded engine."""
+    sharded over the N GPUs; 1 and 16 streams (k_mac_rt, the register-tiled matrix MAC on the FP32 pipes) and 128 streams
+    (tcgen05 K4); partial spectra exchanged by peer stores over NVLink and by NCCL; block 520 is checked against the
+    unsharded engine (a failed check is reported in the entry, it does not end the run: the ranks must stay in step)."""
     import torch
     import torch.distributed as dist
     import fft_convolution_b200 as F
@@ -347,7 +348,7 @@ def run_mimo(local, rank, world, steps, warmup):
     N, B, L = 16, 512, 10 * SAMPLE_RATE
     h = synth_irs(0, N * N, 0, L).reshape(N, N, L)
     res = {"config": f"MIMO {N}x{N}, IR 10 s ({L} taps, S = {(L + B - 1) // B}), block {B}, IR partitions sharded over {world} GPUs"}
-    for NS in (1, 128):
+    for NS in (1, 16, 128):
         x = [torch.from_numpy(synth_noise(0, NS * N, B * i, B)).cuda(local) for i in range(8)]
         ref = None
         NCHK = 520  # past half of the 938-slot ring: every shard's segment range has met real input spectra
@@ -377,7 +378,7 @@ def run_mimo(local, rank, world, steps, warmup):
                 got = out.cpu().numpy()[lo:hi]
                 err = float(np.max(np.abs(got - ref[lo:hi]))) / max(float(np.sqrt(np.mean(ref[lo:hi].astype(np.float64) ** 2))), 1e-9)
                 if err > 1e-5:
-                    raise SystemExit(f"bench.py: sharded matrix differs from the unsharded engine: {err:.3e} x RMS")
+                    print(f"bench.py: sharded matrix ({NS} streams, {exchange}) differs from the unsharded engine: {err:.3e} x RMS", file=sys.stderr)
             for i in range(warmup):
                 m.process_dev(x[i % 8], out)
             torch.cuda.synchronize()
@@ -392,6 +393,7 @@ def run_mimo(local, rank, world, steps, warmup):
             ms = reduce_max([e0.elapsed_time(e1) / steps], device=f"cuda:{local}")[0]
             res[f"streams{NS}_{exchange}" + ("_reduce_scatter" if scatter else "")] = {
                 "ms_per_block": ms, "realtime_factor": 1000.0 * B / SAMPLE_RATE / ms, "tensor_cores": bool(m.m.uses_tensor_cores),
+                "mac_kernel": m.m.mac_kernel, "parity_ok": None if err is None else bool(err <= 1e-5),
                 "output": "sharded by row over the ranks" if scatter else "complete on every rank",
                 "T_cmac_per_s": NS * N * N * ((L + B - 1) // B) * B / (ms / 1e3) / 1e12,
                 "max_abs_err_over_rms_vs_unsharded_after_520_blocks": err}
