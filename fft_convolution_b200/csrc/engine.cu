@@ -671,6 +671,7 @@ int run_mac_tile(int logb, cudaStream_t st, MacTileArgs a, int *zchunks_out)
 extern "C" void fcb_host_mirror_set_mapped_io(int on);
 extern "C" void fcb_host_mirror_set_zero_copy(int on);
 extern "C" void fcb_host_mirror_set_strict_todo(int on);
+extern "C" void fcb_host_mirror_set_xf_speculate(int on);
 
 extern "C" int fcb_tune(const char *key, int value)
 {
@@ -700,6 +701,7 @@ extern "C" int fcb_tune(const char *key, int value)
     else if (!strcmp(key, "mapped_io")) fcb_host_mirror_set_mapped_io(value);
     else if (!strcmp(key, "zero_copy")) fcb_host_mirror_set_zero_copy(value);
     else if (!strcmp(key, "strict_todo")) fcb_host_mirror_set_strict_todo(value);
+    else if (!strcmp(key, "xf_speculate")) fcb_host_mirror_set_xf_speculate(value);
     else return fail(FCB_ERR_ARG, "fcb_tune: unknown key/value %s=%d", key, value);
     return FCB_OK;
 }

@@ -312,6 +312,10 @@ static bool g_zero_copy = true; // fcb_tune("zero_copy", 0): never let kernels t
 extern "C" void fcb_host_mirror_set_mapped_io(int on) { g_mapped_io = on != 0; }
 extern "C" void fcb_host_mirror_set_zero_copy(int on) { g_zero_copy = on != 0; }
 
+// fcb_tune("xf_speculate", 0): the crossfade host call computes every block's gains on the critical path again
+static bool g_xf_speculate = true;
+extern "C" void fcb_host_mirror_set_xf_speculate(int on) { g_xf_speculate = on != 0; }
+
 // device-visible alias of a pinned (page-locked) host pointer, or NULL for pageable / device memory
 static float *pinned_alias(const float *p)
 {
@@ -1065,6 +1069,15 @@ struct fcb_crossfade {
     cudaStream_t stream = nullptr;
     int device = 0;
     float2 *h_gains = nullptr, *d_gains = nullptr;  // pinned / device, max_buffer_size each
+    // Gains of the NEXT call, computed by the synchronous host call while the GPU works on the current block (the
+    // per-sample state machine costs ~20 ns a sample: 10 us per 512-sample block, otherwise ahead of the launch).
+    // `crossfader` itself is not advanced: the speculated copy replaces it when the next call really asks for
+    // `spec_len` samples, and anything else that touches the crossfader (swap, reset, clone) drops the speculation.
+    std::vector<float2> spec_gains;
+    Crossfader spec_after;
+    size_t spec_len = 0;
+    bool spec_valid = false, spec_all_a = false, spec_all_b = false;
+    bool gains_in_flight = false; // h_gains was handed to an upload nobody has waited for yet
     cudaEvent_t ev_gains = nullptr;
     float *d_in = nullptr, *d_out = nullptr;        // host-call staging, [C][max_buffer_size] each (allocated in new())
     float *h_in = nullptr, *h_out = nullptr, *m_in = nullptr, *m_out = nullptr; // small batches: mapped pinned staging
@@ -1136,6 +1149,7 @@ extern "C" int fcb_crossfade_new(fcb_crossfade **out, fcb_fftconv *convolver, si
     cu(cudaMalloc(&c->stored_response, c->C * (max_response_length ? max_response_length : 1) * sizeof(float))); // :26
     cu(cudaMalloc(&c->d_gains, n * sizeof(float2)));
     cu(cudaHostAlloc(&c->h_gains, n * sizeof(float2), cudaHostAllocDefault));
+    c->spec_gains.resize(n); // sized here once: process() never allocates
     cu(cudaMalloc(&c->d_out, c->C * n * sizeof(float)));
     cu(cudaMalloc(&c->d_in, c->C * n * sizeof(float)));
     if (rc == FCB_OK && c->C * n * sizeof(float) <= ((size_t)1 << 20)) { // small batches: mapped pinned staging, read and
@@ -1210,6 +1224,7 @@ static int crossfade_swap(fcb_crossfade *c, const float *irs, size_t len, bool f
         if (rc == FCB_OK && len && !c->update_nowait && pinned_alias(irs)) rc = fcb_engine_update_wait(idle->eng);
     }
     c->stored_staged = false;
+    c->spec_valid = false;
     c->crossfader.fade_into(c->crossfader.target == 0 ? 1 : 0);
     return rc;
 }
@@ -1287,14 +1302,25 @@ extern "C" int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in, size
     if (out_len > M) return fail(FCB_ERR_PANIC, "index out of bounds: the len is %zu but the index is %zu", M, M); // :76
 
     // gains for this call, by the reference's per-sample state machine (:75-77 -> :242-278)
-    FCB_CUDA(cudaEventSynchronize(c->ev_gains)); // previous upload has left the pinned buffer
-    bool all_a = true, all_b = true;
-    for (size_t i = 0; i < out_len; i++) {
-        float2 g = c->crossfader.next_gains();
-        c->h_gains[i] = g;
-        all_a = all_a && g.x == 1.f && g.y == 0.f;
-        all_b = all_b && g.x == 0.f && g.y == 1.f;
+    if (c->gains_in_flight) { // (a completed event still costs 1.4 us to ask: scripts/api_cost_probe.cu)
+        FCB_CUDA(cudaEventSynchronize(c->ev_gains)); // previous upload has left the pinned buffer
+        c->gains_in_flight = false;
     }
+    bool all_a = true, all_b = true;
+    if (c->spec_valid && c->spec_len == out_len) { // computed while the previous block was on the GPU
+        memcpy(c->h_gains, c->spec_gains.data(), out_len * sizeof(float2));
+        c->crossfader = c->spec_after;
+        all_a = c->spec_all_a;
+        all_b = c->spec_all_b;
+    } else {
+        for (size_t i = 0; i < out_len; i++) {
+            float2 g = c->crossfader.next_gains();
+            c->h_gains[i] = g;
+            all_a = all_a && g.x == 1.f && g.y == 0.f;
+            all_b = all_b && g.x == 0.f && g.y == 1.f;
+        }
+    }
+    c->spec_valid = false;
 
     // both convolvers always run, each on max_buffer_size samples (:72-73); A and B are independent,
     // so the one whose result is needed last may write straight into `out`
@@ -1310,6 +1336,7 @@ extern "C" int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in, size
         for (size_t i = 0; i < out_len; i++) c->h_gains[i] = make_float2(c->h_gains[i].y, c->h_gains[i].x); // mine = B
         FCB_CUDA(cudaMemcpyAsync(c->d_gains, c->h_gains, out_len * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         FCB_CUDA(cudaEventRecord(c->ev_gains, c->stream));
+        c->gains_in_flight = true;
         fcb_epilogue epi;
         memset(&epi, 0, sizeof epi);
         epi.mix_other = c->buffer_a;
@@ -1331,6 +1358,7 @@ extern "C" int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in, size
         for (size_t i = 0; i < out_len; i++) c->h_gains[i] = make_float2(c->h_gains[i].y, c->h_gains[i].x);
         FCB_CUDA(cudaMemcpyAsync(c->d_gains, c->h_gains, out_len * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         FCB_CUDA(cudaEventRecord(c->ev_gains, c->stream));
+        c->gains_in_flight = true;
         fcb_epilogue epi;
         memset(&epi, 0, sizeof epi);
         epi.mix_other = c->buffer_a;
@@ -1346,6 +1374,7 @@ extern "C" int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in, size
     } else {
         FCB_CUDA(cudaMemcpyAsync(c->d_gains, c->h_gains, out_len * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         FCB_CUDA(cudaEventRecord(c->ev_gains, c->stream));
+        c->gains_in_flight = true;
         long long total = (long long)c->C * (long long)out_len;
         k_mix<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(out, (long long)out_stride, c->buffer_a, c->buffer_b,
                                                                      (long long)M, c->d_gains, (int)out_len,
@@ -1354,6 +1383,28 @@ extern "C" int fcb_crossfade_process_dev(fcb_crossfade *c, const float *in, size
         FCB_CUDA(cudaGetLastError());
     }
     return FCB_OK;
+}
+
+// the gains the next call of `out_len` samples will need, from a copy of the crossfader (see fcb_crossfade::spec_gains)
+static void crossfade_speculate(fcb_crossfade *c, size_t out_len)
+{
+    c->spec_valid = false;
+    // only while a fade runs (otherwise the gains are constants); a fade that ends inside the speculated block is fine:
+    // the pending response (:67-70) is swapped in by the call AFTER the one that ends the fade, with or without this
+    if (!g_xf_speculate || out_len == 0 || out_len > c->spec_gains.size() || !c->crossfader.approaching) return;
+    Crossfader f = c->crossfader;
+    bool all_a = true, all_b = true;
+    for (size_t i = 0; i < out_len; i++) {
+        const float2 g = f.next_gains();
+        c->spec_gains[i] = g;
+        all_a = all_a && g.x == 1.f && g.y == 0.f;
+        all_b = all_b && g.x == 0.f && g.y == 1.f;
+    }
+    c->spec_after = f;
+    c->spec_len = out_len;
+    c->spec_all_a = all_a;
+    c->spec_all_b = all_b;
+    c->spec_valid = true;
 }
 
 extern "C" int fcb_crossfade_process(fcb_crossfade *c, const float *in, size_t in_len, size_t in_stride, float *out,
@@ -1371,14 +1422,18 @@ extern "C" int fcb_crossfade_process(fcb_crossfade *c, const float *in, size_t i
         float *din = pinned_alias(in), *dout = pinned_alias(out);
         if (din && dout) {
             FCB_TRY(fcb_crossfade_process_dev(c, din, n_in, in_stride, dout, out_len, out_stride));
+            crossfade_speculate(c, out_len);
             FCB_CUDA(cudaStreamSynchronize(c->stream));
+            c->gains_in_flight = false;
             return FCB_OK;
         }
     }
     if (c->m_in && g_mapped_io && M) { // small batch: the kernels read and write mapped pinned staging themselves
         for (size_t ch = 0; ch < c->C; ch++) memcpy(c->h_in + ch * M, in + ch * in_stride, n_in * sizeof(float));
         FCB_TRY(fcb_crossfade_process_dev(c, c->m_in, n_in, M, c->m_out, out_len, M));
+        crossfade_speculate(c, out_len);
         FCB_CUDA(cudaStreamSynchronize(c->stream));
+        c->gains_in_flight = false;
         for (size_t ch = 0; ch < c->C; ch++) memcpy(out + ch * out_stride, c->h_out + ch * M, out_len * sizeof(float));
         return FCB_OK;
     }
@@ -1389,7 +1444,9 @@ extern "C" int fcb_crossfade_process(fcb_crossfade *c, const float *in, size_t i
     if (out_len)
         FCB_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float), c->d_out, (M ? M : 1) * sizeof(float),
                                    out_len * sizeof(float), c->C, cudaMemcpyDeviceToHost, c->stream));
+    crossfade_speculate(c, out_len);
     FCB_CUDA(cudaStreamSynchronize(c->stream));
+    c->gains_in_flight = false;
     return FCB_OK;
 }
 
@@ -1410,6 +1467,7 @@ extern "C" int fcb_crossfade_reset(fcb_crossfade *c)
     const size_t n = c->max_buffer_size ? c->max_buffer_size : 1;
     FCB_CUDA(cudaMemsetAsync(c->buffer_a, 0, c->C * n * sizeof(float), c->stream));
     FCB_CUDA(cudaMemsetAsync(c->buffer_b, 0, c->C * n * sizeof(float), c->stream));
+    c->spec_valid = false;
     if (c->crossfader.approaching) {
         c->crossfader.approaching = false;
         c->crossfader.mix_value = c->crossfader.target == 0 ? 0.f : 1.f;
@@ -1452,6 +1510,7 @@ extern "C" int fcb_crossfade_clone(const fcb_crossfade *s, fcb_crossfade **out)
     fcb_fftconv_free(c->a);
     c->a = a;
     c->crossfader = s->crossfader;
+    c->spec_valid = false;
     c->response_pending = s->response_pending;
     c->rings_same = s->rings_same;
     const size_t n = s->max_buffer_size ? s->max_buffer_size : 1, rows = s->b->opt.shared_ir ? 1 : s->C;

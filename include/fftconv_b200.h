@@ -72,7 +72,9 @@ uint64_t fcb_debug_alloc_count(void);
  * the split aims at, "split_min_stages" = pipeline stages per CTA at least), "k1_late" (1 = the fused kernel transforms a block
  * that sits in host memory AFTER its MAC stream; measured without effect, default 0), "strict_todo"
  * (1 = fcb_twostage_update and fcb_crossfade_reset answer FCB_ERR_TODO like the reference's todo!(); default 0 = the
- * extensions documented at those entry points) */
+ * extensions documented at those entry points), "xf_speculate" (1 = the synchronous crossfade host call computes the
+ * NEXT block's per-sample gains while the GPU works on the current one — same gains, same state, off the critical
+ * path; 0 = every block computes its own before its launch) */
 int fcb_tune(const char *key, int value);
 
 /* live timing of the K2 launches: while enabled every K2 launch is bracketed by CUDA events on
