@@ -339,7 +339,8 @@ def run_realtime(F, lib, local, rank, world, chan0, Cn_head, ms_e2e_per_block_he
 def run_mimo(local, rank, world, steps, warmup):
     """BASELINE configs[4] under the driver's eyes (N > 1): 16 x 16 matrix, 10 s IRs, block 512, the IR partitions
     sharded over the N GPUs; 1 and 16 streams (k_mac_rt, the register-tiled matrix MAC on the FP32 pipes) and 128 streams
-    (tcgen05 K4); partial spectra exchanged by peer stores over NVLink and by NCCL; block 520 is checked against the
+    (tcgen05 K4); partial spectra exchanged by peer stores over NVLink and by NCCL, the peer form also with K3 overlapped
+    with the next block's MAC (`_overlap`); block 520 is checked against the
     unsharded engine (a failed check is reported in the entry, it does not end the run: the ranks must stay in step)."""
     import torch
     import torch.distributed as dist
@@ -363,11 +364,12 @@ def run_mimo(local, rank, world, steps, warmup):
             whole.close()
             del whole
         R = NS * N
-        modes = [("peer", False), ("nccl", False)]
-        if NS > 1 and R % world == 0:
-            modes += [("peer", True), ("nccl", True)]  # reduce-scatter: every rank finishes its own R / N output rows
-        for exchange, scatter in modes:
-            m = ShardedMimoConvolver(h, B, L, n_streams=NS, device=local, exchange=exchange, scatter=scatter)
+        # overlap: K3 of a block (the kernel that waits for the peers) beside K1 and the MAC of the next block
+        modes = [("peer", False, False), ("nccl", False, False), ("peer", False, True)]
+        if NS > 1 and R % world == 0:  # reduce-scatter: every rank finishes its own R / N output rows
+            modes += [("peer", True, False), ("nccl", True, False), ("peer", True, True)]
+        for exchange, scatter, overlap in modes:
+            m = ShardedMimoConvolver(h, B, L, n_streams=NS, device=local, exchange=exchange, scatter=scatter, overlap=overlap)
             out = torch.empty((NS * N, B), dtype=torch.float32, device=f"cuda:{local}")
             err = None
             for i in range(NCHK):
@@ -387,14 +389,16 @@ def run_mimo(local, rank, world, steps, warmup):
             e0.record(m.stream)
             for i in range(steps):
                 m.process_dev(x[i % 8], out)
+            m.join()  # overlap: the last block's K3 belongs to the timed region
             e1.record(m.stream)
             torch.cuda.synchronize()
             m.m.sync()  # surfaces a peer-exchange timeout
             ms = reduce_max([e0.elapsed_time(e1) / steps], device=f"cuda:{local}")[0]
-            res[f"streams{NS}_{exchange}" + ("_reduce_scatter" if scatter else "")] = {
+            res[f"streams{NS}_{exchange}" + ("_reduce_scatter" if scatter else "") + ("_overlap" if overlap else "")] = {
                 "ms_per_block": ms, "realtime_factor": 1000.0 * B / SAMPLE_RATE / ms, "tensor_cores": bool(m.m.uses_tensor_cores),
                 "mac_kernel": m.m.mac_kernel, "parity_ok": None if err is None else bool(err <= 1e-5),
                 "output": "sharded by row over the ranks" if scatter else "complete on every rank",
+                "blocks_in_flight": "K3 of block n beside the MAC of block n + 1 (throughput of queued blocks)" if overlap else "one at a time",
                 "T_cmac_per_s": NS * N * N * ((L + B - 1) // B) * B / (ms / 1e3) / 1e12,
                 "max_abs_err_over_rms_vs_unsharded_after_520_blocks": err}
             m.m.close()

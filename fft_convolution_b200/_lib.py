@@ -165,6 +165,8 @@ SIGNATURES = {
     "fcb_mimo_peer_attach": (_i, [_vp, _vp]),
     "fcb_mimo_peer_inbox": (_vp, [_vp]),
     "fcb_mimo_peer_set_scatter": (_i, [_vp, _i]),
+    "fcb_mimo_set_overlap": (_i, [_vp, _i]),
+    "fcb_mimo_join": (_i, [_vp]),
     "fcb_mimo_owned_rows": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "fcb_mimo_finish_rows_dev": (_i, [_vp, _vp, _sz, _sz, _sz]),
     "fcb_mimo_peer_attach_ptrs": (_i, [_vp, _vp]),

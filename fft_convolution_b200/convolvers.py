@@ -404,6 +404,14 @@ class MimoConvolver:
         """reduce-scatter form of the peer exchange: this shard finishes (and outputs) only its own rows"""
         check(_lib.load().fcb_mimo_peer_set_scatter(self._h, 1 if on else 0))
 
+    def set_overlap(self, on: bool) -> None:
+        """peer exchange: K3 (the kernel that waits for the peers) on its own stream beside the next block's MAC;
+        outputs are ordered on the convolver's stream by join(), for the host by sync()"""
+        check(_lib.load().fcb_mimo_set_overlap(self._h, 1 if on else 0))
+
+    def join(self) -> None:
+        check(_lib.load().fcb_mimo_join(self._h))
+
     @property
     def owned_rows(self):
         lo, hi = C.c_size_t(), C.c_size_t()

@@ -347,6 +347,11 @@ struct fcb_mimo {
     bool peer_on = false;
     bool peer_scatter = false;           // reduce-scatter form: this shard finishes (and outputs) its own rows only
     unsigned int peer_seq = 0;
+    // overlapped finish (fcb_mimo_set_overlap, peer exchange only): K3 of block n — the kernel that waits for the peers —
+    // runs on its own stream beside K1 / the MAC of block n + 1; only the reduce of block n + 1 waits for it
+    bool ovl_fin = false, fin_pending = false;
+    cudaStream_t fin = nullptr;
+    cudaEvent_t ev_red = nullptr, ev_fin = nullptr;
     size_t rows_total() const { return n_streams * n_out; }
     size_t row_lo() const { return rows_total() * shard_index / shard_count; }
     size_t row_hi() const { return rows_total() * (shard_index + 1) / shard_count; }
@@ -377,11 +382,39 @@ struct fcb_mimo {
     size_t rows() const { return seg_hi - seg_lo; }
 };
 
+// Overlapped finish.  The reduce of block n + 1 publishes into the inbox slots (parity n + 1) and, two blocks on, a
+// peer's reduce overwrites the slots K3 of block n reads: the protocol's "a peer runs at most one block ahead" rests on
+// every shard's reduce coming after its own previous K3.  With K3 on its own stream that order is kept by two events:
+// reduce(n + 1) waits for K3(n), K3(n) waits for reduce(n) — and nothing else does, so K1 and the MAC of block n + 1 run
+// while K3 of block n waits for the peers' flags.
+static int overlap_before_reduce(fcb_mimo *m)
+{
+    if (m->ovl_fin && m->fin_pending) FCB_CUDA(cudaStreamWaitEvent(m->stream, m->ev_fin, 0));
+    return FCB_OK;
+}
+static int overlap_after_reduce(fcb_mimo *m)
+{
+    if (m->ovl_fin) FCB_CUDA(cudaEventRecord(m->ev_red, m->stream));
+    return FCB_OK;
+}
+// everything queued on the convolver's stream from here on comes after every K3 launched so far
+static int overlap_join(fcb_mimo *m)
+{
+    if (m->fin_pending) FCB_CUDA(cudaStreamWaitEvent(m->stream, m->ev_fin, 0));
+    return FCB_OK;
+}
+
 extern "C" void fcb_mimo_destroy(fcb_mimo *m)
 {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->fin) {
+        cudaStreamSynchronize(m->fin);
+        cudaStreamDestroy(m->fin);
+    }
+    if (m->ev_red) cudaEventDestroy(m->ev_red);
+    if (m->ev_fin) cudaEventDestroy(m->ev_fin);
     cudaFree(m->ir);
     cudaFree(m->ring);
     cudaFree(m->premul);
@@ -566,6 +599,7 @@ extern "C" int fcb_mimo_reset(fcb_mimo *m)
 {
     if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
     FCB_CUDA(cudaSetDevice(m->device));
+    FCB_TRY(overlap_join(m)); // K3 of the last block may still be adding into `overlap` on its own stream
     const size_t ns = m->n_streams, B = m->B;
     if (m->tc) FCB_CUDA(cudaMemsetAsync(m->ring_t, 0, m->ring_t_elems() * sizeof(float2), m->stream));
     else FCB_CUDA(cudaMemsetAsync(m->ring, 0, ns * m->n_in * m->S * B * sizeof(float2), m->stream));
@@ -623,11 +657,12 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
         k_mimo_tc<16><<<(unsigned)(B * m->tc_groups * m->out_groups * m->stream_groups), TC_THREADS, TcCfg<16>::SMEM, m->stream>>>(t, m->tm_ring, m->tm_ir[0], m->tm_ir[1]);
         if (profiled) cudaEventRecord(prof_stop, m->stream);
         const long long nc = (long long)(ns * m->n_out * B);
+        FCB_TRY(overlap_before_reduce(m));
         if (m->peer_on) k_tc_reduce_peer<<<(unsigned)((nc + 255) / 256), 256, 0, m->stream>>>(m->part_tc, nc, m->tc_groups, m->pub());
         else k_tc_reduce<<<(unsigned)((nc + 255) / 256), 256, 0, m->stream>>>(m->part_tc, m->conv, nc, m->tc_groups);
         g_launches += 3;
         FCB_CUDA(cudaGetLastError());
-        return FCB_OK;
+        return overlap_after_reduce(m);
     }
     const long long ring_stride = (long long)(m->S * B);
     // K1 writes ring slot `current`; the MAC below reads only the older slots (segments >= 1) and the reduce kernel is
@@ -702,6 +737,7 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
         FCB_TRY(run_mac(m->logb, m->stream, a));
     }
     FCB_CUDA(cudaStreamWaitEvent(m->stream, m->ev_k1, 0));
+    FCB_TRY(overlap_before_reduce(m));
     const bool owns0 = m->seg_lo == 0 && m->seg_hi > 0;
     const long long n_so = (long long)(ns * m->n_out);
     k_mimo_reduce<<<(unsigned)(n_so * ((B + 31) / 32)), dim3(32, 8), 0, m->stream>>>(
@@ -709,7 +745,7 @@ extern "C" int fcb_mimo_partial_dev(fcb_mimo *m, const float *in_dev, size_t in_
         (int)m->n_in, (int)m->n_out, n_so, zchunks, part_in, m->pub());
     g_launches++;
     FCB_CUDA(cudaGetLastError());
-    return FCB_OK;
+    return overlap_after_reduce(m);
 }
 
 extern "C" float *fcb_mimo_conv_buffer(fcb_mimo *m, size_t *n_floats)
@@ -751,10 +787,41 @@ static int mimo_finish_rows(fcb_mimo *m, float *out_dev, size_t out_stride, size
             a.gather_n = (int)G;
             a.gather_err = m->peer_err_d;
         }
-        FCB_TRY(run_inverse(m->logb, m->tw, m->stream, a));
+        if (m->ovl_fin && m->peer_on) {
+            FCB_CUDA(cudaStreamWaitEvent(m->fin, m->ev_red, 0));
+            FCB_TRY(run_inverse(m->logb, m->tw, m->fin, a));
+            FCB_CUDA(cudaEventRecord(m->ev_fin, m->fin));
+            m->fin_pending = true;
+        } else {
+            FCB_TRY(run_inverse(m->logb, m->tw, m->stream, a));
+        }
     }
     m->current = m->current > 0 ? m->current - 1 : m->S - 1; // src/fft_convolver.rs:287-291
     return FCB_OK;
+}
+
+// Overlapped finish (see overlap_before_reduce): set on EVERY shard before the first block, peer exchange only.
+// While on, the output of a block is complete — in the order of the convolver's stream — after fcb_mimo_join, and for
+// the host after fcb_mimo_sync (inputs are taken in stream order as before: K1 and the MAC stay on that stream).
+extern "C" int fcb_mimo_set_overlap(fcb_mimo *m, int on)
+{
+    if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
+    if (m->peer_seq != 0) return fail(FCB_ERR_ARG, "fcb_mimo_set_overlap: set before the first block");
+    FCB_CUDA(cudaSetDevice(m->device));
+    if (on && !m->fin) {
+        FCB_CUDA(cudaStreamCreateWithFlags(&m->fin, cudaStreamNonBlocking));
+        FCB_CUDA(cudaEventCreateWithFlags(&m->ev_red, cudaEventDisableTiming));
+        FCB_CUDA(cudaEventCreateWithFlags(&m->ev_fin, cudaEventDisableTiming));
+    }
+    m->ovl_fin = on != 0;
+    return FCB_OK;
+}
+// the convolver's stream waits (on the device) for every K3 launched so far
+extern "C" int fcb_mimo_join(fcb_mimo *m)
+{
+    if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
+    FCB_CUDA(cudaSetDevice(m->device));
+    return overlap_join(m);
 }
 
 // every row — or, in the reduce-scatter form of the peer exchange, the rows this shard owns
@@ -811,6 +878,7 @@ extern "C" int fcb_mimo_sync(fcb_mimo *m)
     if (!m) return fail(FCB_ERR_ARG, "NULL mimo");
     FCB_CUDA(cudaSetDevice(m->device));
     FCB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->fin) FCB_CUDA(cudaStreamSynchronize(m->fin));
     return peer_check(m);
 }
 

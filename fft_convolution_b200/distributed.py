@@ -27,8 +27,11 @@ class ShardedMimoConvolver:
     """One IR-partition shard per rank of the default process group (NCCL on GPUs)."""
 
     def __init__(self, responses, block_size: int, max_response_length: int, *, n_streams: int = 1, device: int = 0,
-                 tensor_cores: bool | None = None, exchange: str = "peer", scatter: bool = False):
-        """scatter=True: reduce-scatter instead of all-gather / all-reduce — every rank FINISHES only its own output rows
+                 tensor_cores: bool | None = None, exchange: str = "peer", scatter: bool = False, overlap: bool = False):
+        """overlap=True (peer exchange): K3 of a block — the kernel that waits for the peers — runs beside K1 and the MAC
+        of the next block (throughput of back-to-back blocks); `out` is ordered on `self.stream` by join(), for the host by
+        sync().
+        scatter=True: reduce-scatter instead of all-gather / all-reduce — every rank FINISHES only its own output rows
         (`self.rows`), the result is sharded by row over the ranks (1/G of the exchange bytes, 1/G of the K3 work)"""
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = device
@@ -45,9 +48,12 @@ class ShardedMimoConvolver:
         self.rows = self.m.owned_rows if self.scatter else (0, n_streams * self.m.n_out)
         if self.scatter and self.exchange == "nccl" and (n_streams * self.m.n_out) % self.world:
             raise ValueError("reduce_scatter needs the output rows to divide evenly over the ranks")
+        self.overlap = bool(overlap) and self.exchange == "peer"
         if self.exchange == "peer":
             if self.scatter:
                 self.m.peer_set_scatter(True)
+            if self.overlap:
+                self.m.set_overlap(True)
             mine = torch.frombuffer(bytearray(self.m.peer_export()), dtype=torch.uint8).to(f"cuda:{device}")
             every = torch.empty((self.world, 64), dtype=torch.uint8, device=f"cuda:{device}")
             dist.all_gather_into_tensor(every, mine)
@@ -68,3 +74,11 @@ class ShardedMimoConvolver:
             if self.exchange == "nccl":
                 dist.all_reduce(self.conv, op=dist.ReduceOp.SUM)
             self.m.finish_dev(out.data_ptr(), out.stride(0))
+
+    def join(self) -> None:
+        """overlap=True: everything queued on self.stream after this call sees the outputs of every block so far"""
+        self.m.join()
+
+    def sync(self) -> None:
+        """host-side wait for every block so far; raises if the peer exchange timed out"""
+        self.m.sync()

@@ -398,6 +398,15 @@ void *fcb_mimo_peer_inbox(fcb_mimo *m);
  * NCCL callers get the same with a reduce_scatter of fcb_mimo_conv_buffer followed by fcb_mimo_finish_rows_dev. */
 int fcb_mimo_peer_set_scatter(fcb_mimo *m, int on);
 int fcb_mimo_owned_rows(const fcb_mimo *m, size_t *lo, size_t *hi);
+/* Overlapped finish (peer exchange, one shard per GPU; throughput of back-to-back blocks).  K3 is the kernel that waits
+ * for the peers' partial spectra; with this on it runs on a stream of its own beside K1 and the MAC of the NEXT block, and
+ * only that block's reduce waits for it (the order the exchange protocol needs: a shard's reduce comes after its own
+ * previous K3).  The output of a block is then complete, in the order of the convolver's stream, after fcb_mimo_join
+ * (a device-side wait) and for the host after fcb_mimo_sync; without a join, work queued on the convolver's stream is NOT
+ * ordered after the block's output.  Set on EVERY shard before the first block.  Shards sharing one GPU keep the rule above
+ * (every partial, synchronised, before any finish). */
+int fcb_mimo_set_overlap(fcb_mimo *m, int on);
+int fcb_mimo_join(fcb_mimo *m);
 int fcb_mimo_finish_rows_dev(fcb_mimo *m, float *out_dev, size_t out_stride, size_t row_lo, size_t row_hi);
 int fcb_mimo_peer_attach_ptrs(fcb_mimo *m, void *const *inboxes);
 /* test hook (host only): segment chunks (count, segments per chunk) the CUDA-core matrix kernel uses for a problem */

@@ -187,6 +187,60 @@ def test_peer_exchange_reduce_scatter_form(F, shards, tc, NS, n_out):
     run.check(TOL, "reduce-scatter peer exchange vs oracle")
 
 
+@pytest.mark.parametrize("shards,tc,scatter,NS,n_out", [(2, False, False, 2, 3), (3, False, True, 4, 6), (2, True, False, 3, 16)])
+def test_peer_exchange_overlapped_finish(F, shards, tc, scatter, NS, n_out):
+    """fcb_mimo_set_overlap: K3 on its own stream, ordered by events only (K3 after its block's reduce, the next block's
+    reduce after K3).  All shards in one process on one GPU — partials, a sync, finishes, a sync per block as that setting
+    demands — so this pins the event plumbing and the join / sync / reset semantics; blocks in flight across GPUs are
+    checked by bench.py's `mimo` block (every `_overlap` entry against the unsharded engine)."""
+    import torch
+    n_in, B = 2, 64
+    L = B * (19 if tc else 11) + 5
+    h = _irs(n_out, n_in, L)
+    nblocks = 24
+    x = np.stack([oracle.gen_noise(800 + i, 0, B * nblocks) for i in range(NS * n_in)])
+    parts = [F.MimoConvolver.init(h, B, L, n_streams=NS, shard_index=g, shard_count=shards, tensor_cores=tc) for g in range(shards)]
+    inboxes = [p.peer_inbox() for p in parts]
+    for p in parts:
+        p.peer_attach_ptrs(inboxes)
+        if scatter:
+            p.peer_set_scatter(True)
+        p.set_overlap(True)
+    refs = [MimoOracle(h, B, L) for _ in range(NS)]
+    R = NS * n_out
+    d_in = torch.empty((NS * n_in, B), dtype=torch.float32, device="cuda")
+    d_out = [torch.empty((R, B), dtype=torch.float32, device="cuda") for _ in parts]
+    if scatter:
+        d_out = [d_out[0]] * shards  # ONE buffer: every shard writes its own rows
+    run = WholeRun()
+    for b in range(nblocks):
+        if b == 15:  # reset in the middle: joins the finish stream before it clears the overlap
+            for p in parts:
+                p.reset()
+            refs = [MimoOracle(h, B, L) for _ in range(NS)]
+        blk = np.ascontiguousarray(x[:, b * B:(b + 1) * B])
+        d_in.copy_(torch.from_numpy(blk))
+        torch.cuda.synchronize()
+        for p in parts:
+            p.partial_dev(d_in.data_ptr(), B)
+        for p in parts:
+            p.sync()
+        for p, o in zip(parts, d_out):
+            p.finish_dev(o.data_ptr(), B)
+        for p in parts:
+            p.join()
+        for p in parts:
+            p.sync()
+        outs = [o.cpu().numpy() for o in d_out]
+        if not scatter:
+            for o in outs[1:]:
+                assert np.array_equal(o, outs[0])
+        for s_ in range(NS):
+            run.add(outs[0][s_ * n_out:(s_ + 1) * n_out], refs[s_].process(blk[s_ * n_in:(s_ + 1) * n_in]))
+    run.check(TOL, "peer exchange with overlapped finish vs oracle")
+
+
+
 def test_nccl_sharded_mimo_two_gpus():
     """IR-partition shards on 2 GPUs, exchanged by NCCL all-reduce and by the NVLink peer exchange (skipped on a 1-GPU box)"""
     import subprocess
