@@ -1,5 +1,5 @@
 #!/bin/bash
-# end-of-round capture, second half of round 2 (after k_mac_rt): suite, smoke, bench line, reference arm, launch list,
+# end-of-round capture, second half of round 2 (after k_mac_rt; the last capture of the round ran its first six steps): suite, smoke, bench line, reference arm, launch list,
 # hash-stamped DRAM traffic, ncu --set full of k_mac_rt at 16 and 32 streams, matrix sweep by stream count.
 # Every step under its own timeout; outputs under gpurun_out/ (copy what is judged into profiles/).
 set -x
