@@ -70,7 +70,10 @@ uint64_t fcb_debug_alloc_count(void);
  * batches cut each delay line of a whole-block launch over several CTAs, partial sums added in slice order by the last
  * CTA to arrive: deterministic, within tolerance, not bit-equal to the unsplit order; 0 = never; sweeps: "split_slots" = CTAs
  * the split aims at, "split_min_stages" = pipeline stages per CTA at least), "k1_late" (1 = the fused kernel transforms a block
- * that sits in host memory AFTER its MAC stream; measured without effect, default 0), "strict_todo"
+ * that sits in host memory AFTER its MAC stream; measured without effect, default 0), "tma_io" (1 = the whole-block
+ * kernels move their input / output blocks with bulk copies when the buffers allow it, 0 = through registers),
+ * "shared_reuse" (1 = engines with one IR for all channels stage each IR tile once per CTA and reuse it for the CTA's
+ * channels, 0 = the per-channel kernel with stride 0), "strict_todo"
  * (1 = fcb_twostage_update and fcb_crossfade_reset answer FCB_ERR_TODO like the reference's todo!(); default 0 = the
  * extensions documented at those entry points), "xf_speculate" (1 = the synchronous crossfade host call computes the
  * NEXT block's per-sample gains while the GPU works on the current one — same gains, same state, off the critical

@@ -59,3 +59,14 @@ def test_product_never_imports_oracle():
     for p in (ROOT / "fft_convolution_b200").rglob("*"):
         if p.suffix in {".py", ".cu", ".cuh", ".cpp", ".h"}:
             assert "oracle" not in p.read_text().lower(), p
+
+
+def test_every_tune_key_is_documented_in_the_header():
+    """fcb_tune's keys (csrc/engine.cu) are part of the ABI's surface: each one is described in include/fftconv_b200.h"""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    keys = set(re.findall(r'!strcmp\(key, "(\w+)"\)', (root / "fft_convolution_b200" / "csrc" / "engine.cu").read_text()))
+    header = (root / "include" / "fftconv_b200.h").read_text()
+    assert len(keys) >= 20
+    assert not [k for k in sorted(keys) if f'"{k}"' not in header]
